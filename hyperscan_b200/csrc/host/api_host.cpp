@@ -1,0 +1,787 @@
+/*
+ * api_host.cpp -- host-only half of the C ABI: compile entry points, the
+ * hs_database container (create / serialize / deserialize / info) and the
+ * allocator hooks.  Names, argument checks and error codes follow the
+ * reference so that its own API tests read the same here:
+ *   compile   src/hs.cpp:168-330 (arg checks), src/compiler/compiler.cpp:391-440
+ *   database  src/database.c:62-468, src/database.h:102-127
+ *   alloc     src/alloc.c:38-135
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../../include/hs_b200.h"
+#include "api_internal.h"
+#include "rose_build.h"
+
+using namespace hsb;
+
+/* ------------------------------------------------------------ allocators */
+
+namespace hsb {
+hs_alloc_t g_db_alloc = malloc, g_misc_alloc = malloc, g_scratch_alloc = malloc,
+           g_stream_alloc = malloc;
+hs_free_t g_db_free = free, g_misc_free = free, g_scratch_free = free,
+          g_stream_free = free;
+
+hs_error_t checkAlloc(const void *p) { /* src/alloc.c:111-119 */
+    if (!p) {
+        return HS_NOMEM;
+    }
+    if ((uintptr_t)p % alignof(unsigned long long)) {
+        return HS_BAD_ALLOC;
+    }
+    return HS_SUCCESS;
+}
+} // namespace hsb
+
+extern "C" {
+
+hs_error_t hs_set_database_allocator(hs_alloc_t a, hs_free_t f) {
+    g_db_alloc = a ? a : malloc;
+    g_db_free = f ? f : free;
+    return HS_SUCCESS;
+}
+hs_error_t hs_set_misc_allocator(hs_alloc_t a, hs_free_t f) {
+    g_misc_alloc = a ? a : malloc;
+    g_misc_free = f ? f : free;
+    return HS_SUCCESS;
+}
+hs_error_t hs_set_scratch_allocator(hs_alloc_t a, hs_free_t f) {
+    g_scratch_alloc = a ? a : malloc;
+    g_scratch_free = f ? f : free;
+    return HS_SUCCESS;
+}
+hs_error_t hs_set_stream_allocator(hs_alloc_t a, hs_free_t f) {
+    g_stream_alloc = a ? a : malloc;
+    g_stream_free = f ? f : free;
+    return HS_SUCCESS;
+}
+hs_error_t hs_set_allocator(hs_alloc_t a, hs_free_t f) {
+    hs_set_database_allocator(a, f);
+    hs_set_misc_allocator(a, f);
+    hs_set_stream_allocator(a, f);
+    hs_set_scratch_allocator(a, f);
+    return HS_SUCCESS;
+}
+
+const char *hs_version(void) { return "5.4.2 b200"; }
+
+/* ------------------------------------------------------ compile errors */
+
+static hs_compile_error_t g_enomem = {(char *)"Unable to allocate memory.", -1};
+
+static hs_compile_error_t *makeError(const std::string &msg, int idx) {
+    hs_compile_error_t *e = (hs_compile_error_t *)g_misc_alloc(sizeof(*e));
+    if (!e) {
+        return &g_enomem;
+    }
+    e->message = (char *)g_misc_alloc(msg.size() + 1);
+    if (!e->message) {
+        g_misc_free(e);
+        return &g_enomem;
+    }
+    memcpy(e->message, msg.c_str(), msg.size() + 1);
+    e->expression = idx;
+    return e;
+}
+
+hs_error_t hs_free_compile_error(hs_compile_error_t *error) {
+    if (!error || error == &g_enomem) {
+        return HS_SUCCESS;
+    }
+    g_misc_free(error->message);
+    g_misc_free(error);
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_populate_platform(hs_platform_info_t *platform) {
+    if (!platform) {
+        return HS_INVALID;
+    }
+    /* The scan engines run on the GPU; the database we emit uses only the
+     * baseline (non-AVX2) table variants, which every reference build also
+     * accepts (src/database.c:115-124). */
+    memset(platform, 0, sizeof(*platform));
+    return HS_SUCCESS;
+}
+
+/* --------------------------------------------------------- db container */
+
+static hs_database_t *dbCreate(const std::vector<u8> &bc, u64 platform,
+                               hs_error_t *err) {
+    const size_t len = sizeof(DbHeader) + bc.size();
+    DbHeader *db = (DbHeader *)g_db_alloc(len);
+    *err = checkAlloc(db);
+    if (*err != HS_SUCCESS) {
+        g_db_free(db);
+        return nullptr;
+    }
+    memset(db, 0, len);
+    const size_t shift = ((uintptr_t)db + sizeof(DbHeader)) & 0x3f;
+    db->bytecode = (u32)(sizeof(DbHeader) - shift);
+    db->magic = DB_MAGIC;
+    db->version = DB_VERSION;
+    db->length = (u32)bc.size();
+    db->platform = platform;
+    u8 *dst = (u8 *)db + db->bytecode;
+    memcpy(dst, bc.data(), bc.size());
+    db->crc32 = crc32c(0, dst, bc.size());
+    return (hs_database_t *)db;
+}
+
+hs_error_t hs_free_database(hs_database_t *db) {
+    if (db && ((DbHeader *)db)->magic != DB_MAGIC) {
+        return HS_INVALID;
+    }
+    g_db_free(db);
+    return HS_SUCCESS;
+}
+
+static bool dbAligned(const void *db) { return (uintptr_t)db % 8 == 0; }
+
+static hs_error_t validDb(const hs_database_t *db) {
+    const DbHeader *h = (const DbHeader *)db;
+    if (!h || h->magic != DB_MAGIC) {
+        return HS_INVALID;
+    }
+    if (h->version != DB_VERSION) {
+        return HS_DB_VERSION_ERROR;
+    }
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_serialize_database(const hs_database_t *db, char **bytes,
+                                 size_t *length) {
+    if (!db || !bytes || !length) {
+        return HS_INVALID;
+    }
+    if (!dbAligned(db)) {
+        return HS_BAD_ALIGN;
+    }
+    hs_error_t ret = validDb(db);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    const DbHeader *h = (const DbHeader *)db;
+    const size_t len = sizeof(DbHeader) + h->length;
+    char *out = (char *)g_misc_alloc(len);
+    ret = checkAlloc(out);
+    if (ret != HS_SUCCESS) {
+        g_misc_free(out);
+        return ret;
+    }
+    memset(out, 0, len);
+    u32 *w = (u32 *)out;
+    w[0] = h->magic;
+    w[1] = h->version;
+    w[2] = h->length;
+    memcpy(w + 3, &h->platform, 8);
+    w[5] = h->crc32;
+    w[6] = h->reserved0;
+    w[7] = h->reserved1;
+    memcpy(w + 8, (const char *)h + h->bytecode, h->length);
+    *bytes = out;
+    *length = len;
+    return HS_SUCCESS;
+}
+
+/* Any combination of the three NO* feature bits is a database some reference
+ * build could have produced; the B200 engines consume every table variant, so
+ * (unlike src/database.c:115-124) none of them is a platform mismatch. */
+static hs_error_t checkPlatform(u64 p) {
+    const u64 known = PLATFORM_NOAVX2 | PLATFORM_NOAVX512 | PLATFORM_NOAVX512VBMI;
+    return (p & ~known) ? HS_DB_PLATFORM_ERROR : HS_SUCCESS;
+}
+
+static hs_error_t decodeHeader(const char **bytes, size_t length, DbHeader *h) {
+    if (!*bytes) {
+        return HS_INVALID;
+    }
+    if (length < sizeof(DbHeader)) {
+        return HS_INVALID;
+    }
+    u32 w[8];
+    memcpy(w, *bytes, sizeof(w));
+    memset(h, 0, sizeof(*h));
+    h->magic = w[0];
+    if (h->magic != DB_MAGIC) {
+        return HS_INVALID;
+    }
+    h->version = w[1];
+    if (h->version != DB_VERSION) {
+        return HS_DB_VERSION_ERROR;
+    }
+    h->length = w[2];
+    if (length != sizeof(DbHeader) + h->length) {
+        return HS_INVALID;
+    }
+    memcpy(&h->platform, &w[3], 8);
+    h->crc32 = w[5];
+    h->reserved0 = w[6];
+    h->reserved1 = w[7];
+    *bytes += 32;
+    return HS_SUCCESS;
+}
+
+static void placeBytecode(const char *ser, DbHeader *db) {
+    const size_t shift = ((uintptr_t)db + sizeof(DbHeader)) & 0x3f;
+    db->bytecode = (u32)(sizeof(DbHeader) - shift);
+    memcpy((char *)db + db->bytecode, ser, db->length);
+}
+
+static hs_error_t checkCrc(const DbHeader *db) {
+    u32 c = crc32c(0, (const char *)db + db->bytecode, db->length);
+    return c == db->crc32 ? HS_SUCCESS : HS_INVALID;
+}
+
+hs_error_t hs_deserialize_database_at(const char *bytes, const size_t length,
+                                      hs_database_t *db) {
+    if (!bytes || !db) {
+        return HS_INVALID;
+    }
+    if (!dbAligned(db)) {
+        return HS_BAD_ALIGN;
+    }
+    DbHeader h;
+    hs_error_t ret = decodeHeader(&bytes, length, &h);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    ret = checkPlatform(h.platform);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    memset(db, 0, sizeof(DbHeader) + h.length);
+    memcpy(db, &h, sizeof(h));
+    placeBytecode(bytes, (DbHeader *)db);
+    return checkCrc((DbHeader *)db);
+}
+
+hs_error_t hs_deserialize_database(const char *bytes, const size_t length,
+                                   hs_database_t **db) {
+    if (!bytes || !db) {
+        return HS_INVALID;
+    }
+    *db = nullptr;
+    DbHeader h;
+    hs_error_t ret = decodeHeader(&bytes, length, &h);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    ret = checkPlatform(h.platform);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    const size_t len = sizeof(DbHeader) + h.length;
+    DbHeader *out = (DbHeader *)g_db_alloc(len);
+    ret = checkAlloc(out);
+    if (ret != HS_SUCCESS) {
+        g_db_free(out);
+        return ret;
+    }
+    memset(out, 0, len);
+    memcpy(out, &h, sizeof(h));
+    placeBytecode(bytes, out);
+    if (checkCrc(out) != HS_SUCCESS) {
+        g_db_free(out);
+        return HS_INVALID;
+    }
+    *db = (hs_database_t *)out;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_database_size(const hs_database_t *db, size_t *size) {
+    if (!size) {
+        return HS_INVALID;
+    }
+    hs_error_t ret = validDb(db);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    *size = sizeof(DbHeader) + ((const DbHeader *)db)->length;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_serialized_database_size(const char *bytes, const size_t length,
+                                       size_t *size) {
+    DbHeader h;
+    hs_error_t ret = decodeHeader(&bytes, length, &h);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    if (!size) {
+        return HS_INVALID;
+    }
+    *size = sizeof(DbHeader) + h.length;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_stream_size(const hs_database_t *db, size_t *stream_size) {
+    if (!stream_size) {
+        return HS_INVALID;
+    }
+    hs_error_t ret = validDb(db);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    const RoseEngine *r = dbRose(db);
+    if (r->mode != MODE_STREAM) { /* src/runtime.c:1058-1080 */
+        return HS_DB_MODE_ERROR;
+    }
+    *stream_size = 16 + r->stateOffsets.end;
+    return HS_SUCCESS;
+}
+
+static hs_error_t infoString(char **s, u32 version, u64 plat, u32 mode) {
+    const char *features =
+        (plat & PLATFORM_NOAVX512VBMI)
+            ? (plat & PLATFORM_NOAVX512) ? (plat & PLATFORM_NOAVX2) ? "" : "AVX2"
+                                         : "AVX512"
+            : "AVX512VBMI";
+    const char *m = mode == MODE_STREAM ? "STREAM"
+                    : mode == MODE_VECTORED ? "VECTORED" : "BLOCK";
+    char tmp[256];
+    int n = snprintf(tmp, sizeof(tmp), "Version: %u.%u.%u Features: %s Mode: %s",
+                     (version >> 24) & 0xff, (version >> 16) & 0xff,
+                     (version >> 8) & 0xff, features, m);
+    char *buf = (char *)g_misc_alloc((size_t)n + 1);
+    hs_error_t ret = checkAlloc(buf);
+    if (ret != HS_SUCCESS) {
+        g_misc_free(buf);
+        return ret;
+    }
+    memcpy(buf, tmp, (size_t)n + 1);
+    *s = buf;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_database_info(const hs_database_t *db, char **info) {
+    if (!info) {
+        return HS_INVALID;
+    }
+    *info = nullptr;
+    const DbHeader *h = (const DbHeader *)db;
+    if (!h || !dbAligned(h) || h->magic != DB_MAGIC) {
+        return HS_INVALID;
+    }
+    return infoString(info, h->version, h->platform, dbRose(db)->mode);
+}
+
+hs_error_t hs_serialized_database_info(const char *bytes, size_t length,
+                                       char **info) {
+    if (!info) {
+        return HS_INVALID;
+    }
+    *info = nullptr;
+    DbHeader h;
+    hs_error_t ret = decodeHeader(&bytes, length, &h);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    u32 mode;
+    memcpy(&mode, bytes + offsetof(RoseEngine, mode), 4);
+    return infoString(info, h.version, h.platform, mode);
+}
+
+hs_error_t hs_b200_db_info(const hs_database_t *db, hs_b200_db_info_t *out) {
+    if (!out) {
+        return HS_INVALID;
+    }
+    hs_error_t ret = validDb(db);
+    if (ret != HS_SUCCESS) {
+        return ret;
+    }
+    memset(out, 0, sizeof(*out));
+    const RoseEngine *r = dbRose(db);
+    out->runtime_impl = r->runtimeImpl;
+    out->bytecode_len = ((const DbHeader *)db)->length;
+    out->min_width = r->minWidth;
+    out->num_literals = r->totalNumLiterals;
+    if (r->fmatcherOffset) {
+        const HWLM *h = (const HWLM *)((const u8 *)r + r->fmatcherOffset);
+        out->hwlm_type = h->type;
+        if (h->type == HWLM_ENGINE_FDR) {
+            const FDR *f = (const FDR *)((const u8 *)h + HWLM_ENGINE_OFFSET);
+            out->engine_id = f->engineID;
+            out->num_literals = f->numStrings;
+            if (f->engineID == 0) {
+                out->fdr_domain = f->domain;
+                out->fdr_stride = f->stride;
+            }
+        }
+    }
+    return HS_SUCCESS;
+}
+
+/* -------------------------------------------------------------- compile */
+
+static bool checkMode(unsigned mode, std::string *why) {
+    const unsigned known = HS_MODE_BLOCK | HS_MODE_STREAM | HS_MODE_VECTORED |
+                           HS_MODE_SOM_HORIZON_LARGE | HS_MODE_SOM_HORIZON_MEDIUM |
+                           HS_MODE_SOM_HORIZON_SMALL;
+    if (mode & ~known) {
+        *why = "Invalid parameter: unrecognised mode flags.";
+        return false;
+    }
+    unsigned m = mode & (HS_MODE_STREAM | HS_MODE_BLOCK | HS_MODE_VECTORED);
+    if (__builtin_popcount(m) != 1) {
+        *why = "Invalid parameter: mode must have one (and only one) of "
+               "HS_MODE_BLOCK, HS_MODE_STREAM or HS_MODE_VECTORED set.";
+        return false;
+    }
+    unsigned som = mode & (HS_MODE_SOM_HORIZON_LARGE | HS_MODE_SOM_HORIZON_MEDIUM |
+                           HS_MODE_SOM_HORIZON_SMALL);
+    if (som) {
+        if (!(mode & HS_MODE_STREAM)) {
+            *why = "Invalid parameter: the HS_MODE_SOM_HORIZON_ mode flags may "
+                   "only be set in streaming mode.";
+            return false;
+        }
+        if (som & (som - 1)) {
+            *why = "Invalid parameter: only one HS_MODE_SOM_HORIZON_ mode flag "
+                   "can be set.";
+            return false;
+        }
+    }
+    if (!(mode & HS_MODE_BLOCK)) {
+        *why = "This build of the B200 runtime compiles block-mode databases only.";
+        return false;
+    }
+    return true;
+}
+
+static bool checkPlatformInfo(const hs_platform_info_t *p, std::string *why) {
+    if (!p) {
+        return true;
+    }
+    const unsigned long long all =
+        HS_CPU_FEATURES_AVX2 | HS_CPU_FEATURES_AVX512 | HS_CPU_FEATURES_AVX512VBMI;
+    if (p->cpu_features & ~all) {
+        *why = "Invalid cpu features specified in the platform information.";
+        return false;
+    }
+    if (p->tune > HS_TUNE_FAMILY_ICX) {
+        *why = "Invalid tuning value specified in the platform information.";
+        return false;
+    }
+    return true;
+}
+
+/* Turn a regex that denotes one literal string into its bytes (PCRE escapes
+ * as the reference parser accepts them, src/parser/Parser.rl).  Throws a
+ * CompileError for every construct that needs the regex back end. */
+static std::string regexToLiteral(const char *re, unsigned flags, int idx) {
+    std::string out;
+    const size_t n = strlen(re);
+    auto hex = [&](char c) -> int {
+        if (c >= '0' && c <= '9') return c - '0';
+        if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+        if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+        return -1;
+    };
+    for (size_t i = 0; i < n; i++) {
+        unsigned char c = (unsigned char)re[i];
+        if (c == '\\') {
+            if (++i >= n) {
+                throw CompileError{"Unterminated escape at end of pattern.", idx};
+            }
+            unsigned char e = (unsigned char)re[i];
+            switch (e) {
+            case 'n': out.push_back('\n'); break;
+            case 't': out.push_back('\t'); break;
+            case 'r': out.push_back('\r'); break;
+            case 'f': out.push_back('\f'); break;
+            case 'a': out.push_back('\a'); break;
+            case 'e': out.push_back('\x1b'); break;
+            case 'x': {
+                int h1 = i + 1 < n ? hex(re[i + 1]) : -1;
+                int h2 = i + 2 < n ? hex(re[i + 2]) : -1;
+                if (h1 < 0 || h2 < 0) {
+                    throw CompileError{"Invalid hex escape; only \\xHH is accepted.", idx};
+                }
+                out.push_back((char)(h1 * 16 + h2));
+                i += 2;
+                break;
+            }
+            default:
+                if ((e >= 'a' && e <= 'z') || (e >= 'A' && e <= 'Z') || (e >= '0' && e <= '9')) {
+                    throw CompileError{std::string("Escape sequence \\") + (char)e +
+                                           " needs the regex back end; this build "
+                                           "compiles literal patterns only.", idx};
+                }
+                out.push_back((char)e); /* escaped punctuation */
+            }
+            continue;
+        }
+        if (strchr(".^$*+?()[]{}|", c)) {
+            throw CompileError{std::string("Metacharacter '") + (char)c +
+                                   "' needs the regex back end; this build compiles "
+                                   "literal patterns only (escape it to match it "
+                                   "literally).", idx};
+        }
+        if (c >= 0x80 && (flags & (HS_FLAG_UTF8 | HS_FLAG_UCP))) {
+            throw CompileError{"Non-ASCII characters under HS_FLAG_UTF8/UCP are not "
+                               "supported by the literal compiler.", idx};
+        }
+        out.push_back((char)c);
+    }
+    return out;
+}
+
+static hs_error_t compileCommon(const char *const *expressions,
+                                const unsigned *flags, const unsigned *ids,
+                                const hs_expr_ext_t *const *ext,
+                                const size_t *lens, unsigned elements,
+                                unsigned mode, const hs_platform_info_t *platform,
+                                hs_database_t **db, hs_compile_error_t **error,
+                                bool litApi) {
+    if (!error) {
+        if (db) {
+            *db = nullptr;
+        }
+        return HS_COMPILER_ERROR;
+    }
+    if (!db) {
+        *error = makeError("Invalid parameter: db is NULL", -1);
+        return HS_COMPILER_ERROR;
+    }
+    *db = nullptr;
+    if (!expressions) {
+        *error = makeError("Invalid parameter: expressions is NULL", -1);
+        return HS_COMPILER_ERROR;
+    }
+    if (litApi && !lens) {
+        *error = makeError("Invalid parameter: len is NULL", -1);
+        return HS_COMPILER_ERROR;
+    }
+    if (elements == 0) {
+        *error = makeError("Invalid parameter: elements is zero", -1);
+        return HS_COMPILER_ERROR;
+    }
+    std::string why;
+    if (!checkMode(mode, &why) || !checkPlatformInfo(platform, &why)) {
+        *error = makeError(why, -1);
+        return HS_COMPILER_ERROR;
+    }
+    try {
+        std::vector<LitPattern> pats;
+        pats.reserve(elements);
+        for (unsigned i = 0; i < elements; i++) {
+            const unsigned f = flags ? flags[i] : 0;
+            if (!expressions[i]) {
+                throw CompileError{"Invalid parameter: expression is NULL", (int)i};
+            }
+            if (ext && ext[i] && ext[i]->flags != 0) {
+                throw CompileError{litApi ? "Extended parameters are not supported for "
+                                            "pure literal matching API."
+                                          : "Extended parameters need the regex back "
+                                            "end; this build compiles literal patterns "
+                                            "only.", (int)i};
+            }
+            if (f & ~0x7ffu) {
+                throw CompileError{"Unrecognised flag.", (int)i};
+            }
+            if ((f & HS_FLAG_SINGLEMATCH) && (f & HS_FLAG_SOM_LEFTMOST)) {
+                throw CompileError{"HS_FLAG_SINGLEMATCH is not supported in "
+                                   "combination with HS_FLAG_SOM_LEFTMOST.", (int)i};
+            }
+            LitPattern p;
+            p.index = i;
+            p.report = ids ? ids[i] : 0;
+            p.caseless = f & HS_FLAG_CASELESS;
+            p.singlematch = f & HS_FLAG_SINGLEMATCH;
+            if (litApi) {
+                const unsigned bad = HS_FLAG_DOTALL | HS_FLAG_ALLOWEMPTY | HS_FLAG_UTF8 |
+                                     HS_FLAG_UCP | HS_FLAG_PREFILTER | HS_FLAG_COMBINATION |
+                                     HS_FLAG_QUIET | HS_FLAG_MULTILINE;
+                if (f & bad) {
+                    throw CompileError{"Only HS_FLAG_CASELESS, HS_FLAG_SINGLEMATCH and "
+                                       "HS_FLAG_SOM_LEFTMOST are supported in literal API.",
+                                       (int)i};
+                }
+                if (lens[i] == 0 || expressions[i][0] == '\0') {
+                    throw CompileError{"Pure literal API doesn't support empty string.", (int)i};
+                }
+                p.s.assign(expressions[i], lens[i]);
+            } else {
+                if (f & (HS_FLAG_COMBINATION | HS_FLAG_QUIET)) {
+                    throw CompileError{"HS_FLAG_COMBINATION / HS_FLAG_QUIET need the regex "
+                                       "back end; this build compiles literal patterns only.",
+                                       (int)i};
+                }
+                p.s = regexToLiteral(expressions[i], f, (int)i);
+                if (p.s.empty()) {
+                    throw CompileError{(f & HS_FLAG_ALLOWEMPTY)
+                                           ? "Empty patterns need the regex back end "
+                                             "(boundary reports)."
+                                           : "Pattern matches empty buffer; use "
+                                             "HS_FLAG_ALLOWEMPTY to enable support.",
+                                       (int)i};
+                }
+            }
+            if (f & HS_FLAG_SOM_LEFTMOST) {
+                throw CompileError{"HS_FLAG_SOM_LEFTMOST is not supported by the B200 "
+                                   "literal compiler yet.", (int)i};
+            }
+            pats.push_back(p);
+        }
+        CompileOpts opts;
+        opts.pureLiteralApi = litApi;
+        if (platform && (platform->cpu_features & HS_CPU_FEATURES_AVX2)) {
+            /* the caller targets AVX2+ reference runtimes: 16-bucket Teddy is
+             * allowed and the database is stamped accordingly
+             * (src/compiler/compiler.cpp:455-470 target_to_platform) */
+            opts.hwlm.allowFatTeddy = true;
+            opts.platform &= ~PLATFORM_NOAVX2;
+            if (platform->cpu_features & HS_CPU_FEATURES_AVX512) {
+                opts.platform &= ~PLATFORM_NOAVX512;
+            }
+            if (platform->cpu_features & HS_CPU_FEATURES_AVX512VBMI) {
+                opts.platform &= ~PLATFORM_NOAVX512VBMI;
+            }
+        }
+        applyBuildOptions(&opts.hwlm);
+        if (opts.hwlm.allowFatTeddy) {
+            opts.platform &= ~PLATFORM_NOAVX2; /* 16-bucket Teddy needs AVX2 on CPUs */
+        }
+        std::vector<u8> bc = buildLiteralRose(pats, opts, nullptr);
+        hs_error_t aerr;
+        hs_database_t *out = dbCreate(bc, opts.platform, &aerr);
+        if (!out) {
+            *error = makeError("Could not allocate memory for bytecode.", -1);
+            return HS_COMPILER_ERROR;
+        }
+        *db = out;
+        *error = nullptr;
+        return HS_SUCCESS;
+    } catch (const CompileError &e) {
+        *error = makeError(e.msg, e.index);
+        return HS_COMPILER_ERROR;
+    } catch (const std::bad_alloc &) {
+        *error = &g_enomem;
+        return HS_COMPILER_ERROR;
+    } catch (const std::exception &e) {
+        *error = makeError(std::string("Internal error: ") + e.what(), -1);
+        return HS_COMPILER_ERROR;
+    }
+}
+
+hs_error_t hs_compile_multi(const char *const *expressions, const unsigned *flags,
+                            const unsigned *ids, unsigned elements, unsigned mode,
+                            const hs_platform_info_t *platform, hs_database_t **db,
+                            hs_compile_error_t **error) {
+    return compileCommon(expressions, flags, ids, nullptr, nullptr, elements, mode,
+                         platform, db, error, false);
+}
+
+hs_error_t hs_compile_ext_multi(const char *const *expressions,
+                                const unsigned *flags, const unsigned *ids,
+                                const hs_expr_ext_t *const *ext, unsigned elements,
+                                unsigned mode, const hs_platform_info_t *platform,
+                                hs_database_t **db, hs_compile_error_t **error) {
+    return compileCommon(expressions, flags, ids, ext, nullptr, elements, mode,
+                         platform, db, error, false);
+}
+
+hs_error_t hs_compile(const char *expression, unsigned flags, unsigned mode,
+                      const hs_platform_info_t *platform, hs_database_t **db,
+                      hs_compile_error_t **error) {
+    if (expression == nullptr) {
+        if (db) {
+            *db = nullptr;
+        }
+        if (error) {
+            *error = makeError("Invalid parameter: expression is NULL", -1);
+        }
+        return HS_COMPILER_ERROR;
+    }
+    unsigned id = 0;
+    return compileCommon(&expression, &flags, &id, nullptr, nullptr, 1, mode,
+                         platform, db, error, false);
+}
+
+hs_error_t hs_compile_lit_multi(const char *const *expressions,
+                                const unsigned *flags, const unsigned *ids,
+                                const size_t *lens, unsigned elements,
+                                unsigned mode, const hs_platform_info_t *platform,
+                                hs_database_t **db, hs_compile_error_t **error) {
+    return compileCommon(expressions, flags, ids, nullptr, lens, elements, mode,
+                         platform, db, error, true);
+}
+
+hs_error_t hs_compile_lit(const char *expression, unsigned flags, const size_t len,
+                          unsigned mode, const hs_platform_info_t *platform,
+                          hs_database_t **db, hs_compile_error_t **error) {
+    if (expression == nullptr) {
+        if (db) {
+            *db = nullptr;
+        }
+        if (error) {
+            *error = makeError("Invalid parameter: expression is NULL", -1);
+        }
+        return HS_COMPILER_ERROR;
+    }
+    unsigned id = 0;
+    return compileCommon(&expression, &flags, &id, nullptr, &len, 1, mode, platform,
+                         db, error, true);
+}
+
+} /* extern "C" */
+
+/* Build tunables (test / tuning hooks): select table variants the way the
+ * reference's unit tests force engines through hints
+ * (unit/internal/fdr.cpp:114-137, src/fdr/fdr_compile.cpp:862-866) and its
+ * tools override Grey values with -G.  Keys: "force_engine" (-1 auto, 0 FDR,
+ * 3..18 Teddy id), "fdr_domain", "fdr_stride", "max_domain", "allow_teddy",
+ * "allow_fat_teddy", "allow_flood", "allow_noodle". */
+namespace hsb {
+static HwlmBuildOpts g_tunables;
+static bool g_tun_set[8];
+void applyBuildOptions(HwlmBuildOpts *o) {
+    if (g_tun_set[0]) o->forceEngine = g_tunables.forceEngine;
+    if (g_tun_set[1]) o->forceDomain = g_tunables.forceDomain;
+    if (g_tun_set[2]) o->forceStride = g_tunables.forceStride;
+    if (g_tun_set[3]) o->maxDomain = g_tunables.maxDomain;
+    if (g_tun_set[4]) o->allowTeddy = g_tunables.allowTeddy;
+    if (g_tun_set[5]) o->allowFatTeddy = g_tunables.allowFatTeddy;
+    if (g_tun_set[6]) o->allowFlood = g_tunables.allowFlood;
+    if (g_tun_set[7]) o->allowNoodle = g_tunables.allowNoodle;
+}
+} // namespace hsb
+
+extern "C" hs_error_t hs_b200_set_build_option(const char *key, int value) {
+    if (!key) {
+        return HS_INVALID;
+    }
+    std::string k(key);
+    if (k == "reset") {
+        memset(g_tun_set, 0, sizeof(g_tun_set));
+        g_tunables = HwlmBuildOpts();
+        return HS_SUCCESS;
+    }
+    struct { const char *n; int i; } keys[] = {
+        {"force_engine", 0}, {"fdr_domain", 1}, {"fdr_stride", 2}, {"max_domain", 3},
+        {"allow_teddy", 4}, {"allow_fat_teddy", 5}, {"allow_flood", 6}, {"allow_noodle", 7}};
+    for (auto &e : keys) {
+        if (k == e.n) {
+            switch (e.i) {
+            case 0: g_tunables.forceEngine = value; break;
+            case 1: g_tunables.forceDomain = value; break;
+            case 2: g_tunables.forceStride = value; break;
+            case 3: g_tunables.maxDomain = value; break;
+            case 4: g_tunables.allowTeddy = value != 0; break;
+            case 5: g_tunables.allowFatTeddy = value != 0; break;
+            case 6: g_tunables.allowFlood = value != 0; break;
+            case 7: g_tunables.allowNoodle = value != 0; break;
+            }
+            g_tun_set[e.i] = true;
+            return HS_SUCCESS;
+        }
+    }
+    return HS_INVALID;
+}

@@ -1,0 +1,355 @@
+/*
+ * rose_build.cpp -- assembles the RoseEngine bytecode of a pure-literal
+ * database: one role program per literal fragment, the dedupe-key table and
+ * the floating HWLM table, behind a RoseEngine header whose fields are set the
+ * way the reference's back end sets them for ROSE_RUNTIME_PURE_LITERAL
+ * databases (src/rose/rose_build_bytecode.cpp:259-305 isPureFloating,
+ * :382-465 fillStateOffsets, :3609-3888 buildFinalEngine).
+ *
+ * Program shapes follow src/rose/rose_build_program.cpp:525-710 (makeReport)
+ * and :780-829 (makeCheckLiteralInstruction):
+ *
+ *   per pattern P of the fragment            (fail_jump -> next pattern / END)
+ *     |P| > 8            CHECK_MED_LIT[_NOCASE]  lit bytes live in the blob
+ *     SINGLEMATCH        CHECK_EXHAUSTED, [DEDUPE,] REPORT_EXHAUST
+ *     shared report id   DEDUPE_AND_REPORT
+ *     otherwise          REPORT
+ *   END
+ *
+ * Literals longer than 8 bytes reach the literal matcher as their 8-byte
+ * suffix (src/rose/rose_build_matchers.cpp:717-720); patterns with equal
+ * suffix/case share one HWLM literal ("fragment") whose id is the byte offset
+ * of its program in the bytecode (src/rose/match.c:238).
+ */
+#include "rose_build.h"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <set>
+#include <stdexcept>
+
+namespace hsb {
+
+namespace {
+
+struct Blob {
+    std::vector<u8> bytes; /* starts at RoseEngine offset `base` */
+    u32 base;
+    explicit Blob(u32 b) : base(b) {}
+    u32 reserve(size_t len, size_t align) {
+        size_t pos = HSB_ROUNDUP(base + bytes.size(), align);
+        bytes.resize(pos - base + len, 0);
+        return (u32)pos;
+    }
+    u32 add(const void *p, size_t len, size_t align) {
+        u32 off = reserve(len, align);
+        memcpy(bytes.data() + (off - base), p, len);
+        return off;
+    }
+    u8 *at(u32 off) { return bytes.data() + (off - base); }
+};
+
+template <class T> u32 instrSize() { return (u32)HSB_ROUNDUP(sizeof(T), INSTR_ALIGN); }
+
+struct PatInfo {
+    const LitPattern *p;
+    std::string folded; /* upper-cased if caseless */
+    bool anyAlpha;
+    u32 ekey, dkey;
+};
+
+u32 blockSize(const PatInfo &pi) {
+    u32 sz = 0;
+    if (pi.p->s.size() > 8) {
+        sz += instrSize<InstrCheckLit>();
+    }
+    if (pi.ekey != INVALID_EKEY) {
+        sz += instrSize<InstrCheckExhausted>();
+        if (pi.dkey != INVALID_DKEY) {
+            sz += instrSize<InstrDedupe>();
+        }
+        sz += instrSize<InstrReportExhaust>();
+    } else if (pi.dkey != INVALID_DKEY) {
+        sz += instrSize<InstrDedupeAndReport>();
+    } else {
+        sz += instrSize<InstrReport>();
+    }
+    return sz;
+}
+
+} // namespace
+
+std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
+                                 const CompileOpts &opts, HwlmBuildInfo *info) {
+    if (patsIn.empty()) {
+        throw CompileError{"Invalid parameter: elements is zero", -1};
+    }
+    if (patsIn.size() > LIMIT_LITERAL_COUNT) {
+        throw CompileError{"Number of patterns too large", -1};
+    }
+
+    /* --- validate, fold case, drop exact duplicates, assign ekeys/dkeys --- */
+    std::vector<PatInfo> pats;
+    std::map<u32, std::pair<bool, u32>> idHighlander; /* report -> (flag, first index) */
+    std::set<std::tuple<std::string, bool, u32>> seen;
+    for (const LitPattern &p : patsIn) {
+        if (p.s.empty()) {
+            throw CompileError{"Pure literal API doesn't support empty string.", (int)p.index};
+        }
+        if (p.s.size() > LIMIT_PATTERN_LENGTH) {
+            throw CompileError{"Pattern length exceeds limit.", (int)p.index};
+        }
+        if (p.s.size() > LIMIT_LITERAL_LENGTH) {
+            throw CompileError{"Resource limit exceeded.", (int)p.index};
+        }
+        auto it = idHighlander.find(p.report);
+        if (it == idHighlander.end()) {
+            idHighlander[p.report] = {p.singlematch, p.index};
+        } else if (it->second.first != p.singlematch) {
+            std::string m = "Expression (index " + std::to_string(p.index) +
+                            ") with match ID " + std::to_string(p.report) + " ";
+            m += p.singlematch ? "specified " : "did not specify ";
+            m += "HS_FLAG_SINGLEMATCH whereas previous expression (index " +
+                 std::to_string(it->second.second) + ") with the same match ID did";
+            m += p.singlematch ? " not." : ".";
+            throw CompileError{m, (int)p.index};
+        }
+        PatInfo pi;
+        pi.p = &p;
+        pi.folded = p.s;
+        pi.anyAlpha = false;
+        for (char &c : pi.folded) {
+            if (isAsciiAlpha((u8)c)) {
+                pi.anyAlpha = true;
+                if (p.caseless) {
+                    c = (char)asciiUpper((u8)c);
+                }
+            }
+        }
+        bool effNocase = p.caseless && pi.anyAlpha;
+        if (!seen.insert(std::make_tuple(pi.folded, effNocase, p.report)).second) {
+            continue; /* identical literal + report: one report source */
+        }
+        pi.ekey = pi.dkey = INVALID_EKEY;
+        pats.push_back(pi);
+    }
+    std::map<u32, u32> perReport;
+    for (const auto &pi : pats) {
+        perReport[pi.p->report]++;
+    }
+    std::map<u32, u32> ekeys, dkeys;
+    bool allHighlander = true;
+    for (auto &pi : pats) {
+        const u32 r = pi.p->report;
+        if (pi.p->singlematch) {
+            auto it = ekeys.find(r);
+            if (it == ekeys.end()) {
+                it = ekeys.emplace(r, (u32)ekeys.size()).first;
+            }
+            pi.ekey = it->second;
+        } else {
+            allHighlander = false;
+        }
+        if (perReport[r] > 1) {
+            auto it = dkeys.find(r);
+            if (it == dkeys.end()) {
+                it = dkeys.emplace(r, (u32)dkeys.size()).first;
+            }
+            pi.dkey = it->second;
+        }
+    }
+
+    /* --- group into fragments by (8-byte suffix, effective nocase) --- */
+    struct Fragment {
+        std::string suffix;
+        bool nocase;
+        std::vector<u32> pats;
+        u32 program = 0;
+    };
+    std::vector<Fragment> frags;
+    std::map<std::pair<std::string, bool>, u32> fragIndex;
+    u32 minLen = ~0u;
+    for (u32 i = 0; i < pats.size(); i++) {
+        const std::string &f = pats[i].folded;
+        minLen = std::min<u32>(minLen, (u32)f.size());
+        std::string suf = f.size() > 8 ? f.substr(f.size() - 8) : f;
+        bool nc = false;
+        if (pats[i].p->caseless) {
+            for (char c : suf) {
+                nc |= isAsciiAlpha((u8)c);
+            }
+        }
+        auto key = std::make_pair(suf, nc);
+        auto it = fragIndex.find(key);
+        if (it == fragIndex.end()) {
+            it = fragIndex.emplace(key, (u32)frags.size()).first;
+            frags.push_back({suf, nc, {}, 0});
+        }
+        frags[it->second].pats.push_back(i);
+    }
+
+    /* --- programs --- */
+    const u32 blobBase = (u32)HSB_ROUNDUP(sizeof(RoseEngine), 64);
+    Blob blob(blobBase);
+    struct PendingLit {
+        u32 instrOff;
+        std::string bytes;
+    };
+    std::vector<PendingLit> pendingLits;
+    for (Fragment &fr : frags) {
+        u32 total = instrSize<InstrEnd>();
+        for (u32 pi : fr.pats) {
+            total += blockSize(pats[pi]);
+        }
+        const u32 start = blob.reserve(total, INSTR_ALIGN);
+        fr.program = start;
+        u32 pc = start;
+        for (size_t k = 0; k < fr.pats.size(); k++) {
+            const PatInfo &pi = pats[fr.pats[k]];
+            const u32 next = pc + blockSize(pi); /* next pattern's block or END */
+            const u32 report = pi.p->report;
+            if (pi.p->s.size() > 8) {
+                InstrCheckLit in;
+                memset(&in, 0, sizeof(in));
+                bool nc = pi.p->caseless && pi.anyAlpha;
+                in.code = nc ? OP_CHECK_MED_LIT_NOCASE : OP_CHECK_MED_LIT;
+                in.lit_length = (u32)pi.folded.size();
+                in.fail_jump = next - pc;
+                memcpy(blob.at(pc), &in, sizeof(in));
+                pendingLits.push_back({pc, pi.folded});
+                pc += instrSize<InstrCheckLit>();
+            }
+            if (pi.ekey != INVALID_EKEY) {
+                InstrCheckExhausted ce;
+                memset(&ce, 0, sizeof(ce));
+                ce.code = OP_CHECK_EXHAUSTED;
+                ce.ekey = pi.ekey;
+                ce.fail_jump = next - pc;
+                memcpy(blob.at(pc), &ce, sizeof(ce));
+                pc += instrSize<InstrCheckExhausted>();
+                if (pi.dkey != INVALID_DKEY) {
+                    InstrDedupe d;
+                    memset(&d, 0, sizeof(d));
+                    d.code = OP_DEDUPE;
+                    d.dkey = pi.dkey;
+                    d.fail_jump = next - pc;
+                    memcpy(blob.at(pc), &d, sizeof(d));
+                    pc += instrSize<InstrDedupe>();
+                }
+                InstrReportExhaust re;
+                memset(&re, 0, sizeof(re));
+                re.code = OP_REPORT_EXHAUST;
+                re.onmatch = report;
+                re.ekey = pi.ekey;
+                memcpy(blob.at(pc), &re, sizeof(re));
+                pc += instrSize<InstrReportExhaust>();
+            } else if (pi.dkey != INVALID_DKEY) {
+                InstrDedupeAndReport dr;
+                memset(&dr, 0, sizeof(dr));
+                dr.code = OP_DEDUPE_AND_REPORT;
+                dr.dkey = pi.dkey;
+                dr.onmatch = report;
+                dr.fail_jump = next - pc;
+                memcpy(blob.at(pc), &dr, sizeof(dr));
+                pc += instrSize<InstrDedupeAndReport>();
+            } else {
+                InstrReport r;
+                memset(&r, 0, sizeof(r));
+                r.code = OP_REPORT;
+                r.onmatch = report;
+                memcpy(blob.at(pc), &r, sizeof(r));
+                pc += instrSize<InstrReport>();
+            }
+        }
+        InstrEnd e;
+        e.code = OP_END;
+        memcpy(blob.at(pc), &e, sizeof(e));
+    }
+    for (const PendingLit &pl : pendingLits) {
+        u32 off = blob.add(pl.bytes.data(), pl.bytes.size(), 1);
+        InstrCheckLit in;
+        memcpy(&in, blob.at(pl.instrOff), sizeof(in));
+        in.lit_offset = off;
+        memcpy(blob.at(pl.instrOff), &in, sizeof(in));
+    }
+
+    /* --- dkey -> external report id table (rose_internal.h:354) --- */
+    u32 invDkeyOffset = 0;
+    if (!dkeys.empty()) {
+        std::vector<u32> inv(dkeys.size());
+        for (const auto &d : dkeys) {
+            inv[d.second] = d.first;
+        }
+        invDkeyOffset = blob.add(inv.data(), inv.size() * sizeof(u32), 4);
+    }
+
+    /* --- floating literal matcher --- */
+    std::vector<HwlmLit> hl;
+    for (const Fragment &fr : frags) {
+        HwlmLit l;
+        l.s = fr.suffix;
+        l.nocase = fr.nocase;
+        l.noruns = false;
+        l.id = fr.program;
+        l.groups = 1;
+        hl.push_back(l);
+    }
+    std::vector<u8> hwlm;
+    try {
+        hwlm = buildHwlm(hl, opts.hwlm, info);
+    } catch (const std::runtime_error &e) {
+        throw CompileError{std::string("Unable to build literal matcher: ") + e.what(), -1};
+    }
+    const u32 fmatcherOffset = blob.add(hwlm.data(), hwlm.size(), 64);
+    const u32 total = (u32)HSB_ROUNDUP(blob.base + blob.bytes.size(), 64);
+
+    /* --- header --- */
+    RoseEngine r;
+    memset(&r, 0, sizeof(r));
+    r.pureLiteral = opts.pureLiteralApi ? 1 : 0;
+    r.runtimeImpl = RUNTIME_PURE_LITERAL;
+    r.canExhaust = allHighlander ? 1 : 0;
+    r.mode = MODE_BLOCK;
+    r.ekeyCount = (u32)ekeys.size();
+    r.dkeyCount = (u32)dkeys.size();
+    r.dkeyLogSize = fatbitSize(r.dkeyCount);
+    r.invDkeyOffset = invDkeyOffset;
+    r.somLocationFatbitSize = fatbitSize(0);
+    r.fmatcherOffset = fmatcherOffset;
+    r.fmatcherMinWidth = minLen;
+    r.activeQueueArraySize = fatbitSize(0);
+    r.handledKeyFatbitSize = fatbitSize(0);
+    r.minWidth = minLen;
+    r.minWidthExcludingBoundaries = minLen;
+    r.maxBiAnchoredWidth = ROSE_BOUND_INF;
+    r.floatingDistance = ROSE_BOUND_INF;
+    r.floatingMinLiteralMatchOffset = minLen;
+    r.initialGroups = 1;
+    r.floating_group_mask = 1;
+    r.size = total;
+    r.delay_fatbit_size = fatbitSize(0);
+    r.anchored_fatbit_size = fatbitSize(0);
+    r.totalNumLiterals = (u32)frags.size();
+    r.initMpvNfa = 0xffffffffu; /* MO_INVALID_IDX: no MPV outfix */
+    StateOffsets &so = r.stateOffsets;
+    u32 cur = 1;                 /* status byte; role multibit is empty */
+    so.activeLeafArray = so.activeLeftArray = so.longLitState = cur;
+    so.leftfixLagTable = so.anchorState = cur;
+    so.groups = cur;
+    so.groups_size = 1;
+    cur += so.groups_size;
+    so.history = cur;
+    so.exhausted = cur;
+    so.exhausted_size = mmbitSize(r.ekeyCount);
+    cur += so.exhausted_size;
+    so.logicalVec = so.combVec = cur;
+    so.nfaStateBegin = so.end = cur;
+
+    std::vector<u8> out(total, 0);
+    memcpy(out.data(), &r, sizeof(r));
+    memcpy(out.data() + blob.base, blob.bytes.data(), blob.bytes.size());
+    return out;
+}
+
+} // namespace hsb

@@ -1,0 +1,47 @@
+/*
+ * rose_build.h -- host-side assembly of a pure-literal RoseEngine bytecode
+ * (programs + floating literal matcher) and the hs_database container.
+ * Stands where the reference's RoseBuildImpl::buildFinalEngine + dbCreate stand
+ * (src/rose/rose_build_bytecode.cpp:3609-3888, src/compiler/compiler.cpp:476-
+ * 536), restricted to databases whose runtimeImpl is ROSE_RUNTIME_PURE_LITERAL.
+ */
+#ifndef HSB200_ROSE_BUILD_H
+#define HSB200_ROSE_BUILD_H
+
+#include <string>
+#include <vector>
+
+#include "hwlm_build.h"
+
+namespace hsb {
+
+struct CompileError {
+    std::string msg;
+    int index; /* expression index or -1 */
+};
+
+struct LitPattern {
+    std::string s;      /* raw bytes of the literal */
+    bool caseless = false;
+    bool singlematch = false;
+    u32 report = 0;     /* user-visible id */
+    u32 index = 0;      /* position in the caller's expression array */
+};
+
+struct CompileOpts {
+    bool pureLiteralApi = false; /* hs_compile_lit*: sets RoseEngine.pureLiteral */
+    u64 platform = PLATFORM_NOAVX2 | PLATFORM_NOAVX512 | PLATFORM_NOAVX512VBMI;
+    HwlmBuildOpts hwlm;
+};
+
+/* grey-box limits mirrored from src/grey.cpp:40-160 */
+static const size_t LIMIT_PATTERN_LENGTH = 16000;
+static const size_t LIMIT_LITERAL_LENGTH = 1600;
+static const size_t LIMIT_LITERAL_COUNT = 8000000;
+
+/** Build the RoseEngine bytecode for a set of literal patterns. */
+std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &pats,
+                                 const CompileOpts &opts, HwlmBuildInfo *info);
+
+} // namespace hsb
+#endif

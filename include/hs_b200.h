@@ -1,0 +1,286 @@
+/*
+ * hs_b200.h -- C ABI of libhs_b200.so, the B200-native block-mode scan runtime
+ * for Hyperscan databases.
+ *
+ * Part 1 re-declares, with identical names, argument meaning and error
+ * behaviour, the subset of the reference's public API (src/hs_common.h,
+ * src/hs_compile.h, src/hs_runtime.h of intel/hyperscan 5.4.2) that sits on the
+ * block-mode hot path, so that an application linked against libhs can be
+ * re-linked against libhs_b200 (`#include <hs.h>` keeps working through
+ * include/hs.h).  Each entry cites the reference declaration it replaces.
+ *
+ * Part 2 adds the batched / device-resident entry points a GPU needs to be fed
+ * efficiently (hsbench scans a corpus of many blocks: tools/hsbench/main.cpp:
+ * 503-527).  Plain pointers and sizes only; no torch / C++ types.
+ */
+#ifndef HS_B200_H
+#define HS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * Part 1: reference-compatible API
+ * ---------------------------------------------------------------------- */
+
+struct hs_database;
+typedef struct hs_database hs_database_t;   /* src/hs_common.h:47 */
+struct hs_scratch;
+typedef struct hs_scratch hs_scratch_t;     /* src/hs_runtime.h:60 */
+typedef int hs_error_t;                     /* src/hs_common.h:52 */
+
+/* error codes: src/hs_common.h:478-588 */
+#define HS_SUCCESS 0
+#define HS_INVALID (-1)
+#define HS_NOMEM (-2)
+#define HS_SCAN_TERMINATED (-3)
+#define HS_COMPILER_ERROR (-4)
+#define HS_DB_VERSION_ERROR (-5)
+#define HS_DB_PLATFORM_ERROR (-6)
+#define HS_DB_MODE_ERROR (-7)
+#define HS_BAD_ALIGN (-8)
+#define HS_BAD_ALLOC (-9)
+#define HS_SCRATCH_IN_USE (-10)
+#define HS_ARCH_ERROR (-11)
+#define HS_INSUFFICIENT_SPACE (-12)
+#define HS_UNKNOWN_ERROR (-13)
+
+/* pattern flags: src/hs_compile.h:869-1005 */
+#define HS_FLAG_CASELESS 1
+#define HS_FLAG_DOTALL 2
+#define HS_FLAG_MULTILINE 4
+#define HS_FLAG_SINGLEMATCH 8
+#define HS_FLAG_ALLOWEMPTY 16
+#define HS_FLAG_UTF8 32
+#define HS_FLAG_UCP 64
+#define HS_FLAG_PREFILTER 128
+#define HS_FLAG_SOM_LEFTMOST 256
+#define HS_FLAG_COMBINATION 512
+#define HS_FLAG_QUIET 1024
+
+/* cpu features / tune: src/hs_compile.h:1011-1110 */
+#define HS_CPU_FEATURES_AVX2 (1ULL << 2)
+#define HS_CPU_FEATURES_AVX512 (1ULL << 3)
+#define HS_CPU_FEATURES_AVX512VBMI (1ULL << 4)
+#define HS_TUNE_FAMILY_GENERIC 0
+#define HS_TUNE_FAMILY_ICX 10
+
+/* modes: src/hs_compile.h:1156-1210 */
+#define HS_MODE_BLOCK 1
+#define HS_MODE_NOSTREAM 1
+#define HS_MODE_STREAM 2
+#define HS_MODE_VECTORED 4
+#define HS_MODE_SOM_HORIZON_LARGE (1U << 24)
+#define HS_MODE_SOM_HORIZON_MEDIUM (1U << 25)
+#define HS_MODE_SOM_HORIZON_SMALL (1U << 26)
+
+typedef struct hs_compile_error {   /* src/hs_compile.h:70-97 */
+    char *message;
+    int expression;
+} hs_compile_error_t;
+
+typedef struct hs_platform_info {   /* src/hs_compile.h:134-165 */
+    unsigned int tune;
+    unsigned long long cpu_features;
+    unsigned long long reserved1;
+    unsigned long long reserved2;
+} hs_platform_info_t;
+
+typedef struct hs_expr_ext {        /* src/hs_compile.h:214-262 */
+    unsigned long long flags;
+    unsigned long long min_offset;
+    unsigned long long max_offset;
+    unsigned long long min_length;
+    unsigned edit_distance;
+    unsigned hamming_distance;
+} hs_expr_ext_t;
+
+typedef void *(*hs_alloc_t)(size_t size);   /* src/hs_common.h:271 */
+typedef void (*hs_free_t)(void *ptr);       /* src/hs_common.h:280 */
+
+/* src/hs_runtime.h:68-129 -- `to` is the offset after the last byte of the
+ * match; `from` is 0 (no SOM); non-zero return stops the scan. */
+typedef int (*match_event_handler)(unsigned int id, unsigned long long from,
+                                   unsigned long long to, unsigned int flags,
+                                   void *context);
+
+/* --- compile (host CPU; src/hs_compile.h:360-854).  This build carries a
+ * literal compiler: every expression must denote one literal string
+ * (hs_compile_lit*: any bytes; hs_compile*: a regex that is a plain literal
+ * after escape processing).  Anything else yields HS_COMPILER_ERROR with an
+ * explanatory hs_compile_error_t, exactly as the reference reports
+ * unsupported constructs. */
+hs_error_t hs_compile(const char *expression, unsigned int flags,
+                      unsigned int mode, const hs_platform_info_t *platform,
+                      hs_database_t **db, hs_compile_error_t **error);
+hs_error_t hs_compile_multi(const char *const *expressions,
+                            const unsigned int *flags, const unsigned int *ids,
+                            unsigned int elements, unsigned int mode,
+                            const hs_platform_info_t *platform,
+                            hs_database_t **db, hs_compile_error_t **error);
+hs_error_t hs_compile_ext_multi(const char *const *expressions,
+                                const unsigned int *flags,
+                                const unsigned int *ids,
+                                const hs_expr_ext_t *const *ext,
+                                unsigned int elements, unsigned int mode,
+                                const hs_platform_info_t *platform,
+                                hs_database_t **db, hs_compile_error_t **error);
+hs_error_t hs_compile_lit(const char *expression, unsigned flags,
+                          const size_t len, unsigned mode,
+                          const hs_platform_info_t *platform,
+                          hs_database_t **db, hs_compile_error_t **error);
+hs_error_t hs_compile_lit_multi(const char *const *expressions,
+                                const unsigned *flags, const unsigned *ids,
+                                const size_t *lens, unsigned elements,
+                                unsigned mode,
+                                const hs_platform_info_t *platform,
+                                hs_database_t **db, hs_compile_error_t **error);
+hs_error_t hs_free_compile_error(hs_compile_error_t *error);
+hs_error_t hs_populate_platform(hs_platform_info_t *platform);
+
+/* --- database container (src/hs_common.h:84-262; format src/database.h) */
+hs_error_t hs_free_database(hs_database_t *db);
+hs_error_t hs_serialize_database(const hs_database_t *db, char **bytes,
+                                 size_t *length);
+hs_error_t hs_deserialize_database(const char *bytes, const size_t length,
+                                   hs_database_t **db);
+hs_error_t hs_deserialize_database_at(const char *bytes, const size_t length,
+                                      hs_database_t *db);
+hs_error_t hs_stream_size(const hs_database_t *database, size_t *stream_size);
+hs_error_t hs_database_size(const hs_database_t *database, size_t *size);
+hs_error_t hs_serialized_database_size(const char *bytes, const size_t length,
+                                       size_t *deserialized_size);
+hs_error_t hs_database_info(const hs_database_t *database, char **info);
+hs_error_t hs_serialized_database_info(const char *bytes, size_t length,
+                                       char **info);
+
+/* --- allocators (src/hs_common.h:288-439; src/alloc.c:38-109) */
+hs_error_t hs_set_allocator(hs_alloc_t alloc_func, hs_free_t free_func);
+hs_error_t hs_set_database_allocator(hs_alloc_t alloc_func, hs_free_t free_func);
+hs_error_t hs_set_misc_allocator(hs_alloc_t alloc_func, hs_free_t free_func);
+hs_error_t hs_set_scratch_allocator(hs_alloc_t alloc_func, hs_free_t free_func);
+hs_error_t hs_set_stream_allocator(hs_alloc_t alloc_func, hs_free_t free_func);
+
+const char *hs_version(void);               /* src/hs_common.h:449 */
+hs_error_t hs_valid_platform(void);         /* src/hs_common.h:467: here it
+                                             * answers "is a CUDA device usable" */
+
+/* --- scratch + scan (src/hs_runtime.h:479-609; src/runtime.c:316,
+ * src/scratch.c:244) */
+hs_error_t hs_alloc_scratch(const hs_database_t *db, hs_scratch_t **scratch);
+hs_error_t hs_clone_scratch(const hs_scratch_t *src, hs_scratch_t **dest);
+hs_error_t hs_scratch_size(const hs_scratch_t *scratch, size_t *scratch_size);
+hs_error_t hs_free_scratch(hs_scratch_t *scratch);
+
+hs_error_t hs_scan(const hs_database_t *db, const char *data,
+                   unsigned int length, unsigned int flags,
+                   hs_scratch_t *scratch, match_event_handler onEvent,
+                   void *context);
+
+/* ------------------------------------------------------------------------
+ * Part 2: B200 batch / device-resident extension
+ * ---------------------------------------------------------------------- */
+
+/* One match record as the device writes it (16 bytes). */
+typedef struct hs_b200_match {
+    unsigned int id;             /* report id the user registered */
+    unsigned int block;          /* index of the block in the batch */
+    unsigned long long to;       /* end offset within the block */
+} hs_b200_match_t;
+
+/* Per-block callback for batched scans: like match_event_handler plus the
+ * block index.  Non-zero return stops delivery for THAT block (the block's
+ * scan is "terminated", like HS_SCAN_TERMINATED for one hs_scan call). */
+typedef int (*hs_b200_block_event_handler)(unsigned int block, unsigned int id,
+                                           unsigned long long from,
+                                           unsigned long long to,
+                                           unsigned int flags, void *context);
+
+/* Scan `nblocks` independent blocks held in HOST memory: block i is
+ * data[offsets[i] .. offsets[i]+lengths[i]).  Equivalent to nblocks hs_scan()
+ * calls (one per hsbench DataBlock), performed as one H2D copy, one kernel
+ * launch and one D2H of the match list; callbacks are replayed on the calling
+ * thread in (block, to) order.  onEvent may be NULL (matches are only
+ * counted).  *nmatches (optional) receives the number of matches delivered. */
+hs_error_t hs_b200_scan_blocks(const hs_database_t *db, const char *data,
+                               const unsigned long long *offsets,
+                               const unsigned int *lengths, size_t nblocks,
+                               hs_scratch_t *scratch,
+                               hs_b200_block_event_handler onEvent,
+                               void *context, unsigned long long *nmatches);
+
+/* Device-resident corpus handle: the packed, 16-byte-aligned copy of a set of
+ * blocks in HBM plus its block table. */
+struct hs_b200_corpus;
+typedef struct hs_b200_corpus hs_b200_corpus_t;
+
+/* Upload a corpus (host -> HBM).  `device` is the CUDA ordinal. */
+hs_error_t hs_b200_corpus_upload(const char *data,
+                                 const unsigned long long *offsets,
+                                 const unsigned int *lengths, size_t nblocks,
+                                 int device, hs_b200_corpus_t **corpus);
+/* Wrap a corpus that is ALREADY in HBM (e.g. a torch tensor): d_data is a
+ * device pointer, block starts must be 16-byte aligned within it; offsets and
+ * lengths are host arrays (copied). */
+hs_error_t hs_b200_corpus_wrap(const void *d_data, size_t data_bytes,
+                               const unsigned long long *offsets,
+                               const unsigned int *lengths, size_t nblocks,
+                               int device, hs_b200_corpus_t **corpus);
+hs_error_t hs_b200_corpus_free(hs_b200_corpus_t *corpus);
+size_t hs_b200_corpus_bytes(const hs_b200_corpus_t *corpus);
+
+/* Enqueue one scan of the whole corpus on `cuda_stream` (a cudaStream_t, or
+ * NULL for the scratch's own stream) and return without synchronising.
+ * Results stay in HBM inside the scratch. */
+hs_error_t hs_b200_scan_corpus_async(const hs_database_t *db,
+                                     const hs_b200_corpus_t *corpus,
+                                     hs_scratch_t *scratch, void *cuda_stream);
+/* Wait for the last enqueued scan; report how many raw match records it
+ * produced and the device pointer of the record array (hs_b200_match_t[]).
+ * Returns HS_INSUFFICIENT_SPACE if the record ring overflowed (after growing
+ * the ring so that a re-run succeeds). */
+hs_error_t hs_b200_scan_corpus_finish(hs_scratch_t *scratch,
+                                      unsigned long long *nrecords,
+                                      const void **d_records);
+/* Copy the records of the last finished scan to the host, apply the
+ * host-side report rules (dedupe per (id,to); HS_FLAG_SINGLEMATCH keeps the
+ * first match per id and block), sort by (block, to, id).  `out` may be NULL
+ * to query the count. */
+hs_error_t hs_b200_fetch_matches(const hs_database_t *db, hs_scratch_t *scratch,
+                                 hs_b200_match_t *out, size_t cap,
+                                 unsigned long long *nmatches);
+
+/* Introspection used by tests and bench.py. */
+typedef struct hs_b200_db_info {
+    unsigned int runtime_impl;   /* RoseEngine.runtimeImpl */
+    unsigned int hwlm_type;      /* 16 noodle, 12 FDR/Teddy, 0 none */
+    unsigned int engine_id;      /* FDR: 0; Teddy: 3..18 */
+    unsigned int fdr_domain;
+    unsigned int fdr_stride;
+    unsigned int num_literals;   /* HWLM literal fragments */
+    unsigned int bytecode_len;
+    unsigned int min_width;
+} hs_b200_db_info_t;
+hs_error_t hs_b200_db_info(const hs_database_t *db, hs_b200_db_info_t *info);
+
+/* Process-wide build tunable (the analogue of the reference tools' -G Grey
+ * overrides and of the engine "hints" its unit tests use,
+ * unit/internal/fdr.cpp:114-137).  Keys: "force_engine" (-1 auto, 0 FDR, 3..18
+ * Teddy engine id), "fdr_domain" (9..15), "fdr_stride" (1,2,4), "max_domain",
+ * "allow_teddy", "allow_fat_teddy", "allow_flood", "allow_noodle"; key "reset"
+ * restores the defaults. */
+hs_error_t hs_b200_set_build_option(const char *key, int value);
+
+/* Number of kernel launches issued by this library since load (bench.py's
+ * "gpu_launches"), and elapsed device time of the last scan kernel in ms
+ * (CUDA events on the launching stream). */
+unsigned long long hs_b200_launch_count(void);
+float hs_b200_last_kernel_ms(const hs_scratch_t *scratch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HS_B200_H */
