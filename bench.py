@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""hsbench-style block-mode throughput of the B200 scan runtime.
+
+  python bench.py --gpus N --steps K --warmup W            (ours)
+  python bench.py --impl reference --gpus N --steps K ...  (reference CPU arm)
+
+One "step" = one pass of the literal scan path over the whole corpus (hsbench's
+inner loop: every block through hs_scan once, tools/hsbench/main.cpp:503-527).
+Metric: Gbit/s = 8 * corpus bytes / seconds / 1e9 (main.cpp:721-725), whole
+job.  Default workload = BASELINE.json configs[1]: 1 000 short literals, 1 GiB
+synthetic corpus as 2^20 blocks x 1 KiB, block mode, one B200 (per rank).
+
+Prints ONE JSON line (rank 0).  `value` is measured with the corpus resident in
+HBM; `e2e` goes through hs_b200_scan_blocks() with HOST (pinned) buffers, H2D
+and D2H copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "hsbench block-mode scan throughput (Gbit/s scanned), match set bit-exact vs CPU ref"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lits", type=int, default=1000)
+    ap.add_argument("--blocks", type=int, default=1 << 20)
+    ap.add_argument("--block-len", type=int, default=1024)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample-mb", type=int, default=64)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--verify-blocks", type=int, default=4096)
+    return ap.parse_args()
+
+
+def workload(args, rank):
+    """Seeded literal set (same on every rank) and this rank's shard of blocks."""
+    from hyperscan_b200 import synth
+    lits, flags, ids = synth.literal_set(args.lits, min_len=4, max_len=8, caseless_frac=0.1, seed=2)
+    data, off, ln, planted = synth.block_corpus(args.blocks, args.block_len, lits, plant_per_kb=0.01,
+                                                seed=7 + 1000 * rank)
+    return lits, flags, ids, data, off, ln, planted
+
+
+def config_of(args, n, info=None):
+    c = {"workload": "hsbench configs[1]: %d short literals (len 4-8, [a-z], 10%% caseless), "
+                     "%d blocks x %d B per GPU, block mode" % (args.lits, args.blocks, args.block_len),
+         "corpus_bytes_per_gpu": args.blocks * args.block_len,
+         "l2": "inputs larger than L2 (corpus >> 126 MB), no flush needed",
+         "sharding": "blocks sharded by rank, database replicated" if n > 1 else "single GPU"}
+    if args.blocks * args.block_len <= 256 << 20:
+        c["l2"] = "WARNING: corpus not much larger than L2"
+    if info is not None:
+        c["engine"] = ("FDR domain %d stride %d" % (info.fdr_domain, info.fdr_stride)
+                       if info.hwlm_type == 12 and info.engine_id == 0 else
+                       "Teddy id %d" % info.engine_id if info.hwlm_type == 12 else "noodle")
+    return c
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"],
+                               f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx or None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(db, data, off, ln, sample_mb, seconds, threads=None):
+    """Time the reference's own CPU hs_scan (oracle/_ref, unmodified sources)
+    on a bounded sample of the workload, hsbench style."""
+    import oracle.ref as ref
+    threads = threads or (os.cpu_count() or 1)
+    nblk = max(1, min(len(off), (sample_mb << 20) // max(1, int(ln[0]))))
+    o, l = off[:nblk], ln[:nblk]
+    sample_bytes = int(l.sum())
+    t1, _, _ = ref.bench_blocks(db.ptr, data, o, l, threads, 1)
+    reps = max(1, int(seconds / max(t1, 1e-4)))
+    t, m, b = ref.bench_blocks(db.ptr, data, o, l, threads, reps)
+    # hsbench runs every thread over the whole corpus; ref_driver splits the
+    # blocks across threads, so `b` is the bytes all threads scanned
+    return {"value": b * 8 / t / 1e9, "unit": "Gbit/s", "cores": threads, "kind": "reference",
+            "isa": ref.best_isa(),
+            "sample": "first %d blocks (%.0f MiB) of the same corpus x %d repeats, %d threads, "
+                      "unmodified reference hs_scan (oracle/_ref, -O3 %s)" %
+                      (nblk, sample_bytes / 2**20, reps, threads, ref.best_isa()),
+            "seconds": t, "matches_per_pass": m // reps}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from hyperscan_b200 import capi
+    lits, flags, ids, data, off, ln, _ = workload(args, 0)
+    db = capi.compile_lit_multi(lits, flags, ids)
+    K, W = args.steps, args.warmup
+    import oracle.ref as ref
+    threads = os.cpu_count() or 1
+    nblk = max(1, min(len(off), (args.cpu_sample_mb << 20) // args.block_len))
+    o, l = off[:nblk], ln[:nblk]
+    for _ in range(W):
+        ref.bench_blocks(db.ptr, data, o, l, threads, 1)
+    t, m, b = ref.bench_blocks(db.ptr, data, o, l, threads, K)
+    val = b * 8 / t / 1e9
+    cb = {"value": val, "unit": "Gbit/s", "cores": threads, "kind": "reference",
+          "sample": "each step = first %d blocks (%.0f MiB) of the corpus, %d threads, unmodified "
+                    "reference hs_scan (oracle/_ref %s)" % (nblk, int(l.sum()) / 2**20, threads, ref.best_isa())}
+    print(json.dumps({"metric": METRIC, "value": val, "unit": "Gbit/s", "n_gpus": args.gpus, "steps": K,
+                      "warmup": W, "ms_per_step": t / K * 1e3, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                      "impl": "reference", "config": config_of(args, args.gpus, db.info()),
+                      "cpu_baseline": cb,
+                      "e2e": {"value": val, "unit": "Gbit/s", "h2d_bytes_per_step": 0,
+                              "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from hyperscan_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scan path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    lits, flags, ids, data, off, ln, planted = workload(args, rank)
+    db = capi.compile_lit_multi(lits, flags, ids)
+    info = db.info()
+    scratch = capi.Scratch(db)
+    corpus = capi.Corpus.upload(data, off, ln, device=local)
+    corpus_bytes = int(ln.sum())
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    gather_buf = {}
+
+    def step_resident():
+        """scan the HBM-resident shard; N>1: all-gather the raw match records"""
+        capi.scan_corpus_async(db, corpus, scratch)
+        rc, n, _ = capi.scan_corpus_finish(scratch)
+        if rc == capi.HS_INSUFFICIENT_SPACE:
+            capi.scan_corpus_async(db, corpus, scratch)
+            rc, n, _ = capi.scan_corpus_finish(scratch)
+        if rc != capi.HS_SUCCESS:
+            raise RuntimeError("scan failed %d" % rc)
+        if world == 1:
+            return n, None
+        cnt = torch.tensor([n], dtype=torch.int64, device=dev)
+        counts = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, cnt)
+        mx = int(counts.max().item())
+        key = (mx + 4095) // 4096 * 4096
+        if key not in gather_buf:
+            gather_buf.clear()
+            gather_buf[key] = (torch.zeros(key * 2, dtype=torch.int64, device=dev),
+                               torch.empty(world * key * 2, dtype=torch.int64, device=dev))
+        mine, allr = gather_buf[key]
+        capi._check(capi.lib().hs_b200_copy_records(scratch.ptr, mine.data_ptr(), key))
+        dist.all_gather_into_tensor(allr, mine)
+        return n, (counts, allr, key)
+
+    for _ in range(W):
+        step_resident()
+    barrier()
+    launches0 = capi.launch_count()
+    sampler = ClockSampler(local) if rank == 0 else None
+    kernel_ms = []
+    t0w = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(K):
+        n, last = step_resident()
+        kernel_ms.append(scratch.last_kernel_ms())
+    barrier()
+    dt = time.perf_counter() - t0
+    t1w = time.time()
+    launches = capi.launch_count() - launches0
+    clocks = sampler.stop(t0w, t1w) if sampler else None
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        tb = torch.tensor([corpus_bytes, launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        total_bytes, launches = int(tb[0].item()), int(tb[1].item())
+    else:
+        total_bytes = corpus_bytes
+    value = total_bytes * 8 * K / dt / 1e9
+
+    # ---- parity spot-check on this run's data (not timed) ----------------------
+    verify = {}
+    matches = capi.fetch_matches(db, scratch)
+    verify["matches_per_pass_rank0"] = int(matches.size)
+    if rank == 0 and args.verify_blocks and not args.no_cpu:
+        import oracle.ref as ref
+        vb = min(args.verify_blocks, len(off))
+        want = ref.scan_sorted(db.ptr, data, off[:vb], ln[:vb])
+        got = matches[matches["block"] < vb]
+        verify["verified_blocks"] = vb
+        verify["bit_exact_vs_reference"] = bool(np.array_equal(np.sort(got, order=["block", "to", "id"]), want))
+    if world > 1 and last is not None and rank == 0:
+        counts, allr, key = last
+        cs = counts.cpu().numpy()
+        verify["gathered_records"] = int(cs.sum())
+
+    # ---- e2e: host (pinned) buffers through the C ABI ----------------------------
+    e2e = None
+    if not args.no_e2e:
+        pinned = torch.empty(data.size, dtype=torch.uint8, pin_memory=True)
+        pinned.numpy()[:] = data
+        hview = pinned.numpy()
+        Ke = args.e2e_steps or min(K, 5)
+        for _ in range(min(W, 3)):
+            capi.scan_blocks(db, hview, off, ln, scratch, collect=False)
+        barrier()
+        t0 = time.perf_counter()
+        nm = 0
+        for _ in range(Ke):
+            nm = capi.scan_blocks(db, hview, off, ln, scratch, collect=False)
+        barrier()
+        de = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([de], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            de = float(tt.item())
+        e2e = {"value": total_bytes * 8 * Ke / de / 1e9, "unit": "Gbit/s",
+               "h2d_bytes_per_step": int(data.size + off.size * 12), "d2h_bytes_per_step": int(32 + nm * 16),
+               "steps": Ke, "ms_per_step": de / Ke * 1e3,
+               "api": "hs_b200_scan_blocks(host pinned buffer) -> sorted match list on host"}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        kms = float(np.mean(kernel_ms))
+        alg_bytes = corpus_bytes + 16 * int(n)
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "scanKernel (first-stage shift-OR + confirm)",
+                "kernel_ms": kms, "algorithmic_bytes_per_launch": alg_bytes}
+        cpu = None
+        if not args.no_cpu:
+            try:
+                cpu = cpu_reference_run(db, data, off, ln, args.cpu_sample_mb, args.cpu_seconds)
+            except Exception as e:  # oracle/_ref missing on this box
+                cpu = {"value": None, "unit": "Gbit/s", "cores": 0, "kind": "reference",
+                       "sample": "unavailable: %s" % e}
+        out = {"metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u8", "data": "synthetic", "config": config_of(args, world, info), "e2e": e2e,
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+               "verify": verify}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

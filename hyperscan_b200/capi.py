@@ -1,0 +1,391 @@
+"""ctypes binding of libhs_b200.so (include/hs_b200.h) for the Python harness
+(tests/, bench.py, __graft_entry__.py).
+
+The product is the C-ABI library; this module only marshals arguments.  It
+fails loudly when the library has not been built -- there is no Python or CPU
+fallback for the scan path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhs_b200.so")
+
+HS_SUCCESS = 0
+HS_INVALID = -1
+HS_NOMEM = -2
+HS_SCAN_TERMINATED = -3
+HS_COMPILER_ERROR = -4
+HS_DB_VERSION_ERROR = -5
+HS_DB_PLATFORM_ERROR = -6
+HS_DB_MODE_ERROR = -7
+HS_BAD_ALIGN = -8
+HS_BAD_ALLOC = -9
+HS_SCRATCH_IN_USE = -10
+HS_ARCH_ERROR = -11
+HS_INSUFFICIENT_SPACE = -12
+HS_UNKNOWN_ERROR = -13
+
+HS_FLAG_CASELESS = 1
+HS_FLAG_DOTALL = 2
+HS_FLAG_MULTILINE = 4
+HS_FLAG_SINGLEMATCH = 8
+HS_FLAG_ALLOWEMPTY = 16
+HS_FLAG_UTF8 = 32
+HS_FLAG_SOM_LEFTMOST = 256
+HS_MODE_BLOCK = 1
+HS_MODE_STREAM = 2
+HS_MODE_VECTORED = 4
+HS_CPU_FEATURES_AVX2 = 1 << 2
+
+MATCH_DTYPE = np.dtype([("id", "<u4"), ("block", "<u4"), ("to", "<u8")])
+
+
+class CompileError(C.Structure):
+    _fields_ = [("message", C.c_char_p), ("expression", C.c_int)]
+
+
+class PlatformInfo(C.Structure):
+    _fields_ = [("tune", C.c_uint), ("cpu_features", C.c_ulonglong),
+                ("reserved1", C.c_ulonglong), ("reserved2", C.c_ulonglong)]
+
+
+class DbInfo(C.Structure):
+    _fields_ = [("runtime_impl", C.c_uint), ("hwlm_type", C.c_uint), ("engine_id", C.c_uint),
+                ("fdr_domain", C.c_uint), ("fdr_stride", C.c_uint), ("num_literals", C.c_uint),
+                ("bytecode_len", C.c_uint), ("min_width", C.c_uint)]
+
+
+MATCH_CB = C.CFUNCTYPE(C.c_int, C.c_uint, C.c_ulonglong, C.c_ulonglong, C.c_uint, C.c_void_p)
+BLOCK_CB = C.CFUNCTYPE(C.c_int, C.c_uint, C.c_uint, C.c_ulonglong, C.c_ulonglong, C.c_uint, C.c_void_p)
+
+_lib = None
+
+
+class HsError(RuntimeError):
+    def __init__(self, code, what=""):
+        super().__init__("hs error %d %s" % (code, what))
+        self.code = code
+
+
+def lib():
+    """Load libhs_b200.so (built by hyperscan_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libhs_b200.so is not built (%s): run `python -m hyperscan_b200.build`; "
+                "there is no fallback scan path" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, cp, u32p, u64p = C.c_void_p, C.c_char_p, C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong)
+        L.hs_compile_lit_multi.argtypes = [C.POINTER(cp), u32p, u32p, C.POINTER(C.c_size_t), C.c_uint,
+                                           C.c_uint, C.POINTER(PlatformInfo), C.POINTER(vp),
+                                           C.POINTER(C.POINTER(CompileError))]
+        L.hs_compile_multi.argtypes = [C.POINTER(cp), u32p, u32p, C.c_uint, C.c_uint,
+                                       C.POINTER(PlatformInfo), C.POINTER(vp),
+                                       C.POINTER(C.POINTER(CompileError))]
+        L.hs_compile.argtypes = [cp, C.c_uint, C.c_uint, C.POINTER(PlatformInfo), C.POINTER(vp),
+                                 C.POINTER(C.POINTER(CompileError))]
+        L.hs_compile_lit.argtypes = [cp, C.c_uint, C.c_size_t, C.c_uint, C.POINTER(PlatformInfo),
+                                     C.POINTER(vp), C.POINTER(C.POINTER(CompileError))]
+        L.hs_free_compile_error.argtypes = [C.POINTER(CompileError)]
+        L.hs_free_database.argtypes = [vp]
+        L.hs_serialize_database.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+        L.hs_deserialize_database.argtypes = [cp, C.c_size_t, C.POINTER(vp)]
+        L.hs_deserialize_database_at.argtypes = [cp, C.c_size_t, vp]
+        L.hs_database_size.argtypes = [vp, C.POINTER(C.c_size_t)]
+        L.hs_serialized_database_size.argtypes = [cp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.hs_stream_size.argtypes = [vp, C.POINTER(C.c_size_t)]
+        L.hs_database_info.argtypes = [vp, C.POINTER(vp)]
+        L.hs_serialized_database_info.argtypes = [cp, C.c_size_t, C.POINTER(vp)]
+        L.hs_version.restype = cp
+        L.hs_alloc_scratch.argtypes = [vp, C.POINTER(vp)]
+        L.hs_clone_scratch.argtypes = [vp, C.POINTER(vp)]
+        L.hs_scratch_size.argtypes = [vp, C.POINTER(C.c_size_t)]
+        L.hs_free_scratch.argtypes = [vp]
+        L.hs_scan.argtypes = [vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
+        L.hs_b200_scan_blocks.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, BLOCK_CB, vp, u64p]
+        L.hs_b200_corpus_upload.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+        L.hs_b200_corpus_wrap.argtypes = [vp, C.c_size_t, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+        L.hs_b200_corpus_free.argtypes = [vp]
+        L.hs_b200_corpus_bytes.argtypes = [vp]
+        L.hs_b200_corpus_bytes.restype = C.c_size_t
+        L.hs_b200_scan_corpus_async.argtypes = [vp, vp, vp, vp]
+        L.hs_b200_scan_corpus_finish.argtypes = [vp, u64p, C.POINTER(vp)]
+        L.hs_b200_copy_records.argtypes = [vp, vp, C.c_size_t]
+        L.hs_b200_postprocess_matches.argtypes = [vp, vp, vp, C.c_size_t, u64p]
+        L.hs_b200_fetch_matches.argtypes = [vp, vp, vp, C.c_size_t, u64p]
+        L.hs_b200_db_info.argtypes = [vp, C.POINTER(DbInfo)]
+        L.hs_b200_set_build_option.argtypes = [cp, C.c_int]
+        L.hs_b200_set_runtime_option.argtypes = [cp, C.c_int]
+        L.hs_b200_launch_count.restype = C.c_ulonglong
+        L.hs_b200_last_kernel_ms.argtypes = [vp]
+        L.hs_b200_last_kernel_ms.restype = C.c_float
+        _lib = L
+    return _lib
+
+
+def _check(rc, what=""):
+    if rc != HS_SUCCESS:
+        raise HsError(rc, what)
+
+
+class Database:
+    """Owner of an hs_database_t* produced by this library's compiler."""
+
+    def __init__(self, ptr):
+        self.ptr = C.c_void_p(ptr) if not isinstance(ptr, C.c_void_p) else ptr
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().hs_free_database(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+    def info(self):
+        d = DbInfo()
+        _check(lib().hs_b200_db_info(self.ptr, C.byref(d)))
+        return d
+
+    def serialize(self):
+        out = C.c_void_p()
+        n = C.c_size_t()
+        _check(lib().hs_serialize_database(self.ptr, C.byref(out), C.byref(n)))
+        b = C.string_at(out, n.value)
+        C.CDLL(None).free(out)
+        return b
+
+    @staticmethod
+    def deserialize(b):
+        out = C.c_void_p()
+        _check(lib().hs_deserialize_database(b, len(b), C.byref(out)))
+        return Database(out)
+
+
+def _raise_compile(rc, err):
+    msg, idx = "?", -1
+    if err:
+        msg = (err.contents.message or b"").decode("latin1")
+        idx = err.contents.expression
+        lib().hs_free_compile_error(err)
+    e = HsError(rc, "compile: %s (expression %d)" % (msg, idx))
+    e.message = msg
+    e.expression = idx
+    raise e
+
+
+def compile_lit_multi(lits, flags=None, ids=None, mode=HS_MODE_BLOCK, platform=None):
+    """hs_compile_lit_multi (src/hs_compile.h:501-560): raw byte literals."""
+    n = len(lits)
+    lits = [bytes(x) for x in lits]
+    flags = list(flags) if flags is not None else [0] * n
+    ids = list(ids) if ids is not None else list(range(n))
+    bufs = [C.create_string_buffer(x, len(x) + 1) for x in lits]
+    arr = (C.c_char_p * n)(*[C.cast(b, C.c_char_p) for b in bufs])
+    fl = (C.c_uint * n)(*flags)
+    idv = (C.c_uint * n)(*ids)
+    lens = (C.c_size_t * n)(*[len(x) for x in lits])
+    db = C.c_void_p()
+    err = C.POINTER(CompileError)()
+    rc = lib().hs_compile_lit_multi(arr, fl, idv, lens, n, mode, platform, C.byref(db), C.byref(err))
+    if rc != HS_SUCCESS:
+        _raise_compile(rc, err)
+    return Database(db)
+
+
+def compile_multi(exprs, flags=None, ids=None, mode=HS_MODE_BLOCK, platform=None):
+    """hs_compile_multi (src/hs_compile.h:360-420): NUL-terminated regex strings."""
+    n = len(exprs)
+    exprs = [x if isinstance(x, bytes) else x.encode("latin1") for x in exprs]
+    flags = list(flags) if flags is not None else [0] * n
+    ids = list(ids) if ids is not None else list(range(n))
+    arr = (C.c_char_p * n)(*exprs)
+    fl = (C.c_uint * n)(*flags)
+    idv = (C.c_uint * n)(*ids)
+    db = C.c_void_p()
+    err = C.POINTER(CompileError)()
+    rc = lib().hs_compile_multi(arr, fl, idv, n, mode, platform, C.byref(db), C.byref(err))
+    if rc != HS_SUCCESS:
+        _raise_compile(rc, err)
+    return Database(db)
+
+
+def set_build_option(key, value):
+    _check(lib().hs_b200_set_build_option(key.encode(), int(value)), key)
+
+
+def set_runtime_option(key, value):
+    _check(lib().hs_b200_set_runtime_option(key.encode(), int(value)), key)
+
+
+def _as_u8(data):
+    if isinstance(data, np.ndarray):
+        a = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    else:
+        a = np.frombuffer(bytes(data), dtype=np.uint8)
+    return a
+
+
+def _blocks(offsets, lengths):
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+    assert off.shape == ln.shape
+    return off, ln
+
+
+class Scratch:
+    def __init__(self, db):
+        self.ptr = C.c_void_p()
+        _check(lib().hs_alloc_scratch(db.ptr, C.byref(self.ptr)), "hs_alloc_scratch")
+
+    def add(self, db):
+        _check(lib().hs_alloc_scratch(db.ptr, C.byref(self.ptr)), "hs_alloc_scratch")
+
+    def free(self):
+        if self.ptr:
+            lib().hs_free_scratch(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def size(self):
+        n = C.c_size_t()
+        _check(lib().hs_scratch_size(self.ptr, C.byref(n)))
+        return n.value
+
+    def last_kernel_ms(self):
+        return float(lib().hs_b200_last_kernel_ms(self.ptr))
+
+
+def scan(db, data, scratch, on_event=None, stop_after=0):
+    """hs_scan(): returns (rc, [(id, to), ...]) in delivery order."""
+    a = _as_u8(data)
+    out = []
+
+    def cb(i, frm, to, flags, ctx):
+        out.append((int(i), int(to)))
+        if on_event is not None:
+            return int(on_event(i, frm, to, flags))
+        if stop_after and len(out) >= stop_after:
+            return 1
+        return 0
+
+    keep = np.zeros(1, dtype=np.uint8) if a.size == 0 else a
+    rc = lib().hs_scan(db.ptr, keep.ctypes.data, a.size, 0, scratch.ptr, MATCH_CB(cb), None)
+    return rc, out
+
+
+def scan_blocks(db, data, offsets, lengths, scratch, collect=True):
+    """hs_b200_scan_blocks() on HOST buffers: returns a MATCH_DTYPE array in
+    (block, to, id) order (or just the count when collect=False)."""
+    a = _as_u8(data)
+    off, ln = _blocks(offsets, lengths)
+    n = C.c_ulonglong()
+    if not collect:
+        rc = lib().hs_b200_scan_blocks(db.ptr, a.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                       off.size, scratch.ptr, BLOCK_CB(), None, C.byref(n))
+        _check(rc, "hs_b200_scan_blocks")
+        return int(n.value)
+    recs = []
+
+    def cb(block, i, frm, to, flags, ctx):
+        recs.append((i, block, to))
+        return 0
+
+    rc = lib().hs_b200_scan_blocks(db.ptr, a.ctypes.data, off.ctypes.data, ln.ctypes.data, off.size,
+                                   scratch.ptr, BLOCK_CB(cb), None, C.byref(n))
+    _check(rc, "hs_b200_scan_blocks")
+    return np.array(recs, dtype=MATCH_DTYPE) if recs else np.zeros(0, dtype=MATCH_DTYPE)
+
+
+class Corpus:
+    """Device-resident corpus (hs_b200_corpus_upload / hs_b200_corpus_wrap)."""
+
+    def __init__(self, ptr, keep=None):
+        self.ptr = ptr
+        self._keep = keep
+
+    @staticmethod
+    def upload(data, offsets, lengths, device=0):
+        a = _as_u8(data)
+        off, ln = _blocks(offsets, lengths)
+        out = C.c_void_p()
+        _check(lib().hs_b200_corpus_upload(a.ctypes.data, off.ctypes.data, ln.ctypes.data, off.size,
+                                           device, C.byref(out)), "corpus_upload")
+        return Corpus(out)
+
+    @staticmethod
+    def wrap(dev_ptr, nbytes, offsets, lengths, device=0, keep=None):
+        off, ln = _blocks(offsets, lengths)
+        out = C.c_void_p()
+        _check(lib().hs_b200_corpus_wrap(C.c_void_p(dev_ptr), nbytes, off.ctypes.data, ln.ctypes.data,
+                                         off.size, device, C.byref(out)), "corpus_wrap")
+        return Corpus(out, keep)
+
+    def payload_bytes(self):
+        return int(lib().hs_b200_corpus_bytes(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            lib().hs_b200_corpus_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def scan_corpus_async(db, corpus, scratch, stream=None):
+    _check(lib().hs_b200_scan_corpus_async(db.ptr, corpus.ptr, scratch.ptr, C.c_void_p(stream or 0)),
+           "scan_corpus_async")
+
+
+def scan_corpus_finish(scratch):
+    """Returns (rc, nrecords, device pointer of the raw record array)."""
+    n = C.c_ulonglong()
+    p = C.c_void_p()
+    rc = lib().hs_b200_scan_corpus_finish(scratch.ptr, C.byref(n), C.byref(p))
+    return rc, int(n.value), p.value
+
+
+def fetch_matches(db, scratch):
+    n = C.c_ulonglong()
+    _check(lib().hs_b200_fetch_matches(db.ptr, scratch.ptr, None, 0, C.byref(n)), "fetch count")
+    out = np.zeros(int(n.value), dtype=MATCH_DTYPE)
+    if n.value:
+        _check(lib().hs_b200_fetch_matches(db.ptr, scratch.ptr, out.ctypes.data, out.size, C.byref(n)),
+               "fetch")
+    return out
+
+
+def scan_corpus(db, corpus, scratch, fetch=True):
+    """Scan a device-resident corpus; re-runs once if the record ring had to grow."""
+    for _ in range(3):
+        scan_corpus_async(db, corpus, scratch)
+        rc, n, _ = scan_corpus_finish(scratch)
+        if rc == HS_INSUFFICIENT_SPACE:
+            continue
+        _check(rc, "scan_corpus_finish")
+        return fetch_matches(db, scratch) if fetch else n
+    raise HsError(HS_INSUFFICIENT_SPACE, "record ring")
+
+
+def postprocess_matches(db, scratch, recs):
+    recs = np.ascontiguousarray(recs, dtype=MATCH_DTYPE)
+    n = C.c_ulonglong()
+    _check(lib().hs_b200_postprocess_matches(db.ptr, scratch.ptr, recs.ctypes.data, recs.size, C.byref(n)))
+    return recs[: int(n.value)]
+
+
+def launch_count():
+    return int(lib().hs_b200_launch_count())

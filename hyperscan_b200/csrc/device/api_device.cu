@@ -1,0 +1,1356 @@
+/*
+ * api_device.cu -- device half of the C ABI: scratch, corpus handles and the
+ * scan entry points (include/hs_b200.h).  The thin host shim around the
+ * sm_100a kernels in scan_kernels.cu:
+ *
+ *   hs_alloc_scratch / hs_clone_scratch / hs_scratch_size / hs_free_scratch
+ *        src/scratch.c:244-460 -- here a scratch owns a CUDA stream, the
+ *        match-record ring in HBM and the device images of the databases it
+ *        was allocated for.
+ *   hs_scan   src/runtime.c:316-475 -- argument checks and early-outs follow
+ *        the reference; the body is "copy block to HBM, launch, read records
+ *        back, replay callbacks in offset order".
+ *   hs_b200_* the batched / device-resident forms of the same (hsbench scans
+ *        a set of blocks: tools/hsbench/main.cpp:503-527).
+ *
+ * There is no CPU scan path in this library: without a usable CUDA device
+ * hs_alloc_scratch fails with HS_ARCH_ERROR.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <unordered_set>
+#include <vector>
+
+#include "../host/api_internal.h"
+#include "kernels.h"
+
+using namespace hsb;
+
+namespace {
+
+const u32 SCRATCH_MAGIC = 0x544F4259; /* src/scratch.h:48 */
+const size_t FRONT_PAD = 256;         /* readable bytes before corpus position 0 */
+
+std::atomic<unsigned long long> g_launches{0};
+
+/* runtime tunables (hs_b200_set_runtime_option / HSB200_* environment) */
+struct RuntimeOpts {
+    int warps = 16;
+    int tileBytes = 2048;
+    int stages = 3;
+    int wideFdr = 0;         /* 1: use all 8 FDR slots (u64 entries) when they fit */
+    int chunkMB = 32;        /* host->device pipeline granularity */
+    int initialRing = 1 << 20;
+};
+RuntimeOpts g_opts;
+bool g_optsInit = false;
+
+void initOpts() {
+    if (g_optsInit) {
+        return;
+    }
+    g_optsInit = true;
+    struct { const char *env; int *v; } e[] = {
+        {"HSB200_WARPS", &g_opts.warps},       {"HSB200_TILE", &g_opts.tileBytes},
+        {"HSB200_STAGES", &g_opts.stages},     {"HSB200_WIDE_FDR", &g_opts.wideFdr},
+        {"HSB200_CHUNK_MB", &g_opts.chunkMB},  {"HSB200_RING", &g_opts.initialRing}};
+    for (auto &x : e) {
+        const char *s = getenv(x.env);
+        if (s && *s) {
+            *x.v = atoi(s);
+        }
+    }
+}
+
+/* ---- device image of one database --------------------------------------- */
+
+struct DevImage {
+    const hs_database_t *db = nullptr;
+    u32 crc = 0, length = 0;
+    u8 *d_bc = nullptr;
+    u8 *d_table = nullptr;
+    u32 tableBytes = 0;
+    int kind = FK_BYTE32;
+    int stride = 1;
+    u32 indexMask = 0;
+    u32 confOff = 0, engineOff = 0;
+    u32 confirmKind = CK_FDR;
+    u64 groups = 0;
+    u32 minWidth = 0;
+    std::unordered_set<u32> exhaustible; /* report ids under HS_FLAG_SINGLEMATCH */
+    size_t deviceBytes = 0;
+};
+
+void collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex) {
+    u32 pc = prog;
+    for (int guard = 0; guard < 4096 && pc < bcLen; guard++) {
+        const u8 code = bc[pc];
+        switch (code) {
+        case OP_END:
+        case OP_FINAL_REPORT:
+            return;
+        case OP_CHECK_GROUPS: pc += HSB_ROUNDUP(sizeof(InstrCheckGroups), 8); break;
+        case OP_CHECK_MASK: pc += HSB_ROUNDUP(sizeof(InstrCheckMask), 8); break;
+        case OP_CHECK_BYTE: pc += HSB_ROUNDUP(sizeof(InstrCheckByte), 8); break;
+        case OP_CHECK_MED_LIT:
+        case OP_CHECK_MED_LIT_NOCASE:
+        case OP_CHECK_LONG_LIT:
+        case OP_CHECK_LONG_LIT_NOCASE: pc += HSB_ROUNDUP(sizeof(InstrCheckLit), 8); break;
+        case OP_CHECK_EXHAUSTED: pc += HSB_ROUNDUP(sizeof(InstrCheckExhausted), 8); break;
+        case OP_DEDUPE: pc += HSB_ROUNDUP(sizeof(InstrDedupe), 8); break;
+        case OP_REPORT: pc += HSB_ROUNDUP(sizeof(InstrReport), 8); break;
+        case OP_REPORT_EXHAUST: {
+            InstrReportExhaust in;
+            memcpy(&in, bc + pc, sizeof(in));
+            ex->insert(in.onmatch);
+            pc += HSB_ROUNDUP(sizeof(InstrReportExhaust), 8);
+            break;
+        }
+        case OP_DEDUPE_AND_REPORT: pc += HSB_ROUNDUP(sizeof(InstrDedupeAndReport), 8); break;
+        case OP_SQUASH_GROUPS: pc += HSB_ROUNDUP(sizeof(InstrSquashGroups), 8); break;
+        case OP_CLEAR_WORK_DONE: pc += 8; break;
+        case OP_INCLUDED_JUMP: pc += HSB_ROUNDUP(sizeof(InstrIncludedJump), 8); break;
+        case OP_SET_EXHAUST: pc += HSB_ROUNDUP(sizeof(InstrSetExhaust), 8); break;
+        default:
+            return;
+        }
+    }
+}
+
+/* Walk the hash-confirm structures to enumerate literal programs
+ * (src/fdr/fdr_confirm.h:36-94). */
+void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
+                 std::unordered_set<u32> *ex) {
+    const u8 *confBase = bc + confOff;
+    for (u32 b = 0; b < nBuckets; b++) {
+        u32 cf;
+        memcpy(&cf, confBase + 4 * b, 4);
+        if (!cf) {
+            continue;
+        }
+        const u8 *fc = confBase + cf;
+        FDRConfirm h;
+        memcpy(&h, fc, sizeof(h));
+        const u32 n = 1u << h.nBits;
+        for (u32 c = 0; c < n; c++) {
+            u32 start;
+            memcpy(&start, fc + sizeof(FDRConfirm) + 4 * c, 4);
+            if (!start) {
+                continue;
+            }
+            const u8 *li = fc + start;
+            for (;;) {
+                LitInfo x;
+                memcpy(&x, li, sizeof(x));
+                collectProgramReports(bc, bcLen, x.id, ex);
+                if (!x.next) {
+                    break;
+                }
+                li += sizeof(LitInfo);
+            }
+        }
+    }
+}
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            return e__ == cudaErrorMemoryAllocation ? HS_NOMEM : HS_UNKNOWN_ERROR;         \
+        }                                                                                  \
+    } while (0)
+
+void freeImage(DevImage *im) {
+    if (!im) {
+        return;
+    }
+    cudaFree(im->d_bc);
+    cudaFree(im->d_table);
+    delete im;
+}
+
+/* Derive the device image: a copy of the bytecode plus the first-stage table
+ * in the form the shift-OR kernel consumes. */
+hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
+    initOpts();
+    const DbHeader *h = (const DbHeader *)db;
+    const RoseEngine *r = dbRose(db);
+    const u8 *bc = (const u8 *)r;
+    if (r->runtimeImpl != RUNTIME_PURE_LITERAL || !r->fmatcherOffset) {
+        /* FULL_ROSE / SINGLE_OUTFIX databases need the regex engines
+         * (SURVEY.md section 8f rank 1): not in this build */
+        return HS_ARCH_ERROR;
+    }
+    DevImage *im = new (std::nothrow) DevImage();
+    if (!im) {
+        return HS_NOMEM;
+    }
+    im->db = db;
+    im->crc = h->crc32;
+    im->length = h->length;
+    im->groups = r->initialGroups & r->floating_group_mask;
+    im->minWidth = r->minWidth;
+    const HWLM *hw = (const HWLM *)(bc + r->fmatcherOffset);
+    const u32 engOff = r->fmatcherOffset + HWLM_ENGINE_OFFSET;
+    std::vector<u8> table;
+    if (hw->type == HWLM_ENGINE_NOOD) {
+        /* single literal: one bucket, slots = the last <= 4 bytes of msk/cmp
+         * (first char in the low byte: src/hwlm/noodle_build.cpp:100-118) */
+        NoodTable n;
+        memcpy(&n, bc + engOff, sizeof(n));
+        im->confirmKind = CK_NOODLE;
+        im->engineOff = engOff;
+        im->kind = FK_BYTE32;
+        im->stride = 1;
+        table.assign(256 * 4, 0);
+        for (u32 b = 0; b < 256; b++) {
+            u32 e = 0;
+            for (u32 p = 0; p < 4; p++) {
+                u8 v = 0xfe; /* buckets 1..7 never match */
+                if (p < n.msk_len) {
+                    const u32 i = n.msk_len - 1 - p;
+                    const u8 m = (u8)(n.msk >> (8 * i)), c = (u8)(n.cmp >> (8 * i));
+                    if ((b & m) != c) {
+                        v |= 1;
+                    }
+                }
+                e |= (u32)v << (8 * p);
+            }
+            memcpy(&table[b * 4], &e, 4);
+        }
+        collectProgramReports(bc, h->length, n.id, &im->exhaustible);
+    } else if (hw->type == HWLM_ENGINE_FDR) {
+        FDR f;
+        memcpy(&f, bc + engOff, sizeof(f));
+        im->confirmKind = CK_FDR;
+        im->confOff = engOff + f.confOffset;
+        if (f.engineID == 0) {
+            const u32 entries = 1u << f.domain;
+            const u8 *src = bc + engOff + FDR_TABLE_OFFSET;
+            im->stride = f.stride;
+            im->indexMask = f.domainMask;
+            int dev = 0, maxSmem = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            const size_t wideNeed = (size_t)entries * 8 + 48 * 1024;
+            if (g_opts.wideFdr && wideNeed <= (size_t)maxSmem) {
+                im->kind = FK_HASH64;
+                table.assign(src, src + (size_t)entries * 8);
+            } else {
+                im->kind = FK_HASH32; /* FDR suffix slots 0..3 */
+                table.resize((size_t)entries * 4);
+                for (u32 i = 0; i < entries; i++) {
+                    memcpy(&table[(size_t)i * 4], src + (size_t)i * 8, 4);
+                }
+            }
+            walkConfirm(bc, h->length, im->confOff, 8, &im->exhaustible);
+        } else if (teddyIdValid(f.engineID)) {
+            /* per-byte entry: slot m = lo_m[b & 15] | hi_m[b >> 4]
+             * (src/fdr/teddy.c:918-969, teddy_compile.cpp:440-509) */
+            const u32 nm = teddyNumMasks(f.engineID);
+            const u32 oct = teddyNumBuckets(f.engineID) / 8;
+            const u8 *mb = bc + engOff + TEDDY_MASK_OFFSET;
+            im->stride = 1;
+            im->kind = oct == 2 ? FK_BYTE64 : FK_BYTE32;
+            table.assign(256 * 4 * oct, 0);
+            for (u32 b = 0; b < 256; b++) {
+                for (u32 o = 0; o < oct; o++) {
+                    u32 e = 0;
+                    for (u32 m = 0; m < nm; m++) {
+                        const u8 *lo = mb + ((2 * m) * oct + o) * 16;
+                        const u8 *hi = mb + ((2 * m + 1) * oct + o) * 16;
+                        e |= (u32)(u8)(lo[b & 15] | hi[b >> 4]) << (8 * m);
+                    }
+                    memcpy(&table[(b * oct + o) * 4], &e, 4);
+                }
+            }
+            walkConfirm(bc, h->length, im->confOff, 8 * oct, &im->exhaustible);
+        } else {
+            delete im;
+            return HS_INVALID;
+        }
+    } else {
+        delete im;
+        return HS_INVALID;
+    }
+    im->tableBytes = (u32)table.size();
+    cudaError_t e = cudaMalloc(&im->d_bc, HSB_ROUNDUP(h->length, 16));
+    if (e == cudaSuccess) {
+        e = cudaMalloc(&im->d_table, HSB_ROUNDUP(table.size(), 16));
+    }
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(im->d_bc, bc, h->length, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(im->d_table, table.data(), table.size(), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        freeImage(im);
+        return e == cudaErrorMemoryAllocation ? HS_NOMEM : HS_UNKNOWN_ERROR;
+    }
+    im->deviceBytes = HSB_ROUNDUP(h->length, 16) + HSB_ROUNDUP(table.size(), 16);
+    *out = im;
+    return HS_SUCCESS;
+}
+
+} // namespace
+
+/* ---- corpus handle --------------------------------------------------------- */
+
+struct hs_b200_corpus {
+    int device = 0;
+    u8 *d_alloc = nullptr;   /* owned allocation (nullptr when wrapping) */
+    u8 *d_data = nullptr;    /* corpus position 0 */
+    u64 bytes = 0;           /* end of the last block */
+    u64 readableEnd = 0;
+    u64 *d_off = nullptr;
+    u32 *d_len = nullptr;
+    size_t nblocks = 0;
+    u32 uniformPitch = 0;
+    u64 payload = 0;         /* sum of block lengths */
+    size_t capData = 0, capBlocks = 0; /* allocation sizes when reused */
+};
+
+/* ---- scratch ------------------------------------------------------------------ */
+
+struct hs_scratch {
+    u32 magic;
+    u8 in_use;
+    int device;
+    void *alloc_base;        /* what g_scratch_alloc returned */
+    cudaStream_t stream, copyStream;
+    cudaStream_t activeStream; /* stream the pending scan was enqueued on */
+    cudaEvent_t evStart, evStop;
+    std::vector<cudaEvent_t> *chunkEvents;
+    std::vector<DevImage *> *images;
+    DevMatch *d_out;
+    u32 outCap;
+    u32 *d_counters;
+    u32 *h_counters;         /* pinned */
+    hs_b200_corpus *inlineCorpus; /* staging for hs_scan / hs_b200_scan_blocks */
+    u8 *h_stage;             /* pinned pack buffer (unaligned host blocks) */
+    size_t h_stageCap;
+    std::vector<u64> *tmpOff;
+    const DevImage *lastImage;
+    const hs_b200_corpus *lastCorpus;
+    bool pending;
+    u32 lastCount;
+    float lastMs;
+    int smCount, maxSmem;
+};
+
+namespace {
+
+hs_error_t validDb(const hs_database_t *db) { /* src/database.h:125-137 */
+    const DbHeader *h = (const DbHeader *)db;
+    if (!h || h->magic != DB_MAGIC) {
+        return HS_INVALID;
+    }
+    if (h->version != DB_VERSION) {
+        return HS_DB_VERSION_ERROR;
+    }
+    return HS_SUCCESS;
+}
+
+hs_error_t dbIsValid(const hs_database_t *db) { /* src/database.c:326-350 */
+    hs_error_t r = validDb(db);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    const DbHeader *h = (const DbHeader *)db;
+    const u64 known = PLATFORM_NOAVX2 | PLATFORM_NOAVX512 | PLATFORM_NOAVX512VBMI;
+    if (h->platform & ~known) {
+        return HS_DB_PLATFORM_ERROR;
+    }
+    if ((uintptr_t)dbRose(db) % 16) {
+        return HS_INVALID;
+    }
+    if (crc32c(0, (const u8 *)dbRose(db), h->length) != h->crc32) {
+        return HS_INVALID;
+    }
+    return HS_SUCCESS;
+}
+
+bool markInUse(hs_scratch *s) { /* src/scratch.h:249-271 */
+    if (s->in_use) {
+        return true;
+    }
+    s->in_use = 1;
+    return false;
+}
+void unmarkInUse(hs_scratch *s) { s->in_use = 0; }
+
+hs_error_t findImage(hs_scratch *s, const hs_database_t *db, const DevImage **out) {
+    const DbHeader *h = (const DbHeader *)db;
+    for (DevImage *im : *s->images) {
+        if (im->db == db && im->crc == h->crc32 && im->length == h->length) {
+            *out = im;
+            return HS_SUCCESS;
+        }
+    }
+    DevImage *im = nullptr;
+    hs_error_t r = buildImage(db, &im);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    s->images->push_back(im);
+    *out = im;
+    return HS_SUCCESS;
+}
+
+hs_error_t growRing(hs_scratch *s, u32 cap) {
+    if (cap <= s->outCap) {
+        return HS_SUCCESS;
+    }
+    DevMatch *n = nullptr;
+    CUDA_TRY(cudaMalloc(&n, (size_t)cap * sizeof(DevMatch)));
+    cudaFree(s->d_out);
+    s->d_out = n;
+    s->outCap = cap;
+    return HS_SUCCESS;
+}
+
+void freeCorpus(hs_b200_corpus *c) {
+    if (!c) {
+        return;
+    }
+    cudaFree(c->d_alloc);
+    cudaFree(c->d_off);
+    cudaFree(c->d_len);
+    delete c;
+}
+
+/* (Re)size a corpus handle's device buffers (grow-only). */
+hs_error_t reserveCorpus(hs_b200_corpus *c, u64 dataBytes, size_t nblocks) {
+    const size_t need = FRONT_PAD + HSB_ROUNDUP(dataBytes, 16) + 64;
+    if (need > c->capData) {
+        cudaFree(c->d_alloc);
+        c->d_alloc = nullptr;
+        c->capData = 0;
+        const size_t cap = need + need / 8;
+        CUDA_TRY(cudaMalloc(&c->d_alloc, cap));
+        CUDA_TRY(cudaMemset(c->d_alloc, 0, FRONT_PAD));
+        c->capData = cap;
+    }
+    c->d_data = c->d_alloc + FRONT_PAD;
+    if (nblocks > c->capBlocks) {
+        cudaFree(c->d_off);
+        cudaFree(c->d_len);
+        c->d_off = nullptr;
+        c->d_len = nullptr;
+        c->capBlocks = 0;
+        const size_t cap = nblocks + nblocks / 8 + 16;
+        CUDA_TRY(cudaMalloc(&c->d_off, cap * sizeof(u64)));
+        CUDA_TRY(cudaMalloc(&c->d_len, cap * sizeof(u32)));
+        c->capBlocks = cap;
+    }
+    return HS_SUCCESS;
+}
+
+u32 detectPitch(const u64 *off, const u32 *len, size_t n) {
+    if (n == 0) {
+        return 0;
+    }
+    if (n == 1) {
+        return off[0] == 0 ? (u32)std::max<u64>(16, HSB_ROUNDUP((u64)len[0], 16)) : 0;
+    }
+    const u64 pitch = off[1] - off[0];
+    if (off[0] != 0 || pitch == 0 || pitch > 0xffffffffu) {
+        return 0;
+    }
+    for (size_t i = 0; i < n; i++) {
+        if (off[i] != i * pitch || len[i] > pitch) {
+            return 0;
+        }
+    }
+    return (u32)pitch;
+}
+
+struct ScanPlan {
+    LaunchCfg cfg;
+    u32 tileBytes, nstages;
+};
+
+hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
+    initOpts();
+    int warps = std::max(1, std::min(32, g_opts.warps));
+    u32 tile = (u32)std::max(512, g_opts.tileBytes) & ~511u;
+    u32 stages = (u32)std::max(2, std::min(8, g_opts.stages));
+    /* shrink until the table + staging fit the opt-in shared memory */
+    for (;;) {
+        const size_t need = scanSmemBytes(im->kind, im->tableBytes, warps, stages, tile);
+        if (need <= (size_t)s->maxSmem) {
+            pl->cfg.smemBytes = need;
+            break;
+        }
+        if (stages > 2) {
+            stages--;
+        } else if (tile > 1024) {
+            tile >>= 1;
+        } else if (warps > 4) {
+            warps -= 4;
+        } else if (tile > 512) {
+            tile >>= 1;
+        } else if (warps > 1) {
+            warps--;
+        } else {
+            return HS_NOMEM;
+        }
+    }
+    pl->cfg.kind = im->kind;
+    pl->cfg.stride = im->stride;
+    pl->cfg.grid = s->smCount;
+    pl->cfg.warps = warps;
+    pl->tileBytes = tile;
+    pl->nstages = stages;
+    return HS_SUCCESS;
+}
+
+void fillParams(const hs_scratch *s, const DevImage *im, const hs_b200_corpus *c,
+                const ScanPlan &pl, ScanParams *p) {
+    memset(p, 0, sizeof(*p));
+    p->corpus = c->d_data;
+    p->corpusBytes = c->bytes;
+    p->readableEnd = c->readableEnd;
+    p->tileBytes = pl.tileBytes;
+    p->nstages = pl.nstages;
+    p->blockOff = c->d_off;
+    p->blockLen = c->d_len;
+    p->nblocks = (u32)c->nblocks;
+    p->uniformPitch = c->uniformPitch;
+    p->bc = im->d_bc;
+    p->table = im->d_table;
+    p->tableBytes = im->tableBytes;
+    p->indexMask = im->indexMask;
+    p->confOff = im->confOff;
+    p->engineOff = im->engineOff;
+    p->confirmKind = im->confirmKind;
+    p->groups = im->groups;
+    p->out = s->d_out;
+    p->outCap = s->outCap;
+    p->counters = s->d_counters;
+}
+
+/* Launch over tiles [t0, t1) of the corpus on `stream`. */
+hs_error_t launchRange(hs_scratch *s, const DevImage *im, const hs_b200_corpus *c,
+                       const ScanPlan &pl, u32 t0, u32 t1, cudaStream_t stream) {
+    if (t1 <= t0) {
+        return HS_SUCCESS;
+    }
+    ScanParams p;
+    fillParams(s, im, c, pl, &p);
+    p.tileFirst = t0;
+    p.ntiles = t1 - t0;
+    LaunchCfg cfg = pl.cfg;
+    const u32 perCta = (u32)cfg.warps;
+    cfg.grid = (int)std::min<u32>((u32)cfg.grid, (p.ntiles + perCta - 1) / perCta);
+    CUDA_TRY(launchScan(cfg, p, stream));
+    g_launches++;
+    return HS_SUCCESS;
+}
+
+/* Order records for delivery and apply the order-dependent report rules the
+ * device skipped: one report per (block, id, to) (dedupe, src/report.h:55-119)
+ * and, for HS_FLAG_SINGLEMATCH reports, only the first match per block
+ * (exhaustion keys, src/report.h:121-147, program_runtime.c:464-481). */
+size_t postprocess(const DevImage *im, DevMatch *m, size_t n) {
+    std::sort(m, m + n, [](const DevMatch &a, const DevMatch &b) {
+        if (a.block != b.block) return a.block < b.block;
+        if (a.to != b.to) return a.to < b.to;
+        return a.id < b.id;
+    });
+    size_t w = 0;
+    std::unordered_set<u32> seen;
+    u32 curBlock = 0xffffffffu;
+    const bool anyEx = !im->exhaustible.empty();
+    for (size_t i = 0; i < n; i++) {
+        if (w && m[w - 1].block == m[i].block && m[w - 1].to == m[i].to && m[w - 1].id == m[i].id) {
+            continue;
+        }
+        if (anyEx) {
+            if (m[i].block != curBlock) {
+                curBlock = m[i].block;
+                seen.clear();
+            }
+            if (im->exhaustible.count(m[i].id) && !seen.insert(m[i].id).second) {
+                continue;
+            }
+        }
+        m[w++] = m[i];
+    }
+    return w;
+}
+
+hs_error_t finishScan(hs_scratch *s, u32 *count) {
+    cudaError_t e = cudaStreamSynchronize(s->activeStream ? s->activeStream : s->stream);
+    s->pending = false;
+    if (e != cudaSuccess) {
+        return HS_UNKNOWN_ERROR;
+    }
+    cudaEventElapsedTime(&s->lastMs, s->evStart, s->evStop);
+    if (s->h_counters[CTR_ERROR]) {
+        return HS_UNKNOWN_ERROR;
+    }
+    *count = s->h_counters[CTR_MATCHES];
+    s->lastCount = *count;
+    return HS_SUCCESS;
+}
+
+/* Enqueue: reset counters, scan the whole corpus, read the counters back. */
+hs_error_t enqueueScan(hs_scratch *s, const DevImage *im, const hs_b200_corpus *c,
+                       cudaStream_t stream) {
+    ScanPlan pl;
+    hs_error_t r = planScan(s, im, &pl);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, CTR_COUNT * sizeof(u32), stream));
+    CUDA_TRY(cudaEventRecord(s->evStart, stream));
+    const u32 ntiles = (u32)((c->bytes + pl.tileBytes - 1) / pl.tileBytes);
+    r = launchRange(s, im, c, pl, 0, ntiles, stream);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    CUDA_TRY(cudaEventRecord(s->evStop, stream));
+    CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, CTR_COUNT * sizeof(u32),
+                             cudaMemcpyDeviceToHost, stream));
+    s->lastImage = im;
+    s->lastCorpus = c;
+    s->activeStream = stream;
+    s->pending = true;
+    return HS_SUCCESS;
+}
+
+/* Fill a corpus handle from host blocks.  Returns through *direct whether the
+ * caller's buffer could be copied as it lies (all starts 16-byte aligned
+ * relative to the first block, ascending, disjoint). */
+hs_error_t layoutBlocks(hs_scratch *s, const unsigned long long *offsets,
+                        const unsigned *lengths, size_t nblocks, std::vector<u64> *packed,
+                        u64 *total, u64 *payload, bool *direct) {
+    (void)s;
+    packed->resize(nblocks);
+    bool ok = nblocks > 0;
+    u64 pay = 0;
+    const u64 base = nblocks ? offsets[0] : 0;
+    u64 prevEnd = 0;
+    for (size_t i = 0; i < nblocks; i++) {
+        pay += lengths[i];
+        if (ok) {
+            if (offsets[i] < base || (offsets[i] - base) % 16 || offsets[i] - base < prevEnd) {
+                ok = false;
+            } else {
+                (*packed)[i] = offsets[i] - base;
+                prevEnd = offsets[i] - base + lengths[i];
+            }
+        }
+    }
+    if (!ok) {
+        u64 pos = 0;
+        for (size_t i = 0; i < nblocks; i++) {
+            (*packed)[i] = pos;
+            pos += HSB_ROUNDUP((u64)lengths[i], 16);
+            if (lengths[i] == 0) {
+                pos += 16; /* keep starts distinct */
+            }
+        }
+        prevEnd = nblocks ? (*packed)[nblocks - 1] + lengths[nblocks - 1] : 0;
+    }
+    *total = prevEnd;
+    *payload = pay;
+    *direct = ok;
+    return HS_SUCCESS;
+}
+
+} // namespace
+
+extern "C" {
+
+hs_error_t hs_valid_platform(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        return HS_ARCH_ERROR;
+    }
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, 0);
+    return major >= 10 ? HS_SUCCESS : HS_ARCH_ERROR;
+}
+
+unsigned long long hs_b200_launch_count(void) { return g_launches.load(); }
+
+float hs_b200_last_kernel_ms(const hs_scratch_t *scratch) {
+    return scratch ? scratch->lastMs : 0.0f;
+}
+
+hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
+    initOpts();
+    if (!key) {
+        return HS_INVALID;
+    }
+    struct { const char *n; int *v; } k[] = {
+        {"warps", &g_opts.warps},       {"tile_bytes", &g_opts.tileBytes},
+        {"stages", &g_opts.stages},     {"wide_fdr", &g_opts.wideFdr},
+        {"chunk_mb", &g_opts.chunkMB},  {"initial_ring", &g_opts.initialRing}};
+    for (auto &x : k) {
+        if (!strcmp(key, x.n)) {
+            *x.v = value;
+            return HS_SUCCESS;
+        }
+    }
+    return HS_INVALID;
+}
+
+/* ---- scratch ---------------------------------------------------------------- */
+
+static hs_error_t newScratch(hs_scratch **out) {
+    initOpts();
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        return HS_ARCH_ERROR; /* no CPU scan path exists */
+    }
+    void *raw = g_scratch_alloc(sizeof(hs_scratch) + 64);
+    hs_error_t r = checkAlloc(raw);
+    if (r != HS_SUCCESS) {
+        g_scratch_free(raw);
+        return r;
+    }
+    hs_scratch *s = (hs_scratch *)HSB_ROUNDUP((uintptr_t)raw, 64);
+    memset(s, 0, sizeof(*s));
+    s->alloc_base = raw;
+    s->magic = SCRATCH_MAGIC;
+    cudaGetDevice(&s->device);
+    cudaDeviceGetAttribute(&s->smCount, cudaDevAttrMultiProcessorCount, s->device);
+    cudaDeviceGetAttribute(&s->maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+    s->images = new std::vector<DevImage *>();
+    s->chunkEvents = new std::vector<cudaEvent_t>();
+    s->tmpOff = new std::vector<u64>();
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->evStart);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->evStop);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, CTR_COUNT * sizeof(u32));
+    if (e == cudaSuccess) e = cudaMallocHost(&s->h_counters, CTR_COUNT * sizeof(u32));
+    if (e == cudaSuccess) {
+        memset(s->h_counters, 0, CTR_COUNT * sizeof(u32));
+        s->inlineCorpus = new hs_b200_corpus();
+        s->inlineCorpus->device = s->device;
+    }
+    if (e != cudaSuccess || growRing(s, (u32)g_opts.initialRing) != HS_SUCCESS) {
+        hs_free_scratch(s);
+        return e == cudaErrorMemoryAllocation ? HS_NOMEM : HS_UNKNOWN_ERROR;
+    }
+    *out = s;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_alloc_scratch(const hs_database_t *db, hs_scratch_t **scratch) {
+    if (!db || !scratch) {
+        return HS_INVALID;
+    }
+    hs_error_t r = dbIsValid(db);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    hs_scratch *s = *scratch;
+    if (s) {
+        if ((uintptr_t)s % 64 || s->magic != SCRATCH_MAGIC) {
+            return HS_INVALID;
+        }
+        if (markInUse(s)) {
+            return HS_SCRATCH_IN_USE;
+        }
+    } else {
+        r = newScratch(&s);
+        if (r != HS_SUCCESS) {
+            *scratch = nullptr;
+            return r;
+        }
+        s->in_use = 1;
+    }
+    const DevImage *im = nullptr;
+    r = findImage(s, db, &im);
+    unmarkInUse(s);
+    if (r != HS_SUCCESS) {
+        if (!*scratch) {
+            hs_free_scratch(s);
+        }
+        return r;
+    }
+    *scratch = s;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_clone_scratch(const hs_scratch_t *src, hs_scratch_t **dest) {
+    if (!dest || !src || (uintptr_t)src % 64 || src->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    *dest = nullptr;
+    hs_scratch *s = nullptr;
+    hs_error_t r = newScratch(&s);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    for (const DevImage *im : *src->images) {
+        const DevImage *mine = nullptr;
+        r = findImage(s, im->db, &mine);
+        if (r != HS_SUCCESS) {
+            hs_free_scratch(s);
+            return r;
+        }
+    }
+    r = growRing(s, src->outCap);
+    if (r != HS_SUCCESS) {
+        hs_free_scratch(s);
+        return r;
+    }
+    *dest = s;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_scratch_size(const hs_scratch_t *scratch, size_t *size) {
+    if (!size || !scratch || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    size_t n = sizeof(hs_scratch) + 64 + (size_t)scratch->outCap * sizeof(DevMatch);
+    for (const DevImage *im : *scratch->images) {
+        n += im->deviceBytes;
+    }
+    if (scratch->inlineCorpus) {
+        n += scratch->inlineCorpus->capData;
+    }
+    *size = n;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_free_scratch(hs_scratch_t *s) {
+    if (!s) {
+        return HS_SUCCESS;
+    }
+    if ((uintptr_t)s % 64 || s->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    if (markInUse(s)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    s->magic = 0;
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->images) {
+        for (DevImage *im : *s->images) {
+            freeImage(im);
+        }
+        delete s->images;
+    }
+    if (s->chunkEvents) {
+        for (cudaEvent_t ev : *s->chunkEvents) {
+            cudaEventDestroy(ev);
+        }
+        delete s->chunkEvents;
+    }
+    delete s->tmpOff;
+    freeCorpus(s->inlineCorpus);
+    cudaFree(s->d_out);
+    cudaFree(s->d_counters);
+    if (s->h_counters) cudaFreeHost(s->h_counters);
+    if (s->h_stage) cudaFreeHost(s->h_stage);
+    if (s->evStart) cudaEventDestroy(s->evStart);
+    if (s->evStop) cudaEventDestroy(s->evStop);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->copyStream) cudaStreamDestroy(s->copyStream);
+    g_scratch_free(s->alloc_base);
+    return HS_SUCCESS;
+}
+
+/* ---- corpus handles ------------------------------------------------------------ */
+
+static hs_error_t setBlocks(hs_b200_corpus *c, const u64 *packed, const unsigned *lengths,
+                            size_t nblocks, u64 total, u64 payload, cudaStream_t stream) {
+    c->nblocks = nblocks;
+    c->bytes = total;
+    c->payload = payload;
+    c->uniformPitch = detectPitch(packed, lengths, nblocks);
+    if (nblocks) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_off, packed, nblocks * sizeof(u64), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(c->d_len, lengths, nblocks * sizeof(u32), cudaMemcpyHostToDevice, stream));
+    }
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_corpus_upload(const char *data, const unsigned long long *offsets,
+                                 const unsigned int *lengths, size_t nblocks, int device,
+                                 hs_b200_corpus_t **corpus) {
+    if (!corpus || (nblocks && (!data || !offsets || !lengths)) || nblocks > 0xfffffff0u) {
+        return HS_INVALID;
+    }
+    *corpus = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        return HS_ARCH_ERROR;
+    }
+    hs_b200_corpus *c = new (std::nothrow) hs_b200_corpus();
+    if (!c) {
+        return HS_NOMEM;
+    }
+    c->device = device;
+    std::vector<u64> packed;
+    u64 total = 0, payload = 0;
+    bool direct = false;
+    layoutBlocks(nullptr, offsets, lengths, nblocks, &packed, &total, &payload, &direct);
+    hs_error_t r = reserveCorpus(c, total, nblocks);
+    if (r != HS_SUCCESS) {
+        freeCorpus(c);
+        return r;
+    }
+    cudaError_t e = cudaSuccess;
+    if (direct) {
+        e = cudaMemcpy(c->d_data, data + offsets[0], total, cudaMemcpyHostToDevice);
+    } else {
+        /* pack through a host buffer in 64 MiB pieces */
+        std::vector<u8> stage;
+        const size_t CH = 64u << 20;
+        size_t i = 0;
+        while (i < nblocks && e == cudaSuccess) {
+            const u64 start = packed[i];
+            size_t j = i;
+            while (j < nblocks && packed[j] + lengths[j] - start <= CH) {
+                j++;
+            }
+            if (j == i) {
+                j = i + 1;
+            }
+            const u64 end = packed[j - 1] + lengths[j - 1];
+            stage.assign(end - start, 0);
+            for (size_t k = i; k < j; k++) {
+                memcpy(stage.data() + (packed[k] - start), data + offsets[k], lengths[k]);
+            }
+            e = cudaMemcpy(c->d_data + start, stage.data(), end - start, cudaMemcpyHostToDevice);
+            i = j;
+        }
+    }
+    if (e == cudaSuccess) {
+        /* zero the tail so the last tile's look-ahead reads defined bytes */
+        e = cudaMemset(c->d_data + total, 0, HSB_ROUNDUP(total, 16) + 32 - total);
+    }
+    c->readableEnd = HSB_ROUNDUP(total, 16) + 16;
+    if (e == cudaSuccess) {
+        r = setBlocks(c, packed.data(), lengths, nblocks, total, payload, 0);
+        if (r == HS_SUCCESS && cudaDeviceSynchronize() != cudaSuccess) {
+            r = HS_UNKNOWN_ERROR;
+        }
+    } else {
+        r = HS_UNKNOWN_ERROR;
+    }
+    if (r != HS_SUCCESS) {
+        freeCorpus(c);
+        return r;
+    }
+    *corpus = c;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_corpus_wrap(const void *d_data, size_t data_bytes,
+                               const unsigned long long *offsets, const unsigned int *lengths,
+                               size_t nblocks, int device, hs_b200_corpus_t **corpus) {
+    if (!corpus || !d_data || (uintptr_t)d_data % 16 || (nblocks && (!offsets || !lengths)) ||
+        nblocks > 0xfffffff0u) {
+        return HS_INVALID;
+    }
+    *corpus = nullptr;
+    u64 prevEnd = 0, payload = 0;
+    for (size_t i = 0; i < nblocks; i++) {
+        if (offsets[i] % 16 || offsets[i] < prevEnd || offsets[i] + lengths[i] > data_bytes) {
+            return HS_INVALID;
+        }
+        prevEnd = offsets[i] + lengths[i];
+        payload += lengths[i];
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        return HS_ARCH_ERROR;
+    }
+    hs_b200_corpus *c = new (std::nothrow) hs_b200_corpus();
+    if (!c) {
+        return HS_NOMEM;
+    }
+    c->device = device;
+    hs_error_t r = HS_SUCCESS;
+    if (nblocks) {
+        cudaError_t e = cudaMalloc(&c->d_off, nblocks * sizeof(u64));
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_len, nblocks * sizeof(u32));
+        if (e != cudaSuccess) {
+            freeCorpus(c);
+            return HS_NOMEM;
+        }
+        c->capBlocks = nblocks;
+    }
+    c->d_data = (u8 *)d_data;
+    /* the caller's buffer must be readable up to data_bytes rounded up to 16 */
+    c->readableEnd = HSB_ROUNDUP((u64)data_bytes, 16);
+    std::vector<u64> off(offsets, offsets + nblocks);
+    r = setBlocks(c, off.data(), lengths, nblocks, prevEnd, payload, 0);
+    if (r == HS_SUCCESS && cudaDeviceSynchronize() != cudaSuccess) {
+        r = HS_UNKNOWN_ERROR;
+    }
+    if (r != HS_SUCCESS) {
+        freeCorpus(c);
+        return r;
+    }
+    *corpus = c;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_corpus_free(hs_b200_corpus_t *corpus) {
+    freeCorpus(corpus);
+    return HS_SUCCESS;
+}
+
+size_t hs_b200_corpus_bytes(const hs_b200_corpus_t *corpus) {
+    return corpus ? (size_t)corpus->payload : 0;
+}
+
+/* ---- device-resident scan --------------------------------------------------------- */
+
+static hs_error_t checkScanArgs(const hs_database_t *db, hs_scratch_t *scratch) {
+    hs_error_t err = validDb(db);
+    if (err != HS_SUCCESS) {
+        return err;
+    }
+    const RoseEngine *rose = dbRose(db);
+    if ((uintptr_t)rose % 16) {
+        return HS_INVALID;
+    }
+    if (rose->mode != MODE_BLOCK) {
+        return HS_DB_MODE_ERROR;
+    }
+    if ((uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_scan_corpus_async(const hs_database_t *db, const hs_b200_corpus_t *corpus,
+                                     hs_scratch_t *scratch, void *cuda_stream) {
+    if (!scratch || !corpus) {
+        return HS_INVALID;
+    }
+    hs_error_t r = checkScanArgs(db, scratch);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    const DevImage *im = nullptr;
+    r = findImage(scratch, db, &im);
+    if (r == HS_SUCCESS) {
+        cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : scratch->stream;
+        if (corpus->bytes == 0 || corpus->nblocks == 0) {
+            scratch->h_counters[CTR_MATCHES] = 0;
+            scratch->h_counters[CTR_ERROR] = 0;
+            scratch->lastImage = im;
+            scratch->lastCorpus = corpus;
+            scratch->pending = false;
+            scratch->lastCount = 0;
+        } else {
+            r = enqueueScan(scratch, im, corpus, st);
+        }
+    }
+    unmarkInUse(scratch);
+    return r;
+}
+
+hs_error_t hs_b200_scan_corpus_finish(hs_scratch_t *scratch, unsigned long long *nrecords,
+                                      const void **d_records) {
+    if (!scratch || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    u32 count = scratch->lastCount;
+    if (scratch->pending) {
+        hs_error_t r = finishScan(scratch, &count);
+        if (r != HS_SUCCESS) {
+            return r;
+        }
+    }
+    if (nrecords) {
+        *nrecords = count;
+    }
+    if (d_records) {
+        *d_records = scratch->d_out;
+    }
+    if (count > scratch->outCap) {
+        /* ring overflowed: grow so that a re-run succeeds */
+        u64 want = (u64)count + count / 4 + 1024;
+        if (want > 0xfffffff0ull) {
+            want = 0xfffffff0ull;
+        }
+        hs_error_t r = growRing(scratch, (u32)want);
+        if (r != HS_SUCCESS) {
+            return r;
+        }
+        return HS_INSUFFICIENT_SPACE;
+    }
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_copy_records(hs_scratch_t *scratch, void *d_dst, size_t cap) {
+    if (!scratch || !d_dst || scratch->pending) {
+        return HS_INVALID;
+    }
+    const size_t n = std::min<size_t>(cap, std::min<u32>(scratch->lastCount, scratch->outCap));
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(d_dst, scratch->d_out, n * sizeof(DevMatch),
+                                 cudaMemcpyDeviceToDevice, scratch->stream));
+        CUDA_TRY(cudaStreamSynchronize(scratch->stream));
+    }
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_postprocess_matches(const hs_database_t *db, hs_scratch_t *scratch,
+                                       hs_b200_match_t *recs, size_t n,
+                                       unsigned long long *nout) {
+    if (!scratch || !db || (n && !recs) || !nout) {
+        return HS_INVALID;
+    }
+    const DevImage *im = nullptr;
+    hs_error_t r = findImage(scratch, db, &im);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    static_assert(sizeof(DevMatch) == sizeof(hs_b200_match_t), "record layout");
+    *nout = postprocess(im, (DevMatch *)recs, n);
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_fetch_matches(const hs_database_t *db, hs_scratch_t *scratch,
+                                 hs_b200_match_t *out, size_t cap,
+                                 unsigned long long *nmatches) {
+    if (!scratch || !db || scratch->pending) {
+        return HS_INVALID;
+    }
+    const DevImage *im = nullptr;
+    hs_error_t r = findImage(scratch, db, &im);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    const u32 n = std::min(scratch->lastCount, scratch->outCap);
+    std::vector<DevMatch> tmp(n);
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(tmp.data(), scratch->d_out, (size_t)n * sizeof(DevMatch),
+                                 cudaMemcpyDeviceToHost, scratch->stream));
+        CUDA_TRY(cudaStreamSynchronize(scratch->stream));
+    }
+    const size_t m = postprocess(im, tmp.data(), n);
+    if (nmatches) {
+        *nmatches = m;
+    }
+    if (out) {
+        if (cap < m) {
+            return HS_INSUFFICIENT_SPACE;
+        }
+        memcpy(out, tmp.data(), m * sizeof(DevMatch));
+    }
+    return HS_SUCCESS;
+}
+
+/* ---- host-buffer scans -------------------------------------------------------------- */
+
+/* Copy host blocks into the scratch's inline corpus and scan them, with the
+ * host->device copy pipelined against the kernel in chunk_mb pieces. */
+static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *data,
+                                 const unsigned long long *offsets, const unsigned *lengths,
+                                 size_t nblocks, std::vector<DevMatch> *matches) {
+    hs_b200_corpus *c = s->inlineCorpus;
+    std::vector<u64> &packed = *s->tmpOff;
+    u64 total = 0, payload = 0;
+    bool direct = false;
+    layoutBlocks(s, offsets, lengths, nblocks, &packed, &total, &payload, &direct);
+    matches->clear();
+    if (total == 0) {
+        return HS_SUCCESS;
+    }
+    hs_error_t r = reserveCorpus(c, total, nblocks);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    c->readableEnd = HSB_ROUNDUP(total, 16) + 16;
+    r = setBlocks(c, packed.data(), lengths, nblocks, total, payload, s->copyStream);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    ScanPlan pl;
+    r = planScan(s, im, &pl);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    const u64 chunk = (u64)std::max(1, g_opts.chunkMB) << 20;
+    const size_t nchunks = (size_t)((total + chunk - 1) / chunk);
+    while (s->chunkEvents->size() < nchunks + 1) {
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        s->chunkEvents->push_back(ev);
+    }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, CTR_COUNT * sizeof(u32), s->stream));
+        CUDA_TRY(cudaEventRecord(s->evStart, s->stream));
+        /* zero the look-ahead bytes after the corpus */
+        CUDA_TRY(cudaMemsetAsync(c->d_data + total, 0, HSB_ROUNDUP(total, 16) + 32 - total,
+                                 s->copyStream));
+        u32 tDone = 0;
+        size_t blk = 0;
+        for (size_t ci = 0; ci < nchunks; ci++) {
+            const u64 from = ci * chunk, to = std::min<u64>(total, from + chunk);
+            if (attempt == 0) {
+                if (direct) {
+                    CUDA_TRY(cudaMemcpyAsync(c->d_data + from, data + offsets[0] + from, to - from,
+                                             cudaMemcpyHostToDevice, s->copyStream));
+                } else {
+                    /* per-block copies (unaligned host layout); blocks that
+                     * straddle the chunk edge are copied whole */
+                    while (blk < nblocks && packed[blk] < to) {
+                        if (lengths[blk]) {
+                            CUDA_TRY(cudaMemcpyAsync(c->d_data + packed[blk], data + offsets[blk],
+                                                     lengths[blk], cudaMemcpyHostToDevice,
+                                                     s->copyStream));
+                        }
+                        blk++;
+                    }
+                }
+                CUDA_TRY(cudaEventRecord((*s->chunkEvents)[ci], s->copyStream));
+                CUDA_TRY(cudaStreamWaitEvent(s->stream, (*s->chunkEvents)[ci], 0));
+            }
+            /* tiles wholly inside the copied prefix (plus look-ahead) */
+            u32 tEnd;
+            if (ci + 1 == nchunks) {
+                tEnd = (u32)((total + pl.tileBytes - 1) / pl.tileBytes);
+            } else {
+                u64 covered = direct ? to : (blk < nblocks ? packed[blk] : total);
+                covered = std::min(covered, to);
+                tEnd = covered > 16 ? (u32)((covered - 16) / pl.tileBytes) : 0;
+            }
+            r = launchRange(s, im, c, pl, tDone, tEnd, s->stream);
+            if (r != HS_SUCCESS) {
+                return r;
+            }
+            tDone = std::max(tDone, tEnd);
+        }
+        CUDA_TRY(cudaEventRecord(s->evStop, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, CTR_COUNT * sizeof(u32),
+                                 cudaMemcpyDeviceToHost, s->stream));
+        s->lastImage = im;
+        s->lastCorpus = c;
+        s->activeStream = s->stream;
+        s->pending = true;
+        u32 count = 0;
+        r = finishScan(s, &count);
+        if (r != HS_SUCCESS) {
+            return r;
+        }
+        if (count <= s->outCap) {
+            matches->resize(count);
+            if (count) {
+                CUDA_TRY(cudaMemcpyAsync(matches->data(), s->d_out, (size_t)count * sizeof(DevMatch),
+                                         cudaMemcpyDeviceToHost, s->stream));
+                CUDA_TRY(cudaStreamSynchronize(s->stream));
+            }
+            matches->resize(postprocess(im, matches->data(), count));
+            return HS_SUCCESS;
+        }
+        /* record ring overflowed: grow it and scan the resident corpus again */
+        u64 want = (u64)count + count / 4 + 1024;
+        if (want > 0xfffffff0ull) {
+            return HS_NOMEM;
+        }
+        r = growRing(s, (u32)want);
+        if (r != HS_SUCCESS) {
+            return r;
+        }
+    }
+    return HS_UNKNOWN_ERROR;
+}
+
+hs_error_t hs_b200_scan_blocks(const hs_database_t *db, const char *data,
+                               const unsigned long long *offsets, const unsigned int *lengths,
+                               size_t nblocks, hs_scratch_t *scratch,
+                               hs_b200_block_event_handler onEvent, void *context,
+                               unsigned long long *nmatches) {
+    if (!scratch || (nblocks && (!data || !offsets || !lengths)) || nblocks > 0xfffffff0u) {
+        return HS_INVALID;
+    }
+    hs_error_t r = checkScanArgs(db, scratch);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    const DevImage *im = nullptr;
+    r = findImage(scratch, db, &im);
+    std::vector<DevMatch> matches;
+    if (r == HS_SUCCESS) {
+        r = scanHostBlocks(im, scratch, data, offsets, lengths, nblocks, &matches);
+    }
+    unsigned long long delivered = 0;
+    if (r == HS_SUCCESS) {
+        if (!onEvent) {
+            delivered = matches.size();
+        } else {
+            u32 stopped = 0xffffffffu;
+            for (const DevMatch &m : matches) {
+                if (m.block == stopped) {
+                    continue;
+                }
+                delivered++;
+                if (onEvent(m.block, m.id, 0, m.to, 0, context)) {
+                    stopped = m.block;
+                }
+            }
+        }
+    }
+    if (nmatches) {
+        *nmatches = delivered;
+    }
+    unmarkInUse(scratch);
+    return r;
+}
+
+hs_error_t hs_scan(const hs_database_t *db, const char *data, unsigned int length,
+                   unsigned int flags, hs_scratch_t *scratch, match_event_handler onEvent,
+                   void *context) {
+    (void)flags;
+    if (!scratch || !data) {
+        return HS_INVALID;
+    }
+    hs_error_t r = checkScanArgs(db, scratch);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    const RoseEngine *rose = dbRose(db);
+    if (rose->minWidth > length) { /* src/runtime.c:346-350 */
+        unmarkInUse(scratch);
+        return HS_SUCCESS;
+    }
+    const DevImage *im = nullptr;
+    r = findImage(scratch, db, &im);
+    std::vector<DevMatch> matches;
+    if (r == HS_SUCCESS) {
+        const unsigned long long off = 0;
+        r = scanHostBlocks(im, scratch, data, &off, &length, 1, &matches);
+    }
+    if (r == HS_SUCCESS && onEvent) {
+        for (const DevMatch &m : matches) {
+            if (onEvent(m.id, 0, m.to, 0, context)) {
+                r = HS_SCAN_TERMINATED; /* src/report.h:324-328 */
+                break;
+            }
+        }
+    }
+    unmarkInUse(scratch);
+    return r;
+}
+
+} /* extern "C" */

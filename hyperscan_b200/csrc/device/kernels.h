@@ -1,0 +1,90 @@
+/*
+ * kernels.h -- launch interface between the C-ABI shim (api_device.cu) and the
+ * sm_100a scan kernels (scan_kernels.cu).  Plain PODs only.
+ */
+#ifndef HSB200_KERNELS_H
+#define HSB200_KERNELS_H
+
+#include <cuda_runtime.h>
+
+#include "../ref_layout.h"
+
+namespace hsb {
+
+/* One match record as the device writes it: identical to hs_b200_match_t
+ * (include/hs_b200.h). */
+struct DevMatch {
+    u32 id;
+    u32 block;
+    u64 to;
+};
+
+/* First-stage ("shift-OR") filter variants.  An entry read at sampled position
+ * x holds SLOTS bytes; byte p has bit b SET iff no literal of bucket b can end
+ * at position x+p given the bytes at x (FDR: src/fdr/fdr.c:157-327; Teddy:
+ * src/fdr/teddy.c:918-969 -- see DESIGN.md section 3 for the derivation). */
+enum FilterKind {
+    FK_BYTE32 = 0, /* index = 1 byte; u32 entry (4 slots x 8 buckets); table
+                      replicated per lane (bank-conflict free). Teddy, noodle */
+    FK_BYTE64 = 1, /* index = 1 byte; 2 x u32 (4 slots x 16 buckets). Fat Teddy */
+    FK_HASH32 = 2, /* index = 2-byte FDR hash; u32 entry (slots 0..3 of FDR) */
+    FK_HASH64 = 3, /* index = 2-byte FDR hash; u64 entry (all 8 FDR slots)   */
+};
+
+enum ConfirmKind {
+    CK_FDR = 0,    /* hash confirm: FDRConfirm / LitInfo (src/fdr/fdr_confirm.h) */
+    CK_NOODLE = 1, /* single literal: noodTable msk/cmp (src/hwlm/noodle_internal.h) */
+};
+
+enum { CTR_MATCHES = 0, CTR_ERROR = 1, CTR_CANDIDATES = 2, CTR_CONFIRMED = 3, CTR_COUNT = 8 };
+enum { ERR_BAD_OPCODE = 1, ERR_INTERNAL = 2 };
+
+struct ScanParams {
+    /* corpus: position 0 = first byte of the packed corpus; bytes
+     * [-16, paddedBytes + 16) are readable; blocks start 16-byte aligned */
+    const u8 *corpus;
+    u64 corpusBytes;       /* end of the last block */
+    u64 readableEnd;       /* multiple of 16, >= corpusBytes: TMA may read up to here */
+    u32 tileFirst;         /* tiles [tileFirst, tileFirst + ntiles) are scanned */
+    u32 ntiles;
+    u32 tileBytes;         /* multiple of 512 */
+    u32 nstages;           /* per-warp TMA ring depth */
+    const u64 *blockOff;   /* ascending, 16-byte aligned */
+    const u32 *blockLen;
+    u32 nblocks;
+    u32 uniformPitch;      /* != 0: blockOff[i] == i * uniformPitch */
+    /* database image */
+    const u8 *bc;          /* RoseEngine bytecode (device copy) */
+    const u8 *table;       /* first-stage table in HBM (copied to smem) */
+    u32 tableBytes;
+    u32 indexMask;         /* FK_HASH*: FDR domainMask */
+    u32 confOff;           /* CK_FDR: offset of the confirm base in bc */
+    u32 engineOff;         /* CK_NOODLE: offset of the noodTable in bc */
+    u32 confirmKind;
+    u64 groups;
+    /* output */
+    DevMatch *out;
+    u32 outCap;
+    u32 *counters;
+};
+
+struct LaunchCfg {
+    int kind;      /* FilterKind */
+    int stride;    /* 1, 2, 4 */
+    int grid;      /* CTAs (one per SM) */
+    int warps;     /* per CTA */
+    size_t smemBytes;
+};
+
+/* Dynamic shared memory the kernel needs. */
+size_t scanSmemBytes(int kind, u32 tableBytes, int warps, u32 nstages, u32 tileBytes);
+
+cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream);
+
+/* accel primitives (src/nfa/shufti.c, truffle.c, vermicelli.h): first
+ * position in [0,len) whose byte is in the class, or len. */
+cudaError_t launchAccelFind(int type, const u8 *params, const u8 *d_buf, u64 len,
+                            u64 *d_result, cudaStream_t stream);
+
+} // namespace hsb
+#endif

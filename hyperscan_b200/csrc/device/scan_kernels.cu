@@ -1,0 +1,699 @@
+/*
+ * scan_kernels.cu -- sm_100a scan kernels for the floating literal matcher:
+ * first-stage shift-OR filter (FDR / Teddy / noodle tables), hash confirm and
+ * the pure-literal rose program, all on the device.
+ *
+ * Replaces the reference's hwlmExec() and everything below it
+ * (src/hwlm/hwlm.c:172-199 -> src/hwlm/noodle_engine.c, src/fdr/fdr.c,
+ * src/fdr/teddy.c, src/fdr/fdr_confirm_runtime.h) together with the
+ * per-literal callback chain roseCallback -> roseRunProgram_l
+ * (src/rose/match.c:479-527, src/rose/program_runtime.c:3101-3522).
+ *
+ * Execution model:
+ *   - persistent grid, one CTA per SM; the first-stage table is pinned in
+ *     shared memory once per CTA;
+ *   - the packed corpus is cut into fixed-size tiles regardless of block
+ *     boundaries (the first stage is position-only; block membership is
+ *     checked in the confirm stage); every warp owns a CONTIGUOUS run of
+ *     tiles so the shift-OR state carries across tiles;
+ *   - tiles are staged global -> shared with 1-D TMA bulk copies
+ *     (cp.async.bulk + mbarrier complete_tx), an NSTAGE-deep ring per warp;
+ *   - per 512-byte step every lane reads its own 16 bytes as one uint4, does
+ *     16/STRIDE table lookups, shift-ORs them into per-end-position bytes;
+ *     the 3 (or 7) bytes that overflow into the next lane travel by
+ *     __shfl_up_sync; a zero bit = candidate (bucket, end position);
+ *   - candidates (rare) are confirmed in place: FDRConfirm hash -> LitInfo
+ *     chain -> block lookup -> rose literal program -> 16-byte match record
+ *     appended to a ring in HBM.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace hsb {
+
+namespace {
+
+/* ---- PTX wrappers: mbarrier + 1-D TMA bulk copy ------------------------- */
+
+__device__ __forceinline__ u32 smemAddr(const void *p) {
+    return (u32)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbarInit(u64 *bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(u64 *bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tmaLoad1d(void *dst, const void *src, u32 bytes, u64 *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smemAddr(dst)),
+        "l"(src), "r"(bytes), "r"(smemAddr(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbarWait(u64 *bar, u32 parity) {
+    u32 done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smemAddr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+/* ---- read-only loads of the database image ------------------------------- */
+
+__device__ __forceinline__ u32 ld32(const u8 *p) { return __ldg((const u32 *)p); }
+__device__ __forceinline__ u64 ld64(const u8 *p) {
+    const uint2 v = __ldg((const uint2 *)p);
+    return ((u64)v.y << 32) | v.x;
+}
+__device__ __forceinline__ u8 ld8(const u8 *p) { return __ldg(p); }
+
+/* ---- confirm stage -------------------------------------------------------- */
+
+struct BlockRef {
+    const u8 *base; /* first byte of the block */
+    u32 len;
+    u32 index;
+};
+
+/* Which block holds corpus position g?  (Blocks are 16-byte aligned, sorted,
+ * disjoint; gaps belong to no block.) */
+__device__ bool findBlock(const ScanParams &p, u64 g, BlockRef *out) {
+    if (g >= p.corpusBytes) {
+        return false;
+    }
+    u32 b;
+    if (p.uniformPitch) {
+        b = (u32)(g / p.uniformPitch);
+    } else {
+        u32 lo = 0, hi = p.nblocks; /* largest b with off[b] <= g */
+        while (hi - lo > 1) {
+            const u32 mid = lo + ((hi - lo) >> 1);
+            if (__ldg(p.blockOff + mid) <= g) {
+                lo = mid;
+            } else {
+                hi = mid;
+            }
+        }
+        b = lo;
+    }
+    if (b >= p.nblocks) {
+        return false;
+    }
+    const u64 off = __ldg(p.blockOff + b);
+    const u32 len = __ldg(p.blockLen + b);
+    if (g < off || g - off >= len) {
+        return false;
+    }
+    out->base = p.corpus + off;
+    out->len = len;
+    out->index = b;
+    return true;
+}
+
+__device__ __forceinline__ void emitMatch(const ScanParams &p, u32 id, u32 block, u64 to) {
+    const u32 i = atomicAdd(p.counters + CTR_MATCHES, 1u);
+    if (i < p.outCap) {
+        DevMatch m;
+        m.id = id;
+        m.block = block;
+        m.to = to;
+        *reinterpret_cast<uint4 *>(p.out + i) = *reinterpret_cast<const uint4 *>(&m);
+    }
+}
+
+__device__ __forceinline__ u8 upperAscii(u8 c) {
+    return (c >= 'a' && c <= 'z') ? (u8)(c - 0x20) : c;
+}
+
+/* CHECK_MED_LIT / CHECK_LONG_LIT, block mode: the lit_length bytes ending at
+ * `to` must equal the stored literal, which is stored upper-cased for the
+ * _NOCASE variants (src/rose/program_runtime.c:1883-2014). */
+__device__ bool checkLiteral(const u8 *bc, const BlockRef &blk, u64 to, u32 litOff, u32 litLen,
+                             bool nocase) {
+    if (to < litLen) {
+        return false;
+    }
+    const u8 *lit = bc + litOff;
+    const u8 *d = blk.base + (to - litLen);
+    for (u32 i = 0; i < litLen; i++) {
+        u8 c = d[i];
+        if (nocase) {
+            c = upperAscii(c);
+        }
+        if (c != ld8(lit + i)) {
+            return false;
+        }
+    }
+    return true;
+}
+
+/* CHECK_MASK: 8 bytes at to+offset; byte lanes outside the block are ignored
+ * (src/rose/program_runtime.c:644-726, src/rose/validate_mask.h:83-103). */
+__device__ bool checkMask8(const BlockRef &blk, u64 to, u64 andM, u64 cmpM, u64 negM, s32 off) {
+    const long long start = (long long)to + off;
+    if (start < 0) {
+        return false; /* "too early, fail": block mode has no history */
+    }
+    for (int i = 0; i < 8; i++) {
+        const long long q = start + i;
+        if (q < 0 || q >= (long long)blk.len) {
+            continue;
+        }
+        const u8 d = blk.base[q];
+        const u8 a = (u8)(andM >> (8 * i)), c = (u8)(cmpM >> (8 * i));
+        const bool eq = ((d & a) ^ c) == 0;
+        const bool neg = ((negM >> (8 * i)) & 0xff) != 0;
+        if (eq == neg) {
+            return false;
+        }
+    }
+    return true;
+}
+
+/* CHECK_BYTE (src/rose/program_runtime.c:600-641). */
+__device__ bool checkByte(const BlockRef &blk, u64 to, u8 andM, u8 cmpM, u8 neg, s32 off) {
+    const long long q = (long long)to + off;
+    if (q < 0) {
+        return false; /* "too early, fail" (no history in block mode) */
+    }
+    if (q >= (long long)blk.len) {
+        return true;  /* in the future: passes */
+    }
+    const u8 c = blk.base[q];
+    return !(((andM & c) != cmpM) ^ (neg != 0));
+}
+
+template <class T> __device__ __forceinline__ T loadInstr(const u8 *pc) {
+    T t;
+    const u32 *s = (const u32 *)pc; /* instructions are 8-byte aligned */
+    u32 *d = (u32 *)&t;
+#pragma unroll
+    for (u32 i = 0; i < (sizeof(T) + 3) / 4; i++) {
+        d[i] = __ldg(s + i);
+    }
+    return t;
+}
+
+/* Literal program at bytecode offset `prog` for a literal whose last byte is
+ * block offset `end` (to = end + 1: lit_offset_adjust, src/rose/match.c:483).
+ * The stateless part of roseRunProgram_l: exhaustion (CHECK_EXHAUSTED /
+ * REPORT_EXHAUST) and dedupe (DEDUPE*) are order-dependent and are applied
+ * when the records are ordered for delivery (host); here
+ * they pass. */
+__device__ void runProgram(const ScanParams &p, const BlockRef &blk, u32 prog, u64 to) {
+    const u8 *pc = p.bc + prog;
+#define NEXT(T) pc += HSB_ROUNDUP(sizeof(T), INSTR_ALIGN)
+    for (int guard = 0; guard < 4096; guard++) {
+        const u8 code = ld8(pc);
+        switch (code) {
+        case OP_END:
+            return;
+        case OP_CHECK_GROUPS: {
+            const InstrCheckGroups in = loadInstr<InstrCheckGroups>(pc);
+            if (!(in.groups & p.groups)) {
+                return;
+            }
+            NEXT(InstrCheckGroups);
+            break;
+        }
+        case OP_CHECK_MASK: {
+            const InstrCheckMask in = loadInstr<InstrCheckMask>(pc);
+            if (!checkMask8(blk, to, in.and_mask, in.cmp_mask, in.neg_mask, in.offset)) {
+                pc += in.fail_jump;
+            } else {
+                NEXT(InstrCheckMask);
+            }
+            break;
+        }
+        case OP_CHECK_BYTE: {
+            const InstrCheckByte in = loadInstr<InstrCheckByte>(pc);
+            if (!checkByte(blk, to, in.and_mask, in.cmp_mask, in.negation, in.offset)) {
+                pc += in.fail_jump;
+            } else {
+                NEXT(InstrCheckByte);
+            }
+            break;
+        }
+        case OP_CHECK_MED_LIT:
+        case OP_CHECK_MED_LIT_NOCASE:
+        case OP_CHECK_LONG_LIT:
+        case OP_CHECK_LONG_LIT_NOCASE: {
+            const InstrCheckLit in = loadInstr<InstrCheckLit>(pc);
+            const bool nc = code == OP_CHECK_MED_LIT_NOCASE || code == OP_CHECK_LONG_LIT_NOCASE;
+            if (!checkLiteral(p.bc, blk, to, in.lit_offset, in.lit_length, nc)) {
+                pc += in.fail_jump;
+            } else {
+                NEXT(InstrCheckLit);
+            }
+            break;
+        }
+        case OP_CHECK_EXHAUSTED:
+            NEXT(InstrCheckExhausted);
+            break;
+        case OP_DEDUPE:
+            NEXT(InstrDedupe);
+            break;
+        case OP_REPORT: {
+            const InstrReport in = loadInstr<InstrReport>(pc);
+            emitMatch(p, in.onmatch, blk.index, to + in.offset_adjust);
+            NEXT(InstrReport);
+            break;
+        }
+        case OP_REPORT_EXHAUST: {
+            const InstrReportExhaust in = loadInstr<InstrReportExhaust>(pc);
+            emitMatch(p, in.onmatch, blk.index, to + in.offset_adjust);
+            NEXT(InstrReportExhaust);
+            break;
+        }
+        case OP_DEDUPE_AND_REPORT: {
+            const InstrDedupeAndReport in = loadInstr<InstrDedupeAndReport>(pc);
+            emitMatch(p, in.onmatch, blk.index, to + in.offset_adjust);
+            NEXT(InstrDedupeAndReport);
+            break;
+        }
+        case OP_FINAL_REPORT: {
+            const InstrFinalReport in = loadInstr<InstrFinalReport>(pc);
+            emitMatch(p, in.onmatch, blk.index, to + in.offset_adjust);
+            return;
+        }
+        case OP_SQUASH_GROUPS: /* group squashing only prunes work */
+            NEXT(InstrSquashGroups);
+            break;
+        case OP_CLEAR_WORK_DONE:
+            pc += INSTR_ALIGN;
+            break;
+        case OP_INCLUDED_JUMP: /* the child literal is confirmed on its own */
+            NEXT(InstrIncludedJump);
+            break;
+        case OP_SET_EXHAUST:
+            NEXT(InstrSetExhaust);
+            break;
+        default:
+            atomicExch(p.counters + CTR_ERROR, (u32)ERR_BAD_OPCODE);
+            return;
+        }
+    }
+#undef NEXT
+    atomicExch(p.counters + CTR_ERROR, (u32)ERR_BAD_OPCODE);
+}
+
+/* Second stage for one candidate (bucket, corpus position g of the last
+ * byte); confVal = little-endian u64 of the bytes [g-7, g].  Restates
+ * confWithBit (src/fdr/fdr_confirm_runtime.h:43-102) minus the callback
+ * feedback: bytes before the block start never decide (every accepted
+ * literal lies inside the block, item 3 of SURVEY.md A.1). */
+__device__ void confirmFdr(const ScanParams &p, u32 bucket, u64 g, u64 confVal, u32 *nconf) {
+    const u8 *confBase = p.bc + p.confOff;
+    const u32 cf = ld32(confBase + 4 * bucket);
+    if (!cf) {
+        return;
+    }
+    const u8 *fc = confBase + cf; /* struct FDRConfirm */
+    if (!(ld64(fc + 24) & p.groups)) {
+        return;
+    }
+    const u64 andmsk = ld64(fc + 0), mult = ld64(fc + 8);
+    const u32 nBits = ld32(fc + 16);
+    const u32 c = (u32)(((confVal & andmsk) * mult) >> (64 - nBits));
+    const u32 start = ld32(fc + sizeof(FDRConfirm) + 4 * c);
+    if (!start) {
+        return;
+    }
+    const u8 *li = fc + start; /* struct LitInfo chain */
+    bool haveBlock = false, inBlock = false;
+    BlockRef blk;
+    for (;;) {
+        const u64 v = ld64(li + 0), msk = ld64(li + 8);
+        const u32 tail = ld32(li + 28); /* size | flags << 8 | next << 16 */
+        if ((confVal & msk) == v && (ld64(li + 16) & p.groups)) {
+            if (!haveBlock) {
+                inBlock = findBlock(p, g, &blk);
+                haveBlock = true;
+            }
+            if (inBlock) {
+                const u64 end = (u64)(p.corpus + g - blk.base);
+                if ((tail & 0xff) <= end + 1) {
+                    (*nconf)++;
+                    runProgram(p, blk, ld32(li + 24), end + 1);
+                }
+            }
+        }
+        if (!((tail >> 16) & 0xff)) {
+            break;
+        }
+        li += sizeof(LitInfo);
+    }
+}
+
+/* Noodle second stage (src/hwlm/noodle_engine.c:114-141): the msk_len bytes
+ * ending at g, first byte in the low lane, under msk must equal cmp. */
+__device__ void confirmNoodle(const ScanParams &p, u64 g, u64 confVal, u32 *nconf) {
+    const u8 *n = p.bc + p.engineOff; /* struct noodTable */
+    const u32 mskLen = ld8(n + 24);
+    const u64 msk = ld64(n + 8), cmp = ld64(n + 16);
+    const u64 v = mskLen >= 8 ? confVal : confVal >> (8 * (8 - mskLen));
+    if ((v & msk) != cmp) {
+        return;
+    }
+    BlockRef blk;
+    if (!findBlock(p, g, &blk)) {
+        return;
+    }
+    const u64 end = (u64)(p.corpus + g - blk.base);
+    if (mskLen > end + 1) {
+        return;
+    }
+    (*nconf)++;
+    runProgram(p, blk, ld32(n + 0), end + 1);
+}
+
+/* ---- first stage ----------------------------------------------------------- */
+
+template <int KIND> struct Kind {
+    static constexpr int NOCT = KIND == FK_BYTE64 ? 2 : 1;  /* bucket octets */
+    static constexpr int SPILL = KIND == FK_HASH64 ? 2 : 1; /* words overflowing into the next lane */
+    static constexpr bool HASH = KIND == FK_HASH32 || KIND == FK_HASH64;
+};
+
+__device__ __forceinline__ void orShift32(u32 *a, int k, int r, u32 e) {
+    if (r == 0) {
+        a[k] |= e;
+    } else {
+        a[k] |= e << (8 * r);
+        a[k + 1] |= e >> (32 - 8 * r);
+    }
+}
+
+/* Shift-OR contributions of one lane's 16 positions.  a[o][0..3]: bytes for
+ * the lane's own 16 end positions (bit set = bucket impossible); a[o][4..]:
+ * overflow that belongs to the NEXT lane's first positions.  Only positions
+ * = 0 mod STRIDE are sampled; skipped positions contribute nothing, i.e.
+ * "possible" (src/fdr/fdr.c:247-327). */
+template <int KIND, int STRIDE>
+__device__ __forceinline__ void laneFilter(const u32 (&w)[5], const u8 *tab, u32 laneOff,
+                                           u32 indexMask, u32 (&a)[2][6]) {
+#pragma unroll
+    for (int o = 0; o < 2; o++) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            a[o][i] = 0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += STRIDE) {
+        const int k = j >> 2, r = j & 3;
+        if (KIND == FK_BYTE32) {
+            const u32 idx = __byte_perm(w[k], 0, 0x4440 + r);
+            const u32 e = *reinterpret_cast<const u32 *>(tab + idx * 128 + laneOff);
+            orShift32(a[0], k, r, e);
+        } else if (KIND == FK_BYTE64) {
+            const u32 idx = __byte_perm(w[k], 0, 0x4440 + r);
+            const uint2 e = *reinterpret_cast<const uint2 *>(tab + idx * 128 + laneOff);
+            orShift32(a[0], k, r, e.x);
+            orShift32(a[1], k, r, e.y);
+        } else {
+            /* byte offset of entry (h & indexMask), h = the two bytes at j */
+            constexpr int SH = KIND == FK_HASH32 ? 2 : 3;
+            u32 off;
+            if (r == 0) {
+                off = w[k] << SH;
+            } else if (r == 3) {
+                off = __funnelshift_r(w[k], w[k + 1], 24 - SH);
+            } else {
+                off = w[k] >> (8 * r - SH);
+            }
+            off &= indexMask << SH;
+            if (KIND == FK_HASH32) {
+                const u32 e = *reinterpret_cast<const u32 *>(tab + off);
+                orShift32(a[0], k, r, e);
+            } else {
+                const uint2 e = *reinterpret_cast<const uint2 *>(tab + off);
+                if (r == 0) {
+                    a[0][k] |= e.x;
+                    a[0][k + 1] |= e.y;
+                } else {
+                    a[0][k] |= e.x << (8 * r);
+                    a[0][k + 1] |= __funnelshift_l(e.x, e.y, 8 * r);
+                    a[0][k + 2] |= e.y >> (32 - 8 * r);
+                }
+            }
+        }
+    }
+}
+
+/* ---- the scan kernel -------------------------------------------------------- */
+
+__host__ __device__ inline u32 tableSmemBytes(int kind, u32 tableBytes) {
+    if (kind == FK_BYTE32 || kind == FK_BYTE64) {
+        return 256 * 128; /* 256 entries, replicated across the 32 banks */
+    }
+    return (tableBytes + 127u) & ~127u;
+}
+
+template <int KIND, int STRIDE>
+__global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
+    extern __shared__ __align__(128) u8 smem[];
+    typedef Kind<KIND> K;
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5;
+    const u32 nwarps = blockDim.x >> 5;
+    const u32 stageBytes = p.tileBytes + 32;
+    const u32 tabBytes = tableSmemBytes(KIND, p.tableBytes);
+
+    u8 *stages = smem + tabBytes + (size_t)warp * p.nstages * stageBytes;
+    u64 *bars = reinterpret_cast<u64 *>(smem + tabBytes + (size_t)nwarps * p.nstages * stageBytes) +
+                warp * p.nstages;
+
+    /* pin the first-stage table in shared memory */
+    if (KIND == FK_BYTE32) {
+        const u32 *g = reinterpret_cast<const u32 *>(p.table);
+        u32 *s = reinterpret_cast<u32 *>(smem);
+        for (u32 i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+            s[i] = __ldg(g + (i >> 5));
+        }
+    } else if (KIND == FK_BYTE64) {
+        const uint2 *g = reinterpret_cast<const uint2 *>(p.table);
+        uint2 *s = reinterpret_cast<uint2 *>(smem);
+        for (u32 i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+            s[i] = __ldg(g + (i >> 4));
+        }
+    } else {
+        const uint4 *g = reinterpret_cast<const uint4 *>(p.table);
+        uint4 *s = reinterpret_cast<uint4 *>(smem);
+        for (u32 i = threadIdx.x; i < p.tableBytes / 16; i += blockDim.x) {
+            s[i] = __ldg(g + i);
+        }
+    }
+    if (lane == 0) {
+        for (u32 s = 0; s < p.nstages; s++) {
+            mbarInit(&bars[s], 1);
+        }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const u8 *tab = smem;
+    const u32 laneOff = KIND == FK_BYTE64 ? (lane & 15) * 8 : lane * 4;
+
+    /* this warp's contiguous run of tiles */
+    const u32 gwarp = blockIdx.x * nwarps + warp;
+    const u32 totalWarps = gridDim.x * nwarps;
+    const u32 q = p.ntiles / totalWarps, rem = p.ntiles % totalWarps;
+    const u32 myCount = q + (gwarp < rem ? 1u : 0u);
+    const u32 myFirst = p.tileFirst + gwarp * q + min(gwarp, rem);
+    const u32 stepsPerTile = p.tileBytes >> 9;
+
+    auto issue = [&](u32 t, u32 s) { /* lane 0: TMA bulk copy of tile t -> stage s */
+        const u64 base = (u64)t * p.tileBytes;
+        u8 *dst = stages + (size_t)s * stageBytes;
+        const u64 readEnd = p.readableEnd;
+        u64 from = base - 16;
+        if (t == 0) { /* nothing before the corpus: stage bytes [0,16) stay unset */
+            from = 0;
+            dst += 16;
+        }
+        u64 to = base + p.tileBytes + 16;
+        if (to > readEnd) {
+            to = readEnd;
+        }
+        const u32 bytes = (u32)(to - from);
+        mbarExpectTx(&bars[s], bytes);
+        tmaLoad1d(dst, p.corpus + from, bytes, &bars[s]);
+    };
+
+    if (lane == 0) {
+        for (u32 i = 0; i < p.nstages && i < myCount; i++) {
+            issue(myFirst + i, i);
+        }
+    }
+
+    u32 carry[2][2] = {{0, 0}, {0, 0}}; /* lane 31's overflow of the previous step */
+    u32 ncand = 0, nconf = 0;
+    u32 s = 0, parity = 0;
+    for (u32 i = 0; i < myCount; i++) {
+        const u32 t = myFirst + i;
+        const u64 tileBase = (u64)t * p.tileBytes;
+        const u8 *st = stages + (size_t)s * stageBytes; /* st[16 + x] = corpus[tileBase + x] */
+        mbarWait(&bars[s], parity);
+
+        if (i == 0 && t != 0) {
+            /* state entering this run: every lane evaluates the 16 bytes
+             * before the tile as if it were "lane -1" */
+            const uint4 v = *reinterpret_cast<const uint4 *>(st);
+            const u32 w[5] = {v.x, v.y, v.z, v.w, *reinterpret_cast<const u32 *>(st + 16)};
+            u32 a[2][6];
+            laneFilter<KIND, STRIDE>(w, tab, laneOff, p.indexMask, a);
+#pragma unroll
+            for (int o = 0; o < K::NOCT; o++) {
+#pragma unroll
+                for (int x = 0; x < K::SPILL; x++) {
+                    carry[o][x] = a[o][4 + x];
+                }
+            }
+        }
+
+        u32 nsteps = stepsPerTile;
+        if (tileBase + p.tileBytes > p.corpusBytes) {
+            nsteps = (u32)((p.corpusBytes - tileBase + 511) >> 9);
+        }
+        for (u32 step = 0; step < nsteps; step++) {
+            const u8 *sp = st + 16 + step * 512 + lane * 16;
+            const uint4 v = *reinterpret_cast<const uint4 *>(sp);
+            u32 w[5] = {v.x, v.y, v.z, v.w, 0};
+            if (K::HASH) {
+                w[4] = __shfl_down_sync(0xffffffffu, v.x, 1);
+                if (lane == 31) {
+                    w[4] = *reinterpret_cast<const u32 *>(sp + 16);
+                }
+            }
+            u32 a[2][6];
+            laneFilter<KIND, STRIDE>(w, tab, laneOff, p.indexMask, a);
+            u32 c[2][4];
+            u32 any = 0;
+#pragma unroll
+            for (int o = 0; o < K::NOCT; o++) {
+#pragma unroll
+                for (int x = 0; x < K::SPILL; x++) {
+                    u32 in = __shfl_up_sync(0xffffffffu, a[o][4 + x], 1);
+                    const u32 last = __shfl_sync(0xffffffffu, a[o][4 + x], 31);
+                    if (lane == 0) {
+                        in = carry[o][x];
+                    }
+                    carry[o][x] = last;
+                    a[o][x] |= in;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    c[o][k] = ~a[o][k];
+                    any |= c[o][k];
+                }
+            }
+            if (__any_sync(0xffffffffu, any != 0)) {
+                if (any) {
+                    const u64 g0 = tileBase + step * 512 + lane * 16;
+                    const u8 *b0 = sp; /* stage address of position g0 */
+                    u32 cc[K::NOCT * 4]; /* rare path only: lives in local memory */
+#pragma unroll
+                    for (int oo = 0; oo < K::NOCT; oo++) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; kk++) {
+                            cc[oo * 4 + kk] = c[oo][kk];
+                        }
+                    }
+#pragma unroll 1
+                    for (int ok = 0; ok < K::NOCT * 4; ok++) {
+                        const int o = ok >> 2, k = ok & 3;
+                        u32 bits = cc[ok];
+                        while (bits) {
+                            const u32 bit = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            const u32 x = 4 * k + (bit >> 3);
+                            const u32 bucket = (bit & 7) + 8 * o;
+                            ncand++;
+                            /* bytes [g-7, g] from the stage (16 bytes of history
+                             * precede every tile) */
+                            u64 confVal = 0;
+#pragma unroll
+                            for (int z = 0; z < 8; z++) {
+                                confVal |= (u64)b0[(int)x - 7 + z] << (8 * z);
+                            }
+                            if (p.confirmKind == CK_NOODLE) {
+                                if (bucket == 0) {
+                                    confirmNoodle(p, g0 + x, confVal, &nconf);
+                                }
+                            } else {
+                                confirmFdr(p, bucket, g0 + x, confVal, &nconf);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        __syncwarp();
+        if (lane == 0 && i + p.nstages < myCount) {
+            issue(t + p.nstages, s); /* refill the stage just drained */
+        }
+        if (++s == p.nstages) {
+            s = 0;
+            parity ^= 1;
+        }
+    }
+    if (ncand) {
+        atomicAdd(p.counters + CTR_CANDIDATES, ncand);
+    }
+    if (nconf) {
+        atomicAdd(p.counters + CTR_CONFIRMED, nconf);
+    }
+}
+
+template <int KIND, int STRIDE>
+cudaError_t launchOne(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(scanKernel<KIND, STRIDE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)cfg.smemBytes);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    scanKernel<KIND, STRIDE><<<cfg.grid, cfg.warps * 32, cfg.smemBytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+size_t scanSmemBytes(int kind, u32 tableBytes, int warps, u32 nstages, u32 tileBytes) {
+    return tableSmemBytes(kind, tableBytes) + (size_t)warps * nstages * (tileBytes + 32) +
+           (size_t)warps * nstages * 8;
+}
+
+cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    switch (cfg.kind) {
+    case FK_BYTE32:
+        return launchOne<FK_BYTE32, 1>(cfg, p, stream);
+    case FK_BYTE64:
+        return launchOne<FK_BYTE64, 1>(cfg, p, stream);
+    case FK_HASH32:
+        if (cfg.stride == 1) return launchOne<FK_HASH32, 1>(cfg, p, stream);
+        if (cfg.stride == 2) return launchOne<FK_HASH32, 2>(cfg, p, stream);
+        if (cfg.stride == 4) return launchOne<FK_HASH32, 4>(cfg, p, stream);
+        break;
+    case FK_HASH64:
+        if (cfg.stride == 1) return launchOne<FK_HASH64, 1>(cfg, p, stream);
+        if (cfg.stride == 2) return launchOne<FK_HASH64, 2>(cfg, p, stream);
+        if (cfg.stride == 4) return launchOne<FK_HASH64, 4>(cfg, p, stream);
+        break;
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace hsb

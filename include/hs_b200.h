@@ -245,6 +245,16 @@ hs_error_t hs_b200_scan_corpus_async(const hs_database_t *db,
 hs_error_t hs_b200_scan_corpus_finish(hs_scratch_t *scratch,
                                       unsigned long long *nrecords,
                                       const void **d_records);
+/* Copy up to `cap` raw records of the last finished scan into another device
+ * buffer (e.g. a torch tensor that is then all-gathered over NCCL). */
+hs_error_t hs_b200_copy_records(hs_scratch_t *scratch, void *d_dst, size_t cap);
+/* Apply the host-side report rules to `n` raw records held in host memory
+ * (in place; e.g. the concatenation of all ranks' records after the
+ * all-gather): sort by (block, to, id), one record per (block, id, to),
+ * HS_FLAG_SINGLEMATCH reports keep their first match per block. */
+hs_error_t hs_b200_postprocess_matches(const hs_database_t *db, hs_scratch_t *scratch,
+                                       hs_b200_match_t *recs, size_t n,
+                                       unsigned long long *nout);
 /* Copy the records of the last finished scan to the host, apply the
  * host-side report rules (dedupe per (id,to); HS_FLAG_SINGLEMATCH keeps the
  * first match per id and block), sort by (block, to, id).  `out` may be NULL
@@ -273,6 +283,12 @@ hs_error_t hs_b200_db_info(const hs_database_t *db, hs_b200_db_info_t *info);
  * "allow_teddy", "allow_fat_teddy", "allow_flood", "allow_noodle"; key "reset"
  * restores the defaults. */
 hs_error_t hs_b200_set_build_option(const char *key, int value);
+
+/* Runtime tunables (process-wide; also HSB200_* environment variables):
+ * "warps" per CTA, "tile_bytes", "stages" (TMA ring depth per warp),
+ * "wide_fdr" (1: use all 8 FDR suffix slots), "chunk_mb" (host->device
+ * pipeline granularity), "initial_ring" (match records). */
+hs_error_t hs_b200_set_runtime_option(const char *key, int value);
 
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches"), and elapsed device time of the last scan kernel in ms

@@ -1,0 +1,42 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def hs():
+    """The product C-ABI library through its ctypes binding (built on demand)."""
+    from hyperscan_b200 import build, capi
+    build.build_product()
+    capi.lib()
+    return capi
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference runtime (oracle/_ref); skipped if not built."""
+    import oracle.ref as r
+    if not r.available():
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    r.lib()
+    return r
+
+
+@pytest.fixture(autouse=True)
+def _reset_build_options():
+    yield
+    try:
+        from hyperscan_b200 import capi
+        if capi._lib is not None:
+            capi.set_build_option("reset", 0)
+    except Exception:
+        pass

@@ -1,0 +1,134 @@
+"""Parity of the B200 scan path (through the C ABI) against the unmodified
+reference runtime scanning the SAME database, and against the definition-level
+brute-force oracle.  Bit-exact on the sorted (block, to, id) multiset."""
+import numpy as np
+import pytest
+
+from hyperscan_b200 import synth
+import oracle.brute as brute
+
+pytestmark = pytest.mark.gpu
+
+F_CASELESS, F_SINGLE = 1, 8
+
+
+def _sorted(recs):
+    return np.sort(np.asarray(recs), order=["block", "to", "id"])
+
+
+def _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=True):
+    db = hs.compile_lit_multi(lits, flags, ids)
+    scratch = hs.Scratch(db)
+    want = ref.scan_sorted(db.ptr, data, off, ln)
+    if use_brute:
+        b = brute.scan_blocks(lits, flags, ids, data, off, ln)
+        assert np.array_equal(want, b), "reference runtime disagrees with the definition"
+    got = _sorted(hs.scan_blocks(db, data, off, ln, scratch))
+    assert got.size == want.size, (got.size, want.size)
+    assert np.array_equal(got, want)
+    corpus = hs.Corpus.upload(data, off, ln)
+    got2 = _sorted(hs.scan_corpus(db, corpus, scratch))
+    assert np.array_equal(got2, want)
+    corpus.free()
+    scratch.free()
+    return db, want
+
+
+# engine id 0 = FDR; 11..18 = Teddy (8 buckets); forced through the build
+# option the way unit/internal/fdr.cpp:114-137 forces engines with hints
+@pytest.mark.parametrize("nlits,engine", [(1, -1), (5, -1), (30, -1), (48, 15), (5, 0), (200, -1),
+                                          (1000, -1), (3000, -1)])
+def test_engines_random_blocks(hs, ref, nlits, engine):
+    lits, flags, ids = synth.literal_set(nlits, min_len=2 if nlits < 40 else 4, max_len=12, seed=nlits,
+                                         caseless_frac=0.2, alphabet=b"abcdefgh")
+    if engine >= 0:
+        hs.set_build_option("force_engine", engine)
+    data, off, ln = synth.ragged_corpus([0, 1, 3, 7, 15, 16, 17, 31, 64, 100, 511, 512, 513, 1024, 2047, 2048,
+                                         2049, 4096, 10000, 65536 + 5], lits, seed=3,
+                                        alphabet=b"abcdefghABCDxy")
+    _check_all(hs, ref, lits, flags, ids, data, off, ln)
+
+
+def test_hs_scan_single_block_and_termination(hs, ref):
+    lits = [b"mnopqr"]
+    db = hs.compile_lit_multi(lits, [0], [7])
+    scratch = hs.Scratch(db)
+    data = b"mnopqrabcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ12345678901234567890mnopqr"
+    rc, out = hs.scan(db, data, scratch)
+    assert rc == hs.HS_SUCCESS
+    # unit/internal/fdr.cpp:167-190 (ends 5, 23, 83) -> to = end + 1
+    assert out == [(7, 6), (7, 24), (7, 84)]
+    rc, out = hs.scan(db, data, scratch, stop_after=2)
+    assert rc == hs.HS_SCAN_TERMINATED and out == [(7, 6), (7, 24)]
+    rc, out = hs.scan(db, b"", scratch)
+    assert rc == hs.HS_SUCCESS and out == []
+
+
+def test_singlematch_and_shared_ids(hs, ref):
+    lits = [b"abc", b"bcd", b"abcd", b"xyzw", b"ABC"]
+    flags = [F_SINGLE, 0, 0, F_SINGLE | F_CASELESS, 0]
+    ids = [1, 2, 2, 3, 1]
+    # id 1 mixes singlematch and not -> compile error like the reference
+    with pytest.raises(hs.HsError):
+        hs.compile_lit_multi(lits, flags, ids)
+    flags[4] = F_SINGLE
+    data, off, ln = synth.ragged_corpus([300, 5000, 64], lits, plant_per_kb=30, seed=5,
+                                        alphabet=b"abcdxyzwXYZW")
+    _check_all(hs, ref, lits, flags, ids, data, off, ln)
+
+
+def test_long_literals_med_lit_check(hs, ref):
+    lits = [b"abcdefghijkl", b"zzabcdefghijkl", b"hijkl", b"ABCDEFGHIJKLMNOPQRSTUVWX"]
+    flags = [0, F_CASELESS, 0, F_CASELESS]
+    ids = [10, 11, 12, 13]
+    data, off, ln = synth.ragged_corpus([2000, 3000, 30], lits, plant_per_kb=20, seed=9,
+                                        alphabet=b"abcdefghijklz")
+    _check_all(hs, ref, lits, flags, ids, data, off, ln)
+
+
+def test_flood_and_ring_growth(hs, ref):
+    # every byte matches (unit/internal/fdr_flood.cpp); the initial record ring
+    # is made tiny so the overflow -> grow -> rescan path runs
+    hs.set_runtime_option("initial_ring", 64)
+    try:
+        lits = [b"a", b"aa", b"aaaa", b"aaaaaaaa", b"aaaaaaaaaaaa"]
+        data = np.full(20000, ord("a"), dtype=np.uint8)
+        off = np.array([0, 10000], dtype=np.uint64)
+        ln = np.array([9999, 10000], dtype=np.uint32)
+        _check_all(hs, ref, lits, [0, 0, F_CASELESS, 0, 0], [1, 2, 3, 4, 5], data, off, ln)
+    finally:
+        hs.set_runtime_option("initial_ring", 1 << 20)
+
+
+def test_block_boundaries_do_not_leak(hs, ref):
+    # literals straddling two adjacent blocks must not match; blocks are packed
+    # back to back (16-byte aligned) so the halo holds the neighbour's bytes
+    lits = [b"abcdefgh", b"efgh", b"h"]
+    data = np.frombuffer(b"xxxxxxxxxxxxabcdefghxxxxxxxxxxxxxxxx" * 4, dtype=np.uint8).copy()
+    off = np.array([0, 16, 32, 48], dtype=np.uint64)
+    ln = np.array([16, 16, 16, 5], dtype=np.uint32)
+    _check_all(hs, ref, lits, [0, 0, 0], [1, 2, 3], data, off, ln)
+
+
+@pytest.mark.parametrize("tile,warps,stages", [(512, 1, 2), (1024, 4, 2), (4096, 8, 4)])
+def test_tile_geometry_invariance(hs, ref, tile, warps, stages):
+    lits, flags, ids = synth.literal_set(300, seed=4, alphabet=b"abcdefgh")
+    data, off, ln, _ = synth.block_corpus(257, 1000, lits, plant_per_kb=2.0, seed=8)
+    try:
+        hs.set_runtime_option("tile_bytes", tile)
+        hs.set_runtime_option("warps", warps)
+        hs.set_runtime_option("stages", stages)
+        _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
+    finally:
+        hs.set_runtime_option("tile_bytes", 2048)
+        hs.set_runtime_option("warps", 16)
+        hs.set_runtime_option("stages", 3)
+
+
+def test_config2_shape_sample(hs, ref):
+    # BASELINE config 2 shape at a size the CPU oracles finish in seconds
+    lits, flags, ids = synth.literal_set(1000)
+    data, off, ln, planted = synth.block_corpus(16384, 1024, lits, plant_per_kb=0.05)
+    db, want = _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
+    assert db.info().engine_id == 0 and db.info().fdr_stride == 2
+    assert want.size >= len(planted) * 0.9
