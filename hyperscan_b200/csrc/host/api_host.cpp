@@ -785,3 +785,48 @@ extern "C" hs_error_t hs_b200_set_build_option(const char *key, int value) {
     }
     return HS_INVALID;
 }
+
+/* Table-builder entry point at the boundary the reference's unit tests use
+ * (hwlmBuild(), unit/internal/fdr.cpp:140-165): builds a raw HWLM table for
+ * literals given as (bytes, nocase, noruns, id).  engine: -1 auto, 0 FDR,
+ * 3..18 Teddy id.  Returns the table size, or -1 if it cannot be built / does
+ * not fit `cap`. */
+extern "C" long hs_b200_test_build_hwlm(const char *const *lits, const size_t *lens,
+                                        const unsigned *nocase, const unsigned *noruns,
+                                        const unsigned *ids, unsigned n, int engine, void *out,
+                                        size_t cap) {
+    try {
+        std::vector<HwlmLit> v;
+        for (unsigned i = 0; i < n; i++) {
+            HwlmLit l;
+            l.s.assign(lits[i], lens[i]);
+            l.nocase = nocase[i] != 0;
+            if (l.nocase) {
+                for (char &c : l.s) {
+                    c = (char)asciiUpper((u8)c);
+                }
+            }
+            l.noruns = noruns[i] != 0;
+            l.id = ids[i];
+            l.groups = 1;
+            v.push_back(l);
+        }
+        HwlmBuildOpts o;
+        o.forceEngine = engine;
+        if (engine == 0) {
+            o.forceDomain = 9; /* the unit-test hint: src/fdr/fdr_compile.cpp:862-866 */
+            o.forceStride = 1;
+        }
+        if (engine >= 3 && engine <= 10) {
+            o.allowFatTeddy = true;
+        }
+        std::vector<u8> t = buildHwlm(v, o, nullptr);
+        if (t.size() > cap) {
+            return -1;
+        }
+        memcpy(out, t.data(), t.size());
+        return (long)t.size();
+    } catch (const std::exception &) {
+        return -1;
+    }
+}

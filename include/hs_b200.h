@@ -284,6 +284,15 @@ hs_error_t hs_b200_db_info(const hs_database_t *db, hs_b200_db_info_t *info);
  * restores the defaults. */
 hs_error_t hs_b200_set_build_option(const char *key, int value);
 
+/* Table builder at the boundary the reference's unit tests use (hwlmBuild(),
+ * unit/internal/fdr.cpp:140-165): raw HWLM table for literals (bytes, nocase,
+ * noruns, id); engine -1 auto, 0 FDR (domain 9, stride 1 like the reference's
+ * unit-test hint), 3..18 Teddy id.  Returns the size or -1. */
+long hs_b200_test_build_hwlm(const char *const *lits, const size_t *lens,
+                             const unsigned *nocase, const unsigned *noruns,
+                             const unsigned *ids, unsigned n, int engine, void *out,
+                             size_t cap);
+
 /* Runtime tunables (process-wide; also HSB200_* environment variables):
  * "warps" per CTA, "tile_bytes", "stages" (TMA ring depth per warp),
  * "wide_fdr" (1: use all 8 FDR suffix slots), "chunk_mb" (host->device
