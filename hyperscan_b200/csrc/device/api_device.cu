@@ -705,6 +705,36 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
     return HS_INVALID;
 }
 
+/* Acceleration primitives on a host buffer (src/nfa/accel.c:35 run_accel):
+ * first position whose byte (pair) is in the class, or len. */
+hs_error_t hs_b200_accel_find(unsigned int type, const unsigned char *params,
+                              const unsigned char *buf, size_t len, unsigned long long *pos) {
+    if (!params || (!buf && len) || !pos) {
+        return HS_INVALID;
+    }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        return HS_ARCH_ERROR;
+    }
+    u8 *d = nullptr;
+    u64 *d_res = nullptr;
+    CUDA_TRY(cudaMalloc(&d, HSB_ROUNDUP(len, 16) + 64));
+    cudaError_t e = cudaMalloc(&d_res, 8);
+    if (e == cudaSuccess) e = cudaMemset(d, 0, HSB_ROUNDUP(len, 16) + 64);
+    if (e == cudaSuccess && len) e = cudaMemcpy(d, buf, len, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launchAccelFind((int)type, params, d, len, d_res, 0);
+    if (e == cudaSuccess) g_launches++;
+    unsigned long long r = len;
+    if (e == cudaSuccess) e = cudaMemcpy(&r, d_res, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaFree(d_res);
+    if (e != cudaSuccess) {
+        return e == cudaErrorInvalidValue ? HS_INVALID : HS_UNKNOWN_ERROR;
+    }
+    *pos = r;
+    return HS_SUCCESS;
+}
+
 /* ---- scratch ---------------------------------------------------------------- */
 
 static hs_error_t newScratch(hs_scratch **out) {

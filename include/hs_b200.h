@@ -284,6 +284,17 @@ hs_error_t hs_b200_db_info(const hs_database_t *db, hs_b200_db_info_t *info);
  * restores the defaults. */
 hs_error_t hs_b200_set_build_option(const char *key, int value);
 
+/* Acceleration primitives (src/nfa/accel.h:46-121; shuftiExec src/nfa/shufti.c:150,
+ * truffleExec src/nfa/truffle.c:118, vermicelliExec / vermicelliDoubleExec
+ * src/nfa/vermicelli.h:43,172) on the device: *pos = first position in
+ * [0, len) whose byte (pair) is in the class, or len.  type = the reference's
+ * AccelType: 1 VERM, 2 VERM_NOCASE, 3 DVERM, 4 DVERM_NOCASE (params = c1[,c2],
+ * upper case for NOCASE), 13 SHUFTI (params = lo[16], hi[16]), 15 TRUFFLE
+ * (params = mask1[16] (bytes < 0x80), mask2[16]). */
+hs_error_t hs_b200_accel_find(unsigned int type, const unsigned char *params,
+                              const unsigned char *buf, size_t len,
+                              unsigned long long *pos);
+
 /* Table builder at the boundary the reference's unit tests use (hwlmBuild(),
  * unit/internal/fdr.cpp:140-165): raw HWLM table for literals (bytes, nocase,
  * noruns, id); engine -1 auto, 0 FDR (domain 9, stride 1 like the reference's
