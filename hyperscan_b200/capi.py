@@ -120,6 +120,7 @@ def lib():
         L.hs_b200_db_info.argtypes = [vp, C.POINTER(DbInfo)]
         L.hs_b200_set_build_option.argtypes = [cp, C.c_int]
         L.hs_b200_set_runtime_option.argtypes = [cp, C.c_int]
+        L.hs_b200_last_counters.argtypes = [vp, C.POINTER(C.c_uint * 8)]
         L.hs_b200_launch_count.restype = C.c_ulonglong
         L.hs_b200_last_kernel_ms.argtypes = [vp]
         L.hs_b200_last_kernel_ms.restype = C.c_float
@@ -260,6 +261,12 @@ class Scratch:
         n = C.c_size_t()
         _check(lib().hs_scratch_size(self.ptr, C.byref(n)))
         return n.value
+
+    def counters(self):
+        """[records, error, candidates, confirmed, prefilter_pass, ...] of the last scan."""
+        out = (C.c_uint * 8)()
+        _check(lib().hs_b200_last_counters(self.ptr, C.byref(out)))
+        return list(out)
 
     def last_kernel_ms(self):
         return float(lib().hs_b200_last_kernel_ms(self.ptr))

@@ -45,6 +45,8 @@ struct RuntimeOpts {
     int tileBytes = 2048;
     int stages = 3;
     int wideFdr = 0;         /* 1: use all 8 FDR slots (u64 entries) when they fit */
+    int stride = 0;          /* first-stage sampling stride override (0 = as compiled) */
+    int prefilter = 1;       /* shared-memory bitmap in front of the hash confirm */
     int chunkMB = 32;        /* host->device pipeline granularity */
     int initialRing = 1 << 20;
 };
@@ -59,7 +61,8 @@ void initOpts() {
     struct { const char *env; int *v; } e[] = {
         {"HSB200_WARPS", &g_opts.warps},       {"HSB200_TILE", &g_opts.tileBytes},
         {"HSB200_STAGES", &g_opts.stages},     {"HSB200_WIDE_FDR", &g_opts.wideFdr},
-        {"HSB200_CHUNK_MB", &g_opts.chunkMB},  {"HSB200_RING", &g_opts.initialRing}};
+        {"HSB200_CHUNK_MB", &g_opts.chunkMB},  {"HSB200_RING", &g_opts.initialRing},
+        {"HSB200_STRIDE", &g_opts.stride},     {"HSB200_PREFILTER", &g_opts.prefilter}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -76,6 +79,8 @@ struct DevImage {
     u8 *d_bc = nullptr;
     u8 *d_table = nullptr;
     u32 tableBytes = 0;
+    u8 *d_bitmap = nullptr;
+    u32 bitmapBytes = 0, bitmapShift = 0, keyBytes = 0;
     int kind = FK_BYTE32;
     int stride = 1;
     u32 indexMask = 0;
@@ -125,8 +130,13 @@ void collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
 
 /* Walk the hash-confirm structures to enumerate literal programs
  * (src/fdr/fdr_confirm.h:36-94). */
+struct LitTail {
+    u64 v, msk;
+    u32 size;
+};
+
 void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
-                 std::unordered_set<u32> *ex) {
+                 std::unordered_set<u32> *ex, std::vector<LitTail> *tails) {
     const u8 *confBase = bc + confOff;
     for (u32 b = 0; b < nBuckets; b++) {
         u32 cf;
@@ -149,6 +159,7 @@ void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
                 LitInfo x;
                 memcpy(&x, li, sizeof(x));
                 collectProgramReports(bc, bcLen, x.id, ex);
+                tails->push_back({x.v, x.msk, x.size});
                 if (!x.next) {
                     break;
                 }
@@ -166,12 +177,59 @@ void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
         }                                                                                  \
     } while (0)
 
+/* Second-stage prefilter: a bitmap over a hash of each literal's last
+ * keyBytes bytes (don't-care bits of LitInfo.msk -- caseless letters --
+ * enumerated).  A clear bit proves no literal ends at a candidate position, so
+ * the hash confirm in HBM/L2 is only reached by ~1% of the first stage's false
+ * positives.  Returns an empty vector when the set cannot be keyed usefully. */
+std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u32 *shift) {
+    std::vector<u8> bm;
+    if (tails.empty()) {
+        return bm;
+    }
+    u32 m = 4;
+    for (const LitTail &t : tails) {
+        m = std::min(m, t.size);
+    }
+    if (m < 2) {
+        return bm; /* single-byte literals: the first stage is already exact */
+    }
+    std::vector<u32> keys;
+    for (const LitTail &t : tails) {
+        const u32 v = (u32)(t.v >> 32) >> (8 * (4 - m));
+        const u32 care = (u32)(t.msk >> 32) >> (8 * (4 - m));
+        const u32 full = m == 4 ? 0xffffffffu : (1u << (8 * m)) - 1;
+        const u32 dc = ~care & full;
+        if (__builtin_popcount(dc) > 10) {
+            return std::vector<u8>(); /* too loose to enumerate */
+        }
+        u32 sub = 0;
+        do {
+            keys.push_back((v & care) | sub);
+            sub = (sub - dc) & dc;
+        } while (sub);
+    }
+    u32 lg = 13; /* 8 Kbit .. 512 Kbit (64 KB), ~256 bits per key when possible */
+    while (lg < 19 && (1ull << lg) < (u64)keys.size() * 256) {
+        lg++;
+    }
+    bm.assign((size_t)1 << (lg - 3), 0);
+    for (u32 k : keys) {
+        const u32 h = (k * 0x9E3779B1u) >> (32 - lg);
+        bm[h >> 3] |= (u8)(1u << (h & 7));
+    }
+    *keyBytes = m;
+    *shift = 32 - lg;
+    return bm;
+}
+
 void freeImage(DevImage *im) {
     if (!im) {
         return;
     }
     cudaFree(im->d_bc);
     cudaFree(im->d_table);
+    cudaFree(im->d_bitmap);
     delete im;
 }
 
@@ -199,6 +257,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     const HWLM *hw = (const HWLM *)(bc + r->fmatcherOffset);
     const u32 engOff = r->fmatcherOffset + HWLM_ENGINE_OFFSET;
     std::vector<u8> table;
+    std::vector<LitTail> tails;
     if (hw->type == HWLM_ENGINE_NOOD) {
         /* single literal: one bucket, slots = the last <= 4 bytes of msk/cmp
          * (first char in the low byte: src/hwlm/noodle_build.cpp:100-118) */
@@ -249,7 +308,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                     memcpy(&table[(size_t)i * 4], src + (size_t)i * 8, 4);
                 }
             }
-            walkConfirm(bc, h->length, im->confOff, 8, &im->exhaustible);
+            walkConfirm(bc, h->length, im->confOff, 8, &im->exhaustible, &tails);
         } else if (teddyIdValid(f.engineID)) {
             /* per-byte entry: slot m = lo_m[b & 15] | hi_m[b >> 4]
              * (src/fdr/teddy.c:918-969, teddy_compile.cpp:440-509) */
@@ -270,7 +329,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                     memcpy(&table[(b * oct + o) * 4], &e, 4);
                 }
             }
-            walkConfirm(bc, h->length, im->confOff, 8 * oct, &im->exhaustible);
+            walkConfirm(bc, h->length, im->confOff, 8 * oct, &im->exhaustible, &tails);
         } else {
             delete im;
             return HS_INVALID;
@@ -280,7 +339,18 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
         return HS_INVALID;
     }
     im->tableBytes = (u32)table.size();
+    std::vector<u8> bitmap;
+    if (g_opts.prefilter) {
+        bitmap = buildBitmap(tails, &im->keyBytes, &im->bitmapShift);
+    }
+    im->bitmapBytes = (u32)bitmap.size();
     cudaError_t e = cudaMalloc(&im->d_bc, HSB_ROUNDUP(h->length, 16));
+    if (e == cudaSuccess && !bitmap.empty()) {
+        e = cudaMalloc(&im->d_bitmap, bitmap.size());
+        if (e == cudaSuccess) {
+            e = cudaMemcpy(im->d_bitmap, bitmap.data(), bitmap.size(), cudaMemcpyHostToDevice);
+        }
+    }
     if (e == cudaSuccess) {
         e = cudaMalloc(&im->d_table, HSB_ROUNDUP(table.size(), 16));
     }
@@ -294,7 +364,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
         freeImage(im);
         return e == cudaErrorMemoryAllocation ? HS_NOMEM : HS_UNKNOWN_ERROR;
     }
-    im->deviceBytes = HSB_ROUNDUP(h->length, 16) + HSB_ROUNDUP(table.size(), 16);
+    im->deviceBytes = HSB_ROUNDUP(h->length, 16) + HSB_ROUNDUP(table.size(), 16) + bitmap.size();
     *out = im;
     return HS_SUCCESS;
 }
@@ -484,7 +554,7 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     u32 stages = (u32)std::max(2, std::min(8, g_opts.stages));
     /* shrink until the table + staging fit the opt-in shared memory */
     for (;;) {
-        const size_t need = scanSmemBytes(im->kind, im->tableBytes, warps, stages, tile);
+        const size_t need = scanSmemBytes(im->kind, im->tableBytes, im->bitmapBytes, warps, stages, tile);
         if (need <= (size_t)s->maxSmem) {
             pl->cfg.smemBytes = need;
             break;
@@ -505,6 +575,10 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     }
     pl->cfg.kind = im->kind;
     pl->cfg.stride = im->stride;
+    if ((g_opts.stride == 1 || g_opts.stride == 2 || g_opts.stride == 4) &&
+        (im->kind == FK_HASH32 || im->kind == FK_HASH64)) {
+        pl->cfg.stride = g_opts.stride; /* any sampling subset is a sound filter */
+    }
     pl->cfg.grid = s->smCount;
     pl->cfg.warps = warps;
     pl->tileBytes = tile;
@@ -528,6 +602,10 @@ void fillParams(const hs_scratch *s, const DevImage *im, const hs_b200_corpus *c
     p->table = im->d_table;
     p->tableBytes = im->tableBytes;
     p->indexMask = im->indexMask;
+    p->bitmap = im->d_bitmap;
+    p->bitmapBytes = im->bitmapBytes;
+    p->bitmapShift = im->bitmapShift;
+    p->keyBytes = im->keyBytes;
     p->confOff = im->confOff;
     p->engineOff = im->engineOff;
     p->confirmKind = im->confirmKind;
@@ -687,6 +765,17 @@ float hs_b200_last_kernel_ms(const hs_scratch_t *scratch) {
     return scratch ? scratch->lastMs : 0.0f;
 }
 
+/* Counters of the last finished scan: [0] raw records, [1] error, [2]
+ * first-stage candidates, [3] byte-confirmed literals, [4] candidates that
+ * passed the prefilter. */
+hs_error_t hs_b200_last_counters(const hs_scratch_t *scratch, unsigned int out[8]) {
+    if (!scratch || !out || scratch->pending) {
+        return HS_INVALID;
+    }
+    memcpy(out, scratch->h_counters, CTR_COUNT * sizeof(u32));
+    return HS_SUCCESS;
+}
+
 hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
     initOpts();
     if (!key) {
@@ -695,7 +784,8 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
     struct { const char *n; int *v; } k[] = {
         {"warps", &g_opts.warps},       {"tile_bytes", &g_opts.tileBytes},
         {"stages", &g_opts.stages},     {"wide_fdr", &g_opts.wideFdr},
-        {"chunk_mb", &g_opts.chunkMB},  {"initial_ring", &g_opts.initialRing}};
+        {"chunk_mb", &g_opts.chunkMB},  {"initial_ring", &g_opts.initialRing},
+        {"stride", &g_opts.stride},     {"prefilter", &g_opts.prefilter}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;

@@ -36,7 +36,8 @@ enum ConfirmKind {
     CK_NOODLE = 1, /* single literal: noodTable msk/cmp (src/hwlm/noodle_internal.h) */
 };
 
-enum { CTR_MATCHES = 0, CTR_ERROR = 1, CTR_CANDIDATES = 2, CTR_CONFIRMED = 3, CTR_COUNT = 8 };
+enum { CTR_MATCHES = 0, CTR_ERROR = 1, CTR_CANDIDATES = 2, CTR_CONFIRMED = 3,
+       CTR_PREFILTER_PASS = 4, CTR_COUNT = 8 };
 enum { ERR_BAD_OPCODE = 1, ERR_INTERNAL = 2 };
 
 struct ScanParams {
@@ -58,6 +59,10 @@ struct ScanParams {
     const u8 *table;       /* first-stage table in HBM (copied to smem) */
     u32 tableBytes;
     u32 indexMask;         /* FK_HASH*: FDR domainMask */
+    const u8 *bitmap;      /* second-stage prefilter (copied to smem), may be null */
+    u32 bitmapBytes;       /* power of two >= 16, or 0 = no prefilter */
+    u32 bitmapShift;       /* 32 - log2(bits) */
+    u32 keyBytes;          /* 1..4: literal tail bytes hashed into the bitmap */
     u32 confOff;           /* CK_FDR: offset of the confirm base in bc */
     u32 engineOff;         /* CK_NOODLE: offset of the noodTable in bc */
     u32 confirmKind;
@@ -77,7 +82,8 @@ struct LaunchCfg {
 };
 
 /* Dynamic shared memory the kernel needs. */
-size_t scanSmemBytes(int kind, u32 tableBytes, int warps, u32 nstages, u32 tileBytes);
+size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 nstages,
+                     u32 tileBytes);
 
 cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream);
 

@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
     const u32 warp = threadIdx.x >> 5;
     const u32 nwarps = blockDim.x >> 5;
     const u32 stageBytes = p.tileBytes + 32;
-    const u32 tabBytes = tableSmemBytes(KIND, p.tableBytes);
+    const u32 tabBytes = tableSmemBytes(KIND, p.tableBytes) + p.bitmapBytes;
 
     u8 *stages = smem + tabBytes + (size_t)warp * p.nstages * stageBytes;
     u64 *bars = reinterpret_cast<u64 *>(smem + tabBytes + (size_t)nwarps * p.nstages * stageBytes) +
@@ -492,6 +492,15 @@ __global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
         uint4 *s = reinterpret_cast<uint4 *>(smem);
         for (u32 i = threadIdx.x; i < p.tableBytes / 16; i += blockDim.x) {
             s[i] = __ldg(g + i);
+        }
+    }
+    /* second-stage prefilter: one bit per hash of a literal's last bytes */
+    const u32 *bitmap = reinterpret_cast<const u32 *>(smem + tableSmemBytes(KIND, p.tableBytes));
+    if (p.bitmapBytes) {
+        const uint4 *g = reinterpret_cast<const uint4 *>(p.bitmap);
+        uint4 *sdst = reinterpret_cast<uint4 *>(smem + tableSmemBytes(KIND, p.tableBytes));
+        for (u32 i = threadIdx.x; i < p.bitmapBytes / 16; i += blockDim.x) {
+            sdst[i] = __ldg(g + i);
         }
     }
     if (lane == 0) {
@@ -538,7 +547,7 @@ __global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
     }
 
     u32 carry[2][2] = {{0, 0}, {0, 0}}; /* lane 31's overflow of the previous step */
-    u32 ncand = 0, nconf = 0;
+    u32 ncand = 0, nconf = 0, npass = 0;
     u32 s = 0, parity = 0;
     for (u32 i = 0; i < myCount; i++) {
         const u32 t = myFirst + i;
@@ -601,7 +610,6 @@ __global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
             if (__any_sync(0xffffffffu, any != 0)) {
                 if (any) {
                     const u64 g0 = tileBase + step * 512 + lane * 16;
-                    const u8 *b0 = sp; /* stage address of position g0 */
                     u32 cc[K::NOCT * 4]; /* rare path only: lives in local memory */
 #pragma unroll
                     for (int oo = 0; oo < K::NOCT; oo++) {
@@ -611,28 +619,47 @@ __global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
                         }
                     }
 #pragma unroll 1
-                    for (int ok = 0; ok < K::NOCT * 4; ok++) {
-                        const int o = ok >> 2, k = ok & 3;
-                        u32 bits = cc[ok];
-                        while (bits) {
-                            const u32 bit = __ffs(bits) - 1;
-                            bits &= bits - 1;
-                            const u32 x = 4 * k + (bit >> 3);
-                            const u32 bucket = (bit & 7) + 8 * o;
+                    for (int k = 0; k < 4; k++) {
+                        const u32 m0 = cc[k], m1 = K::NOCT == 2 ? cc[K::NOCT * 4 - 4 + k] : 0u;
+                        u32 nz = m0 | m1;
+                        while (nz) {
+                            const u32 q = (__ffs(nz) - 1) >> 3; /* byte lane with a candidate */
+                            nz &= ~(0xffu << (8 * q));
+                            u32 buckets = (m0 >> (8 * q)) & 0xff;
+                            if (K::NOCT == 2) {
+                                buckets |= ((m1 >> (8 * q)) & 0xff) << 8;
+                            }
+                            const u32 x = 4 * k + q;
                             ncand++;
                             /* bytes [g-7, g] from the stage (16 bytes of history
-                             * precede every tile) */
-                            u64 confVal = 0;
-#pragma unroll
-                            for (int z = 0; z < 8; z++) {
-                                confVal |= (u64)b0[(int)x - 7 + z] << (8 * z);
+                             * precede every tile): three aligned words + funnel */
+                            const u8 *a = sp + (int)x - 7;
+                            const u32 mis = (u32)(smemAddr(a) & 3);
+                            const u32 *aw = reinterpret_cast<const u32 *>(a - mis);
+                            const u32 w0 = aw[0], w1 = aw[1], w2 = aw[2];
+                            const u32 lo = __funnelshift_r(w0, w1, 8 * mis);
+                            const u32 hi = __funnelshift_r(w1, w2, 8 * mis);
+                            if (p.bitmapBytes) {
+                                /* last keyBytes bytes -> bit; a clear bit proves that
+                                 * no literal of any bucket ends here */
+                                const u32 key = hi >> (8 * (4 - p.keyBytes));
+                                const u32 hsh = (key * 0x9E3779B1u) >> p.bitmapShift;
+                                if (!((bitmap[hsh >> 5] >> (hsh & 31)) & 1)) {
+                                    continue;
+                                }
                             }
+                            npass++;
+                            const u64 confVal = ((u64)hi << 32) | lo;
                             if (p.confirmKind == CK_NOODLE) {
-                                if (bucket == 0) {
+                                if (buckets & 1) {
                                     confirmNoodle(p, g0 + x, confVal, &nconf);
                                 }
                             } else {
-                                confirmFdr(p, bucket, g0 + x, confVal, &nconf);
+                                while (buckets) {
+                                    const u32 bucket = __ffs(buckets) - 1;
+                                    buckets &= buckets - 1;
+                                    confirmFdr(p, bucket, g0 + x, confVal, &nconf);
+                                }
                             }
                         }
                     }
@@ -655,6 +682,9 @@ __global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
     if (nconf) {
         atomicAdd(p.counters + CTR_CONFIRMED, nconf);
     }
+    if (npass) {
+        atomicAdd(p.counters + CTR_PREFILTER_PASS, npass);
+    }
 }
 
 template <int KIND, int STRIDE>
@@ -671,8 +701,9 @@ cudaError_t launchOne(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t st
 
 } // namespace
 
-size_t scanSmemBytes(int kind, u32 tableBytes, int warps, u32 nstages, u32 tileBytes) {
-    return tableSmemBytes(kind, tableBytes) + (size_t)warps * nstages * (tileBytes + 32) +
+size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 nstages,
+                     u32 tileBytes) {
+    return tableSmemBytes(kind, tableBytes) + bitmapBytes + (size_t)warps * nstages * (tileBytes + 32) +
            (size_t)warps * nstages * 8;
 }
 

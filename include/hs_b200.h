@@ -306,9 +306,17 @@ long hs_b200_test_build_hwlm(const char *const *lits, const size_t *lens,
 
 /* Runtime tunables (process-wide; also HSB200_* environment variables):
  * "warps" per CTA, "tile_bytes", "stages" (TMA ring depth per warp),
- * "wide_fdr" (1: use all 8 FDR suffix slots), "chunk_mb" (host->device
- * pipeline granularity), "initial_ring" (match records). */
+ * "wide_fdr" (1: use all 8 FDR suffix slots), "stride" (first-stage sampling
+ * stride override, 0 = as compiled), "prefilter" (shared-memory bitmap before
+ * the hash confirm), "chunk_mb" (host->device pipeline granularity),
+ * "initial_ring" (match records).  Options that shape the device image
+ * ("wide_fdr", "prefilter") apply to scratches allocated afterwards. */
 hs_error_t hs_b200_set_runtime_option(const char *key, int value);
+
+/* Counters of the last finished scan: [0] raw records, [1] error, [2]
+ * first-stage candidates, [3] byte-confirmed literals, [4] candidates that
+ * passed the prefilter. */
+hs_error_t hs_b200_last_counters(const hs_scratch_t *scratch, unsigned int out[8]);
 
 /* Number of kernel launches issued by this library since load (bench.py's
  * "gpu_launches"), and elapsed device time of the last scan kernel in ms
