@@ -29,13 +29,21 @@ namespace hsb {
 
 namespace {
 
+/* PRMT in its default mode: selector nibble bit 3 replicates the selected
+ * byte's sign bit (the __byte_perm intrinsic only honours bits 2:0). */
+__device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {
+    u32 d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 /* 16-entry x 8-bit table lookup for the four nibble indices packed one per
  * byte in idx (0..15), t[0..3] = entries 0-3, 4-7, 8-11, 12-15. */
 __device__ __forceinline__ u32 nibbleLookup(const u32 t[4], u32 idx) {
     u32 x = idx & 0x07070707u;                            /* index within an 8-entry half */
     x |= x >> 4;                                          /* byte0 = i0|i1<<4, byte2 = i2|i3<<4 */
     const u32 sel = __byte_perm(x, 0, 0x4420);            /* selector nibbles i0,i1,i2,i3 */
-    const u32 hiMask = __byte_perm(idx << 4, 0, 0xba98);  /* 0xff where idx >= 8 (sign replicate) */
+    const u32 hiMask = prmt(idx << 4, 0, 0xba98);         /* 0xff where idx >= 8 (sign replicate) */
     const u32 lo8 = __byte_perm(t[0], t[1], sel);
     const u32 hi8 = __byte_perm(t[2], t[3], sel);
     return (lo8 & ~hiMask) | (hi8 & hiMask);
@@ -87,7 +95,7 @@ __global__ void __launch_bounds__(256) accelFindKernel(AccelParams p, const u8 *
             } else if (p.type == ACCEL_TRUFFLE) {
                 const u32 lo = w[k] & 0x0f0f0f0fu;
                 const u32 a = nibbleLookup(p.t0, lo), b = nibbleLookup(p.t1, lo);
-                const u32 top = __byte_perm(w[k], 0, 0xba98); /* 0xff where byte >= 0x80 */
+                const u32 top = prmt(w[k], 0, 0xba98); /* 0xff where byte >= 0x80 */
                 const u32 sel = (a & ~top) | (b & top);
                 /* bit (c >> 4) & 7 of each byte */
                 const u32 sh = (w[k] >> 4) & 0x07070707u;

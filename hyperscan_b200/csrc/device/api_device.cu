@@ -41,11 +41,11 @@ std::atomic<unsigned long long> g_launches{0};
 
 /* runtime tunables (hs_b200_set_runtime_option / HSB200_* environment) */
 struct RuntimeOpts {
-    int warps = 16;
-    int tileBytes = 2048;
-    int stages = 3;
+    int warps = 32;
+    int tileBytes = 1024;
+    int stages = 2;
     int wideFdr = 0;         /* 1: use all 8 FDR slots (u64 entries) when they fit */
-    int stride = 0;          /* first-stage sampling stride override (0 = as compiled) */
+    int stride = 1;          /* first-stage sampling stride (0 = as compiled into the FDR table) */
     int prefilter = 1;       /* shared-memory bitmap in front of the hash confirm */
     int chunkMB = 32;        /* host->device pipeline granularity */
     int initialRing = 1 << 20;

@@ -19,7 +19,7 @@ DEFAULT = ("stride=2;stride=1;stride=2,prefilter=0;stride=1,prefilter=0;"
            "stride=1,warps=8;stride=1,warps=24,tile_bytes=1024;stride=1,warps=32,tile_bytes=1024,stages=2;"
            "stride=1,tile_bytes=4096,warps=8,stages=3;stride=1,stages=2;stride=1,stages=4,tile_bytes=1024;"
            "stride=2,warps=32,tile_bytes=1024,stages=2;stride=2,warps=8,tile_bytes=4096")
-BASE = {"warps": 16, "tile_bytes": 2048, "stages": 3, "wide_fdr": 0, "stride": 0, "prefilter": 1}
+BASE = {"warps": 32, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1}
 
 
 def main():
