@@ -47,6 +47,9 @@ struct RuntimeOpts {
     int wideFdr = 0;         /* 1: use all 8 FDR slots (u64 entries) when they fit */
     int stride = 1;          /* first-stage sampling stride (0 = as compiled into the FDR table) */
     int prefilter = 1;       /* shared-memory bitmap in front of the hash confirm */
+    int rebuild = 1;         /* rebuild the FDR first-stage table over slots 1..4 from the literals */
+    int domain = 0;          /* rebuilt table: hash domain bits (0 = as compiled) */
+    int direct = 1;          /* 1: corpus straight into registers; 0: TMA-staged tiles */
     int chunkMB = 32;        /* host->device pipeline granularity */
     int initialRing = 1 << 20;
 };
@@ -62,7 +65,9 @@ void initOpts() {
         {"HSB200_WARPS", &g_opts.warps},       {"HSB200_TILE", &g_opts.tileBytes},
         {"HSB200_STAGES", &g_opts.stages},     {"HSB200_WIDE_FDR", &g_opts.wideFdr},
         {"HSB200_CHUNK_MB", &g_opts.chunkMB},  {"HSB200_RING", &g_opts.initialRing},
-        {"HSB200_STRIDE", &g_opts.stride},     {"HSB200_PREFILTER", &g_opts.prefilter}};
+        {"HSB200_STRIDE", &g_opts.stride},     {"HSB200_PREFILTER", &g_opts.prefilter},
+        {"HSB200_REBUILD", &g_opts.rebuild},   {"HSB200_DOMAIN", &g_opts.domain},
+        {"HSB200_DIRECT", &g_opts.direct}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -83,6 +88,7 @@ struct DevImage {
     u32 bitmapBytes = 0, bitmapShift = 0, keyBytes = 0;
     int kind = FK_BYTE32;
     int stride = 1;
+    int slotBase = 0;
     u32 indexMask = 0;
     u32 confOff = 0, engineOff = 0;
     u32 confirmKind = CK_FDR;
@@ -133,6 +139,7 @@ void collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
 struct LitTail {
     u64 v, msk;
     u32 size;
+    u32 bucket;
 };
 
 void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
@@ -159,7 +166,7 @@ void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
                 LitInfo x;
                 memcpy(&x, li, sizeof(x));
                 collectProgramReports(bc, bcLen, x.id, ex);
-                tails->push_back({x.v, x.msk, x.size});
+                tails->push_back({x.v, x.msk, x.size, b});
                 if (!x.next) {
                     break;
                 }
@@ -221,6 +228,56 @@ std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u3
     *keyBytes = m;
     *shift = 32 - lg;
     return bm;
+}
+
+/* First-stage table rebuilt from the literal tails (LitInfo v/msk) and their
+ * bucket assignment: u32 entry = 4 slots x 8 buckets indexed by the FDR hash
+ * (two bytes & domain mask, src/fdr/fdr.c:157-170); slot i stands for suffix
+ * distance i + slotBase.  With slotBase 1 the sample at x tests the pairs
+ * (char 1, char 0) .. (char 4, char 3): every character of a 4-byte tail is in a
+ * full two-byte sample, which the reference's slot 0 (second byte unknown)
+ * cannot give, and literals of 5+ bytes gain a sample.  Same construction as
+ * setupTab (src/fdr/fdr_compile.cpp:527-632): bit SET = impossible. */
+std::vector<u8> rebuildHashTable(const std::vector<LitTail> &tails, u32 domain, u32 slotBase) {
+    const u32 entries = 1u << domain, dmask = entries - 1;
+    std::vector<u32> tab(entries, 0xffffffffu);
+    u32 dead = 0;
+    const u32 hiBits = domain - 8;
+    for (const LitTail &t : tails) {
+        for (u32 i = 0; i < 4; i++) {
+            const u32 p = i + slotBase;
+            const u32 bit = 1u << (8 * i + t.bucket);
+            if (p >= t.size) {
+                dead |= bit; /* shorter literal: this slot cannot constrain the bucket */
+                continue;
+            }
+            const u8 c0 = (u8)(t.v >> (8 * (7 - p))), m0 = (u8)(t.msk >> (8 * (7 - p)));
+            u8 c1 = 0, m1 = 0; /* p == 0: the following byte is unknown */
+            if (p > 0) {
+                c1 = (u8)(t.v >> (8 * (8 - p)));
+                m1 = (u8)(t.msk >> (8 * (8 - p)));
+            }
+            const u8 hm = (u8)((1u << hiBits) - 1);
+            bool seen1[256] = {false};
+            for (u32 b1 = 0; b1 < 256; b1++) {
+                if ((b1 & m1) != c1 || seen1[b1 & hm]) {
+                    continue;
+                }
+                seen1[b1 & hm] = true;
+                for (u32 b0 = 0; b0 < 256; b0++) {
+                    if ((b0 & m0) == c0) {
+                        tab[(b0 | (b1 << 8)) & dmask] &= ~bit;
+                    }
+                }
+            }
+        }
+    }
+    std::vector<u8> out((size_t)entries * 4);
+    for (u32 i = 0; i < entries; i++) {
+        const u32 e = tab[i] & ~dead;
+        memcpy(&out[(size_t)i * 4], &e, 4);
+    }
+    return out;
 }
 
 void freeImage(DevImage *im) {
@@ -298,17 +355,29 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
             const size_t wideNeed = (size_t)entries * 8 + 48 * 1024;
+            walkConfirm(bc, h->length, im->confOff, 8, &im->exhaustible, &tails);
             if (g_opts.wideFdr && wideNeed <= (size_t)maxSmem) {
                 im->kind = FK_HASH64;
                 table.assign(src, src + (size_t)entries * 8);
+            } else if (g_opts.rebuild) {
+                u32 minSize = 8, d = f.domain;
+                for (const LitTail &t : tails) {
+                    minSize = std::min(minSize, t.size);
+                }
+                if (g_opts.domain >= 9 && g_opts.domain <= 15) {
+                    d = (u32)g_opts.domain;
+                }
+                im->kind = FK_HASH32;
+                im->slotBase = minSize >= 2 ? 1 : 0;
+                im->indexMask = (1u << d) - 1;
+                table = rebuildHashTable(tails, d, (u32)im->slotBase);
             } else {
-                im->kind = FK_HASH32; /* FDR suffix slots 0..3 */
+                im->kind = FK_HASH32; /* FDR suffix slots 0..3 as compiled */
                 table.resize((size_t)entries * 4);
                 for (u32 i = 0; i < entries; i++) {
                     memcpy(&table[(size_t)i * 4], src + (size_t)i * 8, 4);
                 }
             }
-            walkConfirm(bc, h->length, im->confOff, 8, &im->exhaustible, &tails);
         } else if (teddyIdValid(f.engineID)) {
             /* per-byte entry: slot m = lo_m[b & 15] | hi_m[b >> 4]
              * (src/fdr/teddy.c:918-969, teddy_compile.cpp:440-509) */
@@ -549,12 +618,14 @@ struct ScanPlan {
 
 hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     initOpts();
-    int warps = std::max(1, std::min(32, g_opts.warps));
+    const int direct = g_opts.direct ? 1 : 0;
+    int warps = std::max(1, std::min(direct ? 24 : 32, g_opts.warps));
     u32 tile = (u32)std::max(512, g_opts.tileBytes) & ~511u;
     u32 stages = (u32)std::max(2, std::min(8, g_opts.stages));
     /* shrink until the table + staging fit the opt-in shared memory */
     for (;;) {
-        const size_t need = scanSmemBytes(im->kind, im->tableBytes, im->bitmapBytes, warps, stages, tile);
+        const size_t need = scanSmemBytes(im->kind, im->tableBytes, im->bitmapBytes, direct ? 0 : warps,
+                                          stages, tile);
         if (need <= (size_t)s->maxSmem) {
             pl->cfg.smemBytes = need;
             break;
@@ -574,6 +645,8 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
         }
     }
     pl->cfg.kind = im->kind;
+    pl->cfg.slotBase = im->slotBase;
+    pl->cfg.direct = direct;
     pl->cfg.stride = im->stride;
     if ((g_opts.stride == 1 || g_opts.stride == 2 || g_opts.stride == 4) &&
         (im->kind == FK_HASH32 || im->kind == FK_HASH64)) {
@@ -785,7 +858,9 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"warps", &g_opts.warps},       {"tile_bytes", &g_opts.tileBytes},
         {"stages", &g_opts.stages},     {"wide_fdr", &g_opts.wideFdr},
         {"chunk_mb", &g_opts.chunkMB},  {"initial_ring", &g_opts.initialRing},
-        {"stride", &g_opts.stride},     {"prefilter", &g_opts.prefilter}};
+        {"stride", &g_opts.stride},     {"prefilter", &g_opts.prefilter},
+        {"rebuild", &g_opts.rebuild},   {"domain", &g_opts.domain},
+        {"direct", &g_opts.direct}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;

@@ -76,6 +76,8 @@ struct ScanParams {
 struct LaunchCfg {
     int kind;      /* FilterKind */
     int stride;    /* 1, 2, 4 */
+    int slotBase;  /* FK_HASH32: 0 = slots 0..3 (reference numbering), 1 = slots 1..4 */
+    int direct;    /* 1: corpus loaded straight into registers; 0: TMA-staged tiles */
     int grid;      /* CTAs (one per SM) */
     int warps;     /* per CTA */
     size_t smemBytes;

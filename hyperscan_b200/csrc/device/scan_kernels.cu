@@ -385,22 +385,44 @@ template <int KIND> struct Kind {
     static constexpr bool HASH = KIND == FK_HASH32 || KIND == FK_HASH64;
 };
 
-__device__ __forceinline__ void orShift32(u32 *a, int k, int r, u32 e) {
-    if (r == 0) {
-        a[k] |= e;
+__device__ __forceinline__ u32 lds32(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(u32 addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+/* OR the 128-bit stream E[0..3] (one entry per word of the lane, all at the
+ * same in-word position) into a[] at byte offset O (0..4): one funnel shift
+ * per output word instead of two shifts per entry. */
+template <int O> __device__ __forceinline__ void orStream(u32 (&a)[6], const u32 (&E)[4]) {
+    if (O == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) a[k] |= E[k];
+    } else if (O == 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) a[k + 1] |= E[k];
     } else {
-        a[k] |= e << (8 * r);
-        a[k + 1] |= e >> (32 - 8 * r);
+        a[0] |= E[0] << (8 * O);
+#pragma unroll
+        for (int k = 1; k < 4; k++) a[k] |= __funnelshift_l(E[k - 1], E[k], 8 * O);
+        a[4] |= E[3] >> (32 - 8 * O);
     }
 }
 
 /* Shift-OR contributions of one lane's 16 positions.  a[o][0..3]: bytes for
  * the lane's own 16 end positions (bit set = bucket impossible); a[o][4..]:
- * overflow that belongs to the NEXT lane's first positions.  Only positions
- * = 0 mod STRIDE are sampled; skipped positions contribute nothing, i.e.
- * "possible" (src/fdr/fdr.c:247-327). */
-template <int KIND, int STRIDE>
-__device__ __forceinline__ void laneFilter(const u32 (&w)[5], const u8 *tab, u32 laneOff,
+ * overflow that belongs to the NEXT lane's first positions.  An entry read at
+ * position x applies to end positions x+SB .. x+SB+3 (SB = slot base: 0 for
+ * tables in the reference's own slot numbering, 1 for tables rebuilt over
+ * slots 1..4).  Only positions = 0 mod STRIDE are sampled; skipped positions
+ * contribute nothing, i.e. "possible" (src/fdr/fdr.c:247-327). */
+template <int KIND, int STRIDE, int SB>
+__device__ __forceinline__ void laneFilter(const u32 (&w)[5], u32 tabAddr, u32 laneOff,
                                            u32 indexMask, u32 (&a)[2][6]) {
 #pragma unroll
     for (int o = 0; o < 2; o++) {
@@ -409,43 +431,144 @@ __device__ __forceinline__ void laneFilter(const u32 (&w)[5], const u8 *tab, u32
             a[o][i] = 0;
         }
     }
+    if (KIND == FK_HASH64) {
 #pragma unroll
-    for (int j = 0; j < 16; j += STRIDE) {
-        const int k = j >> 2, r = j & 3;
-        if (KIND == FK_BYTE32) {
-            const u32 idx = __byte_perm(w[k], 0, 0x4440 + r);
-            const u32 e = *reinterpret_cast<const u32 *>(tab + idx * 128 + laneOff);
-            orShift32(a[0], k, r, e);
-        } else if (KIND == FK_BYTE64) {
-            const u32 idx = __byte_perm(w[k], 0, 0x4440 + r);
-            const uint2 e = *reinterpret_cast<const uint2 *>(tab + idx * 128 + laneOff);
-            orShift32(a[0], k, r, e.x);
-            orShift32(a[1], k, r, e.y);
-        } else {
-            /* byte offset of entry (h & indexMask), h = the two bytes at j */
-            constexpr int SH = KIND == FK_HASH32 ? 2 : 3;
+        for (int j = 0; j < 16; j += STRIDE) {
+            const int k = j >> 2, r = j & 3;
             u32 off;
             if (r == 0) {
-                off = w[k] << SH;
+                off = w[k] << 3;
             } else if (r == 3) {
-                off = __funnelshift_r(w[k], w[k + 1], 24 - SH);
+                off = __funnelshift_r(w[k], w[k + 1], 21);
             } else {
-                off = w[k] >> (8 * r - SH);
+                off = w[k] >> (8 * r - 3);
             }
-            off &= indexMask << SH;
-            if (KIND == FK_HASH32) {
-                const u32 e = *reinterpret_cast<const u32 *>(tab + off);
-                orShift32(a[0], k, r, e);
+            const uint2 e = lds64(tabAddr + (off & (indexMask << 3)));
+            if (r == 0) {
+                a[0][k] |= e.x;
+                a[0][k + 1] |= e.y;
             } else {
-                const uint2 e = *reinterpret_cast<const uint2 *>(tab + off);
+                a[0][k] |= e.x << (8 * r);
+                a[0][k + 1] |= __funnelshift_l(e.x, e.y, 8 * r);
+                a[0][k + 2] |= e.y >> (32 - 8 * r);
+            }
+        }
+        return;
+    }
+    /* 32-bit entries: gather the entries of in-word position r for all four
+     * words, then merge the stream with funnel shifts */
+#pragma unroll
+    for (int r = 0; r < 4; r += STRIDE) {
+        u32 E0[4], E1[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (KIND == FK_HASH32) {
+                u32 off;
                 if (r == 0) {
-                    a[0][k] |= e.x;
-                    a[0][k + 1] |= e.y;
+                    off = w[k] << 2;
+                } else if (r == 3) {
+                    off = __funnelshift_r(w[k], w[k + 1], 22);
                 } else {
-                    a[0][k] |= e.x << (8 * r);
-                    a[0][k + 1] |= __funnelshift_l(e.x, e.y, 8 * r);
-                    a[0][k + 2] |= e.y >> (32 - 8 * r);
+                    off = w[k] >> (8 * r - 2);
                 }
+                E0[k] = lds32(tabAddr + (off & (indexMask << 2)));
+            } else {
+                const u32 idx = __byte_perm(w[k], 0, 0x4440 + r);
+                if (KIND == FK_BYTE32) {
+                    E0[k] = lds32(tabAddr + idx * 128 + laneOff);
+                } else {
+                    const uint2 e = lds64(tabAddr + idx * 128 + laneOff);
+                    E0[k] = e.x;
+                    E1[k] = e.y;
+                }
+            }
+        }
+        constexpr int O = 0; (void)O;
+        if (r + SB == 0) orStream<0>(a[0], E0);
+        if (r + SB == 1) orStream<1>(a[0], E0);
+        if (r + SB == 2) orStream<2>(a[0], E0);
+        if (r + SB == 3) orStream<3>(a[0], E0);
+        if (r + SB == 4) orStream<4>(a[0], E0);
+        if (KIND == FK_BYTE64) {
+            if (r + SB == 0) orStream<0>(a[1], E1);
+            if (r + SB == 1) orStream<1>(a[1], E1);
+            if (r + SB == 2) orStream<2>(a[1], E1);
+            if (r + SB == 3) orStream<3>(a[1], E1);
+            if (r + SB == 4) orStream<4>(a[1], E1);
+        }
+    }
+}
+
+/* ---- candidate handling (rare path) ------------------------------------------- */
+
+/* little-endian u64 of corpus bytes [g-7, g] (at least 16 readable bytes
+ * precede position 0) */
+__device__ __forceinline__ u64 confValAt(const ScanParams &p, u64 g) {
+    const u8 *a = p.corpus + g - 7;
+    const u32 mis = (u32)((uintptr_t)a & 3);
+    const u32 *aw = reinterpret_cast<const u32 *>(a - mis);
+    const u32 w0 = __ldg(aw), w1 = __ldg(aw + 1), w2 = __ldg(aw + 2);
+    const u32 lo = __funnelshift_r(w0, w1, 8 * mis);
+    const u32 hi = __funnelshift_r(w1, w2, 8 * mis);
+    return ((u64)hi << 32) | lo;
+}
+
+/* All candidates of one lane: c[o][k] has a set bit per (bucket, byte).  `pw` is
+ * the word before the lane's 16 bytes.  Per candidate byte: hash the last
+ * keyBytes bytes into the prefilter bitmap (shared memory); only survivors pay
+ * for the hash confirm in HBM/L2. */
+template <int NOCT>
+__device__ __noinline__ void laneCandidates(const ScanParams &p, u32 bitmapAddr, u32 c00, u32 c01,
+                                            u32 c02, u32 c03, u32 c10, u32 c11, u32 c12, u32 c13,
+                                            u32 w0, u32 w1, u32 w2, u32 w3, u32 pw, u64 g0,
+                                            u32 *stats) {
+    /* 16-bit map of bytes that carry a candidate */
+    u32 cm = 0;
+    {
+        const u32 n[4] = {c00 | c10, c01 | c11, c02 | c12, c03 | c13};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 t = n[k] | (n[k] >> 4);
+            t |= t >> 2;
+            t |= t >> 1;
+            t &= 0x01010101u;
+            cm |= ((t * 0x01020408u) >> 24) << (4 * k);
+        }
+    }
+    while (cm) {
+        const u32 x = __ffs(cm) - 1;
+        cm &= cm - 1;
+        const u32 k = x >> 2, q = x & 3;
+        const u32 cur = k == 0 ? w0 : k == 1 ? w1 : k == 2 ? w2 : w3;
+        const u32 prv = k == 0 ? pw : k == 1 ? w0 : k == 2 ? w1 : w2;
+        const u32 b0 = k == 0 ? c00 : k == 1 ? c01 : k == 2 ? c02 : c03;
+        u32 buckets = (b0 >> (8 * q)) & 0xff;
+        if (NOCT == 2) {
+            const u32 b1 = k == 0 ? c10 : k == 1 ? c11 : k == 2 ? c12 : c13;
+            buckets |= ((b1 >> (8 * q)) & 0xff) << 8;
+        }
+        stats[0]++;
+        if (p.bitmapBytes) {
+            /* the 4 bytes ending at x, then the last keyBytes of them */
+            const u32 last4 = q == 3 ? cur : __funnelshift_r(prv, cur, 8 * (q + 1));
+            const u32 key = last4 >> (8 * (4 - p.keyBytes));
+            const u32 hsh = (key * 0x9E3779B1u) >> p.bitmapShift;
+            if (!((lds32(bitmapAddr + ((hsh >> 5) << 2)) >> (hsh & 31)) & 1)) {
+                continue; /* no literal of any bucket ends here */
+            }
+        }
+        stats[1]++;
+        const u64 g = g0 + x;
+        const u64 confVal = confValAt(p, g);
+        if (p.confirmKind == CK_NOODLE) {
+            if (buckets & 1) {
+                confirmNoodle(p, g, confVal, &stats[2]);
+            }
+        } else {
+            while (buckets) {
+                const u32 bucket = __ffs(buckets) - 1;
+                buckets &= buckets - 1;
+                confirmFdr(p, bucket, g, confVal, &stats[2]);
             }
         }
     }
@@ -460,19 +583,80 @@ __host__ __device__ inline u32 tableSmemBytes(int kind, u32 tableBytes) {
     return (tableBytes + 127u) & ~127u;
 }
 
-template <int KIND, int STRIDE>
-__global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
+/* One 512-byte step of a warp: v = the lane's own 16 bytes, w4 = the word after
+ * them, pwSrc = loader of the word before the warp's 512 bytes (lane 0 only,
+ * rare path). */
+template <int KIND, int STRIDE, int SB, class PrevWord>
+__device__ __forceinline__ void scanStep(const ScanParams &p, const uint4 v, u32 w4, u32 lane,
+                                         u32 tabAddr, u32 laneOff, u32 bitmapAddr,
+                                         u32 (&carry)[2][2], u64 g0, u32 *stats, PrevWord prevWord) {
+    typedef Kind<KIND> K;
+    const u32 w[5] = {v.x, v.y, v.z, v.w, w4};
+    u32 a[2][6];
+    laneFilter<KIND, STRIDE, SB>(w, tabAddr, laneOff, p.indexMask, a);
+    u32 c[2][4];
+    u32 any = 0;
+#pragma unroll
+    for (int o = 0; o < K::NOCT; o++) {
+#pragma unroll
+        for (int x = 0; x < K::SPILL; x++) {
+            u32 in = __shfl_up_sync(0xffffffffu, a[o][4 + x], 1);
+            const u32 last = __shfl_sync(0xffffffffu, a[o][4 + x], 31);
+            if (lane == 0) {
+                in = carry[o][x];
+            }
+            carry[o][x] = last;
+            a[o][x] |= in;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            c[o][k] = ~a[o][k];
+            any |= c[o][k];
+        }
+    }
+    if (K::NOCT == 1) {
+        c[1][0] = c[1][1] = c[1][2] = c[1][3] = 0;
+    }
+    if (__any_sync(0xffffffffu, any != 0)) {
+        u32 pw = __shfl_up_sync(0xffffffffu, v.w, 1);
+        if (lane == 0) {
+            pw = prevWord();
+        }
+        if (any) {
+            laneCandidates<K::NOCT>(p, bitmapAddr, c[0][0], c[0][1], c[0][2], c[0][3], c[1][0], c[1][1],
+                                    c[1][2], c[1][3], v.x, v.y, v.z, v.w, pw, g0, stats);
+        }
+    }
+}
+
+/* State entering a run of tiles: every lane evaluates the 16 bytes before the
+ * run as if it were "lane -1" and keeps only the overflow. */
+template <int KIND, int STRIDE, int SB>
+__device__ __forceinline__ void haloStep(const ScanParams &p, const uint4 v, u32 w4, u32 tabAddr,
+                                         u32 laneOff, u32 (&carry)[2][2]) {
+    typedef Kind<KIND> K;
+    const u32 w[5] = {v.x, v.y, v.z, v.w, w4};
+    u32 a[2][6];
+    laneFilter<KIND, STRIDE, SB>(w, tabAddr, laneOff, p.indexMask, a);
+#pragma unroll
+    for (int o = 0; o < K::NOCT; o++) {
+#pragma unroll
+        for (int x = 0; x < K::SPILL; x++) {
+            carry[o][x] = a[o][4 + x];
+        }
+    }
+}
+
+template <int KIND, int STRIDE, int SB, int DIRECT>
+__global__ void __launch_bounds__(DIRECT ? 768 : 1024, 1) scanKernel(const ScanParams p) {
     extern __shared__ __align__(128) u8 smem[];
     typedef Kind<KIND> K;
     const u32 lane = threadIdx.x & 31;
     const u32 warp = threadIdx.x >> 5;
     const u32 nwarps = blockDim.x >> 5;
     const u32 stageBytes = p.tileBytes + 32;
-    const u32 tabBytes = tableSmemBytes(KIND, p.tableBytes) + p.bitmapBytes;
-
-    u8 *stages = smem + tabBytes + (size_t)warp * p.nstages * stageBytes;
-    u64 *bars = reinterpret_cast<u64 *>(smem + tabBytes + (size_t)nwarps * p.nstages * stageBytes) +
-                warp * p.nstages;
+    const u32 tab0 = tableSmemBytes(KIND, p.tableBytes);
+    const u32 tabBytes = tab0 + p.bitmapBytes;
 
     /* pin the first-stage table in shared memory */
     if (KIND == FK_BYTE32) {
@@ -495,23 +679,28 @@ __global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
         }
     }
     /* second-stage prefilter: one bit per hash of a literal's last bytes */
-    const u32 *bitmap = reinterpret_cast<const u32 *>(smem + tableSmemBytes(KIND, p.tableBytes));
     if (p.bitmapBytes) {
         const uint4 *g = reinterpret_cast<const uint4 *>(p.bitmap);
-        uint4 *sdst = reinterpret_cast<uint4 *>(smem + tableSmemBytes(KIND, p.tableBytes));
+        uint4 *sdst = reinterpret_cast<uint4 *>(smem + tab0);
         for (u32 i = threadIdx.x; i < p.bitmapBytes / 16; i += blockDim.x) {
             sdst[i] = __ldg(g + i);
         }
     }
-    if (lane == 0) {
+    u8 *stages = smem + tabBytes + (size_t)warp * p.nstages * stageBytes;
+    u64 *bars = reinterpret_cast<u64 *>(smem + tabBytes + (size_t)nwarps * p.nstages * stageBytes) +
+                warp * p.nstages;
+    if (!DIRECT && lane == 0) {
         for (u32 s = 0; s < p.nstages; s++) {
             mbarInit(&bars[s], 1);
         }
     }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (!DIRECT) {
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
-    const u8 *tab = smem;
+    const u32 tabAddr = smemAddr(smem);
+    const u32 bitmapAddr = tabAddr + tab0;
     const u32 laneOff = KIND == FK_BYTE64 ? (lane & 15) * 8 : lane * 4;
 
     /* this warp's contiguous run of tiles */
@@ -520,183 +709,152 @@ __global__ void __launch_bounds__(1024, 1) scanKernel(const ScanParams p) {
     const u32 q = p.ntiles / totalWarps, rem = p.ntiles % totalWarps;
     const u32 myCount = q + (gwarp < rem ? 1u : 0u);
     const u32 myFirst = p.tileFirst + gwarp * q + min(gwarp, rem);
-    const u32 stepsPerTile = p.tileBytes >> 9;
-
-    auto issue = [&](u32 t, u32 s) { /* lane 0: TMA bulk copy of tile t -> stage s */
-        const u64 base = (u64)t * p.tileBytes;
-        u8 *dst = stages + (size_t)s * stageBytes;
-        const u64 readEnd = p.readableEnd;
-        u64 from = base - 16;
-        if (t == 0) { /* nothing before the corpus: stage bytes [0,16) stay unset */
-            from = 0;
-            dst += 16;
-        }
-        u64 to = base + p.tileBytes + 16;
-        if (to > readEnd) {
-            to = readEnd;
-        }
-        const u32 bytes = (u32)(to - from);
-        mbarExpectTx(&bars[s], bytes);
-        tmaLoad1d(dst, p.corpus + from, bytes, &bars[s]);
-    };
-
-    if (lane == 0) {
-        for (u32 i = 0; i < p.nstages && i < myCount; i++) {
-            issue(myFirst + i, i);
-        }
+    if (myCount == 0) {
+        return;
     }
 
     u32 carry[2][2] = {{0, 0}, {0, 0}}; /* lane 31's overflow of the previous step */
-    u32 ncand = 0, nconf = 0, npass = 0;
-    u32 s = 0, parity = 0;
-    for (u32 i = 0; i < myCount; i++) {
-        const u32 t = myFirst + i;
-        const u64 tileBase = (u64)t * p.tileBytes;
-        const u8 *st = stages + (size_t)s * stageBytes; /* st[16 + x] = corpus[tileBase + x] */
-        mbarWait(&bars[s], parity);
+    u32 stats[3] = {0, 0, 0};           /* candidates, prefilter passes, confirmed */
 
-        if (i == 0 && t != 0) {
-            /* state entering this run: every lane evaluates the 16 bytes
-             * before the tile as if it were "lane -1" */
-            const uint4 v = *reinterpret_cast<const uint4 *>(st);
-            const u32 w[5] = {v.x, v.y, v.z, v.w, *reinterpret_cast<const u32 *>(st + 16)};
-            u32 a[2][6];
-            laneFilter<KIND, STRIDE>(w, tab, laneOff, p.indexMask, a);
-#pragma unroll
-            for (int o = 0; o < K::NOCT; o++) {
-#pragma unroll
-                for (int x = 0; x < K::SPILL; x++) {
-                    carry[o][x] = a[o][4 + x];
-                }
-            }
+    if (DIRECT) {
+        /* corpus bytes straight from HBM into registers: one coalesced
+         * 16-byte load per lane and step, three steps in flight per warp */
+        const u64 runStart = (u64)myFirst * p.tileBytes;
+        u64 runEnd = runStart + (u64)myCount * p.tileBytes;
+        if (runEnd > p.corpusBytes) {
+            runEnd = p.corpusBytes;
         }
-
-        u32 nsteps = stepsPerTile;
-        if (tileBase + p.tileBytes > p.corpusBytes) {
-            nsteps = (u32)((p.corpusBytes - tileBase + 511) >> 9);
+        const u32 nsteps = (u32)((runEnd - runStart + 511) >> 9);
+        const u8 *base = p.corpus + runStart + lane * 16;
+        const u64 lanePos = runStart + lane * 16;
+        auto load = [&](u32 step) -> uint4 {
+            const u64 pos = lanePos + (u64)step * 512;
+            if (pos + 16 <= p.readableEnd) {
+                return __ldcs(reinterpret_cast<const uint4 *>(base + (size_t)step * 512));
+            }
+            return make_uint4(0, 0, 0, 0);
+        };
+        uint4 v0 = load(0), v1 = load(1), v2 = load(2);
+        if (runStart != 0) {
+            const uint4 hv = __ldg(reinterpret_cast<const uint4 *>(p.corpus + runStart - 16));
+            const u32 first = __shfl_sync(0xffffffffu, v0.x, 0);
+            haloStep<KIND, STRIDE, SB>(p, hv, first, tabAddr, laneOff, carry);
         }
         for (u32 step = 0; step < nsteps; step++) {
-            const u8 *sp = st + 16 + step * 512 + lane * 16;
-            const uint4 v = *reinterpret_cast<const uint4 *>(sp);
-            u32 w[5] = {v.x, v.y, v.z, v.w, 0};
+            const uint4 v = v0;
+            v0 = v1;
+            v1 = v2;
+            v2 = load(step + 3);
+            u32 w4 = 0;
             if (K::HASH) {
-                w[4] = __shfl_down_sync(0xffffffffu, v.x, 1);
+                w4 = __shfl_down_sync(0xffffffffu, v.x, 1);
+                const u32 nx = __shfl_sync(0xffffffffu, v0.x, 0);
                 if (lane == 31) {
-                    w[4] = *reinterpret_cast<const u32 *>(sp + 16);
+                    w4 = nx;
                 }
             }
-            u32 a[2][6];
-            laneFilter<KIND, STRIDE>(w, tab, laneOff, p.indexMask, a);
-            u32 c[2][4];
-            u32 any = 0;
-#pragma unroll
-            for (int o = 0; o < K::NOCT; o++) {
-#pragma unroll
-                for (int x = 0; x < K::SPILL; x++) {
-                    u32 in = __shfl_up_sync(0xffffffffu, a[o][4 + x], 1);
-                    const u32 last = __shfl_sync(0xffffffffu, a[o][4 + x], 31);
-                    if (lane == 0) {
-                        in = carry[o][x];
-                    }
-                    carry[o][x] = last;
-                    a[o][x] |= in;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    c[o][k] = ~a[o][k];
-                    any |= c[o][k];
-                }
+            const u64 g0 = lanePos + (u64)step * 512;
+            scanStep<KIND, STRIDE, SB>(p, v, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
+                                       [&]() { return __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)); });
+        }
+    } else {
+        const u32 stepsPerTile = p.tileBytes >> 9;
+        auto issue = [&](u32 t, u32 s) { /* lane 0: TMA bulk copy of tile t -> stage s */
+            const u64 base = (u64)t * p.tileBytes;
+            u8 *dst = stages + (size_t)s * stageBytes;
+            const u64 readEnd = p.readableEnd;
+            u64 from = base - 16;
+            if (t == 0) { /* nothing before the corpus: stage bytes [0,16) stay unset */
+                from = 0;
+                dst += 16;
             }
-            if (__any_sync(0xffffffffu, any != 0)) {
-                if (any) {
-                    const u64 g0 = tileBase + step * 512 + lane * 16;
-                    u32 cc[K::NOCT * 4]; /* rare path only: lives in local memory */
-#pragma unroll
-                    for (int oo = 0; oo < K::NOCT; oo++) {
-#pragma unroll
-                        for (int kk = 0; kk < 4; kk++) {
-                            cc[oo * 4 + kk] = c[oo][kk];
-                        }
-                    }
-#pragma unroll 1
-                    for (int k = 0; k < 4; k++) {
-                        const u32 m0 = cc[k], m1 = K::NOCT == 2 ? cc[K::NOCT * 4 - 4 + k] : 0u;
-                        u32 nz = m0 | m1;
-                        while (nz) {
-                            const u32 q = (__ffs(nz) - 1) >> 3; /* byte lane with a candidate */
-                            nz &= ~(0xffu << (8 * q));
-                            u32 buckets = (m0 >> (8 * q)) & 0xff;
-                            if (K::NOCT == 2) {
-                                buckets |= ((m1 >> (8 * q)) & 0xff) << 8;
-                            }
-                            const u32 x = 4 * k + q;
-                            ncand++;
-                            /* bytes [g-7, g] from the stage (16 bytes of history
-                             * precede every tile): three aligned words + funnel */
-                            const u8 *a = sp + (int)x - 7;
-                            const u32 mis = (u32)(smemAddr(a) & 3);
-                            const u32 *aw = reinterpret_cast<const u32 *>(a - mis);
-                            const u32 w0 = aw[0], w1 = aw[1], w2 = aw[2];
-                            const u32 lo = __funnelshift_r(w0, w1, 8 * mis);
-                            const u32 hi = __funnelshift_r(w1, w2, 8 * mis);
-                            if (p.bitmapBytes) {
-                                /* last keyBytes bytes -> bit; a clear bit proves that
-                                 * no literal of any bucket ends here */
-                                const u32 key = hi >> (8 * (4 - p.keyBytes));
-                                const u32 hsh = (key * 0x9E3779B1u) >> p.bitmapShift;
-                                if (!((bitmap[hsh >> 5] >> (hsh & 31)) & 1)) {
-                                    continue;
-                                }
-                            }
-                            npass++;
-                            const u64 confVal = ((u64)hi << 32) | lo;
-                            if (p.confirmKind == CK_NOODLE) {
-                                if (buckets & 1) {
-                                    confirmNoodle(p, g0 + x, confVal, &nconf);
-                                }
-                            } else {
-                                while (buckets) {
-                                    const u32 bucket = __ffs(buckets) - 1;
-                                    buckets &= buckets - 1;
-                                    confirmFdr(p, bucket, g0 + x, confVal, &nconf);
-                                }
-                            }
-                        }
-                    }
-                }
+            u64 to = base + p.tileBytes + 16;
+            if (to > readEnd) {
+                to = readEnd;
+            }
+            const u32 bytes = (u32)(to - from);
+            mbarExpectTx(&bars[s], bytes);
+            tmaLoad1d(dst, p.corpus + from, bytes, &bars[s]);
+        };
+        if (lane == 0) {
+            for (u32 i = 0; i < p.nstages && i < myCount; i++) {
+                issue(myFirst + i, i);
             }
         }
-
-        __syncwarp();
-        if (lane == 0 && i + p.nstages < myCount) {
-            issue(t + p.nstages, s); /* refill the stage just drained */
+        u32 s = 0, parity = 0;
+        for (u32 i = 0; i < myCount; i++) {
+            const u32 t = myFirst + i;
+            const u64 tileBase = (u64)t * p.tileBytes;
+            const u8 *st = stages + (size_t)s * stageBytes; /* st[16 + x] = corpus[tileBase + x] */
+            mbarWait(&bars[s], parity);
+            if (i == 0 && t != 0) {
+                const uint4 hv = *reinterpret_cast<const uint4 *>(st);
+                haloStep<KIND, STRIDE, SB>(p, hv, *reinterpret_cast<const u32 *>(st + 16), tabAddr, laneOff,
+                                           carry);
+            }
+            u32 nsteps = stepsPerTile;
+            if (tileBase + p.tileBytes > p.corpusBytes) {
+                nsteps = (u32)((p.corpusBytes - tileBase + 511) >> 9);
+            }
+            for (u32 step = 0; step < nsteps; step++) {
+                const u8 *sp = st + 16 + step * 512 + lane * 16;
+                const uint4 v = *reinterpret_cast<const uint4 *>(sp);
+                u32 w4 = 0;
+                if (K::HASH) {
+                    w4 = __shfl_down_sync(0xffffffffu, v.x, 1);
+                    if (lane == 31) {
+                        w4 = *reinterpret_cast<const u32 *>(sp + 16);
+                    }
+                }
+                const u64 g0 = tileBase + step * 512 + lane * 16;
+                scanStep<KIND, STRIDE, SB>(p, v, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
+                                           [&]() { return *reinterpret_cast<const u32 *>(sp - 4); });
+            }
+            __syncwarp();
+            if (lane == 0 && i + p.nstages < myCount) {
+                issue(t + p.nstages, s); /* refill the stage just drained */
+            }
+            if (++s == p.nstages) {
+                s = 0;
+                parity ^= 1;
+            }
         }
-        if (++s == p.nstages) {
-            s = 0;
-            parity ^= 1;
-        }
     }
-    if (ncand) {
-        atomicAdd(p.counters + CTR_CANDIDATES, ncand);
+    if (stats[0]) {
+        atomicAdd(p.counters + CTR_CANDIDATES, stats[0]);
     }
-    if (nconf) {
-        atomicAdd(p.counters + CTR_CONFIRMED, nconf);
+    if (stats[1]) {
+        atomicAdd(p.counters + CTR_PREFILTER_PASS, stats[1]);
     }
-    if (npass) {
-        atomicAdd(p.counters + CTR_PREFILTER_PASS, npass);
+    if (stats[2]) {
+        atomicAdd(p.counters + CTR_CONFIRMED, stats[2]);
     }
 }
 
-template <int KIND, int STRIDE>
+template <int KIND, int STRIDE, int SB, int DIRECT>
 cudaError_t launchOne(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(scanKernel<KIND, STRIDE>,
+    cudaError_t e = cudaFuncSetAttribute(scanKernel<KIND, STRIDE, SB, DIRECT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)cfg.smemBytes);
     if (e != cudaSuccess) {
         return e;
     }
-    scanKernel<KIND, STRIDE><<<cfg.grid, cfg.warps * 32, cfg.smemBytes, stream>>>(p);
+    scanKernel<KIND, STRIDE, SB, DIRECT><<<cfg.grid, cfg.warps * 32, cfg.smemBytes, stream>>>(p);
     return cudaGetLastError();
+}
+
+template <int KIND, int STRIDE, int SB>
+cudaError_t launchStaging(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    return cfg.direct ? launchOne<KIND, STRIDE, SB, 1>(cfg, p, stream)
+                      : launchOne<KIND, STRIDE, SB, 0>(cfg, p, stream);
+}
+
+template <int KIND, int SB>
+cudaError_t launchStride(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    if (cfg.stride == 1) return launchStaging<KIND, 1, SB>(cfg, p, stream);
+    if (cfg.stride == 2) return launchStaging<KIND, 2, SB>(cfg, p, stream);
+    if (cfg.stride == 4) return launchStaging<KIND, 4, SB>(cfg, p, stream);
+    return cudaErrorInvalidValue;
 }
 
 } // namespace
@@ -710,19 +868,14 @@ size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 n
 cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
     switch (cfg.kind) {
     case FK_BYTE32:
-        return launchOne<FK_BYTE32, 1>(cfg, p, stream);
+        return launchStaging<FK_BYTE32, 1, 0>(cfg, p, stream);
     case FK_BYTE64:
-        return launchOne<FK_BYTE64, 1>(cfg, p, stream);
+        return launchStaging<FK_BYTE64, 1, 0>(cfg, p, stream);
     case FK_HASH32:
-        if (cfg.stride == 1) return launchOne<FK_HASH32, 1>(cfg, p, stream);
-        if (cfg.stride == 2) return launchOne<FK_HASH32, 2>(cfg, p, stream);
-        if (cfg.stride == 4) return launchOne<FK_HASH32, 4>(cfg, p, stream);
-        break;
+        return cfg.slotBase ? launchStride<FK_HASH32, 1>(cfg, p, stream)
+                            : launchStride<FK_HASH32, 0>(cfg, p, stream);
     case FK_HASH64:
-        if (cfg.stride == 1) return launchOne<FK_HASH64, 1>(cfg, p, stream);
-        if (cfg.stride == 2) return launchOne<FK_HASH64, 2>(cfg, p, stream);
-        if (cfg.stride == 4) return launchOne<FK_HASH64, 4>(cfg, p, stream);
-        break;
+        return launchStride<FK_HASH64, 0>(cfg, p, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -308,9 +308,13 @@ long hs_b200_test_build_hwlm(const char *const *lits, const size_t *lens,
  * "warps" per CTA, "tile_bytes", "stages" (TMA ring depth per warp),
  * "wide_fdr" (1: use all 8 FDR suffix slots), "stride" (first-stage sampling
  * stride override, 0 = as compiled), "prefilter" (shared-memory bitmap before
- * the hash confirm), "chunk_mb" (host->device pipeline granularity),
+ * the hash confirm), "rebuild" (1: rebuild the FDR first-stage table over
+ * suffix slots 1..4 from the literals; 0: use the table as compiled), "domain"
+ * (rebuilt table's hash bits, 0 = as compiled), "direct" (1: corpus loaded
+ * straight into registers, 0: TMA-staged tiles in shared memory), "chunk_mb"
+ * (host->device pipeline granularity),
  * "initial_ring" (match records).  Options that shape the device image
- * ("wide_fdr", "prefilter") apply to scratches allocated afterwards. */
+ * ("wide_fdr", "prefilter", "rebuild", "domain") apply to scratches allocated afterwards. */
 hs_error_t hs_b200_set_runtime_option(const char *key, int value);
 
 /* Counters of the last finished scan: [0] raw records, [1] error, [2]

@@ -110,38 +110,49 @@ def test_block_boundaries_do_not_leak(hs, ref):
     _check_all(hs, ref, lits, [0, 0, 0], [1, 2, 3], data, off, ln)
 
 
-@pytest.mark.parametrize("stride,wide,prefilter", [(0, 0, 1), (1, 1, 1), (2, 0, 0), (4, 1, 1), (1, 0, 0)])
-def test_filter_variants_same_matches(hs, ref, stride, wide, prefilter):
-    """Sampling stride, slot width and the prefilter only change the candidate
-    set of the first stages, never the matches."""
+VARIANT_KEYS = ("stride", "wide_fdr", "prefilter", "rebuild", "domain", "direct")
+VARIANT_DEFAULTS = (1, 0, 1, 1, 0, 1)
+
+
+@pytest.mark.parametrize("variant", [(0, 0, 1, 0, 0, 0), (1, 1, 1, 1, 0, 1), (2, 0, 0, 1, 0, 0), (4, 1, 1, 0, 0, 1),
+                                     (1, 0, 0, 0, 0, 1), (1, 0, 1, 1, 11, 1), (2, 0, 1, 1, 15, 0),
+                                     (1, 0, 1, 1, 9, 0)])
+def test_filter_variants_same_matches(hs, ref, variant):
+    """Sampling stride, slot set, hash domain, staging mode and the prefilter only
+    change the candidate set of the first stages, never the matches."""
     lits, flags, ids = synth.literal_set(500, min_len=4, max_len=14, seed=21, caseless_frac=0.3,
                                          alphabet=b"abcdefgh")
+    lits += [b"ab", b"b", b"cdc"]  # short literals force slot base 0 in some variants
+    flags += [0, 1, 0]
+    ids += [1000, 1001, 1002]
     data, off, ln = synth.ragged_corpus([70000, 33, 5000, 0, 12345], lits, seed=13, plant_per_kb=3,
                                         alphabet=b"abcdefghABCDEFGH")
     try:
-        hs.set_runtime_option("stride", stride)
-        hs.set_runtime_option("wide_fdr", wide)
-        hs.set_runtime_option("prefilter", prefilter)
-        _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
+        for k, v in zip(VARIANT_KEYS, variant):
+            hs.set_runtime_option(k, v)
+        _check_all(hs, ref, lits[:500], flags[:500], ids[:500], data, off, ln, use_brute=False)
+        _check_all(hs, ref, lits, flags, ids, data[:20000], off[:1], ln[:1] // 4, use_brute=False)
     finally:
-        hs.set_runtime_option("stride", 1)
-        hs.set_runtime_option("wide_fdr", 0)
-        hs.set_runtime_option("prefilter", 1)
+        for k, v in zip(VARIANT_KEYS, VARIANT_DEFAULTS):
+            hs.set_runtime_option(k, v)
 
 
-@pytest.mark.parametrize("tile,warps,stages", [(512, 1, 2), (1024, 4, 2), (4096, 8, 4), (2048, 16, 3)])
-def test_tile_geometry_invariance(hs, ref, tile, warps, stages):
+@pytest.mark.parametrize("tile,warps,stages,direct", [(512, 1, 2, 0), (1024, 4, 2, 0), (4096, 8, 4, 0),
+                                                       (2048, 16, 3, 0), (512, 3, 2, 1), (8192, 24, 2, 1)])
+def test_tile_geometry_invariance(hs, ref, tile, warps, stages, direct):
     lits, flags, ids = synth.literal_set(300, seed=4, alphabet=b"abcdefgh")
     data, off, ln, _ = synth.block_corpus(257, 1000, lits, plant_per_kb=2.0, seed=8)
     try:
         hs.set_runtime_option("tile_bytes", tile)
         hs.set_runtime_option("warps", warps)
         hs.set_runtime_option("stages", stages)
+        hs.set_runtime_option("direct", direct)
         _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
     finally:
         hs.set_runtime_option("tile_bytes", 1024)
         hs.set_runtime_option("warps", 32)
         hs.set_runtime_option("stages", 2)
+        hs.set_runtime_option("direct", 1)
 
 
 def test_config2_shape_sample(hs, ref):

@@ -14,12 +14,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hyperscan_b200 import capi, synth  # noqa: E402
 
-DEFAULT = ("stride=2;stride=1;stride=2,prefilter=0;stride=1,prefilter=0;"
-           "stride=1,wide_fdr=1;stride=2,wide_fdr=1;"
-           "stride=1,warps=8;stride=1,warps=24,tile_bytes=1024;stride=1,warps=32,tile_bytes=1024,stages=2;"
-           "stride=1,tile_bytes=4096,warps=8,stages=3;stride=1,stages=2;stride=1,stages=4,tile_bytes=1024;"
-           "stride=2,warps=32,tile_bytes=1024,stages=2;stride=2,warps=8,tile_bytes=4096")
-BASE = {"warps": 32, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1}
+DEFAULT = ("direct=1;direct=0;direct=1,rebuild=0;direct=0,rebuild=0;direct=1,warps=16;direct=1,warps=20;"
+           "direct=1,tile_bytes=4096;direct=1,tile_bytes=16384;direct=1,domain=14;direct=1,domain=15;"
+           "direct=1,domain=12;direct=0,warps=24,tile_bytes=2048;direct=1,prefilter=0;direct=1,stride=2")
+BASE = {"warps": 32, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1,
+        "rebuild": 1, "domain": 0, "direct": 1}
 
 
 def main():
