@@ -50,6 +50,7 @@ struct RuntimeOpts {
     int rebuild = 1;         /* rebuild the FDR first-stage table over slots 1..4 from the literals */
     int domain = 0;          /* rebuilt table: hash domain bits (0 = as compiled) */
     int direct = 1;          /* 1: corpus straight into registers; 0: TMA-staged tiles */
+    int replicas = 0;        /* rebuilt table: copies per entry (0 = fill up to 128 KB, max 16) */
     int chunkMB = 32;        /* host->device pipeline granularity */
     int initialRing = 1 << 20;
 };
@@ -67,7 +68,7 @@ void initOpts() {
         {"HSB200_CHUNK_MB", &g_opts.chunkMB},  {"HSB200_RING", &g_opts.initialRing},
         {"HSB200_STRIDE", &g_opts.stride},     {"HSB200_PREFILTER", &g_opts.prefilter},
         {"HSB200_REBUILD", &g_opts.rebuild},   {"HSB200_DOMAIN", &g_opts.domain},
-        {"HSB200_DIRECT", &g_opts.direct}};
+        {"HSB200_DIRECT", &g_opts.direct},     {"HSB200_REPLICAS", &g_opts.replicas}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -89,6 +90,7 @@ struct DevImage {
     int kind = FK_BYTE32;
     int stride = 1;
     int slotBase = 0;
+    u32 repShift = 0;
     u32 indexMask = 0;
     u32 confOff = 0, engineOff = 0;
     u32 confirmKind = CK_FDR;
@@ -370,7 +372,21 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                 im->kind = FK_HASH32;
                 im->slotBase = minSize >= 2 ? 1 : 0;
                 im->indexMask = (1u << d) - 1;
-                table = rebuildHashTable(tails, d, (u32)im->slotBase);
+                std::vector<u8> one = rebuildHashTable(tails, d, (u32)im->slotBase);
+                /* copies of every entry in adjacent words: lane l reads copy
+                 * l & (R-1), so a lookup's lanes fall into R bank groups */
+                u32 R = 1;
+                const u32 want = g_opts.replicas > 0 ? (u32)g_opts.replicas : 16;
+                while (R * 2 <= want && one.size() * R * 2 <= 128u * 1024) {
+                    R *= 2;
+                }
+                im->repShift = (u32)__builtin_ctz(R);
+                table.resize(one.size() * R);
+                for (size_t i = 0; i < one.size() / 4; i++) {
+                    for (u32 g = 0; g < R; g++) {
+                        memcpy(&table[(i * R + g) * 4], &one[i * 4], 4);
+                    }
+                }
             } else {
                 im->kind = FK_HASH32; /* FDR suffix slots 0..3 as compiled */
                 table.resize((size_t)entries * 4);
@@ -675,6 +691,7 @@ void fillParams(const hs_scratch *s, const DevImage *im, const hs_b200_corpus *c
     p->table = im->d_table;
     p->tableBytes = im->tableBytes;
     p->indexMask = im->indexMask;
+    p->repShift = im->repShift;
     p->bitmap = im->d_bitmap;
     p->bitmapBytes = im->bitmapBytes;
     p->bitmapShift = im->bitmapShift;
@@ -860,7 +877,7 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"chunk_mb", &g_opts.chunkMB},  {"initial_ring", &g_opts.initialRing},
         {"stride", &g_opts.stride},     {"prefilter", &g_opts.prefilter},
         {"rebuild", &g_opts.rebuild},   {"domain", &g_opts.domain},
-        {"direct", &g_opts.direct}};
+        {"direct", &g_opts.direct},     {"replicas", &g_opts.replicas}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;

@@ -59,6 +59,7 @@ struct ScanParams {
     const u8 *table;       /* first-stage table in HBM (copied to smem) */
     u32 tableBytes;
     u32 indexMask;         /* FK_HASH*: FDR domainMask */
+    u32 repShift;          /* FK_HASH32: log2 of the copies per entry (bank partition) */
     const u8 *bitmap;      /* second-stage prefilter (copied to smem), may be null */
     u32 bitmapBytes;       /* power of two >= 16, or 0 = no prefilter */
     u32 bitmapShift;       /* 32 - log2(bits) */

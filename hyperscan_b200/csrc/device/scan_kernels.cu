@@ -423,7 +423,7 @@ template <int O> __device__ __forceinline__ void orStream(u32 (&a)[6], const u32
  * contribute nothing, i.e. "possible" (src/fdr/fdr.c:247-327). */
 template <int KIND, int STRIDE, int SB>
 __device__ __forceinline__ void laneFilter(const u32 (&w)[5], u32 tabAddr, u32 laneOff,
-                                           u32 indexMask, u32 (&a)[2][6]) {
+                                           u32 indexMask, u32 repShift, u32 (&a)[2][6]) {
 #pragma unroll
     for (int o = 0; o < 2; o++) {
 #pragma unroll
@@ -463,15 +463,18 @@ __device__ __forceinline__ void laneFilter(const u32 (&w)[5], u32 tabAddr, u32 l
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if (KIND == FK_HASH32) {
+                /* entry (h & indexMask) has 2^repShift copies in adjacent words;
+                 * tabAddr already points at this lane's copy (bank partition) */
+                const u32 sh = 2 + repShift;
                 u32 off;
                 if (r == 0) {
-                    off = w[k] << 2;
+                    off = w[k] << sh;
                 } else if (r == 3) {
-                    off = __funnelshift_r(w[k], w[k + 1], 22);
+                    off = __funnelshift_r(w[k], w[k + 1], 24 - sh);
                 } else {
-                    off = w[k] >> (8 * r - 2);
+                    off = w[k] >> (8 * r - sh);
                 }
-                E0[k] = lds32(tabAddr + (off & (indexMask << 2)));
+                E0[k] = lds32(tabAddr + (off & (indexMask << sh)));
             } else {
                 const u32 idx = __byte_perm(w[k], 0, 0x4440 + r);
                 if (KIND == FK_BYTE32) {
@@ -593,7 +596,7 @@ __device__ __forceinline__ void scanStep(const ScanParams &p, const uint4 v, u32
     typedef Kind<KIND> K;
     const u32 w[5] = {v.x, v.y, v.z, v.w, w4};
     u32 a[2][6];
-    laneFilter<KIND, STRIDE, SB>(w, tabAddr, laneOff, p.indexMask, a);
+    laneFilter<KIND, STRIDE, SB>(w, tabAddr, laneOff, p.indexMask, p.repShift, a);
     u32 c[2][4];
     u32 any = 0;
 #pragma unroll
@@ -637,7 +640,7 @@ __device__ __forceinline__ void haloStep(const ScanParams &p, const uint4 v, u32
     typedef Kind<KIND> K;
     const u32 w[5] = {v.x, v.y, v.z, v.w, w4};
     u32 a[2][6];
-    laneFilter<KIND, STRIDE, SB>(w, tabAddr, laneOff, p.indexMask, a);
+    laneFilter<KIND, STRIDE, SB>(w, tabAddr, laneOff, p.indexMask, p.repShift, a);
 #pragma unroll
     for (int o = 0; o < K::NOCT; o++) {
 #pragma unroll
@@ -699,8 +702,9 @@ __global__ void __launch_bounds__(DIRECT ? 768 : 1024, 1) scanKernel(const ScanP
     }
     __syncthreads();
 
-    const u32 tabAddr = smemAddr(smem);
-    const u32 bitmapAddr = tabAddr + tab0;
+    const u32 bitmapAddr = smemAddr(smem) + tab0;
+    /* FK_HASH32: each lane reads its own copy of the table (lane & (R-1)) */
+    const u32 tabAddr = smemAddr(smem) + (KIND == FK_HASH32 ? (lane & ((1u << p.repShift) - 1)) * 4 : 0);
     const u32 laneOff = KIND == FK_BYTE64 ? (lane & 15) * 8 : lane * 4;
 
     /* this warp's contiguous run of tiles */

@@ -110,13 +110,13 @@ def test_block_boundaries_do_not_leak(hs, ref):
     _check_all(hs, ref, lits, [0, 0, 0], [1, 2, 3], data, off, ln)
 
 
-VARIANT_KEYS = ("stride", "wide_fdr", "prefilter", "rebuild", "domain", "direct")
-VARIANT_DEFAULTS = (1, 0, 1, 1, 0, 1)
+VARIANT_KEYS = ("stride", "wide_fdr", "prefilter", "rebuild", "domain", "direct", "replicas")
+VARIANT_DEFAULTS = (1, 0, 1, 1, 0, 1, 0)
 
 
-@pytest.mark.parametrize("variant", [(0, 0, 1, 0, 0, 0), (1, 1, 1, 1, 0, 1), (2, 0, 0, 1, 0, 0), (4, 1, 1, 0, 0, 1),
-                                     (1, 0, 0, 0, 0, 1), (1, 0, 1, 1, 11, 1), (2, 0, 1, 1, 15, 0),
-                                     (1, 0, 1, 1, 9, 0)])
+@pytest.mark.parametrize("variant", [(0, 0, 1, 0, 0, 0, 0), (1, 1, 1, 1, 0, 1, 0), (2, 0, 0, 1, 0, 0, 1),
+                                     (4, 1, 1, 0, 0, 1, 0), (1, 0, 0, 0, 0, 1, 0), (1, 0, 1, 1, 11, 1, 16),
+                                     (2, 0, 1, 1, 15, 0, 0), (1, 0, 1, 1, 9, 0, 2), (1, 0, 1, 1, 12, 1, 8)])
 def test_filter_variants_same_matches(hs, ref, variant):
     """Sampling stride, slot set, hash domain, staging mode and the prefilter only
     change the candidate set of the first stages, never the matches."""

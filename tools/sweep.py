@@ -14,11 +14,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hyperscan_b200 import capi, synth  # noqa: E402
 
-DEFAULT = ("direct=1;direct=0;direct=1,rebuild=0;direct=0,rebuild=0;direct=1,warps=16;direct=1,warps=20;"
-           "direct=1,tile_bytes=4096;direct=1,tile_bytes=16384;direct=1,domain=14;direct=1,domain=15;"
-           "direct=1,domain=12;direct=0,warps=24,tile_bytes=2048;direct=1,prefilter=0;direct=1,stride=2")
+DEFAULT = ("replicas=1;replicas=2;replicas=4;domain=12,replicas=8;domain=12,replicas=4;domain=11,replicas=16;"
+           "domain=14,replicas=2;domain=14,replicas=1;domain=10,replicas=16;domain=12,replicas=8,warps=20;"
+           "replicas=4,direct=0,warps=24,tile_bytes=1024;replicas=4,tile_bytes=4096")
 BASE = {"warps": 32, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1,
-        "rebuild": 1, "domain": 0, "direct": 1}
+        "rebuild": 1, "domain": 0, "direct": 1, "replicas": 0}
 
 
 def main():
