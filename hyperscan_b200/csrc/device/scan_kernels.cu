@@ -738,28 +738,41 @@ __global__ void __launch_bounds__(DIRECT ? 768 : 1024, 1) scanKernel(const ScanP
             }
             return make_uint4(0, 0, 0, 0);
         };
-        uint4 v0 = load(0), v1 = load(1), v2 = load(2);
+        /* DEPTH steps in flight; the step loop is unrolled DEPTH times so the
+         * ring of registers is addressed statically (rotating it with moves
+         * would make every iteration wait for the youngest load) */
+        constexpr int DEPTH = 3;
+        uint4 v[DEPTH];
+#pragma unroll
+        for (int i = 0; i < DEPTH; i++) {
+            v[i] = load(i);
+        }
         if (runStart != 0) {
             const uint4 hv = __ldg(reinterpret_cast<const uint4 *>(p.corpus + runStart - 16));
-            const u32 first = __shfl_sync(0xffffffffu, v0.x, 0);
+            const u32 first = __shfl_sync(0xffffffffu, v[0].x, 0);
             haloStep<KIND, STRIDE, SB>(p, hv, first, tabAddr, laneOff, carry);
         }
-        for (u32 step = 0; step < nsteps; step++) {
-            const uint4 v = v0;
-            v0 = v1;
-            v1 = v2;
-            v2 = load(step + 3);
-            u32 w4 = 0;
-            if (K::HASH) {
-                w4 = __shfl_down_sync(0xffffffffu, v.x, 1);
-                const u32 nx = __shfl_sync(0xffffffffu, v0.x, 0);
-                if (lane == 31) {
-                    w4 = nx;
+        for (u32 step0 = 0; step0 < nsteps; step0 += DEPTH) {
+#pragma unroll
+            for (int i = 0; i < DEPTH; i++) {
+                const u32 step = step0 + i;
+                if (step < nsteps) { /* warp-uniform */
+                    const uint4 cur = v[i];
+                    u32 w4 = 0;
+                    if (K::HASH) {
+                        w4 = __shfl_down_sync(0xffffffffu, cur.x, 1);
+                        const u32 nx = __shfl_sync(0xffffffffu, v[(i + 1) % DEPTH].x, 0);
+                        if (lane == 31) {
+                            w4 = nx;
+                        }
+                    }
+                    v[i] = load(step + DEPTH);
+                    const u64 g0 = lanePos + (u64)step * 512;
+                    scanStep<KIND, STRIDE, SB>(
+                        p, cur, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
+                        [&]() { return __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)); });
                 }
             }
-            const u64 g0 = lanePos + (u64)step * 512;
-            scanStep<KIND, STRIDE, SB>(p, v, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
-                                       [&]() { return __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)); });
         }
     } else {
         const u32 stepsPerTile = p.tileBytes >> 9;
