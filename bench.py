@@ -178,7 +178,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from hyperscan_b200 import capi
+    from hyperscan_b200 import capi, dist as hdist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the scan path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -212,19 +212,15 @@ def main():
             raise RuntimeError("scan failed %d" % rc)
         if world == 1:
             return n, None
-        cnt = torch.tensor([n], dtype=torch.int64, device=dev)
-        counts = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts, cnt)
-        mx = int(counts.max().item())
-        key = (mx + 4095) // 4096 * 4096
-        if key not in gather_buf:
-            gather_buf.clear()
-            gather_buf[key] = (torch.zeros(key * 2, dtype=torch.int64, device=dev),
-                               torch.empty(world * key * 2, dtype=torch.int64, device=dev))
-        mine, allr = gather_buf[key]
-        capi._check(capi.lib().hs_b200_copy_records(scratch.ptr, mine.data_ptr(), key))
-        dist.all_gather_into_tensor(allr, mine)
-        return n, (counts, allr, key)
+        # one exchange per scan: counts, then the raw 16-byte records (NCCL)
+        cap = (max(n, 1) + 4095) // 4096 * 4096
+        if gather_buf.get("cap", 0) < cap:
+            gather_buf["cap"] = cap
+            gather_buf["mine"] = torch.zeros((cap, 2), dtype=torch.int64, device=dev)
+        mine = gather_buf["mine"]
+        capi._check(capi.lib().hs_b200_copy_records(scratch.ptr, mine.data_ptr(), min(n, mine.shape[0])))
+        counts, gathered = hdist.all_gather_records(mine, n)
+        return n, (counts, gathered)
 
     for _ in range(W):
         step_resident()
@@ -267,9 +263,14 @@ def main():
         verify["verified_blocks"] = vb
         verify["bit_exact_vs_reference"] = bool(np.array_equal(np.sort(got, order=["block", "to", "id"]), want))
     if world > 1 and last is not None and rank == 0:
-        counts, allr, key = last
-        cs = counts.cpu().numpy()
-        verify["gathered_records"] = int(cs.sum())
+        counts, gathered = last
+        merged = hdist.merge_gathered(counts, gathered, [r * args.blocks for r in range(world)])
+        final = capi.postprocess_matches(db, merged)
+        verify["gathered_records"] = int(sum(counts))
+        verify["merged_matches_all_ranks"] = int(final.size)
+        mine = final[final["block"] < args.blocks]
+        verify["rank0_slice_equals_local_fetch"] = bool(np.array_equal(
+            mine, np.sort(matches, order=["block", "to", "id"])))
 
     # ---- e2e: host (pinned) buffers through the C ABI ----------------------------
     e2e = None

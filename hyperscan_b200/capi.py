@@ -115,7 +115,7 @@ def lib():
         L.hs_b200_scan_corpus_async.argtypes = [vp, vp, vp, vp]
         L.hs_b200_scan_corpus_finish.argtypes = [vp, u64p, C.POINTER(vp)]
         L.hs_b200_copy_records.argtypes = [vp, vp, C.c_size_t]
-        L.hs_b200_postprocess_matches.argtypes = [vp, vp, vp, C.c_size_t, u64p]
+        L.hs_b200_postprocess_matches.argtypes = [vp, vp, C.c_size_t, u64p]
         L.hs_b200_fetch_matches.argtypes = [vp, vp, vp, C.c_size_t, u64p]
         L.hs_b200_db_info.argtypes = [vp, C.POINTER(DbInfo)]
         L.hs_b200_set_build_option.argtypes = [cp, C.c_int]
@@ -387,10 +387,11 @@ def scan_corpus(db, corpus, scratch, fetch=True):
     raise HsError(HS_INSUFFICIENT_SPACE, "record ring")
 
 
-def postprocess_matches(db, scratch, recs):
-    recs = np.ascontiguousarray(recs, dtype=MATCH_DTYPE)
+def postprocess_matches(db, recs):
+    """Host-side report rules over raw records (no GPU needed)."""
+    recs = np.array(recs, dtype=MATCH_DTYPE, copy=True)
     n = C.c_ulonglong()
-    _check(lib().hs_b200_postprocess_matches(db.ptr, scratch.ptr, recs.ctypes.data, recs.size, C.byref(n)))
+    _check(lib().hs_b200_postprocess_matches(db.ptr, recs.ctypes.data, recs.size, C.byref(n)))
     return recs[: int(n.value)]
 
 

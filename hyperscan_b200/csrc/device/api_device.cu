@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../host/api_internal.h"
+#include "../host/db_walk.h"
 #include "kernels.h"
 
 using namespace hsb;
@@ -50,6 +51,7 @@ struct RuntimeOpts {
     int rebuild = 1;         /* rebuild the FDR first-stage table over slots 1..4 from the literals */
     int domain = 0;          /* rebuilt table: hash domain bits (0 = as compiled) */
     int direct = 1;          /* 1: corpus straight into registers; 0: TMA-staged tiles */
+    int pfDist = 8;          /* direct mode: L2 prefetch distance in 512-byte steps */
     int replicas = 0;        /* rebuilt table: copies per entry (0 = fill up to 128 KB, max 16) */
     int chunkMB = 32;        /* host->device pipeline granularity */
     int initialRing = 1 << 20;
@@ -68,7 +70,8 @@ void initOpts() {
         {"HSB200_CHUNK_MB", &g_opts.chunkMB},  {"HSB200_RING", &g_opts.initialRing},
         {"HSB200_STRIDE", &g_opts.stride},     {"HSB200_PREFILTER", &g_opts.prefilter},
         {"HSB200_REBUILD", &g_opts.rebuild},   {"HSB200_DOMAIN", &g_opts.domain},
-        {"HSB200_DIRECT", &g_opts.direct},     {"HSB200_REPLICAS", &g_opts.replicas}};
+        {"HSB200_DIRECT", &g_opts.direct},     {"HSB200_REPLICAS", &g_opts.replicas},
+        {"HSB200_PF_DIST", &g_opts.pfDist}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -99,84 +102,6 @@ struct DevImage {
     std::unordered_set<u32> exhaustible; /* report ids under HS_FLAG_SINGLEMATCH */
     size_t deviceBytes = 0;
 };
-
-void collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex) {
-    u32 pc = prog;
-    for (int guard = 0; guard < 4096 && pc < bcLen; guard++) {
-        const u8 code = bc[pc];
-        switch (code) {
-        case OP_END:
-        case OP_FINAL_REPORT:
-            return;
-        case OP_CHECK_GROUPS: pc += HSB_ROUNDUP(sizeof(InstrCheckGroups), 8); break;
-        case OP_CHECK_MASK: pc += HSB_ROUNDUP(sizeof(InstrCheckMask), 8); break;
-        case OP_CHECK_BYTE: pc += HSB_ROUNDUP(sizeof(InstrCheckByte), 8); break;
-        case OP_CHECK_MED_LIT:
-        case OP_CHECK_MED_LIT_NOCASE:
-        case OP_CHECK_LONG_LIT:
-        case OP_CHECK_LONG_LIT_NOCASE: pc += HSB_ROUNDUP(sizeof(InstrCheckLit), 8); break;
-        case OP_CHECK_EXHAUSTED: pc += HSB_ROUNDUP(sizeof(InstrCheckExhausted), 8); break;
-        case OP_DEDUPE: pc += HSB_ROUNDUP(sizeof(InstrDedupe), 8); break;
-        case OP_REPORT: pc += HSB_ROUNDUP(sizeof(InstrReport), 8); break;
-        case OP_REPORT_EXHAUST: {
-            InstrReportExhaust in;
-            memcpy(&in, bc + pc, sizeof(in));
-            ex->insert(in.onmatch);
-            pc += HSB_ROUNDUP(sizeof(InstrReportExhaust), 8);
-            break;
-        }
-        case OP_DEDUPE_AND_REPORT: pc += HSB_ROUNDUP(sizeof(InstrDedupeAndReport), 8); break;
-        case OP_SQUASH_GROUPS: pc += HSB_ROUNDUP(sizeof(InstrSquashGroups), 8); break;
-        case OP_CLEAR_WORK_DONE: pc += 8; break;
-        case OP_INCLUDED_JUMP: pc += HSB_ROUNDUP(sizeof(InstrIncludedJump), 8); break;
-        case OP_SET_EXHAUST: pc += HSB_ROUNDUP(sizeof(InstrSetExhaust), 8); break;
-        default:
-            return;
-        }
-    }
-}
-
-/* Walk the hash-confirm structures to enumerate literal programs
- * (src/fdr/fdr_confirm.h:36-94). */
-struct LitTail {
-    u64 v, msk;
-    u32 size;
-    u32 bucket;
-};
-
-void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
-                 std::unordered_set<u32> *ex, std::vector<LitTail> *tails) {
-    const u8 *confBase = bc + confOff;
-    for (u32 b = 0; b < nBuckets; b++) {
-        u32 cf;
-        memcpy(&cf, confBase + 4 * b, 4);
-        if (!cf) {
-            continue;
-        }
-        const u8 *fc = confBase + cf;
-        FDRConfirm h;
-        memcpy(&h, fc, sizeof(h));
-        const u32 n = 1u << h.nBits;
-        for (u32 c = 0; c < n; c++) {
-            u32 start;
-            memcpy(&start, fc + sizeof(FDRConfirm) + 4 * c, 4);
-            if (!start) {
-                continue;
-            }
-            const u8 *li = fc + start;
-            for (;;) {
-                LitInfo x;
-                memcpy(&x, li, sizeof(x));
-                collectProgramReports(bc, bcLen, x.id, ex);
-                tails->push_back({x.v, x.msk, x.size, b});
-                if (!x.next) {
-                    break;
-                }
-                li += sizeof(LitInfo);
-            }
-        }
-    }
-}
 
 #define CUDA_TRY(expr)                                                                     \
     do {                                                                                   \
@@ -671,7 +596,7 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     pl->cfg.grid = s->smCount;
     pl->cfg.warps = warps;
     pl->tileBytes = tile;
-    pl->nstages = stages;
+    pl->nstages = direct ? (u32)std::max(0, std::min(64, g_opts.pfDist)) : stages;
     return HS_SUCCESS;
 }
 
@@ -723,36 +648,8 @@ hs_error_t launchRange(hs_scratch *s, const DevImage *im, const hs_b200_corpus *
     return HS_SUCCESS;
 }
 
-/* Order records for delivery and apply the order-dependent report rules the
- * device skipped: one report per (block, id, to) (dedupe, src/report.h:55-119)
- * and, for HS_FLAG_SINGLEMATCH reports, only the first match per block
- * (exhaustion keys, src/report.h:121-147, program_runtime.c:464-481). */
 size_t postprocess(const DevImage *im, DevMatch *m, size_t n) {
-    std::sort(m, m + n, [](const DevMatch &a, const DevMatch &b) {
-        if (a.block != b.block) return a.block < b.block;
-        if (a.to != b.to) return a.to < b.to;
-        return a.id < b.id;
-    });
-    size_t w = 0;
-    std::unordered_set<u32> seen;
-    u32 curBlock = 0xffffffffu;
-    const bool anyEx = !im->exhaustible.empty();
-    for (size_t i = 0; i < n; i++) {
-        if (w && m[w - 1].block == m[i].block && m[w - 1].to == m[i].to && m[w - 1].id == m[i].id) {
-            continue;
-        }
-        if (anyEx) {
-            if (m[i].block != curBlock) {
-                curBlock = m[i].block;
-                seen.clear();
-            }
-            if (im->exhaustible.count(m[i].id) && !seen.insert(m[i].id).second) {
-                continue;
-            }
-        }
-        m[w++] = m[i];
-    }
-    return w;
+    return postprocessRecords(im->exhaustible, (MatchRec *)m, n);
 }
 
 hs_error_t finishScan(hs_scratch *s, u32 *count) {
@@ -877,7 +774,8 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"chunk_mb", &g_opts.chunkMB},  {"initial_ring", &g_opts.initialRing},
         {"stride", &g_opts.stride},     {"prefilter", &g_opts.prefilter},
         {"rebuild", &g_opts.rebuild},   {"domain", &g_opts.domain},
-        {"direct", &g_opts.direct},     {"replicas", &g_opts.replicas}};
+        {"direct", &g_opts.direct},     {"replicas", &g_opts.replicas},
+        {"pf_dist", &g_opts.pfDist}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;
@@ -1316,22 +1214,6 @@ hs_error_t hs_b200_copy_records(hs_scratch_t *scratch, void *d_dst, size_t cap) 
                                  cudaMemcpyDeviceToDevice, scratch->stream));
         CUDA_TRY(cudaStreamSynchronize(scratch->stream));
     }
-    return HS_SUCCESS;
-}
-
-hs_error_t hs_b200_postprocess_matches(const hs_database_t *db, hs_scratch_t *scratch,
-                                       hs_b200_match_t *recs, size_t n,
-                                       unsigned long long *nout) {
-    if (!scratch || !db || (n && !recs) || !nout) {
-        return HS_INVALID;
-    }
-    const DevImage *im = nullptr;
-    hs_error_t r = findImage(scratch, db, &im);
-    if (r != HS_SUCCESS) {
-        return r;
-    }
-    static_assert(sizeof(DevMatch) == sizeof(hs_b200_match_t), "record layout");
-    *nout = postprocess(im, (DevMatch *)recs, n);
     return HS_SUCCESS;
 }
 

@@ -733,46 +733,46 @@ __global__ void __launch_bounds__(DIRECT ? 768 : 1024, 1) scanKernel(const ScanP
         const u64 lanePos = runStart + lane * 16;
         auto load = [&](u32 step) -> uint4 {
             const u64 pos = lanePos + (u64)step * 512;
+            uint4 r = make_uint4(0, 0, 0, 0);
             if (pos + 16 <= p.readableEnd) {
-                return __ldcs(reinterpret_cast<const uint4 *>(base + (size_t)step * 512));
+                /* volatile: keeps the load where it is written (ptxas otherwise
+                 * sinks it next to its first use and the prefetch is lost) */
+                asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                             : "l"(base + (size_t)step * 512));
             }
-            return make_uint4(0, 0, 0, 0);
+            return r;
         };
-        /* DEPTH steps in flight; the step loop is unrolled DEPTH times so the
-         * ring of registers is addressed statically (rotating it with moves
-         * would make every iteration wait for the youngest load) */
-        constexpr int DEPTH = 3;
-        uint4 v[DEPTH];
-#pragma unroll
-        for (int i = 0; i < DEPTH; i++) {
-            v[i] = load(i);
-        }
+        /* two-level prefetch: lines are pulled into L2 `pfDist` steps ahead
+         * (4 lanes x 128 B per step), the register copy runs one step ahead and
+         * so only has to cover an L2 hit */
+        const u32 pfDist = p.nstages; /* direct mode: L2 prefetch distance in steps */
+        uint4 nxt = load(0);
         if (runStart != 0) {
             const uint4 hv = __ldg(reinterpret_cast<const uint4 *>(p.corpus + runStart - 16));
-            const u32 first = __shfl_sync(0xffffffffu, v[0].x, 0);
+            const u32 first = __shfl_sync(0xffffffffu, nxt.x, 0);
             haloStep<KIND, STRIDE, SB>(p, hv, first, tabAddr, laneOff, carry);
         }
-        for (u32 step0 = 0; step0 < nsteps; step0 += DEPTH) {
-#pragma unroll
-            for (int i = 0; i < DEPTH; i++) {
-                const u32 step = step0 + i;
-                if (step < nsteps) { /* warp-uniform */
-                    const uint4 cur = v[i];
-                    u32 w4 = 0;
-                    if (K::HASH) {
-                        w4 = __shfl_down_sync(0xffffffffu, cur.x, 1);
-                        const u32 nx = __shfl_sync(0xffffffffu, v[(i + 1) % DEPTH].x, 0);
-                        if (lane == 31) {
-                            w4 = nx;
-                        }
-                    }
-                    v[i] = load(step + DEPTH);
-                    const u64 g0 = lanePos + (u64)step * 512;
-                    scanStep<KIND, STRIDE, SB>(
-                        p, cur, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
-                        [&]() { return __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)); });
+        for (u32 step = 0; step < nsteps; step++) {
+            const uint4 cur = nxt;
+            nxt = load(step + 1);
+            if ((lane & 7) == 0) {
+                const u64 pos = lanePos + (u64)(step + pfDist) * 512;
+                if (pos < p.readableEnd) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.corpus + pos));
                 }
             }
+            u32 w4 = 0;
+            if (K::HASH) {
+                w4 = __shfl_down_sync(0xffffffffu, cur.x, 1);
+                const u32 nx = __shfl_sync(0xffffffffu, nxt.x, 0);
+                if (lane == 31) {
+                    w4 = nx;
+                }
+            }
+            const u64 g0 = lanePos + (u64)step * 512;
+            scanStep<KIND, STRIDE, SB>(p, cur, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
+                                       [&]() { return __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)); });
         }
     } else {
         const u32 stepsPerTile = p.tileBytes >> 9;

@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing for the sharded block scan: blocks
+shard by rank, the database is replicated, and the only exchange is one
+all-gather of per-rank match records at the end of a scan.
+
+Records travel as int64 pairs (the 16-byte hs_b200_match_t viewed as two
+little-endian words: word0 = id | block << 32, word1 = to).  Works on any
+torch.distributed backend: NCCL on the GPUs (bench.py), gloo on CPU (tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .capi import MATCH_DTYPE
+
+
+def records_to_words(recs):
+    """MATCH_DTYPE array -> int64 tensor [n, 2]."""
+    a = np.ascontiguousarray(recs, dtype=MATCH_DTYPE)
+    return torch.from_numpy(a.view(np.int64).reshape(-1, 2).copy())
+
+
+def words_to_records(words):
+    a = words.detach().cpu().contiguous().numpy().reshape(-1, 2)
+    return a.view(MATCH_DTYPE).reshape(-1)
+
+
+def all_gather_records(local_words, n_local, group=None, pad_to=4096):
+    """All-gather a variable number of records per rank.
+
+    local_words: int64 tensor [cap, 2] on the backend's device whose first
+    n_local rows are valid.  Returns (counts [world] python ints, gathered
+    int64 tensor [world, maxn, 2]); two collectives: counts, then records
+    padded to the max count rounded up to `pad_to` (buffers are reused across
+    steps by the caller when the rounded size is stable)."""
+    world = dist.get_world_size(group)
+    dev = local_words.device
+    cnt = torch.tensor([n_local], dtype=torch.int64, device=dev)
+    counts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, cnt, group=group)
+    counts_h = [int(x) for x in counts.cpu().tolist()]
+    maxn = max(max(counts_h), 1)
+    maxn = (maxn + pad_to - 1) // pad_to * pad_to
+    mine = torch.zeros((maxn, 2), dtype=torch.int64, device=dev)
+    k = min(n_local, local_words.shape[0])
+    mine[:k] = local_words[:k]
+    out = torch.empty((world, maxn, 2), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out.view(-1), mine.view(-1), group=group)
+    return counts_h, out
+
+
+def merge_gathered(counts, gathered, block_base):
+    """Concatenate every rank's valid records, renumbering rank-local block
+    indices into the global numbering (block_base[r] = first global block of
+    rank r).  Returns a MATCH_DTYPE array (unsorted)."""
+    parts = []
+    for r, n in enumerate(counts):
+        if n == 0:
+            continue
+        rec = words_to_records(gathered[r, :n]).copy()
+        rec["block"] += np.uint32(block_base[r])
+        parts.append(rec)
+    if not parts:
+        return np.zeros(0, dtype=MATCH_DTYPE)
+    return np.concatenate(parts)

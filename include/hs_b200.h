@@ -251,8 +251,9 @@ hs_error_t hs_b200_copy_records(hs_scratch_t *scratch, void *d_dst, size_t cap);
 /* Apply the host-side report rules to `n` raw records held in host memory
  * (in place; e.g. the concatenation of all ranks' records after the
  * all-gather): sort by (block, to, id), one record per (block, id, to),
- * HS_FLAG_SINGLEMATCH reports keep their first match per block. */
-hs_error_t hs_b200_postprocess_matches(const hs_database_t *db, hs_scratch_t *scratch,
+ * HS_FLAG_SINGLEMATCH reports keep their first match per block.  Host only
+ * (needs no CUDA device). */
+hs_error_t hs_b200_postprocess_matches(const hs_database_t *db,
                                        hs_b200_match_t *recs, size_t n,
                                        unsigned long long *nout);
 /* Copy the records of the last finished scan to the host, apply the

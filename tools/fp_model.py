@@ -193,3 +193,60 @@ def slots_experiment():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "slots":
     slots_experiment()
+
+
+def class_map(tails, nclass=32, slots=(1, 2, 3, 4)):
+    """byte -> class (nclass-1 = 'other': not in any literal)."""
+    freq = np.zeros(256, dtype=np.int64)
+    allb = np.arange(256, dtype=np.uint32)
+    for (b, v, msk, sz) in tails:
+        for p in set(slots) | {q - 1 for q in slots if q > 0}:
+            if p >= sz or p > 7:
+                continue
+            c = (v >> (8 * (7 - p))) & 0xff
+            m = (msk >> (8 * (7 - p))) & 0xff
+            freq[allb[(allb & m) == c]] += 1
+    used = np.nonzero(freq)[0]
+    order = used[np.argsort(-freq[used], kind="stable")]
+    cls = np.full(256, nclass - 1, dtype=np.uint32)
+    own = nclass - 1
+    if len(order) <= own:
+        for i, bb in enumerate(order):
+            cls[bb] = i
+    else:
+        shared = max(1, min(8, own // 4))
+        for i, bb in enumerate(order):
+            if i < own - shared:
+                cls[bb] = i
+            else:
+                cls[bb] = own - shared + (i % shared)
+    return cls
+
+
+def class_experiment():
+    lits, flags, ids = synth.literal_set(1000)
+    db = capi.compile_lit_multi(lits, flags, ids)
+    tails = tails_from_db(db)
+    data, off, ln, _ = synth.block_corpus(2048, 1024, lits, plant_per_kb=0.0)
+    lower = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz     eeeettaaooiinn", dtype=np.uint8)
+    text2 = lower[np.random.default_rng(5).integers(0, lower.size, size=data.size)]
+    mixed = np.frombuffer(b"abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789 .,;:-_/", dtype=np.uint8)
+    text3 = mixed[np.random.default_rng(6).integers(0, mixed.size, size=data.size)]
+    for nclass in (32,):
+        cls = class_map(tails, nclass)
+        print("classes used", len(set(cls.tolist())))
+        fn = lambda a, b: cls[a] | (cls[b] << 5)
+        for sl in ([1, 2, 3, 4], [0, 1, 2, 3]):
+            T = build_table_slots(tails, fn, 1 << 10, sl)
+            print("cls%d slots %s: printable %.3f/KB lowercase %.2f/KB mixed %.2f/KB" %
+                  (nclass, sl, cand_rate_slots(T, fn, data, sl), cand_rate_slots(T, fn, text2, sl),
+                   cand_rate_slots(T, fn, text3, sl)))
+    fn = lambda a, b: (a | (b << 8)) & 0x1fff
+    T = build_table_slots(tails, fn, 1 << 13, [1, 2, 3, 4])
+    print("fdr13 slots 1-4: printable %.3f lowercase %.2f mixed %.2f" % (
+        cand_rate_slots(T, fn, data, [1, 2, 3, 4]), cand_rate_slots(T, fn, text2, [1, 2, 3, 4]),
+        cand_rate_slots(T, fn, text3, [1, 2, 3, 4])))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "classes":
+    class_experiment()
