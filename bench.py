@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-sample-mb", type=int, default=64)
+    ap.add_argument("--cpu-sample-mb", type=int, default=1024)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--verify-blocks", type=int, default=4096)
     return ap.parse_args()
@@ -212,15 +212,25 @@ def main():
             raise RuntimeError("scan failed %d" % rc)
         if world == 1:
             return n, None
-        # one exchange per scan: counts, then the raw 16-byte records (NCCL)
-        cap = (max(n, 1) + 4095) // 4096 * 4096
-        if gather_buf.get("cap", 0) < cap:
-            gather_buf["cap"] = cap
-            gather_buf["mine"] = torch.zeros((cap, 2), dtype=torch.int64, device=dev)
-        mine = gather_buf["mine"]
-        capi._check(capi.lib().hs_b200_copy_records(scratch.ptr, mine.data_ptr(), min(n, mine.shape[0])))
-        counts, gathered = hdist.all_gather_records(mine, n)
-        return n, (counts, gathered)
+        # ONE exchange per scan: an all-gather of [count | raw 16-byte records]
+        # padded to a capacity that only grows (NCCL over NVLink)
+        while True:
+            cap = gather_buf.get("cap", 0)
+            if cap < n:
+                cap = (max(n, 1) * 5 // 4 + 4095) // 4096 * 4096
+                gather_buf["cap"] = cap
+                gather_buf["buf"] = torch.zeros((cap + 1, 2), dtype=torch.int64, device=dev)
+            buf = gather_buf["buf"]
+            capi._check(capi.lib().hs_b200_copy_records(scratch.ptr, buf[1:].data_ptr(), min(n, cap)))
+            res = hdist.all_gather_records_fused(buf, n)
+            if res is not None:
+                return n, res
+            gather_buf["cap"] = 0  # some rank overflowed: everyone regrows
+            n_all = torch.tensor([n], dtype=torch.int64, device=dev)
+            dist.all_reduce(n_all, op=dist.ReduceOp.MAX)
+            n_grow = int(n_all.item())
+            gather_buf["cap"] = (n_grow * 5 // 4 + 4095) // 4096 * 4096
+            gather_buf["buf"] = torch.zeros((gather_buf["cap"] + 1, 2), dtype=torch.int64, device=dev)
 
     for _ in range(W):
         step_resident()

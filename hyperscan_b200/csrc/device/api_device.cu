@@ -393,6 +393,7 @@ struct hs_b200_corpus {
     u32 *d_len = nullptr;
     size_t nblocks = 0;
     u32 uniformPitch = 0;
+    u32 uniformLen = 0;      /* all blocks equally long (and uniformPitch set): tables not needed */
     u64 payload = 0;         /* sum of block lengths */
     size_t capData = 0, capBlocks = 0; /* allocation sizes when reused */
 };
@@ -612,6 +613,7 @@ void fillParams(const hs_scratch *s, const DevImage *im, const hs_b200_corpus *c
     p->blockLen = c->d_len;
     p->nblocks = (u32)c->nblocks;
     p->uniformPitch = c->uniformPitch;
+    p->uniformLen = c->uniformLen;
     p->bc = im->d_bc;
     p->table = im->d_table;
     p->tableBytes = im->tableBytes;
@@ -983,7 +985,17 @@ static hs_error_t setBlocks(hs_b200_corpus *c, const u64 *packed, const unsigned
     c->bytes = total;
     c->payload = payload;
     c->uniformPitch = detectPitch(packed, lengths, nblocks);
-    if (nblocks) {
+    c->uniformLen = 0;
+    if (c->uniformPitch && nblocks) {
+        u32 l0 = lengths[0];
+        for (size_t i = 1; i < nblocks && l0; i++) {
+            if (lengths[i] != l0) {
+                l0 = 0;
+            }
+        }
+        c->uniformLen = l0;
+    }
+    if (nblocks && !c->uniformLen) {
         CUDA_TRY(cudaMemcpyAsync(c->d_off, packed, nblocks * sizeof(u64), cudaMemcpyHostToDevice, stream));
         CUDA_TRY(cudaMemcpyAsync(c->d_len, lengths, nblocks * sizeof(u32), cudaMemcpyHostToDevice, stream));
     }

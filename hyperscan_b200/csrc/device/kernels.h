@@ -54,6 +54,7 @@ struct ScanParams {
     const u32 *blockLen;
     u32 nblocks;
     u32 uniformPitch;      /* != 0: blockOff[i] == i * uniformPitch */
+    u32 uniformLen;        /* != 0 (with uniformPitch): every block has this length; no table reads */
     /* database image */
     const u8 *bc;          /* RoseEngine bytecode (device copy) */
     const u8 *table;       /* first-stage table in HBM (copied to smem) */

@@ -109,8 +109,15 @@ __device__ bool findBlock(const ScanParams &p, u64 g, BlockRef *out) {
     if (b >= p.nblocks) {
         return false;
     }
-    const u64 off = __ldg(p.blockOff + b);
-    const u32 len = __ldg(p.blockLen + b);
+    u64 off;
+    u32 len;
+    if (p.uniformPitch && p.uniformLen) { /* no table needed */
+        off = (u64)b * p.uniformPitch;
+        len = p.uniformLen;
+    } else {
+        off = __ldg(p.blockOff + b);
+        len = __ldg(p.blockLen + b);
+    }
     if (g < off || g - off >= len) {
         return false;
     }

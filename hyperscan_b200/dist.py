@@ -48,6 +48,21 @@ def all_gather_records(local_words, n_local, group=None, pad_to=4096):
     return counts_h, out
 
 
+def all_gather_records_fused(buf, n_local, group=None):
+    """One collective per scan: `buf` is an int64 tensor [cap + 1, 2] whose rows
+    1.. hold this rank's records; row 0 is set to (n_local, 0) here and travels
+    with them.  Returns (counts, gathered [world, cap, 2]) or None when some
+    rank's count exceeds cap (the caller grows `buf` on every rank and repeats)."""
+    world = dist.get_world_size(group)
+    buf[0, 0] = n_local
+    out = torch.empty((world,) + tuple(buf.shape), dtype=torch.int64, device=buf.device)
+    dist.all_gather_into_tensor(out.view(-1), buf.view(-1), group=group)
+    counts = [int(x) for x in out[:, 0, 0].cpu().tolist()]
+    if max(counts) > buf.shape[0] - 1:
+        return None
+    return counts, out[:, 1:, :]
+
+
 def merge_gathered(counts, gathered, block_base):
     """Concatenate every rank's valid records, renumbering rank-local block
     indices into the global numbering (block_base[r] = first global block of

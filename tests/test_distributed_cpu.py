@@ -46,6 +46,16 @@ def _worker(rank, world, port, q):
     counts, gathered = hd.all_gather_records(words, raw.size, pad_to=64)
     merged = hd.merge_gathered(counts, gathered, [r * nblocks for r in range(world)])
     final = capi.postprocess_matches(db, merged)
+    # the fused single-collective form (what bench.py uses over NCCL)
+    import torch
+    buf = torch.zeros((raw.size + 8 + 1, 2), dtype=torch.int64)
+    buf[1:raw.size + 1] = words
+    res = hd.all_gather_records_fused(buf, raw.size)
+    assert res is not None
+    merged2 = hd.merge_gathered(res[0], res[1], [r * nblocks for r in range(world)])
+    assert np.array_equal(capi.postprocess_matches(db, merged2), final)
+    small = torch.zeros((2, 2), dtype=torch.int64)
+    assert hd.all_gather_records_fused(small, raw.size) is None   # overflow is reported
     if rank == 0:
         want = ref.scan_sorted(db.ptr, data, off, ln)
         q.put((bool(np.array_equal(final, want)), int(final.size), counts))
