@@ -408,6 +408,7 @@ struct hs_scratch {
     cudaStream_t stream, copyStream;
     cudaStream_t activeStream; /* stream the pending scan was enqueued on */
     cudaEvent_t evStart, evStop;
+    cudaEvent_t evDone;       /* counters of the pending scan have landed on the host */
     std::vector<cudaEvent_t> *chunkEvents;
     std::vector<DevImage *> *images;
     DevMatch *d_out;
@@ -655,7 +656,9 @@ size_t postprocess(const DevImage *im, DevMatch *m, size_t n) {
 }
 
 hs_error_t finishScan(hs_scratch *s, u32 *count) {
-    cudaError_t e = cudaStreamSynchronize(s->activeStream ? s->activeStream : s->stream);
+    /* wait for THIS scan only: a later scan may already be queued behind it
+     * on the same stream (double-buffered callers) */
+    cudaError_t e = cudaEventSynchronize(s->evDone);
     s->pending = false;
     if (e != cudaSuccess) {
         return HS_UNKNOWN_ERROR;
@@ -687,6 +690,7 @@ hs_error_t enqueueScan(hs_scratch *s, const DevImage *im, const hs_b200_corpus *
     CUDA_TRY(cudaEventRecord(s->evStop, stream));
     CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, CTR_COUNT * sizeof(u32),
                              cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaEventRecord(s->evDone, stream));
     s->lastImage = im;
     s->lastCorpus = c;
     s->activeStream = stream;
@@ -845,6 +849,7 @@ static hs_error_t newScratch(hs_scratch **out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&s->evStart);
     if (e == cudaSuccess) e = cudaEventCreate(&s->evStop);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->evDone, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, CTR_COUNT * sizeof(u32));
     if (e == cudaSuccess) e = cudaMallocHost(&s->h_counters, CTR_COUNT * sizeof(u32));
     if (e == cudaSuccess) {
@@ -971,6 +976,7 @@ hs_error_t hs_free_scratch(hs_scratch_t *s) {
     if (s->h_stage) cudaFreeHost(s->h_stage);
     if (s->evStart) cudaEventDestroy(s->evStart);
     if (s->evStop) cudaEventDestroy(s->evStop);
+    if (s->evDone) cudaEventDestroy(s->evDone);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copyStream) cudaStreamDestroy(s->copyStream);
     g_scratch_free(s->alloc_base);
@@ -1222,9 +1228,12 @@ hs_error_t hs_b200_copy_records(hs_scratch_t *scratch, void *d_dst, size_t cap) 
     }
     const size_t n = std::min<size_t>(cap, std::min<u32>(scratch->lastCount, scratch->outCap));
     if (n) {
+        /* the records are final once evDone fired (finish waited for it); use
+         * the copy stream so a scan queued behind on the scan stream is not
+         * waited for */
         CUDA_TRY(cudaMemcpyAsync(d_dst, scratch->d_out, n * sizeof(DevMatch),
-                                 cudaMemcpyDeviceToDevice, scratch->stream));
-        CUDA_TRY(cudaStreamSynchronize(scratch->stream));
+                                 cudaMemcpyDeviceToDevice, scratch->copyStream));
+        CUDA_TRY(cudaStreamSynchronize(scratch->copyStream));
     }
     return HS_SUCCESS;
 }
@@ -1244,8 +1253,8 @@ hs_error_t hs_b200_fetch_matches(const hs_database_t *db, hs_scratch_t *scratch,
     std::vector<DevMatch> tmp(n);
     if (n) {
         CUDA_TRY(cudaMemcpyAsync(tmp.data(), scratch->d_out, (size_t)n * sizeof(DevMatch),
-                                 cudaMemcpyDeviceToHost, scratch->stream));
-        CUDA_TRY(cudaStreamSynchronize(scratch->stream));
+                                 cudaMemcpyDeviceToHost, scratch->copyStream));
+        CUDA_TRY(cudaStreamSynchronize(scratch->copyStream));
     }
     const size_t m = postprocess(im, tmp.data(), n);
     if (nmatches) {
@@ -1344,6 +1353,7 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
         CUDA_TRY(cudaEventRecord(s->evStop, s->stream));
         CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, CTR_COUNT * sizeof(u32),
                                  cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaEventRecord(s->evDone, s->stream));
         s->lastImage = im;
         s->lastCorpus = c;
         s->activeStream = s->stream;
