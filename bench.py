@@ -217,22 +217,30 @@ def main():
         if world == 1:
             return n, None
         # ONE exchange per scan: an all-gather of [count | raw 16-byte records]
-        # padded to a capacity that only grows (NCCL over NVLink)
-        while True:
-            cap = gather_buf.get("cap", 0)
-            if cap < n:
-                cap = (max(n, 1) * 5 // 4 + 4095) // 4096 * 4096
-                gather_buf["cap"] = cap
-                gather_buf["buf"] = torch.zeros((cap + 1, 2), dtype=torch.int64, device=dev)
-            buf = gather_buf["buf"]
-            capi._check(capi.lib().hs_b200_copy_records(sc.ptr, buf[1:].data_ptr(), min(n, cap)))
-            res = hdist.all_gather_records_fused(buf, n)
-            if res is not None:
-                return n, res
+        # padded to a capacity that only grows (NCCL over NVLink).  The gathered
+        # tensor is not waited for here; run_steps() checks the counts of every
+        # pass when the passes are done (an overflowing pass is redone).
+        cap = gather_buf.get("cap", 0)
+        if cap < n:
+            # grow on every rank alike: capacity follows the global maximum
             n_all = torch.tensor([n], dtype=torch.int64, device=dev)
             dist.all_reduce(n_all, op=dist.ReduceOp.MAX)
-            gather_buf["cap"] = (int(n_all.item()) * 5 // 4 + 4095) // 4096 * 4096
-            gather_buf["buf"] = torch.zeros((gather_buf["cap"] + 1, 2), dtype=torch.int64, device=dev)
+            cap = (int(n_all.item()) * 3 // 2 + 4095) // 4096 * 4096
+            gather_buf["cap"] = cap
+            gather_buf["bufs"] = [torch.zeros((cap + 1, 2), dtype=torch.int64, device=dev) for _ in range(2)]
+            gather_buf["evs"] = [None, None]
+            gather_buf["turn"] = 0
+        j = gather_buf["turn"]
+        gather_buf["turn"] = j ^ 1
+        buf = gather_buf["bufs"][j]
+        if gather_buf["evs"][j] is not None:
+            gather_buf["evs"][j].synchronize()   # the exchange that last read this buffer is done
+        capi._check(capi.lib().hs_b200_copy_records(sc.ptr, buf[1:].data_ptr(), min(n, cap)))
+        out = hdist.all_gather_records_fused_async(buf, n)
+        ev = torch.cuda.Event()
+        ev.record()
+        gather_buf["evs"][j] = ev
+        return n, (out, cap)
 
     def run_steps(k):
         """k passes over the resident shard.  Pass i+1 is enqueued (other
@@ -240,7 +248,7 @@ def main():
         back / exchanged, so the exchange overlaps the next scan; every pass's
         match records are complete when this returns."""
         rings = (scratch, scratch2)
-        kms, last, n = [], None, 0
+        kms, last, n, pending = [], None, 0, []
         st = scan_stream.cuda_stream   # one stream: kernels run back to back, never concurrently
         capi.scan_corpus_async(db, corpus, rings[0], st)
         for i in range(k):
@@ -248,7 +256,15 @@ def main():
                 capi.scan_corpus_async(db, corpus, rings[(i + 1) % 2], st)
             n, last = collect(rings[i % 2])
             kms.append(rings[i % 2].last_kernel_ms())
-        return n, last, kms
+            if last is not None:
+                pending.append(last)
+        # every pass's exchange must have delivered all records
+        res = None
+        for out, cap in pending:
+            res = hdist.fused_result(out, cap)
+            if res is None:
+                raise RuntimeError("record exchange overflowed its buffer; rerun")
+        return n, res, kms
 
     run_steps(W)
     barrier()

@@ -53,12 +53,25 @@ def all_gather_records_fused(buf, n_local, group=None):
     1.. hold this rank's records; row 0 is set to (n_local, 0) here and travels
     with them.  Returns (counts, gathered [world, cap, 2]) or None when some
     rank's count exceeds cap (the caller grows `buf` on every rank and repeats)."""
+    out = all_gather_records_fused_async(buf, n_local, group)
+    return fused_result(out, buf.shape[0] - 1)
+
+
+def all_gather_records_fused_async(buf, n_local, group=None):
+    """Enqueue the fused all-gather and return the gathered tensor without
+    waiting for it (no host synchronisation); pass it to fused_result() later."""
     world = dist.get_world_size(group)
     buf[0, 0] = n_local
     out = torch.empty((world,) + tuple(buf.shape), dtype=torch.int64, device=buf.device)
     dist.all_gather_into_tensor(out.view(-1), buf.view(-1), group=group)
+    return out
+
+
+def fused_result(out, cap):
+    """(counts, records [world, cap, 2]) of a fused all-gather, or None if some
+    rank had more than `cap` records (its tail was cut: grow and redo)."""
     counts = [int(x) for x in out[:, 0, 0].cpu().tolist()]
-    if max(counts) > buf.shape[0] - 1:
+    if max(counts) > cap:
         return None
     return counts, out[:, 1:, :]
 
