@@ -127,8 +127,9 @@ def cpu_reference_run(db, data, off, ln, sample_mb, seconds, threads=None):
     nblk = max(1, min(len(off), (sample_mb << 20) // max(1, int(ln[0]))))
     o, l = off[:nblk], ln[:nblk]
     sample_bytes = int(l.sum())
-    t1, _, _ = ref.bench_blocks(db.ptr, data, o, l, threads, 1)
-    reps = max(1, int(seconds / max(t1, 1e-4)))
+    ref.bench_blocks(db.ptr, data, o, l, threads, 1)            # warm (threads, page cache)
+    t3, _, _ = ref.bench_blocks(db.ptr, data, o, l, threads, 3)
+    reps = max(1, min(2000, int(seconds / max(t3 / 3, 1e-4))))
     t, m, b = ref.bench_blocks(db.ptr, data, o, l, threads, reps)
     # hsbench runs every thread over the whole corpus; ref_driver splits the
     # blocks across threads, so `b` is the bytes all threads scanned
