@@ -243,6 +243,8 @@ def main():
         gather_buf["evs"][j] = ev
         return n, (out, cap)
 
+    phase = {}
+
     def run_steps(k):
         """k passes over the resident shard.  Pass i+1 is enqueued (other
         scratch, own stream and record ring) before pass i's records are read
@@ -255,16 +257,20 @@ def main():
         for i in range(k):
             if i + 1 < k:
                 capi.scan_corpus_async(db, corpus, rings[(i + 1) % 2], st)
+            tc = time.perf_counter()
             n, last = collect(rings[i % 2])
+            phase["collect_s"] = phase.get("collect_s", 0.0) + time.perf_counter() - tc
             kms.append(rings[i % 2].last_kernel_ms())
             if last is not None:
                 pending.append(last)
         # every pass's exchange must have delivered all records
         res = None
+        tc = time.perf_counter()
         for out, cap in pending:
             res = hdist.fused_result(out, cap)
             if res is None:
                 raise RuntimeError("record exchange overflowed its buffer; rerun")
+        phase["drain_s"] = phase.get("drain_s", 0.0) + time.perf_counter() - tc
         return n, res, kms
 
     run_steps(W)
@@ -274,9 +280,14 @@ def main():
     t0w = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
+    phase.clear()
     n, last, kernel_ms = run_steps(K)
+    t_run = time.perf_counter() - t0
     barrier()
     dt = time.perf_counter() - t0
+    print("[bench rank %d] run %.3f ms, with barrier %.3f ms, collect %.3f ms, drain %.3f ms, kernel sum %.3f ms"
+          % (rank, t_run * 1e3, dt * 1e3, phase.get("collect_s", 0) * 1e3, phase.get("drain_s", 0) * 1e3,
+             sum(kernel_ms)), file=sys.stderr, flush=True)
     t1w = time.time()
     launches = capi.launch_count() - launches0
     clocks = sampler.stop(t0w, t1w) if sampler else None
