@@ -207,71 +207,64 @@ def main():
 
     gather_buf = {}
 
-    def collect(sc):
-        """finish the scan enqueued on scratch `sc`; N>1: all-gather the raw records"""
-        rc, n, _ = capi.scan_corpus_finish(sc)
-        if rc == capi.HS_INSUFFICIENT_SPACE:   # ring grew: run this pass again
-            capi.scan_corpus_async(db, corpus, sc)
-            rc, n, _ = capi.scan_corpus_finish(sc)
-        if rc != capi.HS_SUCCESS:
-            raise RuntimeError("scan failed %d" % rc)
-        if world == 1:
-            return n, None
-        # ONE exchange per scan: an all-gather of [count | raw 16-byte records]
-        # padded to a capacity that only grows (NCCL over NVLink).  The gathered
-        # tensor is not waited for here; run_steps() checks the counts of every
-        # pass when the passes are done (an overflowing pass is redone).
-        cap = gather_buf.get("cap", 0)
-        if cap < n:
-            # grow on every rank alike: capacity follows the global maximum
-            n_all = torch.tensor([n], dtype=torch.int64, device=dev)
-            dist.all_reduce(n_all, op=dist.ReduceOp.MAX)
-            cap = (int(n_all.item()) * 3 // 2 + 4095) // 4096 * 4096
-            gather_buf["cap"] = cap
-            gather_buf["bufs"] = [torch.zeros((cap + 1, 2), dtype=torch.int64, device=dev) for _ in range(2)]
-            gather_buf["evs"] = [None, None]
-            gather_buf["turn"] = 0
-        j = gather_buf["turn"]
-        gather_buf["turn"] = j ^ 1
-        buf = gather_buf["bufs"][j]
-        if gather_buf["evs"][j] is not None:
-            gather_buf["evs"][j].synchronize()   # the exchange that last read this buffer is done
-        capi._check(capi.lib().hs_b200_copy_records(sc.ptr, buf[1:].data_ptr(), min(n, cap)))
-        out = hdist.all_gather_records_fused_async(buf, n)
-        ev = torch.cuda.Event()
-        ev.record()
-        gather_buf["evs"][j] = ev
-        return n, (out, cap)
-
     phase = {}
 
     def run_steps(k):
-        """k passes over the resident shard.  Pass i+1 is enqueued (other
-        scratch, own stream and record ring) before pass i's records are read
-        back / exchanged, so the exchange overlaps the next scan; every pass's
-        match records are complete when this returns."""
+        """k passes over the resident shard, all stream-ordered on ONE stream:
+        scan kernel -> D2D of [count | raw 16-byte records] -> (N>1) one NCCL
+        all-gather -> next scan.  The host only enqueues (it runs up to two
+        passes ahead, two scratches = two record rings) and reads results back
+        when the passes are done; every pass's records are complete and
+        exchanged when this returns."""
         rings = (scratch, scratch2)
-        kms, last, n, pending = [], None, 0, []
-        st = scan_stream.cuda_stream   # one stream: kernels run back to back, never concurrently
-        capi.scan_corpus_async(db, corpus, rings[0], st)
-        for i in range(k):
-            if i + 1 < k:
-                capi.scan_corpus_async(db, corpus, rings[(i + 1) % 2], st)
-            tc = time.perf_counter()
-            n, last = collect(rings[i % 2])
-            phase["collect_s"] = phase.get("collect_s", 0.0) + time.perf_counter() - tc
-            kms.append(rings[i % 2].last_kernel_ms())
-            if last is not None:
-                pending.append(last)
-        # every pass's exchange must have delivered all records
-        res = None
+        st = scan_stream.cuda_stream
+        kms, outs, n = [], [], 0
+
+        def retire(sc):
+            rc, cnt, _ = capi.scan_corpus_finish(sc)
+            if rc != capi.HS_SUCCESS:   # incl. a record ring that had to grow
+                raise RuntimeError("scan failed %d (rerun)" % rc)
+            kms.append(sc.last_kernel_ms())
+            return cnt
+
         tc = time.perf_counter()
-        for out, cap in pending:
-            res = hdist.fused_result(out, cap)
+        with torch.cuda.stream(scan_stream):
+            for i in range(k):
+                sc = rings[i % 2]
+                if i >= 2:
+                    n = retire(sc)          # pass i-2 used this scratch
+                capi.scan_corpus_async(db, corpus, sc, st)
+                if world > 1:
+                    buf = gather_buf["bufs"][i % 2]
+                    capi._check(capi.lib().hs_b200_export_records_async(
+                        sc.ptr, buf[1:].data_ptr(), gather_buf["cap"], buf[0:1].data_ptr(), st))
+                    out = torch.empty((world,) + tuple(buf.shape), dtype=torch.int64, device=dev)
+                    dist.all_gather_into_tensor(out.view(-1), buf.view(-1))
+                    outs.append(out)
+            for i in range(max(0, k - 2), k):
+                n = retire(rings[i % 2])
+        phase["enqueue_s"] = time.perf_counter() - tc
+        scan_stream.synchronize()
+        res = None
+        for out in outs:                    # every pass's exchange delivered every record
+            res = hdist.fused_result(out, gather_buf["cap"])
             if res is None:
-                raise RuntimeError("record exchange overflowed its buffer; rerun")
-        phase["drain_s"] = phase.get("drain_s", 0.0) + time.perf_counter() - tc
+                raise RuntimeError("record exchange overflowed its buffer (cap %d)" % gather_buf["cap"])
         return n, res, kms
+
+    if world > 1:
+        # capacity of the exchange buffers: from one unpipelined pass, with headroom, same on all ranks
+        capi.scan_corpus_async(db, corpus, scratch)
+        rc, n0, _ = capi.scan_corpus_finish(scratch)
+        if rc == capi.HS_INSUFFICIENT_SPACE:
+            capi.scan_corpus_async(db, corpus, scratch)
+            rc, n0, _ = capi.scan_corpus_finish(scratch)
+        capi._check(rc, "first pass")
+        n_all = torch.tensor([n0], dtype=torch.int64, device=dev)
+        dist.all_reduce(n_all, op=dist.ReduceOp.MAX)
+        cap = (int(n_all.item()) * 3 // 2 + 4095) // 4096 * 4096
+        gather_buf["cap"] = cap
+        gather_buf["bufs"] = [torch.zeros((cap + 1, 2), dtype=torch.int64, device=dev) for _ in range(2)]
 
     run_steps(W)
     barrier()
@@ -285,9 +278,9 @@ def main():
     t_run = time.perf_counter() - t0
     barrier()
     dt = time.perf_counter() - t0
-    print("[bench rank %d] run %.3f ms, with barrier %.3f ms, collect %.3f ms, drain %.3f ms, kernel sum %.3f ms"
-          % (rank, t_run * 1e3, dt * 1e3, phase.get("collect_s", 0) * 1e3, phase.get("drain_s", 0) * 1e3,
-             sum(kernel_ms)), file=sys.stderr, flush=True)
+    print("[bench rank %d] run %.3f ms, with barrier %.3f ms, host enqueue %.3f ms, kernel sum %.3f ms"
+          % (rank, t_run * 1e3, dt * 1e3, phase.get("enqueue_s", 0) * 1e3, sum(kernel_ms)),
+          file=sys.stderr, flush=True)
     t1w = time.time()
     launches = capi.launch_count() - launches0
     clocks = sampler.stop(t0w, t1w) if sampler else None

@@ -115,6 +115,7 @@ def lib():
         L.hs_b200_scan_corpus_async.argtypes = [vp, vp, vp, vp]
         L.hs_b200_scan_corpus_finish.argtypes = [vp, u64p, C.POINTER(vp)]
         L.hs_b200_copy_records.argtypes = [vp, vp, C.c_size_t]
+        L.hs_b200_export_records_async.argtypes = [vp, vp, C.c_size_t, vp, vp]
         L.hs_b200_postprocess_matches.argtypes = [vp, vp, C.c_size_t, u64p]
         L.hs_b200_fetch_matches.argtypes = [vp, vp, vp, C.c_size_t, u64p]
         L.hs_b200_db_info.argtypes = [vp, C.POINTER(DbInfo)]

@@ -1223,6 +1223,21 @@ hs_error_t hs_b200_scan_corpus_finish(hs_scratch_t *scratch, unsigned long long 
     return HS_SUCCESS;
 }
 
+hs_error_t hs_b200_export_records_async(hs_scratch_t *scratch, void *d_dst, size_t cap,
+                                        void *d_count, void *cuda_stream) {
+    if (!scratch || !d_dst || !d_count || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : scratch->stream;
+    const size_t n = std::min<size_t>(cap, scratch->outCap);
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(d_dst, scratch->d_out, n * sizeof(DevMatch), cudaMemcpyDeviceToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_count, scratch->d_counters + CTR_MATCHES, sizeof(u32),
+                             cudaMemcpyDeviceToDevice, st));
+    return HS_SUCCESS;
+}
+
 hs_error_t hs_b200_copy_records(hs_scratch_t *scratch, void *d_dst, size_t cap) {
     if (!scratch || !d_dst || scratch->pending) {
         return HS_INVALID;

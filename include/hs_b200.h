@@ -248,6 +248,13 @@ hs_error_t hs_b200_scan_corpus_finish(hs_scratch_t *scratch,
 /* Copy up to `cap` raw records of the last finished scan into another device
  * buffer (e.g. a torch tensor that is then all-gathered over NCCL). */
 hs_error_t hs_b200_copy_records(hs_scratch_t *scratch, void *d_dst, size_t cap);
+/* Stream-ordered form for pipelines that never touch the host between a scan
+ * and the exchange of its records: enqueue, on `cuda_stream` (the stream the
+ * scan was enqueued on), a device-to-device copy of the first `cap` slots of
+ * the record ring into d_dst and of the 32-bit record count into *d_count
+ * (low word of a zeroed 64-bit slot).  Slots beyond the count hold stale data. */
+hs_error_t hs_b200_export_records_async(hs_scratch_t *scratch, void *d_dst, size_t cap,
+                                        void *d_count, void *cuda_stream);
 /* Apply the host-side report rules to `n` raw records held in host memory
  * (in place; e.g. the concatenation of all ranks' records after the
  * all-gather): sort by (block, to, id), one record per (block, id, to),
