@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-sample-mb", type=int, default=1024)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--verify-blocks", type=int, default=4096)
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: p2p = records stored into every rank's buffer by the scan kernel itself over "
+                         "NVLink peer memory; nccl = one all-gather per pass")
     return ap.parse_args()
 
 
@@ -206,6 +209,7 @@ def main():
         torch.cuda.synchronize()
 
     gather_buf = {}
+    peerx = None
 
     phase = {}
 
@@ -234,7 +238,7 @@ def main():
                 if i >= 2:
                     n = retire(sc)          # pass i-2 used this scratch
                 capi.scan_corpus_async(db, corpus, sc, st)
-                if world > 1:
+                if world > 1 and peerx is None:
                     buf = gather_buf["bufs"][i % 2]
                     capi._check(capi.lib().hs_b200_export_records_async(
                         sc.ptr, buf[1:].data_ptr(), gather_buf["cap"], buf[0:1].data_ptr(), st))
@@ -265,6 +269,21 @@ def main():
         cap = (int(n_all.item()) * 3 // 2 + 4095) // 4096 * 4096
         gather_buf["cap"] = cap
         gather_buf["bufs"] = [torch.zeros((cap + 1, 2), dtype=torch.int64, device=dev) for _ in range(2)]
+        if args.exchange == "p2p":
+            try:
+                peerx = hdist.PeerExchange(cap)
+                for sc in (scratch, scratch2):
+                    peerx.attach(sc, rank * args.blocks)
+            except Exception as e:   # no peer access on this box: fall back to the collective
+                print("[bench rank %d] peer exchange unavailable (%s): using NCCL all-gather" % (rank, e),
+                      file=sys.stderr, flush=True)
+                peerx = None
+            ok = torch.tensor([1 if peerx is not None else 0], dtype=torch.int64, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0 and peerx is not None:
+                for sc in (scratch, scratch2):
+                    peerx.detach(sc)
+                peerx = None
 
     run_steps(W)
     barrier()
@@ -306,15 +325,23 @@ def main():
         got = matches[matches["block"] < vb]
         verify["verified_blocks"] = vb
         verify["bit_exact_vs_reference"] = bool(np.array_equal(np.sort(got, order=["block", "to", "id"]), want))
-    if world > 1 and last is not None and rank == 0:
-        counts, gathered = last
-        merged = hdist.merge_gathered(counts, gathered, [r * args.blocks for r in range(world)])
-        final = capi.postprocess_matches(db, merged)
-        verify["gathered_records"] = int(sum(counts))
-        verify["merged_matches_all_ranks"] = int(final.size)
-        mine = final[final["block"] < args.blocks]
-        verify["rank0_slice_equals_local_fetch"] = bool(np.array_equal(
-            mine, np.sort(matches, order=["block", "to", "id"])))
+    if world > 1:
+        verify["exchange"] = "p2p: scan kernel stores records into every rank's buffer over NVLink" \
+            if peerx is not None else "nccl all_gather_into_tensor per pass"
+        barrier()   # every rank's last pass (and its peer stores) has completed
+        if rank == 0:
+            if peerx is not None:
+                counts, merged = peerx.read()
+            else:
+                counts, gathered = last
+                merged = hdist.merge_gathered(counts, gathered, [r * args.blocks for r in range(world)])
+            final = capi.postprocess_matches(db, merged)
+            verify["gathered_records"] = int(sum(counts))
+            verify["merged_matches_all_ranks"] = int(final.size)
+            mine = final[final["block"] < args.blocks]
+            verify["rank0_slice_equals_local_fetch"] = bool(np.array_equal(
+                mine, np.sort(matches, order=["block", "to", "id"])))
+            verify["ranks_with_records"] = int(sum(1 for c in counts if c > 0))
 
     # ---- e2e: host (pinned) buffers through the C ABI ----------------------------
     e2e = None

@@ -116,6 +116,11 @@ def lib():
         L.hs_b200_scan_corpus_finish.argtypes = [vp, u64p, C.POINTER(vp)]
         L.hs_b200_copy_records.argtypes = [vp, vp, C.c_size_t]
         L.hs_b200_export_records_async.argtypes = [vp, vp, C.c_size_t, vp, vp]
+        L.hs_b200_peer_buffer_alloc.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+        L.hs_b200_peer_buffer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+        L.hs_b200_peer_buffer_close.argtypes = [vp, C.c_int]
+        L.hs_b200_peer_buffer_read.argtypes = [vp, vp, C.c_size_t]
+        L.hs_b200_set_peer_exchange.argtypes = [vp, C.c_uint, C.c_uint, C.POINTER(vp), C.c_size_t, C.c_uint]
         L.hs_b200_postprocess_matches.argtypes = [vp, vp, C.c_size_t, u64p]
         L.hs_b200_fetch_matches.argtypes = [vp, vp, vp, C.c_size_t, u64p]
         L.hs_b200_db_info.argtypes = [vp, C.POINTER(DbInfo)]

@@ -422,6 +422,9 @@ struct hs_scratch {
     std::vector<u64> *tmpOff;
     const DevImage *lastImage;
     const hs_b200_corpus *lastCorpus;
+    /* fused exchange over peer memory (hs_b200_set_peer_exchange) */
+    u32 nPeers, myRank, peerCap, blockBase;
+    DevMatch *peers[MAX_PEERS];
     bool pending;
     u32 lastCount;
     float lastMs;
@@ -632,6 +635,13 @@ void fillParams(const hs_scratch *s, const DevImage *im, const hs_b200_corpus *c
     p->out = s->d_out;
     p->outCap = s->outCap;
     p->counters = s->d_counters;
+    p->nPeers = s->nPeers;
+    p->myRank = s->myRank;
+    p->peerCap = s->peerCap;
+    p->blockBase = s->blockBase;
+    for (u32 r = 0; r < s->nPeers; r++) {
+        p->peers[r] = s->peers[r];
+    }
 }
 
 /* Launch over tiles [t0, t1) of the corpus on `stream`. */
@@ -689,6 +699,12 @@ hs_error_t enqueueScan(hs_scratch *s, const DevImage *im, const hs_b200_corpus *
         return r;
     }
     CUDA_TRY(cudaEventRecord(s->evStop, stream));
+    if (s->nPeers) {
+        ScanParams pp;
+        fillParams(s, im, c, pl, &pp);
+        CUDA_TRY(launchPublishCount(pp, stream));
+        g_launches++;
+    }
     CUDA_TRY(cudaMemcpyAsync(s->h_counters, s->d_counters, CTR_COUNT * sizeof(u32),
                              cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaEventRecord(s->evDone, stream));
@@ -1219,6 +1235,76 @@ hs_error_t hs_b200_scan_corpus_finish(hs_scratch_t *scratch, unsigned long long 
             return r;
         }
         return HS_INSUFFICIENT_SPACE;
+    }
+    return HS_SUCCESS;
+}
+
+/* ---- fused exchange over NVLink peer memory ----------------------------------- */
+
+hs_error_t hs_b200_peer_buffer_alloc(size_t bytes, void **d_ptr, unsigned char handle[64]) {
+    if (!d_ptr || !handle || !bytes) {
+        return HS_INVALID;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return HS_UNKNOWN_ERROR;
+    }
+    memcpy(handle, &h, 64);
+    *d_ptr = p;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_peer_buffer_open(const unsigned char handle[64], void **d_ptr) {
+    if (!handle || !d_ptr) {
+        return HS_INVALID;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        return HS_UNKNOWN_ERROR;
+    }
+    *d_ptr = p;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_peer_buffer_read(const void *d_ptr, void *host_dst, size_t bytes) {
+    if (!d_ptr || !host_dst) {
+        return HS_INVALID;
+    }
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(host_dst, d_ptr, bytes, cudaMemcpyDeviceToHost));
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_peer_buffer_close(void *d_ptr, int opened) {
+    if (!d_ptr) {
+        return HS_SUCCESS;
+    }
+    cudaError_t e = opened ? cudaIpcCloseMemHandle(d_ptr) : cudaFree(d_ptr);
+    return e == cudaSuccess ? HS_SUCCESS : HS_UNKNOWN_ERROR;
+}
+
+hs_error_t hs_b200_set_peer_exchange(hs_scratch_t *scratch, unsigned int nranks, unsigned int my_rank,
+                                     void *const *peer_bases, size_t cap_per_rank,
+                                     unsigned int block_base) {
+    if (!scratch || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC || nranks > MAX_PEERS ||
+        (nranks && (!peer_bases || my_rank >= nranks || cap_per_rank == 0 || cap_per_rank > 0xfffffff0u))) {
+        return HS_INVALID;
+    }
+    scratch->nPeers = nranks;
+    scratch->myRank = my_rank;
+    scratch->peerCap = (u32)cap_per_rank;
+    scratch->blockBase = block_base;
+    for (unsigned r = 0; r < nranks; r++) {
+        scratch->peers[r] = (DevMatch *)peer_bases[r];
     }
     return HS_SUCCESS;
 }

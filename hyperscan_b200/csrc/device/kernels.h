@@ -36,6 +36,7 @@ enum ConfirmKind {
     CK_NOODLE = 1, /* single literal: noodTable msk/cmp (src/hwlm/noodle_internal.h) */
 };
 
+enum { MAX_PEERS = 8 };
 enum { CTR_MATCHES = 0, CTR_ERROR = 1, CTR_CANDIDATES = 2, CTR_CONFIRMED = 3,
        CTR_PREFILTER_PASS = 4, CTR_COUNT = 8 };
 enum { ERR_BAD_OPCODE = 1, ERR_INTERNAL = 2 };
@@ -73,6 +74,14 @@ struct ScanParams {
     DevMatch *out;
     u32 outCap;
     u32 *counters;
+    /* fused exchange (multi-GPU): every record is also stored, over NVLink,
+     * into slot [myRank][1 + i] of each peer's exchange buffer (peer-mapped
+     * pointers; layout [nPeers][peerCap + 1] records, slot 0 = count) */
+    u32 nPeers;
+    u32 myRank;
+    u32 peerCap;
+    u32 blockBase;           /* added to block indices in exchanged records */
+    DevMatch *peers[MAX_PEERS];
 };
 
 struct LaunchCfg {
@@ -90,6 +99,10 @@ size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 n
                      u32 tileBytes);
 
 cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream);
+
+/* Publish the record count of a finished scan into slot 0 of this rank's
+ * region in every peer's exchange buffer (runs after the scan on its stream). */
+cudaError_t launchPublishCount(const ScanParams &p, cudaStream_t stream);
 
 /* accel primitives (src/nfa/shufti.c, truffle.c, vermicelli.h): first
  * position in [0,len) whose byte is in the class, or len. */

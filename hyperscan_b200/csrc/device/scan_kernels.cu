@@ -136,6 +136,16 @@ __device__ __forceinline__ void emitMatch(const ScanParams &p, u32 id, u32 block
         m.to = to;
         *reinterpret_cast<uint4 *>(p.out + i) = *reinterpret_cast<const uint4 *>(&m);
     }
+    if (p.nPeers && i < p.peerCap) {
+        /* fused all-gather: the record goes straight into every rank's
+         * exchange buffer (posted 16-byte stores over NVLink peer mappings) */
+        DevMatch g = {id, block + p.blockBase, to};
+        const size_t slot = (size_t)p.myRank * (p.peerCap + 1) + 1 + i;
+#pragma unroll 1
+        for (u32 r = 0; r < p.nPeers; r++) {
+            *reinterpret_cast<uint4 *>(p.peers[r] + slot) = *reinterpret_cast<const uint4 *>(&g);
+        }
+    }
 }
 
 __device__ __forceinline__ u8 upperAscii(u8 c) {
@@ -887,6 +897,25 @@ size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 n
                      u32 tileBytes) {
     return tableSmemBytes(kind, tableBytes) + bitmapBytes + (size_t)warps * nstages * (tileBytes + 32) +
            (size_t)warps * nstages * 8;
+}
+
+namespace {
+__global__ void publishCountKernel(const ScanParams p) {
+    const u32 r = threadIdx.x;
+    if (r < p.nPeers) {
+        DevMatch h;
+        h.id = p.counters[CTR_MATCHES]; /* slot 0 = {count, 0, 0} */
+        h.block = 0;
+        h.to = 0;
+        const size_t slot = (size_t)p.myRank * (p.peerCap + 1);
+        *reinterpret_cast<uint4 *>(p.peers[r] + slot) = *reinterpret_cast<const uint4 *>(&h);
+    }
+}
+} // namespace
+
+cudaError_t launchPublishCount(const ScanParams &p, cudaStream_t stream) {
+    publishCountKernel<<<1, 32, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
 cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {

@@ -90,3 +90,62 @@ def merge_gathered(counts, gathered, block_base):
     if not parts:
         return np.zeros(0, dtype=MATCH_DTYPE)
     return np.concatenate(parts)
+
+
+class PeerExchange:
+    """Fused scan + all-gather over NVLink peer memory (include/hs_b200.h,
+    hs_b200_set_peer_exchange): every rank owns a buffer of world x (cap + 1)
+    records; the scan kernel of rank r stores its records into slot row r of
+    every rank's buffer as it finds them.  Handles travel once through the
+    process group at set-up; the data path has no collective."""
+
+    def __init__(self, cap, group=None):
+        import ctypes as C
+        from . import capi
+        self.capi = capi
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.cap = int(cap)
+        self.bytes = self.world * (self.cap + 1) * 16
+        L = capi.lib()
+        self.mine = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        capi._check(L.hs_b200_peer_buffer_alloc(self.bytes, C.byref(self.mine), handle), "peer_buffer_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        self.bases = (C.c_void_p * self.world)()
+        self.opened = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.bases[r] = self.mine.value
+            else:
+                p = C.c_void_p()
+                capi._check(L.hs_b200_peer_buffer_open(h, C.byref(p)), "peer_buffer_open rank %d" % r)
+                self.bases[r] = p.value
+                self.opened.append(p)
+
+    def attach(self, scratch, block_base):
+        self.capi._check(self.capi.lib().hs_b200_set_peer_exchange(
+            scratch.ptr, self.world, self.rank, self.bases, self.cap, int(block_base)), "set_peer_exchange")
+
+    def detach(self, scratch):
+        self.capi.lib().hs_b200_set_peer_exchange(scratch.ptr, 0, 0, None, 0, 0)
+
+    def read(self):
+        """(counts per rank, merged MATCH_DTYPE array of the valid records) from
+        THIS rank's buffer (block indices are already global)."""
+        raw = np.zeros(self.world * (self.cap + 1), dtype=MATCH_DTYPE)
+        self.capi._check(self.capi.lib().hs_b200_peer_buffer_read(self.mine, raw.ctypes.data, self.bytes))
+        raw = raw.reshape(self.world, self.cap + 1)
+        counts = [int(raw[r, 0]["id"]) for r in range(self.world)]
+        parts = [raw[r, 1:1 + min(counts[r], self.cap)] for r in range(self.world)]
+        return counts, np.concatenate(parts) if parts else np.zeros(0, dtype=MATCH_DTYPE)
+
+    def close(self):
+        L = self.capi.lib()
+        for p in self.opened:
+            L.hs_b200_peer_buffer_close(p, 1)
+        self.opened = []
+        if self.mine:
+            L.hs_b200_peer_buffer_close(self.mine, 0)
+            self.mine = None

@@ -255,6 +255,24 @@ hs_error_t hs_b200_copy_records(hs_scratch_t *scratch, void *d_dst, size_t cap);
  * (low word of a zeroed 64-bit slot).  Slots beyond the count hold stale data. */
 hs_error_t hs_b200_export_records_async(hs_scratch_t *scratch, void *d_dst, size_t cap,
                                         void *d_count, void *cuda_stream);
+/* Fused scan + all-gather over NVLink peer memory (one process per GPU).
+ * Every rank allocates an exchange buffer of nranks x (cap + 1) records with
+ * hs_b200_peer_buffer_alloc (cudaMalloc + cudaIpcGetMemHandle; the 64-byte
+ * handle is sent to the other ranks by any means), opens the others' buffers
+ * with hs_b200_peer_buffer_open (cudaIpcOpenMemHandle, peer access enabled),
+ * and registers all bases -- its own included, in rank order -- with
+ * hs_b200_set_peer_exchange.  From then on the scan kernel itself stores each
+ * match record into slot [my_rank][1 + i] of EVERY rank's buffer as it is
+ * found (block index + block_base), and slot [my_rank][0] receives the count
+ * when the scan completes: no separate collective.  Records beyond `cap` are
+ * only kept in the local ring (the count tells).  nranks = 0 disables it. */
+hs_error_t hs_b200_peer_buffer_alloc(size_t bytes, void **d_ptr, unsigned char handle[64]);
+hs_error_t hs_b200_peer_buffer_open(const unsigned char handle[64], void **d_ptr);
+hs_error_t hs_b200_peer_buffer_read(const void *d_ptr, void *host_dst, size_t bytes);
+hs_error_t hs_b200_peer_buffer_close(void *d_ptr, int opened);
+hs_error_t hs_b200_set_peer_exchange(hs_scratch_t *scratch, unsigned int nranks,
+                                     unsigned int my_rank, void *const *peer_bases,
+                                     size_t cap_per_rank, unsigned int block_base);
 /* Apply the host-side report rules to `n` raw records held in host memory
  * (in place; e.g. the concatenation of all ranks' records after the
  * all-gather): sort by (block, to, id), one record per (block, id, to),
