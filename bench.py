@@ -235,9 +235,13 @@ def main():
         with torch.cuda.stream(scan_stream):
             for i in range(k):
                 sc = rings[i % 2]
+                ta = time.perf_counter()
                 if i >= 2:
                     n = retire(sc)          # pass i-2 used this scratch
+                tb_ = time.perf_counter()
                 capi.scan_corpus_async(db, corpus, sc, st)
+                phase["retire_s"] = phase.get("retire_s", 0.0) + tb_ - ta
+                phase["async_s"] = phase.get("async_s", 0.0) + time.perf_counter() - tb_
                 if world > 1 and peerx is None:
                     buf = gather_buf["bufs"][i % 2]
                     capi._check(capi.lib().hs_b200_export_records_async(
@@ -297,9 +301,15 @@ def main():
     t_run = time.perf_counter() - t0
     barrier()
     dt = time.perf_counter() - t0
-    print("[bench rank %d] run %.3f ms, with barrier %.3f ms, host enqueue %.3f ms, kernel sum %.3f ms"
-          % (rank, t_run * 1e3, dt * 1e3, phase.get("enqueue_s", 0) * 1e3, sum(kernel_ms)),
-          file=sys.stderr, flush=True)
+    try:
+        cpus = len(os.sched_getaffinity(0))
+        cg = open("/sys/fs/cgroup/cpu.max").read().strip()
+    except OSError:
+        cpus, cg = -1, "?"
+    print("[bench rank %d] run %.3f ms, with barrier %.3f ms, host enqueue %.3f ms (retire %.3f, async %.3f), "
+          "kernel sum %.3f ms, affinity %d cpus, cgroup cpu.max %s\n"
+          % (rank, t_run * 1e3, dt * 1e3, phase.get("enqueue_s", 0) * 1e3, phase.get("retire_s", 0) * 1e3,
+             phase.get("async_s", 0) * 1e3, sum(kernel_ms), cpus, cg), file=sys.stderr, flush=True)
     t1w = time.time()
     launches = capi.launch_count() - launches0
     clocks = sampler.stop(t0w, t1w) if sampler else None
