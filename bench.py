@@ -295,15 +295,27 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     t0w = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stat0 = (0, 0, 0)
+    try:
+        d0 = dict(l.split() for l in open("/sys/fs/cgroup/cpu.stat").read().strip().splitlines())
+        stat0 = (int(d0.get("nr_throttled", 0)), int(d0.get("throttled_usec", 0)), int(d0.get("usage_usec", 0)))
+    except (OSError, ValueError):
+        pass
     t0 = time.perf_counter()
     phase.clear()
     n, last, kernel_ms = run_steps(K)
     t_run = time.perf_counter() - t0
     barrier()
     dt = time.perf_counter() - t0
+    def cpu_stat():
+        try:
+            d = dict(l.split() for l in open("/sys/fs/cgroup/cpu.stat").read().strip().splitlines())
+            return int(d.get("nr_throttled", 0)), int(d.get("throttled_usec", 0)), int(d.get("usage_usec", 0))
+        except (OSError, ValueError):
+            return (0, 0, 0)
     try:
         cpus = len(os.sched_getaffinity(0))
-        cg = open("/sys/fs/cgroup/cpu.max").read().strip()
+        cg = open("/sys/fs/cgroup/cpu.max").read().strip() + " stat(after) %s vs (before) %s" % (cpu_stat(), stat0)
     except OSError:
         cpus, cg = -1, "?"
     print("[bench rank %d] run %.3f ms, with barrier %.3f ms, host enqueue %.3f ms (retire %.3f, async %.3f), "

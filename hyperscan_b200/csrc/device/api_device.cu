@@ -866,7 +866,12 @@ static hs_error_t newScratch(hs_scratch **out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->copyStream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&s->evStart);
     if (e == cudaSuccess) e = cudaEventCreate(&s->evStop);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->evDone, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        /* HSB200_BLOCKING_SYNC=1: sleep instead of spinning while a scan is awaited */
+        const char *bs = getenv("HSB200_BLOCKING_SYNC");
+        e = cudaEventCreateWithFlags(&s->evDone, cudaEventDisableTiming |
+                                                      ((bs && *bs == '1') ? cudaEventBlockingSync : 0));
+    }
     if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, CTR_COUNT * sizeof(u32));
     if (e == cudaSuccess) e = cudaMallocHost(&s->h_counters, CTR_COUNT * sizeof(u32));
     if (e == cudaSuccess) {
