@@ -289,10 +289,12 @@ def main():
                     peerx.detach(sc)
                 peerx = None
 
+    # the sampler forks nvidia-smi (~100 ms): start it BEFORE the barrier so that
+    # rank 0 enters the timed region together with the other ranks
+    sampler = ClockSampler(local) if rank == 0 else None
     run_steps(W)
     barrier()
     launches0 = capi.launch_count()
-    sampler = ClockSampler(local) if rank == 0 else None
     t0w = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stat0 = (0, 0, 0)
