@@ -75,6 +75,21 @@ def config_of(args, n, info=None):
     return c
 
 
+def usable_cores():
+    """Host cores this container may actually use: the cgroup CPU quota when
+    there is one (the GPU boxes expose 128 logical CPUs but cap the container at
+    48 or 96 CPUs' worth of time; more runnable threads than that only get
+    throttled), else the affinity mask."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -126,7 +141,7 @@ def cpu_reference_run(db, data, off, ln, sample_mb, seconds, threads=None):
     """Time the reference's own CPU hs_scan (oracle/_ref, unmodified sources)
     on a bounded sample of the workload, hsbench style."""
     import oracle.ref as ref
-    threads = threads or (os.cpu_count() or 1)
+    threads = threads or usable_cores()
     nblk = max(1, min(len(off), (sample_mb << 20) // max(1, int(ln[0]))))
     o, l = off[:nblk], ln[:nblk]
     sample_bytes = int(l.sum())
@@ -152,7 +167,7 @@ def run_reference_arm(args, rank, world):
     db = capi.compile_lit_multi(lits, flags, ids)
     K, W = args.steps, args.warmup
     import oracle.ref as ref
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     nblk = max(1, min(len(off), (args.cpu_sample_mb << 20) // args.block_len))
     o, l = off[:nblk], ln[:nblk]
     for _ in range(W):
