@@ -403,7 +403,8 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             de = float(tt.item())
         e2e = {"value": total_bytes * 8 * Ke / de / 1e9, "unit": "Gbit/s",
-               "h2d_bytes_per_step": int(data.size),  # uniform blocks: no block table travels "d2h_bytes_per_step": int(32 + nm * 16),
+               "h2d_bytes_per_step": int(data.size),   # uniform blocks: no block table travels
+               "d2h_bytes_per_step": int(32 + nm * 16),
                "steps": Ke, "ms_per_step": de / Ke * 1e3,
                "api": "hs_b200_scan_blocks(host pinned buffer) -> sorted match list on host"}
 
