@@ -54,7 +54,7 @@ struct RuntimeOpts {
     int pfDist = 8;          /* direct mode: L2 prefetch distance in 512-byte steps */
     int replicas = 1;        /* rebuilt table: copies per entry (0 = fill up to 128 KB, max 16);
                               * measured: no gain, and a small footprint lets NCCL CTAs co-reside */
-    int chunkMB = 32;        /* host->device pipeline granularity */
+    int chunkMB = 128;       /* host->device pipeline granularity */
     int initialRing = 1 << 20;
 };
 RuntimeOpts g_opts;
@@ -417,8 +417,9 @@ struct hs_scratch {
     u32 *d_counters;
     u32 *h_counters;         /* pinned */
     hs_b200_corpus *inlineCorpus; /* staging for hs_scan / hs_b200_scan_blocks */
-    u8 *h_stage;             /* pinned pack buffer (unaligned host blocks) */
-    size_t h_stageCap;
+    u8 *h_stage, *h_stage2;  /* pinned pack buffers (unaligned host blocks), alternating */
+    size_t h_stageCap, h_stage2Cap;
+    cudaEvent_t evStage, evStage2;
     std::vector<u64> *tmpOff;
     const DevImage *lastImage;
     const hs_b200_corpus *lastCorpus;
@@ -720,8 +721,33 @@ hs_error_t enqueueScan(hs_scratch *s, const DevImage *im, const hs_b200_corpus *
  * relative to the first block, ascending, disjoint). */
 hs_error_t layoutBlocks(hs_scratch *s, const unsigned long long *offsets,
                         const unsigned *lengths, size_t nblocks, std::vector<u64> *packed,
-                        u64 *total, u64 *payload, bool *direct) {
+                        u64 *total, u64 *payload, bool *direct, u32 *uniPitch = nullptr,
+                        u32 *uniLen = nullptr) {
     (void)s;
+    if (uniPitch) {
+        *uniPitch = *uniLen = 0;
+        /* fast path (hsbench-style corpora): equally long blocks at a fixed
+         * 16-byte aligned pitch -- one tight pass, no packed table at all */
+        if (nblocks >= 2 && lengths[0] && offsets[1] > offsets[0]) {
+            const u64 base = offsets[0], pitch = offsets[1] - offsets[0];
+            const u32 len0 = lengths[0];
+            if (pitch % 16 == 0 && pitch <= 0xffffffffu && len0 <= pitch) {
+                size_t bad = 0;
+                for (size_t i = 0; i < nblocks; i++) {
+                    bad += (offsets[i] != base + i * pitch) | (lengths[i] != len0);
+                }
+                if (!bad) {
+                    packed->clear();
+                    *total = (nblocks - 1) * pitch + len0;
+                    *payload = (u64)nblocks * len0;
+                    *direct = true;
+                    *uniPitch = (u32)pitch;
+                    *uniLen = len0;
+                    return HS_SUCCESS;
+                }
+            }
+        }
+    }
     packed->resize(nblocks);
     bool ok = nblocks > 0;
     u64 pay = 0;
@@ -872,6 +898,8 @@ static hs_error_t newScratch(hs_scratch **out) {
         e = cudaEventCreateWithFlags(&s->evDone, cudaEventDisableTiming |
                                                       ((bs && *bs == '1') ? cudaEventBlockingSync : 0));
     }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->evStage, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->evStage2, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_counters, CTR_COUNT * sizeof(u32));
     if (e == cudaSuccess) e = cudaMallocHost(&s->h_counters, CTR_COUNT * sizeof(u32));
     if (e == cudaSuccess) {
@@ -996,6 +1024,9 @@ hs_error_t hs_free_scratch(hs_scratch_t *s) {
     cudaFree(s->d_counters);
     if (s->h_counters) cudaFreeHost(s->h_counters);
     if (s->h_stage) cudaFreeHost(s->h_stage);
+    if (s->h_stage2) cudaFreeHost(s->h_stage2);
+    if (s->evStage) cudaEventDestroy(s->evStage);
+    if (s->evStage2) cudaEventDestroy(s->evStage2);
     if (s->evStart) cudaEventDestroy(s->evStart);
     if (s->evStop) cudaEventDestroy(s->evStop);
     if (s->evDone) cudaEventDestroy(s->evDone);
@@ -1008,10 +1039,16 @@ hs_error_t hs_free_scratch(hs_scratch_t *s) {
 /* ---- corpus handles ------------------------------------------------------------ */
 
 static hs_error_t setBlocks(hs_b200_corpus *c, const u64 *packed, const unsigned *lengths,
-                            size_t nblocks, u64 total, u64 payload, cudaStream_t stream) {
+                            size_t nblocks, u64 total, u64 payload, cudaStream_t stream,
+                            u32 uniPitch = 0, u32 uniLen = 0) {
     c->nblocks = nblocks;
     c->bytes = total;
     c->payload = payload;
+    if (uniPitch && uniLen) { /* layoutBlocks already proved uniformity: no tables */
+        c->uniformPitch = uniPitch;
+        c->uniformLen = uniLen;
+        return HS_SUCCESS;
+    }
     c->uniformPitch = detectPitch(packed, lengths, nblocks);
     c->uniformLen = 0;
     if (c->uniformPitch && nblocks) {
@@ -1048,7 +1085,8 @@ hs_error_t hs_b200_corpus_upload(const char *data, const unsigned long long *off
     std::vector<u64> packed;
     u64 total = 0, payload = 0;
     bool direct = false;
-    layoutBlocks(nullptr, offsets, lengths, nblocks, &packed, &total, &payload, &direct);
+    u32 uniPitch = 0, uniLen = 0;
+    layoutBlocks(nullptr, offsets, lengths, nblocks, &packed, &total, &payload, &direct, &uniPitch, &uniLen);
     hs_error_t r = reserveCorpus(c, total, nblocks);
     if (r != HS_SUCCESS) {
         freeCorpus(c);
@@ -1086,7 +1124,7 @@ hs_error_t hs_b200_corpus_upload(const char *data, const unsigned long long *off
     }
     c->readableEnd = HSB_ROUNDUP(total, 16) + 16;
     if (e == cudaSuccess) {
-        r = setBlocks(c, packed.data(), lengths, nblocks, total, payload, 0);
+        r = setBlocks(c, packed.data(), lengths, nblocks, total, payload, 0, uniPitch, uniLen);
         if (r == HS_SUCCESS && cudaDeviceSynchronize() != cudaSuccess) {
             r = HS_UNKNOWN_ERROR;
         }
@@ -1387,7 +1425,8 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
     std::vector<u64> &packed = *s->tmpOff;
     u64 total = 0, payload = 0;
     bool direct = false;
-    layoutBlocks(s, offsets, lengths, nblocks, &packed, &total, &payload, &direct);
+    u32 uniPitch = 0, uniLen = 0;
+    layoutBlocks(s, offsets, lengths, nblocks, &packed, &total, &payload, &direct, &uniPitch, &uniLen);
     matches->clear();
     if (total == 0) {
         return HS_SUCCESS;
@@ -1397,7 +1436,7 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
         return r;
     }
     c->readableEnd = HSB_ROUNDUP(total, 16) + 16;
-    r = setBlocks(c, packed.data(), lengths, nblocks, total, payload, s->copyStream);
+    r = setBlocks(c, packed.data(), lengths, nblocks, total, payload, s->copyStream, uniPitch, uniLen);
     if (r != HS_SUCCESS) {
         return r;
     }
@@ -1428,15 +1467,37 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
                     CUDA_TRY(cudaMemcpyAsync(c->d_data + from, data + offsets[0] + from, to - from,
                                              cudaMemcpyHostToDevice, s->copyStream));
                 } else {
-                    /* per-block copies (unaligned host layout); blocks that
-                     * straddle the chunk edge are copied whole */
+                    /* unaligned host layout: pack this chunk's blocks (16-byte
+                     * aligned starts, zero gaps) into a pinned staging buffer and
+                     * send it as one copy; blocks that straddle the chunk edge go
+                     * whole with the chunk they start in.  Two buffers alternate. */
+                    const size_t b0 = blk;
+                    u64 end = from;
                     while (blk < nblocks && packed[blk] < to) {
-                        if (lengths[blk]) {
-                            CUDA_TRY(cudaMemcpyAsync(c->d_data + packed[blk], data + offsets[blk],
-                                                     lengths[blk], cudaMemcpyHostToDevice,
-                                                     s->copyStream));
-                        }
+                        end = std::max<u64>(end, packed[blk] + lengths[blk]);
                         blk++;
+                    }
+                    if (blk > b0) {
+                        const u64 start = packed[b0];
+                        const size_t need = (size_t)(end - start);
+                        u8 *&stage = (ci & 1) ? s->h_stage2 : s->h_stage;
+                        size_t &cap = (ci & 1) ? s->h_stage2Cap : s->h_stageCap;
+                        cudaEvent_t ev = (ci & 1) ? s->evStage2 : s->evStage;
+                        CUDA_TRY(cudaEventSynchronize(ev)); /* previous use of this buffer has been sent */
+                        if (need > cap) {
+                            if (stage) cudaFreeHost(stage);
+                            stage = nullptr;
+                            cap = 0;
+                            CUDA_TRY(cudaMallocHost(&stage, need + need / 4 + 4096));
+                            cap = need + need / 4 + 4096;
+                        }
+                        memset(stage, 0, need);
+                        for (size_t k = b0; k < blk; k++) {
+                            memcpy(stage + (packed[k] - start), data + offsets[k], lengths[k]);
+                        }
+                        CUDA_TRY(cudaMemcpyAsync(c->d_data + start, stage, need, cudaMemcpyHostToDevice,
+                                                 s->copyStream));
+                        CUDA_TRY(cudaEventRecord(ev, s->copyStream));
                     }
                 }
                 CUDA_TRY(cudaEventRecord((*s->chunkEvents)[ci], s->copyStream));
