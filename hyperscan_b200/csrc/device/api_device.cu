@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -1418,9 +1419,16 @@ hs_error_t hs_b200_fetch_matches(const hs_database_t *db, hs_scratch_t *scratch,
 
 /* Copy host blocks into the scratch's inline corpus and scan them, with the
  * host->device copy pipelined against the kernel in chunk_mb pieces. */
+static double nowMs() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *data,
                                  const unsigned long long *offsets, const unsigned *lengths,
                                  size_t nblocks, std::vector<DevMatch> *matches) {
+    static const bool trace = getenv("HSB200_TRACE") != nullptr;
+    const double t0 = nowMs();
+    double tLayout = 0, tEnq = 0, tWait = 0, tRec = 0;
     hs_b200_corpus *c = s->inlineCorpus;
     std::vector<u64> &packed = *s->tmpOff;
     u64 total = 0, payload = 0;
@@ -1431,6 +1439,7 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
     if (total == 0) {
         return HS_SUCCESS;
     }
+    tLayout = nowMs();
     hs_error_t r = reserveCorpus(c, total, nblocks);
     if (r != HS_SUCCESS) {
         return r;
@@ -1527,7 +1536,9 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
         s->activeStream = s->stream;
         s->pending = true;
         u32 count = 0;
+        tEnq = nowMs();
         r = finishScan(s, &count);
+        tWait = nowMs();
         if (r != HS_SUCCESS) {
             return r;
         }
@@ -1538,7 +1549,14 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
                                          cudaMemcpyDeviceToHost, s->stream));
                 CUDA_TRY(cudaStreamSynchronize(s->stream));
             }
+            tRec = nowMs();
             matches->resize(postprocess(im, matches->data(), count));
+            if (trace) {
+                fprintf(stderr, "[hs_b200 trace] host scan: layout %.3f ms, enqueue %.3f, wait %.3f, records %.3f, "
+                                "postprocess %.3f (total %.3f, %zu chunks)\n",
+                        tLayout - t0, tEnq - tLayout, tWait - tEnq, tRec - tWait, nowMs() - tRec,
+                        nowMs() - t0, nchunks);
+            }
             return HS_SUCCESS;
         }
         /* record ring overflowed: grow it and scan the resident corpus again */
