@@ -521,9 +521,19 @@ __device__ __forceinline__ void laneFilter(const u32 (&w)[5], u32 tabAddr, u32 l
 
 /* ---- candidate handling (rare path) ------------------------------------------- */
 
-/* little-endian u64 of corpus bytes [g-7, g] (at least 16 readable bytes
- * precede position 0) */
+/* little-endian u64 of corpus bytes [g-7, g]; positions before the corpus
+ * read as zero (a wrapped caller buffer has nothing readable before it) */
 __device__ __forceinline__ u64 confValAt(const ScanParams &p, u64 g) {
+    if (g < 11 || g + 5 > p.readableEnd) { /* rare: the aligned 12-byte window would leave the buffer */
+        u64 v = 0;
+        for (int z = 0; z < 8; z++) {
+            const long long q = (long long)g - 7 + z;
+            if (q >= 0) {
+                v |= (u64)__ldg(p.corpus + q) << (8 * z);
+            }
+        }
+        return v;
+    }
     const u8 *a = p.corpus + g - 7;
     const u32 mis = (u32)((uintptr_t)a & 3);
     const u32 *aw = reinterpret_cast<const u32 *>(a - mis);
@@ -789,7 +799,7 @@ __global__ void __launch_bounds__(DIRECT ? 768 : 1024, 1) scanKernel(const ScanP
             }
             const u64 g0 = lanePos + (u64)step * 512;
             scanStep<KIND, STRIDE, SB>(p, cur, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
-                                       [&]() { return __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)); });
+                                       [&]() { return g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u; });
         }
     } else {
         const u32 stepsPerTile = p.tileBytes >> 9;
