@@ -92,6 +92,8 @@ struct DevImage {
     u32 tableBytes = 0;
     u8 *d_bitmap = nullptr;
     u32 bitmapBytes = 0, bitmapShift = 0, keyBytes = 0;
+    u8 *d_bitmap2 = nullptr; /* second level (HBM / L2) for large literal sets */
+    u32 bitmap2Shift = 0;
     int kind = FK_BYTE32;
     int stride = 1;
     int slotBase = 0;
@@ -118,7 +120,8 @@ struct DevImage {
  * enumerated).  A clear bit proves no literal ends at a candidate position, so
  * the hash confirm in HBM/L2 is only reached by ~1% of the first stage's false
  * positives.  Returns an empty vector when the set cannot be keyed usefully. */
-std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u32 *shift) {
+std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u32 *shift,
+                            std::vector<u8> *level2 = nullptr, u32 *shift2 = nullptr) {
     std::vector<u8> bm;
     if (tails.empty()) {
         return bm;
@@ -156,6 +159,20 @@ std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u3
     }
     *keyBytes = m;
     *shift = 32 - lg;
+    if (level2 && shift2 && keys.size() * 32 > ((size_t)1 << lg)) {
+        /* the shared-memory bitmap is more than ~3 % full: add a level with
+         * ~1024 bits per key (<= 64 MB), probed only by its survivors */
+        u32 lg2 = lg + 1;
+        while (lg2 < 29 && (1ull << lg2) < (u64)keys.size() * 1024) {
+            lg2++;
+        }
+        level2->assign((size_t)1 << (lg2 - 3), 0);
+        for (u32 k : keys) {
+            const u32 h = (k * 0x85EBCA6Bu) >> (32 - lg2);
+            (*level2)[h >> 3] |= (u8)(1u << (h & 7));
+        }
+        *shift2 = 32 - lg2;
+    }
     return bm;
 }
 
@@ -216,6 +233,7 @@ void freeImage(DevImage *im) {
     cudaFree(im->d_bc);
     cudaFree(im->d_table);
     cudaFree(im->d_bitmap);
+    cudaFree(im->d_bitmap2);
     delete im;
 }
 
@@ -351,9 +369,9 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
         return HS_INVALID;
     }
     im->tableBytes = (u32)table.size();
-    std::vector<u8> bitmap;
+    std::vector<u8> bitmap, bitmap2;
     if (g_opts.prefilter) {
-        bitmap = buildBitmap(tails, &im->keyBytes, &im->bitmapShift);
+        bitmap = buildBitmap(tails, &im->keyBytes, &im->bitmapShift, &bitmap2, &im->bitmap2Shift);
     }
     im->bitmapBytes = (u32)bitmap.size();
     cudaError_t e = cudaMalloc(&im->d_bc, HSB_ROUNDUP(h->length, 16));
@@ -362,6 +380,14 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
         if (e == cudaSuccess) {
             e = cudaMemcpy(im->d_bitmap, bitmap.data(), bitmap.size(), cudaMemcpyHostToDevice);
         }
+    }
+    if (e == cudaSuccess && !bitmap2.empty()) {
+        e = cudaMalloc(&im->d_bitmap2, bitmap2.size());
+        if (e == cudaSuccess) {
+            e = cudaMemcpy(im->d_bitmap2, bitmap2.data(), bitmap2.size(), cudaMemcpyHostToDevice);
+        }
+    } else {
+        im->bitmap2Shift = 0;
     }
     if (e == cudaSuccess) {
         e = cudaMalloc(&im->d_table, HSB_ROUNDUP(table.size(), 16));
@@ -376,7 +402,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
         freeImage(im);
         return e == cudaErrorMemoryAllocation ? HS_NOMEM : HS_UNKNOWN_ERROR;
     }
-    im->deviceBytes = HSB_ROUNDUP(h->length, 16) + HSB_ROUNDUP(table.size(), 16) + bitmap.size();
+    im->deviceBytes = HSB_ROUNDUP(h->length, 16) + HSB_ROUNDUP(table.size(), 16) + bitmap.size() + bitmap2.size();
     *out = im;
     return HS_SUCCESS;
 }
@@ -630,6 +656,8 @@ void fillParams(const hs_scratch *s, const DevImage *im, const hs_b200_corpus *c
     p->bitmapBytes = im->bitmapBytes;
     p->bitmapShift = im->bitmapShift;
     p->keyBytes = im->keyBytes;
+    p->bitmap2 = (const u32 *)im->d_bitmap2;
+    p->bitmap2Shift = im->d_bitmap2 ? im->bitmap2Shift : 0;
     p->confOff = im->confOff;
     p->engineOff = im->engineOff;
     p->confirmKind = im->confirmKind;

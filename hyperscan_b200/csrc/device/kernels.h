@@ -66,6 +66,8 @@ struct ScanParams {
     u32 bitmapBytes;       /* power of two >= 16, or 0 = no prefilter */
     u32 bitmapShift;       /* 32 - log2(bits) */
     u32 keyBytes;          /* 1..4: literal tail bytes hashed into the bitmap */
+    const u32 *bitmap2;    /* optional second-level bitmap in HBM/L2 (large literal sets) */
+    u32 bitmap2Shift;      /* 32 - log2(bits); 0 = none */
     u32 confOff;           /* CK_FDR: offset of the confirm base in bc */
     u32 engineOff;         /* CK_NOODLE: offset of the noodTable in bc */
     u32 confirmKind;

@@ -586,6 +586,14 @@ __device__ __noinline__ void laneCandidates(const ScanParams &p, u32 bitmapAddr,
             if (!((lds32(bitmapAddr + ((hsh >> 5) << 2)) >> (hsh & 31)) & 1)) {
                 continue; /* no literal of any bucket ends here */
             }
+            if (p.bitmap2Shift) {
+                /* large sets overload the shared-memory bitmap: a second, much
+                 * sparser one lives in HBM and stays L2-resident */
+                const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
+                if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
+                    continue;
+                }
+            }
         }
         stats[1]++;
         const u64 g = g0 + x;
