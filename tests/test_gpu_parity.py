@@ -49,6 +49,16 @@ def test_engines_random_blocks(hs, ref, nlits, engine):
     _check_all(hs, ref, lits, flags, ids, data, off, ln)
 
 
+def test_large_literal_set_two_level_prefilter(hs, ref):
+    # config 5 shape (50 k literals -> FDR domain 15): the shared-memory bitmap
+    # saturates and the second-level bitmap in HBM takes over
+    lits, flags, ids = synth.literal_set(50000, min_len=4, max_len=16, seed=50, caseless_frac=0.1)
+    data, off, ln, _ = synth.block_corpus(512, 1024, lits, plant_per_kb=1.0, seed=51)
+    db, want = _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
+    assert (db.info().engine_id, db.info().fdr_domain, db.info().fdr_stride) == (0, 15, 1)
+    assert want.size > 300
+
+
 def test_hs_scan_single_block_and_termination(hs, ref):
     lits = [b"mnopqr"]
     db = hs.compile_lit_multi(lits, [0], [7])
