@@ -53,7 +53,7 @@ def build_product(verbose=False):
         src = os.path.join(CSRC, s)
         obj = os.path.join(OBJDIR, os.path.basename(s) + ".o")
         if _newer([src] + hdrs, obj):
-            _run(["g++", "-O2", "-std=c++17", "-fPIC", "-c", src, "-o", obj], verbose)
+            _run(["g++", "-O3", "-std=c++17", "-fPIC", "-c", src, "-o", obj], verbose)
         objs.append(obj)
     for s in CUDA_SRCS:
         src = os.path.join(CSRC, s)
@@ -61,7 +61,7 @@ def build_product(verbose=False):
             continue
         obj = os.path.join(OBJDIR, os.path.basename(s) + ".o")
         if _newer([src] + hdrs, obj):
-            _run([NVCC] + ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+            _run([NVCC] + ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-O3",
                                   "-c", src, "-o", obj], verbose)
         objs.append(obj)
     out = os.path.join(LIBDIR, "libhs_b200.so")

@@ -16,15 +16,21 @@
  *     boundaries (the first stage is position-only; block membership is
  *     checked in the confirm stage); every warp owns a CONTIGUOUS run of
  *     tiles so the shift-OR state carries across tiles;
- *   - tiles are staged global -> shared with 1-D TMA bulk copies
- *     (cp.async.bulk + mbarrier complete_tx), an NSTAGE-deep ring per warp;
- *   - per 512-byte step every lane reads its own 16 bytes as one uint4, does
- *     16/STRIDE table lookups, shift-ORs them into per-end-position bytes;
- *     the 3 (or 7) bytes that overflow into the next lane travel by
- *     __shfl_up_sync; a zero bit = candidate (bucket, end position);
- *   - candidates (rare) are confirmed in place: FDRConfirm hash -> LitInfo
- *     chain -> block lookup -> rose literal program -> 16-byte match record
- *     appended to a ring in HBM.
+ *   - corpus staging, two modes (template DIRECT): each lane loads its 16
+ *     bytes per step straight from HBM into registers one step ahead, with
+ *     prefetch.global.L2 several steps ahead (default); or tiles are staged
+ *     global -> shared with 1-D TMA bulk copies (cp.async.bulk + mbarrier
+ *     complete_tx), an NSTAGE-deep ring per warp, and read as uint4;
+ *   - per 512-byte step every lane does 16/STRIDE table lookups and merges
+ *     the four entries of one in-word position as a 128-bit stream with one
+ *     funnel shift per output word; the 3 (or 7) bytes that overflow into the
+ *     next lane travel by __shfl_up_sync; a zero bit = candidate (bucket, end);
+ *   - candidates (rare) first probe a bitmap over hashes of literal tails in
+ *     shared memory (+ a sparser second level in L2 for large sets); survivors
+ *     are confirmed in place: FDRConfirm hash -> LitInfo chain -> block lookup
+ *     -> rose literal program -> 16-byte match record appended to a ring in
+ *     HBM and, in multi-GPU runs, stored into every rank's exchange buffer over
+ *     NVLink peer mappings (the scan IS the all-gather).
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -503,7 +509,6 @@ __device__ __forceinline__ void laneFilter(const u32 (&w)[5], u32 tabAddr, u32 l
                 }
             }
         }
-        constexpr int O = 0; (void)O;
         if (r + SB == 0) orStream<0>(a[0], E0);
         if (r + SB == 1) orStream<1>(a[0], E0);
         if (r + SB == 2) orStream<2>(a[0], E0);
