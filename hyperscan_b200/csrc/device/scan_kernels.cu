@@ -643,12 +643,16 @@ __device__ __forceinline__ void scanStep(const ScanParams &p, const uint4 v, u32
     for (int o = 0; o < K::NOCT; o++) {
 #pragma unroll
         for (int x = 0; x < K::SPILL; x++) {
-            u32 in = __shfl_up_sync(0xffffffffu, a[o][4 + x], 1);
-            const u32 last = __shfl_sync(0xffffffffu, a[o][4 + x], 31);
+            /* ONE rotate-by-one shuffle: lanes 1..31 receive their left
+             * neighbour's overflow; lane 0 receives lane 31's, which is exactly
+             * the carry into the next step (shuffles ride the shared-memory
+             * data pipe, the limiter of this kernel) */
+            u32 in = __shfl_sync(0xffffffffu, a[o][4 + x], (lane + 31) & 31);
             if (lane == 0) {
+                const u32 next = in;
                 in = carry[o][x];
+                carry[o][x] = next;
             }
-            carry[o][x] = last;
             a[o][x] |= in;
         }
 #pragma unroll
@@ -804,11 +808,9 @@ __global__ void __launch_bounds__(DIRECT ? 768 : 1024, 1) scanKernel(const ScanP
             }
             u32 w4 = 0;
             if (K::HASH) {
-                w4 = __shfl_down_sync(0xffffffffu, cur.x, 1);
-                const u32 nx = __shfl_sync(0xffffffffu, nxt.x, 0);
-                if (lane == 31) {
-                    w4 = nx;
-                }
+                /* the word after the lane's 16 bytes: one rotate shuffle in
+                 * which lane 0 offers the NEXT step's first word (for lane 31) */
+                w4 = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, (lane + 1) & 31);
             }
             const u64 g0 = lanePos + (u64)step * 512;
             scanStep<KIND, STRIDE, SB>(p, cur, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
