@@ -43,7 +43,7 @@ std::atomic<unsigned long long> g_launches{0};
 
 /* runtime tunables (hs_b200_set_runtime_option / HSB200_* environment) */
 struct RuntimeOpts {
-    int warps = 32;
+    int warps = 32;          /* clamped to 28 in direct mode (896 threads x 72 registers) */
     int tileBytes = 1024;
     int stages = 2;
     int wideFdr = 0;         /* 1: use all 8 FDR slots (u64 entries) when they fit */
@@ -596,7 +596,7 @@ struct ScanPlan {
 hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     initOpts();
     const int direct = g_opts.direct ? 1 : 0;
-    int warps = std::max(1, std::min(direct ? 24 : 32, g_opts.warps));
+    int warps = std::max(1, std::min(direct ? 28 : 32, g_opts.warps));
     u32 tile = (u32)std::max(512, g_opts.tileBytes) & ~511u;
     u32 stages = (u32)std::max(2, std::min(8, g_opts.stages));
     /* shrink until the table + staging fit the opt-in shared memory */

@@ -695,7 +695,7 @@ __device__ __forceinline__ void haloStep(const ScanParams &p, const uint4 v, u32
 }
 
 template <int KIND, int STRIDE, int SB, int DIRECT>
-__global__ void __launch_bounds__(DIRECT ? 768 : 1024, 1) scanKernel(const ScanParams p) {
+__global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanParams p) {
     extern __shared__ __align__(128) u8 smem[];
     typedef Kind<KIND> K;
     const u32 lane = threadIdx.x & 31;
