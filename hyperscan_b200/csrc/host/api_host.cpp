@@ -731,6 +731,62 @@ hs_error_t hs_compile_lit(const char *expression, unsigned flags, const size_t l
                          db, error, true);
 }
 
+/* hs_expression_info / hs_expression_ext_info (src/hs.cpp:337-432): widths of
+ * a literal pattern are its byte length; a literal has no out-of-order or
+ * end-of-data matches. */
+static hs_error_t exprInfo(const char *expression, unsigned flags, const hs_expr_ext_t *ext,
+                           hs_expr_info_t **info, hs_compile_error_t **error) {
+    if (!error) {
+        return HS_COMPILER_ERROR;
+    }
+    if (!info) {
+        *error = makeError("Invalid parameter: info is NULL", -1);
+        return HS_COMPILER_ERROR;
+    }
+    *info = nullptr;
+    if (!expression) {
+        *error = makeError("Invalid parameter: expression is NULL", -1);
+        return HS_COMPILER_ERROR;
+    }
+    try {
+        if (flags & ~0x7ffu) {
+            throw CompileError{"Unrecognised flag.", 0};
+        }
+        if (ext && ext->flags != 0) {
+            throw CompileError{"Extended parameters need the regex back end; this build compiles "
+                               "literal patterns only.", 0};
+        }
+        const std::string lit = regexToLiteral(expression, flags, 0);
+        if (lit.size() > LIMIT_PATTERN_LENGTH) {
+            throw CompileError{"Pattern length exceeds limit.", 0};
+        }
+        hs_expr_info_t *out = (hs_expr_info_t *)g_misc_alloc(sizeof(*out));
+        if (!out) {
+            *error = &g_enomem;
+            return HS_COMPILER_ERROR;
+        }
+        memset(out, 0, sizeof(*out));
+        out->min_width = out->max_width = (unsigned)lit.size();
+        *info = out;
+        *error = nullptr;
+        return HS_SUCCESS;
+    } catch (const CompileError &e) {
+        *error = makeError(e.msg, e.index);
+        return HS_COMPILER_ERROR;
+    }
+}
+
+hs_error_t hs_expression_info(const char *expression, unsigned int flags, hs_expr_info_t **info,
+                              hs_compile_error_t **error) {
+    return exprInfo(expression, flags, nullptr, info, error);
+}
+
+hs_error_t hs_expression_ext_info(const char *expression, unsigned int flags,
+                                  const hs_expr_ext_t *ext, hs_expr_info_t **info,
+                                  hs_compile_error_t **error) {
+    return exprInfo(expression, flags, ext, info, error);
+}
+
 } /* extern "C" */
 
 /* Build tunables (test / tuning hooks): select table variants the way the

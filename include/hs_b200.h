@@ -98,6 +98,14 @@ typedef struct hs_expr_ext {        /* src/hs_compile.h:214-262 */
     unsigned hamming_distance;
 } hs_expr_ext_t;
 
+typedef struct hs_expr_info {       /* src/hs_compile.h:169-216 */
+    unsigned int min_width;
+    unsigned int max_width;
+    char unordered_matches;
+    char matches_at_eod;
+    char matches_only_at_eod;
+} hs_expr_info_t;
+
 typedef void *(*hs_alloc_t)(size_t size);   /* src/hs_common.h:271 */
 typedef void (*hs_free_t)(void *ptr);       /* src/hs_common.h:280 */
 
@@ -139,6 +147,12 @@ hs_error_t hs_compile_lit_multi(const char *const *expressions,
                                 const hs_platform_info_t *platform,
                                 hs_database_t **db, hs_compile_error_t **error);
 hs_error_t hs_free_compile_error(hs_compile_error_t *error);
+/* src/hs_compile.h:760-854; *info is allocated with the misc allocator */
+hs_error_t hs_expression_info(const char *expression, unsigned int flags,
+                              hs_expr_info_t **info, hs_compile_error_t **error);
+hs_error_t hs_expression_ext_info(const char *expression, unsigned int flags,
+                                  const hs_expr_ext_t *ext, hs_expr_info_t **info,
+                                  hs_compile_error_t **error);
 hs_error_t hs_populate_platform(hs_platform_info_t *platform);
 
 /* --- database container (src/hs_common.h:84-262; format src/database.h) */

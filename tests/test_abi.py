@@ -169,3 +169,24 @@ def test_allocator_hooks(hs):
             hs.compile_lit_multi([b"abc"])
     finally:
         L.hs_set_database_allocator(AT(), FT())
+
+
+def test_expression_info(hs):
+    # unit/hyperscan/expr_info.cpp: widths of plain literals
+    class Info(C.Structure):
+        _fields_ = [("min_width", C.c_uint), ("max_width", C.c_uint), ("unordered_matches", C.c_char),
+                    ("matches_at_eod", C.c_char), ("matches_only_at_eod", C.c_char)]
+    L = hs.lib()
+    L.hs_expression_info.argtypes = [C.c_char_p, C.c_uint, C.POINTER(C.POINTER(Info)),
+                                     C.POINTER(C.POINTER(hs.CompileError))]
+    info = C.POINTER(Info)()
+    err = C.POINTER(hs.CompileError)()
+    assert L.hs_expression_info(rb"foo\.bar", 0, C.byref(info), C.byref(err)) == 0
+    assert (info.contents.min_width, info.contents.max_width) == (7, 7)
+    assert info.contents.unordered_matches == b"\0" and info.contents.matches_at_eod == b"\0"
+    C.CDLL(None).free(info)
+    assert L.hs_expression_info(b"foo.*bar", 0, C.byref(info), C.byref(err)) == hs.HS_COMPILER_ERROR
+    assert err and err.contents.message
+    L.hs_free_compile_error(err)
+    assert L.hs_expression_info(None, 0, C.byref(info), C.byref(err)) == hs.HS_COMPILER_ERROR
+    L.hs_free_compile_error(err)
