@@ -106,6 +106,12 @@ def lib():
         L.hs_scratch_size.argtypes = [vp, C.POINTER(C.c_size_t)]
         L.hs_free_scratch.argtypes = [vp]
         L.hs_scan.argtypes = [vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
+        L.hs_open_stream.argtypes = [vp, C.c_uint, C.POINTER(vp)]
+        L.hs_scan_stream.argtypes = [vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
+        L.hs_close_stream.argtypes = [vp, vp, MATCH_CB, vp]
+        L.hs_reset_stream.argtypes = [vp, C.c_uint, vp, MATCH_CB, vp]
+        L.hs_copy_stream.argtypes = [C.POINTER(vp), vp]
+        L.hs_reset_and_copy_stream.argtypes = [vp, vp, vp, MATCH_CB, vp]
         L.hs_b200_scan_blocks.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, BLOCK_CB, vp, u64p]
         L.hs_b200_corpus_upload.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
         L.hs_b200_corpus_wrap.argtypes = [vp, C.c_size_t, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
@@ -403,3 +409,41 @@ def postprocess_matches(db, recs):
 
 def launch_count():
     return int(lib().hs_b200_launch_count())
+
+
+class Stream:
+    """hs_open_stream / hs_scan_stream / hs_close_stream."""
+
+    def __init__(self, db, ptr=None):
+        self.db = db
+        self.ptr = ptr or C.c_void_p()
+        if ptr is None:
+            _check(lib().hs_open_stream(db.ptr, 0, C.byref(self.ptr)), "hs_open_stream")
+
+    def scan(self, data, scratch, stop_after=0):
+        """Returns (rc, [(id, to), ...]) for one write."""
+        a = _as_u8(data)
+        out = []
+
+        def cb(i, frm, to, flags, ctx):
+            out.append((int(i), int(to)))
+            return 1 if (stop_after and len(out) >= stop_after) else 0
+
+        keep = np.zeros(1, dtype=np.uint8) if a.size == 0 else a
+        rc = lib().hs_scan_stream(self.ptr, keep.ctypes.data, a.size, 0, scratch.ptr, MATCH_CB(cb), None)
+        return rc, out
+
+    def copy(self):
+        p = C.c_void_p()
+        _check(lib().hs_copy_stream(C.byref(p), self.ptr), "hs_copy_stream")
+        return Stream(self.db, p)
+
+    def reset(self, scratch):
+        _check(lib().hs_reset_stream(self.ptr, 0, scratch.ptr, MATCH_CB(), None))
+
+    def close(self, scratch):
+        if self.ptr:
+            rc = lib().hs_close_stream(self.ptr, scratch.ptr, MATCH_CB(), None)
+            self.ptr = C.c_void_p()
+            return rc
+        return HS_SUCCESS

@@ -1696,4 +1696,200 @@ hs_error_t hs_scan(const hs_database_t *db, const char *data, unsigned int lengt
     return r;
 }
 
+/* ---- streaming mode (src/runtime.c:542-977, pure-literal databases) ------------------
+ *
+ * A stream carries the last historyRequired (<= 7) bytes it has seen, its
+ * offset, a broken/exhausted status and the single-match reports already
+ * raised.  hs_scan_stream scans (history ++ write) as one block on the device
+ * and delivers the matches that END inside the write, at stream offsets --
+ * the restatement of pureLiteralStreamExec / hwlmExecStreaming
+ * (src/runtime.c:801-829, src/hwlm/hwlm.c:201-239) with the look-behind made
+ * explicit. */
+
+struct hs_stream {
+    u32 magic;
+    const hs_database_t *db;
+    u64 offset;
+    u32 hreq, hlen;
+    u8 hist[16];
+    u8 status; /* 1 = terminated by the callback, 2 = all reports exhausted */
+    std::unordered_set<u32> *seen;
+};
+
+static const u32 STREAM_MAGIC = 0x4d525453; /* "STRM" */
+
+static bool validStream(const hs_stream *st) { return st && st->magic == STREAM_MAGIC && st->seen; }
+
+static void resetStreamState(hs_stream *st) {
+    st->offset = 0;
+    st->hlen = 0;
+    st->status = 0;
+    st->seen->clear();
+}
+
+hs_error_t hs_open_stream(const hs_database_t *db, unsigned int flags, hs_stream_t **stream) {
+    (void)flags;
+    if (!stream) {
+        return HS_INVALID;
+    }
+    *stream = nullptr;
+    hs_error_t err = validDb(db);
+    if (err != HS_SUCCESS) {
+        return err;
+    }
+    const RoseEngine *rose = dbRose(db);
+    if ((uintptr_t)rose % 16) {
+        return HS_INVALID;
+    }
+    if (rose->mode != MODE_STREAM) {
+        return HS_DB_MODE_ERROR;
+    }
+    if (rose->runtimeImpl != RUNTIME_PURE_LITERAL || rose->historyRequired > sizeof(((hs_stream *)0)->hist)) {
+        return HS_ARCH_ERROR;
+    }
+    hs_stream *st = (hs_stream *)g_stream_alloc(sizeof(hs_stream));
+    err = checkAlloc(st);
+    if (err != HS_SUCCESS) {
+        g_stream_free(st);
+        return err;
+    }
+    memset(st, 0, sizeof(*st));
+    st->magic = STREAM_MAGIC;
+    st->db = db;
+    st->hreq = rose->historyRequired;
+    st->seen = new (std::nothrow) std::unordered_set<u32>();
+    if (!st->seen) {
+        g_stream_free(st);
+        return HS_NOMEM;
+    }
+    *stream = st;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_scan_stream(hs_stream_t *st, const char *data, unsigned int length, unsigned int flags,
+                          hs_scratch_t *scratch, match_event_handler onEvent, void *context) {
+    (void)flags;
+    if (!validStream(st) || !scratch || !data || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    hs_error_t r = HS_SUCCESS;
+    if (st->status & 1) {
+        r = HS_SCAN_TERMINATED; /* the stream is broken: src/runtime.c:883-893 */
+    } else if (!(st->status & 2) && length != 0) {
+        const DevImage *im = nullptr;
+        r = findImage(scratch, st->db, &im);
+        std::vector<DevMatch> matches;
+        std::vector<char> buf;
+        if (r == HS_SUCCESS) {
+            buf.resize((size_t)st->hlen + length);
+            memcpy(buf.data(), st->hist, st->hlen);
+            memcpy(buf.data() + st->hlen, data, length);
+            const unsigned long long off = 0;
+            const unsigned total = (unsigned)buf.size();
+            r = scanHostBlocks(im, scratch, buf.data(), &off, &total, 1, &matches);
+        }
+        if (r == HS_SUCCESS) {
+            const RoseEngine *rose = dbRose(st->db);
+            for (const DevMatch &m : matches) {
+                if (m.to <= st->hlen) {
+                    continue; /* ended in the look-behind: raised by an earlier write */
+                }
+                if (im->exhaustible.count(m.id) && !st->seen->insert(m.id).second) {
+                    continue; /* HS_FLAG_SINGLEMATCH: already raised on this stream */
+                }
+                if (onEvent && onEvent(m.id, 0, st->offset - st->hlen + m.to, 0, context)) {
+                    st->status |= 1;
+                    r = HS_SCAN_TERMINATED;
+                    break;
+                }
+            }
+            if (r == HS_SUCCESS) {
+                if (rose->canExhaust && rose->ekeyCount && st->seen->size() >= im->exhaustible.size()) {
+                    st->status |= 2;
+                }
+                /* maintainHistoryBuffer (src/runtime.c:478-508) */
+                const size_t keep = std::min<size_t>(buf.size(), st->hreq);
+                memcpy(st->hist, buf.data() + buf.size() - keep, keep);
+                st->hlen = (u32)keep;
+                st->offset += length;
+            }
+        }
+    }
+    unmarkInUse(scratch);
+    return r;
+}
+
+hs_error_t hs_close_stream(hs_stream_t *st, hs_scratch_t *scratch, match_event_handler onEvent,
+                           void *context) {
+    (void)scratch; /* pure-literal databases have no end-of-data work (src/runtime.c:1005-1050) */
+    (void)onEvent;
+    (void)context;
+    if (!validStream(st)) {
+        return HS_INVALID;
+    }
+    st->magic = 0;
+    delete st->seen;
+    g_stream_free(st);
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_reset_stream(hs_stream_t *st, unsigned int flags, hs_scratch_t *scratch,
+                           match_event_handler onEvent, void *context) {
+    (void)flags;
+    (void)scratch;
+    (void)onEvent;
+    (void)context;
+    if (!validStream(st)) {
+        return HS_INVALID;
+    }
+    resetStreamState(st);
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_copy_stream(hs_stream_t **to_id, const hs_stream_t *from_id) {
+    if (!to_id) {
+        return HS_INVALID;
+    }
+    *to_id = nullptr;
+    if (!validStream(from_id)) {
+        return HS_INVALID;
+    }
+    hs_stream *st = (hs_stream *)g_stream_alloc(sizeof(hs_stream));
+    hs_error_t err = checkAlloc(st);
+    if (err != HS_SUCCESS) {
+        g_stream_free(st);
+        return err;
+    }
+    memcpy(st, from_id, sizeof(*st));
+    st->seen = new (std::nothrow) std::unordered_set<u32>(*from_id->seen);
+    if (!st->seen) {
+        g_stream_free(st);
+        return HS_NOMEM;
+    }
+    *to_id = st;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_reset_and_copy_stream(hs_stream_t *to_id, const hs_stream_t *from_id,
+                                    hs_scratch_t *scratch, match_event_handler onEvent,
+                                    void *context) {
+    (void)scratch;
+    (void)onEvent;
+    (void)context;
+    if (!validStream(to_id) || !validStream(from_id) || to_id == from_id) {
+        return HS_INVALID;
+    }
+    if (to_id->db != from_id->db) {
+        return HS_INVALID; /* src/runtime.c:758-760: streams of different databases */
+    }
+    std::unordered_set<u32> *keep = to_id->seen;
+    *keep = *from_id->seen;
+    memcpy(to_id, from_id, sizeof(*to_id));
+    to_id->seen = keep;
+    return HS_SUCCESS;
+}
+
 } /* extern "C" */

@@ -423,10 +423,10 @@ __device__ __forceinline__ uint2 lds64(u32 addr) {
  * same in-word position) into a[] at byte offset O (0..4): one funnel shift
  * per output word instead of two shifts per entry. */
 template <int O> __device__ __forceinline__ void orStream(u32 (&a)[6], const u32 (&E)[4]) {
-    if (O == 0) {
+    if constexpr (O == 0) {
 #pragma unroll
         for (int k = 0; k < 4; k++) a[k] |= E[k];
-    } else if (O == 4) {
+    } else if constexpr (O == 4) {
 #pragma unroll
         for (int k = 0; k < 4; k++) a[k + 1] |= E[k];
     } else {
@@ -480,8 +480,9 @@ __device__ __forceinline__ void laneFilter(const u32 (&w)[5], u32 tabAddr, u32 l
     }
     /* 32-bit entries: gather the entries of in-word position r for all four
      * words, then merge the stream with funnel shifts */
+    constexpr int RSTEP = KIND == FK_HASH64 ? 4 : STRIDE; /* (FK_HASH64 returned above) */
 #pragma unroll
-    for (int r = 0; r < 4; r += STRIDE) {
+    for (int r = 0; r < 4; r += RSTEP) {
         u32 E0[4], E1[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {

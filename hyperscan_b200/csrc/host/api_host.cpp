@@ -448,8 +448,9 @@ static bool checkMode(unsigned mode, std::string *why) {
             return false;
         }
     }
-    if (!(mode & HS_MODE_BLOCK)) {
-        *why = "This build of the B200 runtime compiles block-mode databases only.";
+    if (mode & HS_MODE_VECTORED) {
+        *why = "This build of the B200 runtime compiles block and streaming databases; vectored "
+               "mode is not supported.";
         return false;
     }
     return true;
@@ -632,6 +633,7 @@ static hs_error_t compileCommon(const char *const *expressions,
         }
         CompileOpts opts;
         opts.pureLiteralApi = litApi;
+        opts.streaming = (mode & HS_MODE_STREAM) != 0;
         if (platform && (platform->cpu_features & HS_CPU_FEATURES_AVX2)) {
             /* the caller targets AVX2+ reference runtimes: 16-bucket Teddy is
              * allowed and the database is stamped accordingly

@@ -103,6 +103,13 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
         if (p.s.size() > LIMIT_LITERAL_LENGTH) {
             throw CompileError{"Resource limit exceeded.", (int)p.index};
         }
+        if (opts.streaming && p.s.size() > 8) {
+            /* in streaming mode literals beyond the literal matcher's 8 bytes need
+             * the long-literal table and the full rose runtime
+             * (src/rose/rose_build_bytecode.cpp:292-296 isPureFloating) */
+            throw CompileError{"Streaming mode in this build supports literals of up to 8 bytes; "
+                               "longer literals need the long literal table.", (int)p.index};
+        }
         auto it = idHighlander.find(p.report);
         if (it == idHighlander.end()) {
             idHighlander[p.report] = {p.singlematch, p.index};
@@ -310,7 +317,15 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
     r.pureLiteral = opts.pureLiteralApi ? 1 : 0;
     r.runtimeImpl = RUNTIME_PURE_LITERAL;
     r.canExhaust = allHighlander ? 1 : 0;
-    r.mode = MODE_BLOCK;
+    r.mode = opts.streaming ? MODE_STREAM : MODE_BLOCK;
+    u32 maxLen = 0;
+    for (const auto &pi : pats) {
+        maxLen = std::max<u32>(maxLen, (u32)pi.folded.size());
+    }
+    /* matches may start in earlier writes: keep the last maxLen-1 bytes
+     * (calcHistoryRequired, src/rose/rose_build_misc.cpp; updated by HWLM) */
+    const u32 historyRequired = opts.streaming && maxLen > 1 ? maxLen - 1 : 0;
+    r.historyRequired = historyRequired;
     r.ekeyCount = (u32)ekeys.size();
     r.dkeyCount = (u32)dkeys.size();
     r.dkeyLogSize = fatbitSize(r.dkeyCount);
@@ -340,6 +355,7 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
     so.groups_size = 1;
     cur += so.groups_size;
     so.history = cur;
+    cur += historyRequired;
     so.exhausted = cur;
     so.exhausted_size = mmbitSize(r.ekeyCount);
     cur += so.exhausted_size;

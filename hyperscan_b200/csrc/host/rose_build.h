@@ -30,6 +30,7 @@ struct LitPattern {
 
 struct CompileOpts {
     bool pureLiteralApi = false; /* hs_compile_lit*: sets RoseEngine.pureLiteral */
+    bool streaming = false;      /* HS_MODE_STREAM: history + per-stream state (literals <= 8 bytes) */
     u64 platform = PLATFORM_NOAVX2 | PLATFORM_NOAVX512 | PLATFORM_NOAVX512VBMI;
     HwlmBuildOpts hwlm;
 };

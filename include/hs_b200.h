@@ -194,6 +194,25 @@ hs_error_t hs_scan(const hs_database_t *db, const char *data,
                    hs_scratch_t *scratch, match_event_handler onEvent,
                    void *context);
 
+/* --- streaming mode (src/hs_runtime.h:148-475; src/runtime.c:542-977).  Built
+ * for literal databases compiled with HS_MODE_STREAM (literals up to 8 bytes:
+ * the pure-literal streaming runtime of the reference, src/runtime.c:801-829).
+ * Stream compression (hs_compress_stream / hs_expand_stream) is not built. */
+struct hs_stream;
+typedef struct hs_stream hs_stream_t;       /* src/hs_runtime.h:54 */
+hs_error_t hs_open_stream(const hs_database_t *db, unsigned int flags, hs_stream_t **stream);
+hs_error_t hs_scan_stream(hs_stream_t *id, const char *data, unsigned int length,
+                          unsigned int flags, hs_scratch_t *scratch,
+                          match_event_handler onEvent, void *ctxt);
+hs_error_t hs_close_stream(hs_stream_t *id, hs_scratch_t *scratch,
+                           match_event_handler onEvent, void *ctxt);
+hs_error_t hs_reset_stream(hs_stream_t *id, unsigned int flags, hs_scratch_t *scratch,
+                           match_event_handler onEvent, void *context);
+hs_error_t hs_copy_stream(hs_stream_t **to_id, const hs_stream_t *from_id);
+hs_error_t hs_reset_and_copy_stream(hs_stream_t *to_id, const hs_stream_t *from_id,
+                                    hs_scratch_t *scratch, match_event_handler onEvent,
+                                    void *context);
+
 /* ------------------------------------------------------------------------
  * Part 2: B200 batch / device-resident extension
  * ---------------------------------------------------------------------- */

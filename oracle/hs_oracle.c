@@ -93,6 +93,7 @@ struct scan {
     size_t cap, n, stop_after;
     u32 block;
     u32 last_match;      /* FDR_LIT_FLAG_NOREPEAT state (fdr.c:737 last_match_id) */
+    u64 base_offset;     /* streaming: stream offset of buf[0] (history included) */
 };
 
 /* ---- rose literal programs --------------------------------------------------------- */
@@ -142,7 +143,7 @@ static int dedupe(struct scan *s, u64 offset, u64 to_offset, u32 dkey) {
 /* roseDeliverReport + roseReport (src/report.h:301-337,
  * src/rose/program_runtime.c:464-481).  Returns 0 to halt. */
 static int deliver_report(struct scan *s, u64 end, u32 onmatch, s32 adj, u32 ekey) {
-    if (s->cb && s->cb(onmatch, 0, end + adj, 0, s->cb_ctx)) {
+    if (s->cb && s->cb(onmatch, 0, s->base_offset + end + adj, 0, s->cb_ctx)) {
         s->terminated = 1;
         return 0;
     }
@@ -655,4 +656,133 @@ API double oracle_scan_blocks_mt(const void *db, const char *data, const unsigne
         *total_bytes = b;
     }
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/* ---- streaming ----------------------------------------------------------------------------
+ * hs_open_stream / hs_scan_stream / hs_close_stream for pure-literal databases
+ * (src/runtime.c:542-977): pureLiteralStreamExec = hwlmExecStreaming over the
+ * write with the last historyRequired bytes of the stream as look-behind
+ * (src/hwlm/hwlm.c:201-239, src/fdr/fdr.c:853-881); stream state = status byte,
+ * history, exhaustion vector (src/runtime.c:478-508 maintainHistoryBuffer).
+ * Restated as: scan (history ++ write), report ends inside the write only. */
+
+enum { RE_historyRequired = 16 };
+
+struct ostream {
+    const void *db;
+    u64 offset;
+    u32 hlen, hreq;
+    u8 hist[128];
+    u8 status;           /* 1 terminated, 2 exhausted */
+    u8 *work;            /* evec | dlog0 | dlog1 (evec persists across writes) */
+    size_t work_bytes;
+};
+
+API void *oracle_open_stream(const void *db) {
+    const struct db_header *h = (const struct db_header *)db;
+    if (!h || h->magic != 0xdbdbdbdbU) {
+        return NULL;
+    }
+    const u8 *rose = (const u8 *)db + h->bytecode;
+    if (rd32(rose + RE_mode) != 2 || rose[RE_runtimeImpl] != 1) { /* HS_MODE_STREAM, PURE_LITERAL */
+        return NULL;
+    }
+    struct ostream *st = (struct ostream *)calloc(1, sizeof(*st));
+    st->db = db;
+    st->hreq = rd32(rose + RE_historyRequired);
+    if (st->hreq > sizeof(st->hist)) {
+        free(st);
+        return NULL;
+    }
+    st->work_bytes = work_size(db);
+    st->work = (u8 *)calloc(1, st->work_bytes);
+    return st;
+}
+
+API int oracle_scan_stream(void *stream, const char *data, unsigned len, user_cb cb, void *ctx) {
+    struct ostream *st = (struct ostream *)stream;
+    if (!st || !data) {
+        return -1;
+    }
+    if (st->status & 1) {
+        return -3; /* HS_SCAN_TERMINATED: the stream is broken (src/runtime.c:883-893) */
+    }
+    if ((st->status & 2) || len == 0) {
+        return 0;
+    }
+    const struct db_header *h = (const struct db_header *)st->db;
+    const u8 *rose = (const u8 *)st->db + h->bytecode;
+    u8 *buf = (u8 *)malloc((size_t)st->hlen + len + 8);
+    memcpy(buf, st->hist, st->hlen);
+    memcpy(buf + st->hlen, data, len);
+    struct scan s;
+    memset(&s, 0, sizeof(s));
+    s.rose = rose;
+    s.buf = buf;
+    s.len = (size_t)st->hlen + len;
+    s.base_offset = st->offset - st->hlen;
+    s.cb = cb;
+    s.cb_ctx = ctx;
+    s.ekeyCount = rd32(rose + RE_ekeyCount);
+    s.dkeyCount = rd32(rose + RE_dkeyCount);
+    const size_t eb = (s.ekeyCount + 7) / 8 + 1, dbytes = (s.dkeyCount + 7) / 8 + 1;
+    s.evec = st->work;                      /* persists for the life of the stream */
+    s.dlog[0] = st->work + eb;
+    s.dlog[1] = st->work + eb + dbytes;
+    memset(s.dlog[0], 0, 2 * dbytes);
+    s.dedupe_offset = ~0ULL;
+    s.groups = rd64(rose + RE_initialGroups) & rd64(rose + RE_floating_group_mask);
+    hwlm_exec(&s, rose + rd32(rose + RE_fmatcherOffset), st->hlen);
+    int rv = 0;
+    if (s.terminated == 1) {
+        st->status |= 1;
+        rv = -3;
+    } else if (s.terminated == 2) {
+        rv = -13;
+    } else {
+        if (all_exhausted(&s)) {
+            st->status |= 2;
+        }
+        /* maintainHistoryBuffer: keep the last hreq bytes of the stream */
+        const size_t keep = s.len < st->hreq ? s.len : st->hreq;
+        memmove(st->hist, buf + s.len - keep, keep);
+        st->hlen = (u32)keep;
+        st->offset += len;
+    }
+    free(buf);
+    return rv;
+}
+
+API int oracle_close_stream(void *stream) {
+    struct ostream *st = (struct ostream *)stream;
+    if (st) {
+        free(st->work);
+        free(st);
+    }
+    return 0;
+}
+
+API long oracle_stream_collect(const void *db, const char *data, const unsigned *write_lengths,
+                               size_t nwrites, struct rec16 *out, size_t cap, size_t stop_after,
+                               int *last_err) {
+    void *st = oracle_open_stream(db);
+    if (!st) {
+        return -1;
+    }
+    struct collect c = {out, cap, 0, stop_after, 0};
+    int rv = 0;
+    size_t pos = 0;
+    for (size_t i = 0; i < nwrites; i++) {
+        c.block = (u32)i;
+        rv = oracle_scan_stream(st, data + pos, write_lengths[i], collect_cb, &c);
+        pos += write_lengths[i];
+        if (rv != 0) {
+            break;
+        }
+    }
+    oracle_close_stream(st);
+    if (last_err) {
+        *last_err = rv;
+    }
+    return (long)c.n;
 }

@@ -28,6 +28,9 @@ def lib():
         L.oracle_scan_blocks_mt.restype = C.c_double
         L.oracle_scan_blocks_mt.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_uint, C.c_uint,
                                             C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+        L.oracle_stream_collect.restype = C.c_long
+        L.oracle_stream_collect.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t,
+                                            C.POINTER(C.c_int)]
         L.oracle_hwlm_exec.restype = C.c_long
         L.oracle_hwlm_exec.argtypes = [vp, vp, C.c_size_t, C.c_size_t, C.c_ulonglong, vp, C.c_size_t,
                                        C.c_size_t]
@@ -46,6 +49,23 @@ def scan_collect(db_ptr, data, offsets, lengths, stop_after=0, cap=None):
         err = C.c_int()
         n = lib().oracle_scan_collect(db_ptr, keep.ctypes.data, off.ctypes.data, ln.ctypes.data, off.size,
                                       out.ctypes.data, cap, stop_after, C.byref(err))
+        if n <= cap:
+            return out[:n], err.value
+        cap = int(n) + 16
+
+
+def stream_collect(db_ptr, data, write_lengths, stop_after=0):
+    a = _u8(data)
+    keep = a if a.size else np.zeros(1, dtype=np.uint8)
+    wl = np.ascontiguousarray(write_lengths, dtype=np.uint32)
+    cap = 1 << 18
+    while True:
+        out = np.zeros(cap, dtype=REC_DTYPE)
+        err = C.c_int()
+        n = lib().oracle_stream_collect(db_ptr, keep.ctypes.data, wl.ctypes.data, wl.size, out.ctypes.data,
+                                        cap, stop_after, C.byref(err))
+        if n < 0:
+            raise RuntimeError("oracle stream open failed")
         if n <= cap:
             return out[:n], err.value
         cap = int(n) + 16

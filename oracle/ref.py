@@ -52,6 +52,8 @@ def lib(isa=None):
         L.ref_scan_collect.restype = C.c_long
         L.ref_scan_collect.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t,
                                        C.POINTER(C.c_int)]
+        L.ref_stream_collect.restype = C.c_long
+        L.ref_stream_collect.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_int)]
         L.ref_scan_blocks_mt.restype = C.c_double
         L.ref_scan_blocks_mt.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_uint, C.c_uint,
                                          C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
@@ -90,6 +92,26 @@ def scan_collect(db_ptr, data, offsets, lengths, stop_after=0, isa=None, cap=Non
                                       out.ctypes.data, cap, stop_after, C.byref(err))
         if n < 0:
             raise RuntimeError("reference hs_alloc_scratch failed: %d" % n)
+        if n <= cap:
+            return out[:n], err.value
+        cap = int(n) + 16
+
+
+def stream_collect(db_ptr, data, write_lengths, stop_after=0, isa=None):
+    """Reference streaming scan of `data` cut into consecutive writes; records
+    (id, write index, to = stream offset) in delivery order + last error."""
+    a = _u8(data)
+    keep = a if a.size else np.zeros(1, dtype=np.uint8)
+    wl = np.ascontiguousarray(write_lengths, dtype=np.uint32)
+    assert int(wl.sum()) == a.size
+    cap = 1 << 18
+    while True:
+        out = np.zeros(cap, dtype=REC_DTYPE)
+        err = C.c_int()
+        n = lib(isa).ref_stream_collect(db_ptr, keep.ctypes.data, wl.ctypes.data, wl.size, out.ctypes.data,
+                                        cap, stop_after, C.byref(err))
+        if n < 0:
+            raise RuntimeError("reference stream open failed: %d" % n)
         if n <= cap:
             return out[:n], err.value
         cap = int(n) + 16

@@ -13,6 +13,7 @@
  *                        scratch each, `repeats` passes over a set of blocks,
  *                        counting callback; returns wall seconds.
  *   ref_scan_collect     scan blocks and collect (block,id,to) records.
+ *   ref_stream_collect   one stream cut into writes, (id, write, to) records.
  *   ref_layout_dump      print sizeof/offsetof of every bytecode struct our
  *                        ref_layout.h restates (golden file for layout tests).
  */
@@ -170,6 +171,47 @@ API long ref_scan_collect(const hs_database_t *db, const char *data,
         if (rv != HS_SUCCESS) {
             break;
         }
+    }
+    if (last_err) {
+        *last_err = (int)rv;
+    }
+    hs_free_scratch(scratch);
+    return (long)c.n;
+}
+
+/* Streaming: one stream, the data cut into `nwrites` consecutive writes
+ * (hs_open_stream / hs_scan_stream / hs_close_stream, src/runtime.c:542-977).
+ * Records (id, write index, to) in delivery order; `to` is the stream offset. */
+API long ref_stream_collect(const hs_database_t *db, const char *data,
+                            const unsigned *write_lengths, size_t nwrites,
+                            struct rec16 *out, size_t cap, size_t stop_after,
+                            int *last_err) {
+    hs_scratch_t *scratch = NULL;
+    hs_error_t err = hs_alloc_scratch(db, &scratch);
+    if (err != HS_SUCCESS) {
+        return (long)err;
+    }
+    hs_stream_t *stream = NULL;
+    err = hs_open_stream(db, 0, &stream);
+    if (err != HS_SUCCESS) {
+        hs_free_scratch(scratch);
+        return (long)err;
+    }
+    struct collect_ctx c = {out, cap, 0, 0, stop_after};
+    hs_error_t rv = HS_SUCCESS;
+    size_t pos = 0;
+    for (size_t i = 0; i < nwrites; i++) {
+        c.block = (unsigned)i;
+        rv = hs_scan_stream(stream, data + pos, write_lengths[i], 0, scratch,
+                            collect_cb, &c);
+        pos += write_lengths[i];
+        if (rv != HS_SUCCESS) {
+            break;
+        }
+    }
+    hs_error_t cv = hs_close_stream(stream, scratch, collect_cb, &c);
+    if (rv == HS_SUCCESS) {
+        rv = cv;
     }
     if (last_err) {
         *last_err = (int)rv;

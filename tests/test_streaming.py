@@ -1,0 +1,125 @@
+"""Streaming mode for literal databases (the
+pure-literal part): our compiler's HS_MODE_STREAM databases drive the UNMODIFIED
+reference stream runtime (hs_open_stream / hs_scan_stream / hs_close_stream) to
+the matches the definition demands over any cut of the data into writes; the
+C restatement reproduces the reference's callbacks, order and termination; on
+the GPU box the device stream API does the same."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from hyperscan_b200 import synth
+import oracle.brute as brute
+import oracle.port as port
+
+
+def make(hs, nl, seed, lo=2):
+    lits, flags, ids = synth.literal_set(nl, min_len=1 if nl < 10 else lo, max_len=8, seed=seed,
+                                         caseless_frac=0.2, alphabet=b"abcdef", singlematch_frac=0.15)
+    ids = [i // 2 for i in ids]
+    fm = {}
+    for k in range(nl):
+        fm.setdefault(ids[k], flags[k] & 8)
+        flags[k] = (flags[k] & ~8) | fm[ids[k]]
+    db = hs.compile_lit_multi(lits, flags, ids, mode=hs.HS_MODE_STREAM)
+    data, off, ln = synth.ragged_corpus([7000], lits, seed=seed + 1, plant_per_kb=15, alphabet=b"abcdefAB")
+    return lits, flags, ids, db, data, off, ln
+
+
+def cuts_of(n, seed, k=40):
+    rng = np.random.default_rng(seed)
+    cuts = sorted(set(rng.integers(0, n, size=k).tolist() + [0, n, 1, 2, 3, n - 1]))
+    return np.diff(np.array(cuts)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("nl", [1, 6, 40, 300, 1500])
+def test_streaming_databases_on_reference_runtime(hs, ref, nl):
+    lits, flags, ids, db, data, off, ln = make(hs, nl, nl)
+    want = sorted((int(r["id"]), int(r["to"])) for r in brute.scan_blocks(lits, flags, ids, data, off, ln))
+    for seed in (1, 2):
+        wl = cuts_of(data.size, seed)
+        a, ea = ref.stream_collect(db.ptr, data, wl)
+        assert ea == 0 and sorted((int(r["id"]), int(r["to"])) for r in a) == want
+        b, eb = port.stream_collect(db.ptr, data, wl)
+        assert eb == 0 and np.array_equal(a, b)          # same callbacks in the same order
+        a, ea = ref.stream_collect(db.ptr, data, wl, stop_after=4)
+        b, eb = port.stream_collect(db.ptr, data, wl, stop_after=4)
+        assert ea == eb == hs.HS_SCAN_TERMINATED and np.array_equal(a, b)
+    # byte-at-a-time writes
+    small = data[:300]
+    a, _ = ref.stream_collect(db.ptr, small, np.ones(300, dtype=np.uint32))
+    b, _ = port.stream_collect(db.ptr, small, np.ones(300, dtype=np.uint32))
+    assert np.array_equal(a, b)
+
+
+def test_stream_compile_rules(hs, ref):
+    import ctypes
+    db = hs.compile_lit_multi([b"abcdefgh", b"xy"], mode=hs.HS_MODE_STREAM)
+    sz = ctypes.c_size_t()
+    assert hs.lib().hs_stream_size(db.ptr, ctypes.byref(sz)) == 0
+    assert sz.value == 16 + 1 + 1 + 7            # struct hs_stream + status + groups + history (src/runtime.c:1058)
+    rsz = ctypes.c_size_t()
+    R = ref.lib()
+    R.hs_stream_size.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+    assert R.hs_stream_size(db.ptr, ctypes.byref(rsz)) == 0 and rsz.value == sz.value
+    info = ctypes.c_void_p()
+    assert hs.lib().hs_database_info(db.ptr, ctypes.byref(info)) == 0
+    assert b"Mode: STREAM" in ctypes.string_at(info)
+    with pytest.raises(hs.HsError) as e:          # long literals need the long-literal table
+        hs.compile_lit_multi([b"abcdefghi"], mode=hs.HS_MODE_STREAM)
+    assert "long literal" in e.value.message
+    with pytest.raises(hs.HsError):
+        hs.compile_lit_multi([b"abc"], mode=hs.HS_MODE_VECTORED)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nl", [1, 6, 40, 300, 1500])
+def test_device_stream_api_equals_reference(hs, ref, nl):
+    lits, flags, ids, db, data, off, ln = make(hs, nl, nl + 50)
+    scratch = hs.Scratch(db)
+    for seed in (3, 4):
+        wl = cuts_of(data.size, seed, k=25)
+        want, err = ref.stream_collect(db.ptr, data, wl)
+        st = hs.Stream(db)
+        got, pos = [], 0
+        for i, n in enumerate(wl):
+            rc, out = st.scan(data[pos:pos + int(n)], scratch)
+            assert rc == hs.HS_SUCCESS
+            got += [(i, idv, to) for (idv, to) in out]
+            pos += int(n)
+        assert st.close(scratch) == hs.HS_SUCCESS
+        # per write the API promises non-decreasing `to`; compare as sets per write
+        exp = sorted((int(r["block"]), int(r["id"]), int(r["to"])) for r in want)
+        assert sorted(got) == exp
+        tos = [t for (_, _, t) in got]
+        assert tos == sorted(tos)
+
+
+@pytest.mark.gpu
+def test_device_stream_termination_copy_reset(hs, ref):
+    lits, flags, ids, db, data, off, ln = make(hs, 40, 99)
+    scratch = hs.Scratch(db)
+    st = hs.Stream(db)
+    rc, out = st.scan(data[:3000], scratch, stop_after=3)
+    assert rc == hs.HS_SCAN_TERMINATED and len(out) == 3
+    rc, out = st.scan(data[3000:4000], scratch)           # broken stream stays broken
+    assert rc == hs.HS_SCAN_TERMINATED and out == []
+    st.reset(scratch)
+    rc, a = st.scan(data[:2000], scratch)
+    assert rc == 0
+    twin = st.copy()                                       # same state, independent afterwards
+    rc, b1 = st.scan(data[2000:5000], scratch)
+    rc, b2 = twin.scan(data[2000:5000], scratch)
+    assert b1 == b2 and len(b1) > 0
+    want, _ = ref.stream_collect(db.ptr, data[:5000], np.array([2000, 3000], dtype=np.uint32))
+    assert sorted(a + b1) == sorted((int(r["id"]), int(r["to"])) for r in want)
+    L = hs.lib()
+    assert L.hs_scan_stream(None, b"x", 1, 0, scratch.ptr, hs.MATCH_CB(), None) == hs.HS_INVALID
+    blk = hs.compile_lit_multi([b"abc"])                  # block database: wrong mode for streams
+    p = C.c_void_p()
+    assert L.hs_open_stream(blk.ptr, 0, C.byref(p)) == hs.HS_DB_MODE_ERROR
+    rc, _ = hs.scan(db, b"abc", scratch)                  # and a stream database is refused by hs_scan
+    assert rc == hs.HS_DB_MODE_ERROR
+    st.close(scratch)
+    twin.close(scratch)
