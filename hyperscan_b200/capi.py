@@ -106,6 +106,11 @@ def lib():
         L.hs_scratch_size.argtypes = [vp, C.POINTER(C.c_size_t)]
         L.hs_free_scratch.argtypes = [vp]
         L.hs_scan.argtypes = [vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
+        L.hs_b200_streams_open.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp)]
+        L.hs_b200_streams_scan.argtypes = [vp, vp, vp, vp, vp, BLOCK_CB, vp, u64p]
+        L.hs_b200_streams_close.argtypes = [vp]
+        L.hs_b200_streams_state_bytes.argtypes = [vp]
+        L.hs_b200_streams_state_bytes.restype = C.c_size_t
         L.hs_open_stream.argtypes = [vp, C.c_uint, C.POINTER(vp)]
         L.hs_scan_stream.argtypes = [vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
         L.hs_close_stream.argtypes = [vp, vp, MATCH_CB, vp]
@@ -447,3 +452,37 @@ class Stream:
             self.ptr = C.c_void_p()
             return rc
         return HS_SUCCESS
+
+
+class StreamSet:
+    """hs_b200_streams_open / scan / close: many streams, state resident in HBM."""
+
+    def __init__(self, db, nstreams, device=0):
+        self.db = db
+        self.n = nstreams
+        self.ptr = C.c_void_p()
+        _check(lib().hs_b200_streams_open(db.ptr, nstreams, device, C.byref(self.ptr)), "streams_open")
+
+    def scan(self, data, offsets, lengths, scratch, collect=True):
+        a = _as_u8(data)
+        off, ln = _blocks(offsets, lengths)
+        assert off.size == self.n
+        n = C.c_ulonglong()
+        recs = []
+
+        def cb(block, i, frm, to, flags, ctx):
+            recs.append((i, block, to))
+            return 0
+
+        keep = a if a.size else np.zeros(1, dtype=np.uint8)
+        rc = lib().hs_b200_streams_scan(self.ptr, keep.ctypes.data, off.ctypes.data, ln.ctypes.data, scratch.ptr,
+                                        BLOCK_CB(cb) if collect else BLOCK_CB(), None, C.byref(n))
+        _check(rc, "streams_scan")
+        if not collect:
+            return int(n.value)
+        return np.array(recs, dtype=MATCH_DTYPE) if recs else np.zeros(0, dtype=MATCH_DTYPE)
+
+    def close(self):
+        if self.ptr:
+            lib().hs_b200_streams_close(self.ptr)
+            self.ptr = C.c_void_p()

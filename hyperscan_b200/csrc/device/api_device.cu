@@ -1892,4 +1892,219 @@ hs_error_t hs_reset_and_copy_stream(hs_stream_t *to_id, const hs_stream_t *from_
     return HS_SUCCESS;
 }
 
+/* ---- stream sets: many streams, one write each per call, state resident in HBM ------
+ * (BASELINE config 4 shape: 16 M x 1 KB streams).  Per stream 16 bytes live in
+ * HBM: 7 look-behind bytes + their count, and the 64-bit stream offset.  A scan
+ * copies the writes into a pitched corpus (16-byte header per stream), a
+ * kernel drops each stream's look-behind into its header, the block kernel
+ * scans the lot (blocks = look-behind ++ write, found by division), records
+ * come out at stream offsets, and a kernel rolls history and offsets forward. */
+
+struct hs_b200_stream_set {
+    const hs_database_t *db;
+    int device;
+    size_t nstreams;
+    u32 histReq;
+    u8 *d_hist;     /* 8 bytes per stream */
+    u64 *d_offset;
+    u32 *d_len;     /* per-write lengths when they differ */
+    hs_b200_corpus corpus; /* pitched staging, reused */
+    u32 pitchCap;
+};
+
+hs_error_t hs_b200_streams_open(const hs_database_t *db, size_t nstreams, int device,
+                                hs_b200_stream_set_t **set) {
+    if (!set || nstreams == 0 || nstreams > 0xfffffff0u) {
+        return HS_INVALID;
+    }
+    *set = nullptr;
+    hs_error_t err = validDb(db);
+    if (err != HS_SUCCESS) {
+        return err;
+    }
+    const RoseEngine *rose = dbRose(db);
+    if (rose->mode != MODE_STREAM) {
+        return HS_DB_MODE_ERROR;
+    }
+    if (rose->runtimeImpl != RUNTIME_PURE_LITERAL || rose->historyRequired > 7 || rose->ekeyCount) {
+        /* HS_FLAG_SINGLEMATCH state per stream is kept only by hs_scan_stream */
+        return HS_ARCH_ERROR;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        return HS_ARCH_ERROR;
+    }
+    hs_b200_stream_set *s = new (std::nothrow) hs_b200_stream_set();
+    if (!s) {
+        return HS_NOMEM;
+    }
+    s->db = db;
+    s->device = device;
+    s->nstreams = nstreams;
+    s->histReq = rose->historyRequired;
+    s->d_hist = nullptr;
+    s->d_offset = nullptr;
+    s->d_len = nullptr;
+    s->pitchCap = 0;
+    cudaError_t e = cudaMalloc(&s->d_hist, nstreams * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_offset, nstreams * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_len, nstreams * 4);
+    if (e == cudaSuccess) e = cudaMemset(s->d_hist, 0, nstreams * 8);
+    if (e == cudaSuccess) e = cudaMemset(s->d_offset, 0, nstreams * 8);
+    if (e != cudaSuccess) {
+        hs_b200_streams_close(s);
+        return e == cudaErrorMemoryAllocation ? HS_NOMEM : HS_UNKNOWN_ERROR;
+    }
+    *set = s;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_b200_streams_close(hs_b200_stream_set_t *s) {
+    if (!s) {
+        return HS_SUCCESS;
+    }
+    cudaFree(s->d_hist);
+    cudaFree(s->d_offset);
+    cudaFree(s->d_len);
+    cudaFree(s->corpus.d_alloc);
+    delete s;
+    return HS_SUCCESS;
+}
+
+size_t hs_b200_streams_state_bytes(const hs_b200_stream_set_t *s) { return s ? s->nstreams * 16 : 0; }
+
+hs_error_t hs_b200_streams_scan(hs_b200_stream_set_t *set, const char *data,
+                                const unsigned long long *offsets, const unsigned int *lengths,
+                                hs_scratch_t *scratch, hs_b200_block_event_handler onEvent,
+                                void *context, unsigned long long *nmatches) {
+    if (!set || !scratch || !data || !offsets || !lengths || (uintptr_t)scratch % 64 ||
+        scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    hs_scratch *s = scratch;
+    const size_t n = set->nstreams;
+    hs_error_t r = HS_SUCCESS;
+    std::vector<DevMatch> matches;
+    do {
+        const DevImage *im = nullptr;
+        r = findImage(s, set->db, &im);
+        if (r != HS_SUCCESS) break;
+        /* write lengths: uniform (config 4) or per stream */
+        u32 maxLen = 0, uni = lengths[0];
+        bool contiguous = true;
+        for (size_t i = 0; i < n; i++) {
+            maxLen = std::max(maxLen, lengths[i]);
+            if (lengths[i] != uni) uni = 0;
+            if (offsets[i] != offsets[0] + (u64)i * lengths[0]) contiguous = false;
+        }
+        if (maxLen == 0) break;
+        const u32 pitch = 16 + (u32)HSB_ROUNDUP((u64)maxLen, 16);
+        hs_b200_corpus *c = &set->corpus;
+        const u64 total = (u64)n * pitch;
+        c->device = set->device;
+        r = reserveCorpus(c, total, 0);
+        if (r != HS_SUCCESS) break;
+        cudaStream_t st = s->stream;
+        cudaError_t e;
+        if (uni && contiguous) {
+            e = cudaMemcpy2DAsync(c->d_data + 16, pitch, data + offsets[0], uni, uni, n,
+                                  cudaMemcpyHostToDevice, st);
+        } else {
+            /* ragged writes: pack on the host, one copy */
+            std::vector<u8> pack((size_t)total, 0);
+            for (size_t i = 0; i < n; i++) {
+                memcpy(pack.data() + i * pitch + 16, data + offsets[i], lengths[i]);
+            }
+            e = cudaMemcpyAsync(c->d_data, pack.data(), total, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st); /* `pack` dies at scope end */
+            if (e == cudaSuccess && !uni) {
+                e = cudaMemcpyAsync(set->d_len, lengths, n * 4, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            }
+        }
+        if (e == cudaSuccess) {
+            e = cudaMemsetAsync(c->d_data + total, 0, 48, st);
+        }
+        if (e == cudaSuccess) e = launchStreamAssemble(c->d_data, set->d_hist, (u32)n, pitch, st);
+        if (e != cudaSuccess) { r = HS_UNKNOWN_ERROR; break; }
+        g_launches++;
+        c->nblocks = n;
+        c->bytes = total;
+        c->readableEnd = HSB_ROUNDUP(total, 16) + 16;
+        c->payload = 0;
+        c->uniformPitch = 0;
+        c->uniformLen = uni;
+        c->d_len = set->d_len;
+        ScanPlan pl;
+        r = planScan(s, im, &pl);
+        if (r != HS_SUCCESS) break;
+        for (int attempt = 0; attempt < 2 && r == HS_SUCCESS; attempt++) {
+            ScanParams p;
+            fillParams(s, im, c, pl, &p);
+            p.streamPitch = pitch;
+            p.streamHist = set->d_hist;
+            p.streamOffset = set->d_offset;
+            p.tileFirst = 0;
+            p.ntiles = (u32)((total + pl.tileBytes - 1) / pl.tileBytes);
+            LaunchCfg cfg = pl.cfg;
+            cfg.grid = (int)std::min<u32>((u32)cfg.grid, (p.ntiles + (u32)cfg.warps - 1) / (u32)cfg.warps);
+            e = cudaMemsetAsync(s->d_counters, 0, CTR_COUNT * sizeof(u32), st);
+            if (e == cudaSuccess) e = cudaEventRecord(s->evStart, st);
+            if (e == cudaSuccess) e = launchScan(cfg, p, st);
+            if (e == cudaSuccess) e = cudaEventRecord(s->evStop, st);
+            if (e == cudaSuccess) {
+                e = cudaMemcpyAsync(s->h_counters, s->d_counters, CTR_COUNT * sizeof(u32),
+                                    cudaMemcpyDeviceToHost, st);
+            }
+            if (e == cudaSuccess) e = cudaEventRecord(s->evDone, st);
+            if (e != cudaSuccess) { r = HS_UNKNOWN_ERROR; break; }
+            g_launches++;
+            s->activeStream = st;
+            s->pending = true;
+            u32 count = 0;
+            r = finishScan(s, &count);
+            if (r != HS_SUCCESS) break;
+            if (count <= s->outCap) {
+                matches.resize(count);
+                if (count) {
+                    e = cudaMemcpyAsync(matches.data(), s->d_out, (size_t)count * sizeof(DevMatch),
+                                        cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                    if (e != cudaSuccess) { r = HS_UNKNOWN_ERROR; break; }
+                }
+                matches.resize(postprocess(im, matches.data(), count));
+                break;
+            }
+            u64 want = (u64)count + count / 4 + 1024;
+            r = want > 0xfffffff0ull ? HS_NOMEM : growRing(s, (u32)want);
+        }
+        c->d_len = nullptr; /* borrowed */
+        if (r != HS_SUCCESS) break;
+        e = launchStreamAdvance(c->d_data, set->d_hist, set->d_offset, set->d_len, uni, (u32)n, pitch,
+                                set->histReq, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { r = HS_UNKNOWN_ERROR; break; }
+        g_launches++;
+    } while (0);
+    set->corpus.d_len = nullptr;
+    unsigned long long delivered = 0;
+    if (r == HS_SUCCESS) {
+        if (!onEvent) {
+            delivered = matches.size();
+        } else {
+            for (const DevMatch &m : matches) {
+                delivered++;
+                onEvent(m.block, m.id, 0, m.to, 0, context);
+            }
+        }
+    }
+    if (nmatches) {
+        *nmatches = delivered;
+    }
+    unmarkInUse(scratch);
+    return r;
+}
+
 } /* extern "C" */

@@ -56,6 +56,12 @@ struct ScanParams {
     u32 nblocks;
     u32 uniformPitch;      /* != 0: blockOff[i] == i * uniformPitch */
     u32 uniformLen;        /* != 0 (with uniformPitch): every block has this length; no table reads */
+    /* stream sets (hs_b200_streams_*): stream b's write at b * streamPitch + 16,
+     * preceded by its look-behind; 8 bytes of state per stream (7 history bytes,
+     * right-aligned, + their count) and the stream offset live in HBM */
+    u32 streamPitch;
+    const u8 *streamHist;
+    const u64 *streamOffset;
     /* database image */
     const u8 *bc;          /* RoseEngine bytecode (device copy) */
     const u8 *table;       /* first-stage table in HBM (copied to smem) */
@@ -105,6 +111,12 @@ cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t s
 /* Publish the record count of a finished scan into slot 0 of this rank's
  * region in every peer's exchange buffer (runs after the scan on its stream). */
 cudaError_t launchPublishCount(const ScanParams &p, cudaStream_t stream);
+
+/* stream-set helpers: write every stream's look-behind in front of its write /
+ * roll history and offsets forward after a scan */
+cudaError_t launchStreamAssemble(u8 *corpus, const u8 *hist, u32 nstreams, u32 pitch, cudaStream_t stream);
+cudaError_t launchStreamAdvance(const u8 *corpus, u8 *hist, u64 *offsets, const u32 *lens, u32 uniformLen,
+                                u32 nstreams, u32 pitch, u32 histReq, cudaStream_t stream);
 
 /* accel primitives (src/nfa/shufti.c, truffle.c, vermicelli.h): first
  * position in [0,len) whose byte is in the class, or len. */

@@ -89,6 +89,8 @@ struct BlockRef {
     const u8 *base; /* first byte of the block */
     u32 len;
     u32 index;
+    u32 hist;       /* stream sets: leading bytes that are look-behind (already scanned) */
+    u64 toBase;     /* added to block-relative `to` in emitted records (stream offset) */
 };
 
 /* Which block holds corpus position g?  (Blocks are 16-byte aligned, sorted,
@@ -96,6 +98,28 @@ struct BlockRef {
 __device__ bool findBlock(const ScanParams &p, u64 g, BlockRef *out) {
     if (g >= p.corpusBytes) {
         return false;
+    }
+    out->hist = 0;
+    out->toBase = 0;
+    if (p.streamPitch) {
+        /* stream set: stream b's write sits at b * pitch + 16, its look-behind
+         * (<= 7 bytes kept in HBM) right in front of it */
+        const u32 b = (u32)(g / p.streamPitch);
+        if (b >= p.nblocks) {
+            return false;
+        }
+        const u32 hl = __ldg(p.streamHist + (size_t)b * 8 + 7);
+        const u32 wl = p.uniformLen ? p.uniformLen : __ldg(p.blockLen + b);
+        const u64 off = (u64)b * p.streamPitch + 16 - hl;
+        if (g < off || g - off >= hl + wl) {
+            return false;
+        }
+        out->base = p.corpus + off;
+        out->len = hl + wl;
+        out->index = b;
+        out->hist = hl;
+        out->toBase = __ldg(p.streamOffset + b) - hl;
+        return true;
     }
     u32 b;
     if (p.uniformPitch) {
@@ -288,25 +312,25 @@ __device__ void runProgram(const ScanParams &p, const BlockRef &blk, u32 prog, u
             break;
         case OP_REPORT: {
             const InstrReport in = loadInstr<InstrReport>(pc);
-            emitMatch(p, in.onmatch, blk.index, to + in.offset_adjust);
+            emitMatch(p, in.onmatch, blk.index, blk.toBase + to + in.offset_adjust);
             NEXT(InstrReport);
             break;
         }
         case OP_REPORT_EXHAUST: {
             const InstrReportExhaust in = loadInstr<InstrReportExhaust>(pc);
-            emitMatch(p, in.onmatch, blk.index, to + in.offset_adjust);
+            emitMatch(p, in.onmatch, blk.index, blk.toBase + to + in.offset_adjust);
             NEXT(InstrReportExhaust);
             break;
         }
         case OP_DEDUPE_AND_REPORT: {
             const InstrDedupeAndReport in = loadInstr<InstrDedupeAndReport>(pc);
-            emitMatch(p, in.onmatch, blk.index, to + in.offset_adjust);
+            emitMatch(p, in.onmatch, blk.index, blk.toBase + to + in.offset_adjust);
             NEXT(InstrDedupeAndReport);
             break;
         }
         case OP_FINAL_REPORT: {
             const InstrFinalReport in = loadInstr<InstrFinalReport>(pc);
-            emitMatch(p, in.onmatch, blk.index, to + in.offset_adjust);
+            emitMatch(p, in.onmatch, blk.index, blk.toBase + to + in.offset_adjust);
             return;
         }
         case OP_SQUASH_GROUPS: /* group squashing only prunes work */
@@ -365,7 +389,7 @@ __device__ void confirmFdr(const ScanParams &p, u32 bucket, u64 g, u64 confVal, 
             }
             if (inBlock) {
                 const u64 end = (u64)(p.corpus + g - blk.base);
-                if ((tail & 0xff) <= end + 1) {
+                if ((tail & 0xff) <= end + 1 && end >= blk.hist) { /* ends inside the write */
                     (*nconf)++;
                     runProgram(p, blk, ld32(li + 24), end + 1);
                 }
@@ -393,7 +417,7 @@ __device__ void confirmNoodle(const ScanParams &p, u64 g, u64 confVal, u32 *ncon
         return;
     }
     const u64 end = (u64)(p.corpus + g - blk.base);
-    if (mskLen > end + 1) {
+    if (mskLen > end + 1 || end < blk.hist) {
         return;
     }
     (*nconf)++;
@@ -938,6 +962,69 @@ __global__ void publishCountKernel(const ScanParams p) {
     }
 }
 } // namespace
+
+namespace {
+__global__ void streamAssembleKernel(u8 *corpus, const u8 *hist, u32 nstreams, u32 pitch) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nstreams) {
+        return;
+    }
+    /* header = 16 bytes: zeros, then the hl history bytes right-aligned */
+    const uint2 h = *reinterpret_cast<const uint2 *>(hist + (size_t)b * 8);
+    const u32 hl = h.y >> 24;
+    const u64 hv = (((u64)h.y << 32) | h.x) & 0x00ffffffffffffffULL; /* bytes 0..6 */
+    u64 hi = 0;
+    if (hl) {
+        hi = hv << (8 * (8 - hl)); /* last history byte lands in byte 7 */
+    }
+    uint4 out;
+    out.x = 0;
+    out.y = 0;
+    out.z = (u32)hi;
+    out.w = (u32)(hi >> 32);
+    *reinterpret_cast<uint4 *>(corpus + (size_t)b * pitch) = out;
+}
+
+__global__ void streamAdvanceKernel(const u8 *corpus, u8 *hist, u64 *offsets, const u32 *lens,
+                                    u32 uniformLen, u32 nstreams, u32 pitch, u32 histReq) {
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nstreams) {
+        return;
+    }
+    const u32 hl = hist[(size_t)b * 8 + 7];
+    const u32 wl = uniformLen ? uniformLen : lens[b];
+    if (wl == 0) {
+        return;
+    }
+    /* maintainHistoryBuffer (src/runtime.c:478-508): keep the last histReq bytes */
+    const u32 total = hl + wl;
+    const u32 keep = total < histReq ? total : histReq;
+    const u8 *end = corpus + (size_t)b * pitch + 16 + wl;
+    u64 v = 0;
+    for (u32 i = 0; i < keep; i++) {
+        v |= (u64)end[(int)i - (int)keep] << (8 * i);
+    }
+    v |= (u64)keep << 56;
+    *reinterpret_cast<uint2 *>(hist + (size_t)b * 8) = make_uint2((u32)v, (u32)(v >> 32));
+    offsets[b] += wl;
+}
+} // namespace
+
+cudaError_t launchStreamAssemble(u8 *corpus, const u8 *hist, u32 nstreams, u32 pitch, cudaStream_t stream) {
+    if (nstreams) {
+        streamAssembleKernel<<<(nstreams + 255) / 256, 256, 0, stream>>>(corpus, hist, nstreams, pitch);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launchStreamAdvance(const u8 *corpus, u8 *hist, u64 *offsets, const u32 *lens, u32 uniformLen,
+                                u32 nstreams, u32 pitch, u32 histReq, cudaStream_t stream) {
+    if (nstreams) {
+        streamAdvanceKernel<<<(nstreams + 255) / 256, 256, 0, stream>>>(corpus, hist, offsets, lens, uniformLen,
+                                                                       nstreams, pitch, histReq);
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t launchPublishCount(const ScanParams &p, cudaStream_t stream) {
     publishCountKernel<<<1, 32, 0, stream>>>(p);

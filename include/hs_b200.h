@@ -322,6 +322,26 @@ hs_error_t hs_b200_fetch_matches(const hs_database_t *db, hs_scratch_t *scratch,
                                  hs_b200_match_t *out, size_t cap,
                                  unsigned long long *nmatches);
 
+/* Stream sets: `nstreams` streams of one HS_MODE_STREAM literal database whose
+ * state (7 look-behind bytes + count, 64-bit offset: 16 bytes per stream) stays
+ * in HBM between calls.  hs_b200_streams_scan() gives every stream one write
+ * (stream i: data[offsets[i] .. +lengths[i]), HOST memory; zero-length = no
+ * write) and delivers matches as (stream index, id, to = stream offset),
+ * ordered by (stream, to).  Equivalent to one hs_scan_stream() per stream.
+ * Databases with HS_FLAG_SINGLEMATCH patterns are refused (HS_ARCH_ERROR): their
+ * per-stream exhaustion state is kept only by hs_scan_stream. */
+struct hs_b200_stream_set;
+typedef struct hs_b200_stream_set hs_b200_stream_set_t;
+hs_error_t hs_b200_streams_open(const hs_database_t *db, size_t nstreams, int device,
+                                hs_b200_stream_set_t **set);
+hs_error_t hs_b200_streams_scan(hs_b200_stream_set_t *set, const char *data,
+                                const unsigned long long *offsets,
+                                const unsigned int *lengths, hs_scratch_t *scratch,
+                                hs_b200_block_event_handler onEvent, void *context,
+                                unsigned long long *nmatches);
+size_t hs_b200_streams_state_bytes(const hs_b200_stream_set_t *set);
+hs_error_t hs_b200_streams_close(hs_b200_stream_set_t *set);
+
 /* Introspection used by tests and bench.py. */
 typedef struct hs_b200_db_info {
     unsigned int runtime_impl;   /* RoseEngine.runtimeImpl */

@@ -123,3 +123,55 @@ def test_device_stream_termination_copy_reset(hs, ref):
     assert rc == hs.HS_DB_MODE_ERROR
     st.close(scratch)
     twin.close(scratch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nl,wlen", [(40, 64), (300, 1024), (1, 33)])
+def test_stream_set_equals_per_stream_reference(hs, ref, nl, wlen):
+    """hs_b200_streams_scan (state in HBM) == one reference stream per stream."""
+    lits, flags, ids = synth.literal_set(nl, min_len=2, max_len=8, seed=nl + 7, caseless_frac=0.2,
+                                         alphabet=b"abcdef")
+    db = hs.compile_lit_multi(lits, flags, ids, mode=hs.HS_MODE_STREAM)
+    scratch = hs.Scratch(db)
+    nstreams = 257
+    sset = hs.StreamSet(db, nstreams)
+    rng = np.random.default_rng(nl)
+    rounds = []
+    for rnd in range(4):
+        if rnd == 2:   # a ragged round (some streams get nothing)
+            ln = rng.integers(0, wlen + 1, size=nstreams).astype(np.uint32)
+        else:
+            ln = np.full(nstreams, wlen, dtype=np.uint32)
+        data, off, _ = synth.ragged_corpus([int(x) for x in ln], lits, seed=100 * nl + rnd, plant_per_kb=30,
+                                           align=1, alphabet=b"abcdefAB")
+        rounds.append((data, off, ln))
+    got = []
+    for rnd, (data, off, ln) in enumerate(rounds):
+        recs = sset.scan(data, off, ln, scratch)
+        got.append(recs)
+    sset.close()
+    # reference: every stream on its own, writes = its slice of every round
+    for s in rng.choice(nstreams, size=40, replace=False).tolist() + [0, nstreams - 1]:
+        pieces = [d[int(o[s]):int(o[s]) + int(l[s])] for (d, o, l) in rounds]
+        cat = np.concatenate(pieces) if sum(p.size for p in pieces) else np.zeros(0, np.uint8)
+        wl = np.array([p.size for p in pieces], dtype=np.uint32)
+        want, err = ref.stream_collect(db.ptr, cat, wl)
+        assert err == 0
+        exp = sorted((int(r["block"]), int(r["id"]), int(r["to"])) for r in want)
+        mine = []
+        for rnd, recs in enumerate(got):
+            sel = recs[recs["block"] == s]
+            mine += [(rnd, int(r["id"]), int(r["to"])) for r in sel]
+        assert sorted(mine) == exp, (s, sorted(mine)[:5], exp[:5])
+
+
+@pytest.mark.gpu
+def test_stream_set_rejects_what_it_cannot_do(hs):
+    blk = hs.compile_lit_multi([b"abc"])
+    with pytest.raises(hs.HsError) as e:
+        hs.StreamSet(blk, 4)
+    assert e.value.code == hs.HS_DB_MODE_ERROR
+    single = hs.compile_lit_multi([b"abc"], flags=[8], mode=hs.HS_MODE_STREAM)
+    with pytest.raises(hs.HsError) as e:
+        hs.StreamSet(single, 4)
+    assert e.value.code == hs.HS_ARCH_ERROR
