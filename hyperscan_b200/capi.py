@@ -108,6 +108,7 @@ def lib():
         L.hs_scan.argtypes = [vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
         L.hs_b200_streams_open.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(vp)]
         L.hs_b200_streams_scan.argtypes = [vp, vp, vp, vp, vp, BLOCK_CB, vp, u64p]
+        L.hs_b200_streams_scan_collect.argtypes = [vp, vp, vp, vp, vp, vp, C.c_size_t, u64p]
         L.hs_b200_streams_close.argtypes = [vp]
         L.hs_b200_streams_state_bytes.argtypes = [vp]
         L.hs_b200_streams_state_bytes.restype = C.c_size_t
@@ -457,9 +458,10 @@ class Stream:
 class StreamSet:
     """hs_b200_streams_open / scan / close: many streams, state resident in HBM."""
 
-    def __init__(self, db, nstreams, device=0):
+    def __init__(self, db, nstreams, device=0, out_cap=1 << 22):
         self.db = db
         self.n = nstreams
+        self._out = np.zeros(out_cap, dtype=MATCH_DTYPE)
         self.ptr = C.c_void_p()
         _check(lib().hs_b200_streams_open(db.ptr, nstreams, device, C.byref(self.ptr)), "streams_open")
 
@@ -468,19 +470,18 @@ class StreamSet:
         off, ln = _blocks(offsets, lengths)
         assert off.size == self.n
         n = C.c_ulonglong()
-        recs = []
-
-        def cb(block, i, frm, to, flags, ctx):
-            recs.append((i, block, to))
-            return 0
-
         keep = a if a.size else np.zeros(1, dtype=np.uint8)
-        rc = lib().hs_b200_streams_scan(self.ptr, keep.ctypes.data, off.ctypes.data, ln.ctypes.data, scratch.ptr,
-                                        BLOCK_CB(cb) if collect else BLOCK_CB(), None, C.byref(n))
-        _check(rc, "streams_scan")
         if not collect:
+            rc = lib().hs_b200_streams_scan(self.ptr, keep.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                            scratch.ptr, BLOCK_CB(), None, C.byref(n))
+            _check(rc, "streams_scan")
             return int(n.value)
-        return np.array(recs, dtype=MATCH_DTYPE) if recs else np.zeros(0, dtype=MATCH_DTYPE)
+        rc = lib().hs_b200_streams_scan_collect(self.ptr, keep.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                                scratch.ptr, self._out.ctypes.data, self._out.size, C.byref(n))
+        if rc == HS_INSUFFICIENT_SPACE:
+            raise HsError(rc, "streams_scan_collect: %d matches exceed the harness buffer" % n.value)
+        _check(rc, "streams_scan_collect")
+        return self._out[: int(n.value)].copy()
 
     def close(self):
         if self.ptr:

@@ -1972,21 +1972,12 @@ hs_error_t hs_b200_streams_close(hs_b200_stream_set_t *s) {
 
 size_t hs_b200_streams_state_bytes(const hs_b200_stream_set_t *s) { return s ? s->nstreams * 16 : 0; }
 
-hs_error_t hs_b200_streams_scan(hs_b200_stream_set_t *set, const char *data,
-                                const unsigned long long *offsets, const unsigned int *lengths,
-                                hs_scratch_t *scratch, hs_b200_block_event_handler onEvent,
-                                void *context, unsigned long long *nmatches) {
-    if (!set || !scratch || !data || !offsets || !lengths || (uintptr_t)scratch % 64 ||
-        scratch->magic != SCRATCH_MAGIC) {
-        return HS_INVALID;
-    }
-    if (markInUse(scratch)) {
-        return HS_SCRATCH_IN_USE;
-    }
+static hs_error_t streamsScanImpl(hs_b200_stream_set_t *set, const char *data,
+                                  const unsigned long long *offsets, const unsigned int *lengths,
+                                  hs_scratch_t *scratch, std::vector<DevMatch> &matches) {
     hs_scratch *s = scratch;
     const size_t n = set->nstreams;
     hs_error_t r = HS_SUCCESS;
-    std::vector<DevMatch> matches;
     do {
         const DevImage *im = nullptr;
         r = findImage(s, set->db, &im);
@@ -2089,19 +2080,58 @@ hs_error_t hs_b200_streams_scan(hs_b200_stream_set_t *set, const char *data,
         g_launches++;
     } while (0);
     set->corpus.d_len = nullptr;
+    return r;
+}
+
+hs_error_t hs_b200_streams_scan(hs_b200_stream_set_t *set, const char *data,
+                                const unsigned long long *offsets, const unsigned int *lengths,
+                                hs_scratch_t *scratch, hs_b200_block_event_handler onEvent,
+                                void *context, unsigned long long *nmatches) {
+    if (!set || !scratch || !data || !offsets || !lengths || (uintptr_t)scratch % 64 ||
+        scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    std::vector<DevMatch> matches;
+    hs_error_t r = streamsScanImpl(set, data, offsets, lengths, scratch, matches);
     unsigned long long delivered = 0;
     if (r == HS_SUCCESS) {
-        if (!onEvent) {
-            delivered = matches.size();
-        } else {
+        delivered = matches.size();
+        if (onEvent) {
             for (const DevMatch &m : matches) {
-                delivered++;
                 onEvent(m.block, m.id, 0, m.to, 0, context);
             }
         }
     }
     if (nmatches) {
         *nmatches = delivered;
+    }
+    unmarkInUse(scratch);
+    return r;
+}
+
+hs_error_t hs_b200_streams_scan_collect(hs_b200_stream_set_t *set, const char *data,
+                                        const unsigned long long *offsets,
+                                        const unsigned int *lengths, hs_scratch_t *scratch,
+                                        hs_b200_match_t *out, size_t cap,
+                                        unsigned long long *nmatches) {
+    if (!set || !scratch || !data || !offsets || !lengths || !nmatches || (cap && !out) ||
+        (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    std::vector<DevMatch> matches;
+    hs_error_t r = streamsScanImpl(set, data, offsets, lengths, scratch, matches);
+    if (r == HS_SUCCESS) {
+        *nmatches = matches.size();
+        memcpy(out, matches.data(), std::min(cap, matches.size()) * sizeof(DevMatch));
+        if (matches.size() > cap) {
+            r = HS_INSUFFICIENT_SPACE; /* the stream state HAS advanced; the first cap records are valid */
+        }
     }
     unmarkInUse(scratch);
     return r;

@@ -339,6 +339,14 @@ hs_error_t hs_b200_streams_scan(hs_b200_stream_set_t *set, const char *data,
                                 const unsigned int *lengths, hs_scratch_t *scratch,
                                 hs_b200_block_event_handler onEvent, void *context,
                                 unsigned long long *nmatches);
+/* Same, the ordered matches written to `out` (stream index in `block`) instead
+ * of a callback per match.  HS_INSUFFICIENT_SPACE: more than `cap` matches
+ * (*nmatches tells; the first cap are valid and the streams have advanced). */
+hs_error_t hs_b200_streams_scan_collect(hs_b200_stream_set_t *set, const char *data,
+                                        const unsigned long long *offsets,
+                                        const unsigned int *lengths, hs_scratch_t *scratch,
+                                        hs_b200_match_t *out, size_t cap,
+                                        unsigned long long *nmatches);
 size_t hs_b200_streams_state_bytes(const hs_b200_stream_set_t *set);
 hs_error_t hs_b200_streams_close(hs_b200_stream_set_t *set);
 
