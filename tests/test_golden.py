@@ -49,3 +49,60 @@ def test_cuda_path_reproduces_golden(hs, case):
     corpus = hs.Corpus.upload(data, off, ln)
     got = np.sort(hs.scan_corpus(db, corpus, scratch), order=["block", "to", "id"])
     assert np.array_equal(got, want)
+
+
+# --- the reference's own recorded hscollider vectors for literal patterns ---------------------------
+# tests/golden/hscollider_literals.json (tools/gen_hscollider_golden.py): pattern text and recorded
+# end offsets from tools/hscollider/test_cases/{pcre,corpora}; compare rule for single-match patterns
+# per tools/hscollider/main.cpp:522-537 (exactly one of the recorded matches).
+with open(os.path.join(ROOT, "tests", "golden", "hscollider_literals.json")) as f:
+    COLLIDER = json.load(f)["cases"]
+
+
+def _collider_blocks(case):
+    datas = [base64.b64decode(c["data"]) for c in case["corpora"]]
+    # every corpus is one block at a 16-byte aligned start
+    off, buf = [], bytearray()
+    for d in datas:
+        while len(buf) % 16:
+            buf.append(0)
+        off.append(len(buf))
+        buf += d
+    data = np.frombuffer(bytes(buf) + b"\0" * 16, dtype=np.uint8)
+    return (data, np.array(off, dtype=np.uint64), np.array([len(d) for d in datas], dtype=np.uint32),
+            [c["ends"] for c in case["corpora"]])
+
+
+def _check_collider(case, recs, ends):
+    for b, want in enumerate(ends):
+        tos = [int(r["to"]) for r in recs if r["block"] == b]
+        assert all(int(r["id"]) == case["id"] for r in recs)
+        if "H" in case["flag_letters"]:
+            assert (len(tos) == 1 and tos[0] in want) if want else not tos, (case["id"], b, tos, want)
+        else:
+            assert tos == want, (case["id"], b, tos, want)
+
+
+@pytest.mark.parametrize("case", COLLIDER, ids=[str(c["id"]) for c in COLLIDER])
+def test_oracle_reproduces_hscollider_vectors(hs, case):
+    db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+    data, off, ln, ends = _collider_blocks(case)
+    _check_collider(case, port.scan_sorted(db.ptr, data, off, ln), ends)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", COLLIDER, ids=[str(c["id"]) for c in COLLIDER])
+def test_cuda_path_reproduces_hscollider_vectors(hs, case):
+    db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+    data, off, ln, ends = _collider_blocks(case)
+    scratch = hs.Scratch(db)
+    got = np.sort(hs.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
+    _check_collider(case, got, ends)
+    # and one hs_scan per corpus, the way hscollider drives the engine
+    for c, want in zip(case["corpora"], ends):
+        tos = []
+        hs.scan(db, base64.b64decode(c["data"]), scratch, on_event=lambda i, frm, to, fl: tos.append(to) or 0)
+        if "H" in case["flag_letters"]:
+            assert (len(tos) == 1 and tos[0] in want) if want else not tos
+        else:
+            assert tos == want
