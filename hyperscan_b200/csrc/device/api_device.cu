@@ -55,6 +55,12 @@ struct RuntimeOpts {
     int pfDist = 8;          /* direct mode: L2 prefetch distance in 512-byte steps */
     int replicas = 1;        /* rebuilt table: copies per entry (0 = fill up to 128 KB, max 16);
                               * measured: no gain, and a small footprint lets NCCL CTAs co-reside */
+    int queue = 2;           /* candidates go through the per-warp shared-memory queue: 0 never, 1 always,
+                              * 2 for the per-byte tables (Teddy, noodle: measured +15 %) but not for the
+                              * FDR hash table, whose kernel is shared-memory bound either way */
+    int firstStage = 1;      /* FDR databases: 1 = two-byte hash table (FK_HASH32), 2 = per-byte table
+                              * (FK_BYTE32, conflict-free lookups, more candidates), 0 = choose by the
+                              * modelled candidate rate of the per-byte table */
     int chunkMB = 128;       /* host->device pipeline granularity */
     int initialRing = 1 << 20;
 };
@@ -73,7 +79,8 @@ void initOpts() {
         {"HSB200_STRIDE", &g_opts.stride},     {"HSB200_PREFILTER", &g_opts.prefilter},
         {"HSB200_REBUILD", &g_opts.rebuild},   {"HSB200_DOMAIN", &g_opts.domain},
         {"HSB200_DIRECT", &g_opts.direct},     {"HSB200_REPLICAS", &g_opts.replicas},
-        {"HSB200_PF_DIST", &g_opts.pfDist}};
+        {"HSB200_PF_DIST", &g_opts.pfDist},    {"HSB200_QUEUE", &g_opts.queue},
+        {"HSB200_FIRST_STAGE", &g_opts.firstStage}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -227,6 +234,55 @@ std::vector<u8> rebuildHashTable(const std::vector<LitTail> &tails, u32 domain, 
     return out;
 }
 
+/* Per-byte first-stage table for an FDR literal set: entry b, slot i, bucket k
+ * is CLEAR iff some literal of bucket k can have byte b at suffix distance i
+ * (caseless letters through LitInfo.msk).  The Teddy construction
+ * (src/fdr/teddy_compile.cpp:440-509) applied to the FDR buckets: a weaker
+ * filter than the two-byte hash, but its 256-row table is replicated per lane,
+ * so the lookups are bank-conflict free.  *rate = modelled candidates per byte
+ * on uniformly random printable ASCII. */
+std::vector<u8> buildByteTable(const std::vector<LitTail> &tails, double *rate) {
+    u32 tab[256];
+    for (u32 b = 0; b < 256; b++) {
+        tab[b] = 0xffffffffu;
+    }
+    u32 dead = 0;
+    for (const LitTail &t : tails) {
+        for (u32 i = 0; i < 4; i++) {
+            const u32 bit = 1u << (8 * i + t.bucket);
+            if (i >= t.size) {
+                dead |= bit;
+                continue;
+            }
+            const u8 c = (u8)(t.v >> (8 * (7 - i))), m = (u8)(t.msk >> (8 * (7 - i)));
+            for (u32 b = 0; b < 256; b++) {
+                if ((b & m) == c) {
+                    tab[b] &= ~bit;
+                }
+            }
+        }
+    }
+    std::vector<u8> out(256 * 4);
+    double total = 0;
+    for (u32 k = 0; k < 8; k++) {
+        double pr = 1;
+        for (u32 i = 0; i < 4; i++) {
+            u32 n = 0;
+            for (u32 b = 0x20; b < 0x7f; b++) {
+                n += !(((tab[b] & ~dead) >> (8 * i + k)) & 1);
+            }
+            pr *= n / 95.0;
+        }
+        total += pr;
+    }
+    *rate = total;
+    for (u32 b = 0; b < 256; b++) {
+        const u32 e = tab[b] & ~dead;
+        memcpy(&out[b * 4], &e, 4);
+    }
+    return out;
+}
+
 void freeImage(DevImage *im) {
     if (!im) {
         return;
@@ -305,9 +361,19 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
             cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
             const size_t wideNeed = (size_t)entries * 8 + 48 * 1024;
             walkConfirm(bc, h->length, im->confOff, 8, &im->exhaustible, &tails);
+            double byteRate = 1;
+            std::vector<u8> byteTab;
+            if (g_opts.firstStage != 1) {
+                byteTab = buildByteTable(tails, &byteRate);
+            }
             if (g_opts.wideFdr && wideNeed <= (size_t)maxSmem) {
                 im->kind = FK_HASH64;
                 table.assign(src, src + (size_t)entries * 8);
+            } else if (g_opts.firstStage == 2 || (g_opts.firstStage == 0 && byteRate < 0.01)) {
+                im->kind = FK_BYTE32;
+                im->stride = 1;
+                im->slotBase = 0;
+                table.swap(byteTab);
             } else if (g_opts.rebuild) {
                 u32 minSize = 8, d = f.domain;
                 for (const LitTail &t : tails) {
@@ -600,9 +666,16 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     u32 tile = (u32)std::max(512, g_opts.tileBytes) & ~511u;
     u32 stages = (u32)std::max(2, std::min(8, g_opts.stages));
     /* shrink until the table + staging fit the opt-in shared memory */
+    int stride = im->stride;
+    if ((g_opts.stride == 1 || g_opts.stride == 2 || g_opts.stride == 4) &&
+        (im->kind == FK_HASH32 || im->kind == FK_HASH64)) {
+        stride = g_opts.stride; /* any sampling subset is a sound filter */
+    }
+    const bool byteKind = im->kind == FK_BYTE32 || im->kind == FK_BYTE64;
+    const int queued = direct && stride == 1 && (g_opts.queue == 1 || (g_opts.queue == 2 && byteKind));
     for (;;) {
         const size_t need = scanSmemBytes(im->kind, im->tableBytes, im->bitmapBytes, direct ? 0 : warps,
-                                          stages, tile);
+                                          stages, tile, queued ? warps : 0);
         if (need <= (size_t)s->maxSmem) {
             pl->cfg.smemBytes = need;
             break;
@@ -624,11 +697,8 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     pl->cfg.kind = im->kind;
     pl->cfg.slotBase = im->slotBase;
     pl->cfg.direct = direct;
-    pl->cfg.stride = im->stride;
-    if ((g_opts.stride == 1 || g_opts.stride == 2 || g_opts.stride == 4) &&
-        (im->kind == FK_HASH32 || im->kind == FK_HASH64)) {
-        pl->cfg.stride = g_opts.stride; /* any sampling subset is a sound filter */
-    }
+    pl->cfg.stride = stride;
+    pl->cfg.queued = queued;
     pl->cfg.grid = s->smCount;
     pl->cfg.warps = warps;
     pl->tileBytes = tile;
@@ -860,7 +930,8 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"stride", &g_opts.stride},     {"prefilter", &g_opts.prefilter},
         {"rebuild", &g_opts.rebuild},   {"domain", &g_opts.domain},
         {"direct", &g_opts.direct},     {"replicas", &g_opts.replicas},
-        {"pf_dist", &g_opts.pfDist}};
+        {"pf_dist", &g_opts.pfDist},    {"queue", &g_opts.queue},
+        {"first_stage", &g_opts.firstStage}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;

@@ -25,7 +25,8 @@ struct DevMatch {
  * src/fdr/teddy.c:918-969 -- see DESIGN.md section 3 for the derivation). */
 enum FilterKind {
     FK_BYTE32 = 0, /* index = 1 byte; u32 entry (4 slots x 8 buckets); table
-                      replicated per lane (bank-conflict free). Teddy, noodle */
+                      replicated per lane (bank-conflict free). Teddy, noodle, and
+                      FDR sets whose tails keep the per-byte filter sparse */
     FK_BYTE64 = 1, /* index = 1 byte; 2 x u32 (4 slots x 16 buckets). Fat Teddy */
     FK_HASH32 = 2, /* index = 2-byte FDR hash; u32 entry (slots 0..3 of FDR) */
     FK_HASH64 = 3, /* index = 2-byte FDR hash; u64 entry (all 8 FDR slots)   */
@@ -97,14 +98,16 @@ struct LaunchCfg {
     int stride;    /* 1, 2, 4 */
     int slotBase;  /* FK_HASH32: 0 = slots 0..3 (reference numbering), 1 = slots 1..4 */
     int direct;    /* 1: corpus loaded straight into registers; 0: TMA-staged tiles */
+    int queued;    /* 1 (direct, stride 1 only): candidates go through the per-warp queue */
     int grid;      /* CTAs (one per SM) */
     int warps;     /* per CTA */
     size_t smemBytes;
 };
 
-/* Dynamic shared memory the kernel needs. */
+/* Dynamic shared memory the kernel needs (warps = warps with TMA stages, 0 in
+ * direct mode; queueWarps = warps with a candidate queue, 0 without). */
 size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 nstages,
-                     u32 tileBytes);
+                     u32 tileBytes, int queueWarps);
 
 cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream);
 

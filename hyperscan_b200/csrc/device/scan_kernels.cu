@@ -443,6 +443,21 @@ __device__ __forceinline__ uint2 lds64(u32 addr) {
     return v;
 }
 
+__device__ __forceinline__ uint4 lds128(u32 addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(u32 addr, u32 x, u32 y, u32 z, u32 w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w)
+                 : "memory");
+}
+__device__ __forceinline__ void sts32(u32 addr, u32 x) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
+}
+
 /* OR the 128-bit stream E[0..3] (one entry per word of the lane, all at the
  * same in-word position) into a[] at byte offset O (0..4): one funnel shift
  * per output word instead of two shifts per entry. */
@@ -524,13 +539,14 @@ __device__ __forceinline__ void laneFilter(const u32 (&w)[5], u32 tabAddr, u32 l
                 }
                 E0[k] = lds32(tabAddr + (off & (indexMask << sh)));
             } else {
-                const u32 idx = __byte_perm(w[k], 0, 0x4440 + r);
-                if (KIND == FK_BYTE32) {
-                    E0[k] = lds32(tabAddr + idx * 128 + laneOff);
-                } else {
-                    const uint2 e = lds64(tabAddr + idx * 128 + laneOff);
-                    E0[k] = e.x;
-                    E1[k] = e.y;
+                /* row b of the table is 256 bytes: lane l's copy of the entry at
+                 * l * 4 (second bucket octet at 128 + l * 4), so the row offset
+                 * b << 8 | l << 2 is ONE byte permute of (word, laneOff) and every
+                 * lookup is bank-conflict free */
+                const u32 row = __byte_perm(w[k], laneOff, 0x5504 + (r << 4));
+                E0[k] = lds32(tabAddr + row);
+                if (KIND == FK_BYTE64) {
+                    E1[k] = lds32(tabAddr + row + 128);
                 }
             }
         }
@@ -642,11 +658,55 @@ __device__ __noinline__ void laneCandidates(const ScanParams &p, u32 bitmapAddr,
     }
 }
 
+/* Candidate queue (template QUEUED): instead of every lane walking its own
+ * candidates while the other 31 idle, lanes append {candidate words, chunk
+ * number} to a per-warp queue in shared memory and the warp drains it 32
+ * entries at a time, one entry per lane, all lanes in step through the
+ * prefilter probe.  An entry is NOCT x 16 bytes of candidate bits + the number
+ * of the 16-byte chunk relative to the warp's run; the chunk's bytes are read
+ * back from L2. */
+template <int NOCT> struct QueueEntry {
+    static constexpr u32 BYTES = NOCT == 1 ? 32 : 48;
+    static constexpr u32 SLOTS = 64;                     /* < 32 pending + <= 32 appended per step */
+    static constexpr u32 RUN_START = BYTES * SLOTS;      /* u64: corpus position of the run's chunk 0 */
+    static constexpr u32 WARP_BYTES = RUN_START + 16;    /* one warp's share of shared memory */
+};
+
+template <int NOCT>
+__device__ __noinline__ void drainQueue(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
+                                        u32 count, u32 lane, u32 *stats) {
+    if (lane >= count) {
+        return;
+    }
+    const uint2 rs = lds64(qAddr + QueueEntry<NOCT>::RUN_START);
+    const u64 runStart = ((u64)rs.y << 32) | rs.x;
+    const u32 e = qAddr + (first + lane) * QueueEntry<NOCT>::BYTES;
+    const uint4 c0 = lds128(e);
+    uint4 c1 = make_uint4(0, 0, 0, 0);
+    if (NOCT == 2) {
+        c1 = lds128(e + 16);
+    }
+    const u64 g0 = runStart + (u64)lds32(e + 16 * NOCT) * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g0 + 16 <= p.readableEnd) {
+        v = __ldg(reinterpret_cast<const uint4 *>(p.corpus + g0));
+    }
+    const u32 pw = g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u;
+    laneCandidates<NOCT>(p, bitmapAddr, c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, v.x, v.y, v.z,
+                         v.w, pw, g0, stats);
+}
+
+/* per-warp queue state carried through the run */
+struct WarpQueue {
+    u32 addr; /* shared-memory address of this warp's slots */
+    u32 n;    /* entries pending (warp-uniform) */
+};
+
 /* ---- the scan kernel -------------------------------------------------------- */
 
 __host__ __device__ inline u32 tableSmemBytes(int kind, u32 tableBytes) {
     if (kind == FK_BYTE32 || kind == FK_BYTE64) {
-        return 256 * 128; /* 256 entries, replicated across the 32 banks */
+        return 256 * 256; /* 256 rows: 32 lane copies x (1 or 2) bucket octets */
     }
     return (tableBytes + 127u) & ~127u;
 }
@@ -654,10 +714,11 @@ __host__ __device__ inline u32 tableSmemBytes(int kind, u32 tableBytes) {
 /* One 512-byte step of a warp: v = the lane's own 16 bytes, w4 = the word after
  * them, pwSrc = loader of the word before the warp's 512 bytes (lane 0 only,
  * rare path). */
-template <int KIND, int STRIDE, int SB, class PrevWord>
+template <int KIND, int STRIDE, int SB, int QUEUED, class PrevWord>
 __device__ __forceinline__ void scanStep(const ScanParams &p, const uint4 v, u32 w4, u32 lane,
                                          u32 tabAddr, u32 laneOff, u32 bitmapAddr,
-                                         u32 (&carry)[2][2], u64 g0, u32 *stats, PrevWord prevWord) {
+                                         u32 (&carry)[2][2], u64 g0, u32 *stats, PrevWord prevWord,
+                                         WarpQueue &wq, u32 chunk) {
     typedef Kind<KIND> K;
     const u32 w[5] = {v.x, v.y, v.z, v.w, w4};
     u32 a[2][6];
@@ -689,7 +750,27 @@ __device__ __forceinline__ void scanStep(const ScanParams &p, const uint4 v, u32
     if (K::NOCT == 1) {
         c[1][0] = c[1][1] = c[1][2] = c[1][3] = 0;
     }
-    if (__any_sync(0xffffffffu, any != 0)) {
+    if (QUEUED) {
+        const u32 bal = __ballot_sync(0xffffffffu, any != 0);
+        if (bal) {
+            typedef QueueEntry<K::NOCT> Q;
+            if (any) {
+                const u32 e = wq.addr + (wq.n + __popc(bal & ((1u << lane) - 1))) * Q::BYTES;
+                sts128(e, c[0][0], c[0][1], c[0][2], c[0][3]);
+                if (K::NOCT == 2) {
+                    sts128(e + 16, c[1][0], c[1][1], c[1][2], c[1][3]);
+                }
+                sts32(e + 16 * K::NOCT, chunk);
+            }
+            wq.n += __popc(bal);
+            if (wq.n >= 32) {
+                __syncwarp();
+                wq.n -= 32;
+                drainQueue<K::NOCT>(p, bitmapAddr, wq.addr, wq.n, 32, lane, stats);
+                __syncwarp();
+            }
+        }
+    } else if (__any_sync(0xffffffffu, any != 0)) {
         u32 pw = __shfl_up_sync(0xffffffffu, v.w, 1);
         if (lane == 0) {
             pw = prevWord();
@@ -719,8 +800,9 @@ __device__ __forceinline__ void haloStep(const ScanParams &p, const uint4 v, u32
     }
 }
 
-template <int KIND, int STRIDE, int SB, int DIRECT>
+template <int KIND, int STRIDE, int SB, int DIRECT, int QUEUED>
 __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanParams p) {
+    static_assert(!QUEUED || DIRECT, "the candidate queue reads chunks back from the corpus (direct mode)");
     extern __shared__ __align__(128) u8 smem[];
     typedef Kind<KIND> K;
     const u32 lane = threadIdx.x & 31;
@@ -731,17 +813,13 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
     const u32 tabBytes = tab0 + p.bitmapBytes;
 
     /* pin the first-stage table in shared memory */
-    if (KIND == FK_BYTE32) {
+    if (KIND == FK_BYTE32 || KIND == FK_BYTE64) {
+        /* word i of the table image: row i >> 6, octet (i >> 5) & 1, lane i & 31 */
         const u32 *g = reinterpret_cast<const u32 *>(p.table);
         u32 *s = reinterpret_cast<u32 *>(smem);
-        for (u32 i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
-            s[i] = __ldg(g + (i >> 5));
-        }
-    } else if (KIND == FK_BYTE64) {
-        const uint2 *g = reinterpret_cast<const uint2 *>(p.table);
-        uint2 *s = reinterpret_cast<uint2 *>(smem);
-        for (u32 i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
-            s[i] = __ldg(g + (i >> 4));
+        for (u32 i = threadIdx.x; i < 256 * 64; i += blockDim.x) {
+            const u32 b = i >> 6, o = (i >> 5) & 1;
+            s[i] = KIND == FK_BYTE64 ? __ldg(g + b * 2 + o) : (o ? 0xffffffffu : __ldg(g + b));
         }
     } else {
         const uint4 *g = reinterpret_cast<const uint4 *>(p.table);
@@ -774,7 +852,7 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
     const u32 bitmapAddr = smemAddr(smem) + tab0;
     /* FK_HASH32: each lane reads its own copy of the table (lane & (R-1)) */
     const u32 tabAddr = smemAddr(smem) + (KIND == FK_HASH32 ? (lane & ((1u << p.repShift) - 1)) * 4 : 0);
-    const u32 laneOff = KIND == FK_BYTE64 ? (lane & 15) * 8 : lane * 4;
+    const u32 laneOff = lane * 4;
 
     /* this warp's contiguous run of tiles */
     const u32 gwarp = blockIdx.x * nwarps + warp;
@@ -788,8 +866,87 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
 
     u32 carry[2][2] = {{0, 0}, {0, 0}}; /* lane 31's overflow of the previous step */
     u32 stats[3] = {0, 0, 0};           /* candidates, prefilter passes, confirmed */
+    WarpQueue wq;
+    wq.addr = smemAddr(smem) + tabBytes + warp * QueueEntry<K::NOCT>::WARP_BYTES;
+    wq.n = 0;
 
-    if (DIRECT) {
+    if (DIRECT && QUEUED) {
+        /* corpus bytes straight from HBM into registers: one coalesced
+         * 16-byte load per lane and step, three steps in flight per warp */
+        const u64 runStart = (u64)myFirst * p.tileBytes;
+        u64 runEnd = runStart + (u64)myCount * p.tileBytes;
+        if (runEnd > p.corpusBytes) {
+            runEnd = p.corpusBytes;
+        }
+        const u32 nsteps = (u32)((runEnd - runStart + 511) >> 9);
+        const u8 *ptr = p.corpus + runStart + lane * 16; /* this lane's 16 bytes of the current step */
+        const u8 *const endPtr = p.corpus + p.readableEnd;
+        if (QUEUED && lane == 0) {
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wq.addr + QueueEntry<K::NOCT>::RUN_START),
+                         "r"((u32)runStart), "r"((u32)(runStart >> 32))
+                         : "memory");
+        }
+        auto load = [&](const u8 *q, bool guard) -> uint4 {
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (!guard || q + 16 <= endPtr) {
+                /* volatile: keeps the load where it is written (ptxas otherwise
+                 * sinks it next to its first use and the prefetch is lost) */
+                asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                             : "l"(q));
+            }
+            return r;
+        };
+        /* two-level prefetch: every fourth step the even lanes pull the 2 KiB
+         * that lie `pfDist` steps ahead into L2 (16 x 128 B), the register copy
+         * runs one step ahead and so only has to cover an L2 hit */
+        const size_t pfBytes = (size_t)p.nstages * 512 + lane * 48; /* + (lane / 2) * 128 - lane * 16 */
+        uint4 nxt = load(ptr, true);
+        if (runStart != 0) {
+            const uint4 hv = __ldg(reinterpret_cast<const uint4 *>(p.corpus + runStart - 16));
+            const u32 first = __shfl_sync(0xffffffffu, nxt.x, 0);
+            haloStep<KIND, STRIDE, SB>(p, hv, first, tabAddr, laneOff, carry);
+        }
+        u32 step = 0;
+        auto body = [&](const bool guard) {
+            const uint4 cur = nxt;
+            nxt = load(ptr + 512, guard);
+            if ((step & 3) == 0 && (lane & 1) == 0) {
+                const u8 *pf = ptr + pfBytes;
+                if (pf < endPtr) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                }
+            }
+            u32 w4 = 0;
+            if (K::HASH) {
+                /* the word after the lane's 16 bytes: one rotate shuffle in
+                 * which lane 0 offers the NEXT step's first word (for lane 31) */
+                w4 = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, (lane + 1) & 31);
+            }
+            const u64 g0 = (u64)(ptr - p.corpus);
+            scanStep<KIND, STRIDE, SB, QUEUED>(
+                p, cur, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
+                [&]() { return g0 ? __ldg(reinterpret_cast<const u32 *>(ptr - 4)) : 0u; }, wq,
+                step * 32 + lane);
+        };
+        /* the load issued in iteration `step` fetches step + 1: it needs no
+         * bounds check while the whole warp's 512 bytes of that step are
+         * readable -- everywhere except at the very end of the corpus */
+        const u64 readableSteps = (p.readableEnd - runStart) >> 9;
+        const u32 nFast = readableSteps >= (u64)nsteps + 1 ? nsteps : (readableSteps ? (u32)readableSteps - 1 : 0);
+#pragma unroll 1
+        for (; step < nFast; step++, ptr += 512) {
+            body(false);
+        }
+#pragma unroll 1
+        for (; step < nsteps; step++, ptr += 512) {
+            body(true);
+        }
+        if (QUEUED && wq.n) {
+            __syncwarp();
+            drainQueue<K::NOCT>(p, bitmapAddr, wq.addr, 0, wq.n, lane, stats);
+        }
+    } else if (DIRECT) {
         /* corpus bytes straight from HBM into registers: one coalesced
          * 16-byte load per lane and step, three steps in flight per warp */
         const u64 runStart = (u64)myFirst * p.tileBytes;
@@ -838,8 +995,9 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
                 w4 = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, (lane + 1) & 31);
             }
             const u64 g0 = lanePos + (u64)step * 512;
-            scanStep<KIND, STRIDE, SB>(p, cur, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
-                                       [&]() { return g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u; });
+            scanStep<KIND, STRIDE, SB, 0>(
+                p, cur, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
+                [&]() { return g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u; }, wq, 0);
         }
     } else {
         const u32 stepsPerTile = p.tileBytes >> 9;
@@ -891,8 +1049,8 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
                     }
                 }
                 const u64 g0 = tileBase + step * 512 + lane * 16;
-                scanStep<KIND, STRIDE, SB>(p, v, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
-                                           [&]() { return *reinterpret_cast<const u32 *>(sp - 4); });
+                scanStep<KIND, STRIDE, SB, 0>(p, v, w4, lane, tabAddr, laneOff, bitmapAddr, carry, g0, stats,
+                                              [&]() { return *reinterpret_cast<const u32 *>(sp - 4); }, wq, 0);
             }
             __syncwarp();
             if (lane == 0 && i + p.nstages < myCount) {
@@ -915,22 +1073,30 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
     }
 }
 
-template <int KIND, int STRIDE, int SB, int DIRECT>
+template <int KIND, int STRIDE, int SB, int DIRECT, int QUEUED>
 cudaError_t launchOne(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(scanKernel<KIND, STRIDE, SB, DIRECT>,
+    cudaError_t e = cudaFuncSetAttribute(scanKernel<KIND, STRIDE, SB, DIRECT, QUEUED>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)cfg.smemBytes);
     if (e != cudaSuccess) {
         return e;
     }
-    scanKernel<KIND, STRIDE, SB, DIRECT><<<cfg.grid, cfg.warps * 32, cfg.smemBytes, stream>>>(p);
+    scanKernel<KIND, STRIDE, SB, DIRECT, QUEUED><<<cfg.grid, cfg.warps * 32, cfg.smemBytes, stream>>>(p);
     return cudaGetLastError();
 }
 
 template <int KIND, int STRIDE, int SB>
 cudaError_t launchStaging(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
-    return cfg.direct ? launchOne<KIND, STRIDE, SB, 1>(cfg, p, stream)
-                      : launchOne<KIND, STRIDE, SB, 0>(cfg, p, stream);
+    if (cfg.direct && cfg.queued) {
+        /* the queue variant is built for the default sampling stride only */
+        if constexpr (STRIDE == 1) {
+            return launchOne<KIND, STRIDE, SB, 1, 1>(cfg, p, stream);
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
+    return cfg.direct ? launchOne<KIND, STRIDE, SB, 1, 0>(cfg, p, stream)
+                      : launchOne<KIND, STRIDE, SB, 0, 0>(cfg, p, stream);
 }
 
 template <int KIND, int SB>
@@ -944,9 +1110,10 @@ cudaError_t launchStride(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t
 } // namespace
 
 size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 nstages,
-                     u32 tileBytes) {
+                     u32 tileBytes, int queueWarps) {
+    const size_t perWarp = kind == FK_BYTE64 ? QueueEntry<2>::WARP_BYTES : QueueEntry<1>::WARP_BYTES;
     return tableSmemBytes(kind, tableBytes) + bitmapBytes + (size_t)warps * nstages * (tileBytes + 32) +
-           (size_t)warps * nstages * 8;
+           (size_t)warps * nstages * 8 + (size_t)queueWarps * perWarp;
 }
 
 namespace {
