@@ -58,6 +58,8 @@ struct RuntimeOpts {
     int queue = 2;           /* candidates go through the per-warp shared-memory queue: 0 never, 1 always,
                               * 2 for the per-byte tables (Teddy, noodle: measured +15 %) but not for the
                               * FDR hash table, whose kernel is shared-memory bound either way */
+    int wide = 0;            /* 1: wide-step kernel (32-byte lanes, always queued) for FK_BYTE32 / FK_HASH32;
+                              * built at the end of round 1, not yet measured */
     int firstStage = 1;      /* FDR databases: 1 = two-byte hash table (FK_HASH32), 2 = per-byte table
                               * (FK_BYTE32, conflict-free lookups, more candidates), 0 = choose by the
                               * modelled candidate rate of the per-byte table */
@@ -80,7 +82,7 @@ void initOpts() {
         {"HSB200_REBUILD", &g_opts.rebuild},   {"HSB200_DOMAIN", &g_opts.domain},
         {"HSB200_DIRECT", &g_opts.direct},     {"HSB200_REPLICAS", &g_opts.replicas},
         {"HSB200_PF_DIST", &g_opts.pfDist},    {"HSB200_QUEUE", &g_opts.queue},
-        {"HSB200_FIRST_STAGE", &g_opts.firstStage}};
+        {"HSB200_FIRST_STAGE", &g_opts.firstStage}, {"HSB200_WIDE", &g_opts.wide}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -672,10 +674,14 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
         stride = g_opts.stride; /* any sampling subset is a sound filter */
     }
     const bool byteKind = im->kind == FK_BYTE32 || im->kind == FK_BYTE64;
+    const int wide = g_opts.wide && direct && stride == 1 && (im->kind == FK_BYTE32 || im->kind == FK_HASH32);
     const int queued = direct && stride == 1 && (g_opts.queue == 1 || (g_opts.queue == 2 && byteKind));
+    if (wide) {
+        tile = std::max(1024u, tile & ~1023u); /* a warp-iteration covers 1 KiB */
+    }
     for (;;) {
         const size_t need = scanSmemBytes(im->kind, im->tableBytes, im->bitmapBytes, direct ? 0 : warps,
-                                          stages, tile, queued ? warps : 0);
+                                          stages, tile, wide ? -warps : queued ? warps : 0);
         if (need <= (size_t)s->maxSmem) {
             pl->cfg.smemBytes = need;
             break;
@@ -699,6 +705,7 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     pl->cfg.direct = direct;
     pl->cfg.stride = stride;
     pl->cfg.queued = queued;
+    pl->cfg.wide = wide;
     pl->cfg.grid = s->smCount;
     pl->cfg.warps = warps;
     pl->tileBytes = tile;
@@ -931,7 +938,7 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"rebuild", &g_opts.rebuild},   {"domain", &g_opts.domain},
         {"direct", &g_opts.direct},     {"replicas", &g_opts.replicas},
         {"pf_dist", &g_opts.pfDist},    {"queue", &g_opts.queue},
-        {"first_stage", &g_opts.firstStage}};
+        {"first_stage", &g_opts.firstStage}, {"wide", &g_opts.wide}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;

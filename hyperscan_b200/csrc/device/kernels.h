@@ -99,13 +99,15 @@ struct LaunchCfg {
     int slotBase;  /* FK_HASH32: 0 = slots 0..3 (reference numbering), 1 = slots 1..4 */
     int direct;    /* 1: corpus loaded straight into registers; 0: TMA-staged tiles */
     int queued;    /* 1 (direct, stride 1 only): candidates go through the per-warp queue */
+    int wide;      /* 1 (direct, stride 1, FK_BYTE32 / FK_HASH32, tileBytes % 1024 == 0): 32-byte lanes */
     int grid;      /* CTAs (one per SM) */
     int warps;     /* per CTA */
     size_t smemBytes;
 };
 
 /* Dynamic shared memory the kernel needs (warps = warps with TMA stages, 0 in
- * direct mode; queueWarps = warps with a candidate queue, 0 without). */
+ * direct mode; queueWarps = warps with a candidate queue, 0 without, negative =
+ * that many warps of the wide-step variant). */
 size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 nstages,
                      u32 tileBytes, int queueWarps);
 

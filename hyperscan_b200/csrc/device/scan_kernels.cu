@@ -1073,6 +1073,266 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
     }
 }
 
+/* ---- wide-step variant (opt-in, runtime option `wide`) ---------------------------
+ *
+ * Every lane owns 32 CONTIGUOUS bytes (8 words) per iteration and the warp 1 KiB:
+ * the per-step overhead (carry shuffle, vote, loop, prefetch, next-word shuffle)
+ * is paid once per 1 KiB instead of once per 512 bytes and the overflow into the
+ * next lane once per 32 bytes.  Direct mode, stride 1, FK_BYTE32 / FK_HASH32 only;
+ * candidates always go through the per-warp queue (entry = 8 candidate words +
+ * the number of the 32-byte chunk). */
+
+struct WideQueue {
+    static constexpr u32 BYTES = 48;
+    static constexpr u32 SLOTS = 64;
+    static constexpr u32 RUN_START = BYTES * SLOTS;
+    static constexpr u32 WARP_BYTES = RUN_START + 16;
+};
+
+template <int O> __device__ __forceinline__ void orStreamWide(u32 (&a)[9], const u32 (&E)[8]) {
+    if constexpr (O == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] |= E[k];
+    } else if constexpr (O == 4) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k + 1] |= E[k];
+    } else {
+        a[0] |= E[0] << (8 * O);
+#pragma unroll
+        for (int k = 1; k < 8; k++) a[k] |= __funnelshift_l(E[k - 1], E[k], 8 * O);
+        a[8] |= E[7] >> (32 - 8 * O);
+    }
+}
+
+/* a[0..7]: the lane's own 32 end positions, a[8]: overflow into the next lane */
+template <int KIND, int SB>
+__device__ __forceinline__ void laneFilterWide(const u32 (&w)[9], u32 tabAddr, u32 laneOff, u32 indexMask,
+                                               u32 repShift, u32 (&a)[9]) {
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        a[i] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        u32 E[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (KIND == FK_HASH32) {
+                const u32 sh = 2 + repShift;
+                u32 off;
+                if (r == 0) {
+                    off = w[k] << sh;
+                } else if (r == 3) {
+                    off = __funnelshift_r(w[k], w[k + 1], 24 - sh);
+                } else {
+                    off = w[k] >> (8 * r - sh);
+                }
+                E[k] = lds32(tabAddr + (off & (indexMask << sh)));
+            } else {
+                E[k] = lds32(tabAddr + __byte_perm(w[k], laneOff, 0x5504 + (r << 4)));
+            }
+        }
+        if (r + SB == 0) orStreamWide<0>(a, E);
+        if (r + SB == 1) orStreamWide<1>(a, E);
+        if (r + SB == 2) orStreamWide<2>(a, E);
+        if (r + SB == 3) orStreamWide<3>(a, E);
+        if (r + SB == 4) orStreamWide<4>(a, E);
+    }
+}
+
+__device__ __noinline__ void drainWide(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first, u32 count,
+                                       u32 lane, u32 *stats) {
+    if (lane >= count) {
+        return;
+    }
+    const uint2 rs = lds64(qAddr + WideQueue::RUN_START);
+    const u64 runStart = ((u64)rs.y << 32) | rs.x;
+    const u32 e = qAddr + (first + lane) * WideQueue::BYTES;
+    const uint4 c0 = lds128(e), c1 = lds128(e + 16);
+    const u64 g0 = runStart + (u64)lds32(e + 32) * 32;
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+    if (g0 + 16 <= p.readableEnd) {
+        v0 = __ldg(reinterpret_cast<const uint4 *>(p.corpus + g0));
+    }
+    if (g0 + 32 <= p.readableEnd) {
+        v1 = __ldg(reinterpret_cast<const uint4 *>(p.corpus + g0 + 16));
+    }
+    const u32 pw = g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u;
+    if (c0.x | c0.y | c0.z | c0.w) {
+        laneCandidates<1>(p, bitmapAddr, c0.x, c0.y, c0.z, c0.w, 0, 0, 0, 0, v0.x, v0.y, v0.z, v0.w, pw, g0,
+                          stats);
+    }
+    if (c1.x | c1.y | c1.z | c1.w) {
+        laneCandidates<1>(p, bitmapAddr, c1.x, c1.y, c1.z, c1.w, 0, 0, 0, 0, v1.x, v1.y, v1.z, v1.w, v0.w,
+                          g0 + 16, stats);
+    }
+}
+
+template <int KIND, int SB>
+__global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
+    static_assert(KIND == FK_BYTE32 || KIND == FK_HASH32, "wide steps: 8-bucket tables only");
+    extern __shared__ __align__(128) u8 smem[];
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5;
+    const u32 nwarps = blockDim.x >> 5;
+    const u32 tab0 = tableSmemBytes(KIND, p.tableBytes);
+    const u32 tabBytes = tab0 + p.bitmapBytes;
+
+    if (KIND == FK_BYTE32) {
+        const u32 *g = reinterpret_cast<const u32 *>(p.table);
+        u32 *s = reinterpret_cast<u32 *>(smem);
+        for (u32 i = threadIdx.x; i < 256 * 64; i += blockDim.x) {
+            s[i] = ((i >> 5) & 1) ? 0xffffffffu : __ldg(g + (i >> 6));
+        }
+    } else {
+        const uint4 *g = reinterpret_cast<const uint4 *>(p.table);
+        uint4 *s = reinterpret_cast<uint4 *>(smem);
+        for (u32 i = threadIdx.x; i < p.tableBytes / 16; i += blockDim.x) {
+            s[i] = __ldg(g + i);
+        }
+    }
+    if (p.bitmapBytes) {
+        const uint4 *g = reinterpret_cast<const uint4 *>(p.bitmap);
+        uint4 *sdst = reinterpret_cast<uint4 *>(smem + tab0);
+        for (u32 i = threadIdx.x; i < p.bitmapBytes / 16; i += blockDim.x) {
+            sdst[i] = __ldg(g + i);
+        }
+    }
+    __syncthreads();
+
+    const u32 bitmapAddr = smemAddr(smem) + tab0;
+    const u32 tabAddr = smemAddr(smem) + (KIND == FK_HASH32 ? (lane & ((1u << p.repShift) - 1)) * 4 : 0);
+    const u32 laneOff = lane * 4;
+    const u32 qAddr = smemAddr(smem) + tabBytes + warp * WideQueue::WARP_BYTES;
+
+    /* this warp's contiguous run of tiles (tileBytes is a multiple of 1024 here) */
+    const u32 gwarp = blockIdx.x * nwarps + warp;
+    const u32 totalWarps = gridDim.x * nwarps;
+    const u32 q = p.ntiles / totalWarps, rem = p.ntiles % totalWarps;
+    const u32 myCount = q + (gwarp < rem ? 1u : 0u);
+    const u32 myFirst = p.tileFirst + gwarp * q + min(gwarp, rem);
+    if (myCount == 0) {
+        return;
+    }
+    const u64 runStart = (u64)myFirst * p.tileBytes;
+    u64 runEnd = runStart + (u64)myCount * p.tileBytes;
+    if (runEnd > p.corpusBytes) {
+        runEnd = p.corpusBytes;
+    }
+    const u32 niter = (u32)((runEnd - runStart + 1023) >> 10);
+    const u8 *base = p.corpus + runStart + lane * 32;
+    const u64 lanePos = runStart + lane * 32;
+    if (lane == 0) {
+        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(qAddr + WideQueue::RUN_START), "r"((u32)runStart),
+                     "r"((u32)(runStart >> 32))
+                     : "memory");
+    }
+
+    u32 carry[2][2] = {{0, 0}, {0, 0}};
+    u32 stats[3] = {0, 0, 0};
+    u32 qn = 0;
+
+    auto load = [&](u32 it, uint4 &lo, uint4 &hi) {
+        const u64 pos = lanePos + (u64)it * 1024;
+        lo = make_uint4(0, 0, 0, 0);
+        hi = make_uint4(0, 0, 0, 0);
+        const u8 *q0 = base + (size_t)it * 1024;
+        if (pos + 32 <= p.readableEnd) {
+            asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w)
+                         : "l"(q0));
+            asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+                         : "l"(q0 + 16));
+        } else if (pos + 16 <= p.readableEnd) {
+            asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w)
+                         : "l"(q0));
+        }
+    };
+    const u32 pfDist = p.nstages; /* L2 prefetch distance in 1 KiB iterations */
+    uint4 nlo, nhi;
+    load(0, nlo, nhi);
+    if (runStart != 0) {
+        /* only the 4 bytes before the run (and its first word) reach into it */
+        const uint4 hv = __ldg(reinterpret_cast<const uint4 *>(p.corpus + runStart - 16));
+        const u32 first = __shfl_sync(0xffffffffu, nlo.x, 0);
+        haloStep<KIND, 1, SB>(p, hv, first, tabAddr, laneOff, carry);
+    }
+    for (u32 it = 0; it < niter; it++) {
+        const uint4 lo = nlo, hi = nhi;
+        load(it + 1, nlo, nhi);
+        if ((lane & 3) == 0) {
+            const u64 pos = lanePos + (u64)(it + pfDist) * 1024;
+            if (pos < p.readableEnd) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.corpus + pos));
+            }
+        }
+        u32 w8 = 0;
+        if (KIND == FK_HASH32) {
+            w8 = __shfl_sync(0xffffffffu, lane == 0 ? nlo.x : lo.x, (lane + 1) & 31);
+        }
+        const u32 w[9] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w, w8};
+        u32 a[9];
+        laneFilterWide<KIND, SB>(w, tabAddr, laneOff, p.indexMask, p.repShift, a);
+        {
+            u32 in = __shfl_sync(0xffffffffu, a[8], (lane + 31) & 31);
+            if (lane == 0) {
+                const u32 next = in;
+                in = carry[0][0];
+                carry[0][0] = next;
+            }
+            a[0] |= in;
+        }
+        u32 any = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            a[k] = ~a[k];
+            any |= a[k];
+        }
+        const u32 bal = __ballot_sync(0xffffffffu, any != 0);
+        if (bal) {
+            if (any) {
+                const u32 e = qAddr + (qn + __popc(bal & ((1u << lane) - 1))) * WideQueue::BYTES;
+                sts128(e, a[0], a[1], a[2], a[3]);
+                sts128(e + 16, a[4], a[5], a[6], a[7]);
+                sts32(e + 32, it * 32 + lane);
+            }
+            qn += __popc(bal);
+            if (qn >= 32) {
+                __syncwarp();
+                qn -= 32;
+                drainWide(p, bitmapAddr, qAddr, qn, 32, lane, stats);
+                __syncwarp();
+            }
+        }
+    }
+    if (qn) {
+        __syncwarp();
+        drainWide(p, bitmapAddr, qAddr, 0, qn, lane, stats);
+    }
+    if (stats[0]) {
+        atomicAdd(p.counters + CTR_CANDIDATES, stats[0]);
+    }
+    if (stats[1]) {
+        atomicAdd(p.counters + CTR_PREFILTER_PASS, stats[1]);
+    }
+    if (stats[2]) {
+        atomicAdd(p.counters + CTR_CONFIRMED, stats[2]);
+    }
+}
+
+template <int KIND, int SB>
+cudaError_t launchWide(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(scanKernelWide<KIND, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)cfg.smemBytes);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    scanKernelWide<KIND, SB><<<cfg.grid, cfg.warps * 32, cfg.smemBytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
 template <int KIND, int STRIDE, int SB, int DIRECT, int QUEUED>
 cudaError_t launchOne(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(scanKernel<KIND, STRIDE, SB, DIRECT, QUEUED>,
@@ -1111,7 +1371,12 @@ cudaError_t launchStride(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t
 
 size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 nstages,
                      u32 tileBytes, int queueWarps) {
-    const size_t perWarp = kind == FK_BYTE64 ? QueueEntry<2>::WARP_BYTES : QueueEntry<1>::WARP_BYTES;
+    const size_t perWarp = queueWarps < 0          ? WideQueue::WARP_BYTES /* wide-step variant */
+                           : kind == FK_BYTE64     ? QueueEntry<2>::WARP_BYTES
+                                                   : QueueEntry<1>::WARP_BYTES;
+    if (queueWarps < 0) {
+        queueWarps = -queueWarps;
+    }
     return tableSmemBytes(kind, tableBytes) + bitmapBytes + (size_t)warps * nstages * (tileBytes + 32) +
            (size_t)warps * nstages * 8 + (size_t)queueWarps * perWarp;
 }
@@ -1199,6 +1464,19 @@ cudaError_t launchPublishCount(const ScanParams &p, cudaStream_t stream) {
 }
 
 cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    if (cfg.wide) {
+        if (!cfg.direct || cfg.stride != 1 || (p.tileBytes & 1023)) {
+            return cudaErrorInvalidValue;
+        }
+        if (cfg.kind == FK_BYTE32) {
+            return launchWide<FK_BYTE32, 0>(cfg, p, stream);
+        }
+        if (cfg.kind == FK_HASH32) {
+            return cfg.slotBase ? launchWide<FK_HASH32, 1>(cfg, p, stream)
+                                : launchWide<FK_HASH32, 0>(cfg, p, stream);
+        }
+        return cudaErrorInvalidValue;
+    }
     switch (cfg.kind) {
     case FK_BYTE32:
         return launchStaging<FK_BYTE32, 1, 0>(cfg, p, stream);

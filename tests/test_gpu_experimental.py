@@ -1,0 +1,57 @@
+"""Parity of the opt-in kernel variants that were written but not yet measured
+or validated on a GPU (runtime options `wide`, `queue=1` on hash tables,
+`first_stage=2`).  They are not on any default path; this file only runs with
+HSB200_EXPERIMENTAL=1 so that an unvalidated variant cannot fail the default
+GPU suite.  Same checks as tests/test_gpu_parity.py::_check_all."""
+import os
+
+import numpy as np
+import pytest
+
+from hyperscan_b200 import synth
+from test_gpu_parity import _check_all
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("HSB200_EXPERIMENTAL") != "1",
+                                 reason="opt-in variants: set HSB200_EXPERIMENTAL=1")]
+
+DEFAULTS = {"wide": 0, "queue": 2, "first_stage": 1, "replicas": 1, "domain": 0, "tile_bytes": 1024,
+            "warps": 32}
+VARIANTS = [
+    {"wide": 1},
+    {"wide": 1, "domain": 12, "replicas": 8},
+    {"wide": 1, "tile_bytes": 4096, "warps": 5},
+    {"queue": 1},
+    {"queue": 1, "first_stage": 2},
+    {"wide": 1, "first_stage": 2},
+]
+
+
+@pytest.mark.parametrize("opts", VARIANTS, ids=[",".join("%s=%d" % kv for kv in v.items()) for v in VARIANTS])
+@pytest.mark.parametrize("nlits", [1, 30, 48, 300, 1000])
+def test_variant_parity(hs, ref, opts, nlits):
+    lits, flags, ids = synth.literal_set(nlits, min_len=2 if nlits < 40 else 4, max_len=12, seed=nlits + 7,
+                                         caseless_frac=0.2, alphabet=b"abcdefgh")
+    data, off, ln = synth.ragged_corpus([0, 1, 3, 15, 16, 17, 31, 32, 33, 100, 511, 512, 513, 1023, 1024, 1025,
+                                         2047, 2048, 2049, 4096, 10000, 65536 + 5, 200000], lits, seed=3,
+                                        alphabet=b"abcdefghABCDxy")
+    try:
+        for k, v in opts.items():
+            hs.set_runtime_option(k, v)
+        _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
+    finally:
+        for k, v in DEFAULTS.items():
+            hs.set_runtime_option(k, v)
+
+
+@pytest.mark.parametrize("opts", VARIANTS[:3], ids=["wide", "wide-d12x8", "wide-geom"])
+def test_variant_config2_sample(hs, ref, opts):
+    lits, flags, ids = synth.literal_set(1000)
+    data, off, ln, _ = synth.block_corpus(4096, 1024, lits, plant_per_kb=0.05, seed=9)
+    try:
+        for k, v in opts.items():
+            hs.set_runtime_option(k, v)
+        _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
+    finally:
+        for k, v in DEFAULTS.items():
+            hs.set_runtime_option(k, v)
