@@ -115,6 +115,7 @@ def lib():
         L.hs_b200_streams_state_bytes.restype = C.c_size_t
         L.hs_open_stream.argtypes = [vp, C.c_uint, C.POINTER(vp)]
         L.hs_scan_stream.argtypes = [vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
+        L.hs_scan_vector.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
         L.hs_close_stream.argtypes = [vp, vp, MATCH_CB, vp]
         L.hs_reset_stream.argtypes = [vp, C.c_uint, vp, MATCH_CB, vp]
         L.hs_copy_stream.argtypes = [C.POINTER(vp), vp]
@@ -454,6 +455,23 @@ class Stream:
             self.ptr = C.c_void_p()
             return rc
         return HS_SUCCESS
+
+
+def scan_vector(db, buffers, scratch, stop_after=0):
+    """hs_scan_vector(): `buffers` = list of bytes-like; returns (rc, [(id, to), ...])
+    in delivery order, `to` counted from the start of the first buffer."""
+    arrs = [_as_u8(b) for b in buffers]
+    pad = np.zeros(1, dtype=np.uint8)
+    ptrs = (C.c_void_p * max(1, len(arrs)))(*[(a if a.size else pad).ctypes.data for a in arrs])
+    lens = (C.c_uint * max(1, len(arrs)))(*[a.size for a in arrs])
+    out = []
+
+    def cb(i, frm, to, flags, ctx):
+        out.append((int(i), int(to)))
+        return 1 if (stop_after and len(out) >= stop_after) else 0
+
+    rc = lib().hs_scan_vector(db.ptr, ptrs, lens, len(arrs), 0, scratch.ptr, MATCH_CB(cb), None)
+    return rc, out
 
 
 class StreamSet:

@@ -1844,15 +1844,12 @@ hs_error_t hs_open_stream(const hs_database_t *db, unsigned int flags, hs_stream
     return HS_SUCCESS;
 }
 
-hs_error_t hs_scan_stream(hs_stream_t *st, const char *data, unsigned int length, unsigned int flags,
-                          hs_scratch_t *scratch, match_event_handler onEvent, void *context) {
-    (void)flags;
-    if (!validStream(st) || !scratch || !data || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
-        return HS_INVALID;
-    }
-    if (markInUse(scratch)) {
-        return HS_SCRATCH_IN_USE;
-    }
+/* One write of one stream (hs_scan_stream_internal, src/runtime.c:870-977):
+ * scan look-behind ++ write as a block, deliver the matches that end inside the
+ * write at stream offsets, roll the history forward.  The scratch is already
+ * marked in use by the caller. */
+static hs_error_t streamWrite(hs_stream *st, const char *data, unsigned int length, hs_scratch_t *scratch,
+                              match_event_handler onEvent, void *context) {
     hs_error_t r = HS_SUCCESS;
     if (st->status & 1) {
         r = HS_SCAN_TERMINATED; /* the stream is broken: src/runtime.c:883-893 */
@@ -1895,6 +1892,67 @@ hs_error_t hs_scan_stream(hs_stream_t *st, const char *data, unsigned int length
                 st->offset += length;
             }
         }
+    }
+    return r;
+}
+
+hs_error_t hs_scan_stream(hs_stream_t *st, const char *data, unsigned int length, unsigned int flags,
+                          hs_scratch_t *scratch, match_event_handler onEvent, void *context) {
+    (void)flags;
+    if (!validStream(st) || !scratch || !data || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    const hs_error_t r = streamWrite(st, data, length, scratch, onEvent, context);
+    unmarkInUse(scratch);
+    return r;
+}
+
+/* src/runtime.c:1106-1175: a temporary stream, one write per buffer, closed at
+ * the end (pure-literal databases have no end-of-data reports). */
+hs_error_t hs_scan_vector(const hs_database_t *db, const char *const *data, const unsigned int *length,
+                          unsigned int count, unsigned int flags, hs_scratch_t *scratch,
+                          match_event_handler onEvent, void *context) {
+    (void)flags;
+    if (!scratch || !data || !length) {
+        return HS_INVALID;
+    }
+    hs_error_t err = validDb(db);
+    if (err != HS_SUCCESS) {
+        return err;
+    }
+    const RoseEngine *rose = dbRose(db);
+    if ((uintptr_t)rose % 16) {
+        return HS_INVALID;
+    }
+    if (rose->mode != MODE_VECTORED) {
+        return HS_DB_MODE_ERROR;
+    }
+    if ((uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
+        return HS_INVALID;
+    }
+    if (rose->runtimeImpl != RUNTIME_PURE_LITERAL || rose->historyRequired > sizeof(((hs_stream *)0)->hist)) {
+        return HS_ARCH_ERROR;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    std::unordered_set<u32> seen;
+    hs_stream st;
+    memset(&st, 0, sizeof(st));
+    st.magic = STREAM_MAGIC;
+    st.db = db;
+    st.hreq = rose->historyRequired;
+    st.seen = &seen;
+    hs_error_t r = HS_SUCCESS;
+    for (unsigned int i = 0; i < count && r == HS_SUCCESS; i++) {
+        if (!data[i]) {
+            r = HS_INVALID; /* hs_scan_stream_internal: src/runtime.c:875 */
+            break;
+        }
+        r = streamWrite(&st, data[i], length[i], scratch, onEvent, context);
     }
     unmarkInUse(scratch);
     return r;

@@ -448,11 +448,6 @@ static bool checkMode(unsigned mode, std::string *why) {
             return false;
         }
     }
-    if (mode & HS_MODE_VECTORED) {
-        *why = "This build of the B200 runtime compiles block and streaming databases; vectored "
-               "mode is not supported.";
-        return false;
-    }
     return true;
 }
 
@@ -633,7 +628,8 @@ static hs_error_t compileCommon(const char *const *expressions,
         }
         CompileOpts opts;
         opts.pureLiteralApi = litApi;
-        opts.streaming = (mode & HS_MODE_STREAM) != 0;
+        opts.streaming = (mode & (HS_MODE_STREAM | HS_MODE_VECTORED)) != 0; /* isStreaming || isVectored: src/hs.cpp, util/compile_context.h:47-48 */
+        opts.vectored = (mode & HS_MODE_VECTORED) != 0;
         if (platform && (platform->cpu_features & HS_CPU_FEATURES_AVX2)) {
             /* the caller targets AVX2+ reference runtimes: 16-bucket Teddy is
              * allowed and the database is stamped accordingly

@@ -107,8 +107,8 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
             /* in streaming mode literals beyond the literal matcher's 8 bytes need
              * the long-literal table and the full rose runtime
              * (src/rose/rose_build_bytecode.cpp:292-296 isPureFloating) */
-            throw CompileError{"Streaming mode in this build supports literals of up to 8 bytes; "
-                               "longer literals need the long literal table.", (int)p.index};
+            throw CompileError{"Streaming and vectored modes in this build support literals of up to 8 "
+                               "bytes; longer literals need the long literal table.", (int)p.index};
         }
         auto it = idHighlander.find(p.report);
         if (it == idHighlander.end()) {
@@ -317,7 +317,8 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
     r.pureLiteral = opts.pureLiteralApi ? 1 : 0;
     r.runtimeImpl = RUNTIME_PURE_LITERAL;
     r.canExhaust = allHighlander ? 1 : 0;
-    r.mode = opts.streaming ? MODE_STREAM : MODE_BLOCK;
+    /* src/rose/rose_build_bytecode.cpp:3615-3622 */
+    r.mode = !opts.streaming ? MODE_BLOCK : opts.vectored ? MODE_VECTORED : MODE_STREAM;
     u32 maxLen = 0;
     for (const auto &pi : pats) {
         maxLen = std::max<u32>(maxLen, (u32)pi.folded.size());

@@ -30,7 +30,9 @@ struct LitPattern {
 
 struct CompileOpts {
     bool pureLiteralApi = false; /* hs_compile_lit*: sets RoseEngine.pureLiteral */
-    bool streaming = false;      /* HS_MODE_STREAM: history + per-stream state (literals <= 8 bytes) */
+    bool streaming = false;      /* HS_MODE_STREAM / HS_MODE_VECTORED: history + per-stream state
+                                  * (literals <= 8 bytes); src/util/compile_context.h:47-48 */
+    bool vectored = false;       /* HS_MODE_VECTORED: a streaming database stamped for hs_scan_vector */
     u64 platform = PLATFORM_NOAVX2 | PLATFORM_NOAVX512 | PLATFORM_NOAVX512VBMI;
     HwlmBuildOpts hwlm;
 };

@@ -213,6 +213,16 @@ hs_error_t hs_reset_and_copy_stream(hs_stream_t *to_id, const hs_stream_t *from_
                                     hs_scratch_t *scratch, match_event_handler onEvent,
                                     void *context);
 
+/* --- vectored mode (src/hs_runtime.h:484-527; src/runtime.c:1106-1175): the
+ * `count` buffers are scanned as ONE stream in the order given -- matches may
+ * span buffers and `to` counts from the start of the first buffer.  Needs a
+ * database compiled with HS_MODE_VECTORED (HS_DB_MODE_ERROR otherwise); built,
+ * like streaming, for literals of up to 8 bytes. */
+hs_error_t hs_scan_vector(const hs_database_t *db, const char *const *data,
+                          const unsigned int *length, unsigned int count,
+                          unsigned int flags, hs_scratch_t *scratch,
+                          match_event_handler onEvent, void *context);
+
 /* ------------------------------------------------------------------------
  * Part 2: B200 batch / device-resident extension
  * ---------------------------------------------------------------------- */

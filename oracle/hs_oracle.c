@@ -678,13 +678,13 @@ struct ostream {
     size_t work_bytes;
 };
 
-API void *oracle_open_stream(const void *db) {
+static void *open_stream_mode(const void *db, u32 mode) {
     const struct db_header *h = (const struct db_header *)db;
     if (!h || h->magic != 0xdbdbdbdbU) {
         return NULL;
     }
     const u8 *rose = (const u8 *)db + h->bytecode;
-    if (rd32(rose + RE_mode) != 2 || rose[RE_runtimeImpl] != 1) { /* HS_MODE_STREAM, PURE_LITERAL */
+    if (rd32(rose + RE_mode) != mode || rose[RE_runtimeImpl] != 1) { /* HS_MODE_*, PURE_LITERAL */
         return NULL;
     }
     struct ostream *st = (struct ostream *)calloc(1, sizeof(*st));
@@ -697,6 +697,10 @@ API void *oracle_open_stream(const void *db) {
     st->work_bytes = work_size(db);
     st->work = (u8 *)calloc(1, st->work_bytes);
     return st;
+}
+
+API void *oracle_open_stream(const void *db) {
+    return open_stream_mode(db, 2); /* HS_MODE_STREAM */
 }
 
 API int oracle_scan_stream(void *stream, const char *data, unsigned len, user_cb cb, void *ctx) {
@@ -776,6 +780,32 @@ API long oracle_stream_collect(const void *db, const char *data, const unsigned 
         c.block = (u32)i;
         rv = oracle_scan_stream(st, data + pos, write_lengths[i], collect_cb, &c);
         pos += write_lengths[i];
+        if (rv != 0) {
+            break;
+        }
+    }
+    oracle_close_stream(st);
+    if (last_err) {
+        *last_err = rv;
+    }
+    return (long)c.n;
+}
+
+/* hs_scan_vector (src/runtime.c:1106-1175): a temporary stream over a
+ * HS_MODE_VECTORED database, one write per buffer, closed at the end. */
+API long oracle_vector_collect(const void *db, const char *data, const unsigned *buf_lengths,
+                               size_t nbufs, struct rec16 *out, size_t cap, size_t stop_after,
+                               int *last_err) {
+    void *st = open_stream_mode(db, 4); /* HS_MODE_VECTORED */
+    if (!st) {
+        return -1;
+    }
+    struct collect c = {out, cap, 0, stop_after, 0};
+    int rv = 0;
+    size_t pos = 0;
+    for (size_t i = 0; i < nbufs; i++) {
+        rv = oracle_scan_stream(st, data + pos, buf_lengths[i], collect_cb, &c);
+        pos += buf_lengths[i];
         if (rv != 0) {
             break;
         }

@@ -29,6 +29,9 @@ def lib():
         L.oracle_scan_blocks_mt.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_uint, C.c_uint,
                                             C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
         L.oracle_stream_collect.restype = C.c_long
+        L.oracle_vector_collect.restype = C.c_long
+        L.oracle_vector_collect.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t,
+                                            C.POINTER(C.c_int)]
         L.oracle_stream_collect.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t,
                                             C.POINTER(C.c_int)]
         L.oracle_hwlm_exec.restype = C.c_long
@@ -66,6 +69,23 @@ def stream_collect(db_ptr, data, write_lengths, stop_after=0):
                                         cap, stop_after, C.byref(err))
         if n < 0:
             raise RuntimeError("oracle stream open failed")
+        if n <= cap:
+            return out[:n], err.value
+        cap = int(n) + 16
+
+
+def vector_collect(db_ptr, data, buf_lengths, stop_after=0):
+    a = _u8(data)
+    keep = a if a.size else np.zeros(1, dtype=np.uint8)
+    bl = np.ascontiguousarray(buf_lengths, dtype=np.uint32)
+    cap = 1 << 18
+    while True:
+        out = np.zeros(cap, dtype=REC_DTYPE)
+        err = C.c_int()
+        n = lib().oracle_vector_collect(db_ptr, keep.ctypes.data, bl.ctypes.data, bl.size, out.ctypes.data,
+                                        cap, stop_after, C.byref(err))
+        if n < 0:
+            raise RuntimeError("oracle: not a vectored pure-literal database")
         if n <= cap:
             return out[:n], err.value
         cap = int(n) + 16

@@ -53,6 +53,8 @@ def lib(isa=None):
         L.ref_scan_collect.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t,
                                        C.POINTER(C.c_int)]
         L.ref_stream_collect.restype = C.c_long
+        L.ref_vector_collect.restype = C.c_long
+        L.ref_vector_collect.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_int)]
         L.ref_stream_collect.argtypes = [vp, vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.POINTER(C.c_int)]
         L.ref_scan_blocks_mt.restype = C.c_double
         L.ref_scan_blocks_mt.argtypes = [vp, vp, vp, vp, C.c_size_t, C.c_uint, C.c_uint,
@@ -112,6 +114,27 @@ def stream_collect(db_ptr, data, write_lengths, stop_after=0, isa=None):
                                         cap, stop_after, C.byref(err))
         if n < 0:
             raise RuntimeError("reference stream open failed: %d" % n)
+        if n <= cap:
+            return out[:n], err.value
+        cap = int(n) + 16
+
+
+def vector_collect(db_ptr, data, buf_lengths, stop_after=0, isa=None):
+    """Reference hs_scan_vector over `data` cut into consecutive buffers; records
+    (id, 0, to counted from the first buffer) in delivery order + the call's
+    return code."""
+    a = _u8(data)
+    keep = a if a.size else np.zeros(1, dtype=np.uint8)
+    bl = np.ascontiguousarray(buf_lengths, dtype=np.uint32)
+    assert int(bl.sum()) == a.size
+    cap = 1 << 18
+    while True:
+        out = np.zeros(cap, dtype=REC_DTYPE)
+        err = C.c_int()
+        n = lib(isa).ref_vector_collect(db_ptr, keep.ctypes.data, bl.ctypes.data, bl.size, out.ctypes.data,
+                                        cap, stop_after, C.byref(err))
+        if n < 0:
+            raise RuntimeError("reference scratch allocation failed: %d" % n)
         if n <= cap:
             return out[:n], err.value
         cap = int(n) + 16

@@ -14,6 +14,7 @@
  *                        counting callback; returns wall seconds.
  *   ref_scan_collect     scan blocks and collect (block,id,to) records.
  *   ref_stream_collect   one stream cut into writes, (id, write, to) records.
+ *   ref_vector_collect   hs_scan_vector over consecutive buffers, (id, 0, to).
  *   ref_layout_dump      print sizeof/offsetof of every bytecode struct our
  *                        ref_layout.h restates (golden file for layout tests).
  */
@@ -216,6 +217,35 @@ API long ref_stream_collect(const hs_database_t *db, const char *data,
     if (last_err) {
         *last_err = (int)rv;
     }
+    hs_free_scratch(scratch);
+    return (long)c.n;
+}
+
+/* Vectored mode: the data cut into `nbufs` consecutive buffers handed to the
+ * reference hs_scan_vector() (src/runtime.c:1106-1175) in one call.  Records
+ * (id, 0, to) in delivery order; `to` counts from the first buffer. */
+API long ref_vector_collect(const hs_database_t *db, const char *data,
+                            const unsigned *buf_lengths, size_t nbufs,
+                            struct rec16 *out, size_t cap, size_t stop_after,
+                            int *last_err) {
+    hs_scratch_t *scratch = NULL;
+    hs_error_t err = hs_alloc_scratch(db, &scratch);
+    if (err != HS_SUCCESS) {
+        return (long)err;
+    }
+    const char **ptrs = (const char **)malloc((nbufs + 1) * sizeof(*ptrs));
+    size_t pos = 0;
+    for (size_t i = 0; i < nbufs; i++) {
+        ptrs[i] = data + pos;
+        pos += buf_lengths[i];
+    }
+    struct collect_ctx c = {out, cap, 0, 0, stop_after};
+    hs_error_t rv = hs_scan_vector(db, ptrs, buf_lengths, (unsigned)nbufs, 0,
+                                   scratch, collect_cb, &c);
+    if (last_err) {
+        *last_err = (int)rv;
+    }
+    free(ptrs);
     hs_free_scratch(scratch);
     return (long)c.n;
 }

@@ -69,8 +69,8 @@ def test_stream_compile_rules(hs, ref):
     with pytest.raises(hs.HsError) as e:          # long literals need the long-literal table
         hs.compile_lit_multi([b"abcdefghi"], mode=hs.HS_MODE_STREAM)
     assert "long literal" in e.value.message
-    with pytest.raises(hs.HsError):
-        hs.compile_lit_multi([b"abc"], mode=hs.HS_MODE_VECTORED)
+    with pytest.raises(hs.HsError):               # one (and only one) of BLOCK / STREAM / VECTORED
+        hs.compile_lit_multi([b"abc"], mode=hs.HS_MODE_VECTORED | hs.HS_MODE_STREAM)
 
 
 @pytest.mark.gpu
