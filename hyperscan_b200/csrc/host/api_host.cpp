@@ -10,7 +10,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <cctype>
 #include <new>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -468,65 +471,296 @@ static bool checkPlatformInfo(const hs_platform_info_t *p, std::string *why) {
     return true;
 }
 
-/* Turn a regex that denotes one literal string into its bytes (PCRE escapes
- * as the reference parser accepts them, src/parser/Parser.rl).  Throws a
- * CompileError for every construct that needs the regex back end. */
-static std::string regexToLiteral(const char *re, unsigned flags, int idx) {
-    std::string out;
-    const size_t n = strlen(re);
-    auto hex = [&](char c) -> int {
+/* Turn a regex that denotes a FINITE set of strings into that set: literal
+ * characters and PCRE escapes as the reference parser accepts them
+ * (src/parser/Parser.rl), groups "(...)" / "(?:...)" (Hyperscan does not
+ * capture), alternation, character classes without negation, and the bounded
+ * repeats "?", "{n}", "{n,m}".  Every string of the set becomes one literal of
+ * the pure-literal matcher under the expression's id (the report rules dedupe
+ * equal (id, to)), so such an expression needs none of the regex engines.
+ * Throws a CompileError for every construct that does. */
+class FiniteRegex {
+public:
+    FiniteRegex(const char *re_in, unsigned flags_in, int idx_in)
+        : re(re_in), n(strlen(re_in)), flags(flags_in), idx(idx_in) {}
+
+    std::vector<std::string> expand() {
+        std::set<std::string> out = alt();
+        if (pos != n) {
+            fail("Unmatched parentheses.");
+        }
+        return std::vector<std::string>(out.begin(), out.end());
+    }
+
+private:
+    static const size_t MAX_STRINGS = 4096;   /* literals one expression may expand to */
+    static const size_t MAX_CLASS = 64;
+
+    const char *re;
+    size_t n, pos = 0;
+    unsigned flags;
+    int idx;
+
+    [[noreturn]] void fail(const std::string &m) const { throw CompileError{m, idx}; }
+    [[noreturn]] void needsRegex(const std::string &what) const {
+        fail(what + " needs the regex back end; this build compiles expressions that denote a "
+                    "finite set of literals only.");
+    }
+    bool at(char c) const { return pos < n && re[pos] == c; }
+
+    static void cap(const std::set<std::string> &s, const FiniteRegex *self) {
+        if (s.size() > MAX_STRINGS) {
+            self->fail("Expression expands to more than 4096 literals; it needs the regex back end.");
+        }
+    }
+
+    std::set<std::string> product(const std::set<std::string> &a, const std::set<std::string> &b) const {
+        std::set<std::string> r;
+        for (const std::string &x : a) {
+            for (const std::string &y : b) {
+                if (x.size() + y.size() > LIMIT_PATTERN_LENGTH) {
+                    fail("Pattern length exceeds limit.");
+                }
+                r.insert(x + y);
+            }
+            cap(r, this);
+        }
+        return r;
+    }
+
+    std::set<std::string> alt() {
+        std::set<std::string> r = seq();
+        while (at('|')) {
+            pos++;
+            std::set<std::string> t = seq();
+            r.insert(t.begin(), t.end());
+            cap(r, this);
+        }
+        return r;
+    }
+
+    std::set<std::string> seq() {
+        std::set<std::string> cur = {std::string()};
+        while (pos < n && re[pos] != '|' && re[pos] != ')') {
+            const std::set<std::string> a = atom();
+            unsigned lo = 1, hi = 1;
+            quantifier(&lo, &hi);
+            std::set<std::string> opts, power = {std::string()};
+            for (unsigned k = 0; k <= hi; k++) {
+                if (k >= lo) {
+                    opts.insert(power.begin(), power.end());
+                    cap(opts, this);
+                }
+                if (k < hi) {
+                    power = product(power, a);
+                }
+            }
+            cur = product(cur, opts);
+        }
+        return cur;
+    }
+
+    void quantifier(unsigned *lo, unsigned *hi) {
+        if (pos >= n) {
+            return;
+        }
+        const char c = re[pos];
+        if (c == '*' || c == '+') {
+            needsRegex(std::string("Unbounded repeat '") + c + "'");
+        }
+        if (c == '?') {
+            pos++;
+            *lo = 0;
+            *hi = 1;
+        } else if (c == '{') {
+            size_t q = pos + 1;
+            unsigned long a = 0, b = 0;
+            bool haveA = false, haveB = false, comma = false;
+            while (q < n && isdigit((unsigned char)re[q])) {
+                a = std::min(a * 10 + (re[q++] - '0'), 100000ul);
+                haveA = true;
+            }
+            if (q < n && re[q] == ',') {
+                comma = true;
+                q++;
+                while (q < n && isdigit((unsigned char)re[q])) {
+                    b = std::min(b * 10 + (re[q++] - '0'), 100000ul);
+                    haveB = true;
+                }
+            }
+            if (!haveA || q >= n || re[q] != '}') {
+                needsRegex("A '{' that does not start a repeat"); /* PCRE: literal brace */
+            }
+            if (comma && !haveB) {
+                needsRegex("Unbounded repeat '{n,}'");
+            }
+            if (!comma) {
+                b = a;
+            }
+            if (b < a) {
+                fail("Bounded repeat is invalid: min > max.");
+            }
+            if (b > LIMIT_PATTERN_LENGTH) {
+                fail("Bounded repeat is too large.");
+            }
+            pos = q + 1;
+            *lo = (unsigned)a;
+            *hi = (unsigned)b;
+        } else {
+            return;
+        }
+        if (pos < n && (re[pos] == '?' || re[pos] == '+')) {
+            needsRegex("Lazy / possessive quantifier");
+        }
+    }
+
+    static int hexval(char c) {
         if (c >= '0' && c <= '9') return c - '0';
         if (c >= 'a' && c <= 'f') return c - 'a' + 10;
         if (c >= 'A' && c <= 'F') return c - 'A' + 10;
         return -1;
-    };
-    for (size_t i = 0; i < n; i++) {
-        unsigned char c = (unsigned char)re[i];
-        if (c == '\\') {
-            if (++i >= n) {
-                throw CompileError{"Unterminated escape at end of pattern.", idx};
+    }
+
+    /* one escaped character; pos is at the backslash */
+    unsigned char escape(bool inClass) {
+        if (++pos >= n) {
+            fail("Unterminated escape at end of pattern.");
+        }
+        const unsigned char e = (unsigned char)re[pos++];
+        switch (e) {
+        case 'n': return '\n';
+        case 't': return '\t';
+        case 'r': return '\r';
+        case 'f': return '\f';
+        case 'a': return '\a';
+        case 'e': return 0x1b;
+        case 'x': {
+            const int h1 = pos < n ? hexval(re[pos]) : -1;
+            const int h2 = pos + 1 < n ? hexval(re[pos + 1]) : -1;
+            if (h1 < 0 || h2 < 0) {
+                fail("Invalid hex escape; only \\xHH is accepted.");
             }
-            unsigned char e = (unsigned char)re[i];
-            switch (e) {
-            case 'n': out.push_back('\n'); break;
-            case 't': out.push_back('\t'); break;
-            case 'r': out.push_back('\r'); break;
-            case 'f': out.push_back('\f'); break;
-            case 'a': out.push_back('\a'); break;
-            case 'e': out.push_back('\x1b'); break;
-            case 'x': {
-                int h1 = i + 1 < n ? hex(re[i + 1]) : -1;
-                int h2 = i + 2 < n ? hex(re[i + 2]) : -1;
-                if (h1 < 0 || h2 < 0) {
-                    throw CompileError{"Invalid hex escape; only \\xHH is accepted.", idx};
-                }
-                out.push_back((char)(h1 * 16 + h2));
-                i += 2;
+            pos += 2;
+            return (unsigned char)(h1 * 16 + h2);
+        }
+        default:
+            if (inClass && e == 'b') {
+                return 0x08; /* backspace inside a class */
+            }
+            if (isalnum(e)) {
+                needsRegex(std::string("Escape sequence \\") + (char)e);
+            }
+            return e; /* escaped punctuation */
+        }
+    }
+
+    unsigned char plain(unsigned char c) const {
+        if (c >= 0x80 && (flags & (HS_FLAG_UTF8 | HS_FLAG_UCP))) {
+            fail("Non-ASCII characters under HS_FLAG_UTF8/UCP are not supported by the literal "
+                 "compiler.");
+        }
+        return c;
+    }
+
+    /* "[...]": PCRE rules -- "]" first is literal, "-" is literal first, last or
+     * right after a range */
+    std::set<std::string> charClass() {
+        pos++; /* [ */
+        if (at('^')) {
+            needsRegex("Negated character class");
+        }
+        bool present[256] = {false};
+        bool first = true;
+        int prev = -1; /* last single character that may start a range */
+        for (;; first = false) {
+            if (pos >= n) {
+                fail("Unterminated character class.");
+            }
+            unsigned char c = (unsigned char)re[pos];
+            if (c == ']' && !first) {
+                pos++;
                 break;
             }
-            default:
-                if ((e >= 'a' && e <= 'z') || (e >= 'A' && e <= 'Z') || (e >= '0' && e <= '9')) {
-                    throw CompileError{std::string("Escape sequence \\") + (char)e +
-                                           " needs the regex back end; this build "
-                                           "compiles literal patterns only.", idx};
-                }
-                out.push_back((char)e); /* escaped punctuation */
+            if (c == '[' && pos + 1 < n && (re[pos + 1] == ':' || re[pos + 1] == '.' || re[pos + 1] == '=')) {
+                needsRegex("POSIX character class");
             }
-            continue;
+            int lo;
+            if (c == '-' && prev >= 0 && pos + 1 < n && re[pos + 1] != ']') {
+                /* range prev-hi */
+                pos++;
+                unsigned char hi;
+                if (re[pos] == '\\') {
+                    hi = escape(true);
+                } else {
+                    hi = plain((unsigned char)re[pos++]);
+                }
+                if (hi < prev) {
+                    fail("Invalid range in character class.");
+                }
+                for (int v = prev; v <= hi; v++) {
+                    present[v] = true;
+                }
+                prev = -1; /* a "-" right after a range is literal */
+                continue;
+            }
+            if (c == '\\') {
+                lo = escape(true);
+            } else {
+                lo = plain(c);
+                pos++;
+            }
+            present[lo] = true;
+            prev = lo;
         }
-        if (strchr(".^$*+?()[]{}|", c)) {
-            throw CompileError{std::string("Metacharacter '") + (char)c +
-                                   "' needs the regex back end; this build compiles "
-                                   "literal patterns only (escape it to match it "
-                                   "literally).", idx};
+        std::set<std::string> r;
+        for (int v = 0; v < 256; v++) {
+            if (present[v]) {
+                r.insert(std::string(1, (char)v));
+            }
         }
-        if (c >= 0x80 && (flags & (HS_FLAG_UTF8 | HS_FLAG_UCP))) {
-            throw CompileError{"Non-ASCII characters under HS_FLAG_UTF8/UCP are not "
-                               "supported by the literal compiler.", idx};
+        if (r.size() > MAX_CLASS) {
+            needsRegex("A character class of more than 64 characters");
         }
-        out.push_back((char)c);
+        return r;
     }
-    return out;
+
+    std::set<std::string> atom() {
+        const unsigned char c = (unsigned char)re[pos];
+        if (c == '(') {
+            pos++;
+            if (at('?')) {
+                if (pos + 1 < n && re[pos + 1] == ':') {
+                    pos += 2;
+                } else {
+                    needsRegex("Group option / assertion \"(?\"");
+                }
+            }
+            std::set<std::string> r = alt();
+            if (!at(')')) {
+                fail("Missing close parenthesis.");
+            }
+            pos++;
+            return r;
+        }
+        if (c == '[') {
+            return charClass();
+        }
+        if (c == '\\') {
+            return {std::string(1, (char)escape(false))};
+        }
+        if (strchr(".^$", c)) {
+            needsRegex(std::string("Metacharacter '") + (char)c + "'");
+        }
+        if (strchr("*+?{", c)) {
+            fail("Invalid repeat: nothing to repeat.");
+        }
+        pos++;
+        return {std::string(1, (char)plain(c))};
+    }
+};
+
+static std::vector<std::string> regexToLiterals(const char *re, unsigned flags, int idx) {
+    return FiniteRegex(re, flags, idx).expand();
 }
 
 static hs_error_t compileCommon(const char *const *expressions,
@@ -610,15 +844,26 @@ static hs_error_t compileCommon(const char *const *expressions,
                                        "back end; this build compiles literal patterns only.",
                                        (int)i};
                 }
-                p.s = regexToLiteral(expressions[i], f, (int)i);
-                if (p.s.empty()) {
-                    throw CompileError{(f & HS_FLAG_ALLOWEMPTY)
-                                           ? "Empty patterns need the regex back end "
-                                             "(boundary reports)."
-                                           : "Pattern matches empty buffer; use "
-                                             "HS_FLAG_ALLOWEMPTY to enable support.",
-                                       (int)i};
+                if (f & HS_FLAG_SOM_LEFTMOST) {
+                    throw CompileError{"HS_FLAG_SOM_LEFTMOST is not supported by the B200 "
+                                       "literal compiler yet.", (int)i};
                 }
+                /* one literal per string of the expression's (finite) language,
+                 * all under the expression's id */
+                const std::vector<std::string> lang = regexToLiterals(expressions[i], f, (int)i);
+                for (const std::string &str : lang) {
+                    if (str.empty()) {
+                        throw CompileError{(f & HS_FLAG_ALLOWEMPTY)
+                                               ? "Empty patterns need the regex back end "
+                                                 "(boundary reports)."
+                                               : "Pattern matches empty buffer; use "
+                                                 "HS_FLAG_ALLOWEMPTY to enable support.",
+                                           (int)i};
+                    }
+                    p.s = str;
+                    pats.push_back(p);
+                }
+                continue;
             }
             if (f & HS_FLAG_SOM_LEFTMOST) {
                 throw CompileError{"HS_FLAG_SOM_LEFTMOST is not supported by the B200 "
@@ -754,9 +999,11 @@ static hs_error_t exprInfo(const char *expression, unsigned flags, const hs_expr
             throw CompileError{"Extended parameters need the regex back end; this build compiles "
                                "literal patterns only.", 0};
         }
-        const std::string lit = regexToLiteral(expression, flags, 0);
-        if (lit.size() > LIMIT_PATTERN_LENGTH) {
-            throw CompileError{"Pattern length exceeds limit.", 0};
+        const std::vector<std::string> lang = regexToLiterals(expression, flags, 0);
+        size_t minW = lang.empty() ? 0 : lang[0].size(), maxW = 0;
+        for (const std::string &str : lang) {
+            minW = std::min(minW, str.size());
+            maxW = std::max(maxW, str.size());
         }
         hs_expr_info_t *out = (hs_expr_info_t *)g_misc_alloc(sizeof(*out));
         if (!out) {
@@ -764,7 +1011,8 @@ static hs_error_t exprInfo(const char *expression, unsigned flags, const hs_expr
             return HS_COMPILER_ERROR;
         }
         memset(out, 0, sizeof(*out));
-        out->min_width = out->max_width = (unsigned)lit.size();
+        out->min_width = (unsigned)minW;
+        out->max_width = (unsigned)maxW;
         *info = out;
         *error = nullptr;
         return HS_SUCCESS;

@@ -116,10 +116,13 @@ typedef int (*match_event_handler)(unsigned int id, unsigned long long from,
                                    void *context);
 
 /* --- compile (host CPU; src/hs_compile.h:360-854).  This build carries a
- * literal compiler: every expression must denote one literal string
- * (hs_compile_lit*: any bytes; hs_compile*: a regex that is a plain literal
- * after escape processing).  Anything else yields HS_COMPILER_ERROR with an
- * explanatory hs_compile_error_t, exactly as the reference reports
+ * literal compiler: hs_compile_lit* take any bytes; hs_compile* take a regex
+ * that denotes a FINITE set of strings -- literal text and PCRE escapes,
+ * groups, alternation, character classes without negation, the bounded
+ * repeats ?, {n}, {n,m} (at most 4096 strings per expression) -- each string
+ * becoming one literal under the expression's id.  Anything else (., *, +,
+ * anchors, look-around, back-references, ...) yields HS_COMPILER_ERROR with
+ * an explanatory hs_compile_error_t, exactly as the reference reports
  * unsupported constructs. */
 hs_error_t hs_compile(const char *expression, unsigned int flags,
                       unsigned int mode, const hs_platform_info_t *platform,

@@ -5,7 +5,10 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
+
+import oracle.port as port
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -190,3 +193,56 @@ def test_expression_info(hs):
     L.hs_free_compile_error(err)
     assert L.hs_expression_info(None, 0, C.byref(info), C.byref(err)) == hs.HS_COMPILER_ERROR
     L.hs_free_compile_error(err)
+
+
+FINITE = [
+    (rb"(foo){2,3}bar", 0), (rb"x?(foo){2,3}bar", 0), (rb"[fg]oo|ba[rz]", 0), (rb"abc|bc|c", 0),
+    (rb"a{3}", 0), (rb"a{3}", 1), (rb"(ab|ba){2}", 0), (rb"[a-c]{2}d", 1), (rb"(?:ab)?cd", 0),
+    (rb"[]a]b", 0), (rb"[a\-c]b", 0), (rb"[A-C-E]", 0), (rb"a[\x62\x63]", 0), (rb"((a|b)(c|d)){2}", 0),
+    (rb"ab{0,2}c", 0), (rb"(a|ab)(c|bcd)", 0),
+]
+
+
+@pytest.mark.parametrize("pat,caseless", [(p, c) for (p, c) in FINITE], ids=[p.decode() for (p, _) in FINITE])
+def test_finite_language_expressions(hs, ref, pat, caseless):
+    """hs_compile accepts expressions that denote a finite set of literals (groups,
+    alternation, classes, bounded repeats): every end offset where Python's re
+    (PCRE-compatible for these constructs) finds a match ending -- and no other --
+    is reported once by the reference runtime scanning our database."""
+    import re
+    rng = np.random.default_rng(len(pat))
+    data = bytes(rng.choice(np.frombuffer(b"abcdfoorzABC-]", dtype=np.uint8), size=700).tolist())
+    data += b"foofoobar xfoofoofoobar abccd ab]b a-b bab"
+    rx = re.compile(b"(?:" + pat + rb")\Z", re.I if caseless else 0)
+    want = [e for e in range(1, len(data) + 1) if rx.search(data[:e])]
+    db = hs.compile_multi([pat], flags=[hs.HS_FLAG_CASELESS if caseless else 0], ids=[9])
+    got = ref.scan_sorted(db.ptr, data, [0], [len(data)])
+    assert [int(r["to"]) for r in got] == want and all(int(r["id"]) == 9 for r in got)
+    b = port.scan_sorted(db.ptr, np.frombuffer(data, dtype=np.uint8), np.array([0], dtype=np.uint64),
+                         np.array([len(data)], dtype=np.uint32))
+    assert np.array_equal(b, got)
+
+
+def test_finite_language_limits_and_errors(hs):
+    for bad, why in [(rb"a*", "Unbounded"), (rb"a+b", "Unbounded"), (rb"a.b", "Metacharacter"),
+                     (rb"^ab", "Metacharacter"), (rb"ab$", "Metacharacter"), (rb"[^a]b", "Negated"),
+                     (rb"a{2,}", "Unbounded"), (rb"(?i)ab", "Group option"), (rb"a|", "empty buffer"),
+                     (rb"(ab", "parenthesis"), (rb"ab)", "parentheses"), (rb"\d+", "Escape sequence"),
+                     (rb"a??", "Lazy"), (rb"[[:alpha:]]", "POSIX"), (rb"[a-z]{4}", "4096"),
+                     (rb"a{3,2}", "min > max"), (rb"*a", "nothing to repeat"), (rb"[ab", "Unterminated")]:
+        with pytest.raises(hs.HsError) as e:
+            hs.compile_multi([b"ok", bad])
+        assert why in e.value.message, (bad, e.value.message)
+        assert e.value.expression == 1
+    # widths reported by hs_expression_info follow the language
+    class Info(C.Structure):
+        _fields_ = [("min_width", C.c_uint), ("max_width", C.c_uint), ("unordered_matches", C.c_char),
+                    ("matches_at_eod", C.c_char), ("matches_only_at_eod", C.c_char)]
+    L = hs.lib()
+    L.hs_expression_info.argtypes = [C.c_char_p, C.c_uint, C.POINTER(C.POINTER(Info)),
+                                     C.POINTER(C.POINTER(hs.CompileError))]
+    info = C.POINTER(Info)()
+    err = C.POINTER(hs.CompileError)()
+    assert L.hs_expression_info(rb"x?(foo){2,3}bar", 0, C.byref(info), C.byref(err)) == 0
+    assert (info.contents.min_width, info.contents.max_width) == (9, 13)
+    C.CDLL(None).free(info)

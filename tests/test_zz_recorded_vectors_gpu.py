@@ -1,0 +1,29 @@
+"""The reference's recorded hscollider vectors (tests/golden/hscollider_literals.json,
+tools/gen_hscollider_golden.py) through the CUDA path.  The CPU half (C oracle
+against the same fixture) is in tests/test_golden.py; this file sorts last on
+purpose: it is the widest sweep over compiler-accepted expressions (groups,
+alternation, classes, bounded repeats -> many literals under one id)."""
+import base64
+
+import numpy as np
+import pytest
+
+from test_golden import COLLIDER, _check_collider, _collider_blocks
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", COLLIDER, ids=[str(c["id"]) for c in COLLIDER])
+def test_cuda_path_reproduces_hscollider_vectors(hs, case):
+    db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+    data, off, ln, ends = _collider_blocks(case)
+    scratch = hs.Scratch(db)
+    got = np.sort(hs.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
+    _check_collider(case, got, ends)
+    # and one hs_scan per corpus, the way hscollider drives the engine
+    for c, want in zip(case["corpora"], ends):
+        tos = []
+        hs.scan(db, base64.b64decode(c["data"]), scratch, on_event=lambda i, frm, to, fl: tos.append(to) or 0)
+        if "H" in case["flag_letters"]:
+            assert (len(tos) == 1 and tos[0] in want) if want else not tos
+        else:
+            assert tos == want

@@ -2,8 +2,10 @@
 """Generate tests/golden/hscollider_literals.json from the reference's own
 recorded regression vectors (tools/hscollider/test_cases/{pcre,corpora}/*.txt).
 
-Only entries on this path are kept: patterns that are plain literals after
-escape processing with flags out of {i, s, m, H, O}, together with the corpora
+Only entries on this path are kept: patterns this library's hs_compile accepts
+(expressions that denote a finite set of literals: literal text, groups,
+alternation, character classes, bounded repeats) with flags out of
+{i, s, m, H, O}, together with the corpora
 lines that carry recorded match offsets (`id="data": to1,to2,...`, format per
 tools/hscollider/ColliderCorporaParser.rl:100-150; pattern flag letters per
 util/ExpressionParser.rl:60-85).  The pattern TEXT and the recorded offsets are
@@ -30,8 +32,6 @@ import oracle.ref as ref  # noqa: E402
 BASE = "/root/reference/tools/hscollider/test_cases"
 FLAG = {"i": capi.HS_FLAG_CASELESS, "s": 2, "m": 4, "H": capi.HS_FLAG_SINGLEMATCH, "O": 0}
 SPECIAL = {"0": 0, "a": 7, "e": 27, "f": 12, "n": 10, "v": 11, "r": 13, "t": 9}
-META = re.compile(rb"(?<!\\)[.^$*+?()\[\]{}|]")
-ESC_OK = re.compile(rb"(?:[^\\]|\\x[0-9a-fA-F]{2}|\\[^a-zA-Z0-9])*")
 
 
 def decode_corpus(s):
@@ -67,8 +67,15 @@ def main():
             if not m:
                 continue
             pid, pat, fl = int(m.group(1)), m.group(2), m.group(3).decode()
-            if META.search(pat) or not ESC_OK.fullmatch(pat) or set(fl) - set(FLAG):
+            if set(fl) - set(FLAG):
                 continue
+            flags = 0
+            for c in fl:
+                flags |= FLAG[c]
+            try:
+                capi.compile_multi([pat], [flags], [pid])
+            except capi.HsError:
+                continue  # needs the regex back end
             pats[pid] = (pat, fl, os.path.basename(f))
     cases = {}
     for f in sorted(glob.glob(BASE + "/corpora/*.txt")):
