@@ -11,8 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# HSB200_LIB: A/B runs of tools/sweep.py against another build of the same ABI
-LIB_PATH = os.environ.get("HSB200_LIB") or os.path.join(_HERE, "lib", "libhs_b200.so")
+LIB_PATH = os.path.join(_HERE, "lib", "libhs_b200.so")
 
 HS_SUCCESS = 0
 HS_INVALID = -1

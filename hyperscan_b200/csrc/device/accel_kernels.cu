@@ -32,9 +32,13 @@ namespace {
 /* PRMT in its default mode: selector nibble bit 3 replicates the selected
  * byte's sign bit (the __byte_perm intrinsic only honours bits 2:0). */
 __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {
+#ifdef HSB_HOST_EMU /* SIMT emulator of tests/emu (test infrastructure) */
+    return hsb_emu_prmt(a, b, sel);
+#else
     u32 d;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
     return d;
+#endif
 }
 
 /* 16-entry x 8-bit table lookup for the four nibble indices packed one per
@@ -64,9 +68,16 @@ __global__ void __launch_bounds__(256) accelFindKernel(AccelParams p, const u8 *
                                                        unsigned long long *result) {
     const u64 chunks = (len + 15) / 16;
     for (u64 ch = (u64)blockIdx.x * blockDim.x + threadIdx.x;; ch += (u64)gridDim.x * blockDim.x) {
-        /* whole warps leave together (ballot below) */
+        /* whole warps leave together (ballot below): one lane reads the best
+         * position found so far and broadcasts it, so that every lane of the
+         * warp takes the same decision whatever the other warps publish meanwhile */
         const u64 warpFirst = ch - (threadIdx.x & 31);
-        if (warpFirst >= chunks || warpFirst * 16 >= *(volatile unsigned long long *)result) {
+        u64 best = 0;
+        if ((threadIdx.x & 31) == 0) {
+            best = *(volatile unsigned long long *)result;
+        }
+        best = __shfl_sync(0xffffffffu, best, 0);
+        if (warpFirst >= chunks || warpFirst * 16 >= best) {
             return;
         }
         u32 w[5] = {0, 0, 0, 0, 0};
@@ -192,7 +203,7 @@ cudaError_t launchAccelFind(int type, const u8 *params, const u8 *d_buf, u64 len
     const u64 chunks = (len + 15) / 16;
     const u64 blocks = (chunks + 255) / 256;
     const int grid = (int)(blocks < (u64)sms * 8 ? blocks : (u64)sms * 8);
-    accelFindKernel<<<grid, 256, 0, stream>>>(p, d_buf, len, (unsigned long long *)d_result);
+    HSB_LAUNCH(accelFindKernel, grid, 256, 0, stream, p, d_buf, len, (unsigned long long *)d_result);
     return cudaGetLastError();
 }
 

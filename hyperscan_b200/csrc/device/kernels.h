@@ -9,6 +9,22 @@
 
 #include "../ref_layout.h"
 
+/* Kernel launches and the dynamic shared-memory window are spelled through two
+ * macros so that the same sources also compile as plain C++ for the SIMT
+ * emulator of tests/emu (TEST infrastructure, -DHSB_HOST_EMU: kernel logic under
+ * `pytest -m "not gpu"`).  In the product build they are exactly the CUDA forms;
+ * libhs_b200.so contains no emulator and has no CPU scan path. */
+#ifdef HSB_HOST_EMU
+#define HSB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    hsb_emu::launch(dim3(grid), dim3(block), smem, [=]() { kern(__VA_ARGS__); })
+#define HSB_DYNAMIC_SMEM(name) u8 *name = hsb_emu::dynamicSmem()
+#define HSB_NOINLINE __attribute__((noinline))
+#else
+#define HSB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define HSB_DYNAMIC_SMEM(name) extern __shared__ __align__(128) u8 name[]
+#define HSB_NOINLINE __noinline__
+#endif
+
 namespace hsb {
 
 /* One match record as the device writes it: identical to hs_b200_match_t

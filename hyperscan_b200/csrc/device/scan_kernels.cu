@@ -41,8 +41,32 @@ namespace hsb {
 
 namespace {
 
-/* ---- PTX wrappers: mbarrier + 1-D TMA bulk copy ------------------------- */
-
+/* ---- PTX wrappers: mbarrier + 1-D TMA bulk copy, shared-memory access, streaming
+ * loads.  The HSB_HOST_EMU forms belong to the SIMT emulator of tests/emu (test
+ * infrastructure): shared-memory "addresses" are offsets into the block's window
+ * and a bulk copy completes at once. */
+#ifdef HSB_HOST_EMU
+__device__ __forceinline__ u32 smemAddr(const void *p) {
+    return (u32)((const u8 *)p - hsb_emu::dynamicSmem());
+}
+/* the barrier word counts completed phases; try_wait.parity(P) succeeds once the
+ * barrier's current phase differs from P */
+__device__ __forceinline__ void mbarInit(u64 *bar, u32) { *bar = 0; }
+__device__ __forceinline__ void mbarExpectTx(u64 *, u32) {}
+__device__ __forceinline__ void tmaLoad1d(void *dst, const void *src, u32 bytes, u64 *bar) {
+    memcpy(dst, src, bytes);
+    (*bar)++;
+    hsb_emu::noteProgress();
+}
+__device__ __forceinline__ void mbarWait(u64 *bar, u32 parity) {
+    while (((u32)*(volatile u64 *)bar & 1) == parity) {
+        hsb_emu::yieldThread();
+    }
+}
+__device__ __forceinline__ void fenceMbarInit() {}
+__device__ __forceinline__ uint4 ldCs128(const u8 *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void prefetchL2(const void *) {}
+#else
 __device__ __forceinline__ u32 smemAddr(const void *p) {
     return (u32)__cvta_generic_to_shared(p);
 }
@@ -73,6 +97,22 @@ __device__ __forceinline__ void mbarWait(u64 *bar, u32 parity) {
             : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void fenceMbarInit() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+/* volatile: keeps the load where it is written (ptxas otherwise sinks it next to
+ * its first use and the prefetch is lost) */
+__device__ __forceinline__ uint4 ldCs128(const u8 *p) {
+    uint4 r;
+    asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void prefetchL2(const void *p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+#endif
 
 /* ---- read-only loads of the database image ------------------------------- */
 
@@ -432,6 +472,32 @@ template <int KIND> struct Kind {
     static constexpr bool HASH = KIND == FK_HASH32 || KIND == FK_HASH64;
 };
 
+#ifdef HSB_HOST_EMU
+__device__ __forceinline__ u32 lds32(u32 addr) {
+    u32 v;
+    memcpy(&v, hsb_emu::dynamicSmem() + addr, 4);
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(u32 addr) {
+    uint2 v;
+    memcpy(&v, hsb_emu::dynamicSmem() + addr, 8);
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(u32 addr) {
+    uint4 v;
+    memcpy(&v, hsb_emu::dynamicSmem() + addr, 16);
+    return v;
+}
+__device__ __forceinline__ void sts128(u32 addr, u32 x, u32 y, u32 z, u32 w) {
+    const u32 v[4] = {x, y, z, w};
+    memcpy(hsb_emu::dynamicSmem() + addr, v, 16);
+}
+__device__ __forceinline__ void sts64(u32 addr, u32 x, u32 y) {
+    const u32 v[2] = {x, y};
+    memcpy(hsb_emu::dynamicSmem() + addr, v, 8);
+}
+__device__ __forceinline__ void sts32(u32 addr, u32 x) { memcpy(hsb_emu::dynamicSmem() + addr, &x, 4); }
+#else
 __device__ __forceinline__ u32 lds32(u32 addr) {
     u32 v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -442,7 +508,6 @@ __device__ __forceinline__ uint2 lds64(u32 addr) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
-
 __device__ __forceinline__ uint4 lds128(u32 addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -454,9 +519,13 @@ __device__ __forceinline__ void sts128(u32 addr, u32 x, u32 y, u32 z, u32 w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w)
                  : "memory");
 }
+__device__ __forceinline__ void sts64(u32 addr, u32 x, u32 y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void sts32(u32 addr, u32 x) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
 }
+#endif
 
 /* OR the 128-bit stream E[0..3] (one entry per word of the lane, all at the
  * same in-word position) into a[] at byte offset O (0..4): one funnel shift
@@ -594,7 +663,7 @@ __device__ __forceinline__ u64 confValAt(const ScanParams &p, u64 g) {
  * keyBytes bytes into the prefilter bitmap (shared memory); only survivors pay
  * for the hash confirm in HBM/L2. */
 template <int NOCT>
-__device__ __noinline__ void laneCandidates(const ScanParams &p, u32 bitmapAddr, u32 c00, u32 c01,
+__device__ HSB_NOINLINE void laneCandidates(const ScanParams &p, u32 bitmapAddr, u32 c00, u32 c01,
                                             u32 c02, u32 c03, u32 c10, u32 c11, u32 c12, u32 c13,
                                             u32 w0, u32 w1, u32 w2, u32 w3, u32 pw, u64 g0,
                                             u32 *stats) {
@@ -673,7 +742,7 @@ template <int NOCT> struct QueueEntry {
 };
 
 template <int NOCT>
-__device__ __noinline__ void drainQueue(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
+__device__ HSB_NOINLINE void drainQueue(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
                                         u32 count, u32 lane, u32 *stats) {
     if (lane >= count) {
         return;
@@ -803,7 +872,7 @@ __device__ __forceinline__ void haloStep(const ScanParams &p, const uint4 v, u32
 template <int KIND, int STRIDE, int SB, int DIRECT, int QUEUED>
 __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanParams p) {
     static_assert(!QUEUED || DIRECT, "the candidate queue reads chunks back from the corpus (direct mode)");
-    extern __shared__ __align__(128) u8 smem[];
+    HSB_DYNAMIC_SMEM(smem);
     typedef Kind<KIND> K;
     const u32 lane = threadIdx.x & 31;
     const u32 warp = threadIdx.x >> 5;
@@ -845,7 +914,7 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
         }
     }
     if (!DIRECT) {
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fenceMbarInit();
     }
     __syncthreads();
 
@@ -882,18 +951,12 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
         const u8 *ptr = p.corpus + runStart + lane * 16; /* this lane's 16 bytes of the current step */
         const u8 *const endPtr = p.corpus + p.readableEnd;
         if (QUEUED && lane == 0) {
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(wq.addr + QueueEntry<K::NOCT>::RUN_START),
-                         "r"((u32)runStart), "r"((u32)(runStart >> 32))
-                         : "memory");
+            sts64(wq.addr + QueueEntry<K::NOCT>::RUN_START, (u32)runStart, (u32)(runStart >> 32));
         }
         auto load = [&](const u8 *q, bool guard) -> uint4 {
             uint4 r = make_uint4(0, 0, 0, 0);
             if (!guard || q + 16 <= endPtr) {
-                /* volatile: keeps the load where it is written (ptxas otherwise
-                 * sinks it next to its first use and the prefetch is lost) */
-                asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                             : "l"(q));
+                r = ldCs128(q);
             }
             return r;
         };
@@ -914,7 +977,7 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
             if ((step & 3) == 0 && (lane & 1) == 0) {
                 const u8 *pf = ptr + pfBytes;
                 if (pf < endPtr) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+                    prefetchL2(pf);
                 }
             }
             u32 w4 = 0;
@@ -961,11 +1024,7 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
             const u64 pos = lanePos + (u64)step * 512;
             uint4 r = make_uint4(0, 0, 0, 0);
             if (pos + 16 <= p.readableEnd) {
-                /* volatile: keeps the load where it is written (ptxas otherwise
-                 * sinks it next to its first use and the prefetch is lost) */
-                asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                             : "l"(base + (size_t)step * 512));
+                r = ldCs128(base + (size_t)step * 512);
             }
             return r;
         };
@@ -985,7 +1044,7 @@ __global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanP
             if ((lane & 7) == 0) {
                 const u64 pos = lanePos + (u64)(step + pfDist) * 512;
                 if (pos < p.readableEnd) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.corpus + pos));
+                    prefetchL2(p.corpus + pos);
                 }
             }
             u32 w4 = 0;
@@ -1140,7 +1199,7 @@ __device__ __forceinline__ void laneFilterWide(const u32 (&w)[9], u32 tabAddr, u
     }
 }
 
-__device__ __noinline__ void drainWide(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first, u32 count,
+__device__ HSB_NOINLINE void drainWide(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first, u32 count,
                                        u32 lane, u32 *stats) {
     if (lane >= count) {
         return;
@@ -1171,7 +1230,7 @@ __device__ __noinline__ void drainWide(const ScanParams &p, u32 bitmapAddr, u32 
 template <int KIND, int SB>
 __global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
     static_assert(KIND == FK_BYTE32 || KIND == FK_HASH32, "wide steps: 8-bucket tables only");
-    extern __shared__ __align__(128) u8 smem[];
+    HSB_DYNAMIC_SMEM(smem);
     const u32 lane = threadIdx.x & 31;
     const u32 warp = threadIdx.x >> 5;
     const u32 nwarps = blockDim.x >> 5;
@@ -1223,9 +1282,7 @@ __global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
     const u8 *base = p.corpus + runStart + lane * 32;
     const u64 lanePos = runStart + lane * 32;
     if (lane == 0) {
-        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(qAddr + WideQueue::RUN_START), "r"((u32)runStart),
-                     "r"((u32)(runStart >> 32))
-                     : "memory");
+        sts64(qAddr + WideQueue::RUN_START, (u32)runStart, (u32)(runStart >> 32));
     }
 
     u32 carry[2][2] = {{0, 0}, {0, 0}};
@@ -1238,16 +1295,10 @@ __global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
         hi = make_uint4(0, 0, 0, 0);
         const u8 *q0 = base + (size_t)it * 1024;
         if (pos + 32 <= p.readableEnd) {
-            asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w)
-                         : "l"(q0));
-            asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
-                         : "l"(q0 + 16));
+            lo = ldCs128(q0);
+            hi = ldCs128(q0 + 16);
         } else if (pos + 16 <= p.readableEnd) {
-            asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w)
-                         : "l"(q0));
+            lo = ldCs128(q0);
         }
     };
     const u32 pfDist = p.nstages; /* L2 prefetch distance in 1 KiB iterations */
@@ -1265,7 +1316,7 @@ __global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
         if ((lane & 3) == 0) {
             const u64 pos = lanePos + (u64)(it + pfDist) * 1024;
             if (pos < p.readableEnd) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.corpus + pos));
+                prefetchL2(p.corpus + pos);
             }
         }
         u32 w8 = 0;
@@ -1324,24 +1375,23 @@ __global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
 
 template <int KIND, int SB>
 cudaError_t launchWide(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(scanKernelWide<KIND, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)cfg.smemBytes);
+    void (*kern)(const ScanParams) = scanKernelWide<KIND, SB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smemBytes);
     if (e != cudaSuccess) {
         return e;
     }
-    scanKernelWide<KIND, SB><<<cfg.grid, cfg.warps * 32, cfg.smemBytes, stream>>>(p);
+    HSB_LAUNCH(kern, cfg.grid, cfg.warps * 32, cfg.smemBytes, stream, p);
     return cudaGetLastError();
 }
 
 template <int KIND, int STRIDE, int SB, int DIRECT, int QUEUED>
 cudaError_t launchOne(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(scanKernel<KIND, STRIDE, SB, DIRECT, QUEUED>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)cfg.smemBytes);
+    void (*kern)(const ScanParams) = scanKernel<KIND, STRIDE, SB, DIRECT, QUEUED>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smemBytes);
     if (e != cudaSuccess) {
         return e;
     }
-    scanKernel<KIND, STRIDE, SB, DIRECT, QUEUED><<<cfg.grid, cfg.warps * 32, cfg.smemBytes, stream>>>(p);
+    HSB_LAUNCH(kern, cfg.grid, cfg.warps * 32, cfg.smemBytes, stream, p);
     return cudaGetLastError();
 }
 
@@ -1444,7 +1494,7 @@ __global__ void streamAdvanceKernel(const u8 *corpus, u8 *hist, u64 *offsets, co
 
 cudaError_t launchStreamAssemble(u8 *corpus, const u8 *hist, u32 nstreams, u32 pitch, cudaStream_t stream) {
     if (nstreams) {
-        streamAssembleKernel<<<(nstreams + 255) / 256, 256, 0, stream>>>(corpus, hist, nstreams, pitch);
+        HSB_LAUNCH(streamAssembleKernel, (nstreams + 255) / 256, 256, 0, stream, corpus, hist, nstreams, pitch);
     }
     return cudaGetLastError();
 }
@@ -1452,14 +1502,14 @@ cudaError_t launchStreamAssemble(u8 *corpus, const u8 *hist, u32 nstreams, u32 p
 cudaError_t launchStreamAdvance(const u8 *corpus, u8 *hist, u64 *offsets, const u32 *lens, u32 uniformLen,
                                 u32 nstreams, u32 pitch, u32 histReq, cudaStream_t stream) {
     if (nstreams) {
-        streamAdvanceKernel<<<(nstreams + 255) / 256, 256, 0, stream>>>(corpus, hist, offsets, lens, uniformLen,
-                                                                       nstreams, pitch, histReq);
+        HSB_LAUNCH(streamAdvanceKernel, (nstreams + 255) / 256, 256, 0, stream, corpus, hist, offsets, lens,
+                   uniformLen, nstreams, pitch, histReq);
     }
     return cudaGetLastError();
 }
 
 cudaError_t launchPublishCount(const ScanParams &p, cudaStream_t stream) {
-    publishCountKernel<<<1, 32, 0, stream>>>(p);
+    HSB_LAUNCH(publishCountKernel, 1, 32, 0, stream, p);
     return cudaGetLastError();
 }
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("direct", [1, 0])
-def test_wrap_exact_device_buffer(hs, ref, direct):
+def test_wrap_exact_device_buffer(hs, ref, direct, real_gpu):
     torch = pytest.importorskip("torch")
     lits, flags, ids = synth.literal_set(300, min_len=2, max_len=10, seed=12, alphabet=b"abcdef")
     db = hs.compile_lit_multi(lits, flags, ids)

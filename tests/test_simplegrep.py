@@ -34,7 +34,7 @@ def test_header_is_c99_and_example_links(tmp_path, hs):
 
 
 @pytest.mark.gpu
-def test_simplegrep_config1(tmp_path, hs, ref):
+def test_simplegrep_config1(tmp_path, hs, ref, real_gpu):
     exe = build_example(tmp_path, hs)
     rng = np.random.default_rng(1)
     data = rng.integers(0x20, 0x7F, size=1 << 20, dtype=np.uint8)

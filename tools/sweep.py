@@ -32,7 +32,10 @@ def main():
     ap.add_argument("--configs", default=DEFAULT)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--alphabet", default="")
+    ap.add_argument("--lib", default="", help="A/B: another build of libhs_b200.so (same ABI)")
     args = ap.parse_args()
+    if args.lib:
+        capi.LIB_PATH = os.path.abspath(args.lib)
     lits, flags, ids = synth.literal_set(args.lits, min_len=args.min_len, max_len=args.max_len)
     nblocks = (args.mb << 20) // args.block_len
     data, off, ln, _ = synth.block_corpus(nblocks, args.block_len, lits, plant_per_kb=0.01)
@@ -56,7 +59,7 @@ def main():
             try:
                 capi.set_runtime_option(k, v)
             except capi.HsError:
-                pass  # an older build of the library (HSB200_LIB) without this option
+                pass  # an older build of the library (--lib) without this option
         scratch = capi.Scratch(db)
         ms = []
         try:
