@@ -60,3 +60,9 @@ def _reset_build_options():
             capi.set_build_option("reset", 0)
     except Exception:
         pass
+
+
+@pytest.fixture
+def emu_only():
+    if not EMU:
+        pytest.skip("single-process stand-in for a multi-GPU path: runs on the SIMT emulator only")

@@ -86,8 +86,16 @@ static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cuda
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaErrorNotSupported; }
+/* "peer" buffers live in this process: the handle carries the pointer */
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+    memset(h, 0, sizeof(*h));
+    memcpy(h->reserved, &p, sizeof(p));
+    return cudaSuccess;
+}
+static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+    memcpy(p, h.reserved, sizeof(*p));
+    return cudaSuccess;
+}
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 
 #endif
