@@ -115,6 +115,9 @@ def lib():
         L.hs_open_stream.argtypes = [vp, C.c_uint, C.POINTER(vp)]
         L.hs_scan_stream.argtypes = [vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
         L.hs_scan_vector.argtypes = [vp, vp, vp, C.c_uint, C.c_uint, vp, MATCH_CB, vp]
+        L.hs_compress_stream.argtypes = [vp, cp, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.hs_expand_stream.argtypes = [vp, C.POINTER(vp), cp, C.c_size_t]
+        L.hs_reset_and_expand_stream.argtypes = [vp, cp, C.c_size_t, vp, MATCH_CB, vp]
         L.hs_close_stream.argtypes = [vp, vp, MATCH_CB, vp]
         L.hs_reset_stream.argtypes = [vp, C.c_uint, vp, MATCH_CB, vp]
         L.hs_copy_stream.argtypes = [C.POINTER(vp), vp]
@@ -444,6 +447,25 @@ class Stream:
         p = C.c_void_p()
         _check(lib().hs_copy_stream(C.byref(p), self.ptr), "hs_copy_stream")
         return Stream(self.db, p)
+
+    def compress(self):
+        """hs_compress_stream: size query with a NULL buffer, then the bytes."""
+        used = C.c_size_t()
+        rc = lib().hs_compress_stream(self.ptr, None, 0, C.byref(used))
+        if rc != HS_INSUFFICIENT_SPACE:
+            raise HsError(rc, "hs_compress_stream size query")
+        buf = C.create_string_buffer(used.value)
+        _check(lib().hs_compress_stream(self.ptr, buf, used.value, C.byref(used)), "hs_compress_stream")
+        return buf.raw[:used.value]
+
+    @staticmethod
+    def expand(db, blob):
+        p = C.c_void_p()
+        _check(lib().hs_expand_stream(db.ptr, C.byref(p), blob, len(blob)), "hs_expand_stream")
+        return Stream(db, p)
+
+    def reset_and_expand(self, blob, scratch):
+        return lib().hs_reset_and_expand_stream(self.ptr, blob, len(blob), scratch.ptr, MATCH_CB(), None)
 
     def reset(self, scratch):
         _check(lib().hs_reset_stream(self.ptr, 0, scratch.ptr, MATCH_CB(), None))

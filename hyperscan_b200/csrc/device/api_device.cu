@@ -2028,6 +2028,118 @@ hs_error_t hs_reset_and_copy_stream(hs_stream_t *to_id, const hs_stream_t *from_
     return HS_SUCCESS;
 }
 
+/* ---- stream compression (src/runtime.c:1177-1282, src/stream_compress_impl.h) ------
+ * Flat form of a hs_stream: header {magic, database crc, status, look-behind
+ * length, number of single-match ids already raised, stream offset}, the
+ * look-behind bytes, the ids. */
+
+namespace {
+const u32 COMPRESS_MAGIC = 0x504d4353; /* "SCMP" */
+struct CompressedHeader {
+    u32 magic, crc, status, hlen, nseen, reserved;
+    u64 offset;
+};
+
+size_t compressedSize(const hs_stream *st) {
+    return sizeof(CompressedHeader) + st->hlen + 4 * st->seen->size();
+}
+
+/* fills *st (whose db, hreq and seen set are already in place) from buf */
+bool expandInto(hs_stream *st, const char *buf, size_t size) {
+    CompressedHeader h;
+    if (size < sizeof(h)) {
+        return false;
+    }
+    memcpy(&h, buf, sizeof(h));
+    const DbHeader *dh = (const DbHeader *)st->db;
+    if (h.magic != COMPRESS_MAGIC || h.crc != dh->crc32 || h.hlen > st->hreq || h.hlen > sizeof(st->hist) ||
+        h.status > 3 || size != sizeof(h) + h.hlen + 4ull * h.nseen) {
+        return false;
+    }
+    st->offset = h.offset;
+    st->hlen = h.hlen;
+    st->status = (u8)h.status;
+    memcpy(st->hist, buf + sizeof(h), h.hlen);
+    st->seen->clear();
+    for (u32 i = 0; i < h.nseen; i++) {
+        u32 id;
+        memcpy(&id, buf + sizeof(h) + h.hlen + 4ull * i, 4);
+        st->seen->insert(id);
+    }
+    return true;
+}
+} // namespace
+
+hs_error_t hs_compress_stream(const hs_stream_t *st, char *buf, size_t buf_space, size_t *used_space) {
+    if (!validStream(st) || !used_space || (buf_space && !buf)) {
+        return HS_INVALID;
+    }
+    const size_t need = compressedSize(st);
+    *used_space = need;
+    if (buf_space < need) {
+        return HS_INSUFFICIENT_SPACE;
+    }
+    CompressedHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = COMPRESS_MAGIC;
+    h.crc = ((const DbHeader *)st->db)->crc32;
+    h.status = st->status;
+    h.hlen = st->hlen;
+    h.nseen = (u32)st->seen->size();
+    h.offset = st->offset;
+    memcpy(buf, &h, sizeof(h));
+    memcpy(buf + sizeof(h), st->hist, st->hlen);
+    size_t pos = sizeof(h) + st->hlen;
+    std::vector<u32> ids(st->seen->begin(), st->seen->end());
+    std::sort(ids.begin(), ids.end()); /* equal states compress to equal bytes */
+    for (u32 id : ids) {
+        memcpy(buf + pos, &id, 4);
+        pos += 4;
+    }
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_expand_stream(const hs_database_t *db, hs_stream_t **stream, const char *buf, size_t buf_size) {
+    if (!stream || !buf) {
+        return HS_INVALID;
+    }
+    *stream = nullptr;
+    hs_stream_t *st = nullptr;
+    hs_error_t err = hs_open_stream(db, 0, &st); /* same checks: validity, alignment, mode, engine */
+    if (err != HS_SUCCESS) {
+        return err;
+    }
+    if (!expandInto(st, buf, buf_size)) {
+        hs_close_stream(st, nullptr, nullptr, nullptr);
+        return HS_INVALID;
+    }
+    *stream = st;
+    return HS_SUCCESS;
+}
+
+hs_error_t hs_reset_and_expand_stream(hs_stream_t *to_stream, const char *buf, size_t buf_size,
+                                      hs_scratch_t *scratch, match_event_handler onEvent, void *context) {
+    (void)context;
+    if (!validStream(to_stream) || !buf) {
+        return HS_INVALID;
+    }
+    if (onEvent && (!scratch || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC)) {
+        return HS_INVALID; /* pure-literal databases have no end-of-data reports to deliver */
+    }
+    /* expand into a copy first: a bad buffer must leave the stream as it was */
+    hs_stream tmp = *to_stream;
+    std::unordered_set<u32> seen;
+    tmp.seen = &seen;
+    if (!expandInto(&tmp, buf, buf_size)) {
+        return HS_INVALID;
+    }
+    std::unordered_set<u32> *keep = to_stream->seen;
+    *keep = seen;
+    *to_stream = tmp;
+    to_stream->seen = keep;
+    return HS_SUCCESS;
+}
+
 /* ---- stream sets: many streams, one write each per call, state resident in HBM ------
  * (BASELINE config 4 shape: 16 M x 1 KB streams).  Per stream 16 bytes live in
  * HBM: 7 look-behind bytes + their count, and the 64-bit stream offset.  A scan

@@ -200,7 +200,7 @@ hs_error_t hs_scan(const hs_database_t *db, const char *data,
 /* --- streaming mode (src/hs_runtime.h:148-475; src/runtime.c:542-977).  Built
  * for literal databases compiled with HS_MODE_STREAM (literals up to 8 bytes:
  * the pure-literal streaming runtime of the reference, src/runtime.c:801-829).
- * Stream compression (hs_compress_stream / hs_expand_stream) is not built. */
+ */
 struct hs_stream;
 typedef struct hs_stream hs_stream_t;       /* src/hs_runtime.h:54 */
 hs_error_t hs_open_stream(const hs_database_t *db, unsigned int flags, hs_stream_t **stream);
@@ -215,6 +215,20 @@ hs_error_t hs_copy_stream(hs_stream_t **to_id, const hs_stream_t *from_id);
 hs_error_t hs_reset_and_copy_stream(hs_stream_t *to_id, const hs_stream_t *from_id,
                                     hs_scratch_t *scratch, match_event_handler onEvent,
                                     void *context);
+
+/* Stream compression (src/hs_runtime.h:365-366, 395-397, 438-443;
+ * src/runtime.c:1177-1282): a stream's state as a flat byte string.  The
+ * format is private to a build, as in the reference; what is promised is the
+ * round trip: a stream expanded from the bytes continues exactly as the
+ * compressed one would have.  hs_compress_stream with too small a buffer
+ * (NULL/0 allowed) returns HS_INSUFFICIENT_SPACE and the size needed. */
+hs_error_t hs_compress_stream(const hs_stream_t *stream, char *buf, size_t buf_space,
+                              size_t *used_space);
+hs_error_t hs_expand_stream(const hs_database_t *db, hs_stream_t **stream, const char *buf,
+                            size_t buf_size);
+hs_error_t hs_reset_and_expand_stream(hs_stream_t *to_stream, const char *buf, size_t buf_size,
+                                      hs_scratch_t *scratch, match_event_handler onEvent,
+                                      void *context);
 
 /* --- vectored mode (src/hs_runtime.h:484-527; src/runtime.c:1106-1175): the
  * `count` buffers are scanned as ONE stream in the order given -- matches may

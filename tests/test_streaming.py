@@ -175,3 +175,49 @@ def test_stream_set_rejects_what_it_cannot_do(hs):
     with pytest.raises(hs.HsError) as e:
         hs.StreamSet(single, 4)
     assert e.value.code == hs.HS_ARCH_ERROR
+
+
+@pytest.mark.gpu
+def test_stream_compress_expand_round_trip(hs, ref):
+    """hs_compress_stream / hs_expand_stream / hs_reset_and_expand_stream
+    (src/runtime.c:1177-1282): a stream expanded from the bytes continues exactly
+    as the compressed one; the whole run equals the reference's uninterrupted stream."""
+    lits, flags, ids, db, data, off, ln = make(hs, 40, 123)
+    scratch = hs.Scratch(db)
+    st = hs.Stream(db)
+    rc, a = st.scan(data[:2500], scratch)
+    assert rc == 0
+    blob = st.compress()
+    assert len(blob) >= 32 and st.compress() == blob                  # deterministic
+    L = hs.lib()
+    used = C.c_size_t()
+    small = C.create_string_buffer(8)
+    assert L.hs_compress_stream(st.ptr, small, 8, C.byref(used)) == hs.HS_INSUFFICIENT_SPACE
+    assert used.value == len(blob)
+    assert L.hs_compress_stream(st.ptr, None, 8, C.byref(used)) == hs.HS_INVALID
+    twin = hs.Stream.expand(db, blob)
+    rc, b1 = st.scan(data[2500:6000], scratch)
+    rc, b2 = twin.scan(data[2500:6000], scratch)
+    assert b1 == b2 and len(b1) > 0
+    want, _ = ref.stream_collect(db.ptr, data[:6000], np.array([2500, 3500], dtype=np.uint32))
+    assert sorted(a + b1) == sorted((int(r["id"]), int(r["to"])) for r in want)
+    # reset_and_expand rewinds an existing stream to the compressed point
+    assert twin.reset_and_expand(blob, scratch) == 0
+    rc, b3 = twin.scan(data[2500:6000], scratch)
+    assert b3 == b1
+    # a damaged buffer is refused and leaves the stream untouched
+    bad = bytearray(blob)
+    bad[0] ^= 0xff
+    assert twin.reset_and_expand(bytes(bad), scratch) == hs.HS_INVALID
+    assert twin.reset_and_expand(blob[:-1], scratch) == hs.HS_INVALID
+    p = C.c_void_p()
+    assert L.hs_expand_stream(db.ptr, C.byref(p), bytes(bad), len(bad)) == hs.HS_INVALID
+    other = hs.compile_lit_multi([b"zz"], mode=hs.HS_MODE_STREAM)       # another database's stream bytes
+    assert L.hs_expand_stream(other.ptr, C.byref(p), blob, len(blob)) == hs.HS_INVALID
+    blk = hs.compile_lit_multi([b"zz"])
+    assert L.hs_expand_stream(blk.ptr, C.byref(p), blob, len(blob)) == hs.HS_DB_MODE_ERROR
+    rc, b4 = twin.scan(data[6000:7000], scratch)
+    rc, b5 = st.scan(data[6000:7000], scratch)
+    assert b4 == b5
+    st.close(scratch)
+    twin.close(scratch)
