@@ -60,6 +60,8 @@ struct RuntimeOpts {
                               * FDR hash table, whose kernel is shared-memory bound either way */
     int wide = 0;            /* 1: wide-step kernel (32-byte lanes, always queued) for FK_BYTE32 / FK_HASH32;
                               * built at the end of round 1, not yet measured */
+    int split = 0;           /* 1 (with wide): scan kernel stops at the prefilter, confirmKernel finishes the
+                              * candidates from a list in HBM (second half of the record ring) */
     int firstStage = 1;      /* FDR databases: 1 = two-byte hash table (FK_HASH32), 2 = per-byte table
                               * (FK_BYTE32, conflict-free lookups, more candidates), 0 = choose by the
                               * modelled candidate rate of the per-byte table */
@@ -82,7 +84,8 @@ void initOpts() {
         {"HSB200_REBUILD", &g_opts.rebuild},   {"HSB200_DOMAIN", &g_opts.domain},
         {"HSB200_DIRECT", &g_opts.direct},     {"HSB200_REPLICAS", &g_opts.replicas},
         {"HSB200_PF_DIST", &g_opts.pfDist},    {"HSB200_QUEUE", &g_opts.queue},
-        {"HSB200_FIRST_STAGE", &g_opts.firstStage}, {"HSB200_WIDE", &g_opts.wide}};
+        {"HSB200_FIRST_STAGE", &g_opts.firstStage}, {"HSB200_WIDE", &g_opts.wide},
+        {"HSB200_SPLIT", &g_opts.split}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -511,6 +514,7 @@ struct hs_scratch {
     std::vector<DevImage *> *images;
     DevMatch *d_out;
     u32 outCap;
+    bool ringSplit;          /* d_out holds 2 * outCap records: ring + candidate list (split mode) */
     u32 *d_counters;
     u32 *h_counters;         /* pinned */
     hs_b200_corpus *inlineCorpus; /* staging for hs_scan / hs_b200_scan_blocks */
@@ -589,14 +593,18 @@ hs_error_t findImage(hs_scratch *s, const hs_database_t *db, const DevImage **ou
 }
 
 hs_error_t growRing(hs_scratch *s, u32 cap) {
-    if (cap <= s->outCap) {
+    initOpts();
+    const bool split = g_opts.split != 0;
+    if (cap <= s->outCap && (s->ringSplit || !split)) {
         return HS_SUCCESS;
     }
+    cap = std::max(cap, s->outCap);
     DevMatch *n = nullptr;
-    CUDA_TRY(cudaMalloc(&n, (size_t)cap * sizeof(DevMatch)));
+    CUDA_TRY(cudaMalloc(&n, (size_t)cap * sizeof(DevMatch) * (split ? 2 : 1)));
     cudaFree(s->d_out);
     s->d_out = n;
     s->outCap = cap;
+    s->ringSplit = split;
     return HS_SUCCESS;
 }
 
@@ -706,6 +714,7 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     pl->cfg.stride = stride;
     pl->cfg.queued = queued;
     pl->cfg.wide = wide;
+    pl->cfg.split = wide && g_opts.split && s->ringSplit;
     pl->cfg.grid = s->smCount;
     pl->cfg.warps = warps;
     pl->tileBytes = tile;
@@ -766,8 +775,15 @@ hs_error_t launchRange(hs_scratch *s, const DevImage *im, const hs_b200_corpus *
     LaunchCfg cfg = pl.cfg;
     const u32 perCta = (u32)cfg.warps;
     cfg.grid = (int)std::min<u32>((u32)cfg.grid, (p.ntiles + perCta - 1) / perCta);
+    if (cfg.split) {
+        CUDA_TRY(cudaMemsetAsync(s->d_counters + CTR_CANDQ, 0, sizeof(u32), stream));
+    }
     CUDA_TRY(launchScan(cfg, p, stream));
     g_launches++;
+    if (cfg.split) {
+        CUDA_TRY(launchConfirm(cfg, p, stream));
+        g_launches++;
+    }
     return HS_SUCCESS;
 }
 
@@ -938,7 +954,8 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"rebuild", &g_opts.rebuild},   {"domain", &g_opts.domain},
         {"direct", &g_opts.direct},     {"replicas", &g_opts.replicas},
         {"pf_dist", &g_opts.pfDist},    {"queue", &g_opts.queue},
-        {"first_stage", &g_opts.firstStage}, {"wide", &g_opts.wide}};
+        {"first_stage", &g_opts.firstStage}, {"wide", &g_opts.wide},
+        {"split", &g_opts.split}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;

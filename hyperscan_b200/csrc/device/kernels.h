@@ -55,7 +55,20 @@ enum ConfirmKind {
 
 enum { MAX_PEERS = 8 };
 enum { CTR_MATCHES = 0, CTR_ERROR = 1, CTR_CANDIDATES = 2, CTR_CONFIRMED = 3,
-       CTR_PREFILTER_PASS = 4, CTR_COUNT = 8 };
+       CTR_PREFILTER_PASS = 4, CTR_CANDQ = 5 /* split mode: candidates handed to the confirm kernel */,
+       CTR_COUNT = 8 };
+
+/* Split mode (opt-in): the scan kernel stops at the prefilter and appends the
+ * surviving candidates to a list in HBM; confirmKernel finishes them, one thread
+ * per candidate.  The list is the SECOND half of the record ring the scratch
+ * allocated (records [outCap, 2 * outCap) of ScanParams.out), so no launch
+ * parameter changes; if it overflows, the record count is raised above outCap
+ * and the caller's grow-and-rescan path takes over. */
+struct DevCand {
+    u64 g;       /* corpus position of the candidate's last byte */
+    u32 buckets; /* first-stage bucket bits */
+    u32 pad;
+};
 enum { ERR_BAD_OPCODE = 1, ERR_INTERNAL = 2 };
 
 struct ScanParams {
@@ -116,6 +129,7 @@ struct LaunchCfg {
     int direct;    /* 1: corpus loaded straight into registers; 0: TMA-staged tiles */
     int queued;    /* 1 (direct, stride 1 only): candidates go through the per-warp queue */
     int wide;      /* 1 (direct, stride 1, FK_BYTE32 / FK_HASH32, tileBytes % 1024 == 0): 32-byte lanes */
+    int split;     /* 1 (wide only): candidates go to the list in HBM, confirmKernel finishes them */
     int grid;      /* CTAs (one per SM) */
     int warps;     /* per CTA */
     size_t smemBytes;
@@ -128,6 +142,9 @@ size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 n
                      u32 tileBytes, int queueWarps);
 
 cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream);
+
+/* Split mode: finish the candidates the scan kernel left in the list (same stream, after it). */
+cudaError_t launchConfirm(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream);
 
 /* Publish the record count of a finished scan into slot 0 of this rank's
  * region in every peer's exchange buffer (runs after the scan on its stream). */

@@ -662,7 +662,7 @@ __device__ __forceinline__ u64 confValAt(const ScanParams &p, u64 g) {
  * the word before the lane's 16 bytes.  Per candidate byte: hash the last
  * keyBytes bytes into the prefilter bitmap (shared memory); only survivors pay
  * for the hash confirm in HBM/L2. */
-template <int NOCT>
+template <int NOCT, int SPLIT = 0>
 __device__ HSB_NOINLINE void laneCandidates(const ScanParams &p, u32 bitmapAddr, u32 c00, u32 c01,
                                             u32 c02, u32 c03, u32 c10, u32 c11, u32 c12, u32 c13,
                                             u32 w0, u32 w1, u32 w2, u32 w3, u32 pw, u64 g0,
@@ -712,6 +712,19 @@ __device__ HSB_NOINLINE void laneCandidates(const ScanParams &p, u32 bitmapAddr,
         }
         stats[1]++;
         const u64 g = g0 + x;
+        if (SPLIT) {
+            /* hand the candidate to confirmKernel (list = second half of the ring) */
+            const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
+            if (i < p.outCap) {
+                DevCand cnd;
+                cnd.g = g;
+                cnd.buckets = buckets;
+                cnd.pad = 0;
+                *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
+                    *reinterpret_cast<const uint4 *>(&cnd);
+            }
+            continue;
+        }
         const u64 confVal = confValAt(p, g);
         if (p.confirmKind == CK_NOODLE) {
             if (buckets & 1) {
@@ -1199,6 +1212,7 @@ __device__ __forceinline__ void laneFilterWide(const u32 (&w)[9], u32 tabAddr, u
     }
 }
 
+template <int SPLIT>
 __device__ HSB_NOINLINE void drainWide(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first, u32 count,
                                        u32 lane, u32 *stats) {
     if (lane >= count) {
@@ -1218,16 +1232,16 @@ __device__ HSB_NOINLINE void drainWide(const ScanParams &p, u32 bitmapAddr, u32 
     }
     const u32 pw = g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u;
     if (c0.x | c0.y | c0.z | c0.w) {
-        laneCandidates<1>(p, bitmapAddr, c0.x, c0.y, c0.z, c0.w, 0, 0, 0, 0, v0.x, v0.y, v0.z, v0.w, pw, g0,
-                          stats);
+        laneCandidates<1, SPLIT>(p, bitmapAddr, c0.x, c0.y, c0.z, c0.w, 0, 0, 0, 0, v0.x, v0.y, v0.z, v0.w, pw,
+                                 g0, stats);
     }
     if (c1.x | c1.y | c1.z | c1.w) {
-        laneCandidates<1>(p, bitmapAddr, c1.x, c1.y, c1.z, c1.w, 0, 0, 0, 0, v1.x, v1.y, v1.z, v1.w, v0.w,
-                          g0 + 16, stats);
+        laneCandidates<1, SPLIT>(p, bitmapAddr, c1.x, c1.y, c1.z, c1.w, 0, 0, 0, 0, v1.x, v1.y, v1.z, v1.w,
+                                 v0.w, g0 + 16, stats);
     }
 }
 
-template <int KIND, int SB>
+template <int KIND, int SB, int SPLIT>
 __global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
     static_assert(KIND == FK_BYTE32 || KIND == FK_HASH32, "wide steps: 8-bucket tables only");
     HSB_DYNAMIC_SMEM(smem);
@@ -1353,14 +1367,14 @@ __global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
             if (qn >= 32) {
                 __syncwarp();
                 qn -= 32;
-                drainWide(p, bitmapAddr, qAddr, qn, 32, lane, stats);
+                drainWide<SPLIT>(p, bitmapAddr, qAddr, qn, 32, lane, stats);
                 __syncwarp();
             }
         }
     }
     if (qn) {
         __syncwarp();
-        drainWide(p, bitmapAddr, qAddr, 0, qn, lane, stats);
+        drainWide<SPLIT>(p, bitmapAddr, qAddr, 0, qn, lane, stats);
     }
     if (stats[0]) {
         atomicAdd(p.counters + CTR_CANDIDATES, stats[0]);
@@ -1373,9 +1387,43 @@ __global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
     }
 }
 
+/* Split mode, second kernel: one thread per candidate of the list the scan
+ * kernel filled -- hash confirm, block lookup, literal program, record. */
+__global__ void __launch_bounds__(256) confirmKernel(const ScanParams p) {
+    const u32 total = p.counters[CTR_CANDQ];
+    const u32 n = total < p.outCap ? total : p.outCap;
+    if (total > p.outCap && blockIdx.x == 0 && threadIdx.x == 0) {
+        /* the list overflowed: make the scan report more records than the ring
+         * holds, which sends the caller down its grow-and-rescan path */
+        atomicMax(p.counters + CTR_MATCHES, total);
+    }
+    const DevCand *list = reinterpret_cast<const DevCand *>(p.out + p.outCap);
+    u32 nconf = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(list + i));
+        const u64 g = ((u64)raw.y << 32) | raw.x;
+        u32 buckets = raw.z;
+        const u64 confVal = confValAt(p, g);
+        if (p.confirmKind == CK_NOODLE) {
+            if (buckets & 1) {
+                confirmNoodle(p, g, confVal, &nconf);
+            }
+        } else {
+            while (buckets) {
+                const u32 bucket = __ffs(buckets) - 1;
+                buckets &= buckets - 1;
+                confirmFdr(p, bucket, g, confVal, &nconf);
+            }
+        }
+    }
+    if (nconf) {
+        atomicAdd(p.counters + CTR_CONFIRMED, nconf);
+    }
+}
+
 template <int KIND, int SB>
 cudaError_t launchWide(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
-    void (*kern)(const ScanParams) = scanKernelWide<KIND, SB>;
+    void (*kern)(const ScanParams) = cfg.split ? scanKernelWide<KIND, SB, 1> : scanKernelWide<KIND, SB, 0>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smemBytes);
     if (e != cudaSuccess) {
         return e;
@@ -1505,6 +1553,11 @@ cudaError_t launchStreamAdvance(const u8 *corpus, u8 *hist, u64 *offsets, const 
         HSB_LAUNCH(streamAdvanceKernel, (nstreams + 255) / 256, 256, 0, stream, corpus, hist, offsets, lens,
                    uniformLen, nstreams, pitch, histReq);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launchConfirm(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    HSB_LAUNCH(confirmKernel, cfg.grid * 2, 256, 0, stream, p);
     return cudaGetLastError();
 }
 

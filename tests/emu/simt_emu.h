@@ -136,5 +136,6 @@ using std::min;
 template <class T> static inline T atomicAdd(T *p, T v) { const T o = *p; *p = o + v; return o; }
 template <class T> static inline T atomicExch(T *p, T v) { const T o = *p; *p = v; return o; }
 template <class T> static inline T atomicMin(T *p, T v) { const T o = *p; if (v < o) *p = v; return o; }
+template <class T> static inline T atomicMax(T *p, T v) { const T o = *p; if (v > o) *p = v; return o; }
 
 #endif

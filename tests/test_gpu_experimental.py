@@ -16,7 +16,7 @@ pytestmark = [pytest.mark.gpu,
                                  reason="opt-in variants: set HSB200_EXPERIMENTAL=1")]
 
 DEFAULTS = {"wide": 0, "queue": 2, "first_stage": 1, "replicas": 1, "domain": 0, "tile_bytes": 1024,
-            "warps": 32}
+            "warps": 32, "split": 0, "initial_ring": 1 << 20}
 VARIANTS = [
     {"wide": 1},
     {"wide": 1, "domain": 12, "replicas": 8},
@@ -24,6 +24,9 @@ VARIANTS = [
     {"queue": 1},
     {"queue": 1, "first_stage": 2},
     {"wide": 1, "first_stage": 2},
+    {"wide": 1, "split": 1},
+    {"wide": 1, "split": 1, "domain": 12, "replicas": 8},
+    {"wide": 1, "split": 1, "initial_ring": 16},       # candidate list and ring overflow -> grow and rescan
 ]
 
 
