@@ -1241,8 +1241,8 @@ __device__ HSB_NOINLINE void drainWide(const ScanParams &p, u32 bitmapAddr, u32 
     }
 }
 
-template <int KIND, int SB, int SPLIT>
-__global__ void __launch_bounds__(896, 1) scanKernelWide(const ScanParams p) {
+template <int KIND, int SB, int SPLIT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const ScanParams p) {
     static_assert(KIND == FK_BYTE32 || KIND == FK_HASH32, "wide steps: 8-bucket tables only");
     HSB_DYNAMIC_SMEM(smem);
     const u32 lane = threadIdx.x & 31;
@@ -1423,7 +1423,14 @@ __global__ void __launch_bounds__(256) confirmKernel(const ScanParams p) {
 
 template <int KIND, int SB>
 cudaError_t launchWide(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
-    void (*kern)(const ScanParams) = cfg.split ? scanKernelWide<KIND, SB, 1> : scanKernelWide<KIND, SB, 0>;
+    /* up to 24 warps the kernel is built for 768 threads (80 registers: the split
+     * variant's loop is spill-free there), above for 896 (72 registers) */
+    void (*kern)(const ScanParams);
+    if (cfg.warps <= 24) {
+        kern = cfg.split ? scanKernelWide<KIND, SB, 1, 768> : scanKernelWide<KIND, SB, 0, 768>;
+    } else {
+        kern = cfg.split ? scanKernelWide<KIND, SB, 1, 896> : scanKernelWide<KIND, SB, 0, 896>;
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smemBytes);
     if (e != cudaSuccess) {
         return e;

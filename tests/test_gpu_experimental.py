@@ -27,6 +27,7 @@ VARIANTS = [
     {"wide": 1, "split": 1},
     {"wide": 1, "split": 1, "domain": 12, "replicas": 8},
     {"wide": 1, "split": 1, "initial_ring": 16},       # candidate list and ring overflow -> grow and rescan
+    {"wide": 1, "split": 1, "warps": 24},               # the 768-thread build of the kernel
 ]
 
 
