@@ -8,7 +8,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "hyperscan_b200", "csrc")
-OUT_DIR = os.path.join(HERE, "_build")
+# HSB_EMU_SANITIZE=1: AddressSanitizer build (run pytest with LD_PRELOAD=libasan.so and
+# ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0) -- a memcheck for host and kernel logic
+SANITIZE = os.environ.get("HSB_EMU_SANITIZE") == "1"
+OUT_DIR = os.path.join(HERE, "_build_asan" if SANITIZE else "_build")
 OUT = os.path.join(OUT_DIR, "libhs_b200_simt_emu.so")
 HOST = ["host/api_host.cpp", "host/rose_build.cpp", "host/hwlm_build.cpp", "host/db_walk.cpp"]
 DEVICE = ["device/scan_kernels.cu", "device/api_device.cu", "device/accel_kernels.cu"]
@@ -28,6 +31,8 @@ def build(verbose=False):
         return OUT
     objs = []
     common = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-fno-strict-aliasing", "-Wno-unused-value"]
+    if SANITIZE:
+        common += ["-fsanitize=address", "-fno-omit-frame-pointer"]
     jobs = [(os.path.join(CSRC, s), common) for s in HOST]
     jobs += [(os.path.join(CSRC, s), common + ["-x", "c++", "-DHSB_HOST_EMU", "-I", HERE]) for s in DEVICE]
     jobs += [(os.path.join(HERE, "simt_emu.cpp"), common)]
@@ -42,7 +47,7 @@ def build(verbose=False):
     for full, pr in procs:
         if pr.wait() != 0:
             raise RuntimeError("emulator build failed: " + " ".join(full))
-    subprocess.run(["g++", "-shared", "-o", OUT] + objs, check=True)
+    subprocess.run(["g++", "-shared"] + (["-fsanitize=address"] if SANITIZE else []) + ["-o", OUT] + objs, check=True)
     return OUT
 
 
