@@ -662,11 +662,11 @@ __device__ __forceinline__ u64 confValAt(const ScanParams &p, u64 g) {
  * the word before the lane's 16 bytes.  Per candidate byte: hash the last
  * keyBytes bytes into the prefilter bitmap (shared memory); only survivors pay
  * for the hash confirm in HBM/L2. */
-template <int NOCT, int SPLIT = 0>
-__device__ HSB_NOINLINE void laneCandidates(const ScanParams &p, u32 bitmapAddr, u32 c00, u32 c01,
-                                            u32 c02, u32 c03, u32 c10, u32 c11, u32 c12, u32 c13,
-                                            u32 w0, u32 w1, u32 w2, u32 w3, u32 pw, u64 g0,
-                                            u32 *stats) {
+template <int NOCT, int SPLIT>
+__device__ __forceinline__ void laneCandidatesBody(const ScanParams &p, u32 bitmapAddr, u32 c00, u32 c01,
+                                                   u32 c02, u32 c03, u32 c10, u32 c11, u32 c12, u32 c13,
+                                                   u32 w0, u32 w1, u32 w2, u32 w3, u32 pw, u64 g0,
+                                                   u32 *stats) {
     /* 16-bit map of bytes that carry a candidate */
     u32 cm = 0;
     {
@@ -738,6 +738,19 @@ __device__ HSB_NOINLINE void laneCandidates(const ScanParams &p, u32 bitmapAddr,
             }
         }
     }
+}
+
+/* Out of line in the fused kernels (it carries the confirm and the literal
+ * programs); the split kernels inline the body, which then ends at the append
+ * to the candidate list, so nothing in them takes the parameters' address (no
+ * per-thread copy of ScanParams on the stack). */
+template <int NOCT>
+__device__ HSB_NOINLINE void laneCandidates(const ScanParams &p, u32 bitmapAddr, u32 c00, u32 c01,
+                                            u32 c02, u32 c03, u32 c10, u32 c11, u32 c12, u32 c13,
+                                            u32 w0, u32 w1, u32 w2, u32 w3, u32 pw, u64 g0,
+                                            u32 *stats) {
+    laneCandidatesBody<NOCT, 0>(p, bitmapAddr, c00, c01, c02, c03, c10, c11, c12, c13, w0, w1, w2, w3, pw, g0,
+                                stats);
 }
 
 /* Candidate queue (template QUEUED): instead of every lane walking its own
@@ -1213,7 +1226,7 @@ __device__ __forceinline__ void laneFilterWide(const u32 (&w)[9], u32 tabAddr, u
 }
 
 template <int SPLIT>
-__device__ HSB_NOINLINE void drainWide(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first, u32 count,
+__device__ __forceinline__ void drainWideBody(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first, u32 count,
                                        u32 lane, u32 *stats) {
     if (lane >= count) {
         return;
@@ -1232,13 +1245,28 @@ __device__ HSB_NOINLINE void drainWide(const ScanParams &p, u32 bitmapAddr, u32 
     }
     const u32 pw = g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u;
     if (c0.x | c0.y | c0.z | c0.w) {
-        laneCandidates<1, SPLIT>(p, bitmapAddr, c0.x, c0.y, c0.z, c0.w, 0, 0, 0, 0, v0.x, v0.y, v0.z, v0.w, pw,
-                                 g0, stats);
+        if constexpr (SPLIT) {
+            laneCandidatesBody<1, 1>(p, bitmapAddr, c0.x, c0.y, c0.z, c0.w, 0, 0, 0, 0, v0.x, v0.y, v0.z, v0.w,
+                                     pw, g0, stats);
+        } else {
+            laneCandidates<1>(p, bitmapAddr, c0.x, c0.y, c0.z, c0.w, 0, 0, 0, 0, v0.x, v0.y, v0.z, v0.w, pw, g0,
+                              stats);
+        }
     }
     if (c1.x | c1.y | c1.z | c1.w) {
-        laneCandidates<1, SPLIT>(p, bitmapAddr, c1.x, c1.y, c1.z, c1.w, 0, 0, 0, 0, v1.x, v1.y, v1.z, v1.w,
-                                 v0.w, g0 + 16, stats);
+        if constexpr (SPLIT) {
+            laneCandidatesBody<1, 1>(p, bitmapAddr, c1.x, c1.y, c1.z, c1.w, 0, 0, 0, 0, v1.x, v1.y, v1.z, v1.w,
+                                     v0.w, g0 + 16, stats);
+        } else {
+            laneCandidates<1>(p, bitmapAddr, c1.x, c1.y, c1.z, c1.w, 0, 0, 0, 0, v1.x, v1.y, v1.z, v1.w, v0.w,
+                              g0 + 16, stats);
+        }
     }
+}
+
+__device__ HSB_NOINLINE void drainWide(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first, u32 count,
+                                       u32 lane, u32 *stats) {
+    drainWideBody<0>(p, bitmapAddr, qAddr, first, count, lane, stats);
 }
 
 template <int KIND, int SB, int SPLIT, int MAXT>
@@ -1367,14 +1395,22 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const ScanParams p) {
             if (qn >= 32) {
                 __syncwarp();
                 qn -= 32;
-                drainWide<SPLIT>(p, bitmapAddr, qAddr, qn, 32, lane, stats);
+                if constexpr (SPLIT) {
+                    drainWideBody<1>(p, bitmapAddr, qAddr, qn, 32, lane, stats);
+                } else {
+                    drainWide(p, bitmapAddr, qAddr, qn, 32, lane, stats);
+                }
                 __syncwarp();
             }
         }
     }
     if (qn) {
         __syncwarp();
-        drainWide<SPLIT>(p, bitmapAddr, qAddr, 0, qn, lane, stats);
+        if constexpr (SPLIT) {
+            drainWideBody<1>(p, bitmapAddr, qAddr, 0, qn, lane, stats);
+        } else {
+            drainWide(p, bitmapAddr, qAddr, 0, qn, lane, stats);
+        }
     }
     if (stats[0]) {
         atomicAdd(p.counters + CTR_CANDIDATES, stats[0]);
