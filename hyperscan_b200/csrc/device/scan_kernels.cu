@@ -1212,7 +1212,11 @@ __device__ __forceinline__ void laneFilterWide(const u32 (&w)[9], u32 tabAddr, u
                 } else {
                     off = w[k] >> (8 * r - sh);
                 }
-                E[k] = lds32(tabAddr + (off & (indexMask << sh)));
+                /* (masked offset | this lane's copy) is ONE three-input logic op and
+                 * the table base stays a uniform register of the load: 3 instructions
+                 * per lookup (the 16-byte kernels spend a 4th on adding a per-lane
+                 * base; to be folded the same way once this variant is measured) */
+                E[k] = lds32(tabAddr + ((off & (indexMask << sh)) | laneOff));
             } else {
                 E[k] = lds32(tabAddr + __byte_perm(w[k], laneOff, 0x5504 + (r << 4)));
             }
@@ -1302,8 +1306,10 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const ScanParams p) {
     __syncthreads();
 
     const u32 bitmapAddr = smemAddr(smem) + tab0;
-    const u32 tabAddr = smemAddr(smem) + (KIND == FK_HASH32 ? (lane & ((1u << p.repShift) - 1)) * 4 : 0);
-    const u32 laneOff = lane * 4;
+    /* laneOff: FK_BYTE32 = the lane's column of a table row; FK_HASH32 = the
+     * lane's copy of an entry (bank partition), OR-ed into the masked offset */
+    const u32 tabAddr = smemAddr(smem);
+    const u32 laneOff = KIND == FK_HASH32 ? (lane & ((1u << p.repShift) - 1)) * 4 : lane * 4;
     const u32 qAddr = smemAddr(smem) + tabBytes + warp * WideQueue::WARP_BYTES;
 
     /* this warp's contiguous run of tiles (tileBytes is a multiple of 1024 here) */
