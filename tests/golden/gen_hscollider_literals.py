@@ -24,7 +24,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from hyperscan_b200 import capi  # noqa: E402
 import oracle.ref as ref  # noqa: E402
@@ -110,7 +110,7 @@ def main():
                     "hs_flags": flags, "file": pfile, "corpora": corp})
         print(pid, pat, fl, len(corp), "corpora")
     with open(os.path.join(ROOT, "tests", "golden", "hscollider_literals.json"), "w") as f:
-        json.dump({"generator": "tools/gen_hscollider_golden.py",
+        json.dump({"generator": "tests/golden/gen_hscollider_literals.py",
                    "source": "intel/hyperscan 5.4.2 tools/hscollider/test_cases (recorded offsets)",
                    "cases": out}, f, indent=0)
     print(len(out), "patterns,", sum(len(c["corpora"]) for c in out), "corpora")

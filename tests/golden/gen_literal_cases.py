@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from hyperscan_b200 import capi, synth  # noqa: E402
 import oracle.ref as ref  # noqa: E402
@@ -46,7 +46,7 @@ def main():
         })
         print(name, "engine", out[-1]["engine"], "matches", len(want))
     with open(os.path.join(ROOT, "tests", "golden", "literal_cases.json"), "w") as f:
-        json.dump({"generator": "tools/gen_golden.py", "reference": "intel/hyperscan 5.4.2 runtime (oracle/_ref)",
+        json.dump({"generator": "tests/golden/gen_literal_cases.py", "reference": "intel/hyperscan 5.4.2 runtime (oracle/_ref)",
                    "cases": out}, f)
 
 

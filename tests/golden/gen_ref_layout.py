@@ -8,7 +8,7 @@ committed JSON lets tests/test_layout.py pin our restated layouts on machines
 that have no /root/reference (the GPU box).
 """
 import ctypes, json, os, subprocess, sys
-root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 so = os.path.join(root, "oracle", "_ref", "libhsref_corei7.so")
 code = "import ctypes,sys; ctypes.CDLL(sys.argv[1]).ref_layout_dump()"
 out = subprocess.run([sys.executable, "-c", code, so], capture_output=True, text=True, check=True).stdout

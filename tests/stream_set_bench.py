@@ -4,7 +4,7 @@ HBM): N streams x W-byte writes, R rounds through hs_b200_streams_scan from
 pinned host memory; prints one JSON line.  Parity is spot-checked against the
 reference stream runtime on a sample of streams.
 
-  python tools/bench_streams.py [--streams 1048576] [--write 1024] [--rounds 4] [--lits 5000]
+  python tests/stream_set_bench.py [--streams 1048576] [--write 1024] [--rounds 4] [--lits 5000]
 """
 import argparse
 import json

@@ -1,5 +1,5 @@
 """Committed golden vectors (tests/golden/literal_cases.json, produced by
-tools/gen_golden.py from the unmodified reference runtime): the C restatement
+tests/golden/gen_literal_cases.py from the unmodified reference runtime): the C restatement
 and -- on the GPU box -- the CUDA path must reproduce them.  These do not need
 oracle/_ref or /root/reference at run time."""
 import base64
@@ -52,7 +52,7 @@ def test_cuda_path_reproduces_golden(hs, case):
 
 
 # --- the reference's own recorded hscollider vectors for literal patterns ---------------------------
-# tests/golden/hscollider_literals.json (tools/gen_hscollider_golden.py): pattern text and recorded
+# tests/golden/hscollider_literals.json (tests/golden/gen_hscollider_literals.py): pattern text and recorded
 # end offsets from tools/hscollider/test_cases/{pcre,corpora}; compare rule for single-match patterns
 # per tools/hscollider/main.cpp:522-537 (exactly one of the recorded matches).
 with open(os.path.join(ROOT, "tests", "golden", "hscollider_literals.json")) as f:

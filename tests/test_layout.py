@@ -1,6 +1,6 @@
 """Database layout pins: every sizeof/offsetof hyperscan_b200/csrc/ref_layout.h
 restates equals the value the reference's own headers give
-(tests/golden/ref_layout.json, produced by tools/gen_ref_layout.py from
+(tests/golden/ref_layout.json, produced by tests/golden/gen_ref_layout.py from
 /root/reference).  The serialized database format is the drop-in boundary."""
 import json
 import os

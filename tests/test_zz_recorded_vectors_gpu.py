@@ -1,5 +1,5 @@
 """The reference's recorded hscollider vectors (tests/golden/hscollider_literals.json,
-tools/gen_hscollider_golden.py) through the CUDA path.  The CPU half (C oracle
+tests/golden/gen_hscollider_literals.py) through the CUDA path.  The CPU half (C oracle
 against the same fixture) is in tests/test_golden.py; this file sorts last on
 purpose: it is the widest sweep over compiler-accepted expressions (groups,
 alternation, classes, bounded repeats -> many literals under one id)."""
