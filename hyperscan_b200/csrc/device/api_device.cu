@@ -1592,7 +1592,9 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
         CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         s->chunkEvents->push_back(ev);
     }
-    for (int attempt = 0; attempt < 2; attempt++) {
+    /* a second pass after the record ring grew; split mode may need a third (its
+     * candidate list can overflow before the ring does) */
+    for (int attempt = 0; attempt < 3; attempt++) {
         CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, CTR_COUNT * sizeof(u32), s->stream));
         CUDA_TRY(cudaEventRecord(s->evStart, s->stream));
         /* zero the look-ahead bytes after the corpus */

@@ -637,13 +637,15 @@ __device__ __forceinline__ void laneFilter(const u32 (&w)[5], u32 tabAddr, u32 l
 /* ---- candidate handling (rare path) ------------------------------------------- */
 
 /* little-endian u64 of corpus bytes [g-7, g]; positions before the corpus
- * read as zero (a wrapped caller buffer has nothing readable before it) */
+ * read as zero (a wrapped caller buffer has nothing readable before it), and so
+ * do positions past its readable end: a first-stage candidate can sit in the
+ * padding after the last block (it is rejected later, by the block lookup) */
 __device__ __forceinline__ u64 confValAt(const ScanParams &p, u64 g) {
     if (g < 11 || g + 5 > p.readableEnd) { /* rare: the aligned 12-byte window would leave the buffer */
         u64 v = 0;
         for (int z = 0; z < 8; z++) {
             const long long q = (long long)g - 7 + z;
-            if (q >= 0) {
+            if (q >= 0 && (u64)q < p.readableEnd) {
                 v |= (u64)__ldg(p.corpus + q) << (8 * z);
             }
         }

@@ -141,6 +141,10 @@ void launch(dim3 grid, dim3 block, size_t smemBytes, const std::function<void()>
     if (g_blk) {
         die("nested launch");
     }
+    static const bool trace = getenv("HSB_EMU_TRACE") != nullptr;
+    if (trace) {
+        fprintf(stderr, "simt_emu: launch grid %u block %u smem %zu\n", grid.x, block.x, smemBytes);
+    }
     const unsigned nthreads = block.x, nwarps = (nthreads + 31) / 32;
     BlockState b;
     b.fibers.resize(nthreads);

@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Randomised parity fuzzing of the kernels on the SIMT emulator (tests/emu) against the
+unmodified reference runtime: random literal sets, block layouts and runtime options
+(default and opt-in kernel variants).  Not collected by pytest; run by hand:
+
+  python tests/fuzz_emu.py [--seconds 300] [--seed 1]
+"""
+import argparse
+import faulthandler
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+from hyperscan_b200 import capi, synth  # noqa: E402
+import build_emu  # noqa: E402
+import oracle.ref as ref  # noqa: E402
+
+DEFAULTS = {"warps": 32, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1, "rebuild": 1,
+            "domain": 0, "direct": 1, "replicas": 1, "pf_dist": 8, "queue": 2, "first_stage": 1, "wide": 0,
+            "split": 0, "initial_ring": 1 << 20}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seconds", type=float, default=300)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--dump", default="", help="write every case here before running it (post-mortem)")
+    ap.add_argument("--replay", default="", help="run the one case of a --dump file")
+    ap.add_argument("--cases", default="", help="comma list: execute only these case numbers (the others only advance the RNG)")
+    args = ap.parse_args()
+    capi.LIB_PATH = build_emu.build()
+    if args.replay:
+        import pickle
+        with open(args.replay, "rb") as f:
+            c = pickle.load(f)
+        for k, v in c["opts"].items():
+            capi.set_runtime_option(k, v)
+        db = capi.compile_lit_multi(c["lits"], c["flags"], c["ids"])
+        scratch = capi.Scratch(db)
+        want = ref.scan_sorted(db.ptr, c["data"], c["off"], c["ln"])
+        got = np.sort(capi.scan_blocks(db, c["data"], c["off"], c["ln"], scratch), order=["block", "to", "id"])
+        print("replay host blocks:", len(got), len(want), np.array_equal(got, want), flush=True)
+        corpus = capi.Corpus.upload(c["data"], c["off"], c["ln"])
+        got2 = np.sort(capi.scan_corpus(db, corpus, scratch), order=["block", "to", "id"])
+        print("replay resident corpus:", len(got2), np.array_equal(got2, want))
+        return 0
+    rng = np.random.default_rng(args.seed)
+    t0, n, skipped = time.time(), 0, 0
+    alphabets = [b"ab", b"abcd", b"abcdefgh", b"abcdefghijklmnopqrstuvwxyz", bytes(range(0x20, 0x7f)), bytes(range(256))]
+    while time.time() - t0 < args.seconds:
+        n += 1
+        nl = int(rng.choice([1, 2, 5, 8, 20, 48, 60, 96, 200, 700, 2000]))
+        al = alphabets[int(rng.integers(0, len(alphabets)))]
+        lo = int(rng.integers(1, 6))
+        hi = lo + int(rng.integers(0, 14))
+        while len(al) ** hi < nl * 8:   # enough distinct strings for literal_set to terminate
+            hi += 1
+            lo = max(lo, hi - 6)
+        lits, flags, ids = synth.literal_set(nl, min_len=lo, max_len=hi, seed=int(rng.integers(1 << 30)),
+                                             caseless_frac=float(rng.choice([0, 0.2, 1.0])),
+                                             singlematch_frac=float(rng.choice([0, 0.1])), alphabet=al)
+        if rng.random() < 0.3:
+            ids = [i // 3 for i in ids]
+            fm = {}
+            for k in range(nl):
+                fm.setdefault(ids[k], flags[k] & 8)
+                flags[k] = (flags[k] & ~8) | fm[ids[k]]
+        opts = dict(DEFAULTS)
+        opts["warps"] = int(rng.choice([1, 2, 3, 5, 8]))
+        mode = rng.integers(0, 8)
+        if mode == 0:
+            opts.update(direct=0, tile_bytes=int(rng.choice([512, 1024, 2048])), stages=int(rng.choice([2, 3])))
+        elif mode == 1:
+            opts.update(wide=1, split=int(rng.integers(0, 2)), tile_bytes=int(rng.choice([1024, 4096])))
+        elif mode == 2:
+            opts.update(wide=1, split=1, domain=int(rng.choice([0, 10, 12])), replicas=int(rng.choice([1, 4, 8])))
+        elif mode == 3:
+            opts.update(queue=int(rng.integers(0, 2)), first_stage=int(rng.choice([1, 2])))
+        elif mode == 4:
+            opts.update(stride=int(rng.choice([0, 2, 4])), rebuild=int(rng.integers(0, 2)), prefilter=int(rng.integers(0, 2)))
+        elif mode == 5:
+            opts.update(domain=int(rng.choice([9, 11, 14])), replicas=int(rng.choice([0, 2, 16])), wide_fdr=int(rng.integers(0, 2)))
+        elif mode == 6:
+            opts.update(initial_ring=int(rng.choice([16, 256])), wide=int(rng.integers(0, 2)), split=int(rng.integers(0, 2)))
+        for k, v in opts.items():
+            capi.set_runtime_option(k, v)
+        lens = [int(x) for x in rng.choice([0, 1, 2, 3, 15, 16, 17, 31, 32, 33, 63, 511, 512, 513, 1023, 1024, 1025, 3000, 9000],
+                                           size=int(rng.integers(1, 12)))]
+        data, off, ln = synth.ragged_corpus(lens, lits, seed=int(rng.integers(1 << 30)),
+                                            plant_per_kb=float(rng.choice([0.5, 5, 30])), alphabet=al)
+        if args.verbose:
+            print("case", n, "nl", nl, "alphabet", len(al), "len", lo, hi,
+                  {k: v for k, v in opts.items() if DEFAULTS[k] != v}, "lens", lens, flush=True)
+        if args.cases and str(n) not in args.cases.split(","):
+            continue
+        faulthandler.dump_traceback_later(120, exit=True)  # a case takes seconds: anything longer is a hang
+        if args.dump:
+            import pickle
+            with open(args.dump, "wb") as f:
+                pickle.dump({"lits": lits, "flags": flags, "ids": ids, "data": data, "off": off, "ln": ln,
+                             "opts": opts}, f)
+        try:
+            db = capi.compile_lit_multi(lits, flags, ids)
+        except capi.HsError:
+            skipped += 1
+            continue
+        scratch = capi.Scratch(db)
+        want = ref.scan_sorted(db.ptr, data, off, ln)
+        got = np.sort(capi.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
+        corpus = capi.Corpus.upload(data, off, ln)
+        got2 = np.sort(capi.scan_corpus(db, corpus, scratch), order=["block", "to", "id"])
+        corpus.free()
+        scratch.free()
+        faulthandler.cancel_dump_traceback_later()
+        if not (np.array_equal(got, want) and np.array_equal(got2, want)):
+            print("MISMATCH case", n, "nl", nl, "alphabet", len(al), "len", lo, hi, "opts",
+                  {k: v for k, v in opts.items() if DEFAULTS[k] != v}, "lens", lens, len(got), len(got2), len(want))
+            return 1
+    print("fuzz: %d cases (%d refused by the compiler), all bit-exact vs the reference runtime (%.0f s)"
+          % (n - skipped, skipped, time.time() - t0))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
