@@ -25,6 +25,87 @@ DEFAULTS = {"warps": 32, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride
             "split": 0, "initial_ring": 1 << 20}
 
 
+def fuzz_streams(args, rng):
+    """Streaming API, vectored mode and stream sets against the reference stream runtime."""
+    t0, n = time.time(), 0
+    while time.time() - t0 < args.seconds:
+        n += 1
+        nl = int(rng.choice([1, 3, 8, 40, 100, 400]))
+        al = [b"abcdef", b"abcdefghijklmnopqrstuvwxyz", bytes(range(0x20, 0x7f))][int(rng.integers(0, 3))]
+        single = float(rng.choice([0, 0.2]))
+        lits, flags, ids = synth.literal_set(nl, min_len=1 if nl < 10 else 2, max_len=8, seed=int(rng.integers(1 << 30)),
+                                             caseless_frac=float(rng.choice([0, 0.3])), singlematch_frac=single,
+                                             alphabet=al)
+        for k, v in DEFAULTS.items():
+            capi.set_runtime_option(k, v)
+        capi.set_runtime_option("warps", int(rng.choice([1, 2, 5])))
+        capi.set_runtime_option("direct", int(rng.integers(0, 2)))
+        total = int(rng.choice([50, 700, 5000]))
+        data, _, _ = synth.ragged_corpus([total], lits, seed=int(rng.integers(1 << 30)), plant_per_kb=20, alphabet=al)
+        data = data[:total]
+        cuts = np.sort(rng.integers(0, total + 1, size=int(rng.integers(1, 20))))
+        wl = np.diff(np.concatenate([[0], cuts, [total]])).astype(np.uint32)
+        # 1. hs_open_stream / hs_scan_stream / compress + expand half way
+        db = capi.compile_lit_multi(lits, flags, ids, mode=capi.HS_MODE_STREAM)
+        scratch = capi.Scratch(db)
+        want, err = ref.stream_collect(db.ptr, data, wl)
+        st = capi.Stream(db)
+        got, pos = [], 0
+        for i, w in enumerate(wl):
+            if i == len(wl) // 2:
+                twin = capi.Stream.expand(db, st.compress())
+                st.close(scratch)
+                st = twin
+            rc, out = st.scan(data[pos:pos + int(w)], scratch)
+            assert rc == 0
+            got += [(i, a, b) for (a, b) in out]
+            pos += int(w)
+        st.close(scratch)
+        exp = sorted((int(r["block"]), int(r["id"]), int(r["to"])) for r in want)
+        if err != 0 or sorted(got) != exp:
+            print("STREAM MISMATCH case", n, nl, len(al), wl.tolist()[:10], len(got), len(exp))
+            return 1
+        # 2. stream set (no single-match ids): every stream gets the same cuts of its own data
+        if single == 0:
+            ns = int(rng.choice([1, 33, 130]))
+            sset = capi.StreamSet(db, ns)
+            datas = [synth.ragged_corpus([total], lits, seed=int(rng.integers(1 << 30)), plant_per_kb=20, alphabet=al)[0][:total]
+                     for _ in range(ns)]
+            recs_all, pos = [], 0
+            for i, w in enumerate(wl):
+                w = int(w)
+                buf = np.concatenate([d[pos:pos + w] for d in datas]) if w else np.zeros(0, np.uint8)
+                off = (np.arange(ns, dtype=np.uint64) * np.uint64(w))
+                recs_all.append(sset.scan(buf, off, np.full(ns, w, dtype=np.uint32), scratch))
+                pos += w
+            sset.close()
+            for sidx in {0, ns - 1, int(rng.integers(0, ns))}:
+                w2, _ = ref.stream_collect(db.ptr, datas[sidx], wl)
+                exp2 = sorted((int(r["block"]), int(r["id"]), int(r["to"])) for r in w2)
+                mine = []
+                for i, recs in enumerate(recs_all):
+                    mine += [(i, int(r["id"]), int(r["to"])) for r in recs[recs["block"] == sidx]]
+                if sorted(mine) != exp2:
+                    print("STREAM SET MISMATCH case", n, nl, ns, sidx, len(mine), len(exp2))
+                    return 1
+        scratch.free()
+        # 3. vectored mode
+        vdb = capi.compile_lit_multi(lits, flags, ids, mode=capi.HS_MODE_VECTORED)
+        vs = capi.Scratch(vdb)
+        wantv, errv = ref.vector_collect(vdb.ptr, data, wl)
+        bufs, pos = [], 0
+        for w in wl:
+            bufs.append(data[pos:pos + int(w)])
+            pos += int(w)
+        rc, gotv = capi.scan_vector(vdb, bufs, vs)
+        vs.free()
+        if rc != 0 or errv != 0 or sorted(gotv) != sorted((int(r["id"]), int(r["to"])) for r in wantv):
+            print("VECTORED MISMATCH case", n, nl, wl.tolist()[:10], len(gotv), len(wantv))
+            return 1
+    print("fuzz streams: %d cases, all equal to the reference stream runtime (%.0f s)" % (n, time.time() - t0))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=300)
@@ -32,6 +113,8 @@ def main():
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--dump", default="", help="write every case here before running it (post-mortem)")
     ap.add_argument("--replay", default="", help="run the one case of a --dump file")
+    ap.add_argument("--mode", default="blocks", choices=["blocks", "streams"],
+                    help="blocks: block-mode scans; streams: hs_*_stream, hs_scan_vector and stream sets")
     ap.add_argument("--cases", default="", help="comma list: execute only these case numbers (the others only advance the RNG)")
     args = ap.parse_args()
     capi.LIB_PATH = build_emu.build()
@@ -51,6 +134,8 @@ def main():
         print("replay resident corpus:", len(got2), np.array_equal(got2, want))
         return 0
     rng = np.random.default_rng(args.seed)
+    if args.mode == "streams":
+        return fuzz_streams(args, rng)
     t0, n, skipped = time.time(), 0, 0
     alphabets = [b"ab", b"abcd", b"abcdefgh", b"abcdefghijklmnopqrstuvwxyz", bytes(range(0x20, 0x7f)), bytes(range(256))]
     while time.time() - t0 < args.seconds:
