@@ -1360,9 +1360,18 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const ScanParams p) {
         const u32 first = __shfl_sync(0xffffffffu, nlo.x, 0);
         haloStep<KIND, 1, SB>(p, hv, first, tabAddr, laneOff, carry);
     }
-    for (u32 it = 0; it < niter; it++) {
+    /* one iteration; `fast` (split variants, every iteration but the last ones of
+     * the corpus): the load of iteration it + 1 needs no bounds check because that
+     * whole KiB is readable for every lane */
+    auto iteration = [&](const u32 it, const bool fast) {
         const uint4 lo = nlo, hi = nhi;
-        load(it + 1, nlo, nhi);
+        if (fast) {
+            const u8 *q0 = base + (size_t)(it + 1) * 1024;
+            nlo = ldCs128(q0);
+            nhi = ldCs128(q0 + 16);
+        } else {
+            load(it + 1, nlo, nhi);
+        }
         if ((lane & 3) == 0) {
             const u64 pos = lanePos + (u64)(it + pfDist) * 1024;
             if (pos < p.readableEnd) {
@@ -1411,6 +1420,19 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const ScanParams p) {
                 __syncwarp();
             }
         }
+    };
+    u32 it = 0;
+    if (SPLIT) {
+        const u64 readableIters = (p.readableEnd - runStart) >> 10;
+        const u32 nFast = readableIters >= (u64)niter + 1 ? niter : (readableIters ? (u32)readableIters - 1 : 0);
+#pragma unroll 1
+        for (; it < nFast; it++) {
+            iteration(it, true);
+        }
+    }
+#pragma unroll 1
+    for (; it < niter; it++) {
+        iteration(it, false);
     }
     if (qn) {
         __syncwarp();
