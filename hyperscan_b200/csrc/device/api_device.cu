@@ -672,7 +672,7 @@ struct ScanPlan {
 hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     initOpts();
     const int direct = g_opts.direct ? 1 : 0;
-    int warps = std::max(1, std::min(direct ? 28 : 32, g_opts.warps));
+    int warps = std::max(1, std::min(32, g_opts.warps));
     u32 tile = (u32)std::max(512, g_opts.tileBytes) & ~511u;
     u32 stages = (u32)std::max(2, std::min(8, g_opts.stages));
     /* shrink until the table + staging fit the opt-in shared memory */
@@ -684,6 +684,11 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     const bool byteKind = im->kind == FK_BYTE32 || im->kind == FK_BYTE64;
     const int wide = g_opts.wide && direct && stride == 1 && (im->kind == FK_BYTE32 || im->kind == FK_HASH32);
     const int queued = direct && stride == 1 && (g_opts.queue == 1 || (g_opts.queue == 2 && byteKind));
+    const int split = wide && g_opts.split && s->ringSplit;
+    if (direct && !(wide && split)) {
+        warps = std::min(warps, 28); /* direct kernels are built for 896 threads (72 registers); the
+                                      * split wide variant also for 1024 (64 registers, spill-free) */
+    }
     if (wide) {
         tile = std::max(1024u, tile & ~1023u); /* a warp-iteration covers 1 KiB */
     }
@@ -714,7 +719,7 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     pl->cfg.stride = stride;
     pl->cfg.queued = queued;
     pl->cfg.wide = wide;
-    pl->cfg.split = wide && g_opts.split && s->ringSplit;
+    pl->cfg.split = split;
     pl->cfg.grid = s->smCount;
     pl->cfg.warps = warps;
     pl->tileBytes = tile;

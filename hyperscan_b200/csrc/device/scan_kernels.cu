@@ -1489,13 +1489,14 @@ __global__ void __launch_bounds__(256) confirmKernel(const ScanParams p) {
 
 template <int KIND, int SB>
 cudaError_t launchWide(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
-    /* up to 24 warps the kernel is built for 768 threads (80 registers: the split
-     * variant's loop is spill-free there), above for 896 (72 registers) */
+    /* builds for 768 threads (80 registers), 896 (72) and, split variant only, 1024 (64) */
     void (*kern)(const ScanParams);
     if (cfg.warps <= 24) {
         kern = cfg.split ? scanKernelWide<KIND, SB, 1, 768> : scanKernelWide<KIND, SB, 0, 768>;
-    } else {
+    } else if (cfg.warps <= 28 || !cfg.split) {
         kern = cfg.split ? scanKernelWide<KIND, SB, 1, 896> : scanKernelWide<KIND, SB, 0, 896>;
+    } else {
+        kern = scanKernelWide<KIND, SB, 1, 1024>; /* split only: 64 registers, still no spills */
     }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smemBytes);
     if (e != cudaSuccess) {

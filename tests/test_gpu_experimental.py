@@ -28,6 +28,7 @@ VARIANTS = [
     {"wide": 1, "split": 1, "domain": 12, "replicas": 8},
     {"wide": 1, "split": 1, "initial_ring": 16},       # candidate list and ring overflow -> grow and rescan
     {"wide": 1, "split": 1, "warps": 24},               # the 768-thread build of the kernel
+    {"wide": 1, "split": 1, "warps": 32},               # the 1024-thread build
 ]
 
 

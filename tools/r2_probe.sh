@@ -11,9 +11,9 @@ O=gpurun_out
 tail -3 $O/r2_exp_tests.log
 
 python tools/sweep.py --mb 512 --reps 7 --configs \
-"queue=2;wide=1;wide=1,split=1;wide=1,split=1,warps=24;wide=1,domain=12,replicas=8;wide=1,split=1,domain=12,replicas=8;wide=1,split=1,domain=12,replicas=8,warps=24;wide=1,domain=12,replicas=4;wide=1,replicas=4;wide=1,warps=24;wide=1,pf_dist=4;wide=1,pf_dist=16;queue=1;domain=12,replicas=8,queue=1" \
+"queue=2;wide=1;wide=1,split=1;wide=1,split=1,warps=32;wide=1,split=1,warps=24;wide=1,domain=12,replicas=8;wide=1,split=1,domain=12,replicas=8;wide=1,split=1,domain=12,replicas=8,warps=32;wide=1,split=1,domain=12,replicas=8,warps=24;wide=1,domain=12,replicas=4;wide=1,replicas=4;wide=1,warps=24;wide=1,pf_dist=4;wide=1,pf_dist=16;queue=1;domain=12,replicas=8,queue=1" \
   > $O/r2_sweep_fdr1000.log 2>&1
-python tools/sweep.py --mb 512 --reps 7 --lits 48 --configs "queue=2;queue=0;wide=1;wide=1,split=1;wide=1,warps=24;wide=1,split=1,warps=24" > $O/r2_sweep_teddy48.log 2>&1
+python tools/sweep.py --mb 512 --reps 7 --lits 48 --configs "queue=2;queue=0;wide=1;wide=1,split=1;wide=1,warps=24;wide=1,split=1,warps=24;wide=1,split=1,warps=32" > $O/r2_sweep_teddy48.log 2>&1
 python tools/sweep.py --mb 512 --reps 7 --lits 1 --min-len 6 --max-len 6 --configs "queue=2;queue=0;wide=1" > $O/r2_sweep_noodle.log 2>&1
 python tools/sweep.py --mb 256 --reps 5 --lits 50000 --max-len 16 --configs "queue=2;queue=1;wide=1;first_stage=2,queue=1;first_stage=2,wide=1" > $O/r2_sweep_50k.log 2>&1
 cat $O/r2_sweep_*.log
