@@ -527,3 +527,31 @@ class StreamSet:
         if self.ptr:
             lib().hs_b200_streams_close(self.ptr)
             self.ptr = C.c_void_p()
+
+
+def test_program_base():
+    lib().hs_b200_test_program_base.restype = C.c_uint
+    return lib().hs_b200_test_program_base()
+
+
+def compile_programs(lits, nocase, prog_off, area, ekey_count=0, inv_dkey=()):
+    """hs_b200_test_compile_programs: pure-literal block database whose literal
+    programs are the raw instruction bytes in `area` (test hook)."""
+    n = len(lits)
+    lits = [bytes(x) for x in lits]
+    bufs = [C.create_string_buffer(x, len(x) + 1) for x in lits]
+    arr = (C.c_char_p * n)(*[C.cast(b, C.c_char_p) for b in bufs])
+    lens = (C.c_size_t * n)(*[len(x) for x in lits])
+    nc = (C.c_uint * n)(*[int(bool(x)) for x in nocase])
+    po = (C.c_uint * n)(*prog_off)
+    inv = (C.c_uint * max(1, len(inv_dkey)))(*inv_dkey)
+    db = C.c_void_p()
+    L = lib()
+    L.hs_b200_test_compile_programs.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t),
+                                                C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.c_uint,
+                                                C.c_char_p, C.c_size_t, C.c_uint, C.POINTER(C.c_uint),
+                                                C.c_uint, C.POINTER(C.c_void_p)]
+    area = bytes(area)
+    _check(L.hs_b200_test_compile_programs(arr, lens, nc, po, n, area, len(area), ekey_count, inv,
+                                           len(inv_dkey), C.byref(db)), "test_compile_programs")
+    return Database(db)

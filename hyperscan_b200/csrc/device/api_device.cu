@@ -325,6 +325,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     const u32 engOff = r->fmatcherOffset + HWLM_ENGINE_OFFSET;
     std::vector<u8> table;
     std::vector<LitTail> tails;
+    bool programsOk = true;
     if (hw->type == HWLM_ENGINE_NOOD) {
         /* single literal: one bucket, slots = the last <= 4 bytes of msk/cmp
          * (first char in the low byte: src/hwlm/noodle_build.cpp:100-118) */
@@ -350,7 +351,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
             }
             memcpy(&table[b * 4], &e, 4);
         }
-        collectProgramReports(bc, h->length, n.id, &im->exhaustible);
+        programsOk = collectProgramReports(bc, h->length, n.id, &im->exhaustible);
     } else if (hw->type == HWLM_ENGINE_FDR) {
         FDR f;
         memcpy(&f, bc + engOff, sizeof(f));
@@ -365,7 +366,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
             const size_t wideNeed = (size_t)entries * 8 + 48 * 1024;
-            walkConfirm(bc, h->length, im->confOff, 8, &im->exhaustible, &tails);
+            programsOk = walkConfirm(bc, h->length, im->confOff, 8, &im->exhaustible, &tails);
             double byteRate = 1;
             std::vector<u8> byteTab;
             if (g_opts.firstStage != 1) {
@@ -432,7 +433,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                     memcpy(&table[(b * oct + o) * 4], &e, 4);
                 }
             }
-            walkConfirm(bc, h->length, im->confOff, 8 * oct, &im->exhaustible, &tails);
+            programsOk = walkConfirm(bc, h->length, im->confOff, 8 * oct, &im->exhaustible, &tails);
         } else {
             delete im;
             return HS_INVALID;
@@ -440,6 +441,13 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     } else {
         delete im;
         return HS_INVALID;
+    }
+    if (!programsOk) {
+        /* a literal program uses a state-carrying opcode of roseRunProgram_l that
+         * the device interpreter does not implement (delayed literals, SOM,
+         * chained / logical reports): refuse here rather than mid-scan */
+        delete im;
+        return HS_ARCH_ERROR;
     }
     im->tableBytes = (u32)table.size();
     std::vector<u8> bitmap, bitmap2;

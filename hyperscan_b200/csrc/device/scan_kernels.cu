@@ -382,9 +382,6 @@ __device__ void runProgram(const ScanParams &p, const BlockRef &blk, u32 prog, u
         case OP_INCLUDED_JUMP: /* the child literal is confirmed on its own */
             NEXT(InstrIncludedJump);
             break;
-        case OP_SET_EXHAUST:
-            NEXT(InstrSetExhaust);
-            break;
         default:
             atomicExch(p.counters + CTR_ERROR, (u32)ERR_BAD_OPCODE);
             return;

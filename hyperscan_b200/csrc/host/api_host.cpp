@@ -1132,3 +1132,57 @@ extern "C" long hs_b200_test_build_hwlm(const char *const *lits, const size_t *l
         return -1;
     }
 }
+
+/* Test hook: a pure-literal block database whose literal programs are raw
+ * instruction bytes supplied by the caller (tests/test_programs.py assembles them
+ * from the layouts in src/rose/rose_program.h), so that every opcode of
+ * roseRunProgram_l can be reached on the device and by the reference runtime
+ * from the same bytes.  `area` lands at hs_b200_test_program_base() in the
+ * bytecode; prog_off[i] is literal i's program inside it. */
+extern "C" unsigned hs_b200_test_program_base(void) { return programAreaBase(); }
+
+extern "C" hs_error_t hs_b200_test_compile_programs(const char *const *lits, const size_t *lens,
+                                                    const unsigned *nocase, const unsigned *prog_off,
+                                                    unsigned n, const void *area, size_t area_len,
+                                                    unsigned ekey_count, const unsigned *inv_dkey,
+                                                    unsigned dkey_count, hs_database_t **db) {
+    if (!lits || !lens || !nocase || !prog_off || !area || !db || !n) {
+        return HS_INVALID;
+    }
+    try {
+        std::vector<HwlmLit> v;
+        for (unsigned i = 0; i < n; i++) {
+            HwlmLit l;
+            l.s.assign(lits[i], lens[i]);
+            l.nocase = nocase[i] != 0;
+            if (l.nocase) {
+                for (char &c : l.s) {
+                    c = (char)asciiUpper((u8)c);
+                }
+            }
+            l.id = prog_off[i];
+            l.groups = 1;
+            v.push_back(l);
+        }
+        CompileOpts opts;
+        opts.pureLiteralApi = true;
+        applyBuildOptions(&opts.hwlm);
+        if (opts.hwlm.allowFatTeddy) {
+            opts.platform &= ~PLATFORM_NOAVX2;
+        }
+        std::vector<u8> a((const u8 *)area, (const u8 *)area + area_len);
+        std::vector<u32> inv(inv_dkey ? inv_dkey : nullptr, inv_dkey ? inv_dkey + dkey_count : nullptr);
+        std::vector<u8> bc = buildRawProgramRose(v, a, ekey_count, inv, opts, nullptr);
+        hs_error_t aerr;
+        hs_database_t *out = dbCreate(bc, opts.platform, &aerr);
+        if (!out) {
+            return aerr;
+        }
+        *db = out;
+        return HS_SUCCESS;
+    } catch (const CompileError &) {
+        return HS_COMPILER_ERROR;
+    } catch (const std::exception &) {
+        return HS_COMPILER_ERROR;
+    }
+}

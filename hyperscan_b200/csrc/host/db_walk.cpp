@@ -8,46 +8,78 @@
 
 namespace hsb {
 
-void collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex) {
-    u32 pc = prog;
-    for (int guard = 0; guard < 4096 && pc < bcLen; guard++) {
+/* Linear walk over one literal program.  A program is a sequence of blocks, each
+ * ending in END or FINAL_REPORT; later blocks are reached through the fail_jump
+ * of a check in an earlier one (src/rose/rose_build_program.cpp:525-829), so
+ * the walk continues past a terminator while a jump target lies beyond it.
+ * Returns false on an opcode the device interpreter (scan_kernels.cu
+ * runProgram) does not implement -- the state-carrying ones of
+ * roseRunProgram_l: PUSH_DELAYED, CATCH_UP*, SOM_*, TRIGGER_SUFFIX, REPORT_CHAIN,
+ * REPORT_SOM*, SET_LOGICAL, SET_COMBINATION, FLUSH_COMBINATION, SET_EXHAUST. */
+bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex) {
+    u32 pc = prog, furthest = prog;
+    auto jump = [&](u32 from, u32 rel) { furthest = std::max(furthest, from + rel); };
+#define STEP(T) pc += (u32)HSB_ROUNDUP(sizeof(T), INSTR_ALIGN)
+#define STEP_JUMP(T)                                \
+    do {                                            \
+        T in;                                       \
+        memcpy(&in, bc + pc, sizeof(in));           \
+        jump(pc, in.fail_jump);                     \
+        STEP(T);                                    \
+    } while (0)
+    for (int guard = 0; guard < 65536; guard++) {
+        if (pc + 8 > bcLen) {
+            return false;
+        }
         const u8 code = bc[pc];
         switch (code) {
         case OP_END:
+            if (furthest <= pc) {
+                return true;
+            }
+            STEP(InstrEnd);
+            break;
         case OP_FINAL_REPORT:
-            return;
-        case OP_CHECK_GROUPS: pc += HSB_ROUNDUP(sizeof(InstrCheckGroups), 8); break;
-        case OP_CHECK_MASK: pc += HSB_ROUNDUP(sizeof(InstrCheckMask), 8); break;
-        case OP_CHECK_BYTE: pc += HSB_ROUNDUP(sizeof(InstrCheckByte), 8); break;
+            if (furthest <= pc) {
+                return true;
+            }
+            STEP(InstrFinalReport);
+            break;
+        case OP_CHECK_GROUPS: STEP(InstrCheckGroups); break;
+        case OP_CHECK_MASK: STEP_JUMP(InstrCheckMask); break;
+        case OP_CHECK_BYTE: STEP_JUMP(InstrCheckByte); break;
         case OP_CHECK_MED_LIT:
         case OP_CHECK_MED_LIT_NOCASE:
         case OP_CHECK_LONG_LIT:
-        case OP_CHECK_LONG_LIT_NOCASE: pc += HSB_ROUNDUP(sizeof(InstrCheckLit), 8); break;
-        case OP_CHECK_EXHAUSTED: pc += HSB_ROUNDUP(sizeof(InstrCheckExhausted), 8); break;
-        case OP_DEDUPE: pc += HSB_ROUNDUP(sizeof(InstrDedupe), 8); break;
-        case OP_REPORT: pc += HSB_ROUNDUP(sizeof(InstrReport), 8); break;
+        case OP_CHECK_LONG_LIT_NOCASE: STEP_JUMP(InstrCheckLit); break;
+        case OP_CHECK_EXHAUSTED: STEP_JUMP(InstrCheckExhausted); break;
+        case OP_DEDUPE: STEP_JUMP(InstrDedupe); break;
+        case OP_REPORT: STEP(InstrReport); break;
         case OP_REPORT_EXHAUST: {
             InstrReportExhaust in;
             memcpy(&in, bc + pc, sizeof(in));
             ex->insert(in.onmatch);
-            pc += HSB_ROUNDUP(sizeof(InstrReportExhaust), 8);
+            STEP(InstrReportExhaust);
             break;
         }
-        case OP_DEDUPE_AND_REPORT: pc += HSB_ROUNDUP(sizeof(InstrDedupeAndReport), 8); break;
-        case OP_SQUASH_GROUPS: pc += HSB_ROUNDUP(sizeof(InstrSquashGroups), 8); break;
-        case OP_CLEAR_WORK_DONE: pc += 8; break;
-        case OP_INCLUDED_JUMP: pc += HSB_ROUNDUP(sizeof(InstrIncludedJump), 8); break;
-        case OP_SET_EXHAUST: pc += HSB_ROUNDUP(sizeof(InstrSetExhaust), 8); break;
+        case OP_DEDUPE_AND_REPORT: STEP_JUMP(InstrDedupeAndReport); break;
+        case OP_SQUASH_GROUPS: STEP(InstrSquashGroups); break;
+        case OP_CLEAR_WORK_DONE: pc += INSTR_ALIGN; break;
+        case OP_INCLUDED_JUMP: STEP(InstrIncludedJump); break;
         default:
-            return;
+            return false;
         }
     }
+#undef STEP
+#undef STEP_JUMP
+    return false;
 }
 
 /* Walk the hash-confirm structures to enumerate literal programs
  * (src/fdr/fdr_confirm.h:36-94). */
-void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
+bool walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
                  std::unordered_set<u32> *ex, std::vector<LitTail> *tails) {
+    bool ok = true;
     const u8 *confBase = bc + confOff;
     for (u32 b = 0; b < nBuckets; b++) {
         u32 cf;
@@ -69,7 +101,7 @@ void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
             for (;;) {
                 LitInfo x;
                 memcpy(&x, li, sizeof(x));
-                collectProgramReports(bc, bcLen, x.id, ex);
+                ok &= collectProgramReports(bc, bcLen, x.id, ex);
                 tails->push_back({x.v, x.msk, x.size, b});
                 if (!x.next) {
                     break;
@@ -78,6 +110,7 @@ void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
             }
         }
     }
+    return ok;
 }
 
 hs_error_t collectExhaustible(const hs_database_t *db, std::unordered_set<u32> *ex) {
@@ -95,15 +128,13 @@ hs_error_t collectExhaustible(const hs_database_t *db, std::unordered_set<u32> *
     if (hw->type == HWLM_ENGINE_NOOD) {
         NoodTable n;
         memcpy(&n, bc + engOff, sizeof(n));
-        collectProgramReports(bc, h->length, n.id, ex);
-        return HS_SUCCESS;
+        return collectProgramReports(bc, h->length, n.id, ex) ? HS_SUCCESS : HS_ARCH_ERROR;
     }
     FDR f;
     memcpy(&f, bc + engOff, sizeof(f));
     const u32 nb = f.engineID == 0 ? 8 : teddyNumBuckets(f.engineID);
     std::vector<LitTail> tails;
-    walkConfirm(bc, h->length, engOff + f.confOffset, nb, ex, &tails);
-    return HS_SUCCESS;
+    return walkConfirm(bc, h->length, engOff + f.confOffset, nb, ex, &tails) ? HS_SUCCESS : HS_ARCH_ERROR;
 }
 
 size_t postprocessRecords(const std::unordered_set<u32> &exhaustible, MatchRec *m, size_t n) {

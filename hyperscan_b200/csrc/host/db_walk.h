@@ -28,9 +28,11 @@ struct MatchRec { /* == hs_b200_match_t */
     u64 to;
 };
 
-void collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex);
+/* Both return false if a program holds an opcode the device does not implement
+ * (callers refuse the database with HS_ARCH_ERROR instead of failing mid-scan). */
+bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex);
 
-void walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
+bool walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
                  std::unordered_set<u32> *ex, std::vector<LitTail> *tails);
 
 /** Reports compiled with HS_FLAG_SINGLEMATCH in a pure-literal database. */

@@ -78,6 +78,78 @@ u32 blockSize(const PatInfo &pi) {
     return sz;
 }
 
+/* What the header needs to know about the literal set. */
+struct RoseTail {
+    u32 minLen, maxLen, ekeyCount, dkeyCount, invDkeyOffset;
+    bool canExhaust;
+};
+
+/* Floating literal matcher + RoseEngine header around a finished program blob. */
+std::vector<u8> finishRose(Blob &blob, const std::vector<HwlmLit> &hl, const RoseTail &t,
+                           const CompileOpts &opts, HwlmBuildInfo *info) {
+    std::vector<u8> hwlm;
+    try {
+        hwlm = buildHwlm(hl, opts.hwlm, info);
+    } catch (const std::runtime_error &e) {
+        throw CompileError{std::string("Unable to build literal matcher: ") + e.what(), -1};
+    }
+    const u32 fmatcherOffset = blob.add(hwlm.data(), hwlm.size(), 64);
+    const u32 total = (u32)HSB_ROUNDUP(blob.base + blob.bytes.size(), 64);
+
+    /* --- header --- */
+    RoseEngine r;
+    memset(&r, 0, sizeof(r));
+    r.pureLiteral = opts.pureLiteralApi ? 1 : 0;
+    r.runtimeImpl = RUNTIME_PURE_LITERAL;
+    r.canExhaust = t.canExhaust ? 1 : 0;
+    /* src/rose/rose_build_bytecode.cpp:3615-3622 */
+    r.mode = !opts.streaming ? MODE_BLOCK : opts.vectored ? MODE_VECTORED : MODE_STREAM;
+    /* matches may start in earlier writes: keep the last maxLen-1 bytes
+     * (calcHistoryRequired, src/rose/rose_build_misc.cpp; updated by HWLM) */
+    const u32 historyRequired = opts.streaming && t.maxLen > 1 ? t.maxLen - 1 : 0;
+    r.historyRequired = historyRequired;
+    r.ekeyCount = t.ekeyCount;
+    r.dkeyCount = t.dkeyCount;
+    r.dkeyLogSize = fatbitSize(r.dkeyCount);
+    r.invDkeyOffset = t.invDkeyOffset;
+    r.somLocationFatbitSize = fatbitSize(0);
+    r.fmatcherOffset = fmatcherOffset;
+    r.fmatcherMinWidth = t.minLen;
+    r.activeQueueArraySize = fatbitSize(0);
+    r.handledKeyFatbitSize = fatbitSize(0);
+    r.minWidth = t.minLen;
+    r.minWidthExcludingBoundaries = t.minLen;
+    r.maxBiAnchoredWidth = ROSE_BOUND_INF;
+    r.floatingDistance = ROSE_BOUND_INF;
+    r.floatingMinLiteralMatchOffset = t.minLen;
+    r.initialGroups = 1;
+    r.floating_group_mask = 1;
+    r.size = total;
+    r.delay_fatbit_size = fatbitSize(0);
+    r.anchored_fatbit_size = fatbitSize(0);
+    r.totalNumLiterals = (u32)hl.size();
+    r.initMpvNfa = 0xffffffffu; /* MO_INVALID_IDX: no MPV outfix */
+    StateOffsets &so = r.stateOffsets;
+    u32 cur = 1;                 /* status byte; role multibit is empty */
+    so.activeLeafArray = so.activeLeftArray = so.longLitState = cur;
+    so.leftfixLagTable = so.anchorState = cur;
+    so.groups = cur;
+    so.groups_size = 1;
+    cur += so.groups_size;
+    so.history = cur;
+    cur += historyRequired;
+    so.exhausted = cur;
+    so.exhausted_size = mmbitSize(r.ekeyCount);
+    cur += so.exhausted_size;
+    so.logicalVec = so.combVec = cur;
+    so.nfaStateBegin = so.end = cur;
+
+    std::vector<u8> out(total, 0);
+    memcpy(out.data(), &r, sizeof(r));
+    memcpy(out.data() + blob.base, blob.bytes.data(), blob.bytes.size());
+    return out;
+}
+
 } // namespace
 
 std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
@@ -302,71 +374,52 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
         l.groups = 1;
         hl.push_back(l);
     }
-    std::vector<u8> hwlm;
-    try {
-        hwlm = buildHwlm(hl, opts.hwlm, info);
-    } catch (const std::runtime_error &e) {
-        throw CompileError{std::string("Unable to build literal matcher: ") + e.what(), -1};
-    }
-    const u32 fmatcherOffset = blob.add(hwlm.data(), hwlm.size(), 64);
-    const u32 total = (u32)HSB_ROUNDUP(blob.base + blob.bytes.size(), 64);
-
-    /* --- header --- */
-    RoseEngine r;
-    memset(&r, 0, sizeof(r));
-    r.pureLiteral = opts.pureLiteralApi ? 1 : 0;
-    r.runtimeImpl = RUNTIME_PURE_LITERAL;
-    r.canExhaust = allHighlander ? 1 : 0;
-    /* src/rose/rose_build_bytecode.cpp:3615-3622 */
-    r.mode = !opts.streaming ? MODE_BLOCK : opts.vectored ? MODE_VECTORED : MODE_STREAM;
     u32 maxLen = 0;
     for (const auto &pi : pats) {
         maxLen = std::max<u32>(maxLen, (u32)pi.folded.size());
     }
-    /* matches may start in earlier writes: keep the last maxLen-1 bytes
-     * (calcHistoryRequired, src/rose/rose_build_misc.cpp; updated by HWLM) */
-    const u32 historyRequired = opts.streaming && maxLen > 1 ? maxLen - 1 : 0;
-    r.historyRequired = historyRequired;
-    r.ekeyCount = (u32)ekeys.size();
-    r.dkeyCount = (u32)dkeys.size();
-    r.dkeyLogSize = fatbitSize(r.dkeyCount);
-    r.invDkeyOffset = invDkeyOffset;
-    r.somLocationFatbitSize = fatbitSize(0);
-    r.fmatcherOffset = fmatcherOffset;
-    r.fmatcherMinWidth = minLen;
-    r.activeQueueArraySize = fatbitSize(0);
-    r.handledKeyFatbitSize = fatbitSize(0);
-    r.minWidth = minLen;
-    r.minWidthExcludingBoundaries = minLen;
-    r.maxBiAnchoredWidth = ROSE_BOUND_INF;
-    r.floatingDistance = ROSE_BOUND_INF;
-    r.floatingMinLiteralMatchOffset = minLen;
-    r.initialGroups = 1;
-    r.floating_group_mask = 1;
-    r.size = total;
-    r.delay_fatbit_size = fatbitSize(0);
-    r.anchored_fatbit_size = fatbitSize(0);
-    r.totalNumLiterals = (u32)frags.size();
-    r.initMpvNfa = 0xffffffffu; /* MO_INVALID_IDX: no MPV outfix */
-    StateOffsets &so = r.stateOffsets;
-    u32 cur = 1;                 /* status byte; role multibit is empty */
-    so.activeLeafArray = so.activeLeftArray = so.longLitState = cur;
-    so.leftfixLagTable = so.anchorState = cur;
-    so.groups = cur;
-    so.groups_size = 1;
-    cur += so.groups_size;
-    so.history = cur;
-    cur += historyRequired;
-    so.exhausted = cur;
-    so.exhausted_size = mmbitSize(r.ekeyCount);
-    cur += so.exhausted_size;
-    so.logicalVec = so.combVec = cur;
-    so.nfaStateBegin = so.end = cur;
+    RoseTail t;
+    t.minLen = minLen;
+    t.maxLen = maxLen;
+    t.ekeyCount = (u32)ekeys.size();
+    t.dkeyCount = (u32)dkeys.size();
+    t.invDkeyOffset = invDkeyOffset;
+    t.canExhaust = allHighlander;
+    return finishRose(blob, hl, t, opts, info);
+}
 
-    std::vector<u8> out(total, 0);
-    memcpy(out.data(), &r, sizeof(r));
-    memcpy(out.data() + blob.base, blob.bytes.data(), blob.bytes.size());
-    return out;
+/* Test hook (hs_b200_test_compile_programs): a pure-literal block database whose
+ * literal programs are given as raw instruction bytes -- the way to reach every
+ * opcode of roseRunProgram_l (src/rose/program_runtime.c:3101-3522) that this
+ * compiler does not emit itself.  lits[i].id = offset of its program inside
+ * `area`, which is placed at programAreaBase(); absolute offsets inside the
+ * programs (lit_offset, child_offset) are the caller's business. */
+u32 programAreaBase() { return (u32)HSB_ROUNDUP(sizeof(RoseEngine), 64); }
+
+std::vector<u8> buildRawProgramRose(std::vector<HwlmLit> lits, const std::vector<u8> &area,
+                                    u32 ekeyCount, const std::vector<u32> &invDkey,
+                                    const CompileOpts &opts, HwlmBuildInfo *info) {
+    if (lits.empty()) {
+        throw CompileError{"Invalid parameter: elements is zero", -1};
+    }
+    Blob blob(programAreaBase());
+    blob.add(area.data(), area.size(), INSTR_ALIGN);
+    RoseTail t;
+    t.minLen = ~0u;
+    t.maxLen = 0;
+    for (HwlmLit &l : lits) {
+        if (l.s.empty() || l.s.size() > 8 || l.id >= area.size() || (l.id % INSTR_ALIGN)) {
+            throw CompileError{"bad literal or program offset", -1};
+        }
+        l.id += blob.base;
+        t.minLen = std::min<u32>(t.minLen, (u32)l.s.size());
+        t.maxLen = std::max<u32>(t.maxLen, (u32)l.s.size());
+    }
+    t.ekeyCount = ekeyCount;
+    t.dkeyCount = (u32)invDkey.size();
+    t.invDkeyOffset = invDkey.empty() ? 0 : blob.add(invDkey.data(), invDkey.size() * sizeof(u32), 4);
+    t.canExhaust = false;
+    return finishRose(blob, lits, t, opts, info);
 }
 
 } // namespace hsb

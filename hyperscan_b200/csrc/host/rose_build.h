@@ -46,5 +46,12 @@ static const size_t LIMIT_LITERAL_COUNT = 8000000;
 std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &pats,
                                  const CompileOpts &opts, HwlmBuildInfo *info);
 
+/** Test hook: pure-literal block database from raw literal programs (`area`
+ * is placed at programAreaBase(); lits[i].id = its program's offset in area). */
+u32 programAreaBase();
+std::vector<u8> buildRawProgramRose(std::vector<HwlmLit> lits, const std::vector<u8> &area,
+                                    u32 ekeyCount, const std::vector<u32> &invDkey,
+                                    const CompileOpts &opts, HwlmBuildInfo *info);
+
 } // namespace hsb
 #endif

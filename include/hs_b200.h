@@ -418,6 +418,19 @@ long hs_b200_test_build_hwlm(const char *const *lits, const size_t *lens,
                              const unsigned *ids, unsigned n, int engine, void *out,
                              size_t cap);
 
+/* Test hook: pure-literal block database whose literal programs are raw
+ * instruction bytes (layouts: src/rose/rose_program.h:214-724).  `area` is
+ * placed at bytecode offset hs_b200_test_program_base(); prog_off[i] = offset of
+ * literal i's program inside `area` (8-byte aligned).  Lets the tests reach every
+ * opcode of roseRunProgram_l (src/rose/program_runtime.c:3101-3522) on the device
+ * and on the unmodified reference runtime from the same bytes. */
+unsigned hs_b200_test_program_base(void);
+hs_error_t hs_b200_test_compile_programs(const char *const *lits, const size_t *lens,
+                                         const unsigned *nocase, const unsigned *prog_off,
+                                         unsigned n, const void *area, size_t area_len,
+                                         unsigned ekey_count, const unsigned *inv_dkey,
+                                         unsigned dkey_count, hs_database_t **db);
+
 /* Runtime tunables (process-wide; also HSB200_* environment variables):
  * "warps" per CTA, "tile_bytes", "stages" (TMA ring depth per warp),
  * "wide_fdr" (1: use all 8 FDR suffix slots), "stride" (first-stage sampling

@@ -288,8 +288,10 @@ static int run_program_l(struct scan *s, u32 prog, u64 end) {
             break;
         }
         case OP_FINAL_REPORT:
-            deliver_report(s, end, rd32(pc + 4), rds32(pc + 8), 0xffffffffu);
-            return 0; /* "one-shot specialisation: this pattern will never match again" */
+            /* "One-shot specialisation: this instruction always terminates execution
+             * of the program" -- of the PROGRAM, matching goes on
+             * (src/rose/program_runtime.c:3349-3358) */
+            return deliver_report(s, end, rd32(pc + 4), rds32(pc + 8), 0xffffffffu) ? 1 : 0;
         case OP_SQUASH_GROUPS: /* {u8; u64 groups}: groups &= mask */
             s->groups &= rd64(pc + 8);
             pc += 16;

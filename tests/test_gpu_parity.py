@@ -16,8 +16,8 @@ def _sorted(recs):
     return np.sort(np.asarray(recs), order=["block", "to", "id"])
 
 
-def _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=True):
-    db = hs.compile_lit_multi(lits, flags, ids)
+def _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=True, platform=None):
+    db = hs.compile_lit_multi(lits, flags, ids, platform=platform)
     scratch = hs.Scratch(db)
     want = ref.scan_sorted(db.ptr, data, off, ln)
     if use_brute:
@@ -47,6 +47,38 @@ def test_engines_random_blocks(hs, ref, nlits, engine):
                                          2049, 4096, 10000, 65536 + 5], lits, seed=3,
                                         alphabet=b"abcdefghABCDxy")
     _check_all(hs, ref, lits, flags, ids, data, off, ln)
+
+
+def _avx2(hs):
+    import ctypes as C
+    return C.byref(hs.PlatformInfo(0, hs.HS_CPU_FEATURES_AVX2, 0, 0))
+
+
+@pytest.mark.parametrize("nlits,lo,hi", [(49, 2, 8), (64, 3, 12), (90, 3, 8), (96, 4, 12)])
+def test_fat_teddy_16_buckets(hs, ref, nlits, lo, hi):
+    """Databases compiled for an AVX2 platform carry 16-bucket ("fat") Teddy
+    (engine ids 3..10, src/fdr/teddy_avx2.c:395-447): the device runs them
+    through the FK_BYTE64 first stage (two u32 lookups per byte)."""
+    if ref.best_isa() == "corei7":
+        pytest.skip("the reference build on this host has no fat Teddy")
+    lits, flags, ids = synth.literal_set(nlits, min_len=lo, max_len=hi, seed=90 + nlits, caseless_frac=0.2,
+                                         alphabet=b"abcdefgh")
+    data, off, ln = synth.ragged_corpus([0, 1, 3, 15, 16, 17, 33, 100, 511, 512, 513, 1024, 2049, 4096, 20000,
+                                         65536 + 5], lits, seed=2, alphabet=b"abcdefghABCDxy", plant_per_kb=4)
+    db, want = _check_all(hs, ref, lits, flags, ids, data, off, ln, platform=_avx2(hs))
+    assert 3 <= db.info().engine_id <= 10, db.info().engine_id
+    assert want.size > 100
+    # the opt-in staging / queue variants of the same first stage
+    try:
+        for opts in ({"queue": 0}, {"direct": 0, "warps": 8, "tile_bytes": 2048, "stages": 3}):
+            for k, v in opts.items():
+                hs.set_runtime_option(k, v)
+            _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False, platform=_avx2(hs))
+            for k, v in (("queue", 2), ("direct", 1), ("warps", 32), ("tile_bytes", 1024), ("stages", 2)):
+                hs.set_runtime_option(k, v)
+    finally:
+        for k, v in (("queue", 2), ("direct", 1), ("warps", 32), ("tile_bytes", 1024), ("stages", 2)):
+            hs.set_runtime_option(k, v)
 
 
 def test_large_literal_set_two_level_prefilter(hs, ref):

@@ -11,8 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_restated_layouts_match_reference(tmp_path):
     exe = str(tmp_path / "layout_check")
-    subprocess.run(["g++", "-std=c++17", "-o", exe,
-                    os.path.join(ROOT, "hyperscan_b200", "csrc", "layout_check.cpp")], check=True)
+    subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "hyperscan_b200", "csrc"), "-o", exe,
+                    os.path.join(ROOT, "tests", "layout_check.cpp")], check=True)
     ours = json.loads(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
     with open(os.path.join(ROOT, "tests", "golden", "ref_layout.json")) as f:
         gold = json.load(f)

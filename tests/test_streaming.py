@@ -126,12 +126,20 @@ def test_device_stream_termination_copy_reset(hs, ref):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nl,wlen", [(40, 64), (300, 1024), (1, 33)])
-def test_stream_set_equals_per_stream_reference(hs, ref, nl, wlen):
-    """hs_b200_streams_scan (state in HBM) == one reference stream per stream."""
+@pytest.mark.parametrize("nl,wlen,fat", [(40, 64, 0), (300, 1024, 0), (1, 33, 0), (80, 200, 1)])
+def test_stream_set_equals_per_stream_reference(hs, ref, nl, wlen, fat):
+    """hs_b200_streams_scan (state in HBM) == one reference stream per stream.
+    fat: compiled for an AVX2 platform -> 16-bucket Teddy (FK_BYTE64 first stage)."""
     lits, flags, ids = synth.literal_set(nl, min_len=2, max_len=8, seed=nl + 7, caseless_frac=0.2,
                                          alphabet=b"abcdef")
-    db = hs.compile_lit_multi(lits, flags, ids, mode=hs.HS_MODE_STREAM)
+    plat = None
+    if fat:
+        if ref.best_isa() == "corei7":
+            pytest.skip("the reference build on this host has no fat Teddy")
+        plat = C.byref(hs.PlatformInfo(0, hs.HS_CPU_FEATURES_AVX2, 0, 0))
+    db = hs.compile_lit_multi(lits, flags, ids, mode=hs.HS_MODE_STREAM, platform=plat)
+    if fat:
+        assert 3 <= db.info().engine_id <= 10
     scratch = hs.Scratch(db)
     nstreams = 257
     sset = hs.StreamSet(db, nstreams)
