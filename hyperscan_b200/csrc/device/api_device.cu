@@ -30,6 +30,7 @@
 
 #include "../host/api_internal.h"
 #include "../host/db_walk.h"
+#include "../host/pair_table.h"
 #include "kernels.h"
 
 using namespace hsb;
@@ -62,9 +63,10 @@ struct RuntimeOpts {
                               * built at the end of round 1, not yet measured */
     int split = 0;           /* 1 (with wide): scan kernel stops at the prefilter, confirmKernel finishes the
                               * candidates from a list in HBM (second half of the record ring) */
-    int firstStage = 1;      /* FDR databases: 1 = two-byte hash table (FK_HASH32), 2 = per-byte table
-                              * (FK_BYTE32, conflict-free lookups, more candidates), 0 = choose by the
-                              * modelled candidate rate of the per-byte table */
+    int firstStage = 3;      /* FDR databases: 3 = class-pair tables (FK_PAIR32: two conflict-free lookups per
+                              * byte), 1 = two-byte hash table (FK_HASH32, ~3.3-way bank conflicts), 2 = per-byte
+                              * table (FK_BYTE32, conflict-free, many more candidates), 0 = choose between 1
+                              * and 2 by the modelled candidate rate of the per-byte table */
     int chunkMB = 128;       /* host->device pipeline granularity */
     int initialRing = 1 << 20;
 };
@@ -134,7 +136,7 @@ struct DevImage {
  * the hash confirm in HBM/L2 is only reached by ~1% of the first stage's false
  * positives.  Returns an empty vector when the set cannot be keyed usefully. */
 std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u32 *shift,
-                            std::vector<u8> *level2 = nullptr, u32 *shift2 = nullptr) {
+                            std::vector<u8> *level2 = nullptr, u32 *shift2 = nullptr, u32 fixedLg = 0) {
     std::vector<u8> bm;
     if (tails.empty()) {
         return bm;
@@ -164,6 +166,9 @@ std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u3
     u32 lg = 13; /* 8 Kbit .. 512 Kbit (64 KB), ~256 bits per key when possible */
     while (lg < 19 && (1ull << lg) < (u64)keys.size() * 256) {
         lg++;
+    }
+    if (fixedLg) {
+        lg = fixedLg; /* FK_PAIR32: exactly the 32 KB that fit the class rows' upper halves */
     }
     bm.assign((size_t)1 << (lg - 3), 0);
     for (u32 k : keys) {
@@ -375,6 +380,19 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
             if (g_opts.wideFdr && wideNeed <= (size_t)maxSmem) {
                 im->kind = FK_HASH64;
                 table.assign(src, src + (size_t)entries * 8);
+            } else if (g_opts.firstStage == 3) {
+                u32 minSize = 8;
+                for (const LitTail &t : tails) {
+                    minSize = std::min(minSize, t.size);
+                }
+                im->kind = FK_PAIR32;
+                im->stride = 1;
+                im->slotBase = minSize >= 2 ? 1 : 0;
+                PairTables pt;
+                buildPairTables(tails, (u32)im->slotBase, &pt);
+                table.resize(sizeof(pt.classWord) + sizeof(pt.pair));
+                memcpy(table.data(), pt.classWord, sizeof(pt.classWord));
+                memcpy(table.data() + sizeof(pt.classWord), pt.pair, sizeof(pt.pair));
             } else if (g_opts.firstStage == 2 || (g_opts.firstStage == 0 && byteRate < 0.01)) {
                 im->kind = FK_BYTE32;
                 im->stride = 1;
@@ -452,7 +470,8 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     im->tableBytes = (u32)table.size();
     std::vector<u8> bitmap, bitmap2;
     if (g_opts.prefilter) {
-        bitmap = buildBitmap(tails, &im->keyBytes, &im->bitmapShift, &bitmap2, &im->bitmap2Shift);
+        bitmap = buildBitmap(tails, &im->keyBytes, &im->bitmapShift, &bitmap2, &im->bitmap2Shift,
+                             im->kind == FK_PAIR32 ? 18u : 0u);
     }
     im->bitmapBytes = (u32)bitmap.size();
     cudaError_t e = cudaMalloc(&im->d_bc, HSB_ROUNDUP(h->length, 16));
@@ -602,7 +621,7 @@ hs_error_t findImage(hs_scratch *s, const hs_database_t *db, const DevImage **ou
 
 hs_error_t growRing(hs_scratch *s, u32 cap) {
     initOpts();
-    const bool split = g_opts.split != 0;
+    const bool split = true; /* second half = candidate list of the split kernels (FK_PAIR32 always) */
     if (cap <= s->outCap && (s->ringSplit || !split)) {
         return HS_SUCCESS;
     }
@@ -688,6 +707,30 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     if ((g_opts.stride == 1 || g_opts.stride == 2 || g_opts.stride == 4) &&
         (im->kind == FK_HASH32 || im->kind == FK_HASH64)) {
         stride = g_opts.stride; /* any sampling subset is a sound filter */
+    }
+    if (im->kind == FK_PAIR32) {
+        /* class-pair kernel: direct loads, stride 1, queued candidates, split confirm;
+         * as many warps as the queues leave room for (896 threads x 72 registers at most) */
+        warps = std::min(warps, 28);
+        while (warps > 1 && scanSmemBytes(FK_PAIR32, 0, 0, 0, 0, 0, warps) > (size_t)s->maxSmem) {
+            warps--;
+        }
+        pl->cfg.smemBytes = scanSmemBytes(FK_PAIR32, 0, 0, 0, 0, 0, warps);
+        if (pl->cfg.smemBytes > (size_t)s->maxSmem || !s->ringSplit) {
+            return HS_NOMEM;
+        }
+        pl->cfg.kind = im->kind;
+        pl->cfg.slotBase = im->slotBase;
+        pl->cfg.direct = 1;
+        pl->cfg.stride = 1;
+        pl->cfg.queued = 1;
+        pl->cfg.wide = 0;
+        pl->cfg.split = 1;
+        pl->cfg.grid = s->smCount;
+        pl->cfg.warps = warps;
+        pl->tileBytes = tile;
+        pl->nstages = (u32)std::max(0, std::min(64, g_opts.pfDist));
+        return HS_SUCCESS;
     }
     const bool byteKind = im->kind == FK_BYTE32 || im->kind == FK_BYTE64;
     const int wide = g_opts.wide && direct && stride == 1 && (im->kind == FK_BYTE32 || im->kind == FK_HASH32);

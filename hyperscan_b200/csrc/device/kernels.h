@@ -19,10 +19,15 @@
     hsb_emu::launch(dim3(grid), dim3(block), smem, [=]() { kern(__VA_ARGS__); })
 #define HSB_DYNAMIC_SMEM(name) u8 *name = hsb_emu::dynamicSmem()
 #define HSB_NOINLINE __attribute__((noinline))
+#define HSB_GRID_CONSTANT
 #else
 #define HSB_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #define HSB_DYNAMIC_SMEM(name) extern __shared__ __align__(128) u8 name[]
 #define HSB_NOINLINE __noinline__
+/* kernel parameters whose address is taken (passed by reference into the out-of-line
+ * candidate path) stay in the constant bank instead of being copied to every
+ * thread's stack */
+#define HSB_GRID_CONSTANT __grid_constant__
 #endif
 
 namespace hsb {
@@ -46,6 +51,10 @@ enum FilterKind {
     FK_BYTE64 = 1, /* index = 1 byte; 2 x u32 (4 slots x 16 buckets). Fat Teddy */
     FK_HASH32 = 2, /* index = 2-byte FDR hash; u32 entry (slots 0..3 of FDR) */
     FK_HASH64 = 3, /* index = 2-byte FDR hash; u64 entry (all 8 FDR slots)   */
+    FK_PAIR32 = 4, /* index = (class of byte 0, class of byte 1), 5 bits each, classes
+                      from a per-lane byte table; u32 entry; both tables replicated per
+                      lane (bank-conflict free).  FDR sets.  Table image: 256 class words
+                      (c0 << 7 | c1 << 12), then 1024 pair entries; bitmapBytes = 32 KB or 0 */
 };
 
 enum ConfirmKind {

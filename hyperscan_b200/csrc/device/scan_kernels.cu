@@ -661,7 +661,17 @@ __device__ __forceinline__ u64 confValAt(const ScanParams &p, u64 g) {
  * the word before the lane's 16 bytes.  Per candidate byte: hash the last
  * keyBytes bytes into the prefilter bitmap (shared memory); only survivors pay
  * for the hash confirm in HBM/L2. */
-template <int NOCT, int SPLIT>
+/* First-level prefilter bitmap word holding bit `hsh`.  HOLES (class-pair kernel):
+ * the 32 KB bitmap lives in the unused upper halves of the 256-byte class rows,
+ * word i at row i >> 5, byte 128 + 4 * (i & 31). */
+template <int HOLES> __device__ __forceinline__ u32 bitmapWord(u32 bitmapAddr, u32 hsh) {
+    if (HOLES) {
+        return lds32(bitmapAddr + ((hsh >> 10) << 8) + ((hsh >> 3) & 0x7cu));
+    }
+    return lds32(bitmapAddr + ((hsh >> 5) << 2));
+}
+
+template <int NOCT, int SPLIT, int HOLES = 0>
 __device__ __forceinline__ void laneCandidatesBody(const ScanParams &p, u32 bitmapAddr, u32 c00, u32 c01,
                                                    u32 c02, u32 c03, u32 c10, u32 c11, u32 c12, u32 c13,
                                                    u32 w0, u32 w1, u32 w2, u32 w3, u32 pw, u64 g0,
@@ -697,7 +707,7 @@ __device__ __forceinline__ void laneCandidatesBody(const ScanParams &p, u32 bitm
             const u32 last4 = q == 3 ? cur : __funnelshift_r(prv, cur, 8 * (q + 1));
             const u32 key = last4 >> (8 * (4 - p.keyBytes));
             const u32 hsh = (key * 0x9E3779B1u) >> p.bitmapShift;
-            if (!((lds32(bitmapAddr + ((hsh >> 5) << 2)) >> (hsh & 31)) & 1)) {
+            if (!((bitmapWord<HOLES>(bitmapAddr, hsh) >> (hsh & 31)) & 1)) {
                 continue; /* no literal of any bucket ends here */
             }
             if (p.bitmap2Shift) {
@@ -895,7 +905,7 @@ __device__ __forceinline__ void haloStep(const ScanParams &p, const uint4 v, u32
 }
 
 template <int KIND, int STRIDE, int SB, int DIRECT, int QUEUED>
-__global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const ScanParams p) {
+__global__ void __launch_bounds__(DIRECT ? 896 : 1024, 1) scanKernel(const HSB_GRID_CONSTANT ScanParams p) {
     static_assert(!QUEUED || DIRECT, "the candidate queue reads chunks back from the corpus (direct mode)");
     HSB_DYNAMIC_SMEM(smem);
     typedef Kind<KIND> K;
@@ -1273,7 +1283,7 @@ __device__ HSB_NOINLINE void drainWide(const ScanParams &p, u32 bitmapAddr, u32 
 }
 
 template <int KIND, int SB, int SPLIT, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const ScanParams p) {
+__global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const HSB_GRID_CONSTANT ScanParams p) {
     static_assert(KIND == FK_BYTE32 || KIND == FK_HASH32, "wide steps: 8-bucket tables only");
     HSB_DYNAMIC_SMEM(smem);
     const u32 lane = threadIdx.x & 31;
@@ -1450,9 +1460,245 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const ScanParams p) {
     }
 }
 
+/* ---- class-pair variant (FK_PAIR32): conflict-free two-byte first stage -------------
+ *
+ * The FDR hash lookup costs ~3.3 shared-memory wavefronts (random 4-byte gather of
+ * 32 lanes into 32 banks; replicas only help once every lane has its own copy).
+ * A copy per lane needs a table of <= 1024 entries, i.e. a 10-bit key for the two
+ * bytes: each byte is first mapped to a 5-bit CLASS by a per-lane byte table
+ * (conflict free, like the Teddy rows), two classes index a per-lane pair table
+ * (conflict free): 2 wavefronts per input byte instead of 3.3, for a candidate
+ * rate of the same order (the classes are chosen for the literal set on the host:
+ * bytes that no literal uses share one class, api_device.cu buildPairTables).
+ *
+ *   class row b (256 B): [lane l: c0(b) << 7 | c1(b) << 12 | l << 2] x 32 | 128 B of the
+ *                        first-level prefilter bitmap (32 KB in the 256 rows' upper halves)
+ *   pair row (c1 << 5 | c0) (128 B): [u32 entry: 4 slots x 8 buckets] x 32 lanes
+ *
+ * so the pair address is ONE logic op of the two class words and every lookup is
+ * PRMT/LOP3 + LDS.  Sample at x = bytes (x, x+1) keyed (c0(byte x), c1(byte x+1));
+ * entry byte i says which buckets cannot END at x + i + SB (as FK_HASH32).
+ * Candidates: per-warp queue -> prefilter bitmaps -> candidate list in HBM ->
+ * confirmKernel (always "split": the hot kernel carries no confirm code). */
+
+struct PairQueue {
+    static constexpr u32 SLOTS = 64;                      /* < 32 pending + <= 32 appended per step */
+    static constexpr u32 CHUNK = 16 * SLOTS;              /* u32 chunk[SLOTS] after uint4 cand[SLOTS] */
+    static constexpr u32 RUN_START = CHUNK + 4 * SLOTS;   /* u64: corpus position of the run's chunk 0 */
+    static constexpr u32 WARP_BYTES = RUN_START + 16;
+};
+enum { PAIR_CLASS_BYTES = 256 * 256, PAIR_TABLE_BYTES = 1024 * 128 };
+
+/* Row offset in the pair table: l << 2 | c0 << 7 from the first byte's class word,
+ * c1 << 12 from the second's -- bit-field select (a & 0xfff) | (b & ~0xfff), ONE
+ * LOP3 (left to itself the compiler emits and / and / add3). */
+__device__ __forceinline__ u32 pairIndex(u32 a, u32 b) {
+#ifdef HSB_HOST_EMU
+    return (a & 0xfffu) | (b & ~0xfffu);
+#else
+    u32 d;
+    asm("lop3.b32 %0, %1, %2, 0xfff, 0xE4;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+#endif
+}
+
+/* Shift-OR contributions of one lane's 16 positions: w[0..3] the lane's bytes,
+ * w[4] the word after them.  a[0..3]: own end positions, a[4]: overflow into the
+ * next lane (bit set = bucket impossible). */
+template <int SB>
+__device__ __forceinline__ void pairFilter(const u32 (&w)[5], u32 clsAddr, u32 laneOff, u32 (&a)[6]) {
+    u32 E[17];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            E[4 * k + r] = lds32(clsAddr + __byte_perm(w[k], laneOff, 0x5504 + (r << 4)));
+        }
+    }
+    E[16] = lds32(clsAddr + __byte_perm(w[4], laneOff, 0x5504));
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        a[i] = 0;
+    }
+    const u32 pairAddr = clsAddr + PAIR_CLASS_BYTES;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        u32 P[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            /* l << 2 | c0(x) << 7 from the first byte's word, c1(x + 1) << 12 from the second's */
+            P[k] = lds32(pairAddr + pairIndex(E[4 * k + r], E[4 * k + r + 1]));
+        }
+        if (r + SB == 0) orStream<0>(a, P);
+        if (r + SB == 1) orStream<1>(a, P);
+        if (r + SB == 2) orStream<2>(a, P);
+        if (r + SB == 3) orStream<3>(a, P);
+        if (r + SB == 4) orStream<4>(a, P);
+    }
+}
+
+__device__ HSB_NOINLINE void drainPair(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
+                                          u32 count, u32 lane, u32 *stats) {
+    if (lane >= count) {
+        return;
+    }
+    const uint2 rs = lds64(qAddr + PairQueue::RUN_START);
+    const u64 runStart = ((u64)rs.y << 32) | rs.x;
+    const uint4 c = lds128(qAddr + (first + lane) * 16);
+    const u64 g0 = runStart + (u64)lds32(qAddr + PairQueue::CHUNK + (first + lane) * 4) * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g0 + 16 <= p.readableEnd) {
+        v = __ldg(reinterpret_cast<const uint4 *>(p.corpus + g0));
+    }
+    const u32 pw = g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u;
+    laneCandidatesBody<1, 1, 1>(p, bitmapAddr, c.x, c.y, c.z, c.w, 0, 0, 0, 0, v.x, v.y, v.z, v.w, pw, g0,
+                                stats);
+}
+
+template <int SB, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTANT ScanParams p) {
+    HSB_DYNAMIC_SMEM(smem);
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5;
+    const u32 nwarps = blockDim.x >> 5;
+
+    /* expand the tables: p.table = 256 class words, then 1024 pair entries */
+    {
+        const u32 *g = reinterpret_cast<const u32 *>(p.table);
+        const u32 *bm = reinterpret_cast<const u32 *>(p.bitmap);
+        u32 *s = reinterpret_cast<u32 *>(smem);
+        for (u32 i = threadIdx.x; i < 256 * 64; i += blockDim.x) {
+            const u32 row = i >> 6, l = i & 31;
+            if ((i >> 5) & 1) {
+                s[i] = p.bitmapBytes ? __ldg(bm + row * 32 + l) : 0u;
+            } else {
+                s[i] = __ldg(g + row) | (l << 2);
+            }
+        }
+        u32 *sp = s + 256 * 64;
+        for (u32 i = threadIdx.x; i < 1024 * 32; i += blockDim.x) {
+            sp[i] = __ldg(g + 256 + (i >> 5));
+        }
+    }
+    __syncthreads();
+
+    const u32 clsAddr = smemAddr(smem);
+    const u32 bitmapAddr = clsAddr + 128;
+    const u32 laneOff = lane * 4;
+    const u32 qAddr = clsAddr + PAIR_CLASS_BYTES + PAIR_TABLE_BYTES + warp * PairQueue::WARP_BYTES;
+
+    /* this warp's contiguous run of tiles */
+    const u32 gwarp = blockIdx.x * nwarps + warp;
+    const u32 totalWarps = gridDim.x * nwarps;
+    const u32 q = p.ntiles / totalWarps, rem = p.ntiles % totalWarps;
+    const u32 myCount = q + (gwarp < rem ? 1u : 0u);
+    const u32 myFirst = p.tileFirst + gwarp * q + min(gwarp, rem);
+    if (myCount == 0) {
+        return;
+    }
+    const u64 runStart = (u64)myFirst * p.tileBytes;
+    u64 runEnd = runStart + (u64)myCount * p.tileBytes;
+    if (runEnd > p.corpusBytes) {
+        runEnd = p.corpusBytes;
+    }
+    const u32 nsteps = (u32)((runEnd - runStart + 511) >> 9);
+    const u8 *ptr = p.corpus + runStart + lane * 16; /* this lane's 16 bytes of the current step */
+    const u8 *const endPtr = p.corpus + p.readableEnd;
+    if (lane == 0) {
+        sts64(qAddr + PairQueue::RUN_START, (u32)runStart, (u32)(runStart >> 32));
+    }
+
+    u32 carry = 0; /* lane 31's overflow of the previous step */
+    u32 stats[3] = {0, 0, 0};
+    u32 qn = 0;
+
+    auto load = [&](const u8 *src, bool guard) -> uint4 {
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (!guard || src + 16 <= endPtr) {
+            r = ldCs128(src);
+        }
+        return r;
+    };
+    const size_t pfBytes = (size_t)p.nstages * 512 + lane * 48; /* even lanes: 16 x 128 B, 2 KiB */
+    uint4 nxt = load(ptr, true);
+    if (runStart != 0) {
+        /* state entering the run: the 16 bytes before it, as "lane -1" */
+        const uint4 hv = __ldg(reinterpret_cast<const uint4 *>(p.corpus + runStart - 16));
+        const u32 hw[5] = {hv.x, hv.y, hv.z, hv.w, __shfl_sync(0xffffffffu, nxt.x, 0)};
+        u32 ha[6];
+        pairFilter<SB>(hw, clsAddr, laneOff, ha);
+        carry = ha[4];
+    }
+    u32 step = 0;
+    auto body = [&](const bool guard) {
+        const uint4 cur = nxt;
+        nxt = load(ptr + 512, guard);
+        if ((step & 3) == 0 && (lane & 1) == 0) {
+            const u8 *pf = ptr + pfBytes;
+            if (pf < endPtr) {
+                prefetchL2(pf);
+            }
+        }
+        /* the word after the lane's 16 bytes: one rotate shuffle in which lane 0
+         * offers the NEXT step's first word (for lane 31) */
+        const u32 w4 = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, (lane + 1) & 31);
+        const u32 w[5] = {cur.x, cur.y, cur.z, cur.w, w4};
+        u32 a[6];
+        pairFilter<SB>(w, clsAddr, laneOff, a);
+        {
+            u32 in = __shfl_sync(0xffffffffu, a[4], (lane + 31) & 31);
+            if (lane == 0) {
+                const u32 next = in;
+                in = carry;
+                carry = next;
+            }
+            a[0] |= in;
+        }
+        const u32 c0 = ~a[0], c1 = ~a[1], c2 = ~a[2], c3 = ~a[3];
+        const u32 any = c0 | c1 | c2 | c3;
+        const u32 bal = __ballot_sync(0xffffffffu, any != 0);
+        if (bal) {
+            if (any) {
+                const u32 e = qn + __popc(bal & ((1u << lane) - 1));
+                sts128(qAddr + e * 16, c0, c1, c2, c3);
+                sts32(qAddr + PairQueue::CHUNK + e * 4, step * 32 + lane);
+            }
+            qn += __popc(bal);
+            if (qn >= 32) {
+                __syncwarp();
+                qn -= 32;
+                drainPair(p, bitmapAddr, qAddr, qn, 32, lane, stats);
+                __syncwarp();
+            }
+        }
+    };
+    /* the load issued in iteration `step` fetches step + 1: no bounds check while
+     * that whole step is readable for every lane */
+    const u64 readableSteps = (p.readableEnd - runStart) >> 9;
+    const u32 nFast = readableSteps >= (u64)nsteps + 1 ? nsteps : (readableSteps ? (u32)readableSteps - 1 : 0);
+#pragma unroll 1
+    for (; step < nFast; step++, ptr += 512) {
+        body(false);
+    }
+#pragma unroll 1
+    for (; step < nsteps; step++, ptr += 512) {
+        body(true);
+    }
+    if (qn) {
+        __syncwarp();
+        drainPair(p, bitmapAddr, qAddr, 0, qn, lane, stats);
+    }
+    if (stats[0]) {
+        atomicAdd(p.counters + CTR_CANDIDATES, stats[0]);
+    }
+    if (stats[1]) {
+        atomicAdd(p.counters + CTR_PREFILTER_PASS, stats[1]);
+    }
+}
+
 /* Split mode, second kernel: one thread per candidate of the list the scan
  * kernel filled -- hash confirm, block lookup, literal program, record. */
-__global__ void __launch_bounds__(256) confirmKernel(const ScanParams p) {
+__global__ void __launch_bounds__(256) confirmKernel(const HSB_GRID_CONSTANT ScanParams p) {
     const u32 total = p.counters[CTR_CANDQ];
     const u32 n = total < p.outCap ? total : p.outCap;
     if (total > p.outCap && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1503,6 +1749,16 @@ cudaError_t launchWide(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t s
     return cudaGetLastError();
 }
 
+template <int SB> cudaError_t launchPair(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    void (*kern)(const ScanParams) = cfg.warps <= 24 ? scanKernelPair<SB, 768> : scanKernelPair<SB, 896>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smemBytes);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    HSB_LAUNCH(kern, cfg.grid, cfg.warps * 32, cfg.smemBytes, stream, p);
+    return cudaGetLastError();
+}
+
 template <int KIND, int STRIDE, int SB, int DIRECT, int QUEUED>
 cudaError_t launchOne(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
     void (*kern)(const ScanParams) = scanKernel<KIND, STRIDE, SB, DIRECT, QUEUED>;
@@ -1540,6 +1796,9 @@ cudaError_t launchStride(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t
 
 size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 nstages,
                      u32 tileBytes, int queueWarps) {
+    if (kind == FK_PAIR32) { /* class rows (bitmap in their upper halves) + pair table + queues */
+        return (size_t)PAIR_CLASS_BYTES + PAIR_TABLE_BYTES + (size_t)queueWarps * PairQueue::WARP_BYTES;
+    }
     const size_t perWarp = queueWarps < 0          ? WideQueue::WARP_BYTES /* wide-step variant */
                            : kind == FK_BYTE64     ? QueueEntry<2>::WARP_BYTES
                                                    : QueueEntry<1>::WARP_BYTES;
@@ -1638,6 +1897,12 @@ cudaError_t launchPublishCount(const ScanParams &p, cudaStream_t stream) {
 }
 
 cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    if (cfg.kind == FK_PAIR32) {
+        if (!cfg.split || cfg.warps > 28) {
+            return cudaErrorInvalidValue;
+        }
+        return cfg.slotBase ? launchPair<1>(cfg, p, stream) : launchPair<0>(cfg, p, stream);
+    }
     if (cfg.wide) {
         if (!cfg.direct || cfg.stride != 1 || (p.tileBytes & 1023)) {
             return cudaErrorInvalidValue;
