@@ -122,6 +122,28 @@ struct DevImage {
     size_t deviceBytes = 0;
 };
 
+/* A scratch (and a corpus / stream set) is bound to the CUDA device that was current
+ * when it was created: its streams, events, record ring and database images live
+ * there.  The reference lets any thread use any scratch, and a fresh thread's current
+ * device is 0, so every entry point that touches one switches to its device for the
+ * duration of the call and restores the caller's. */
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            switched = cudaSetDevice(dev) == cudaSuccess;
+        }
+    }
+    ~DeviceGuard() {
+        if (switched) {
+            cudaSetDevice(prev);
+        }
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
 #define CUDA_TRY(expr)                                                                     \
     do {                                                                                   \
         cudaError_t e__ = (expr);                                                          \
@@ -609,6 +631,7 @@ hs_error_t findImage(hs_scratch *s, const hs_database_t *db, const DevImage **ou
             return HS_SUCCESS;
         }
     }
+    DeviceGuard guard(s->device); /* the image is allocated on the scratch's device */
     DevImage *im = nullptr;
     hs_error_t r = buildImage(db, &im);
     if (r != HS_SUCCESS) {
@@ -626,6 +649,7 @@ hs_error_t growRing(hs_scratch *s, u32 cap) {
         return HS_SUCCESS;
     }
     cap = std::max(cap, s->outCap);
+    DeviceGuard guard(s->device);
     DevMatch *n = nullptr;
     CUDA_TRY(cudaMalloc(&n, (size_t)cap * sizeof(DevMatch) * (split ? 2 : 1)));
     cudaFree(s->d_out);
@@ -647,6 +671,7 @@ void freeCorpus(hs_b200_corpus *c) {
 
 /* (Re)size a corpus handle's device buffers (grow-only). */
 hs_error_t reserveCorpus(hs_b200_corpus *c, u64 dataBytes, size_t nblocks) {
+    DeviceGuard guard(c->device);
     const size_t need = FRONT_PAD + HSB_ROUNDUP(dataBytes, 16) + 64;
     if (need > c->capData) {
         cudaFree(c->d_alloc);
@@ -1126,6 +1151,7 @@ hs_error_t hs_alloc_scratch(const hs_database_t *db, hs_scratch_t **scratch) {
         }
         s->in_use = 1;
     }
+    DeviceGuard guard(s->device);
     const DevImage *im = nullptr;
     r = findImage(s, db, &im);
     unmarkInUse(s);
@@ -1144,6 +1170,7 @@ hs_error_t hs_clone_scratch(const hs_scratch_t *src, hs_scratch_t **dest) {
         return HS_INVALID;
     }
     *dest = nullptr;
+    DeviceGuard guard(src->device); /* the clone lives on the source's device */
     hs_scratch *s = nullptr;
     hs_error_t r = newScratch(&s);
     if (r != HS_SUCCESS) {
@@ -1191,6 +1218,7 @@ hs_error_t hs_free_scratch(hs_scratch_t *s) {
     if (markInUse(s)) {
         return HS_SCRATCH_IN_USE;
     }
+    DeviceGuard guard(s->device);
     s->magic = 0;
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->images) {
@@ -1417,6 +1445,7 @@ hs_error_t hs_b200_scan_corpus_async(const hs_database_t *db, const hs_b200_corp
     if (markInUse(scratch)) {
         return HS_SCRATCH_IN_USE;
     }
+    DeviceGuard guard(scratch->device);
     const DevImage *im = nullptr;
     r = findImage(scratch, db, &im);
     if (r == HS_SUCCESS) {
@@ -1441,6 +1470,7 @@ hs_error_t hs_b200_scan_corpus_finish(hs_scratch_t *scratch, unsigned long long 
     if (!scratch || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
         return HS_INVALID;
     }
+    DeviceGuard guard(scratch->device);
     u32 count = scratch->lastCount;
     if (scratch->pending) {
         hs_error_t r = finishScan(scratch, &count);
@@ -1452,7 +1482,8 @@ hs_error_t hs_b200_scan_corpus_finish(hs_scratch_t *scratch, unsigned long long 
         *nrecords = count;
     }
     if (d_records) {
-        *d_records = scratch->d_out;
+        /* on overflow the ring is reallocated below: hand out no pointer */
+        *d_records = count > scratch->outCap ? nullptr : scratch->d_out;
     }
     if (count > scratch->outCap) {
         /* ring overflowed: grow so that a re-run succeeds */
@@ -1544,6 +1575,7 @@ hs_error_t hs_b200_export_records_async(hs_scratch_t *scratch, void *d_dst, size
     if (!scratch || !d_dst || !d_count || (uintptr_t)scratch % 64 || scratch->magic != SCRATCH_MAGIC) {
         return HS_INVALID;
     }
+    DeviceGuard guard(scratch->device);
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : scratch->stream;
     const size_t n = std::min<size_t>(cap, scratch->outCap);
     if (n) {
@@ -1558,6 +1590,7 @@ hs_error_t hs_b200_copy_records(hs_scratch_t *scratch, void *d_dst, size_t cap) 
     if (!scratch || !d_dst || scratch->pending) {
         return HS_INVALID;
     }
+    DeviceGuard guard(scratch->device);
     const size_t n = std::min<size_t>(cap, std::min<u32>(scratch->lastCount, scratch->outCap));
     if (n) {
         /* the records are final once evDone fired (finish waited for it); use
@@ -1576,6 +1609,7 @@ hs_error_t hs_b200_fetch_matches(const hs_database_t *db, hs_scratch_t *scratch,
     if (!scratch || !db || scratch->pending) {
         return HS_INVALID;
     }
+    DeviceGuard guard(scratch->device);
     const DevImage *im = nullptr;
     hs_error_t r = findImage(scratch, db, &im);
     if (r != HS_SUCCESS) {
@@ -1614,6 +1648,7 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
                                  size_t nblocks, std::vector<DevMatch> *matches,
                                  bool countOnly = false) {
     static const bool trace = getenv("HSB200_TRACE") != nullptr;
+    DeviceGuard guard(s->device); /* every host-buffer scan (hs_scan, hs_b200_scan_blocks, streams) ends up here */
     const double t0 = nowMs();
     double tLayout = 0, tEnq = 0, tWait = 0, tRec = 0;
     hs_b200_corpus *c = s->inlineCorpus;
@@ -2285,6 +2320,7 @@ hs_error_t hs_b200_streams_close(hs_b200_stream_set_t *s) {
     if (!s) {
         return HS_SUCCESS;
     }
+    DeviceGuard guard(s->device);
     cudaFree(s->d_hist);
     cudaFree(s->d_offset);
     cudaFree(s->d_len);
@@ -2301,6 +2337,10 @@ static hs_error_t streamsScanImpl(hs_b200_stream_set_t *set, const char *data,
     hs_scratch *s = scratch;
     const size_t n = set->nstreams;
     hs_error_t r = HS_SUCCESS;
+    if (s->device != set->device) {
+        return HS_INVALID; /* the set's state and the scratch's ring must share a device */
+    }
+    DeviceGuard guard(set->device);
     do {
         const DevImage *im = nullptr;
         r = findImage(s, set->db, &im);
@@ -2367,6 +2407,10 @@ static hs_error_t streamsScanImpl(hs_b200_stream_set_t *set, const char *data,
             e = cudaMemsetAsync(s->d_counters, 0, CTR_COUNT * sizeof(u32), st);
             if (e == cudaSuccess) e = cudaEventRecord(s->evStart, st);
             if (e == cudaSuccess) e = launchScan(cfg, p, st);
+            if (e == cudaSuccess && cfg.split) {
+                e = launchConfirm(cfg, p, st); /* candidate list -> records (counters were just cleared) */
+                g_launches++;
+            }
             if (e == cudaSuccess) e = cudaEventRecord(s->evStop, st);
             if (e == cudaSuccess) {
                 e = cudaMemcpyAsync(s->h_counters, s->d_counters, CTR_COUNT * sizeof(u32),

@@ -1630,38 +1630,27 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
         carry = ha[4];
     }
     u32 step = 0;
-    auto body = [&](const bool guard) {
-        const uint4 cur = nxt;
-        nxt = load(ptr + 512, guard);
-        if ((step & 3) == 0 && (lane & 1) == 0) {
-            const u8 *pf = ptr + pfBytes;
-            if (pf < endPtr) {
-                prefetchL2(pf);
-            }
-        }
-        /* the word after the lane's 16 bytes: one rotate shuffle in which lane 0
-         * offers the NEXT step's first word (for lane 31) */
-        const u32 w4 = __shfl_sync(0xffffffffu, lane == 0 ? nxt.x : cur.x, (lane + 1) & 31);
+    u32 prevRecv = carry;
+    /* one 512-byte step: cur = the lane's 16 bytes, nextFirst = first word of the NEXT
+     * step (lane 0 hands it to lane 31 in the rotate shuffle) */
+    auto compute = [&](const uint4 cur, const u32 nextFirst, const u32 chunk) {
+        const u32 w4 = __shfl_sync(0xffffffffu, lane == 0 ? nextFirst : cur.x, (lane + 1) & 31);
         const u32 w[5] = {cur.x, cur.y, cur.z, cur.w, w4};
         u32 a[6];
         pairFilter<SB>(w, clsAddr, laneOff, a);
-        {
-            u32 in = __shfl_sync(0xffffffffu, a[4], (lane + 31) & 31);
-            if (lane == 0) {
-                const u32 next = in;
-                in = carry;
-                carry = next;
-            }
-            a[0] |= in;
-        }
-        const u32 c0 = ~a[0], c1 = ~a[1], c2 = ~a[2], c3 = ~a[3];
-        const u32 any = c0 | c1 | c2 | c3;
-        const u32 bal = __ballot_sync(0xffffffffu, any != 0);
+        /* ONE rotate-by-one shuffle: lanes 1..31 receive their left neighbour's
+         * overflow, lane 0 receives lane 31's = the carry into the NEXT step */
+        const u32 recv = __shfl_sync(0xffffffffu, a[4], (lane + 31) & 31);
+        a[0] |= lane == 0 ? prevRecv : recv;
+        prevRecv = recv;
+        /* a zero bit anywhere = candidate: test the AND of the four words */
+        const u32 all = a[0] & a[1] & a[2] & a[3];
+        const u32 bal = __ballot_sync(0xffffffffu, all != 0xffffffffu);
         if (bal) {
-            if (any) {
+            if (all != 0xffffffffu) {
                 const u32 e = qn + __popc(bal & ((1u << lane) - 1));
-                sts128(qAddr + e * 16, c0, c1, c2, c3);
-                sts32(qAddr + PairQueue::CHUNK + e * 4, step * 32 + lane);
+                sts128(qAddr + e * 16, ~a[0], ~a[1], ~a[2], ~a[3]);
+                sts32(qAddr + PairQueue::CHUNK + e * 4, chunk);
             }
             qn += __popc(bal);
             if (qn >= 32) {
@@ -1672,17 +1661,36 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
             }
         }
     };
-    /* the load issued in iteration `step` fetches step + 1: no bounds check while
-     * that whole step is readable for every lane */
+    /* the load issued for step s fetches step s + 1: no bounds check while that whole
+     * step is readable for every lane -- everywhere but at the very end of the corpus */
     const u64 readableSteps = (p.readableEnd - runStart) >> 9;
     const u32 nFast = readableSteps >= (u64)nsteps + 1 ? nsteps : (readableSteps ? (u32)readableSteps - 1 : 0);
+    /* main loop: four steps per iteration (loads at immediate offsets, no register
+     * moves between steps) and ONE L2 prefetch of the 2 KiB that lie pfDist steps ahead
+     * (even lanes, 16 x 128 B) */
 #pragma unroll 1
-    for (; step < nFast; step++, ptr += 512) {
-        body(false);
+    for (; step + 4 <= nFast; step += 4, ptr += 2048) {
+        if ((lane & 1) == 0) {
+            const u8 *pf = ptr + pfBytes;
+            if (pf < endPtr) {
+                prefetchL2(pf);
+            }
+        }
+        const uint4 v0 = nxt;
+        const uint4 v1 = ldCs128(ptr + 512);
+        compute(v0, v1.x, step * 32 + lane);
+        const uint4 v2 = ldCs128(ptr + 1024);
+        compute(v1, v2.x, step * 32 + 32 + lane);
+        const uint4 v3 = ldCs128(ptr + 1536);
+        compute(v2, v3.x, step * 32 + 64 + lane);
+        nxt = ldCs128(ptr + 2048);
+        compute(v3, nxt.x, step * 32 + 96 + lane);
     }
 #pragma unroll 1
     for (; step < nsteps; step++, ptr += 512) {
-        body(true);
+        const uint4 cur = nxt;
+        nxt = load(ptr + 512, step >= nFast);
+        compute(cur, nxt.x, step * 32 + lane);
     }
     if (qn) {
         __syncwarp();

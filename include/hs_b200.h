@@ -431,6 +431,15 @@ hs_error_t hs_b200_test_compile_programs(const char *const *lits, const size_t *
                                          unsigned ekey_count, const unsigned *inv_dkey,
                                          unsigned dkey_count, hs_database_t **db);
 
+/* Device binding.  A scratch owns CUDA streams, events, the match-record ring and
+ * the device images of its databases on the CUDA device that was current when
+ * hs_alloc_scratch created it (hs_clone_scratch: the source's device); corpus handles and
+ * stream sets name their device explicitly.  Like the reference (src/hs_runtime.h:530-541:
+ * any thread may use any scratch, one scan at a time), every entry point switches to
+ * the object's device for the duration of the call and restores the caller's current
+ * device, so a thread whose current device differs -- e.g. a fresh thread, device 0 --
+ * can scan with a scratch that lives on another GPU. */
+
 /* Runtime tunables (process-wide; also HSB200_* environment variables):
  * "warps" per CTA, "tile_bytes", "stages" (TMA ring depth per warp),
  * "wide_fdr" (1: use all 8 FDR suffix slots), "stride" (first-stage sampling

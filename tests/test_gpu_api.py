@@ -125,3 +125,39 @@ def test_unaligned_and_gapped_host_layouts(hs, ref):
         scratch = hs.Scratch(db)
         got = np.sort(hs.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
         assert np.array_equal(got, ref.scan_sorted(db.ptr, data, off, ln))
+
+
+def test_scratch_is_usable_from_a_thread_with_another_current_device(hs, ref, real_gpu):
+    """A scratch is bound to the device it was allocated on; a thread whose current
+    CUDA device differs (a fresh thread starts on device 0) must still be able to
+    scan with it -- the library switches devices inside the call and restores the
+    caller's (round-1 advisor finding).  Needs two GPUs for the interesting case;
+    on one GPU it still checks the cross-thread use."""
+    import threading
+    import numpy as np
+    import torch
+    from hyperscan_b200 import synth
+    ndev = torch.cuda.device_count()
+    dev = ndev - 1
+    torch.cuda.set_device(dev)
+    lits, flags, ids = synth.literal_set(200, seed=5)
+    data, off, ln, _ = synth.block_corpus(64, 1024, lits, plant_per_kb=1.0, seed=6)
+    db = hs.compile_lit_multi(lits, flags, ids)
+    scratch = hs.Scratch(db)                      # lives on device `dev`
+    want = ref.scan_sorted(db.ptr, data, off, ln)
+    out = {}
+
+    def worker():
+        torch.cuda.set_device(0)                  # what a fresh thread has anyway
+        out["recs"] = np.sort(hs.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
+        rc, m = hs.scan(db, bytes(data[:1024]), scratch)
+        out["rc"] = rc
+        out["dev"] = torch.cuda.current_device()
+
+    t = threading.Thread(target=worker)
+    t.start()
+    t.join()
+    assert np.array_equal(out["recs"], want)
+    assert out["rc"] == hs.HS_SUCCESS and out["dev"] == 0
+    scratch.free()
+    torch.cuda.set_device(0)
