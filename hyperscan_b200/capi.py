@@ -123,6 +123,7 @@ def lib():
         L.hs_copy_stream.argtypes = [C.POINTER(vp), vp]
         L.hs_reset_and_copy_stream.argtypes = [vp, vp, vp, MATCH_CB, vp]
         L.hs_b200_scan_blocks.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, BLOCK_CB, vp, u64p]
+        L.hs_b200_scan_blocks_collect.argtypes = [vp, vp, vp, vp, C.c_size_t, vp, vp, C.c_size_t, u64p]
         L.hs_b200_corpus_upload.argtypes = [vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
         L.hs_b200_corpus_wrap.argtypes = [vp, C.c_size_t, vp, vp, C.c_size_t, C.c_int, C.POINTER(vp)]
         L.hs_b200_corpus_free.argtypes = [vp]
@@ -333,6 +334,19 @@ def scan_blocks(db, data, offsets, lengths, scratch, collect=True):
                                    scratch.ptr, BLOCK_CB(cb), None, C.byref(n))
     _check(rc, "hs_b200_scan_blocks")
     return np.array(recs, dtype=MATCH_DTYPE) if recs else np.zeros(0, dtype=MATCH_DTYPE)
+
+
+def scan_blocks_collect(db, data, offsets, lengths, scratch, out):
+    """hs_b200_scan_blocks_collect() on HOST buffers: the delivered matches, ordered
+    by (block, to, id), land in the caller's MATCH_DTYPE array `out`; returns the
+    count (grows nothing: HsError HS_INSUFFICIENT_SPACE if `out` is too small)."""
+    a = _as_u8(data)
+    off, ln = _blocks(offsets, lengths)
+    n = C.c_ulonglong()
+    rc = lib().hs_b200_scan_blocks_collect(db.ptr, a.ctypes.data, off.ctypes.data, ln.ctypes.data, off.size,
+                                           scratch.ptr, out.ctypes.data, out.size, C.byref(n))
+    _check(rc, "hs_b200_scan_blocks_collect")
+    return int(n.value)
 
 
 class Corpus:

@@ -44,7 +44,8 @@ std::atomic<unsigned long long> g_launches{0};
 
 /* runtime tunables (hs_b200_set_runtime_option / HSB200_* environment) */
 struct RuntimeOpts {
-    int warps = 32;          /* clamped to 28 in direct mode (896 threads x 72 registers) */
+    int warps = 0;           /* per CTA; 0 = what measured best for the kernel (28 in direct mode: 896
+                              * threads x 72 registers; 32 with TMA staging) */
     int tileBytes = 1024;
     int stages = 2;
     int wideFdr = 0;         /* 1: use all 8 FDR slots (u64 entries) when they fit */
@@ -59,14 +60,18 @@ struct RuntimeOpts {
     int queue = 2;           /* candidates go through the per-warp shared-memory queue: 0 never, 1 always,
                               * 2 for the per-byte tables (Teddy, noodle: measured +15 %) but not for the
                               * FDR hash table, whose kernel is shared-memory bound either way */
-    int wide = 0;            /* 1: wide-step kernel (32-byte lanes, always queued) for FK_BYTE32 / FK_HASH32;
-                              * built at the end of round 1, not yet measured */
-    int split = 0;           /* 1 (with wide): scan kernel stops at the prefilter, confirmKernel finishes the
+    int wide = 1;            /* 1: wide-step kernel (32-byte lanes, always queued) for FK_BYTE32 / FK_HASH32.
+                              * Measured with split=1 and 28 warps: Teddy-48 4.14 TB/s against 3.08 for the
+                              * 16-byte queued kernel, noodle 4.43 against 3.19 (profiles/r02_*) */
+    int split = 1;           /* 1 (with wide): scan kernel stops at the prefilter, confirmKernel finishes the
                               * candidates from a list in HBM (second half of the record ring) */
     int firstStage = 3;      /* FDR databases: 3 = class-pair tables (FK_PAIR32: two conflict-free lookups per
                               * byte), 1 = two-byte hash table (FK_HASH32, ~3.3-way bank conflicts), 2 = per-byte
                               * table (FK_BYTE32, conflict-free, many more candidates), 0 = choose between 1
                               * and 2 by the modelled candidate rate of the per-byte table */
+    int bigSet = 1;          /* FK_PAIR32: sets that would overfill the 32 KiB bitmap trade classes of the
+                              * second byte for a large contiguous bitmap */
+    int bigSetClasses = 4;   /* ... classes left to the second byte (pair table = 4 KiB each) */
     int chunkMB = 128;       /* host->device pipeline granularity */
     int initialRing = 1 << 20;
 };
@@ -87,7 +92,8 @@ void initOpts() {
         {"HSB200_DIRECT", &g_opts.direct},     {"HSB200_REPLICAS", &g_opts.replicas},
         {"HSB200_PF_DIST", &g_opts.pfDist},    {"HSB200_QUEUE", &g_opts.queue},
         {"HSB200_FIRST_STAGE", &g_opts.firstStage}, {"HSB200_WIDE", &g_opts.wide},
-        {"HSB200_SPLIT", &g_opts.split}};
+        {"HSB200_SPLIT", &g_opts.split},       {"HSB200_BIG_SET", &g_opts.bigSet},
+        {"HSB200_BIG_SET_CLASSES", &g_opts.bigSetClasses}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -106,6 +112,7 @@ struct DevImage {
     u32 tableBytes = 0;
     u8 *d_bitmap = nullptr;
     u32 bitmapBytes = 0, bitmapShift = 0, keyBytes = 0;
+    u32 pairBytes = 0, bitmapHoles = 0, bitmapBits = 0; /* FK_PAIR32 layout (kernels.h) */
     u8 *d_bitmap2 = nullptr; /* second level (HBM / L2) for large literal sets */
     u32 bitmap2Shift = 0;
     int kind = FK_BYTE32;
@@ -158,7 +165,7 @@ struct DeviceGuard {
  * the hash confirm in HBM/L2 is only reached by ~1% of the first stage's false
  * positives.  Returns an empty vector when the set cannot be keyed usefully. */
 std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u32 *shift,
-                            std::vector<u8> *level2 = nullptr, u32 *shift2 = nullptr, u32 fixedLg = 0) {
+                            std::vector<u8> *level2 = nullptr, u32 *shift2 = nullptr) {
     std::vector<u8> bm;
     if (tails.empty()) {
         return bm;
@@ -189,9 +196,6 @@ std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u3
     while (lg < 19 && (1ull << lg) < (u64)keys.size() * 256) {
         lg++;
     }
-    if (fixedLg) {
-        lg = fixedLg; /* FK_PAIR32: exactly the 32 KB that fit the class rows' upper halves */
-    }
     bm.assign((size_t)1 << (lg - 3), 0);
     for (u32 k : keys) {
         const u32 h = (k * 0x9E3779B1u) >> (32 - lg);
@@ -214,6 +218,62 @@ std::vector<u8> buildBitmap(const std::vector<LitTail> &tails, u32 *keyBytes, u3
         *shift2 = 32 - lg2;
     }
     return bm;
+}
+
+/* Keys of the prefilter bitmaps: every literal's last m <= 4 bytes with the
+ * don't-care bits of LitInfo.msk enumerated.  false = cannot be keyed usefully. */
+bool tailKeys(const std::vector<LitTail> &tails, u32 *keyBytes, std::vector<u32> *keys) {
+    if (tails.empty()) {
+        return false;
+    }
+    u32 m = 4;
+    for (const LitTail &t : tails) {
+        m = std::min(m, t.size);
+    }
+    if (m < 2) {
+        return false;
+    }
+    for (const LitTail &t : tails) {
+        const u32 v = (u32)(t.v >> 32) >> (8 * (4 - m));
+        const u32 care = (u32)(t.msk >> 32) >> (8 * (4 - m));
+        const u32 full = m == 4 ? 0xffffffffu : (1u << (8 * m)) - 1;
+        const u32 dc = ~care & full;
+        if (__builtin_popcount(dc) > 10) {
+            return false;
+        }
+        u32 sub = 0;
+        do {
+            keys->push_back((v & care) | sub);
+            sub = (sub - dc) & dc;
+        } while (sub);
+    }
+    *keyBytes = m;
+    return true;
+}
+
+/* FK_PAIR32 bitmaps: first level of `bits` bits (index = mulhi(key * K, bits)) in
+ * shared memory, second level (~1024 bits per key, <= 64 MB) in HBM / L2 when the
+ * first is more than ~3 % full. */
+void buildPairBitmaps(const std::vector<u32> &keys, u32 bits, std::vector<u8> *level1,
+                      std::vector<u8> *level2, u32 *shift2) {
+    level1->assign((size_t)(bits + 31) / 32 * 4, 0);
+    for (u32 k : keys) {
+        const u32 h = (u32)(((u64)(k * 0x9E3779B1u) * bits) >> 32);
+        (*level1)[h >> 3] |= (u8)(1u << (h & 7));
+    }
+    *shift2 = 0;
+    if (keys.size() * 32 > bits) {
+        u32 lg2 = 20;
+        while (lg2 < 29 && (1ull << lg2) < (u64)keys.size() * 1024) {
+            lg2++;
+        }
+        level2->assign((size_t)1 << (lg2 - 3), 0);
+        for (u32 k : keys) {
+            const u32 h = (k * 0x85EBCA6Bu) >> (32 - lg2);
+            (*level2)[h >> 3] |= (u8)(1u << (h & 7));
+        }
+        *shift2 = 32 - lg2;
+    }
 }
 
 /* First-stage table rebuilt from the literal tails (LitInfo v/msk) and their
@@ -350,7 +410,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     im->hasDedupe = r->dkeyCount != 0;
     const HWLM *hw = (const HWLM *)(bc + r->fmatcherOffset);
     const u32 engOff = r->fmatcherOffset + HWLM_ENGINE_OFFSET;
-    std::vector<u8> table;
+    std::vector<u8> table, pairBitmap, pairBitmap2;
     std::vector<LitTail> tails;
     bool programsOk = true;
     if (hw->type == HWLM_ENGINE_NOOD) {
@@ -410,11 +470,34 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                 im->kind = FK_PAIR32;
                 im->stride = 1;
                 im->slotBase = minSize >= 2 ? 1 : 0;
+                /* shared memory: 64 KiB class rows + pair table + (large sets) bitmap +
+                 * queues.  Small sets: 32 x 32 classes (128 KiB pair table), the 32 KiB
+                 * bitmap in the class rows' upper halves.  Sets whose keys would fill that
+                 * bitmap beyond ~10 %: the pair filter is saturated anyway, so the second
+                 * byte gets few classes and the freed space a large contiguous bitmap. */
+                std::vector<u32> keys;
+                u32 kb = 0;
+                const bool keyed = g_opts.prefilter && tailKeys(tails, &kb, &keys);
+                const bool big = keyed && keys.size() * 10 > 262144 && g_opts.bigSet != 0;
                 PairTables pt;
-                buildPairTables(tails, (u32)im->slotBase, &pt);
+                buildPairTables(tails, (u32)im->slotBase, &pt, 32, big ? (u32)std::max(1, g_opts.bigSetClasses) : 32);
+                im->pairBytes = pt.nClass1 * 4096;
                 table.resize(sizeof(pt.classWord) + sizeof(pt.pair));
                 memcpy(table.data(), pt.classWord, sizeof(pt.classWord));
                 memcpy(table.data() + sizeof(pt.classWord), pt.pair, sizeof(pt.pair));
+                if (keyed) {
+                    im->keyBytes = kb;
+                    im->bitmapHoles = big ? 0 : 1;
+                    u32 bits = 262144;
+                    if (big) {
+                        /* everything the pair table and 27 queues leave of the 227 KiB */
+                        const u32 queues = (u32)scanSmemBytes(FK_PAIR32, 0, 0, 0, 0, 0, 27) - 65536u;
+                        const u32 room = (u32)maxSmem - 65536u - im->pairBytes - queues;
+                        bits = (room & ~127u) * 8;
+                    }
+                    im->bitmapBits = bits;
+                    buildPairBitmaps(keys, bits, &pairBitmap, &pairBitmap2, &im->bitmap2Shift);
+                }
             } else if (g_opts.firstStage == 2 || (g_opts.firstStage == 0 && byteRate < 0.01)) {
                 im->kind = FK_BYTE32;
                 im->stride = 1;
@@ -491,9 +574,11 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     }
     im->tableBytes = (u32)table.size();
     std::vector<u8> bitmap, bitmap2;
-    if (g_opts.prefilter) {
-        bitmap = buildBitmap(tails, &im->keyBytes, &im->bitmapShift, &bitmap2, &im->bitmap2Shift,
-                             im->kind == FK_PAIR32 ? 18u : 0u);
+    if (im->kind == FK_PAIR32) {
+        bitmap.swap(pairBitmap);
+        bitmap2.swap(pairBitmap2);
+    } else if (g_opts.prefilter) {
+        bitmap = buildBitmap(tails, &im->keyBytes, &im->bitmapShift, &bitmap2, &im->bitmap2Shift);
     }
     im->bitmapBytes = (u32)bitmap.size();
     cudaError_t e = cudaMalloc(&im->d_bc, HSB_ROUNDUP(h->length, 16));
@@ -724,7 +809,7 @@ struct ScanPlan {
 hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     initOpts();
     const int direct = g_opts.direct ? 1 : 0;
-    int warps = std::max(1, std::min(32, g_opts.warps));
+    int warps = g_opts.warps > 0 ? std::min(32, g_opts.warps) : (direct ? 28 : 32);
     u32 tile = (u32)std::max(512, g_opts.tileBytes) & ~511u;
     u32 stages = (u32)std::max(2, std::min(8, g_opts.stages));
     /* shrink until the table + staging fit the opt-in shared memory */
@@ -736,11 +821,12 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     if (im->kind == FK_PAIR32) {
         /* class-pair kernel: direct loads, stride 1, queued candidates, split confirm;
          * as many warps as the queues leave room for (896 threads x 72 registers at most) */
+        const u32 contiguous = im->bitmapHoles ? 0 : im->bitmapBytes;
         warps = std::min(warps, 28);
-        while (warps > 1 && scanSmemBytes(FK_PAIR32, 0, 0, 0, 0, 0, warps) > (size_t)s->maxSmem) {
+        while (warps > 1 && scanSmemBytes(FK_PAIR32, im->pairBytes, contiguous, 0, 0, 0, warps) > (size_t)s->maxSmem) {
             warps--;
         }
-        pl->cfg.smemBytes = scanSmemBytes(FK_PAIR32, 0, 0, 0, 0, 0, warps);
+        pl->cfg.smemBytes = scanSmemBytes(FK_PAIR32, im->pairBytes, contiguous, 0, 0, 0, warps);
         if (pl->cfg.smemBytes > (size_t)s->maxSmem || !s->ringSplit) {
             return HS_NOMEM;
         }
@@ -823,6 +909,9 @@ void fillParams(const hs_scratch *s, const DevImage *im, const hs_b200_corpus *c
     p->repShift = im->repShift;
     p->bitmap = im->d_bitmap;
     p->bitmapBytes = im->bitmapBytes;
+    p->pairBytes = im->pairBytes;
+    p->bitmapHoles = im->bitmapHoles;
+    p->bitmapBits = im->bitmapBits;
     p->bitmapShift = im->bitmapShift;
     p->keyBytes = im->keyBytes;
     p->bitmap2 = (const u32 *)im->d_bitmap2;
@@ -1036,7 +1125,8 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"direct", &g_opts.direct},     {"replicas", &g_opts.replicas},
         {"pf_dist", &g_opts.pfDist},    {"queue", &g_opts.queue},
         {"first_stage", &g_opts.firstStage}, {"wide", &g_opts.wide},
-        {"split", &g_opts.split}};
+        {"split", &g_opts.split},       {"big_set", &g_opts.bigSet},
+        {"big_set_classes", &g_opts.bigSetClasses}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;
@@ -1841,6 +1931,40 @@ hs_error_t hs_b200_scan_blocks(const hs_database_t *db, const char *data,
     }
     if (nmatches) {
         *nmatches = delivered;
+    }
+    unmarkInUse(scratch);
+    return r;
+}
+
+hs_error_t hs_b200_scan_blocks_collect(const hs_database_t *db, const char *data,
+                                       const unsigned long long *offsets, const unsigned int *lengths,
+                                       size_t nblocks, hs_scratch_t *scratch, hs_b200_match_t *out,
+                                       size_t cap, unsigned long long *nmatches) {
+    if (!scratch || (nblocks && (!data || !offsets || !lengths)) || nblocks > 0xfffffff0u || (cap && !out)) {
+        return HS_INVALID;
+    }
+    hs_error_t r = checkScanArgs(db, scratch);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    if (markInUse(scratch)) {
+        return HS_SCRATCH_IN_USE;
+    }
+    const DevImage *im = nullptr;
+    r = findImage(scratch, db, &im);
+    std::vector<DevMatch> matches;
+    if (r == HS_SUCCESS) {
+        r = scanHostBlocks(im, scratch, data, offsets, lengths, nblocks, &matches, false);
+    }
+    if (r == HS_SUCCESS) {
+        if (nmatches) {
+            *nmatches = matches.size();
+        }
+        static_assert(sizeof(DevMatch) == sizeof(hs_b200_match_t), "record layout");
+        memcpy(out, matches.data(), std::min(cap, matches.size()) * sizeof(DevMatch));
+        if (matches.size() > cap) {
+            r = HS_INSUFFICIENT_SPACE;
+        }
     }
     unmarkInUse(scratch);
     return r;

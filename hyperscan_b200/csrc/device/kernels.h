@@ -54,7 +54,7 @@ enum FilterKind {
     FK_PAIR32 = 4, /* index = (class of byte 0, class of byte 1), 5 bits each, classes
                       from a per-lane byte table; u32 entry; both tables replicated per
                       lane (bank-conflict free).  FDR sets.  Table image: 256 class words
-                      (c0 << 7 | c1 << 12), then 1024 pair entries; bitmapBytes = 32 KB or 0 */
+                      (c0 << 7 | c1 << 12), then 1024 pair entries */
 };
 
 enum ConfirmKind {
@@ -111,6 +111,11 @@ struct ScanParams {
     u32 bitmapBytes;       /* power of two >= 16, or 0 = no prefilter */
     u32 bitmapShift;       /* 32 - log2(bits) */
     u32 keyBytes;          /* 1..4: literal tail bytes hashed into the bitmap */
+    u32 pairBytes;         /* FK_PAIR32: shared-memory bytes of the pair table = 4 KiB x classes of the
+                            * second byte (<= 128 KiB) */
+    u32 bitmapHoles;       /* FK_PAIR32: 1 = the (32 KiB) bitmap sits in the class rows' upper halves;
+                            * 0 = bitmapBytes contiguous bytes after the pair table (large sets) */
+    u32 bitmapBits;        /* FK_PAIR32: bits of the first-level bitmap; index = mulhi(key * K, bits) */
     const u32 *bitmap2;    /* optional second-level bitmap in HBM/L2 (large literal sets) */
     u32 bitmap2Shift;      /* 32 - log2(bits); 0 = none */
     u32 confOff;           /* CK_FDR: offset of the confirm base in bc */

@@ -1537,8 +1537,19 @@ __device__ __forceinline__ void pairFilter(const u32 (&w)[5], u32 clsAddr, u32 l
     }
 }
 
+/* First-level bitmap word of the class-pair kernel: index = mulhi(key * K, bits).
+ * holes: word i lives in class row i >> 5 at byte 128 + 4 * (i & 31). */
+__device__ __forceinline__ bool pairBitmapTest(const ScanParams &p, u32 bitmapAddr, u32 key) {
+    const u32 h = __umulhi(key * 0x9E3779B1u, p.bitmapBits);
+    const u32 wi = h >> 5;
+    const u32 addr = p.bitmapHoles ? bitmapAddr + ((wi >> 5) << 8) + ((wi & 31u) << 2) : bitmapAddr + (wi << 2);
+    return (lds32(addr) >> (h & 31)) & 1;
+}
+
+/* One queue entry per lane: the lane's candidate bytes go through the prefilter
+ * bitmaps; survivors are appended to the candidate list in HBM (confirmKernel). */
 __device__ HSB_NOINLINE void drainPair(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
-                                          u32 count, u32 lane, u32 *stats) {
+                                       u32 count, u32 lane, u32 *stats) {
     if (lane >= count) {
         return;
     }
@@ -1551,8 +1562,46 @@ __device__ HSB_NOINLINE void drainPair(const ScanParams &p, u32 bitmapAddr, u32 
         v = __ldg(reinterpret_cast<const uint4 *>(p.corpus + g0));
     }
     const u32 pw = g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u;
-    laneCandidatesBody<1, 1, 1>(p, bitmapAddr, c.x, c.y, c.z, c.w, 0, 0, 0, 0, v.x, v.y, v.z, v.w, pw, g0,
-                                stats);
+    const u32 cw[4] = {c.x, c.y, c.z, c.w};
+    const u32 w[5] = {pw, v.x, v.y, v.z, v.w};
+    const u32 keyShift = 8 * (4 - p.keyBytes);
+    u32 ncand = 0, npass = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u32 m = cw[k];
+        while (m) { /* one candidate byte (8 bucket bits) of word k per iteration */
+            const u32 q = (u32)(__ffs(m) - 1) >> 3;
+            const u32 buckets = (m >> (8 * q)) & 0xffu;
+            m &= ~(0xffu << (8 * q));
+            ncand++;
+            if (p.bitmapBytes) {
+                /* the 4 bytes ending at byte q of word k, then the last keyBytes of them */
+                const u32 last4 = __funnelshift_rc(w[k], w[k + 1], 8 * (q + 1));
+                const u32 key = last4 >> keyShift;
+                if (!pairBitmapTest(p, bitmapAddr, key)) {
+                    continue; /* no literal of any bucket ends here */
+                }
+                if (p.bitmap2Shift) {
+                    const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
+                    if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
+                        continue;
+                    }
+                }
+            }
+            npass++;
+            const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
+            if (i < p.outCap) {
+                DevCand cnd;
+                cnd.g = g0 + 4 * k + q;
+                cnd.buckets = buckets;
+                cnd.pad = 0;
+                *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
+                    *reinterpret_cast<const uint4 *>(&cnd);
+            }
+        }
+    }
+    stats[0] += ncand;
+    stats[1] += npass;
 }
 
 template <int SB, int MAXT>
@@ -1567,25 +1616,33 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
         const u32 *g = reinterpret_cast<const u32 *>(p.table);
         const u32 *bm = reinterpret_cast<const u32 *>(p.bitmap);
         u32 *s = reinterpret_cast<u32 *>(smem);
+        const bool holes = p.bitmapHoles && p.bitmapBytes;
         for (u32 i = threadIdx.x; i < 256 * 64; i += blockDim.x) {
             const u32 row = i >> 6, l = i & 31;
             if ((i >> 5) & 1) {
-                s[i] = p.bitmapBytes ? __ldg(bm + row * 32 + l) : 0u;
+                s[i] = holes ? __ldg(bm + row * 32 + l) : 0u;
             } else {
                 s[i] = __ldg(g + row) | (l << 2);
             }
         }
         u32 *sp = s + 256 * 64;
-        for (u32 i = threadIdx.x; i < 1024 * 32; i += blockDim.x) {
+        for (u32 i = threadIdx.x; i < p.pairBytes / 4; i += blockDim.x) {
             sp[i] = __ldg(g + 256 + (i >> 5));
+        }
+        if (p.bitmapBytes && !holes) {
+            u32 *sb = sp + p.pairBytes / 4;
+            for (u32 i = threadIdx.x; i < p.bitmapBytes / 4; i += blockDim.x) {
+                sb[i] = __ldg(bm + i);
+            }
         }
     }
     __syncthreads();
 
     const u32 clsAddr = smemAddr(smem);
-    const u32 bitmapAddr = clsAddr + 128;
+    const u32 contiguous = (p.bitmapHoles || !p.bitmapBytes) ? 0u : p.bitmapBytes;
+    const u32 bitmapAddr = p.bitmapHoles ? clsAddr + 128 : clsAddr + PAIR_CLASS_BYTES + p.pairBytes;
     const u32 laneOff = lane * 4;
-    const u32 qAddr = clsAddr + PAIR_CLASS_BYTES + PAIR_TABLE_BYTES + warp * PairQueue::WARP_BYTES;
+    const u32 qAddr = clsAddr + PAIR_CLASS_BYTES + p.pairBytes + contiguous + warp * PairQueue::WARP_BYTES;
 
     /* this warp's contiguous run of tiles */
     const u32 gwarp = blockIdx.x * nwarps + warp;
@@ -1661,10 +1718,15 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
             }
         }
     };
-    /* the load issued for step s fetches step s + 1: no bounds check while that whole
-     * step is readable for every lane -- everywhere but at the very end of the corpus */
+    /* Register pipeline two steps deep: the first thing a step does is hand lane 31
+     * the next step's first word, so a load issued only one step ahead would be waited
+     * for at once (long-scoreboard stalls of a full L2 round trip per step).  The load
+     * issued in step s fetches step s + 2; it needs no bounds check while that whole
+     * step is readable for every lane -- everywhere but at the very end of the corpus. */
     const u64 readableSteps = (p.readableEnd - runStart) >> 9;
-    const u32 nFast = readableSteps >= (u64)nsteps + 1 ? nsteps : (readableSteps ? (u32)readableSteps - 1 : 0);
+    const u32 nFast = readableSteps >= (u64)nsteps + 2 ? nsteps : (readableSteps > 2 ? (u32)readableSteps - 2 : 0);
+    uint4 cur = nxt;                    /* step 0 */
+    nxt = load(ptr + 512, true);        /* step 1 */
     /* main loop: four steps per iteration (loads at immediate offsets, no register
      * moves between steps) and ONE L2 prefetch of the 2 KiB that lie pfDist steps ahead
      * (even lanes, 16 x 128 B) */
@@ -1676,21 +1738,21 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
                 prefetchL2(pf);
             }
         }
-        const uint4 v0 = nxt;
-        const uint4 v1 = ldCs128(ptr + 512);
-        compute(v0, v1.x, step * 32 + lane);
-        const uint4 v2 = ldCs128(ptr + 1024);
-        compute(v1, v2.x, step * 32 + 32 + lane);
-        const uint4 v3 = ldCs128(ptr + 1536);
-        compute(v2, v3.x, step * 32 + 64 + lane);
-        nxt = ldCs128(ptr + 2048);
-        compute(v3, nxt.x, step * 32 + 96 + lane);
+        const uint4 n2 = ldCs128(ptr + 1024);
+        compute(cur, nxt.x, step * 32 + lane);
+        const uint4 n3 = ldCs128(ptr + 1536);
+        compute(nxt, n2.x, step * 32 + 32 + lane);
+        cur = ldCs128(ptr + 2048);
+        compute(n2, n3.x, step * 32 + 64 + lane);
+        nxt = ldCs128(ptr + 2560);
+        compute(n3, cur.x, step * 32 + 96 + lane);
     }
 #pragma unroll 1
     for (; step < nsteps; step++, ptr += 512) {
-        const uint4 cur = nxt;
-        nxt = load(ptr + 512, step >= nFast);
+        const uint4 n2 = load(ptr + 1024, step >= nFast);
         compute(cur, nxt.x, step * 32 + lane);
+        cur = nxt;
+        nxt = n2;
     }
     if (qn) {
         __syncwarp();
@@ -1804,8 +1866,8 @@ cudaError_t launchStride(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t
 
 size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 nstages,
                      u32 tileBytes, int queueWarps) {
-    if (kind == FK_PAIR32) { /* class rows (bitmap in their upper halves) + pair table + queues */
-        return (size_t)PAIR_CLASS_BYTES + PAIR_TABLE_BYTES + (size_t)queueWarps * PairQueue::WARP_BYTES;
+    if (kind == FK_PAIR32) { /* class rows + pair table (tableBytes) + contiguous bitmap, if any + queues */
+        return (size_t)PAIR_CLASS_BYTES + tableBytes + bitmapBytes + (size_t)queueWarps * PairQueue::WARP_BYTES;
     }
     const size_t perWarp = queueWarps < 0          ? WideQueue::WARP_BYTES /* wide-step variant */
                            : kind == FK_BYTE64     ? QueueEntry<2>::WARP_BYTES

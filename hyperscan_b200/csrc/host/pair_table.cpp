@@ -9,7 +9,6 @@ namespace hsb {
 
 namespace {
 
-const u32 MAX_CLASSES = 32;  /* 5 bits per byte of the sample */
 const u32 GREEDY_LIMIT = 72; /* above this many classes a cheap pre-merge runs first */
 
 struct Side {                       /* one partition of the byte values (rows: first byte, columns: second) */
@@ -132,7 +131,11 @@ double bestMerge(const Model &m, int axis, u32 *bi, u32 *bj) {
 
 } // namespace
 
-void buildPairTables(const std::vector<LitTail> &tails, u32 slotBase, PairTables *out) {
+void buildPairTables(const std::vector<LitTail> &tails, u32 slotBase, PairTables *out, u32 maxClass0,
+                     u32 maxClass1) {
+    /* 5 bits per byte of the sample; fewer classes of the second byte shrink the
+     * pair table (4 KiB per class) in favour of a larger prefilter bitmap */
+    const u32 maxClasses[2] = {std::max(1u, std::min(32u, maxClass0)), std::max(1u, std::min(32u, maxClass1))};
     /* poss[b0][b1]: bit 8 * i + bucket SET iff some literal of the bucket can have
      * byte b0 at suffix distance i + slotBase and b1 right after it (don't-care
      * bits of LitInfo.msk -- caseless letters -- admit both cases; distance 0 has
@@ -229,12 +232,12 @@ void buildPairTables(const std::vector<LitTail> &tails, u32 slotBase, PairTables
             mergeClasses(m, axis, std::min(a, b), std::max(a, b));
         }
     }
-    while (m.side[0].w.size() > MAX_CLASSES || m.side[1].w.size() > MAX_CLASSES) {
+    while (m.side[0].w.size() > maxClasses[0] || m.side[1].w.size() > maxClasses[1]) {
         int axis = -1;
         u32 bi = 0, bj = 0;
         double best = -1;
         for (int a = 0; a < 2; a++) {
-            if (m.side[a].w.size() <= MAX_CLASSES) {
+            if (m.side[a].w.size() <= maxClasses[a]) {
                 continue;
             }
             u32 i = 0, j = 0;

@@ -31,7 +31,8 @@ struct PairTables {
 
 /* tails: LitInfo v/msk/size + bucket of every literal (walkConfirm); slotBase:
  * 0 = suffix slots 0..3 (sets with one-byte literals), 1 = slots 1..4. */
-void buildPairTables(const std::vector<LitTail> &tails, u32 slotBase, PairTables *out);
+void buildPairTables(const std::vector<LitTail> &tails, u32 slotBase, PairTables *out,
+                     u32 maxClass0 = 32, u32 maxClass1 = 32);
 
 } // namespace hsb
 #endif

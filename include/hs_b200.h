@@ -272,6 +272,16 @@ hs_error_t hs_b200_scan_blocks(const hs_database_t *db, const char *data,
                                hs_b200_block_event_handler onEvent,
                                void *context, unsigned long long *nmatches);
 
+/* Same, the delivered matches written to `out` in (block, to, id) order (the order
+ * the callbacks would fire in, all report rules applied) instead of one callback
+ * per match.  HS_INSUFFICIENT_SPACE: more than `cap` matches (*nmatches tells; the
+ * first cap are valid). */
+hs_error_t hs_b200_scan_blocks_collect(const hs_database_t *db, const char *data,
+                                       const unsigned long long *offsets,
+                                       const unsigned int *lengths, size_t nblocks,
+                                       hs_scratch_t *scratch, hs_b200_match_t *out, size_t cap,
+                                       unsigned long long *nmatches);
+
 /* Device-resident corpus handle: the packed, 16-byte-aligned copy of a set of
  * blocks in HBM plus its block table. */
 struct hs_b200_corpus;

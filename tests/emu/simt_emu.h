@@ -103,6 +103,11 @@ static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
     const uint64_t v = ((uint64_t)hi << 32) | lo;
     return (uint32_t)(v >> (s & 31));
 }
+static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) { /* shift clamped to 32 */
+    const uint64_t v = ((uint64_t)hi << 32) | lo;
+    return (uint32_t)(v >> (s > 32 ? 32 : s));
+}
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 /* PRMT, default mode, selector nibble bit 3 = replicate the byte's sign */
 static inline uint32_t hsb_emu_prmt(uint32_t a, uint32_t b, uint32_t sel) {
     const uint64_t ab = ((uint64_t)b << 32) | a;

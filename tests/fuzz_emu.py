@@ -20,9 +20,9 @@ from hyperscan_b200 import capi, synth  # noqa: E402
 import build_emu  # noqa: E402
 import oracle.ref as ref  # noqa: E402
 
-DEFAULTS = {"warps": 32, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1, "rebuild": 1,
-            "domain": 0, "direct": 1, "replicas": 1, "pf_dist": 8, "queue": 2, "first_stage": 1, "wide": 0,
-            "split": 0, "initial_ring": 1 << 20}
+DEFAULTS = {"warps": 0, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1, "rebuild": 1,
+            "domain": 0, "direct": 1, "replicas": 1, "pf_dist": 8, "queue": 2, "first_stage": 3, "wide": 1,
+            "split": 1, "big_set": 1, "big_set_classes": 4, "initial_ring": 1 << 20}
 
 
 def fuzz_streams(args, rng):
@@ -158,21 +158,32 @@ def main():
                 flags[k] = (flags[k] & ~8) | fm[ids[k]]
         opts = dict(DEFAULTS)
         opts["warps"] = int(rng.choice([1, 2, 3, 5, 8]))
-        mode = rng.integers(0, 8)
+        mode = rng.integers(0, 10)
         if mode == 0:
-            opts.update(direct=0, tile_bytes=int(rng.choice([512, 1024, 2048])), stages=int(rng.choice([2, 3])))
+            opts.update(direct=0, wide=0, split=0, first_stage=int(rng.choice([1, 2])),
+                        tile_bytes=int(rng.choice([512, 1024, 2048])), stages=int(rng.choice([2, 3])))
         elif mode == 1:
-            opts.update(wide=1, split=int(rng.integers(0, 2)), tile_bytes=int(rng.choice([1024, 4096])))
+            opts.update(wide=1, split=int(rng.integers(0, 2)), first_stage=int(rng.choice([1, 2, 3])),
+                        tile_bytes=int(rng.choice([1024, 4096])))
         elif mode == 2:
-            opts.update(wide=1, split=1, domain=int(rng.choice([0, 10, 12])), replicas=int(rng.choice([1, 4, 8])))
+            opts.update(wide=1, split=1, first_stage=1, domain=int(rng.choice([0, 10, 12])),
+                        replicas=int(rng.choice([1, 4, 8])))
         elif mode == 3:
-            opts.update(queue=int(rng.integers(0, 2)), first_stage=int(rng.choice([1, 2])))
+            opts.update(wide=0, split=0, queue=int(rng.integers(0, 2)), first_stage=int(rng.choice([1, 2])))
         elif mode == 4:
-            opts.update(stride=int(rng.choice([0, 2, 4])), rebuild=int(rng.integers(0, 2)), prefilter=int(rng.integers(0, 2)))
+            opts.update(wide=0, split=0, first_stage=1, stride=int(rng.choice([0, 2, 4])),
+                        rebuild=int(rng.integers(0, 2)), prefilter=int(rng.integers(0, 2)))
         elif mode == 5:
-            opts.update(domain=int(rng.choice([9, 11, 14])), replicas=int(rng.choice([0, 2, 16])), wide_fdr=int(rng.integers(0, 2)))
+            opts.update(wide=int(rng.integers(0, 2)), first_stage=1, domain=int(rng.choice([9, 11, 14])),
+                        replicas=int(rng.choice([0, 2, 16])), wide_fdr=int(rng.integers(0, 2)))
         elif mode == 6:
-            opts.update(initial_ring=int(rng.choice([16, 256])), wide=int(rng.integers(0, 2)), split=int(rng.integers(0, 2)))
+            opts.update(initial_ring=int(rng.choice([16, 256])), wide=int(rng.integers(0, 2)),
+                        split=int(rng.integers(0, 2)), first_stage=int(rng.choice([1, 3])))
+        elif mode == 7:   # class-pair kernel: layouts and prefilter
+            opts.update(first_stage=3, big_set=int(rng.integers(0, 2)), big_set_classes=int(rng.choice([1, 2, 4, 8])),
+                        prefilter=int(rng.integers(0, 2)), tile_bytes=int(rng.choice([512, 1024, 4096])))
+        # modes 8, 9: the defaults (class-pair for FDR sets, wide + split for the per-byte tables)
+        fat = 48 < nl <= 96 and rng.random() < 0.5 and ref.best_isa() != "corei7"
         for k, v in opts.items():
             capi.set_runtime_option(k, v)
         lens = [int(x) for x in rng.choice([0, 1, 2, 3, 15, 16, 17, 31, 32, 33, 63, 511, 512, 513, 1023, 1024, 1025, 3000, 9000],
@@ -191,7 +202,9 @@ def main():
                 pickle.dump({"lits": lits, "flags": flags, "ids": ids, "data": data, "off": off, "ln": ln,
                              "opts": opts}, f)
         try:
-            db = capi.compile_lit_multi(lits, flags, ids)
+            import ctypes as C
+            plat = C.byref(capi.PlatformInfo(0, capi.HS_CPU_FEATURES_AVX2, 0, 0)) if fat else None
+            db = capi.compile_lit_multi(lits, flags, ids, platform=plat)   # fat: 16-bucket Teddy (FK_BYTE64)
         except capi.HsError:
             skipped += 1
             continue

@@ -1,23 +1,23 @@
-"""Parity of the opt-in kernel variants that were written but not yet measured
-or validated on a GPU (runtime options `wide`, `queue=1` on hash tables,
-`first_stage=2`).  They are not on any default path; this file only runs with
-HSB200_EXPERIMENTAL=1 so that an unvalidated variant cannot fail the default
-GPU suite.  Same checks as tests/test_gpu_parity.py::_check_all."""
-import os
-
+"""Parity of every kernel variant a runtime option can select: the 16-byte-lane
+kernels (queued and not), the wide-step kernels with and without the split
+confirm, their 768 / 896 / 1024-thread builds, the hash-table and per-byte first
+stages for FDR sets (the class-pair kernel is the default and is what
+tests/test_gpu_parity.py runs).  Same checks as tests/test_gpu_parity.py::_check_all."""
 import numpy as np
 import pytest
 
 from hyperscan_b200 import synth
 from test_gpu_parity import _check_all
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("HSB200_EXPERIMENTAL") != "1",
-                                 reason="opt-in variants: set HSB200_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
-DEFAULTS = {"wide": 0, "queue": 2, "first_stage": 1, "replicas": 1, "domain": 0, "tile_bytes": 1024,
-            "warps": 32, "split": 0, "initial_ring": 1 << 20}
+DEFAULTS = {"wide": 1, "queue": 2, "first_stage": 3, "replicas": 1, "domain": 0, "tile_bytes": 1024,
+            "warps": 0, "split": 1, "initial_ring": 1 << 20}
+# every variant pins first_stage: 1 = hash table, 2 = per-byte table (FDR sets only; Teddy and
+# noodle sets use their per-byte tables whatever this says)
+BASE = {"first_stage": 1, "wide": 0, "split": 0}
 VARIANTS = [
+    {},                                                 # 16-byte lanes, queue for byte tables only (round-1 default)
     {"wide": 1},
     {"wide": 1, "domain": 12, "replicas": 8},
     {"wide": 1, "tile_bytes": 4096, "warps": 5},
@@ -41,7 +41,7 @@ def test_variant_parity(hs, ref, opts, nlits):
                                          2047, 2048, 2049, 4096, 10000, 65536 + 5, 200000], lits, seed=3,
                                         alphabet=b"abcdefghABCDxy")
     try:
-        for k, v in opts.items():
+        for k, v in dict(BASE, **opts).items():
             hs.set_runtime_option(k, v)
         _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
     finally:
@@ -49,12 +49,12 @@ def test_variant_parity(hs, ref, opts, nlits):
             hs.set_runtime_option(k, v)
 
 
-@pytest.mark.parametrize("opts", VARIANTS[:3], ids=["wide", "wide-d12x8", "wide-geom"])
+@pytest.mark.parametrize("opts", VARIANTS[1:4], ids=["wide", "wide-d12x8", "wide-geom"])
 def test_variant_config2_sample(hs, ref, opts):
     lits, flags, ids = synth.literal_set(1000)
     data, off, ln, _ = synth.block_corpus(4096, 1024, lits, plant_per_kb=0.05, seed=9)
     try:
-        for k, v in opts.items():
+        for k, v in dict(BASE, **opts).items():
             hs.set_runtime_option(k, v)
         _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
     finally:

@@ -74,10 +74,10 @@ def test_fat_teddy_16_buckets(hs, ref, nlits, lo, hi):
             for k, v in opts.items():
                 hs.set_runtime_option(k, v)
             _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False, platform=_avx2(hs))
-            for k, v in (("queue", 2), ("direct", 1), ("warps", 32), ("tile_bytes", 1024), ("stages", 2)):
+            for k, v in (("queue", 2), ("direct", 1), ("warps", 0), ("tile_bytes", 1024), ("stages", 2)):
                 hs.set_runtime_option(k, v)
     finally:
-        for k, v in (("queue", 2), ("direct", 1), ("warps", 32), ("tile_bytes", 1024), ("stages", 2)):
+        for k, v in (("queue", 2), ("direct", 1), ("warps", 0), ("tile_bytes", 1024), ("stages", 2)):
             hs.set_runtime_option(k, v)
 
 
@@ -89,6 +89,33 @@ def test_large_literal_set_two_level_prefilter(hs, ref):
     db, want = _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
     assert (db.info().engine_id, db.info().fdr_domain, db.info().fdr_stride) == (0, 15, 1)
     assert want.size > 300
+
+
+@pytest.mark.parametrize("opts", [{"big_set": 0}, {"big_set_classes": 1}, {"big_set_classes": 8},
+                                  {"first_stage": 1}, {"first_stage": 3, "prefilter": 0}],
+                         ids=["small-layout", "1-class", "8-classes", "hash-table", "no-prefilter"])
+def test_large_literal_set_layout_variants(hs, ref, opts):
+    """The class-pair kernel's shared-memory layouts (pair table size vs. bitmap
+    size) and the older hash-table first stage give the same matches."""
+    lits, flags, ids = synth.literal_set(20000, min_len=4, max_len=16, seed=52, caseless_frac=0.1)
+    data, off, ln, _ = synth.block_corpus(256, 1024, lits, plant_per_kb=1.0, seed=53)
+    try:
+        for k, v in opts.items():
+            hs.set_runtime_option(k, v)
+        _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
+    finally:
+        for k, v in (("big_set", 1), ("big_set_classes", 4), ("first_stage", 3), ("prefilter", 1)):
+            hs.set_runtime_option(k, v)
+
+
+def test_config5_shape_at_scale(hs, ref, real_gpu):
+    """BASELINE config 5 shape (50 000 literals, FDR domain 15) over 64 Ki blocks:
+    bit-exact against the reference runtime on the whole 64 MiB."""
+    lits, flags, ids = synth.literal_set(50000, min_len=4, max_len=16, seed=50, caseless_frac=0.1)
+    data, off, ln, _ = synth.block_corpus(65536, 1024, lits, plant_per_kb=0.05, seed=54)
+    db, want = _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
+    assert (db.info().engine_id, db.info().fdr_domain, db.info().fdr_stride) == (0, 15, 1)
+    assert want.size > 3000
 
 
 def test_hs_scan_single_block_and_termination(hs, ref):
@@ -192,7 +219,7 @@ def test_tile_geometry_invariance(hs, ref, tile, warps, stages, direct):
         _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
     finally:
         hs.set_runtime_option("tile_bytes", 1024)
-        hs.set_runtime_option("warps", 32)
+        hs.set_runtime_option("warps", 0)
         hs.set_runtime_option("stages", 2)
         hs.set_runtime_option("direct", 1)
 
