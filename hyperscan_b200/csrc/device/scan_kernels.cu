@@ -1481,10 +1481,12 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const HSB_GRID_CONSTAN
  * Candidates: per-warp queue -> prefilter bitmaps -> candidate list in HBM ->
  * confirmKernel (always "split": the hot kernel carries no confirm code). */
 
+/* Per-warp candidate queue: one 8-byte entry PER CANDIDATE BYTE {offset of the byte in
+ * the warp's run, bucket bits}, so that the drain works on 32 candidates at a time, one
+ * per lane, with no per-lane loops (large sets pass ~45 candidates per 512-byte step). */
 struct PairQueue {
-    static constexpr u32 SLOTS = 64;                      /* < 32 pending + <= 32 appended per step */
-    static constexpr u32 CHUNK = 16 * SLOTS;              /* u32 chunk[SLOTS] after uint4 cand[SLOTS] */
-    static constexpr u32 RUN_START = CHUNK + 4 * SLOTS;   /* u64: corpus position of the run's chunk 0 */
+    static constexpr u32 SLOTS = 64;                      /* < 32 pending + <= 32 appended at a time */
+    static constexpr u32 RUN_START = 8 * SLOTS;           /* u64: corpus position of the run's first byte */
     static constexpr u32 WARP_BYTES = RUN_START + 16;
 };
 enum { PAIR_CLASS_BYTES = 256 * 256, PAIR_TABLE_BYTES = 1024 * 128 };
@@ -1546,62 +1548,59 @@ __device__ __forceinline__ bool pairBitmapTest(const ScanParams &p, u32 bitmapAd
     return (lds32(addr) >> (h & 31)) & 1;
 }
 
-/* One queue entry per lane: the lane's candidate bytes go through the prefilter
- * bitmaps; survivors are appended to the candidate list in HBM (confirmKernel). */
+/* The 4 corpus bytes ending at position g (little-endian, byte g in the top lane);
+ * positions outside the readable corpus read as zero. */
+__device__ __forceinline__ u32 last4At(const ScanParams &p, u64 g) {
+    if (g < 3 || g + 5 > p.readableEnd) { /* rare: the aligned 8-byte window would leave the buffer */
+        u32 v = 0;
+        for (int z = 0; z < 4; z++) {
+            const long long q = (long long)g - 3 + z;
+            if (q >= 0 && (u64)q < p.readableEnd) {
+                v |= (u32)__ldg(p.corpus + q) << (8 * z);
+            }
+        }
+        return v;
+    }
+    const u8 *a = p.corpus + g - 3;
+    const u32 mis = (u32)((uintptr_t)a & 3);
+    const u32 *aw = reinterpret_cast<const u32 *>(a - mis);
+    return __funnelshift_r(__ldg(aw), __ldg(aw + 1), 8 * mis);
+}
+
+/* 32 queue entries, one candidate byte per lane: prefilter bitmaps (shared memory,
+ * then L2 for large sets); survivors are appended to the candidate list in HBM
+ * (confirmKernel). */
 __device__ HSB_NOINLINE void drainPair(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
                                        u32 count, u32 lane, u32 *stats) {
     if (lane >= count) {
         return;
     }
     const uint2 rs = lds64(qAddr + PairQueue::RUN_START);
-    const u64 runStart = ((u64)rs.y << 32) | rs.x;
-    const uint4 c = lds128(qAddr + (first + lane) * 16);
-    const u64 g0 = runStart + (u64)lds32(qAddr + PairQueue::CHUNK + (first + lane) * 4) * 16;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (g0 + 16 <= p.readableEnd) {
-        v = __ldg(reinterpret_cast<const uint4 *>(p.corpus + g0));
-    }
-    const u32 pw = g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u;
-    const u32 cw[4] = {c.x, c.y, c.z, c.w};
-    const u32 w[5] = {pw, v.x, v.y, v.z, v.w};
-    const u32 keyShift = 8 * (4 - p.keyBytes);
-    u32 ncand = 0, npass = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        u32 m = cw[k];
-        while (m) { /* one candidate byte (8 bucket bits) of word k per iteration */
-            const u32 q = (u32)(__ffs(m) - 1) >> 3;
-            const u32 buckets = (m >> (8 * q)) & 0xffu;
-            m &= ~(0xffu << (8 * q));
-            ncand++;
-            if (p.bitmapBytes) {
-                /* the 4 bytes ending at byte q of word k, then the last keyBytes of them */
-                const u32 last4 = __funnelshift_rc(w[k], w[k + 1], 8 * (q + 1));
-                const u32 key = last4 >> keyShift;
-                if (!pairBitmapTest(p, bitmapAddr, key)) {
-                    continue; /* no literal of any bucket ends here */
-                }
-                if (p.bitmap2Shift) {
-                    const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
-                    if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
-                        continue;
-                    }
-                }
-            }
-            npass++;
-            const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
-            if (i < p.outCap) {
-                DevCand cnd;
-                cnd.g = g0 + 4 * k + q;
-                cnd.buckets = buckets;
-                cnd.pad = 0;
-                *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
-                    *reinterpret_cast<const uint4 *>(&cnd);
+    const uint2 e = lds64(qAddr + (first + lane) * 8);
+    const u64 g = (((u64)rs.y << 32) | rs.x) + e.x;
+    stats[0]++;
+    if (p.bitmapBytes) {
+        const u32 key = last4At(p, g) >> (8 * (4 - p.keyBytes));
+        if (!pairBitmapTest(p, bitmapAddr, key)) {
+            return; /* no literal of any bucket ends here */
+        }
+        if (p.bitmap2Shift) {
+            const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
+            if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
+                return;
             }
         }
     }
-    stats[0] += ncand;
-    stats[1] += npass;
+    stats[1]++;
+    const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
+    if (i < p.outCap) {
+        DevCand cnd;
+        cnd.g = g;
+        cnd.buckets = e.y;
+        cnd.pad = 0;
+        *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
+            *reinterpret_cast<const uint4 *>(&cnd);
+    }
 }
 
 template <int SB, int MAXT>
@@ -1702,19 +1701,33 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
         prevRecv = recv;
         /* a zero bit anywhere = candidate: test the AND of the four words */
         const u32 all = a[0] & a[1] & a[2] & a[3];
-        const u32 bal = __ballot_sync(0xffffffffu, all != 0xffffffffu);
-        if (bal) {
-            if (all != 0xffffffffu) {
-                const u32 e = qn + __popc(bal & ((1u << lane) - 1));
-                sts128(qAddr + e * 16, ~a[0], ~a[1], ~a[2], ~a[3]);
-                sts32(qAddr + PairQueue::CHUNK + e * 4, chunk);
-            }
-            qn += __popc(bal);
-            if (qn >= 32) {
-                __syncwarp();
-                qn -= 32;
-                drainPair(p, bitmapAddr, qAddr, qn, 32, lane, stats);
-                __syncwarp();
+        if (__any_sync(0xffffffffu, all != 0xffffffffu)) {
+            /* rare for small sets, the rule for large ones: every candidate BYTE becomes a
+             * queue entry.  Word by word, rank by rank: in each round the lanes that still
+             * have a candidate byte in word k append one entry at a slot given by a ballot
+             * prefix; 32 pending entries are drained at once, one per lane. */
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                u32 m = ~a[k];
+                for (;;) {
+                    const u32 bal = __ballot_sync(0xffffffffu, m != 0);
+                    if (!bal) {
+                        break;
+                    }
+                    if (m) {
+                        const u32 q = (u32)(__ffs(m) - 1) >> 3;
+                        const u32 slot = qn + __popc(bal & ((1u << lane) - 1));
+                        sts64(qAddr + slot * 8, chunk * 16 + 4 * k + q, (m >> (8 * q)) & 0xffu);
+                        m &= ~(0xffu << (8 * q));
+                    }
+                    qn += __popc(bal);
+                    if (qn >= 32) {
+                        __syncwarp();
+                        qn -= 32;
+                        drainPair(p, bitmapAddr, qAddr, qn, 32, lane, stats);
+                        __syncwarp();
+                    }
+                }
             }
         }
     };

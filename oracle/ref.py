@@ -149,6 +149,31 @@ def scan_sorted(db_ptr, data, offsets, lengths, isa=None):
     return np.sort(r, order=["block", "to", "id"])
 
 
+def physical_core_cpus():
+    """CPUs of the affinity mask, one hardware thread per physical core first (then
+    the SMT siblings), for pinning the bench threads 1:1 the way hsbench does."""
+    cpus = sorted(os.sched_getaffinity(0))
+    first, rest, seen = [], [], set()
+    for c in cpus:
+        try:
+            with open("/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list" % c) as f:
+                sib = f.read().strip()
+        except OSError:
+            sib = str(c)
+        if sib in seen:
+            rest.append(c)
+        else:
+            seen.add(sib)
+            first.append(c)
+    return first + rest
+
+
+def pin_bench_threads(cpus):
+    """Pin bench thread i to cpus[i % len(cpus)]; an empty list unpins."""
+    arr = (C.c_int * max(1, len(cpus)))(*cpus)
+    lib().ref_set_bench_cpus(arr, len(cpus))
+
+
 def bench_blocks(db_ptr, data, offsets, lengths, threads, repeats, isa=None):
     """hsbench-style timing loop (tools/hsbench/main.cpp:503-527).  Returns
     (seconds, matches, bytes)."""

@@ -20,6 +20,7 @@
  */
 #define _GNU_SOURCE
 #include <pthread.h>
+#include <sched.h>
 #include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -252,7 +253,20 @@ API long ref_vector_collect(const hs_database_t *db, const char *data,
 
 /* ---- hsbench-style multi-threaded timing ------------------------------ */
 
+/* CPUs the bench threads are pinned to, thread i -> cpu[i % n]; n == 0: unpinned.
+ * hsbench pins its scan threads 1:1 (tools/hsbench/main.cpp:211-222 setAffinity). */
+static int g_bench_cpus[1024];
+static unsigned g_bench_ncpus;
+
+API void ref_set_bench_cpus(const int *cpus, unsigned n) {
+    g_bench_ncpus = n > 1024 ? 1024 : n;
+    for (unsigned i = 0; i < g_bench_ncpus; i++) {
+        g_bench_cpus[i] = cpus[i];
+    }
+}
+
 struct bench_thread {
+    unsigned index;
     pthread_t tid;
     const hs_database_t *db;
     const char *data;
@@ -278,6 +292,12 @@ static int count_cb(unsigned id, unsigned long long from,
 
 static void *bench_main(void *p) {
     struct bench_thread *t = (struct bench_thread *)p;
+    if (g_bench_ncpus) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(g_bench_cpus[t->index % g_bench_ncpus], &set);
+        pthread_setaffinity_np(pthread_self(), sizeof(set), &set); /* best effort */
+    }
     hs_scratch_t *scratch = NULL;
     t->err = hs_alloc_scratch(t->db, &scratch);
     pthread_barrier_wait(t->bar);
@@ -310,6 +330,7 @@ API double ref_scan_blocks_mt(const hs_database_t *db, const char *data,
     pthread_barrier_t bar;
     pthread_barrier_init(&bar, NULL, nthreads + 1);
     for (unsigned i = 0; i < nthreads; i++) {
+        th[i].index = i;
         th[i].db = db;
         th[i].data = data;
         th[i].offsets = offsets;
