@@ -240,15 +240,18 @@ class Passes:
         self.cap = 0
         self.bufs = None
         self.phase = {}
-        if world > 1:
-            # capacity of the exchange buffers: from one unpipelined pass, with headroom, same on all ranks
-            sc = self.rings[0]
-            capi.scan_corpus_async(db, corpus, sc)
-            rc, n0, _ = capi.scan_corpus_finish(sc)
-            if rc == capi.HS_INSUFFICIENT_SPACE:
+        # one unpipelined pass per record ring: a ring (or its candidate list) that is too small
+        # for this workload grows here, not in the timed region
+        n0 = 0
+        for sc in self.rings:
+            for attempt in range(4):
                 capi.scan_corpus_async(db, corpus, sc)
                 rc, n0, _ = capi.scan_corpus_finish(sc)
+                if rc != capi.HS_INSUFFICIENT_SPACE:
+                    break
             capi._check(rc, "first pass")
+        if world > 1:
+            # capacity of the exchange buffers: from that pass, with headroom, same on all ranks
             n_all = torch.tensor([n0], dtype=torch.int64, device=dev)
             dist.all_reduce(n_all, op=dist.ReduceOp.MAX)
             self.cap = (int(n_all.item()) * 3 // 2 + 4095) // 4096 * 4096

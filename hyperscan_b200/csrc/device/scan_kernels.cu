@@ -494,6 +494,13 @@ __device__ __forceinline__ void sts64(u32 addr, u32 x, u32 y) {
     memcpy(hsb_emu::dynamicSmem() + addr, v, 8);
 }
 __device__ __forceinline__ void sts32(u32 addr, u32 x) { memcpy(hsb_emu::dynamicSmem() + addr, &x, 4); }
+__device__ __forceinline__ u32 atomicAdd_shared(u32 addr, u32 v) { /* fibers switch only at warp syncs */
+    u32 old;
+    memcpy(&old, hsb_emu::dynamicSmem() + addr, 4);
+    const u32 nv = old + v;
+    memcpy(hsb_emu::dynamicSmem() + addr, &nv, 4);
+    return old;
+}
 #else
 __device__ __forceinline__ u32 lds32(u32 addr) {
     u32 v;
@@ -521,6 +528,11 @@ __device__ __forceinline__ void sts64(u32 addr, u32 x, u32 y) {
 }
 __device__ __forceinline__ void sts32(u32 addr, u32 x) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
+}
+__device__ __forceinline__ u32 atomicAdd_shared(u32 addr, u32 v) {
+    u32 old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+    return old;
 }
 #endif
 
@@ -1481,13 +1493,16 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const HSB_GRID_CONSTAN
  * Candidates: per-warp queue -> prefilter bitmaps -> candidate list in HBM ->
  * confirmKernel (always "split": the hot kernel carries no confirm code). */
 
-/* Per-warp candidate queue: one 8-byte entry PER CANDIDATE BYTE {offset of the byte in
- * the warp's run, bucket bits}, so that the drain works on 32 candidates at a time, one
- * per lane, with no per-lane loops (large sets pass ~45 candidates per 512-byte step). */
+/* Per-warp queue of candidates that passed the first-level bitmap and still owe the
+ * second-level (L2) probe -- large sets only: 8-byte entries {offset of the byte in the
+ * warp's run, bucket bits}, pushed from inside the lanes' candidate loops (shared-memory
+ * atomic on COUNT), drained 32 at a time, one per lane, so that the L2 round trips of a
+ * drain overlap. */
 struct PairQueue {
-    static constexpr u32 SLOTS = 64;                      /* < 32 pending + <= 32 appended at a time */
-    static constexpr u32 RUN_START = 8 * SLOTS;           /* u64: corpus position of the run's first byte */
-    static constexpr u32 WARP_BYTES = RUN_START + 16;
+    static constexpr u32 SLOTS = 64;                      /* < 32 pending + what one step pushes (more: in place) */
+    static constexpr u32 COUNT = 16 * SLOTS;              /* u32: entries pending; entry = {offset, buckets, key, -} */
+    static constexpr u32 RUN_START = COUNT + 8;           /* u64: corpus position of the run's first byte */
+    static constexpr u32 WARP_BYTES = RUN_START + 8;
 };
 enum { PAIR_CLASS_BYTES = 256 * 256, PAIR_TABLE_BYTES = 1024 * 128 };
 
@@ -1548,59 +1563,87 @@ __device__ __forceinline__ bool pairBitmapTest(const ScanParams &p, u32 bitmapAd
     return (lds32(addr) >> (h & 31)) & 1;
 }
 
-/* The 4 corpus bytes ending at position g (little-endian, byte g in the top lane);
- * positions outside the readable corpus read as zero. */
-__device__ __forceinline__ u32 last4At(const ScanParams &p, u64 g) {
-    if (g < 3 || g + 5 > p.readableEnd) { /* rare: the aligned 8-byte window would leave the buffer */
-        u32 v = 0;
-        for (int z = 0; z < 4; z++) {
-            const long long q = (long long)g - 3 + z;
-            if (q >= 0 && (u64)q < p.readableEnd) {
-                v |= (u32)__ldg(p.corpus + q) << (8 * z);
-            }
-        }
-        return v;
-    }
-    const u8 *a = p.corpus + g - 3;
-    const u32 mis = (u32)((uintptr_t)a & 3);
-    const u32 *aw = reinterpret_cast<const u32 *>(a - mis);
-    return __funnelshift_r(__ldg(aw), __ldg(aw + 1), 8 * mis);
-}
-
-/* 32 queue entries, one candidate byte per lane: prefilter bitmaps (shared memory,
- * then L2 for large sets); survivors are appended to the candidate list in HBM
- * (confirmKernel). */
-__device__ HSB_NOINLINE void drainPair(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
-                                       u32 count, u32 lane, u32 *stats) {
-    if (lane >= count) {
-        return;
-    }
-    const uint2 rs = lds64(qAddr + PairQueue::RUN_START);
-    const uint2 e = lds64(qAddr + (first + lane) * 8);
-    const u64 g = (((u64)rs.y << 32) | rs.x) + e.x;
-    stats[0]++;
-    if (p.bitmapBytes) {
-        const u32 key = last4At(p, g) >> (8 * (4 - p.keyBytes));
-        if (!pairBitmapTest(p, bitmapAddr, key)) {
-            return; /* no literal of any bucket ends here */
-        }
-        if (p.bitmap2Shift) {
-            const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
-            if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
-                return;
-            }
-        }
-    }
-    stats[1]++;
+/* Append a candidate that passed every prefilter to the list confirmKernel works through. */
+__device__ __forceinline__ void pushCandidate(const ScanParams &p, u64 g, u32 buckets) {
     const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
     if (i < p.outCap) {
         DevCand cnd;
         cnd.g = g;
-        cnd.buckets = e.y;
+        cnd.buckets = buckets;
         cnd.pad = 0;
         *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
             *reinterpret_cast<const uint4 *>(&cnd);
     }
+}
+
+__device__ __forceinline__ bool pairBitmap2Test(const ScanParams &p, u32 key) {
+    const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
+    return (__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1;
+}
+
+/* `count` queue entries from slot `first`, one per lane: second-level probe (the key
+ * travels in the entry), then the list. */
+__device__ HSB_NOINLINE void drainPair(const ScanParams &p, u32 qAddr, u32 first, u32 count, u32 lane,
+                                       u32 *stats) {
+    if (lane >= count) {
+        return;
+    }
+    const uint2 rs = lds64(qAddr + PairQueue::RUN_START);
+    const uint4 e = lds128(qAddr + (first + lane) * 16);
+    if (!pairBitmap2Test(p, e.z)) {
+        return;
+    }
+    stats[1]++;
+    pushCandidate(p, (((u64)rs.y << 32) | rs.x) + e.x, e.y);
+}
+
+/* The candidate bytes of one lane (m[k]: candidate bits of word k; w[k + 1] = word k of
+ * the lane's 16 bytes, w[0] = the word before them): first-level bitmap straight from the
+ * registers; survivors go to the candidate list, or -- sets with a second-level bitmap --
+ * to the warp's queue. */
+__device__ HSB_NOINLINE void pairCandidates(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 m0, u32 m1,
+                                            u32 m2, u32 m3, u32 w0, u32 w1, u32 w2, u32 w3, u32 w4, u32 pos,
+                                            u32 *stats) {
+    const u32 m[4] = {m0, m1, m2, m3};
+    const u32 w[5] = {w0, w1, w2, w3, w4};
+    const u32 keyShift = 8 * (4 - p.keyBytes);
+    const uint2 rs = lds64(qAddr + PairQueue::RUN_START);
+    const u64 runStart = ((u64)rs.y << 32) | rs.x;
+    u32 ncand = 0, npass = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u32 mk = m[k];
+        while (mk) { /* one candidate byte (8 bucket bits) of word k per iteration */
+            const u32 q = (u32)(__ffs(mk) - 1) >> 3;
+            const u32 buckets = (mk >> (8 * q)) & 0xffu;
+            mk &= ~(0xffu << (8 * q));
+            ncand++;
+            u32 key = 0;
+            if (p.bitmapBytes) {
+                /* the 4 bytes ending at byte q of word k, then the last keyBytes of them */
+                key = __funnelshift_rc(w[k], w[k + 1], 8 * (q + 1)) >> keyShift;
+                if (!pairBitmapTest(p, bitmapAddr, key)) {
+                    continue; /* no literal of any bucket ends here */
+                }
+            }
+            const u32 off = pos + 4 * k + q;
+            if (p.bitmapBytes && p.bitmap2Shift) {
+                const u32 slot = atomicAdd_shared(qAddr + PairQueue::COUNT, 1u);
+                if (slot < PairQueue::SLOTS) {
+                    sts128(qAddr + slot * 16, off, buckets, key, 0);
+                    continue;
+                }
+                /* queue full (floods): finish this one in place */
+                if (!pairBitmap2Test(p, key)) {
+                    continue;
+                }
+            }
+            npass++;
+            pushCandidate(p, runStart + off, buckets);
+        }
+    }
+    stats[0] += ncand;
+    stats[1] += npass;
 }
 
 template <int SB, int MAXT>
@@ -1662,11 +1705,12 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
     const u8 *const endPtr = p.corpus + p.readableEnd;
     if (lane == 0) {
         sts64(qAddr + PairQueue::RUN_START, (u32)runStart, (u32)(runStart >> 32));
+        sts32(qAddr + PairQueue::COUNT, 0);
     }
+    __syncwarp();
 
     u32 carry = 0; /* lane 31's overflow of the previous step */
     u32 stats[3] = {0, 0, 0};
-    u32 qn = 0;
 
     auto load = [&](const u8 *src, bool guard) -> uint4 {
         uint4 r = make_uint4(0, 0, 0, 0);
@@ -1702,32 +1746,32 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
         /* a zero bit anywhere = candidate: test the AND of the four words */
         const u32 all = a[0] & a[1] & a[2] & a[3];
         if (__any_sync(0xffffffffu, all != 0xffffffffu)) {
-            /* rare for small sets, the rule for large ones: every candidate BYTE becomes a
-             * queue entry.  Word by word, rank by rank: in each round the lanes that still
-             * have a candidate byte in word k append one entry at a slot given by a ballot
-             * prefix; 32 pending entries are drained at once, one per lane. */
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                u32 m = ~a[k];
-                for (;;) {
-                    const u32 bal = __ballot_sync(0xffffffffu, m != 0);
-                    if (!bal) {
-                        break;
-                    }
-                    if (m) {
-                        const u32 q = (u32)(__ffs(m) - 1) >> 3;
-                        const u32 slot = qn + __popc(bal & ((1u << lane) - 1));
-                        sts64(qAddr + slot * 8, chunk * 16 + 4 * k + q, (m >> (8 * q)) & 0xffu);
-                        m &= ~(0xffu << (8 * q));
-                    }
-                    qn += __popc(bal);
-                    if (qn >= 32) {
-                        __syncwarp();
-                        qn -= 32;
-                        drainPair(p, bitmapAddr, qAddr, qn, 32, lane, stats);
-                        __syncwarp();
-                    }
+            /* rare for small sets, the rule for large ones.  Every lane walks its own
+             * candidate bytes (keys straight from its registers); what survives the
+             * first-level bitmap goes to the list or, for sets with a second level, to the
+             * warp's queue, drained below once 32 are pending. */
+            u32 pw = __shfl_up_sync(0xffffffffu, cur.w, 1);
+            if (all != 0xffffffffu) {
+                if (lane == 0) { /* the word before this step's 512 bytes */
+                    pw = (runStart | chunk) ? __ldg(reinterpret_cast<const u32 *>(p.corpus + runStart) + chunk * 4 - 1)
+                                            : 0u;
                 }
+                pairCandidates(p, bitmapAddr, qAddr, ~a[0], ~a[1], ~a[2], ~a[3], pw, cur.x, cur.y, cur.z, cur.w,
+                               chunk * 16, stats);
+            }
+            if (p.bitmap2Shift) {
+                __syncwarp();
+                u32 n = lds32(qAddr + PairQueue::COUNT);
+                n = n < PairQueue::SLOTS ? n : (u32)PairQueue::SLOTS;
+                while (n >= 32) {
+                    n -= 32;
+                    drainPair(p, qAddr, n, 32, lane, stats);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    sts32(qAddr + PairQueue::COUNT, n);
+                }
+                __syncwarp();
             }
         }
     };
@@ -1767,9 +1811,13 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
         cur = nxt;
         nxt = n2;
     }
-    if (qn) {
+    if (p.bitmap2Shift) {
         __syncwarp();
-        drainPair(p, bitmapAddr, qAddr, 0, qn, lane, stats);
+        u32 n = lds32(qAddr + PairQueue::COUNT);
+        n = n < PairQueue::SLOTS ? n : (u32)PairQueue::SLOTS;
+        for (u32 first = 0; first < n; first += 32) {
+            drainPair(p, qAddr, first, n - first < 32 ? n - first : 32, lane, stats);
+        }
     }
     if (stats[0]) {
         atomicAdd(p.counters + CTR_CANDIDATES, stats[0]);

@@ -401,6 +401,32 @@ struct McClellan {
     u32 wide_offset;
 };
 
+/* ---- Sheng: src/nfa/sheng_internal.h:36-79 ------------------------------ */
+
+static const u8 SHENG_STATE_ACCEPT = 0x10, SHENG_STATE_DEAD = 0x20, SHENG_STATE_ACCEL = 0x40,
+                SHENG_STATE_MASK = 0xf;
+static const u8 SHENG_FLAG_SINGLE_REPORT = 1, SHENG_FLAG_CAN_DIE = 2, SHENG_FLAG_HAS_ACCEL = 4;
+
+struct SstateAux { u32 accept; u32 accept_eod; u32 accel; u32 top; };
+
+struct alignas(16) Sheng {
+    u8 shuffle_masks[256][16]; /* m128 per input byte: next state (with flags) of each of the 16 states */
+    u32 length;
+    u32 aux_offset;
+    u32 report_offset;
+    u32 accel_offset;
+    u8 n_states;
+    u8 anchored;
+    u8 floating;
+    u8 flags;
+    u32 report;
+};
+
+/* Sherman state record (src/nfa/mcclellan_internal.h:43-49): 32 bytes */
+static const u32 SHERMAN_FIXED_SIZE = 32, SHERMAN_TYPE_OFFSET = 0, SHERMAN_LEN_OFFSET = 1,
+                 SHERMAN_DADDY_OFFSET = 2, SHERMAN_CHARS_OFFSET = 4;
+static const u8 SHERMAN_STATE = 1;
+
 /* ---- multibit sizing: src/util/multibit_build.cpp:49-73 ---------------- */
 
 static inline u32 mmbitSize(u32 total_bits) {

@@ -40,6 +40,10 @@
 #include "rose/rose_program.h"
 #include "nfa/nfa_internal.h"
 #include "nfa/mcclellan_internal.h"
+#include "nfa/nfa_api.h"
+#include "nfa/mcclellan.h"
+#include "nfa/sheng.h"
+#include "nfa/callback.h"
 #include "nfa/accel.h"
 #include "nfa/shufti.h"
 #include "nfa/truffle.h"
@@ -371,11 +375,62 @@ API double ref_scan_blocks_mt(const hs_database_t *db, const char *data,
            1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
+/* ---- DFA engines in block mode ------------------------------------------- */
+
+struct nfa_collect {
+    struct rec16 *out;
+    size_t cap, n;
+    unsigned block;
+};
+
+static int nfa_cb(u64a start, u64a end, ReportID id, void *ctx) {
+    (void)start;
+    struct nfa_collect *c = (struct nfa_collect *)ctx;
+    if (c->n < c->cap) {
+        c->out[c->n].id = id;
+        c->out[c->n].block = c->block;
+        c->out[c->n].to = end;
+    }
+    c->n++;
+    return MO_CONTINUE_MATCHING;
+}
+
+/* nfaExecMcClellan8_B / nfaExecMcClellan16_B / nfaExecSheng_B (src/nfa/mcclellan.c:
+ * 937,963; src/nfa/sheng.c:706) over every block, offset 0 each, callbacks collected
+ * as (report, block, end).  `nfa` must be 64-byte aligned.  Returns the number of
+ * callbacks (may exceed cap) or -1 for an engine type not handled here. */
+API long ref_nfa_exec_blocks(const void *nfa, const char *data, const unsigned long long *offsets,
+                             const unsigned *lengths, size_t nblocks, struct rec16 *out,
+                             size_t cap) {
+    const struct NFA *n = (const struct NFA *)nfa;
+    struct nfa_collect c = {out, cap, 0, 0};
+    for (size_t b = 0; b < nblocks; b++) {
+        const u8 *buf = (const u8 *)data + offsets[b];
+        c.block = (unsigned)b;
+        switch (n->type) {
+        case MCCLELLAN_NFA_8:
+            nfaExecMcClellan8_B(n, 0, buf, lengths[b], nfa_cb, &c);
+            break;
+        case MCCLELLAN_NFA_16:
+            nfaExecMcClellan16_B(n, 0, buf, lengths[b], nfa_cb, &c);
+            break;
+        case SHENG_NFA:
+            nfaExecSheng_B(n, 0, buf, lengths[b], nfa_cb, &c);
+            break;
+        default:
+            return -1;
+        }
+    }
+    return (long)c.n;
+}
+
 /* ---- layout dump -------------------------------------------------------- */
 
 #define SZ(s) printf("  \"sizeof(%s)\": %zu,\n", #s, sizeof(struct s))
 #define OFF(s, f)                                                              \
     printf("  \"%s.%s\": %zu,\n", #s, #f, offsetof(struct s, f))
+
+void ref_layout_dump_sheng(void); /* ref_sheng_layout.c: sheng_internal.h redefines report_list */
 
 API void ref_layout_dump(void) {
     printf("{\n");
@@ -510,6 +565,8 @@ API void ref_layout_dump(void) {
     SZ(mstate_aux);
     OFF(mstate_aux, accept); OFF(mstate_aux, accept_eod);
     OFF(mstate_aux, top); OFF(mstate_aux, accel_offset);
+
+ref_layout_dump_sheng();
 
     /* rose program instruction sizes (8-byte rounded stride is what matters) */
 #define ISZ(n) printf("  \"sizeof(ROSE_STRUCT_%s)\": %zu,\n", #n, sizeof(struct ROSE_STRUCT_##n))
