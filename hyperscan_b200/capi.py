@@ -569,3 +569,73 @@ def compile_programs(lits, nocase, prog_off, area, ekey_count=0, inv_dkey=()):
     _check(L.hs_b200_test_compile_programs(arr, lens, nc, po, n, area, len(area), ekey_count, inv,
                                            len(inv_dkey), C.byref(db)), "test_compile_programs")
     return Database(db)
+
+
+def dfa_from_literals(lits, caseless=None, reports=None, anchored=False, kind=0, sherman=False):
+    """hs_b200_dfa_from_literals: Aho-Corasick DFA of a literal set as a reference-format
+    engine (struct NFA + McClellan 8/16 or Sheng).  Returns the bytes."""
+    n = len(lits)
+    lits = [bytes(x) for x in lits]
+    bufs = [C.create_string_buffer(x, len(x) + 1) for x in lits]
+    arr = (C.c_char_p * n)(*[C.cast(b, C.c_char_p) for b in bufs])
+    lens = (C.c_size_t * n)(*[len(x) for x in lits])
+    cl = (C.c_uint * n)(*[int(bool(x)) for x in (caseless or [0] * n)])
+    rp = (C.c_uint * n)(*(reports if reports is not None else list(range(n))))
+    L = lib()
+    L.hs_b200_dfa_from_literals.restype = C.c_long
+    L.hs_b200_dfa_from_literals.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint),
+                                            C.POINTER(C.c_uint), C.c_uint, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_size_t]
+    cap = 64 << 20
+    out = C.create_string_buffer(cap)
+    sz = L.hs_b200_dfa_from_literals(arr, lens, cl, rp, n, int(anchored), kind, int(sherman), out, cap)
+    if sz < 0:
+        raise HsError(HS_COMPILER_ERROR, "dfa_from_literals")
+    return out.raw[:sz]
+
+
+def dfa_from_table(next_table, start_anchored, start_floating, reports, reports_eod, kind=0, sherman=False):
+    """hs_b200_dfa_from_table: next_table uint16 [nstates, 256]; reports / reports_eod: one list
+    of report ids per state.  Returns the engine bytes."""
+    nt = np.ascontiguousarray(next_table, dtype=np.uint16)
+    n = nt.shape[0]
+
+    def flat(lists):
+        off = np.zeros(n + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(x) for x in lists])
+        vals = np.array([v for x in lists for v in x] + [0], dtype=np.uint32)
+        return off, vals
+
+    ro, rv = flat(reports)
+    eo, ev = flat(reports_eod)
+    L = lib()
+    L.hs_b200_dfa_from_table.restype = C.c_long
+    L.hs_b200_dfa_from_table.argtypes = [C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    cap = 64 << 20
+    out = C.create_string_buffer(cap)
+    sz = L.hs_b200_dfa_from_table(n, nt.ctypes.data, start_anchored, start_floating, ro.ctypes.data, rv.ctypes.data,
+                                  eo.ctypes.data, ev.ctypes.data, kind, int(sherman), out, cap)
+    if sz < 0:
+        raise HsError(HS_COMPILER_ERROR, "dfa_from_table")
+    return out.raw[:sz]
+
+
+def nfa_scan_corpus(nfa_bytes, corpus, cap=1 << 20):
+    """hs_b200_nfa_scan_corpus: the engine over every block of a resident corpus.
+    Returns (records MATCH_DTYPE ordered by (block, to, id), kernel ms)."""
+    L = lib()
+    L.hs_b200_nfa_scan_corpus.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.POINTER(C.c_ulonglong), C.POINTER(C.c_float)]
+    n = C.c_ulonglong()
+    ms = C.c_float()
+    for _ in range(3):
+        out = np.zeros(cap, dtype=MATCH_DTYPE)
+        rc = L.hs_b200_nfa_scan_corpus(nfa_bytes, len(nfa_bytes), corpus.ptr, out.ctypes.data, cap, C.byref(n),
+                                       C.byref(ms))
+        if rc == HS_INSUFFICIENT_SPACE:
+            cap = int(n.value) + 16
+            continue
+        _check(rc, "nfa_scan_corpus")
+        return out[: int(n.value)], float(ms.value)
+    raise HsError(HS_INSUFFICIENT_SPACE, "nfa_scan_corpus")

@@ -1725,6 +1725,122 @@ hs_error_t hs_b200_fetch_matches(const hs_database_t *db, hs_scratch_t *scratch,
     return HS_SUCCESS;
 }
 
+/* ---- DFA engines in block mode ------------------------------------------------------
+ *
+ * nfaExecMcClellan8_B / nfaExecMcClellan16_B / nfaExecSheng_B (src/nfa/mcclellan.c:
+ * 937-973, src/nfa/sheng.c:706-739) over every block of a resident corpus, offset 0
+ * per block.  The callbacks the reference would fire (report, end offset) come back
+ * as records {report, block, to}, ordered by (block, to, report). */
+hs_error_t hs_b200_nfa_scan_corpus(const void *nfa, size_t nfa_len, const hs_b200_corpus_t *corpus,
+                                   hs_b200_match_t *out, size_t cap, unsigned long long *nmatches,
+                                   float *kernel_ms) {
+    if (!nfa || nfa_len < sizeof(NFA) + 64 || !corpus || (cap && !out) || !nmatches) {
+        return HS_INVALID;
+    }
+    NFA hdr;
+    memcpy(&hdr, nfa, sizeof(hdr));
+    if (hdr.length > nfa_len) {
+        return HS_INVALID;
+    }
+    DfaParams p;
+    memset(&p, 0, sizeof(p));
+    p.kind = hdr.type;
+    if (hdr.type == NFA_MCCLELLAN_8 || hdr.type == NFA_MCCLELLAN_16) {
+        if (nfa_len < sizeof(NFA) + sizeof(McClellan)) {
+            return HS_INVALID;
+        }
+        McClellan m;
+        memcpy(&m, (const u8 *)nfa + sizeof(NFA), sizeof(m));
+        if (m.has_wide) {
+            return HS_ARCH_ERROR; /* wide states (mcclellan.c:168-225) are not built here */
+        }
+        const u32 rows = hdr.type == NFA_MCCLELLAN_16 ? m.sherman_limit : m.state_count;
+        p.tableBytes = (rows << m.alphaShift) * (hdr.type == NFA_MCCLELLAN_16 ? 2u : 1u);
+        if (sizeof(NFA) + sizeof(McClellan) + p.tableBytes > nfa_len) {
+            return HS_INVALID;
+        }
+    } else if (hdr.type == NFA_SHENG) {
+        if (nfa_len < sizeof(NFA) + sizeof(Sheng)) {
+            return HS_INVALID;
+        }
+    } else {
+        return HS_ARCH_ERROR; /* LimEx, McSheng, Gough, Castle, ...: not built */
+    }
+    DeviceGuard guard(corpus->device);
+    int smCount = 0, maxSmem = 0;
+    cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, corpus->device);
+    cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, corpus->device);
+    u8 *d_nfa = nullptr;
+    u32 *d_ctr = nullptr;
+    DevMatch *d_out = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    hs_error_t rv = HS_SUCCESS;
+    u32 capDev = (u32)std::min<size_t>(std::max<size_t>(cap, 1u << 16), 0xfffffff0u);
+    std::vector<DevMatch> host;
+    cudaError_t e = cudaMalloc(&d_nfa, HSB_ROUNDUP(nfa_len, 16));
+    if (e == cudaSuccess) e = cudaMemcpy(d_nfa, nfa, nfa_len, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&d_ctr, CTR_COUNT * sizeof(u32));
+    if (e == cudaSuccess) e = cudaEventCreate(&ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ev1);
+    for (int attempt = 0; e == cudaSuccess && attempt < 3; attempt++) {
+        e = cudaMalloc(&d_out, (size_t)capDev * sizeof(DevMatch));
+        if (e != cudaSuccess) break;
+        e = cudaMemset(d_ctr, 0, CTR_COUNT * sizeof(u32));
+        p.corpus = corpus->d_data;
+        p.readableEnd = corpus->readableEnd;
+        p.blockOff = corpus->d_off;
+        p.blockLen = corpus->d_len;
+        p.nblocks = (u32)corpus->nblocks;
+        p.uniformPitch = corpus->uniformPitch;
+        p.uniformLen = corpus->uniformLen;
+        p.nfa = d_nfa;
+        p.out = d_out;
+        p.outCap = capDev;
+        p.counters = d_ctr;
+        if (e == cudaSuccess) e = cudaEventRecord(ev0, 0);
+        if (e == cudaSuccess) e = launchDfa(p, smCount, maxSmem, 0);
+        if (e == cudaSuccess) e = cudaEventRecord(ev1, 0);
+        g_launches++;
+        u32 ctr[CTR_COUNT] = {0};
+        if (e == cudaSuccess) e = cudaMemcpy(ctr, d_ctr, sizeof(ctr), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) break;
+        if (ctr[CTR_MATCHES] > capDev) { /* grow and run again */
+            cudaFree(d_out);
+            d_out = nullptr;
+            capDev = ctr[CTR_MATCHES] + ctr[CTR_MATCHES] / 8 + 1024;
+            continue;
+        }
+        host.resize(ctr[CTR_MATCHES]);
+        if (!host.empty()) {
+            e = cudaMemcpy(host.data(), d_out, host.size() * sizeof(DevMatch), cudaMemcpyDeviceToHost);
+        }
+        if (kernel_ms && e == cudaSuccess) {
+            cudaEventElapsedTime(kernel_ms, ev0, ev1);
+        }
+        break;
+    }
+    if (e != cudaSuccess) {
+        rv = e == cudaErrorMemoryAllocation ? HS_NOMEM : HS_UNKNOWN_ERROR;
+    } else {
+        std::sort(host.begin(), host.end(), [](const DevMatch &a, const DevMatch &b) {
+            if (a.block != b.block) return a.block < b.block;
+            if (a.to != b.to) return a.to < b.to;
+            return a.id < b.id;
+        });
+        *nmatches = host.size();
+        memcpy(out, host.data(), std::min(cap, host.size()) * sizeof(DevMatch));
+        if (host.size() > cap) {
+            rv = HS_INSUFFICIENT_SPACE;
+        }
+    }
+    cudaFree(d_nfa);
+    cudaFree(d_ctr);
+    cudaFree(d_out);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    return rv;
+}
+
 /* ---- host-buffer scans -------------------------------------------------------------- */
 
 /* Copy host blocks into the scratch's inline corpus and scan them, with the

@@ -170,6 +170,24 @@ cudaError_t launchStreamAssemble(u8 *corpus, const u8 *hist, u32 nstreams, u32 p
 cudaError_t launchStreamAdvance(const u8 *corpus, u8 *hist, u64 *offsets, const u32 *lens, u32 uniformLen,
                                 u32 nstreams, u32 pitch, u32 histReq, cudaStream_t stream);
 
+/* DFA engines in block mode (dfa_kernels.cu): McClellan 8 / 16, Sheng -- the engine's
+ * own bytes (struct NFA first) in device memory, one thread per block. */
+struct DfaParams {
+    const u8 *corpus;
+    u64 readableEnd;
+    const u64 *blockOff;
+    const u32 *blockLen;
+    u32 nblocks;
+    u32 uniformPitch, uniformLen;
+    const u8 *nfa;
+    u32 kind;        /* NFA.type: NFA_MCCLELLAN_8 / NFA_MCCLELLAN_16 / NFA_SHENG */
+    u32 tableBytes;  /* McClellan: bytes of the successor table (staged in shared memory if it fits) */
+    DevMatch *out;   /* {report, block, offset after the last byte} */
+    u32 outCap;
+    u32 *counters;   /* CTR_MATCHES */
+};
+cudaError_t launchDfa(const DfaParams &p, int smCount, int maxSmem, cudaStream_t stream);
+
 /* accel primitives (src/nfa/shufti.c, truffle.c, vermicelli.h): first
  * position in [0,len) whose byte is in the class, or len. */
 cudaError_t launchAccelFind(int type, const u8 *params, const u8 *d_buf, u64 len,

@@ -20,6 +20,7 @@
 #include "../../../include/hs_b200.h"
 #include "api_internal.h"
 #include "rose_build.h"
+#include "dfa_build.h"
 
 using namespace hsb;
 
@@ -1184,5 +1185,64 @@ extern "C" hs_error_t hs_b200_test_compile_programs(const char *const *lits, con
         return HS_COMPILER_ERROR;
     } catch (const std::exception &) {
         return HS_COMPILER_ERROR;
+    }
+}
+
+/* ---- DFA engine emitters (host/dfa_build.h) ---------------------------------------
+ * Return the engine's size in bytes (struct NFA first, the reference's own layout),
+ * or -1 if it cannot be built / does not fit `cap`. */
+static long emitInto(const hsb::RawDfa &d, int kind, int sherman, void *out, size_t cap) {
+    std::vector<u8> b = hsb::emitDfa(d, (hsb::DfaKind)kind, sherman != 0);
+    if (b.size() > cap || !out) {
+        return -1;
+    }
+    memcpy(out, b.data(), b.size());
+    return (long)b.size();
+}
+
+extern "C" long hs_b200_dfa_from_literals(const char *const *lits, const size_t *lens, const unsigned *caseless,
+                                          const unsigned *reports, unsigned n, int anchored, int kind,
+                                          int sherman, void *out, size_t cap) {
+    if (!lits || !lens || !reports || !n) {
+        return -1;
+    }
+    try {
+        std::vector<hsb::DfaLiteral> v(n);
+        for (unsigned i = 0; i < n; i++) {
+            v[i].s.assign(lits[i], lens[i]);
+            v[i].caseless = caseless && caseless[i];
+            v[i].report = reports[i];
+        }
+        return emitInto(hsb::dfaFromLiterals(v, anchored != 0), kind, sherman, out, cap);
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+extern "C" long hs_b200_dfa_from_table(unsigned nstates, const unsigned short *next, unsigned start_anchored,
+                                       unsigned start_floating, const unsigned *report_off,
+                                       const unsigned *reports, const unsigned *eod_off,
+                                       const unsigned *eod_reports, int kind, int sherman, void *out,
+                                       size_t cap) {
+    if (!next || !report_off || !eod_off || nstates < 2) {
+        return -1;
+    }
+    try {
+        hsb::RawDfa d;
+        d.next.resize(nstates);
+        d.reports.resize(nstates);
+        d.reportsEod.resize(nstates);
+        for (unsigned s = 0; s < nstates; s++) {
+            for (unsigned c = 0; c < 256; c++) {
+                d.next[s][c] = next[(size_t)s * 256 + c];
+            }
+            d.reports[s].assign(reports + report_off[s], reports + report_off[s + 1]);
+            d.reportsEod[s].assign(eod_reports + eod_off[s], eod_reports + eod_off[s + 1]);
+        }
+        d.startAnchored = (u16)start_anchored;
+        d.startFloating = (u16)start_floating;
+        return emitInto(d, kind, sherman, out, cap);
+    } catch (const std::exception &) {
+        return -1;
     }
 }

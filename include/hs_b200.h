@@ -428,6 +428,38 @@ long hs_b200_test_build_hwlm(const char *const *lits, const size_t *lens,
                              const unsigned *ids, unsigned n, int engine, void *out,
                              size_t cap);
 
+/* ---- DFA engines (part of the regex half of the path) ----
+ *
+ * The reference's DFA engines in block mode, from the engines' own serialized bytes
+ * (`struct NFA` header, src/nfa/nfa_internal.h:84-126, followed by `struct mcclellan`
+ * or `struct sheng`): replaces nfaExecMcClellan8_B / nfaExecMcClellan16_B
+ * (src/nfa/mcclellan.c:937-973) and nfaExecSheng_B (src/nfa/sheng.c:706-739), the
+ * entry points the block runtime uses for its anchored table (src/rose/block.c:42-91)
+ * and its small-write engine (src/runtime.c:285-315).  Run over every block of a
+ * resident corpus (offset 0 per block); every callback (report, end) the reference
+ * would fire comes back as a record {id = report, block, to = end}, ordered by
+ * (block, to, id).  HS_ARCH_ERROR: engine type or feature (wide states) not built;
+ * HS_INSUFFICIENT_SPACE: more than `cap` records (*nmatches tells). */
+hs_error_t hs_b200_nfa_scan_corpus(const void *nfa, size_t nfa_len, const hs_b200_corpus_t *corpus,
+                                   hs_b200_match_t *out, size_t cap, unsigned long long *nmatches,
+                                   float *kernel_ms);
+
+/* Emit such engines on the host (the reference's compile side -- parser, Glushkov
+ * graph, determinisation -- stays out of scope; what can be given is a literal set,
+ * for which the Aho-Corasick automaton is built, or a finished DFA table).
+ * kind: 0 auto (Sheng <= 16 states, McClellan8 <= 256, else McClellan16), 1 McClellan8,
+ * 2 McClellan16, 3 Sheng; sherman != 0: McClellan16 stores states close to the start
+ * state's row as 32-byte Sherman exception lists.  State 0 is the dead state.
+ * report_off / eod_off: nstates + 1 offsets into reports / eod_reports.
+ * Return the size written to `out`, or -1. */
+long hs_b200_dfa_from_literals(const char *const *lits, const size_t *lens, const unsigned *caseless,
+                               const unsigned *reports, unsigned n, int anchored, int kind, int sherman,
+                               void *out, size_t cap);
+long hs_b200_dfa_from_table(unsigned nstates, const unsigned short *next, unsigned start_anchored,
+                            unsigned start_floating, const unsigned *report_off, const unsigned *reports,
+                            const unsigned *eod_off, const unsigned *eod_reports, int kind, int sherman,
+                            void *out, size_t cap);
+
 /* Test hook: pure-literal block database whose literal programs are raw
  * instruction bytes (layouts: src/rose/rose_program.h:214-724).  `area` is
  * placed at bytecode offset hs_b200_test_program_base(); prog_off[i] = offset of

@@ -203,3 +203,28 @@ def hwlm_exec(hwlm_bytes, data, start=0, groups=0xFFFFFFFFFFFFFFFF, stop_after=0
     n = lib(isa).ref_hwlm_exec(raw.ctypes.data + o, buf.ctypes.data + 64, a.size, start, groups,
                                out.ctypes.data, cap, stop_after)
     return [(int(r["to"]), int(r["id"])) for r in out[:min(n, cap)]]
+
+
+def nfa_exec_blocks(nfa_bytes, data, offsets, lengths, isa=None, cap=1 << 20):
+    """Reference nfaExecMcClellan8_B / 16_B / nfaExecSheng_B over every block (offset 0):
+    the callbacks as records sorted by (block, to, id)."""
+    a = _u8(data)
+    keep = a if a.size else np.zeros(1, dtype=np.uint8)
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+    raw = np.zeros(len(nfa_bytes) + 64, dtype=np.uint8)     # struct NFA is cache-line aligned
+    shift = (-raw.ctypes.data) % 64
+    raw[shift:shift + len(nfa_bytes)] = np.frombuffer(nfa_bytes, dtype=np.uint8)
+    L = lib(isa)
+    L.ref_nfa_exec_blocks.restype = C.c_long
+    L.ref_nfa_exec_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_size_t]
+    while True:
+        out = np.zeros(cap, dtype=REC_DTYPE)
+        n = L.ref_nfa_exec_blocks(raw.ctypes.data + shift, keep.ctypes.data, off.ctypes.data, ln.ctypes.data,
+                                  off.size, out.ctypes.data, cap)
+        if n < 0:
+            raise RuntimeError("reference: engine type not handled")
+        if n <= cap:
+            return np.sort(out[:n], order=["block", "to", "id"])
+        cap = int(n) + 16
