@@ -71,6 +71,8 @@ struct RuntimeOpts {
                               * and 2 by the modelled candidate rate of the per-byte table */
     int bigSet = 1;          /* FK_PAIR32: sets that would overfill the 32 KiB bitmap trade classes of the
                               * second byte for a large contiguous bitmap */
+    int heavy = 1;           /* FK_PAIR32 candidate path: 0 = per-lane entries, 2 = per-word entries (sets that
+                              * pass many candidates), 1 = by the modelled first-stage rate */
     int bigSetClasses = 4;   /* ... classes left to the second byte (pair table = 4 KiB each) */
     int chunkMB = 128;       /* host->device pipeline granularity */
     int initialRing = 1 << 20;
@@ -93,7 +95,7 @@ void initOpts() {
         {"HSB200_PF_DIST", &g_opts.pfDist},    {"HSB200_QUEUE", &g_opts.queue},
         {"HSB200_FIRST_STAGE", &g_opts.firstStage}, {"HSB200_WIDE", &g_opts.wide},
         {"HSB200_SPLIT", &g_opts.split},       {"HSB200_BIG_SET", &g_opts.bigSet},
-        {"HSB200_BIG_SET_CLASSES", &g_opts.bigSetClasses}};
+        {"HSB200_BIG_SET_CLASSES", &g_opts.bigSetClasses}, {"HSB200_HEAVY", &g_opts.heavy}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -113,6 +115,7 @@ struct DevImage {
     u8 *d_bitmap = nullptr;
     u32 bitmapBytes = 0, bitmapShift = 0, keyBytes = 0;
     u32 pairBytes = 0, bitmapHoles = 0, bitmapBits = 0; /* FK_PAIR32 layout (kernels.h) */
+    double pairRate = 0;     /* FK_PAIR32: modelled first-stage candidates per byte (printable ASCII) */
     u8 *d_bitmap2 = nullptr; /* second level (HBM / L2) for large literal sets */
     u32 bitmap2Shift = 0;
     int kind = FK_BYTE32;
@@ -482,6 +485,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                 PairTables pt;
                 buildPairTables(tails, (u32)im->slotBase, &pt, 32, big ? (u32)std::max(1, g_opts.bigSetClasses) : 32);
                 im->pairBytes = pt.nClass1 * 4096;
+                im->pairRate = pt.modelRate;
                 table.resize(sizeof(pt.classWord) + sizeof(pt.pair));
                 memcpy(table.data(), pt.classWord, sizeof(pt.classWord));
                 memcpy(table.data() + sizeof(pt.classWord), pt.pair, sizeof(pt.pair));
@@ -834,7 +838,9 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
         pl->cfg.slotBase = im->slotBase;
         pl->cfg.direct = 1;
         pl->cfg.stride = 1;
-        pl->cfg.queued = 1;
+        /* candidate path: per-lane queue entries while candidates are rare; one entry per
+         * word with candidates once the modelled rate passes ~2 per KiB (heavy=2 forces it) */
+        pl->cfg.queued = g_opts.heavy == 2 || (g_opts.heavy == 1 && im->pairRate > 0.002) ? 2 : 1;
         pl->cfg.wide = 0;
         pl->cfg.split = 1;
         pl->cfg.grid = s->smCount;
@@ -1126,7 +1132,7 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"pf_dist", &g_opts.pfDist},    {"queue", &g_opts.queue},
         {"first_stage", &g_opts.firstStage}, {"wide", &g_opts.wide},
         {"split", &g_opts.split},       {"big_set", &g_opts.bigSet},
-        {"big_set_classes", &g_opts.bigSetClasses}};
+        {"big_set_classes", &g_opts.bigSetClasses}, {"heavy", &g_opts.heavy}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;

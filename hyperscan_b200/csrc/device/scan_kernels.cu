@@ -494,13 +494,6 @@ __device__ __forceinline__ void sts64(u32 addr, u32 x, u32 y) {
     memcpy(hsb_emu::dynamicSmem() + addr, v, 8);
 }
 __device__ __forceinline__ void sts32(u32 addr, u32 x) { memcpy(hsb_emu::dynamicSmem() + addr, &x, 4); }
-__device__ __forceinline__ u32 atomicAdd_shared(u32 addr, u32 v) { /* fibers switch only at warp syncs */
-    u32 old;
-    memcpy(&old, hsb_emu::dynamicSmem() + addr, 4);
-    const u32 nv = old + v;
-    memcpy(hsb_emu::dynamicSmem() + addr, &nv, 4);
-    return old;
-}
 #else
 __device__ __forceinline__ u32 lds32(u32 addr) {
     u32 v;
@@ -528,11 +521,6 @@ __device__ __forceinline__ void sts64(u32 addr, u32 x, u32 y) {
 }
 __device__ __forceinline__ void sts32(u32 addr, u32 x) {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(x) : "memory");
-}
-__device__ __forceinline__ u32 atomicAdd_shared(u32 addr, u32 v) {
-    u32 old;
-    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
-    return old;
 }
 #endif
 
@@ -1493,16 +1481,11 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelWide(const HSB_GRID_CONSTAN
  * Candidates: per-warp queue -> prefilter bitmaps -> candidate list in HBM ->
  * confirmKernel (always "split": the hot kernel carries no confirm code). */
 
-/* Per-warp queue of candidates that passed the first-level bitmap and still owe the
- * second-level (L2) probe -- large sets only: 8-byte entries {offset of the byte in the
- * warp's run, bucket bits}, pushed from inside the lanes' candidate loops (shared-memory
- * atomic on COUNT), drained 32 at a time, one per lane, so that the L2 round trips of a
- * drain overlap. */
 struct PairQueue {
-    static constexpr u32 SLOTS = 64;                      /* < 32 pending + what one step pushes (more: in place) */
-    static constexpr u32 COUNT = 16 * SLOTS;              /* u32: entries pending; entry = {offset, buckets, key, -} */
-    static constexpr u32 RUN_START = COUNT + 8;           /* u64: corpus position of the run's first byte */
-    static constexpr u32 WARP_BYTES = RUN_START + 8;
+    static constexpr u32 SLOTS = 64;                      /* < 32 pending + <= 32 appended per step */
+    static constexpr u32 CHUNK = 16 * SLOTS;              /* u32 chunk[SLOTS] after uint4 cand[SLOTS] */
+    static constexpr u32 RUN_START = CHUNK + 4 * SLOTS;   /* u64: corpus position of the run's chunk 0 */
+    static constexpr u32 WARP_BYTES = RUN_START + 16;
 };
 enum { PAIR_CLASS_BYTES = 256 * 256, PAIR_TABLE_BYTES = 1024 * 128 };
 
@@ -1563,90 +1546,112 @@ __device__ __forceinline__ bool pairBitmapTest(const ScanParams &p, u32 bitmapAd
     return (lds32(addr) >> (h & 31)) & 1;
 }
 
-/* Append a candidate that passed every prefilter to the list confirmKernel works through. */
-__device__ __forceinline__ void pushCandidate(const ScanParams &p, u64 g, u32 buckets) {
-    const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
-    if (i < p.outCap) {
-        DevCand cnd;
-        cnd.g = g;
-        cnd.buckets = buckets;
-        cnd.pad = 0;
-        *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
-            *reinterpret_cast<const uint4 *>(&cnd);
-    }
-}
-
-__device__ __forceinline__ bool pairBitmap2Test(const ScanParams &p, u32 key) {
-    const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
-    return (__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1;
-}
-
-/* `count` queue entries from slot `first`, one per lane: second-level probe (the key
- * travels in the entry), then the list. */
-__device__ HSB_NOINLINE void drainPair(const ScanParams &p, u32 qAddr, u32 first, u32 count, u32 lane,
-                                       u32 *stats) {
+/* One queue entry per lane: the lane's candidate bytes go through the prefilter
+ * bitmaps; survivors are appended to the candidate list in HBM (confirmKernel). */
+__device__ HSB_NOINLINE void drainPair(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
+                                       u32 count, u32 lane, u32 *stats) {
     if (lane >= count) {
         return;
     }
     const uint2 rs = lds64(qAddr + PairQueue::RUN_START);
-    const uint4 e = lds128(qAddr + (first + lane) * 16);
-    if (!pairBitmap2Test(p, e.z)) {
-        return;
-    }
-    stats[1]++;
-    pushCandidate(p, (((u64)rs.y << 32) | rs.x) + e.x, e.y);
-}
-
-/* The candidate bytes of one lane (m[k]: candidate bits of word k; w[k + 1] = word k of
- * the lane's 16 bytes, w[0] = the word before them): first-level bitmap straight from the
- * registers; survivors go to the candidate list, or -- sets with a second-level bitmap --
- * to the warp's queue. */
-__device__ HSB_NOINLINE void pairCandidates(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 m0, u32 m1,
-                                            u32 m2, u32 m3, u32 w0, u32 w1, u32 w2, u32 w3, u32 w4, u32 pos,
-                                            u32 *stats) {
-    const u32 m[4] = {m0, m1, m2, m3};
-    const u32 w[5] = {w0, w1, w2, w3, w4};
-    const u32 keyShift = 8 * (4 - p.keyBytes);
-    const uint2 rs = lds64(qAddr + PairQueue::RUN_START);
     const u64 runStart = ((u64)rs.y << 32) | rs.x;
+    const uint4 c = lds128(qAddr + (first + lane) * 16);
+    const u64 g0 = runStart + (u64)lds32(qAddr + PairQueue::CHUNK + (first + lane) * 4) * 16;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (g0 + 16 <= p.readableEnd) {
+        v = __ldg(reinterpret_cast<const uint4 *>(p.corpus + g0));
+    }
+    const u32 pw = g0 ? __ldg(reinterpret_cast<const u32 *>(p.corpus + g0 - 4)) : 0u;
+    const u32 cw[4] = {c.x, c.y, c.z, c.w};
+    const u32 w[5] = {pw, v.x, v.y, v.z, v.w};
+    const u32 keyShift = 8 * (4 - p.keyBytes);
     u32 ncand = 0, npass = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        u32 mk = m[k];
-        while (mk) { /* one candidate byte (8 bucket bits) of word k per iteration */
-            const u32 q = (u32)(__ffs(mk) - 1) >> 3;
-            const u32 buckets = (mk >> (8 * q)) & 0xffu;
-            mk &= ~(0xffu << (8 * q));
+        u32 m = cw[k];
+        while (m) { /* one candidate byte (8 bucket bits) of word k per iteration */
+            const u32 q = (u32)(__ffs(m) - 1) >> 3;
+            const u32 buckets = (m >> (8 * q)) & 0xffu;
+            m &= ~(0xffu << (8 * q));
             ncand++;
-            u32 key = 0;
             if (p.bitmapBytes) {
                 /* the 4 bytes ending at byte q of word k, then the last keyBytes of them */
-                key = __funnelshift_rc(w[k], w[k + 1], 8 * (q + 1)) >> keyShift;
+                const u32 last4 = __funnelshift_rc(w[k], w[k + 1], 8 * (q + 1));
+                const u32 key = last4 >> keyShift;
                 if (!pairBitmapTest(p, bitmapAddr, key)) {
                     continue; /* no literal of any bucket ends here */
                 }
-            }
-            const u32 off = pos + 4 * k + q;
-            if (p.bitmapBytes && p.bitmap2Shift) {
-                const u32 slot = atomicAdd_shared(qAddr + PairQueue::COUNT, 1u);
-                if (slot < PairQueue::SLOTS) {
-                    sts128(qAddr + slot * 16, off, buckets, key, 0);
-                    continue;
-                }
-                /* queue full (floods): finish this one in place */
-                if (!pairBitmap2Test(p, key)) {
-                    continue;
+                if (p.bitmap2Shift) {
+                    const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
+                    if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
+                        continue;
+                    }
                 }
             }
             npass++;
-            pushCandidate(p, runStart + off, buckets);
+            const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
+            if (i < p.outCap) {
+                DevCand cnd;
+                cnd.g = g0 + 4 * k + q;
+                cnd.buckets = buckets;
+                cnd.pad = 0;
+                *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
+                    *reinterpret_cast<const uint4 *>(&cnd);
+            }
         }
     }
     stats[0] += ncand;
     stats[1] += npass;
 }
 
-template <int SB, int MAXT>
+/* Heavy variant (large / saturating sets: tens of candidates per 512-byte step).  A queue
+ * entry is ONE WORD of one lane with at least one candidate byte: {offset of the word in
+ * the warp's run, its candidate bits, the word before it, the word} -- the bytes travel
+ * with the entry, so the drain needs no corpus read, and an entry holds 1..4 candidates
+ * (1.1 on average), so the 32 lanes of a drain stay in step. */
+__device__ HSB_NOINLINE void drainPairWords(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
+                                            u32 count, u32 lane, u32 *stats) {
+    if (lane >= count) {
+        return;
+    }
+    const uint2 rs = lds64(qAddr + PairQueue::RUN_START);
+    const u64 runStart = ((u64)rs.y << 32) | rs.x;
+    const uint4 e = lds128(qAddr + (first + lane) * 16); /* x = offset, y = candidate bits, z = previous word, w = word */
+    const u32 keyShift = 8 * (4 - p.keyBytes);
+    u32 m = e.y, ncand = 0, npass = 0;
+    while (m) {
+        const u32 q = (u32)(__ffs(m) - 1) >> 3;
+        const u32 buckets = (m >> (8 * q)) & 0xffu;
+        m &= ~(0xffu << (8 * q));
+        ncand++;
+        if (p.bitmapBytes) {
+            const u32 key = __funnelshift_rc(e.z, e.w, 8 * (q + 1)) >> keyShift;
+            if (!pairBitmapTest(p, bitmapAddr, key)) {
+                continue;
+            }
+            if (p.bitmap2Shift) {
+                const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
+                if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
+                    continue;
+                }
+            }
+        }
+        npass++;
+        const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
+        if (i < p.outCap) {
+            DevCand cnd;
+            cnd.g = runStart + e.x + q;
+            cnd.buckets = buckets;
+            cnd.pad = 0;
+            *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
+                *reinterpret_cast<const uint4 *>(&cnd);
+        }
+    }
+    stats[0] += ncand;
+    stats[1] += npass;
+}
+
+template <int SB, int MAXT, int HEAVY>
 __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTANT ScanParams p) {
     HSB_DYNAMIC_SMEM(smem);
     const u32 lane = threadIdx.x & 31;
@@ -1705,12 +1710,11 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
     const u8 *const endPtr = p.corpus + p.readableEnd;
     if (lane == 0) {
         sts64(qAddr + PairQueue::RUN_START, (u32)runStart, (u32)(runStart >> 32));
-        sts32(qAddr + PairQueue::COUNT, 0);
     }
-    __syncwarp();
 
     u32 carry = 0; /* lane 31's overflow of the previous step */
     u32 stats[3] = {0, 0, 0};
+    u32 qn = 0;
 
     auto load = [&](const u8 *src, bool guard) -> uint4 {
         uint4 r = make_uint4(0, 0, 0, 0);
@@ -1745,32 +1749,51 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
         prevRecv = recv;
         /* a zero bit anywhere = candidate: test the AND of the four words */
         const u32 all = a[0] & a[1] & a[2] & a[3];
-        if (__any_sync(0xffffffffu, all != 0xffffffffu)) {
-            /* rare for small sets, the rule for large ones.  Every lane walks its own
-             * candidate bytes (keys straight from its registers); what survives the
-             * first-level bitmap goes to the list or, for sets with a second level, to the
-             * warp's queue, drained below once 32 are pending. */
-            u32 pw = __shfl_up_sync(0xffffffffu, cur.w, 1);
-            if (all != 0xffffffffu) {
+        if (HEAVY) {
+            if (__any_sync(0xffffffffu, all != 0xffffffffu)) {
+                /* four static rounds, one per word of the lane: the lanes whose word k has
+                 * a candidate byte append it (slot from a ballot prefix); 32 pending
+                 * entries are drained at once */
+                u32 pw = __shfl_up_sync(0xffffffffu, cur.w, 1);
                 if (lane == 0) { /* the word before this step's 512 bytes */
-                    pw = (runStart | chunk) ? __ldg(reinterpret_cast<const u32 *>(p.corpus + runStart) + chunk * 4 - 1)
-                                            : 0u;
+                    pw = (runStart | chunk)
+                             ? __ldg(reinterpret_cast<const u32 *>(p.corpus + runStart) + (size_t)chunk * 4 - 1)
+                             : 0u;
                 }
-                pairCandidates(p, bitmapAddr, qAddr, ~a[0], ~a[1], ~a[2], ~a[3], pw, cur.x, cur.y, cur.z, cur.w,
-                               chunk * 16, stats);
+                const u32 wv[5] = {pw, cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const u32 m = ~a[k];
+                    const u32 bal = __ballot_sync(0xffffffffu, m != 0);
+                    if (bal) {
+                        if (m) {
+                            const u32 slot = qn + __popc(bal & ((1u << lane) - 1));
+                            sts128(qAddr + slot * 16, chunk * 16 + 4 * k, m, wv[k], wv[k + 1]);
+                        }
+                        qn += __popc(bal);
+                        if (qn >= 32) {
+                            __syncwarp();
+                            qn -= 32;
+                            drainPairWords(p, bitmapAddr, qAddr, qn, 32, lane, stats);
+                            __syncwarp();
+                        }
+                    }
+                }
             }
-            if (p.bitmap2Shift) {
+            return;
+        }
+        const u32 bal = __ballot_sync(0xffffffffu, all != 0xffffffffu);
+        if (bal) {
+            if (all != 0xffffffffu) {
+                const u32 e = qn + __popc(bal & ((1u << lane) - 1));
+                sts128(qAddr + e * 16, ~a[0], ~a[1], ~a[2], ~a[3]);
+                sts32(qAddr + PairQueue::CHUNK + e * 4, chunk);
+            }
+            qn += __popc(bal);
+            if (qn >= 32) {
                 __syncwarp();
-                u32 n = lds32(qAddr + PairQueue::COUNT);
-                n = n < PairQueue::SLOTS ? n : (u32)PairQueue::SLOTS;
-                while (n >= 32) {
-                    n -= 32;
-                    drainPair(p, qAddr, n, 32, lane, stats);
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    sts32(qAddr + PairQueue::COUNT, n);
-                }
+                qn -= 32;
+                drainPair(p, bitmapAddr, qAddr, qn, 32, lane, stats);
                 __syncwarp();
             }
         }
@@ -1811,12 +1834,12 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
         cur = nxt;
         nxt = n2;
     }
-    if (p.bitmap2Shift) {
+    if (qn) {
         __syncwarp();
-        u32 n = lds32(qAddr + PairQueue::COUNT);
-        n = n < PairQueue::SLOTS ? n : (u32)PairQueue::SLOTS;
-        for (u32 first = 0; first < n; first += 32) {
-            drainPair(p, qAddr, first, n - first < 32 ? n - first : 32, lane, stats);
+        if (HEAVY) {
+            drainPairWords(p, bitmapAddr, qAddr, 0, qn, lane, stats);
+        } else {
+            drainPair(p, bitmapAddr, qAddr, 0, qn, lane, stats);
         }
     }
     if (stats[0]) {
@@ -1881,7 +1904,10 @@ cudaError_t launchWide(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t s
 }
 
 template <int SB> cudaError_t launchPair(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
-    void (*kern)(const ScanParams) = cfg.warps <= 24 ? scanKernelPair<SB, 768> : scanKernelPair<SB, 896>;
+    /* cfg.queued == 2: the heavy candidate path (one queue entry per word with candidates) */
+    void (*kern)(const ScanParams) =
+        cfg.queued == 2 ? (cfg.warps <= 24 ? scanKernelPair<SB, 768, 1> : scanKernelPair<SB, 896, 1>)
+                        : (cfg.warps <= 24 ? scanKernelPair<SB, 768, 0> : scanKernelPair<SB, 896, 0>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smemBytes);
     if (e != cudaSuccess) {
         return e;
