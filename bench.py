@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--cpu-sample-mb", type=int, default=1024)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--verify-blocks", type=int, default=4096)
-    ap.add_argument("--secondary-mb", type=int, default=256)
+    ap.add_argument("--secondary-mb", type=int, default=512)
     ap.add_argument("--shard-gib", type=int, default=8, help="N>1 secondary: config-5 shape, GiB per GPU")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="N>1: p2p = records stored into every rank's buffer by the confirm kernel itself over "

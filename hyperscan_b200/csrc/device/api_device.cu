@@ -69,7 +69,7 @@ struct RuntimeOpts {
                               * byte), 1 = two-byte hash table (FK_HASH32, ~3.3-way bank conflicts), 2 = per-byte
                               * table (FK_BYTE32, conflict-free, many more candidates), 0 = choose between 1
                               * and 2 by the modelled candidate rate of the per-byte table */
-    int bigSet = 1;          /* FK_PAIR32: sets that would overfill the 32 KiB bitmap trade classes of the
+    int bigSet = 0;          /* FK_PAIR32: sets that would overfill the 32 KiB bitmap trade classes of the
                               * second byte for a large contiguous bitmap */
     int heavy = 1;           /* FK_PAIR32 candidate path: 0 = per-lane entries, 2 = per-word entries (sets that
                               * pass many candidates), 1 = by the modelled first-stage rate */
@@ -486,6 +486,11 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                 buildPairTables(tails, (u32)im->slotBase, &pt, 32, big ? (u32)std::max(1, g_opts.bigSetClasses) : 32);
                 im->pairBytes = pt.nClass1 * 4096;
                 im->pairRate = pt.modelRate;
+                if (getenv("HSB200_TRACE")) {
+                    fprintf(stderr, "[hs_b200] class-pair tables: %u x %u classes, modelled %.4f candidates/byte, "
+                                    "%zu prefilter keys%s\n", pt.nClass0, pt.nClass1, pt.modelRate, keys.size(),
+                            big ? " (large-set layout)" : "");
+                }
                 table.resize(sizeof(pt.classWord) + sizeof(pt.pair));
                 memcpy(table.data(), pt.classWord, sizeof(pt.classWord));
                 memcpy(table.data() + sizeof(pt.classWord), pt.pair, sizeof(pt.pair));
@@ -839,8 +844,11 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
         pl->cfg.direct = 1;
         pl->cfg.stride = 1;
         /* candidate path: per-lane queue entries while candidates are rare; one entry per
-         * word with candidates once the modelled rate passes ~2 per KiB (heavy=2 forces it) */
-        pl->cfg.queued = g_opts.heavy == 2 || (g_opts.heavy == 1 && im->pairRate > 0.002) ? 2 : 1;
+         * word with candidates for sets that saturate the first stage (heavy=2 forces it).
+         * The modelled rate assumes independent slots and is ~30x below what is measured:
+         * 0.0015 modelled is ~40 candidates per KiB, where the per-word path starts to win
+         * (profiles/r02_sweep_candidate_paths.log) */
+        pl->cfg.queued = g_opts.heavy == 2 || (g_opts.heavy == 1 && im->pairRate > 0.0015) ? 2 : 1;
         pl->cfg.wide = 0;
         pl->cfg.split = 1;
         pl->cfg.grid = s->smCount;

@@ -4,7 +4,6 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
-#include <queue>
 #include <stdexcept>
 
 #include "hwlm_build.h"
@@ -359,94 +358,147 @@ std::vector<u8> emitSheng(const RawDfa &d) {
 } // namespace
 
 RawDfa dfaFromLiterals(const std::vector<DfaLiteral> &lits, bool anchored) {
-    /* trie over exact byte strings; caseless literals enter as their case variants */
-    struct Node {
-        std::map<u8, u32> child;
-        std::vector<u32> out;
-        u32 fail = 0;
+    /* Position automaton of the set -- one chain of positions per literal, a caseless
+     * letter admitting both cases, the start position looping on every byte unless the
+     * set is anchored -- determinised by the subset construction over byte classes
+     * (bytes no literal tells apart).  For literal sets this is the Aho-Corasick
+     * automaton, without enumerating case variants. */
+    struct Pos {
+        u8 lo, hi;  /* the two bytes accepted (equal unless a caseless letter) */
+        u32 next;   /* following position, 0 = the literal ends here */
+        u32 report;
     };
-    std::vector<Node> t(1);
+    std::vector<Pos> pos(1); /* position 0 = start */
+    std::vector<u32> first;  /* first position of every literal */
     for (const DfaLiteral &l : lits) {
         if (l.s.empty()) {
             throw std::runtime_error("empty literal");
         }
-        std::vector<u32> letters;
-        for (u32 i = 0; i < l.s.size(); i++) {
-            if (l.caseless && isAsciiAlpha((u8)l.s[i])) {
-                letters.push_back(i);
-            }
-        }
-        if (letters.size() > 12) {
-            throw std::runtime_error("caseless literal with too many letters for this builder");
-        }
-        for (u32 v = 0; v < (1u << letters.size()); v++) {
-            std::string s = l.s;
-            for (u32 k = 0; k < letters.size(); k++) {
-                u8 c = (u8)s[letters[k]];
-                s[letters[k]] = (char)(((v >> k) & 1) ? asciiUpper(c) : asciiLower(c));
-            }
-            u32 cur = 0;
-            for (char ch : s) {
-                auto it = t[cur].child.find((u8)ch);
-                if (it == t[cur].child.end()) {
-                    t.push_back(Node());
-                    it = t[cur].child.emplace((u8)ch, (u32)t.size() - 1).first;
-                }
-                cur = it->second;
-            }
-            t[cur].out.push_back(l.report);
+        first.push_back((u32)pos.size());
+        for (size_t i = 0; i < l.s.size(); i++) {
+            Pos p;
+            const u8 c = (u8)l.s[i];
+            const bool fold = l.caseless && isAsciiAlpha(c);
+            p.lo = fold ? asciiLower(c) : c;
+            p.hi = fold ? asciiUpper(c) : c;
+            p.next = i + 1 < l.s.size() ? (u32)pos.size() + 1 : 0;
+            p.report = l.report;
+            pos.push_back(p);
         }
     }
-    if (t.size() + 1 > 16383) {
-        throw std::runtime_error("literal set too large for a 16-bit DFA");
+    /* byte classes: bytes that occur in no literal behave alike */
+    bool used[256] = {false};
+    for (size_t i = 1; i < pos.size(); i++) {
+        used[pos[i].lo] = used[pos[i].hi] = true;
     }
-    RawDfa d;
-    const u32 n = (u32)t.size() + 1; /* state 0 = dead, trie node i = state i + 1 */
-    d.next.assign(n, std::array<u16, 256>());
-    d.reports.assign(n, {});
-    d.reportsEod.assign(n, {});
-    for (auto &row : d.next) {
-        row.fill(0);
-    }
-    d.startAnchored = 1;
-    d.startFloating = anchored ? 0 : 1;
-    if (anchored) {
-        for (u32 i = 0; i < t.size(); i++) {
-            for (const auto &kv : t[i].child) {
-                d.next[i + 1][kv.first] = (u16)(kv.second + 1);
-            }
-            d.reports[i + 1] = t[i].out;
-        }
-        return d;
-    }
-    /* Aho-Corasick: breadth first, delta(s, c) = child or delta(fail(s), c) */
-    std::queue<u32> q;
+    std::vector<u8> reps;
+    int other = -1;
     for (u32 c = 0; c < 256; c++) {
-        auto it = t[0].child.find((u8)c);
-        d.next[1][c] = it == t[0].child.end() ? 1 : (u16)(it->second + 1);
-        if (it != t[0].child.end()) {
-            t[it->second].fail = 0;
-            q.push(it->second);
+        if (used[c]) {
+            reps.push_back((u8)c);
+        } else if (other < 0) {
+            other = (int)c;
+            reps.push_back((u8)c);
         }
     }
-    while (!q.empty()) {
-        const u32 s = q.front();
-        q.pop();
-        const u32 f = t[s].fail;
-        t[s].out.insert(t[s].out.end(), t[f].out.begin(), t[f].out.end());
-        for (u32 c = 0; c < 256; c++) {
-            auto it = t[s].child.find((u8)c);
-            if (it == t[s].child.end()) {
-                d.next[s + 1][c] = d.next[f + 1][c];
+    /* DFA state = sorted set of "literal positions about to be matched" (the start
+     * position is implicit: always active when floating, active in the start state only
+     * when anchored) */
+    typedef std::vector<u32> Set;
+    std::map<Set, u32> idOf;
+    std::vector<Set> sets;
+    RawDfa d;
+    auto addState = [&](const Set &st, const std::vector<u32> &reports) -> u32 {
+        /* accepting-ness is part of the state's identity: it is entered WITH these reports */
+        Set key = st;
+        key.push_back(0xffffffffu);
+        key.insert(key.end(), reports.begin(), reports.end());
+        auto it = idOf.find(key);
+        if (it != idOf.end()) {
+            return it->second;
+        }
+        const u32 id = (u32)sets.size();
+        if (id >= 16383) {
+            throw std::runtime_error("literal set too large for a 16-bit DFA");
+        }
+        idOf.emplace(std::move(key), id);
+        sets.push_back(st);
+        d.next.push_back(std::array<u16, 256>());
+        d.next.back().fill(0);
+        d.reports.push_back(reports);
+        d.reportsEod.push_back({});
+        return id;
+    };
+    /* 0 = dead: a row of its own, never looked up by set */
+    sets.push_back(Set());
+    d.next.push_back(std::array<u16, 256>());
+    d.next.back().fill(0);
+    d.reports.push_back({});
+    d.reportsEod.push_back({});
+    /* the literals' first positions are active in the start state and -- floating sets --
+     * in every other state too, so they stay out of the sets: per byte, what stepping them
+     * yields */
+    std::vector<std::vector<u32>> firstNext(256), firstReports(256);
+    for (u32 f : first) {
+        for (u32 c : {(u32)pos[f].lo, (u32)pos[f].hi}) {
+            if (pos[f].next) {
+                firstNext[c].push_back(pos[f].next);
             } else {
-                d.next[s + 1][c] = (u16)(it->second + 1);
-                t[it->second].fail = d.next[f + 1][c] - 1;
-                q.push(it->second);
+                firstReports[c].push_back(pos[f].report);
+            }
+            if (pos[f].lo == pos[f].hi) {
+                break;
             }
         }
     }
-    for (u32 i = 0; i < t.size(); i++) {
-        d.reports[i + 1] = t[i].out;
+    Set startMark;
+    if (anchored) {
+        startMark.push_back(0); /* position 0 marks "at offset 0": only there do the literals begin */
+    }
+    const u32 start = addState(startMark, {});
+    d.startAnchored = (u16)start;
+    d.startFloating = anchored ? 0 : (u16)start;
+    for (u32 sid = 1; sid < sets.size(); sid++) {
+        const Set cur = sets[sid];
+        for (u8 c : reps) {
+            Set nxt;
+            std::vector<u32> reports;
+            bool starts = !anchored;
+            for (u32 pi : cur) {
+                if (pi == 0) {
+                    starts = true;
+                    continue;
+                }
+                const Pos &p = pos[pi];
+                if (c == p.lo || c == p.hi) {
+                    if (p.next) {
+                        nxt.push_back(p.next);
+                    } else {
+                        reports.push_back(p.report);
+                    }
+                }
+            }
+            if (starts) {
+                nxt.insert(nxt.end(), firstNext[c].begin(), firstNext[c].end());
+                reports.insert(reports.end(), firstReports[c].begin(), firstReports[c].end());
+            }
+            std::sort(nxt.begin(), nxt.end());
+            nxt.erase(std::unique(nxt.begin(), nxt.end()), nxt.end());
+            std::sort(reports.begin(), reports.end());
+            reports.erase(std::unique(reports.begin(), reports.end()), reports.end());
+            /* floating: the empty set is the start state (it can always begin a literal);
+             * anchored: nothing left to match = dead */
+            const u32 tid = nxt.empty() && reports.empty() ? (anchored ? 0 : start) : addState(nxt, reports);
+            d.next[sid][c] = (u16)tid;
+        }
+        /* bytes outside every literal share the transition of their representative */
+        if (other >= 0) {
+            for (u32 c = 0; c < 256; c++) {
+                if (!used[c]) {
+                    d.next[sid][c] = d.next[sid][other];
+                }
+            }
+        }
     }
     return d;
 }

@@ -22,6 +22,7 @@
  * of its program in the bytecode (src/rose/match.c:238).
  */
 #include "rose_build.h"
+#include "dfa_build.h"
 
 #include <algorithm>
 #include <cstring>
@@ -82,6 +83,7 @@ u32 blockSize(const PatInfo &pi) {
 struct RoseTail {
     u32 minLen, maxLen, ekeyCount, dkeyCount, invDkeyOffset;
     bool canExhaust;
+    u32 smallWriteOffset = 0;
 };
 
 /* Floating literal matcher + RoseEngine header around a finished program blob. */
@@ -114,6 +116,7 @@ std::vector<u8> finishRose(Blob &blob, const std::vector<HwlmLit> &hl, const Ros
     r.invDkeyOffset = t.invDkeyOffset;
     r.somLocationFatbitSize = fatbitSize(0);
     r.fmatcherOffset = fmatcherOffset;
+    r.smallWriteOffset = t.smallWriteOffset;
     r.fmatcherMinWidth = t.minLen;
     r.activeQueueArraySize = fatbitSize(0);
     r.handledKeyFatbitSize = fatbitSize(0);
@@ -385,6 +388,95 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
     t.dkeyCount = (u32)dkeys.size();
     t.invDkeyOffset = invDkeyOffset;
     t.canExhaust = allHighlander;
+
+    /* --- small-write engine (src/smallwrite/smallwrite_build.cpp; used by hs_scan for
+     * buffers shorter than largestBuffer, src/runtime.c:401-413): one DFA over the WHOLE
+     * literals whose reports are the offsets of report programs -- the literal's program
+     * without the literal check, which the DFA has already done -- run through
+     * roseReportAdaptor (src/rose/match.c:611-633).  Only while the automaton stays small
+     * (12 000 literal bytes, 16 K states); otherwise no engine, like the reference when its
+     * DFA limits are exceeded. --- */
+    if (opts.smallWrite && !opts.streaming) {
+        const u32 LARGEST_BUFFER = 70; /* Grey::smallWriteLargestBuffer, src/grey.cpp:135 */
+        std::vector<DfaLiteral> dl;
+        size_t budget = 0;
+        bool ok = true;
+        for (const PatInfo &pi : pats) {
+            if (pi.p->s.size() >= LARGEST_BUFFER) {
+                continue; /* cannot match in a buffer that short */
+            }
+            const bool nc = pi.p->caseless && pi.anyAlpha;
+            budget += pi.p->s.size();
+            if (budget > 12000) { /* positions of the automaton; it may still grow past 16 K states */
+                ok = false;
+                break;
+            }
+            /* report program: [CHECK_EXHAUSTED] [DEDUPE] REPORT_EXHAUST | DEDUPE_AND_REPORT | REPORT, END */
+            const u32 sz = blockSize(pi) - (pi.p->s.size() > 8 ? instrSize<InstrCheckLit>() : 0) + instrSize<InstrEnd>();
+            u32 pc = blob.reserve(sz, INSTR_ALIGN);
+            const u32 prog = pc, endAt = pc + sz - instrSize<InstrEnd>();
+            if (pi.ekey != INVALID_EKEY) {
+                InstrCheckExhausted ce;
+                memset(&ce, 0, sizeof(ce));
+                ce.code = OP_CHECK_EXHAUSTED;
+                ce.ekey = pi.ekey;
+                ce.fail_jump = endAt - pc;
+                memcpy(blob.at(pc), &ce, sizeof(ce));
+                pc += instrSize<InstrCheckExhausted>();
+                if (pi.dkey != INVALID_DKEY) {
+                    InstrDedupe dd;
+                    memset(&dd, 0, sizeof(dd));
+                    dd.code = OP_DEDUPE;
+                    dd.dkey = pi.dkey;
+                    dd.fail_jump = endAt - pc;
+                    memcpy(blob.at(pc), &dd, sizeof(dd));
+                    pc += instrSize<InstrDedupe>();
+                }
+                InstrReportExhaust re;
+                memset(&re, 0, sizeof(re));
+                re.code = OP_REPORT_EXHAUST;
+                re.onmatch = pi.p->report;
+                re.ekey = pi.ekey;
+                memcpy(blob.at(pc), &re, sizeof(re));
+            } else if (pi.dkey != INVALID_DKEY) {
+                InstrDedupeAndReport dr;
+                memset(&dr, 0, sizeof(dr));
+                dr.code = OP_DEDUPE_AND_REPORT;
+                dr.dkey = pi.dkey;
+                dr.onmatch = pi.p->report;
+                dr.fail_jump = endAt - pc;
+                memcpy(blob.at(pc), &dr, sizeof(dr));
+            } else {
+                InstrReport rr;
+                memset(&rr, 0, sizeof(rr));
+                rr.code = OP_REPORT;
+                rr.onmatch = pi.p->report;
+                memcpy(blob.at(pc), &rr, sizeof(rr));
+            }
+            InstrEnd e;
+            e.code = OP_END;
+            memcpy(blob.at(endAt), &e, sizeof(e));
+            DfaLiteral l;
+            l.s = pi.p->s;
+            l.caseless = nc;
+            l.report = prog;
+            dl.push_back(l);
+        }
+        if (ok && !dl.empty()) {
+            try {
+                const std::vector<u8> nfa = emitDfa(dfaFromLiterals(dl, false), DFA_AUTO, false);
+                SmallWriteEngine sw;
+                memset(&sw, 0, sizeof(sw));
+                sw.largestBuffer = LARGEST_BUFFER;
+                sw.start_offset = 0;
+                sw.size = (u32)(sizeof(SmallWriteEngine) + nfa.size());
+                t.smallWriteOffset = blob.add(&sw, sizeof(sw), 64);
+                blob.add(nfa.data(), nfa.size(), 64);
+            } catch (const std::runtime_error &) {
+                /* automaton too large: no small-write engine */
+            }
+        }
+    }
     return finishRose(blob, hl, t, opts, info);
 }
 

@@ -33,6 +33,8 @@ struct CompileOpts {
     bool streaming = false;      /* HS_MODE_STREAM / HS_MODE_VECTORED: history + per-stream state
                                   * (literals <= 8 bytes); src/util/compile_context.h:47-48 */
     bool vectored = false;       /* HS_MODE_VECTORED: a streaming database stamped for hs_scan_vector */
+    bool smallWrite = true;      /* block mode: also emit the small-write DFA (src/smallwrite/) for buffers
+                                  * shorter than 70 bytes when the literal set's automaton stays small */
     u64 platform = PLATFORM_NOAVX2 | PLATFORM_NOAVX512 | PLATFORM_NOAVX512VBMI;
     HwlmBuildOpts hwlm;
 };

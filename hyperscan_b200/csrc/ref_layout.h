@@ -401,6 +401,14 @@ struct McClellan {
     u32 wide_offset;
 };
 
+/* ---- small-write engine header: src/smallwrite/smallwrite_internal.h:35-39 (the
+ *      struct NFA of a McClellan / Sheng DFA follows at the next cache line) ------ */
+struct alignas(64) SmallWriteEngine {
+    u32 largestBuffer; /* buffers shorter than this go through the DFA instead of rose */
+    u32 start_offset;
+    u32 size;          /* of the engine in bytes, including the NFA */
+};
+
 /* ---- Sheng: src/nfa/sheng_internal.h:36-79 ------------------------------ */
 
 static const u8 SHENG_STATE_ACCEPT = 0x10, SHENG_STATE_DEAD = 0x20, SHENG_STATE_ACCEL = 0x40,

@@ -91,7 +91,7 @@ def test_large_literal_set_two_level_prefilter(hs, ref):
     assert want.size > 300
 
 
-@pytest.mark.parametrize("opts", [{"big_set": 0}, {"big_set_classes": 1}, {"big_set_classes": 8},
+@pytest.mark.parametrize("opts", [{"big_set": 0}, {"big_set": 1, "big_set_classes": 1}, {"big_set": 1, "big_set_classes": 8},
                                   {"first_stage": 1}, {"first_stage": 3, "prefilter": 0}, {"heavy": 0},
                                   {"heavy": 2, "big_set": 0}, {"heavy": 2, "prefilter": 0}],
                          ids=["small-layout", "1-class", "8-classes", "hash-table", "no-prefilter", "lane-entries",
@@ -106,7 +106,7 @@ def test_large_literal_set_layout_variants(hs, ref, opts):
             hs.set_runtime_option(k, v)
         _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
     finally:
-        for k, v in (("big_set", 1), ("big_set_classes", 4), ("first_stage", 3), ("prefilter", 1), ("heavy", 1)):
+        for k, v in (("big_set", 0), ("big_set_classes", 4), ("first_stage", 3), ("prefilter", 1), ("heavy", 1)):
             hs.set_runtime_option(k, v)
 
 
