@@ -71,6 +71,9 @@ struct RuntimeOpts {
                               * and 2 by the modelled candidate rate of the per-byte table */
     int bigSet = 0;          /* FK_PAIR32: sets that would overfill the 32 KiB bitmap trade classes of the
                               * second byte for a large contiguous bitmap */
+    int gram = 1;            /* FDR sets: 1 = class 4-gram first stage (FK_GRAM4) for sets that would fill the
+                              * pair kernel's 32 KiB bitmap beyond 10 % (all literals >= 4 bytes), 2 = whenever
+                              * possible, 0 = never */
     int heavy = 1;           /* FK_PAIR32 candidate path: 0 = per-lane entries, 2 = per-word entries (sets that
                               * pass many candidates), 1 = by the modelled first-stage rate */
     int bigSetClasses = 4;   /* ... classes left to the second byte (pair table = 4 KiB each) */
@@ -95,7 +98,8 @@ void initOpts() {
         {"HSB200_PF_DIST", &g_opts.pfDist},    {"HSB200_QUEUE", &g_opts.queue},
         {"HSB200_FIRST_STAGE", &g_opts.firstStage}, {"HSB200_WIDE", &g_opts.wide},
         {"HSB200_SPLIT", &g_opts.split},       {"HSB200_BIG_SET", &g_opts.bigSet},
-        {"HSB200_BIG_SET_CLASSES", &g_opts.bigSetClasses}, {"HSB200_HEAVY", &g_opts.heavy}};
+        {"HSB200_BIG_SET_CLASSES", &g_opts.bigSetClasses}, {"HSB200_HEAVY", &g_opts.heavy},
+        {"HSB200_GRAM", &g_opts.gram}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -277,6 +281,120 @@ void buildPairBitmaps(const std::vector<u32> &keys, u32 bits, std::vector<u8> *l
         }
         *shift2 = 32 - lg2;
     }
+}
+
+/* FK_GRAM4 tables: a byte -> class map (<= 32 classes) and the 1 Mbit bitmap of the class
+ * 4-grams that some literal's last four bytes can produce (caseless letters through
+ * LitInfo.msk).  Bytes no tail uses share class 0; if more than 31 byte values are in
+ * use, the two cases of a letter share a class first (a case-sensitive literal then also
+ * admits the other case at the first stage -- the exact 4-byte bitmap in L2 and the
+ * confirm sort that out), then the rarest byte values are folded together. */
+bool buildGramTables(const std::vector<LitTail> &tails, std::vector<u8> *classWords, std::vector<u8> *bitmap) {
+    u32 count[256] = {0};
+    for (const LitTail &t : tails) {
+        if (t.size < 4) {
+            return false; /* needs four known bytes per literal */
+        }
+        for (u32 p = 0; p < 4; p++) {
+            const u8 c = (u8)(t.v >> (8 * (7 - p))), m = (u8)(t.msk >> (8 * (7 - p)));
+            for (u32 b = 0; b < 256; b++) {
+                if ((b & m) == c) {
+                    count[b]++;
+                }
+            }
+        }
+    }
+    u32 cls[256];
+    std::vector<std::vector<u32>> groups; /* groups[i] = byte values of class i + 1 */
+    for (u32 b = 0; b < 256; b++) {
+        if (count[b]) {
+            groups.push_back({b});
+        }
+    }
+    auto weight = [&](const std::vector<u32> &g) {
+        u64 w = 0;
+        for (u32 b : g) {
+            w += count[b];
+        }
+        return w;
+    };
+    if (groups.size() > 31) { /* fold the cases of letters */
+        std::vector<std::vector<u32>> folded;
+        std::vector<bool> done(256, false);
+        for (const auto &g : groups) {
+            const u32 b = g[0];
+            if (done[b]) {
+                continue;
+            }
+            done[b] = true;
+            std::vector<u32> ng = {b};
+            const bool alpha = (b >= 'a' && b <= 'z') || (b >= 'A' && b <= 'Z');
+            if (alpha && count[b ^ 0x20]) {
+                ng.push_back(b ^ 0x20);
+                done[b ^ 0x20] = true;
+            }
+            folded.push_back(ng);
+        }
+        groups.swap(folded);
+    }
+    while (groups.size() > 31) { /* fold the two rarest groups */
+        size_t a = 0, b = 1;
+        if (weight(groups[b]) < weight(groups[a])) {
+            std::swap(a, b);
+        }
+        for (size_t i = 2; i < groups.size(); i++) {
+            if (weight(groups[i]) < weight(groups[a])) {
+                b = a;
+                a = i;
+            } else if (weight(groups[i]) < weight(groups[b])) {
+                b = i;
+            }
+        }
+        groups[std::min(a, b)].insert(groups[std::min(a, b)].end(), groups[std::max(a, b)].begin(),
+                                      groups[std::max(a, b)].end());
+        groups.erase(groups.begin() + (long)std::max(a, b));
+    }
+    for (u32 b = 0; b < 256; b++) {
+        cls[b] = 0;
+    }
+    for (size_t i = 0; i < groups.size(); i++) {
+        for (u32 b : groups[i]) {
+            cls[b] = (u32)i + 1;
+        }
+    }
+    classWords->resize(256 * 4);
+    for (u32 b = 0; b < 256; b++) {
+        const u32 e = (cls[b] << 2) | (cls[b] << 7) | (cls[b] << 12);
+        memcpy(classWords->data() + 4 * b, &e, 4);
+    }
+    bitmap->assign(128 * 1024, 0);
+    for (const LitTail &t : tails) {
+        /* classes each of the last four bytes can take: [0] = byte e-3 ... [3] = byte e */
+        u32 opts[4] = {0, 0, 0, 0}; /* bitmask over classes */
+        for (u32 p = 0; p < 4; p++) {
+            const u8 c = (u8)(t.v >> (8 * (7 - p))), m = (u8)(t.msk >> (8 * (7 - p)));
+            for (u32 b = 0; b < 256; b++) {
+                if ((b & m) == c) {
+                    opts[3 - p] |= 1u << cls[b];
+                }
+            }
+        }
+        for (u32 c3 = 0; c3 < 32; c3++) {
+            if (!((opts[0] >> c3) & 1)) continue;
+            for (u32 c2 = 0; c2 < 32; c2++) {
+                if (!((opts[1] >> c2) & 1)) continue;
+                for (u32 c1 = 0; c1 < 32; c1++) {
+                    if (!((opts[2] >> c1) & 1)) continue;
+                    const u32 word = c3 | (c2 << 5) | (c1 << 10);
+                    u32 w;
+                    memcpy(&w, bitmap->data() + 4 * (size_t)word, 4);
+                    w |= opts[3];
+                    memcpy(bitmap->data() + 4 * (size_t)word, &w, 4);
+                }
+            }
+        }
+    }
+    return true;
 }
 
 /* First-stage table rebuilt from the literal tails (LitInfo v/msk) and their
@@ -481,7 +599,30 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                 std::vector<u32> keys;
                 u32 kb = 0;
                 const bool keyed = g_opts.prefilter && tailKeys(tails, &kb, &keys);
-                const bool big = keyed && keys.size() * 10 > 262144 && g_opts.bigSet != 0;
+                const bool large = keyed && keys.size() * 10 > 262144; /* would fill the 32 KiB bitmap > 10 % */
+                std::vector<u8> gramBitmap;
+                if ((g_opts.gram == 2 || (g_opts.gram == 1 && large)) && keyed && kb == 4 &&
+                    buildGramTables(tails, &table, &gramBitmap)) {
+                    /* the pair evidence saturates for such sets: exact class 4-gram membership
+                     * instead (FK_GRAM4), exact raw 4-byte keys in L2 behind it */
+                    im->kind = FK_GRAM4;
+                    im->keyBytes = 4;
+                    pairBitmap.swap(gramBitmap);
+                    std::vector<u8> unused;
+                    u32 lg2 = 20;
+                    while (lg2 < 29 && (1ull << lg2) < (u64)keys.size() * 1024) {
+                        lg2++;
+                    }
+                    pairBitmap2.assign((size_t)1 << (lg2 - 3), 0);
+                    for (u32 k : keys) {
+                        const u32 hh = (k * 0x85EBCA6Bu) >> (32 - lg2);
+                        pairBitmap2[hh >> 3] |= (u8)(1u << (hh & 7));
+                    }
+                    im->bitmap2Shift = 32 - lg2;
+                    goto tables_done;
+                }
+                {
+                const bool big = large && g_opts.bigSet != 0;
                 PairTables pt;
                 buildPairTables(tails, (u32)im->slotBase, &pt, 32, big ? (u32)std::max(1, g_opts.bigSetClasses) : 32);
                 im->pairBytes = pt.nClass1 * 4096;
@@ -507,6 +648,8 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                     im->bitmapBits = bits;
                     buildPairBitmaps(keys, bits, &pairBitmap, &pairBitmap2, &im->bitmap2Shift);
                 }
+                }
+            tables_done:;
             } else if (g_opts.firstStage == 2 || (g_opts.firstStage == 0 && byteRate < 0.01)) {
                 im->kind = FK_BYTE32;
                 im->stride = 1;
@@ -583,7 +726,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     }
     im->tableBytes = (u32)table.size();
     std::vector<u8> bitmap, bitmap2;
-    if (im->kind == FK_PAIR32) {
+    if (im->kind == FK_PAIR32 || im->kind == FK_GRAM4) {
         bitmap.swap(pairBitmap);
         bitmap2.swap(pairBitmap2);
     } else if (g_opts.prefilter) {
@@ -826,6 +969,28 @@ hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     if ((g_opts.stride == 1 || g_opts.stride == 2 || g_opts.stride == 4) &&
         (im->kind == FK_HASH32 || im->kind == FK_HASH64)) {
         stride = g_opts.stride; /* any sampling subset is a sound filter */
+    }
+    if (im->kind == FK_GRAM4) {
+        warps = std::min(warps, 28);
+        while (warps > 1 && scanSmemBytes(FK_GRAM4, 0, 0, 0, 0, 0, warps) > (size_t)s->maxSmem) {
+            warps--;
+        }
+        pl->cfg.smemBytes = scanSmemBytes(FK_GRAM4, 0, 0, 0, 0, 0, warps);
+        if (pl->cfg.smemBytes > (size_t)s->maxSmem || !s->ringSplit) {
+            return HS_NOMEM;
+        }
+        pl->cfg.kind = im->kind;
+        pl->cfg.slotBase = 0;
+        pl->cfg.direct = 1;
+        pl->cfg.stride = 1;
+        pl->cfg.queued = 1;
+        pl->cfg.wide = 0;
+        pl->cfg.split = 1;
+        pl->cfg.grid = s->smCount;
+        pl->cfg.warps = warps;
+        pl->tileBytes = tile;
+        pl->nstages = (u32)std::max(0, std::min(64, g_opts.pfDist));
+        return HS_SUCCESS;
     }
     if (im->kind == FK_PAIR32) {
         /* class-pair kernel: direct loads, stride 1, queued candidates, split confirm;
@@ -1140,7 +1305,8 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"pf_dist", &g_opts.pfDist},    {"queue", &g_opts.queue},
         {"first_stage", &g_opts.firstStage}, {"wide", &g_opts.wide},
         {"split", &g_opts.split},       {"big_set", &g_opts.bigSet},
-        {"big_set_classes", &g_opts.bigSetClasses}, {"heavy", &g_opts.heavy}};
+        {"big_set_classes", &g_opts.bigSetClasses}, {"heavy", &g_opts.heavy},
+        {"gram", &g_opts.gram}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;

@@ -55,6 +55,11 @@ enum FilterKind {
                       from a per-lane byte table; u32 entry; both tables replicated per
                       lane (bank-conflict free).  FDR sets.  Table image: 256 class words
                       (c0 << 7 | c1 << 12), then 1024 pair entries */
+    FK_GRAM4 = 5,  /* index = classes of the FOUR bytes ending at a position (5 bits each) into
+                      a 1 Mbit bitmap in shared memory; no buckets.  Large FDR sets whose
+                      literals are all >= 4 bytes.  Table image: 256 class words
+                      (c << 2 | c << 7 | c << 12); ScanParams.bitmap = the 128 KiB bitmap
+                      (bit index = c[e-3] << 5 | c[e-2] << 10 | c[e-1] << 15 | c[e]) */
 };
 
 enum ConfirmKind {

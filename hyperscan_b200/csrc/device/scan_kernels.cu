@@ -1850,6 +1850,265 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
     }
 }
 
+/* ---- class 4-gram variant (FK_GRAM4): sets whose two-byte evidence saturates ----------
+ *
+ * With tens of thousands of literals every pair of letters occurs in every bucket and
+ * the pair filter above passes any four letters (~6 % of printable text).  What still
+ * separates such a set from the text is the JOINT last four bytes, so the first stage
+ * becomes an exact membership test of the class 4-gram: every byte maps to one of 32
+ * classes (per-lane rows as above, conflict free), the classes of the four bytes ending
+ * at a position form a 20-bit index into a 1 Mbit bitmap in shared memory (128 KiB;
+ * word = the three older classes, bit = the newest), one random 4-byte lookup per
+ * position.  No buckets: a set bit is a candidate for every bucket, the second-level
+ * bitmap in L2 (raw 4-byte key) and the hash confirm sort that out.
+ *
+ *   class row b (256 B): [c(b) << 2 | c(b) << 7 | c(b) << 12] x 32 lanes | 128 B unused
+ *   word address of position e = field 2..6 of E[e-3] | field 7..11 of E[e-2] | field 12..16 of E[e-1]
+ *                               (two bit-field selects), bit = E[e] >> 2 (low five bits)
+ */
+struct GramQueue {
+    static constexpr u32 SLOTS = 64;                      /* < 32 pending + <= 32 appended per step */
+    static constexpr u32 RUN_START = 8 * SLOTS;           /* entry = {chunk number, 16-bit candidate map} */
+    static constexpr u32 WARP_BYTES = RUN_START + 16;
+};
+enum { GRAM_CLASS_BYTES = 256 * 256, GRAM_BITMAP_BYTES = 128 * 1024 };
+
+/* (a & m) | (b & ~m) */
+template <u32 M> __device__ __forceinline__ u32 bitSelect(u32 a, u32 b) {
+#ifdef HSB_HOST_EMU
+    return (a & M) | (b & ~M);
+#else
+    u32 d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "n"(M));
+    return d;
+#endif
+}
+
+/* The 4 corpus bytes ending at position g (little-endian, byte g in the top lane);
+ * positions outside the readable corpus read as zero. */
+__device__ __forceinline__ u32 last4At(const ScanParams &p, u64 g) {
+    if (g < 3 || g + 5 > p.readableEnd) { /* rare: the aligned 8-byte window would leave the buffer */
+        u32 v = 0;
+        for (int z = 0; z < 4; z++) {
+            const long long q = (long long)g - 3 + z;
+            if (q >= 0 && (u64)q < p.readableEnd) {
+                v |= (u32)__ldg(p.corpus + q) << (8 * z);
+            }
+        }
+        return v;
+    }
+    const u8 *a = p.corpus + g - 3;
+    const u32 mis = (u32)((uintptr_t)a & 3);
+    const u32 *aw = reinterpret_cast<const u32 *>(a - mis);
+    return __funnelshift_r(__ldg(aw), __ldg(aw + 1), 8 * mis);
+}
+
+/* one queue entry per lane: its candidate positions against the exact 4-byte bitmap in
+ * L2; survivors go to the candidate list with every bucket set */
+__device__ HSB_NOINLINE void drainGram(const ScanParams &p, u32 qAddr, u32 first, u32 count, u32 lane,
+                                       u32 *stats) {
+    if (lane >= count) {
+        return;
+    }
+    const uint2 rs = lds64(qAddr + GramQueue::RUN_START);
+    const uint2 e = lds64(qAddr + (first + lane) * 8);
+    const u64 g0 = (((u64)rs.y << 32) | rs.x) + (u64)e.x * 16;
+    u32 cm = e.y, ncand = 0, npass = 0;
+    while (cm) {
+        const u32 j = (u32)__ffs(cm) - 1;
+        cm &= cm - 1;
+        ncand++;
+        if (p.bitmap2Shift) {
+            const u32 key = last4At(p, g0 + j);
+            const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
+            if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
+                continue;
+            }
+        }
+        npass++;
+        const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
+        if (i < p.outCap) {
+            DevCand cnd;
+            cnd.g = g0 + j;
+            cnd.buckets = 0xffu;
+            cnd.pad = 0;
+            *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
+                *reinterpret_cast<const uint4 *>(&cnd);
+        }
+    }
+    stats[0] += ncand;
+    stats[1] += npass;
+}
+
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) scanKernelGram(const HSB_GRID_CONSTANT ScanParams p) {
+    HSB_DYNAMIC_SMEM(smem);
+    const u32 lane = threadIdx.x & 31;
+    const u32 warp = threadIdx.x >> 5;
+    const u32 nwarps = blockDim.x >> 5;
+    {
+        /* p.table = 256 class words; p.bitmap = the 128 KiB class 4-gram bitmap */
+        const u32 *g = reinterpret_cast<const u32 *>(p.table);
+        u32 *s = reinterpret_cast<u32 *>(smem);
+        for (u32 i = threadIdx.x; i < 256 * 64; i += blockDim.x) {
+            s[i] = ((i >> 5) & 1) ? 0u : __ldg(g + (i >> 6));
+        }
+        const uint4 *bm = reinterpret_cast<const uint4 *>(p.bitmap);
+        uint4 *sb = reinterpret_cast<uint4 *>(smem + GRAM_CLASS_BYTES);
+        for (u32 i = threadIdx.x; i < GRAM_BITMAP_BYTES / 16; i += blockDim.x) {
+            sb[i] = __ldg(bm + i);
+        }
+    }
+    __syncthreads();
+    const u32 clsAddr = smemAddr(smem);
+    const u32 gramAddr = clsAddr + GRAM_CLASS_BYTES;
+    const u32 laneOff = lane * 4;
+    const u32 qAddr = gramAddr + GRAM_BITMAP_BYTES + warp * GramQueue::WARP_BYTES;
+
+    const u32 gwarp = blockIdx.x * nwarps + warp;
+    const u32 totalWarps = gridDim.x * nwarps;
+    const u32 qq = p.ntiles / totalWarps, rem = p.ntiles % totalWarps;
+    const u32 myCount = qq + (gwarp < rem ? 1u : 0u);
+    const u32 myFirst = p.tileFirst + gwarp * qq + min(gwarp, rem);
+    if (myCount == 0) {
+        return;
+    }
+    const u64 runStart = (u64)myFirst * p.tileBytes;
+    u64 runEnd = runStart + (u64)myCount * p.tileBytes;
+    if (runEnd > p.corpusBytes) {
+        runEnd = p.corpusBytes;
+    }
+    const u32 nsteps = (u32)((runEnd - runStart + 511) >> 9);
+    const u8 *ptr = p.corpus + runStart + lane * 16;
+    const u8 *const endPtr = p.corpus + p.readableEnd;
+    if (lane == 0) {
+        sts64(qAddr + GramQueue::RUN_START, (u32)runStart, (u32)(runStart >> 32));
+    }
+    u32 stats[3] = {0, 0, 0};
+    u32 qn = 0;
+    auto load = [&](const u8 *src, bool guard) -> uint4 {
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (!guard || src + 16 <= endPtr) {
+            r = ldCs128(src);
+        }
+        return r;
+    };
+    auto cls = [&](u32 w, int r) -> u32 { return lds32(clsAddr + __byte_perm(w, laneOff, 0x5504 + (r << 4))); };
+    const size_t pfBytes = (size_t)p.nstages * 512 + lane * 48;
+
+    /* prevTail: word address (fields of the classes) of the three bytes before the lane's
+     * chunk, i.e. the address its first position uses; lane 0 inherits lane 31's of the
+     * previous step.  Entering a run: the 16 bytes before it. */
+    u32 carryTail = 0;
+    if (runStart != 0) {
+        const u32 hw = __ldg(reinterpret_cast<const u32 *>(p.corpus + runStart - 4));
+        carryTail = bitSelect<0x7fu>(cls(hw, 1), bitSelect<0xfffu>(cls(hw, 2), cls(hw, 3)));
+    } else {
+        /* nothing before the corpus: the class of byte 0x00 stands in (a literal cannot
+         * start before position 0, the block lookup in confirm rejects such candidates) */
+        const u32 z = cls(0, 0);
+        carryTail = bitSelect<0x7fu>(z, bitSelect<0xfffu>(z, z));
+    }
+    auto compute = [&](const uint4 cur, const u32 chunk) {
+        const u32 w[4] = {cur.x, cur.y, cur.z, cur.w};
+        u32 E[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                E[4 * k + r] = cls(w[k], r);
+            }
+        }
+        /* address of the position AFTER this lane's chunk = what the next lane starts from */
+        const u32 myTail = bitSelect<0x7fu>(E[13], bitSelect<0xfffu>(E[14], E[15]));
+        const u32 recv = __shfl_sync(0xffffffffu, myTail, (lane + 31) & 31);
+        const u32 tail = lane == 0 ? carryTail : recv;
+        carryTail = recv; /* lane 0: lane 31's tail, for the next step */
+        u32 cm = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            u32 addr;
+            if (j == 0) {
+                addr = tail;
+            } else if (j == 1) {
+                /* (c[-2], c[-1], c[0]): the tail moved down one field, E[0] on top */
+                addr = bitSelect<0xfffu>((tail >> 5) & 0xffcu, E[0]);
+            } else if (j == 2) {
+                addr = bitSelect<0x7fu>((tail >> 10) & 0x7cu, bitSelect<0xfffu>(E[0], E[1]));
+            } else {
+                addr = bitSelect<0x7fu>(E[j - 3], bitSelect<0xfffu>(E[j - 2], E[j - 1]));
+            }
+            const u32 word = lds32(gramAddr + addr);
+            const u32 t = __funnelshift_r(word, 0, E[j] >> 2); /* bit c(byte j) of the word */
+            cm = __funnelshift_r(cm, t, 1);
+        }
+        cm >>= 16;
+        const u32 bal = __ballot_sync(0xffffffffu, cm != 0);
+        if (bal) {
+            if (cm) {
+                const u32 e = qn + __popc(bal & ((1u << lane) - 1));
+                sts64(qAddr + e * 8, chunk, cm);
+            }
+            qn += __popc(bal);
+            if (qn >= 32) {
+                __syncwarp();
+                qn -= 32;
+                drainGram(p, qAddr, qn, 32, lane, stats);
+                __syncwarp();
+            }
+        }
+    };
+    const u64 readableSteps = (p.readableEnd - runStart) >> 9;
+    const u32 nFast = readableSteps >= (u64)nsteps + 2 ? nsteps : (readableSteps > 2 ? (u32)readableSteps - 2 : 0);
+    uint4 cur = load(ptr, true);
+    uint4 nxt = load(ptr + 512, true);
+    u32 step = 0;
+#pragma unroll 1
+    for (; step + 4 <= nFast; step += 4, ptr += 2048) {
+        if ((lane & 1) == 0) {
+            const u8 *pf = ptr + pfBytes;
+            if (pf < endPtr) {
+                prefetchL2(pf);
+            }
+        }
+        const uint4 n2 = ldCs128(ptr + 1024);
+        compute(cur, step * 32 + lane);
+        const uint4 n3 = ldCs128(ptr + 1536);
+        compute(nxt, step * 32 + 32 + lane);
+        cur = ldCs128(ptr + 2048);
+        compute(n2, step * 32 + 64 + lane);
+        nxt = ldCs128(ptr + 2560);
+        compute(n3, step * 32 + 96 + lane);
+    }
+#pragma unroll 1
+    for (; step < nsteps; step++, ptr += 512) {
+        const uint4 n2 = load(ptr + 1024, step >= nFast);
+        compute(cur, step * 32 + lane);
+        cur = nxt;
+        nxt = n2;
+    }
+    if (qn) {
+        __syncwarp();
+        drainGram(p, qAddr, 0, qn, lane, stats);
+    }
+    if (stats[0]) {
+        atomicAdd(p.counters + CTR_CANDIDATES, stats[0]);
+    }
+    if (stats[1]) {
+        atomicAdd(p.counters + CTR_PREFILTER_PASS, stats[1]);
+    }
+}
+
+cudaError_t launchGram(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    void (*kern)(const ScanParams) = cfg.warps <= 24 ? scanKernelGram<768> : scanKernelGram<896>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smemBytes);
+    if (e != cudaSuccess) {
+        return e;
+    }
+    HSB_LAUNCH(kern, cfg.grid, cfg.warps * 32, cfg.smemBytes, stream, p);
+    return cudaGetLastError();
+}
+
 /* Split mode, second kernel: one thread per candidate of the list the scan
  * kernel filled -- hash confirm, block lookup, literal program, record. */
 __global__ void __launch_bounds__(256) confirmKernel(const HSB_GRID_CONSTANT ScanParams p) {
@@ -1953,6 +2212,9 @@ cudaError_t launchStride(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t
 
 size_t scanSmemBytes(int kind, u32 tableBytes, u32 bitmapBytes, int warps, u32 nstages,
                      u32 tileBytes, int queueWarps) {
+    if (kind == FK_GRAM4) { /* class rows + 1 Mbit class 4-gram bitmap + queues */
+        return (size_t)GRAM_CLASS_BYTES + GRAM_BITMAP_BYTES + (size_t)queueWarps * GramQueue::WARP_BYTES;
+    }
     if (kind == FK_PAIR32) { /* class rows + pair table (tableBytes) + contiguous bitmap, if any + queues */
         return (size_t)PAIR_CLASS_BYTES + tableBytes + bitmapBytes + (size_t)queueWarps * PairQueue::WARP_BYTES;
     }
@@ -2054,6 +2316,12 @@ cudaError_t launchPublishCount(const ScanParams &p, cudaStream_t stream) {
 }
 
 cudaError_t launchScan(const LaunchCfg &cfg, const ScanParams &p, cudaStream_t stream) {
+    if (cfg.kind == FK_GRAM4) {
+        if (!cfg.split || cfg.warps > 28) {
+            return cudaErrorInvalidValue;
+        }
+        return launchGram(cfg, p, stream);
+    }
     if (cfg.kind == FK_PAIR32) {
         if (!cfg.split || cfg.warps > 28) {
             return cudaErrorInvalidValue;

@@ -22,7 +22,7 @@ import oracle.ref as ref  # noqa: E402
 
 DEFAULTS = {"warps": 0, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1, "rebuild": 1,
             "domain": 0, "direct": 1, "replicas": 1, "pf_dist": 8, "queue": 2, "first_stage": 3, "wide": 1,
-            "split": 1, "big_set": 0, "big_set_classes": 4, "heavy": 1, "initial_ring": 1 << 20}
+            "split": 1, "big_set": 0, "big_set_classes": 4, "heavy": 1, "gram": 1, "initial_ring": 1 << 20}
 
 
 def fuzz_streams(args, rng):
@@ -181,7 +181,7 @@ def main():
                         split=int(rng.integers(0, 2)), first_stage=int(rng.choice([1, 3])))
         elif mode == 7:   # class-pair kernel: layouts and prefilter
             opts.update(first_stage=3, big_set=int(rng.integers(0, 2)), big_set_classes=int(rng.choice([1, 2, 4, 8])),
-                        heavy=int(rng.choice([0, 1, 2])),
+                        heavy=int(rng.choice([0, 1, 2])), gram=int(rng.choice([0, 1, 2, 2])),
                         prefilter=int(rng.integers(0, 2)), tile_bytes=int(rng.choice([512, 1024, 4096])))
         # modes 8, 9: the defaults (class-pair for FDR sets, wide + split for the per-byte tables)
         fat = 48 < nl <= 96 and rng.random() < 0.5 and ref.best_isa() != "corei7"

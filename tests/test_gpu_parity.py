@@ -93,9 +93,10 @@ def test_large_literal_set_two_level_prefilter(hs, ref):
 
 @pytest.mark.parametrize("opts", [{"big_set": 0}, {"big_set": 1, "big_set_classes": 1}, {"big_set": 1, "big_set_classes": 8},
                                   {"first_stage": 1}, {"first_stage": 3, "prefilter": 0}, {"heavy": 0},
-                                  {"heavy": 2, "big_set": 0}, {"heavy": 2, "prefilter": 0}],
+                                  {"heavy": 2, "big_set": 0}, {"heavy": 2, "prefilter": 0}, {"gram": 2},
+                                  {"gram": 0}],
                          ids=["small-layout", "1-class", "8-classes", "hash-table", "no-prefilter", "lane-entries",
-                              "word-entries", "word-entries-no-prefilter"])
+                              "word-entries", "word-entries-no-prefilter", "class-4-gram", "no-4-gram"])
 def test_large_literal_set_layout_variants(hs, ref, opts):
     """The class-pair kernel's shared-memory layouts (pair table size vs. bitmap
     size) and the older hash-table first stage give the same matches."""
@@ -106,8 +107,23 @@ def test_large_literal_set_layout_variants(hs, ref, opts):
             hs.set_runtime_option(k, v)
         _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
     finally:
-        for k, v in (("big_set", 0), ("big_set_classes", 4), ("first_stage", 3), ("prefilter", 1), ("heavy", 1)):
+        for k, v in (("big_set", 0), ("big_set_classes", 4), ("first_stage", 3), ("prefilter", 1), ("heavy", 1),
+                     ("gram", 1)):
             hs.set_runtime_option(k, v)
+
+
+@pytest.mark.parametrize("alphabet", [b"abcdefghijklmnopqrstuvwxyz", bytes(range(0x21, 0x7f)), bytes(range(256))])
+def test_class_4gram_first_stage_alphabets(hs, ref, alphabet):
+    """FK_GRAM4 forced on sets over few and over many byte values (more than 31 in use:
+    case folding, then the rarest values share classes)."""
+    lits, flags, ids = synth.literal_set(400, min_len=4, max_len=10, seed=61, caseless_frac=0.3, alphabet=alphabet)
+    data, off, ln = synth.ragged_corpus([0, 3, 4, 5, 100, 1024, 5000, 70000], lits, seed=62, plant_per_kb=5,
+                                        alphabet=alphabet + b"AB")
+    try:
+        hs.set_runtime_option("gram", 2)
+        _check_all(hs, ref, lits, flags, ids, data, off, ln, use_brute=False)
+    finally:
+        hs.set_runtime_option("gram", 1)
 
 
 def test_config5_shape_at_scale(hs, ref, real_gpu):
