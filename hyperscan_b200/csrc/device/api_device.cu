@@ -364,10 +364,11 @@ bool buildGramTables(const std::vector<LitTail> &tails, std::vector<u8> *classWo
     }
     classWords->resize(256 * 4);
     for (u32 b = 0; b < 256; b++) {
-        const u32 e = (cls[b] << 2) | (cls[b] << 7) | (cls[b] << 12);
+        const u32 e = cls[b] * 4;
         memcpy(classWords->data() + 4 * b, &e, 4);
     }
-    bitmap->assign(128 * 1024, 0);
+    /* word index c[e-3] + 33 c[e-2] + 1025 c[e-1] (kernels.h FK_GRAM4): sized like the kernel's window */
+    bitmap->assign((size_t)scanSmemBytes(FK_GRAM4, 0, 0, 0, 0, 0, 0) - 65536, 0);
     for (const LitTail &t : tails) {
         /* classes each of the last four bytes can take: [0] = byte e-3 ... [3] = byte e */
         u32 opts[4] = {0, 0, 0, 0}; /* bitmask over classes */
@@ -385,7 +386,7 @@ bool buildGramTables(const std::vector<LitTail> &tails, std::vector<u8> *classWo
                 if (!((opts[1] >> c2) & 1)) continue;
                 for (u32 c1 = 0; c1 < 32; c1++) {
                     if (!((opts[2] >> c1) & 1)) continue;
-                    const u32 word = c3 | (c2 << 5) | (c1 << 10);
+                    const u32 word = c3 + 33 * c2 + 1025 * c1;
                     u32 w;
                     memcpy(&w, bitmap->data() + 4 * (size_t)word, 4);
                     w |= opts[3];

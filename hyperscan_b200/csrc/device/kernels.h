@@ -58,8 +58,8 @@ enum FilterKind {
     FK_GRAM4 = 5,  /* index = classes of the FOUR bytes ending at a position (5 bits each) into
                       a 1 Mbit bitmap in shared memory; no buckets.  Large FDR sets whose
                       literals are all >= 4 bytes.  Table image: 256 class words
-                      (c << 2 | c << 7 | c << 12); ScanParams.bitmap = the 128 KiB bitmap
-                      (bit index = c[e-3] << 5 | c[e-2] << 10 | c[e-1] << 15 | c[e]) */
+                      (4 * c); ScanParams.bitmap = the bitmap (bitmapBytes), bit c[e] of word
+                      c[e-3] + 33 c[e-2] + 1025 c[e-1] */
 };
 
 enum ConfirmKind {

@@ -1862,27 +1862,21 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
  * position.  No buckets: a set bit is a candidate for every bucket, the second-level
  * bitmap in L2 (raw 4-byte key) and the hash confirm sort that out.
  *
- *   class row b (256 B): [c(b) << 2 | c(b) << 7 | c(b) << 12] x 32 lanes | 128 B unused
- *   word address of position e = field 2..6 of E[e-3] | field 7..11 of E[e-2] | field 12..16 of E[e-1]
- *                               (two bit-field selects), bit = E[e] >> 2 (low five bits)
- */
+ *   class row b (256 B): [E = 4 * c(b)] x 32 lanes | 128 B unused
+ *   byte address of position e's word = E[e-3] + 33 * E[e-2] + 1025 * E[e-1]   (two IMADs)
+ *   bit = E[e] >> 2
+ *
+ * The word index c[e-3] + 33 c[e-2] + 1025 c[e-1] instead of the plain bit fields
+ * c[e-3] | c[e-2] << 5 | c[e-1] << 10: the bank of a lookup is then (c[e-3] + c[e-2] +
+ * c[e-1]) mod 32, not c[e-3] alone -- with the plain fields every lane whose byte e-3 is
+ * no letter (class 0: half of printable text) hits bank 0 at a different address, 11
+ * wavefronts per lookup measured (profiles/r02_ncu_gram_plain_fields.csv) against ~3.5 now. */
 struct GramQueue {
     static constexpr u32 SLOTS = 64;                      /* < 32 pending + <= 32 appended per step */
     static constexpr u32 RUN_START = 8 * SLOTS;           /* entry = {chunk number, 16-bit candidate map} */
     static constexpr u32 WARP_BYTES = RUN_START + 16;
 };
-enum { GRAM_CLASS_BYTES = 256 * 256, GRAM_BITMAP_BYTES = 128 * 1024 };
-
-/* (a & m) | (b & ~m) */
-template <u32 M> __device__ __forceinline__ u32 bitSelect(u32 a, u32 b) {
-#ifdef HSB_HOST_EMU
-    return (a & M) | (b & ~M);
-#else
-    u32 d;
-    asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(d) : "r"(a), "r"(b), "n"(M));
-    return d;
-#endif
-}
+enum { GRAM_CLASS_BYTES = 256 * 256, GRAM_BITMAP_BYTES = 4 * (31 * (1 + 33 + 1025) + 1 + 63) / 64 * 64 };
 
 /* The 4 corpus bytes ending at position g (little-endian, byte g in the top lane);
  * positions outside the readable corpus read as zero. */
@@ -1996,50 +1990,41 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelGram(const HSB_GRID_CONSTAN
     auto cls = [&](u32 w, int r) -> u32 { return lds32(clsAddr + __byte_perm(w, laneOff, 0x5504 + (r << 4))); };
     const size_t pfBytes = (size_t)p.nstages * 512 + lane * 48;
 
-    /* prevTail: word address (fields of the classes) of the three bytes before the lane's
-     * chunk, i.e. the address its first position uses; lane 0 inherits lane 31's of the
-     * previous step.  Entering a run: the 16 bytes before it. */
-    u32 carryTail = 0;
+    /* carryPack: E of the three bytes before the lane's chunk, one per byte lane (E < 128);
+     * lane 0 inherits lane 31's of the previous step.  Entering a run: the bytes before it;
+     * at the very start of the corpus the class of byte 0x00 stands in (a literal cannot
+     * begin before position 0: the block lookup in confirm rejects such candidates). */
+    u32 carryPack;
     if (runStart != 0) {
         const u32 hw = __ldg(reinterpret_cast<const u32 *>(p.corpus + runStart - 4));
-        carryTail = bitSelect<0x7fu>(cls(hw, 1), bitSelect<0xfffu>(cls(hw, 2), cls(hw, 3)));
+        carryPack = cls(hw, 1) | (cls(hw, 2) << 8) | (cls(hw, 3) << 16);
     } else {
-        /* nothing before the corpus: the class of byte 0x00 stands in (a literal cannot
-         * start before position 0, the block lookup in confirm rejects such candidates) */
         const u32 z = cls(0, 0);
-        carryTail = bitSelect<0x7fu>(z, bitSelect<0xfffu>(z, z));
+        carryPack = z | (z << 8) | (z << 16);
     }
     auto compute = [&](const uint4 cur, const u32 chunk) {
         const u32 w[4] = {cur.x, cur.y, cur.z, cur.w};
-        u32 E[16];
+        u32 E[19]; /* E[3 + j] = 4 * class of the lane's byte j; E[0..2] = the three bytes before */
 #pragma unroll
         for (int k = 0; k < 4; k++) {
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                E[4 * k + r] = cls(w[k], r);
+                E[3 + 4 * k + r] = cls(w[k], r);
             }
         }
-        /* address of the position AFTER this lane's chunk = what the next lane starts from */
-        const u32 myTail = bitSelect<0x7fu>(E[13], bitSelect<0xfffu>(E[14], E[15]));
-        const u32 recv = __shfl_sync(0xffffffffu, myTail, (lane + 31) & 31);
-        const u32 tail = lane == 0 ? carryTail : recv;
-        carryTail = recv; /* lane 0: lane 31's tail, for the next step */
+        const u32 myPack = E[16] | (E[17] << 8) | (E[18] << 16);
+        const u32 recv = __shfl_sync(0xffffffffu, myPack, (lane + 31) & 31);
+        const u32 prev = lane == 0 ? carryPack : recv;
+        carryPack = recv; /* lane 0: lane 31's, for the next step */
+        E[0] = prev & 0xffu;
+        E[1] = (prev >> 8) & 0xffu;
+        E[2] = prev >> 16;
         u32 cm = 0;
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-            u32 addr;
-            if (j == 0) {
-                addr = tail;
-            } else if (j == 1) {
-                /* (c[-2], c[-1], c[0]): the tail moved down one field, E[0] on top */
-                addr = bitSelect<0xfffu>((tail >> 5) & 0xffcu, E[0]);
-            } else if (j == 2) {
-                addr = bitSelect<0x7fu>((tail >> 10) & 0x7cu, bitSelect<0xfffu>(E[0], E[1]));
-            } else {
-                addr = bitSelect<0x7fu>(E[j - 3], bitSelect<0xfffu>(E[j - 2], E[j - 1]));
-            }
+            const u32 addr = E[j] + 33u * E[j + 1] + 1025u * E[j + 2];
             const u32 word = lds32(gramAddr + addr);
-            const u32 t = __funnelshift_r(word, 0, E[j] >> 2); /* bit c(byte j) of the word */
+            const u32 t = __funnelshift_r(word, 0, E[j + 3] >> 2); /* bit c(byte j) of the word */
             cm = __funnelshift_r(cm, t, 1);
         }
         cm >>= 16;
