@@ -609,15 +609,22 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                     im->kind = FK_GRAM4;
                     im->keyBytes = 4;
                     pairBitmap.swap(gramBitmap);
-                    std::vector<u8> unused;
-                    u32 lg2 = 20;
-                    while (lg2 < 29 && (1ull << lg2) < (u64)keys.size() * 1024) {
+                    /* second level in L2: one BYTE per slot = the buckets of the literals whose
+                     * raw 4-byte key hashes there (~64 slots per key, <= 64 MB), so that a
+                     * survivor reaches confirm with its real buckets, not all eight */
+                    u32 lg2 = 16;
+                    while (lg2 < 26 && (1ull << lg2) < (u64)keys.size() * 64) {
                         lg2++;
                     }
-                    pairBitmap2.assign((size_t)1 << (lg2 - 3), 0);
-                    for (u32 k : keys) {
-                        const u32 hh = (k * 0x85EBCA6Bu) >> (32 - lg2);
-                        pairBitmap2[hh >> 3] |= (u8)(1u << (hh & 7));
+                    pairBitmap2.assign((size_t)1 << lg2, 0);
+                    for (const LitTail &t : tails) {
+                        const u32 v = (u32)(t.v >> 32), care = (u32)(t.msk >> 32), dc = ~care;
+                        u32 sub = 0;
+                        do {
+                            const u32 k = (v & care) | sub;
+                            pairBitmap2[(k * 0x85EBCA6Bu) >> (32 - lg2)] |= (u8)(1u << (t.bucket & 7));
+                            sub = (sub - dc) & dc;
+                        } while (sub);
                     }
                     im->bitmap2Shift = 32 - lg2;
                     goto tables_done;

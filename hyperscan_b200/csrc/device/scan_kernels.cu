@@ -1872,50 +1872,36 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
  * no letter (class 0: half of printable text) hits bank 0 at a different address, 11
  * wavefronts per lookup measured (profiles/r02_ncu_gram_plain_fields.csv) against ~3.5 now. */
 struct GramQueue {
-    static constexpr u32 SLOTS = 64;                      /* < 32 pending + <= 32 appended per step */
-    static constexpr u32 RUN_START = 8 * SLOTS;           /* entry = {chunk number, 16-bit candidate map} */
+    static constexpr u32 SLOTS = 64;                      /* < 32 pending + <= 32 appended per round */
+    static constexpr u32 RUN_START = 16 * SLOTS;          /* entry = {word offset in the run, 4-bit candidate map,
+                                                           * the word before, the word}: the bytes travel along */
     static constexpr u32 WARP_BYTES = RUN_START + 16;
 };
 enum { GRAM_CLASS_BYTES = 256 * 256, GRAM_BITMAP_BYTES = 4 * (31 * (1 + 33 + 1025) + 1 + 63) / 64 * 64 };
 
-/* The 4 corpus bytes ending at position g (little-endian, byte g in the top lane);
- * positions outside the readable corpus read as zero. */
-__device__ __forceinline__ u32 last4At(const ScanParams &p, u64 g) {
-    if (g < 3 || g + 5 > p.readableEnd) { /* rare: the aligned 8-byte window would leave the buffer */
-        u32 v = 0;
-        for (int z = 0; z < 4; z++) {
-            const long long q = (long long)g - 3 + z;
-            if (q >= 0 && (u64)q < p.readableEnd) {
-                v |= (u32)__ldg(p.corpus + q) << (8 * z);
-            }
-        }
-        return v;
-    }
-    const u8 *a = p.corpus + g - 3;
-    const u32 mis = (u32)((uintptr_t)a & 3);
-    const u32 *aw = reinterpret_cast<const u32 *>(a - mis);
-    return __funnelshift_r(__ldg(aw), __ldg(aw + 1), 8 * mis);
-}
-
-/* one queue entry per lane: its candidate positions against the exact 4-byte bitmap in
- * L2; survivors go to the candidate list with every bucket set */
+/* 32 queue entries, one word with candidates per lane (1.02 candidates on average, so the
+ * lanes stay in step and a drain costs about ONE L2 round trip): the exact raw 4-byte key
+ * against the second-level table in L2 -- one BYTE per slot, the buckets whose literals
+ * own a key hashing there -- and the survivors, with those buckets, to the candidate list. */
 __device__ HSB_NOINLINE void drainGram(const ScanParams &p, u32 qAddr, u32 first, u32 count, u32 lane,
                                        u32 *stats) {
     if (lane >= count) {
         return;
     }
     const uint2 rs = lds64(qAddr + GramQueue::RUN_START);
-    const uint2 e = lds64(qAddr + (first + lane) * 8);
-    const u64 g0 = (((u64)rs.y << 32) | rs.x) + (u64)e.x * 16;
+    const uint4 e = lds128(qAddr + (first + lane) * 16);
+    const u64 g0 = (((u64)rs.y << 32) | rs.x) + e.x;
     u32 cm = e.y, ncand = 0, npass = 0;
     while (cm) {
-        const u32 j = (u32)__ffs(cm) - 1;
+        const u32 q = (u32)__ffs(cm) - 1;
         cm &= cm - 1;
         ncand++;
+        u32 buckets = 0xffu;
         if (p.bitmap2Shift) {
-            const u32 key = last4At(p, g0 + j);
+            const u32 key = __funnelshift_rc(e.z, e.w, 8 * (q + 1));
             const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
-            if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
+            buckets = __ldg(reinterpret_cast<const u8 *>(p.bitmap2) + h2);
+            if (!buckets) {
                 continue;
             }
         }
@@ -1923,8 +1909,8 @@ __device__ HSB_NOINLINE void drainGram(const ScanParams &p, u32 qAddr, u32 first
         const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
         if (i < p.outCap) {
             DevCand cnd;
-            cnd.g = g0 + j;
-            cnd.buckets = 0xffu;
+            cnd.g = g0 + q;
+            cnd.buckets = buckets;
             cnd.pad = 0;
             *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
                 *reinterpret_cast<const uint4 *>(&cnd);
@@ -2028,18 +2014,32 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelGram(const HSB_GRID_CONSTAN
             cm = __funnelshift_r(cm, t, 1);
         }
         cm >>= 16;
-        const u32 bal = __ballot_sync(0xffffffffu, cm != 0);
-        if (bal) {
-            if (cm) {
-                const u32 e = qn + __popc(bal & ((1u << lane) - 1));
-                sts64(qAddr + e * 8, chunk, cm);
+        if (__any_sync(0xffffffffu, cm != 0)) {
+            /* four static rounds, one per word of the lane: the lanes whose word k holds a
+             * candidate append it with its bytes; 32 pending entries are drained at once */
+            u32 pw = __shfl_up_sync(0xffffffffu, cur.w, 1);
+            if (lane == 0) { /* the word before this step's 512 bytes */
+                pw = (runStart | chunk) ? __ldg(reinterpret_cast<const u32 *>(p.corpus + runStart) + (size_t)chunk * 4 - 1)
+                                        : 0u;
             }
-            qn += __popc(bal);
-            if (qn >= 32) {
-                __syncwarp();
-                qn -= 32;
-                drainGram(p, qAddr, qn, 32, lane, stats);
-                __syncwarp();
+            const u32 wv[5] = {pw, cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const u32 m = (cm >> (4 * k)) & 0xfu;
+                const u32 bal = __ballot_sync(0xffffffffu, m != 0);
+                if (bal) {
+                    if (m) {
+                        const u32 slot = qn + __popc(bal & ((1u << lane) - 1));
+                        sts128(qAddr + slot * 16, chunk * 16 + 4 * k, m, wv[k], wv[k + 1]);
+                    }
+                    qn += __popc(bal);
+                    if (qn >= 32) {
+                        __syncwarp();
+                        qn -= 32;
+                        drainGram(p, qAddr, qn, 32, lane, stats);
+                        __syncwarp();
+                    }
+                }
             }
         }
     };
