@@ -111,7 +111,11 @@ void initOpts() {
 /* ---- device image of one database --------------------------------------- */
 
 struct DevImage {
-    const hs_database_t *db = nullptr;
+    const hs_database_t *db = nullptr;   /* identity of the database the image was built from (a key: never
+                                          * dereferenced -- the application may have freed it) */
+    std::vector<u8> dbCopy;
+    u32 dbCopyShift = 0;              /* its bytes (header + bytecode, bytecode offset preserved), so that
+                                          * hs_clone_scratch can rebuild the image without the original */
     u32 crc = 0, length = 0;
     u8 *d_bc = nullptr;
     u8 *d_table = nullptr;
@@ -525,6 +529,14 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
         return HS_NOMEM;
     }
     im->db = db;
+    {
+        /* same address modulo 64 as the original, so that every offset-derived alignment holds */
+        const size_t total = sizeof(DbHeader) + h->length;
+        im->dbCopy.resize(total + 128);
+        const size_t want = (uintptr_t)db & 63, have = (uintptr_t)im->dbCopy.data() & 63;
+        im->dbCopyShift = (u32)((want + 64 - have) & 63);
+        memcpy(im->dbCopy.data() + im->dbCopyShift, db, std::min(total, (size_t)h->bytecode + h->length));
+    }
     im->crc = h->crc32;
     im->length = h->length;
     im->groups = r->initialGroups & r->floating_group_mask;
@@ -1456,7 +1468,16 @@ hs_error_t hs_clone_scratch(const hs_scratch_t *src, hs_scratch_t **dest) {
     }
     for (const DevImage *im : *src->images) {
         const DevImage *mine = nullptr;
-        r = findImage(s, im->db, &mine);
+        /* rebuild from the source image's own copy of the database: the application may
+         * have freed the original (legal in the reference, whose clone never touches it) */
+        const hs_database_t *copy = (const hs_database_t *)(im->dbCopy.data() + im->dbCopyShift);
+        DevImage *fresh = nullptr;
+        r = buildImage(copy, &fresh);
+        if (r == HS_SUCCESS) {
+            fresh->db = im->db; /* keep the identity the application knows */
+            s->images->push_back(fresh);
+            mine = fresh;
+        }
         if (r != HS_SUCCESS) {
             hs_free_scratch(s);
             return r;

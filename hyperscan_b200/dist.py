@@ -138,7 +138,10 @@ class PeerExchange:
         self.capi._check(self.capi.lib().hs_b200_peer_buffer_read(self.mine, raw.ctypes.data, self.bytes))
         raw = raw.reshape(self.world, self.cap + 1)
         counts = [int(raw[r, 0]["id"]) for r in range(self.world)]
-        parts = [raw[r, 1:1 + min(counts[r], self.cap)] for r in range(self.world)]
+        if max(counts) > self.cap:
+            raise RuntimeError("peer exchange buffer overflowed: a rank published %d records, capacity %d"
+                               % (max(counts), self.cap))
+        parts = [raw[r, 1:1 + counts[r]] for r in range(self.world)]
         return counts, np.concatenate(parts) if parts else np.zeros(0, dtype=MATCH_DTYPE)
 
     def close(self):

@@ -161,3 +161,24 @@ def test_scratch_is_usable_from_a_thread_with_another_current_device(hs, ref, re
     assert out["rc"] == hs.HS_SUCCESS and out["dev"] == 0
     scratch.free()
     torch.cuda.set_device(0)
+
+
+def test_clone_scratch_after_the_database_was_freed(hs):
+    """The reference's hs_clone_scratch never touches a database; here the clone rebuilds
+    its device images from the source scratch's own copy of the bytes, so a database the
+    application has already freed is not dereferenced (round-1 advisor finding)."""
+    import ctypes as C
+    db = hs.compile_lit_multi([b"abcdef", b"xyz"], [0, 0], [1, 2])
+    keep = hs.compile_lit_multi([b"abcdef", b"xyz"], [0, 0], [1, 2])
+    scratch = hs.Scratch(db)
+    db.__del__()                                   # hs_free_database
+    db.ptr = None
+    clone = C.c_void_p()
+    assert hs.lib().hs_clone_scratch(scratch.ptr, C.byref(clone)) == hs.HS_SUCCESS
+    twin = hs.Scratch.__new__(hs.Scratch)
+    twin.ptr = clone
+    rc, out = hs.scan(keep, b"..abcdef..xyz", twin)
+    assert rc == hs.HS_SUCCESS and out == [(1, 8), (2, 13)]
+    assert hs.lib().hs_free_scratch(clone) == hs.HS_SUCCESS
+    twin.ptr = None
+    scratch.free()
