@@ -1604,51 +1604,80 @@ __device__ HSB_NOINLINE void drainPair(const ScanParams &p, u32 bitmapAddr, u32 
     stats[1] += npass;
 }
 
+/* Word-entry drains (heavy pair kernel, 4-gram kernel): every lane holds up to four
+ * survivors {position, buckets[q] != 0}.  ONE atomicAdd per warp reserves their slots in
+ * the candidate list (ballot prefix per round), instead of one same-address atomic -- and
+ * one dependent L2 round trip -- per candidate. */
+__device__ __forceinline__ void appendWordCandidates(const ScanParams &p, u64 g0, const u32 (&bk)[4], u32 lane) {
+    const u32 full = 0xffffffffu;
+    const u32 b0 = __ballot_sync(full, bk[0] != 0), b1 = __ballot_sync(full, bk[1] != 0);
+    const u32 b2 = __ballot_sync(full, bk[2] != 0), b3 = __ballot_sync(full, bk[3] != 0);
+    const u32 o1 = __popc(b0), o2 = o1 + __popc(b1), o3 = o2 + __popc(b2), total = o3 + __popc(b3);
+    if (total == 0) {
+        return;
+    }
+    u32 base = 0;
+    if (lane == 0) {
+        base = atomicAdd(p.counters + CTR_CANDQ, total);
+    }
+    base = __shfl_sync(full, base, 0);
+    const u32 below = (1u << lane) - 1;
+    const u32 idx[4] = {base + __popc(b0 & below), base + o1 + __popc(b1 & below), base + o2 + __popc(b2 & below),
+                        base + o3 + __popc(b3 & below)};
+    DevCand *const list = reinterpret_cast<DevCand *>(p.out + p.outCap);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (bk[q] && idx[q] < p.outCap) {
+            DevCand cnd;
+            cnd.g = g0 + q;
+            cnd.buckets = bk[q];
+            cnd.pad = 0;
+            *reinterpret_cast<uint4 *>(list + idx[q]) = *reinterpret_cast<const uint4 *>(&cnd);
+        }
+    }
+}
+
 /* Heavy variant (large / saturating sets: tens of candidates per 512-byte step).  A queue
  * entry is ONE WORD of one lane with at least one candidate byte: {offset of the word in
  * the warp's run, its candidate bits, the word before it, the word} -- the bytes travel
- * with the entry, so the drain needs no corpus read, and an entry holds 1..4 candidates
- * (1.1 on average), so the 32 lanes of a drain stay in step. */
+ * with the entry, so the drain needs no corpus read.  The four bytes of the word are
+ * tested in four static rounds (an entry holds 1.1 candidates on average): the shared-
+ * memory probes, then ALL second-level probes in flight together, then one reservation. */
 __device__ HSB_NOINLINE void drainPairWords(const ScanParams &p, u32 bitmapAddr, u32 qAddr, u32 first,
                                             u32 count, u32 lane, u32 *stats) {
-    if (lane >= count) {
-        return;
-    }
     const uint2 rs = lds64(qAddr + PairQueue::RUN_START);
     const u64 runStart = ((u64)rs.y << 32) | rs.x;
-    const uint4 e = lds128(qAddr + (first + lane) * 16); /* x = offset, y = candidate bits, z = previous word, w = word */
+    uint4 e = make_uint4(0, 0, 0, 0); /* x = offset, y = candidate bits, z = previous word, w = word */
+    if (lane < count) {
+        e = lds128(qAddr + (first + lane) * 16);
+    }
     const u32 keyShift = 8 * (4 - p.keyBytes);
-    u32 m = e.y, ncand = 0, npass = 0;
-    while (m) {
-        const u32 q = (u32)(__ffs(m) - 1) >> 3;
-        const u32 buckets = (m >> (8 * q)) & 0xffu;
-        m &= ~(0xffu << (8 * q));
-        ncand++;
-        if (p.bitmapBytes) {
-            const u32 key = __funnelshift_rc(e.z, e.w, 8 * (q + 1)) >> keyShift;
-            if (!pairBitmapTest(p, bitmapAddr, key)) {
-                continue;
-            }
-            if (p.bitmap2Shift) {
-                const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
-                if (!((__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1)) {
-                    continue;
-                }
-            }
+    u32 bk[4], key[4];
+    u32 ncand = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        bk[q] = (e.y >> (8 * q)) & 0xffu;
+        ncand += bk[q] != 0;
+        key[q] = __funnelshift_rc(e.z, e.w, 8 * (q + 1)) >> keyShift;
+        if (bk[q] && p.bitmapBytes && !pairBitmapTest(p, bitmapAddr, key[q])) {
+            bk[q] = 0;
         }
-        npass++;
-        const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
-        if (i < p.outCap) {
-            DevCand cnd;
-            cnd.g = runStart + e.x + q;
-            cnd.buckets = buckets;
-            cnd.pad = 0;
-            *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
-                *reinterpret_cast<const uint4 *>(&cnd);
+    }
+    if (p.bitmapBytes && p.bitmap2Shift) {
+        u32 w2[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const u32 h2 = (key[q] * 0x85EBCA6Bu) >> p.bitmap2Shift;
+            w2[q] = bk[q] ? (__ldg(p.bitmap2 + (h2 >> 5)) >> (h2 & 31)) & 1u : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            bk[q] = w2[q] ? bk[q] : 0u;
         }
     }
     stats[0] += ncand;
-    stats[1] += npass;
+    stats[1] += (bk[0] != 0) + (bk[1] != 0) + (bk[2] != 0) + (bk[3] != 0);
+    appendWordCandidates(p, runStart + e.x, bk, lane);
 }
 
 template <int SB, int MAXT, int HEAVY>
@@ -1725,6 +1754,7 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
     };
     const size_t pfBytes = (size_t)p.nstages * 512 + lane * 48; /* even lanes: 16 x 128 B, 2 KiB */
     uint4 nxt = load(ptr, true);
+    u32 prevW = 0; /* heavy: the last word of the previous step (own lane's; lane 31's is the one used) */
     if (runStart != 0) {
         /* state entering the run: the 16 bytes before it, as "lane -1" */
         const uint4 hv = __ldg(reinterpret_cast<const uint4 *>(p.corpus + runStart - 16));
@@ -1732,6 +1762,7 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
         u32 ha[6];
         pairFilter<SB>(hw, clsAddr, laneOff, ha);
         carry = ha[4];
+        prevW = hv.w;
     }
     u32 step = 0;
     u32 prevRecv = carry;
@@ -1754,12 +1785,9 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
                 /* four static rounds, one per word of the lane: the lanes whose word k has
                  * a candidate byte append it (slot from a ballot prefix); 32 pending
                  * entries are drained at once */
-                u32 pw = __shfl_up_sync(0xffffffffu, cur.w, 1);
-                if (lane == 0) { /* the word before this step's 512 bytes */
-                    pw = (runStart | chunk)
-                             ? __ldg(reinterpret_cast<const u32 *>(p.corpus + runStart) + (size_t)chunk * 4 - 1)
-                             : 0u;
-                }
+                /* the word before the lane's: the left neighbour's last, lane 0: lane 31's
+                 * of the previous step (kept in a register, no corpus read) */
+                const u32 pw = __shfl_sync(0xffffffffu, lane == 31 ? prevW : cur.w, (lane + 31) & 31);
                 const u32 wv[5] = {pw, cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
@@ -1780,6 +1808,7 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelPair(const HSB_GRID_CONSTAN
                     }
                 }
             }
+            prevW = cur.w;
             return;
         }
         const u32 bal = __ballot_sync(0xffffffffu, all != 0xffffffffu);
@@ -1879,45 +1908,34 @@ struct GramQueue {
 };
 enum { GRAM_CLASS_BYTES = 256 * 256, GRAM_BITMAP_BYTES = 4 * (31 * (1 + 33 + 1025) + 1 + 63) / 64 * 64 };
 
-/* 32 queue entries, one word with candidates per lane (1.02 candidates on average, so the
- * lanes stay in step and a drain costs about ONE L2 round trip): the exact raw 4-byte key
- * against the second-level table in L2 -- one BYTE per slot, the buckets whose literals
- * own a key hashing there -- and the survivors, with those buckets, to the candidate list. */
+/* 32 queue entries, one word with candidates per lane (1.02 candidates on average): the
+ * exact raw 4-byte keys against the second-level table in L2 -- one BYTE per slot, the
+ * buckets whose literals own a key hashing there -- all probes of the warp in flight
+ * together (a drain costs ONE L2 round trip), and the survivors, with those buckets, to
+ * the candidate list through one reservation. */
 __device__ HSB_NOINLINE void drainGram(const ScanParams &p, u32 qAddr, u32 first, u32 count, u32 lane,
                                        u32 *stats) {
-    if (lane >= count) {
-        return;
-    }
     const uint2 rs = lds64(qAddr + GramQueue::RUN_START);
-    const uint4 e = lds128(qAddr + (first + lane) * 16);
-    const u64 g0 = (((u64)rs.y << 32) | rs.x) + e.x;
-    u32 cm = e.y, ncand = 0, npass = 0;
-    while (cm) {
-        const u32 q = (u32)__ffs(cm) - 1;
-        cm &= cm - 1;
-        ncand++;
-        u32 buckets = 0xffu;
-        if (p.bitmap2Shift) {
-            const u32 key = __funnelshift_rc(e.z, e.w, 8 * (q + 1));
-            const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
-            buckets = __ldg(reinterpret_cast<const u8 *>(p.bitmap2) + h2);
-            if (!buckets) {
-                continue;
+    uint4 e = make_uint4(0, 0, 0, 0);
+    if (lane < count) {
+        e = lds128(qAddr + (first + lane) * 16);
+    }
+    u32 bk[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        bk[q] = 0;
+        if ((e.y >> q) & 1) {
+            bk[q] = 0xffu;
+            if (p.bitmap2Shift) {
+                const u32 key = __funnelshift_rc(e.z, e.w, 8 * (q + 1));
+                const u32 h2 = (key * 0x85EBCA6Bu) >> p.bitmap2Shift;
+                bk[q] = __ldg(reinterpret_cast<const u8 *>(p.bitmap2) + h2);
             }
         }
-        npass++;
-        const u32 i = atomicAdd(p.counters + CTR_CANDQ, 1u);
-        if (i < p.outCap) {
-            DevCand cnd;
-            cnd.g = g0 + q;
-            cnd.buckets = buckets;
-            cnd.pad = 0;
-            *reinterpret_cast<uint4 *>(reinterpret_cast<DevCand *>(p.out + p.outCap) + i) =
-                *reinterpret_cast<const uint4 *>(&cnd);
-        }
     }
-    stats[0] += ncand;
-    stats[1] += npass;
+    stats[0] += __popc(e.y & 0xfu);
+    stats[1] += (bk[0] != 0) + (bk[1] != 0) + (bk[2] != 0) + (bk[3] != 0);
+    appendWordCandidates(p, (((u64)rs.y << 32) | rs.x) + e.x, bk, lane);
 }
 
 template <int MAXT>
@@ -1981,9 +1999,11 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelGram(const HSB_GRID_CONSTAN
      * at the very start of the corpus the class of byte 0x00 stands in (a literal cannot
      * begin before position 0: the block lookup in confirm rejects such candidates). */
     u32 carryPack;
+    u32 prevW = 0; /* the last word of the previous step (own lane's; lane 31's is the one used) */
     if (runStart != 0) {
         const u32 hw = __ldg(reinterpret_cast<const u32 *>(p.corpus + runStart - 4));
         carryPack = cls(hw, 1) | (cls(hw, 2) << 8) | (cls(hw, 3) << 16);
+        prevW = hw;
     } else {
         const u32 z = cls(0, 0);
         carryPack = z | (z << 8) | (z << 16);
@@ -2017,11 +2037,9 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelGram(const HSB_GRID_CONSTAN
         if (__any_sync(0xffffffffu, cm != 0)) {
             /* four static rounds, one per word of the lane: the lanes whose word k holds a
              * candidate append it with its bytes; 32 pending entries are drained at once */
-            u32 pw = __shfl_up_sync(0xffffffffu, cur.w, 1);
-            if (lane == 0) { /* the word before this step's 512 bytes */
-                pw = (runStart | chunk) ? __ldg(reinterpret_cast<const u32 *>(p.corpus + runStart) + (size_t)chunk * 4 - 1)
-                                        : 0u;
-            }
+            /* the word before the lane's: the left neighbour's last, lane 0: lane 31's of
+             * the previous step (kept in a register, no corpus read) */
+            const u32 pw = __shfl_sync(0xffffffffu, lane == 31 ? prevW : cur.w, (lane + 31) & 31);
             const u32 wv[5] = {pw, cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
             for (int k = 0; k < 4; k++) {
@@ -2042,6 +2060,7 @@ __global__ void __launch_bounds__(MAXT, 1) scanKernelGram(const HSB_GRID_CONSTAN
                 }
             }
         }
+        prevW = cur.w;
     };
     const u64 readableSteps = (p.readableEnd - runStart) >> 9;
     const u32 nFast = readableSteps >= (u64)nsteps + 2 ? nsteps : (readableSteps > 2 ? (u32)readableSteps - 2 : 0);
