@@ -267,6 +267,29 @@ __device__ bool checkMask8(const BlockRef &blk, u64 to, u64 andM, u64 cmpM, u64 
     return true;
 }
 
+/* CHECK_MASK_32 / CHECK_MASK_64: N bytes at to+offset, one negation BIT per byte; bytes
+ * in the future are ignored, a window starting before the block fails
+ * (src/rose/program_runtime.c:729-801 and :805-877, src/rose/validate_mask.h:106-153).
+ * The masks are read from the instruction in the bytecode. */
+__device__ bool checkMaskWide(const BlockRef &blk, u64 to, const u8 *andM, const u8 *cmpM, u64 negM, s32 off,
+                              int nbytes) {
+    const long long start = (long long)to + off;
+    if (start < 0) {
+        return false; /* "too early, fail": block mode has no history */
+    }
+    for (int i = 0; i < nbytes; i++) {
+        const long long q = start + i;
+        if (q >= (long long)blk.len) {
+            break;
+        }
+        const bool ne = (blk.base[q] & __ldg(andM + i)) != __ldg(cmpM + i);
+        if (ne != (bool)((negM >> i) & 1)) {
+            return false;
+        }
+    }
+    return true;
+}
+
 /* CHECK_BYTE (src/rose/program_runtime.c:600-641). */
 __device__ bool checkByte(const BlockRef &blk, u64 to, u8 andM, u8 cmpM, u8 neg, s32 off) {
     const long long q = (long long)to + off;
@@ -319,6 +342,28 @@ __device__ void runProgram(const ScanParams &p, const BlockRef &blk, u32 prog, u
                 pc += in.fail_jump;
             } else {
                 NEXT(InstrCheckMask);
+            }
+            break;
+        }
+        case OP_CHECK_MASK_32: {
+            const u32 neg = __ldg((const u32 *)(pc + offsetof(InstrCheckMask32, neg_mask)));
+            const s32 off = (s32)__ldg((const u32 *)(pc + offsetof(InstrCheckMask32, offset)));
+            if (!checkMaskWide(blk, to, pc + offsetof(InstrCheckMask32, and_mask),
+                               pc + offsetof(InstrCheckMask32, cmp_mask), neg, off, 32)) {
+                pc += __ldg((const u32 *)(pc + offsetof(InstrCheckMask32, fail_jump)));
+            } else {
+                NEXT(InstrCheckMask32);
+            }
+            break;
+        }
+        case OP_CHECK_MASK_64: {
+            const u64 neg = __ldg((const u64 *)(pc + offsetof(InstrCheckMask64, neg_mask)));
+            const s32 off = (s32)__ldg((const u32 *)(pc + offsetof(InstrCheckMask64, offset)));
+            if (!checkMaskWide(blk, to, pc + offsetof(InstrCheckMask64, and_mask),
+                               pc + offsetof(InstrCheckMask64, cmp_mask), neg, off, 64)) {
+                pc += __ldg((const u32 *)(pc + offsetof(InstrCheckMask64, fail_jump)));
+            } else {
+                NEXT(InstrCheckMask64);
             }
             break;
         }

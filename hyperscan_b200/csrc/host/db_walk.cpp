@@ -47,6 +47,8 @@ bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
             break;
         case OP_CHECK_GROUPS: STEP(InstrCheckGroups); break;
         case OP_CHECK_MASK: STEP_JUMP(InstrCheckMask); break;
+        case OP_CHECK_MASK_32: STEP_JUMP(InstrCheckMask32); break;
+        case OP_CHECK_MASK_64: STEP_JUMP(InstrCheckMask64); break;
         case OP_CHECK_BYTE: STEP_JUMP(InstrCheckByte); break;
         case OP_CHECK_MED_LIT:
         case OP_CHECK_MED_LIT_NOCASE:

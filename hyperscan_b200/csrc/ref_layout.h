@@ -328,6 +328,7 @@ enum RoseOp {
     OP_CLEAR_WORK_DONE = 55,
     OP_INCLUDED_JUMP = 61,
     OP_SET_EXHAUST = 65,
+    OP_CHECK_MASK_64 = 69,
     OP_LAST = 69
 };
 
@@ -338,6 +339,8 @@ static const u32 INVALID_DKEY = 0xffffffffu; /* MO_INVALID_IDX */
 struct InstrEnd { u8 code; };
 struct InstrCheckGroups { u8 code; u64 groups; };
 struct InstrCheckMask { u8 code; u64 and_mask, cmp_mask, neg_mask; s32 offset; u32 fail_jump; };
+struct InstrCheckMask32 { u8 code; u8 and_mask[32]; u8 cmp_mask[32]; u32 neg_mask; s32 offset; u32 fail_jump; };
+struct InstrCheckMask64 { u8 code; u8 and_mask[64]; u8 cmp_mask[64]; u64 neg_mask; s32 offset; u32 fail_jump; };
 struct InstrCheckByte { u8 code, and_mask, cmp_mask, negation; s32 offset; u32 fail_jump; };
 struct InstrDedupe { u8 code, quash_som; u32 dkey; s32 offset_adjust; u32 fail_jump; };
 struct InstrReport { u8 code; u32 onmatch; s32 offset_adjust; };

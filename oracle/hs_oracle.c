@@ -99,7 +99,7 @@ struct scan {
 /* ---- rose literal programs --------------------------------------------------------- */
 
 enum {
-    OP_END = 0, OP_CHECK_GROUPS = 3, OP_CHECK_MASK = 9, OP_CHECK_BYTE = 11, OP_DEDUPE = 28,
+    OP_END = 0, OP_CHECK_GROUPS = 3, OP_CHECK_MASK = 9, OP_CHECK_MASK_32 = 10, OP_CHECK_BYTE = 11, OP_CHECK_MASK_64 = 69, OP_DEDUPE = 28,
     OP_REPORT = 33, OP_REPORT_EXHAUST = 34, OP_DEDUPE_AND_REPORT = 37, OP_FINAL_REPORT = 38,
     OP_CHECK_EXHAUSTED = 39, OP_SQUASH_GROUPS = 43, OP_CHECK_LONG_LIT = 51, OP_CHECK_LONG_LIT_NOCASE = 52,
     OP_CHECK_MED_LIT = 53, OP_CHECK_MED_LIT_NOCASE = 54, OP_CLEAR_WORK_DONE = 55, OP_INCLUDED_JUMP = 61,
@@ -207,6 +207,29 @@ static int check_mask(const struct scan *s, u64 end, u64 and_mask, u64 cmp_mask,
     return 1;
 }
 
+/* roseCheckMask32 / roseCheckMask64 + validateMask32 / 64 (src/rose/program_runtime.c:729-801,
+ * :805-877; src/rose/validate_mask.h:106-153), block mode: n bytes at end + off, one
+ * negation bit per byte, bytes past the buffer are masked out of the comparison. */
+static int check_mask_wide(const struct scan *s, u64 end, const u8 *and_mask, const u8 *cmp_mask, u64 neg_mask,
+                           s32 off, int n) {
+    if (off < 0 && (u64)(0 - (long long)off) > end) {
+        return 0; /* too early */
+    }
+    const long long start = (long long)end + off;
+    u64 cmp_result = 0, valid = 0;
+    for (int i = 0; i < n; i++) {
+        const long long q = start + i;
+        if (q < 0 || q >= (long long)s->len) {
+            continue;
+        }
+        valid |= 1ull << i;
+        if ((s->buf[q] & and_mask[i]) != cmp_mask[i]) {
+            cmp_result |= 1ull << i;
+        }
+    }
+    return (cmp_result & valid) == (neg_mask & valid);
+}
+
 /* roseRunProgram_l: the pure-literal interpreter.  `end` is the offset after
  * the literal's last byte.  Returns 0 to halt matching. */
 static int run_program_l(struct scan *s, u32 prog, u64 end) {
@@ -226,6 +249,20 @@ static int run_program_l(struct scan *s, u32 prog, u64 end) {
                 pc += rd32(pc + 36);
             } else {
                 pc += 40;
+            }
+            break;
+        case OP_CHECK_MASK_32: /* {u8; u8 and[32], cmp[32]; u32 neg; s32 offset; u32 fail_jump} */
+            if (!check_mask_wide(s, end, pc + 1, pc + 33, rd32(pc + 68), rds32(pc + 72), 32)) {
+                pc += rd32(pc + 76);
+            } else {
+                pc += 80;
+            }
+            break;
+        case OP_CHECK_MASK_64: /* {u8; u8 and[64], cmp[64]; u64 neg; s32 offset; u32 fail_jump} */
+            if (!check_mask_wide(s, end, pc + 1, pc + 65, rd64(pc + 136), rds32(pc + 144), 64)) {
+                pc += rd32(pc + 148);
+            } else {
+                pc += 152;
             }
             break;
         case OP_CHECK_BYTE: /* {u8 code,and,cmp,neg; s32 offset; u32 fail_jump} */

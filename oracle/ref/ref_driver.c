@@ -575,6 +575,10 @@ ref_layout_dump_sheng();
     ISZ(CHECK_MASK); IOFF(CHECK_MASK, and_mask); IOFF(CHECK_MASK, cmp_mask);
     IOFF(CHECK_MASK, neg_mask); IOFF(CHECK_MASK, offset);
     IOFF(CHECK_MASK, fail_jump);
+    ISZ(CHECK_MASK_32); IOFF(CHECK_MASK_32, and_mask); IOFF(CHECK_MASK_32, cmp_mask);
+    IOFF(CHECK_MASK_32, neg_mask); IOFF(CHECK_MASK_32, offset); IOFF(CHECK_MASK_32, fail_jump);
+    ISZ(CHECK_MASK_64); IOFF(CHECK_MASK_64, and_mask); IOFF(CHECK_MASK_64, cmp_mask);
+    IOFF(CHECK_MASK_64, neg_mask); IOFF(CHECK_MASK_64, offset); IOFF(CHECK_MASK_64, fail_jump);
     ISZ(CHECK_BYTE); IOFF(CHECK_BYTE, and_mask); IOFF(CHECK_BYTE, cmp_mask);
     IOFF(CHECK_BYTE, negation); IOFF(CHECK_BYTE, offset);
     IOFF(CHECK_BYTE, fail_jump);
@@ -601,6 +605,8 @@ ref_layout_dump_sheng();
     printf("  \"ROSE_INSTR_CHECK_GROUPS\": %d,\n", ROSE_INSTR_CHECK_GROUPS);
     printf("  \"ROSE_INSTR_CHECK_MASK\": %d,\n", ROSE_INSTR_CHECK_MASK);
     printf("  \"ROSE_INSTR_CHECK_BYTE\": %d,\n", ROSE_INSTR_CHECK_BYTE);
+    printf("  \"ROSE_INSTR_CHECK_MASK_32\": %d,\n", ROSE_INSTR_CHECK_MASK_32);
+    printf("  \"ROSE_INSTR_CHECK_MASK_64\": %d,\n", ROSE_INSTR_CHECK_MASK_64);
     printf("  \"ROSE_INSTR_DEDUPE\": %d,\n", ROSE_INSTR_DEDUPE);
     printf("  \"ROSE_INSTR_REPORT\": %d,\n", ROSE_INSTR_REPORT);
     printf("  \"ROSE_INSTR_REPORT_EXHAUST\": %d,\n", ROSE_INSTR_REPORT_EXHAUST);

@@ -17,7 +17,8 @@ import pytest
 import oracle.port as port
 
 END, CHECK_GROUPS, CHECK_MASK, CHECK_BYTE = 0, 3, 9, 11
-PUSH_DELAYED, DEDUPE, REPORT_CHAIN, REPORT, REPORT_EXHAUST = 14, 28, 30, 33, 34
+PUSH_DELAYED, DEDUPE, REPORT_CHAIN, REPORT, REPORT_EXHAUST = 18, 28, 30, 33, 34
+CHECK_MASK_32, CHECK_MASK_64 = 10, 69
 DEDUPE_AND_REPORT, FINAL_REPORT, CHECK_EXHAUSTED, SQUASH_GROUPS = 37, 38, 39, 43
 CHECK_LONG_LIT, CHECK_LONG_LIT_NOCASE, CHECK_MED_LIT, CHECK_MED_LIT_NOCASE = 51, 52, 53, 54
 INCLUDED_JUMP, SET_EXHAUST = 61, 65
@@ -41,6 +42,16 @@ def i_squash_groups(groups):
 
 def i_check_mask(and_m, cmp_m, neg_m, offset, fail_jump):
     return _pad(struct.pack("<B7xQQQiI", CHECK_MASK, and_m, cmp_m, neg_m, offset, fail_jump))
+
+
+def i_check_mask_32(and_m, cmp_m, neg_m, offset, fail_jump):
+    """ROSE_STRUCT_CHECK_MASK_32 (src/rose/rose_program.h:283-290): one negation BIT per byte"""
+    return _pad(struct.pack("<B32s32s3xIiI", CHECK_MASK_32, bytes(and_m), bytes(cmp_m), neg_m, offset, fail_jump))
+
+
+def i_check_mask_64(and_m, cmp_m, neg_m, offset, fail_jump):
+    """ROSE_STRUCT_CHECK_MASK_64 (src/rose/rose_program.h:292-299)"""
+    return _pad(struct.pack("<B64s64s7xQiI", CHECK_MASK_64, bytes(and_m), bytes(cmp_m), neg_m, offset, fail_jump))
 
 
 def i_check_byte(and_m, cmp_m, neg, offset, fail_jump):
@@ -141,6 +152,137 @@ def test_validate_mask_kats_device(hs, ref, ti):
     raw = struct.pack("<Q", t[0])
     for k in range(0, 9):
         assert _scan_dev(hs, db, b"Z" + raw[:k], scratch) == _mask_expect(t, k), (ti, k)
+    scratch.free()
+
+
+# ---- ValidateMask32 / 64 known answers (unit/internal/rose_mask_32.cpp:57-131) ------------
+
+# (index, data, and_mask, cmp_mask, negated) per line, as in testBasicIdx
+TEST_BASIC_32 = [
+    [(1, 0x34, 0xf8, 0x30, 0), (2, 0x34, 0xf8, 0x30, 0), (8, 0x23, 0xff, 0x23, 0), (9, 0x34, 0xf8, 0x30, 0),
+     (10, 0x41, 0xdf, 0x41, 0), (11, 0x63, 0xdd, 0x41, 0), (12, 0x61, 0xdd, 0x41, 0), (13, 0x41, 0xdf, 0x41, 0),
+     (14, 0x61, 0xdf, 0x41, 0), (15, 0x41, 0xdf, 0x41, 0), (16, 0x43, 0xdd, 0x41, 0), (17, 0x61, 0xdd, 0x41, 0),
+     (23, 0x63, 0xdd, 0x41, 0), (24, 0x4f, 0xfc, 0x4c, 0), (25, 0x4d, 0xfc, 0x4c, 0), (26, 0x4d, 0xfc, 0x4c, 0)],
+    [(11, 0, 0xff, 0x55, 1), (12, 0, 0xff, 0x36, 1), (13, 0, 0xfe, 0x34, 1), (14, 0x4d, 0xfe, 0x4c, 0),
+     (15, 0x41, 0xbf, 0x01, 0), (16, 0x53, 0xdf, 0x73, 1), (17, 0x4b, 0, 0, 0), (18, 0, 0x2c, 0x2c, 1)],
+    [(15, 0x46, 0xdf, 0x46, 0), (16, 0x4f, 0xdf, 0x46, 1), (17, 0x6f, 0xff, 0x6f, 0), (18, 0x31, 0xfe, 0x30, 0),
+     (19, 0x34, 0xf8, 0x30, 0), (20, 0x66, 0xc0, 0x40, 0), (21, 0x6f, 0xf0, 0x60, 0), (22, 0x6f, 0, 0, 0),
+     (23, 0x46, 0xdf, 0x44, 1), (24, 0x4f, 0xdf, 0x46, 1), (25, 0x6f, 0xff, 0x4f, 1), (26, 0x31, 0xfe, 0x30, 0),
+     (27, 0x34, 0xf8, 0x34, 1), (28, 0x66, 0xc0, 0x60, 1), (29, 0x6f, 0xf0, 0x6f, 1), (30, 0x6f, 0, 0x60, 1)],
+    [(31, 0x4a, 0x80, 0, 0)],
+    [(12, 0x2b, 0x3d, 0x2d, 1), (13, 0x2b, 0x3d, 0x4c, 1), (23, 0x4a, 0x88, 0x0a, 1)],
+]
+
+
+def _wide_case(ti, width):
+    """data / and / cmp arrays of `width` bytes and the truth mask (bit i = byte i differs);
+    width 64: the 32-byte vectors twice, the second copy with the bytes reversed"""
+    data, and_m, cmp_m = bytearray(width), bytearray(width), bytearray(width)
+    for idx, d, a, c, _ in TEST_BASIC_32[ti]:
+        for pos in ([idx] if width == 32 else [idx, 63 - idx]):
+            data[pos], and_m[pos], cmp_m[pos] = d, a, c
+    truth = sum(1 << i for i in range(width) if (data[i] & and_m[i]) != cmp_m[i])
+    return data, and_m, cmp_m, truth
+
+
+def _wide_negs(truth, width, seed):
+    rng = np.random.default_rng(seed)
+    full = (1 << width) - 1
+    negs = [0, full, truth, truth ^ 1, truth ^ (1 << (width - 1))]
+    negs += [truth ^ (1 << int(rng.integers(0, width))) for _ in range(8)]
+    negs += [int(rng.integers(0, 1 << 32)) | (int(rng.integers(0, 1 << 32)) << 32 if width == 64 else 0)
+             for _ in range(16)]
+    return [n & full for n in negs]
+
+
+def _wide_db(hs, ti, width, offset=0):
+    data, and_m, cmp_m, truth = _wide_case(ti, width)
+    negs = _wide_negs(truth, width, 451 + ti)
+    ins = i_check_mask_32 if width == 32 else i_check_mask_64
+    sz = len(ins(and_m, cmp_m, 0, 0, 0))
+    prog = b"".join(ins(and_m, cmp_m, nm, offset, sz + SZ_REPORT) + i_report(j) for j, nm in enumerate(negs))
+    return hs.compile_programs([b"Z"], [0], [0], prog + i_end()), data, truth, negs
+
+
+def _wide_expect(truth, negs, k, to=1):
+    """rose_mask_32.cpp:148-170: passes iff (cmp_result & valid) == (neg_mask & valid); in block
+    mode the valid bytes are the first k of the window (the rest lie in the future)"""
+    vdm = (1 << k) - 1
+    return sorted((j, to) for j, nm in enumerate(negs) if (truth & vdm) == (nm & vdm))
+
+
+def _isa_has_mask64(ref):
+    return ref.best_isa().startswith("avx512")      # L_PROGRAM_CASE(CHECK_MASK_64) is HAVE_AVX512 only
+
+
+@pytest.mark.parametrize("width", [32, 64])
+@pytest.mark.parametrize("ti", range(len(TEST_BASIC_32)))
+def test_validate_mask_wide_kats_reference_and_port(hs, ref, ti, width):
+    db, data, truth, negs = _wide_db(hs, ti, width)
+    assert truth == sum(neg << idx for idx, _, _, _, neg in TEST_BASIC_32[ti]) or width == 64   # testMask32_1
+    for k in list(range(0, width + 1)) + [width + 5]:
+        buf = b"Z" + bytes(data[:k]) + b"\x01" * max(0, k - width)
+        want = _wide_expect(truth, negs, min(k, width))
+        assert _scan_port(db, buf) == want, (ti, k)
+        if width == 32 or _isa_has_mask64(ref):
+            assert _scan_ref(ref, db, buf) == want, (ti, k)
+    # a window that starts before the buffer fails whatever the masks say ("too early")
+    db2, data, truth, negs = _wide_db(hs, ti, width, offset=-3)
+    for buf in (b"Z" + bytes(data[2:]), b"xZ" + bytes(data[1:]), b"xyZ" + bytes(data), b"xyzZ" + bytes(data[1:])):
+        want = _scan_port(db2, buf)
+        z = buf.index(b"Z") + 1
+        assert want == ([] if z < 3 else _wide_expect(sum(
+            1 << i for i in range(min(width, len(buf) - z + 3)) if
+            (buf[z - 3 + i] & _wide_case(ti, width)[1][i]) != _wide_case(ti, width)[2][i]), negs,
+            min(width, len(buf) - z + 3), to=z))
+        if width == 32 or _isa_has_mask64(ref):
+            assert _scan_ref(ref, db2, buf) == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("width", [32, 64])
+@pytest.mark.parametrize("ti", range(len(TEST_BASIC_32)))
+def test_validate_mask_wide_kats_device(hs, ref, ti, width):
+    db, data, truth, negs = _wide_db(hs, ti, width)
+    scratch = hs.Scratch(db)
+    for k in list(range(0, width + 1)) + [width + 5]:
+        buf = b"Z" + bytes(data[:k]) + b"\x01" * max(0, k - width)
+        assert _scan_dev(hs, db, buf, scratch) == _wide_expect(truth, negs, min(k, width)), (ti, k)
+    scratch.free()
+    db2, data, truth, negs = _wide_db(hs, ti, width, offset=-3)
+    scratch = hs.Scratch(db2)
+    for buf in (b"Z" + bytes(data[2:]), b"xZ" + bytes(data[1:]), b"xyZ" + bytes(data), b"xyzZ" + bytes(data[1:])):
+        assert _scan_dev(hs, db2, buf, scratch) == _scan_port(db2, buf)
+    scratch.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_wide_mask_programs_device(hs, ref, seed):
+    """seeded CHECK_MASK_32 / _64 at assorted offsets on a corpus with many hits: the device,
+    the restatement and (where its build has the opcode) the reference agree"""
+    rng = np.random.default_rng(seed)
+    prog = b""
+    for j in range(20):
+        width = 32 if j % 2 == 0 else 64
+        live = set(int(x) for x in rng.choice(width, size=3, replace=False))   # three constrained bytes
+        and_m = bytes(int(rng.choice([0x01, 0x20, 0x03])) if i in live else 0 for i in range(width))
+        cmp_m = bytes(int(rng.choice([0x61, 0x62, 0x41, 0x42])) & a for a in and_m)
+        neg = sum(1 << i for i in live if rng.integers(0, 2))
+        ins = i_check_mask_32 if width == 32 else i_check_mask_64
+        sz = len(ins(and_m, cmp_m, 0, 0, 0))
+        prog += ins(and_m, cmp_m, neg, int(rng.integers(-40, 8)), sz + SZ_REPORT) + i_report(100 + j)
+    db = hs.compile_programs([b"ab"], [0], [0], prog + i_end())
+    alpha = np.frombuffer(b"abAB", dtype=np.uint8)
+    data = alpha[rng.integers(0, alpha.size, size=3000)].tobytes()
+    scratch = hs.Scratch(db)
+    want = _scan_port(db, data)
+    assert len(want) > 50
+    assert _scan_dev(hs, db, data, scratch) == want
+    if _isa_has_mask64(ref):
+        assert _scan_ref(ref, db, data) == want
+    for cut in (1, 2, 3, 9, 33, 65, 100):
+        assert _scan_dev(hs, db, data[:cut], scratch) == _scan_port(db, data[:cut]), cut
     scratch.free()
 
 
