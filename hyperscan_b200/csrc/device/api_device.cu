@@ -77,6 +77,8 @@ struct RuntimeOpts {
     int heavy = 1;           /* FK_PAIR32 candidate path: 0 = per-lane entries, 2 = per-word entries (sets that
                               * pass many candidates), 1 = by the modelled first-stage rate */
     int bigSetClasses = 4;   /* ... classes left to the second byte (pair table = 4 KiB each) */
+    int fatPair = 1;         /* fat Teddy (16 buckets): 1 = class-pair first stage with the buckets folded onto
+                              * 8 bits (3.0 TB/s), 0 = 64-bit per-byte entries (FK_BYTE64, 1.75 TB/s) */
     int chunkMB = 128;       /* host->device pipeline granularity */
     int initialRing = 1 << 20;
 };
@@ -99,7 +101,7 @@ void initOpts() {
         {"HSB200_FIRST_STAGE", &g_opts.firstStage}, {"HSB200_WIDE", &g_opts.wide},
         {"HSB200_SPLIT", &g_opts.split},       {"HSB200_BIG_SET", &g_opts.bigSet},
         {"HSB200_BIG_SET_CLASSES", &g_opts.bigSetClasses}, {"HSB200_HEAVY", &g_opts.heavy},
-        {"HSB200_GRAM", &g_opts.gram}};
+        {"HSB200_GRAM", &g_opts.gram},         {"HSB200_FAT_PAIR", &g_opts.fatPair}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -123,6 +125,7 @@ struct DevImage {
     u8 *d_bitmap = nullptr;
     u32 bitmapBytes = 0, bitmapShift = 0, keyBytes = 0;
     u32 pairBytes = 0, bitmapHoles = 0, bitmapBits = 0; /* FK_PAIR32 layout (kernels.h) */
+    u32 bucketFold = 0;
     double pairRate = 0;     /* FK_PAIR32: modelled first-stage candidates per byte (printable ASCII) */
     u8 *d_bitmap2 = nullptr; /* second level (HBM / L2) for large literal sets */
     u32 bitmap2Shift = 0;
@@ -547,6 +550,88 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     std::vector<u8> table, pairBitmap, pairBitmap2;
     std::vector<LitTail> tails;
     bool programsOk = true;
+    /* FK_PAIR32 / FK_GRAM4 tables from the literals' tails (FDR sets, and fat Teddy with its 16
+     * buckets folded onto 8 first-stage bits) */
+    auto pairStage = [&](bool allowGram) {
+        int dev = 0, maxSmem = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+                u32 minSize = 8;
+                for (const LitTail &t : tails) {
+                    minSize = std::min(minSize, t.size);
+                }
+                im->kind = FK_PAIR32;
+                im->stride = 1;
+                im->slotBase = minSize >= 2 ? 1 : 0;
+                /* shared memory: 64 KiB class rows + pair table + (large sets) bitmap +
+                 * queues.  Small sets: 32 x 32 classes (128 KiB pair table), the 32 KiB
+                 * bitmap in the class rows' upper halves.  Sets whose keys would fill that
+                 * bitmap beyond ~10 %: the pair filter is saturated anyway, so the second
+                 * byte gets few classes and the freed space a large contiguous bitmap. */
+                std::vector<u32> keys;
+                u32 kb = 0;
+                const bool keyed = g_opts.prefilter && tailKeys(tails, &kb, &keys);
+                const bool large = keyed && keys.size() * 10 > 262144; /* would fill the 32 KiB bitmap > 10 % */
+                std::vector<u8> gramBitmap;
+                /* measured crossover (DESIGN.md section 3.7): 5 000 literals (12.5 k keys) scan
+                 * 10 % faster through the 4-gram kernel, 1 000 literals 38 % slower */
+                const bool gramWorth = keys.size() >= 10000;
+                if (allowGram && (g_opts.gram == 2 || (g_opts.gram == 1 && gramWorth)) && keyed && kb == 4 &&
+                    buildGramTables(tails, &table, &gramBitmap)) {
+                    /* the pair evidence saturates for such sets: exact class 4-gram membership
+                     * instead (FK_GRAM4), exact raw 4-byte keys in L2 behind it */
+                    im->kind = FK_GRAM4;
+                    im->keyBytes = 4;
+                    pairBitmap.swap(gramBitmap);
+                    /* second level in L2: one BYTE per slot = the buckets of the literals whose
+                     * raw 4-byte key hashes there (~64 slots per key, <= 64 MB), so that a
+                     * survivor reaches confirm with its real buckets, not all eight */
+                    u32 lg2 = 16;
+                    while (lg2 < 26 && (1ull << lg2) < (u64)keys.size() * 64) {
+                        lg2++;
+                    }
+                    pairBitmap2.assign((size_t)1 << lg2, 0);
+                    for (const LitTail &t : tails) {
+                        const u32 v = (u32)(t.v >> 32), care = (u32)(t.msk >> 32), dc = ~care;
+                        u32 sub = 0;
+                        do {
+                            const u32 k = (v & care) | sub;
+                            pairBitmap2[(k * 0x85EBCA6Bu) >> (32 - lg2)] |= (u8)(1u << (t.bucket & 7));
+                            sub = (sub - dc) & dc;
+                        } while (sub);
+                    }
+                    im->bitmap2Shift = 32 - lg2;
+                    return;
+                }
+                {
+                const bool big = large && g_opts.bigSet != 0;
+                PairTables pt;
+                buildPairTables(tails, (u32)im->slotBase, &pt, 32, big ? (u32)std::max(1, g_opts.bigSetClasses) : 32);
+                im->pairBytes = pt.nClass1 * 4096;
+                im->pairRate = pt.modelRate;
+                if (getenv("HSB200_TRACE")) {
+                    fprintf(stderr, "[hs_b200] class-pair tables: %u x %u classes, modelled %.4f candidates/byte, "
+                                    "%zu prefilter keys%s\n", pt.nClass0, pt.nClass1, pt.modelRate, keys.size(),
+                            big ? " (large-set layout)" : "");
+                }
+                table.resize(sizeof(pt.classWord) + sizeof(pt.pair));
+                memcpy(table.data(), pt.classWord, sizeof(pt.classWord));
+                memcpy(table.data() + sizeof(pt.classWord), pt.pair, sizeof(pt.pair));
+                if (keyed) {
+                    im->keyBytes = kb;
+                    im->bitmapHoles = big ? 0 : 1;
+                    u32 bits = 262144;
+                    if (big) {
+                        /* everything the pair table and 27 queues leave of the 227 KiB */
+                        const u32 queues = (u32)scanSmemBytes(FK_PAIR32, 0, 0, 0, 0, 0, 27) - 65536u;
+                        const u32 room = (u32)maxSmem - 65536u - im->pairBytes - queues;
+                        bits = (room & ~127u) * 8;
+                    }
+                    im->bitmapBits = bits;
+                    buildPairBitmaps(keys, bits, &pairBitmap, &pairBitmap2, &im->bitmap2Shift);
+                }
+                }
+    };
     if (hw->type == HWLM_ENGINE_NOOD) {
         /* single literal: one bucket, slots = the last <= 4 bytes of msk/cmp
          * (first char in the low byte: src/hwlm/noodle_build.cpp:100-118) */
@@ -597,82 +682,7 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                 im->kind = FK_HASH64;
                 table.assign(src, src + (size_t)entries * 8);
             } else if (g_opts.firstStage == 3) {
-                u32 minSize = 8;
-                for (const LitTail &t : tails) {
-                    minSize = std::min(minSize, t.size);
-                }
-                im->kind = FK_PAIR32;
-                im->stride = 1;
-                im->slotBase = minSize >= 2 ? 1 : 0;
-                /* shared memory: 64 KiB class rows + pair table + (large sets) bitmap +
-                 * queues.  Small sets: 32 x 32 classes (128 KiB pair table), the 32 KiB
-                 * bitmap in the class rows' upper halves.  Sets whose keys would fill that
-                 * bitmap beyond ~10 %: the pair filter is saturated anyway, so the second
-                 * byte gets few classes and the freed space a large contiguous bitmap. */
-                std::vector<u32> keys;
-                u32 kb = 0;
-                const bool keyed = g_opts.prefilter && tailKeys(tails, &kb, &keys);
-                const bool large = keyed && keys.size() * 10 > 262144; /* would fill the 32 KiB bitmap > 10 % */
-                std::vector<u8> gramBitmap;
-                /* measured crossover (DESIGN.md section 3.7): 5 000 literals (12.5 k keys) scan
-                 * 10 % faster through the 4-gram kernel, 1 000 literals 38 % slower */
-                const bool gramWorth = keys.size() >= 10000;
-                if ((g_opts.gram == 2 || (g_opts.gram == 1 && gramWorth)) && keyed && kb == 4 &&
-                    buildGramTables(tails, &table, &gramBitmap)) {
-                    /* the pair evidence saturates for such sets: exact class 4-gram membership
-                     * instead (FK_GRAM4), exact raw 4-byte keys in L2 behind it */
-                    im->kind = FK_GRAM4;
-                    im->keyBytes = 4;
-                    pairBitmap.swap(gramBitmap);
-                    /* second level in L2: one BYTE per slot = the buckets of the literals whose
-                     * raw 4-byte key hashes there (~64 slots per key, <= 64 MB), so that a
-                     * survivor reaches confirm with its real buckets, not all eight */
-                    u32 lg2 = 16;
-                    while (lg2 < 26 && (1ull << lg2) < (u64)keys.size() * 64) {
-                        lg2++;
-                    }
-                    pairBitmap2.assign((size_t)1 << lg2, 0);
-                    for (const LitTail &t : tails) {
-                        const u32 v = (u32)(t.v >> 32), care = (u32)(t.msk >> 32), dc = ~care;
-                        u32 sub = 0;
-                        do {
-                            const u32 k = (v & care) | sub;
-                            pairBitmap2[(k * 0x85EBCA6Bu) >> (32 - lg2)] |= (u8)(1u << (t.bucket & 7));
-                            sub = (sub - dc) & dc;
-                        } while (sub);
-                    }
-                    im->bitmap2Shift = 32 - lg2;
-                    goto tables_done;
-                }
-                {
-                const bool big = large && g_opts.bigSet != 0;
-                PairTables pt;
-                buildPairTables(tails, (u32)im->slotBase, &pt, 32, big ? (u32)std::max(1, g_opts.bigSetClasses) : 32);
-                im->pairBytes = pt.nClass1 * 4096;
-                im->pairRate = pt.modelRate;
-                if (getenv("HSB200_TRACE")) {
-                    fprintf(stderr, "[hs_b200] class-pair tables: %u x %u classes, modelled %.4f candidates/byte, "
-                                    "%zu prefilter keys%s\n", pt.nClass0, pt.nClass1, pt.modelRate, keys.size(),
-                            big ? " (large-set layout)" : "");
-                }
-                table.resize(sizeof(pt.classWord) + sizeof(pt.pair));
-                memcpy(table.data(), pt.classWord, sizeof(pt.classWord));
-                memcpy(table.data() + sizeof(pt.classWord), pt.pair, sizeof(pt.pair));
-                if (keyed) {
-                    im->keyBytes = kb;
-                    im->bitmapHoles = big ? 0 : 1;
-                    u32 bits = 262144;
-                    if (big) {
-                        /* everything the pair table and 27 queues leave of the 227 KiB */
-                        const u32 queues = (u32)scanSmemBytes(FK_PAIR32, 0, 0, 0, 0, 0, 27) - 65536u;
-                        const u32 room = (u32)maxSmem - 65536u - im->pairBytes - queues;
-                        bits = (room & ~127u) * 8;
-                    }
-                    im->bitmapBits = bits;
-                    buildPairBitmaps(keys, bits, &pairBitmap, &pairBitmap2, &im->bitmap2Shift);
-                }
-                }
-            tables_done:;
+                pairStage(true);
             } else if (g_opts.firstStage == 2 || (g_opts.firstStage == 0 && byteRate < 0.01)) {
                 im->kind = FK_BYTE32;
                 im->stride = 1;
@@ -732,6 +742,14 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
                 }
             }
             programsOk = walkConfirm(bc, h->length, im->confOff, 8 * oct, &im->exhaustible, &tails);
+            if (oct == 2 && g_opts.fatPair && g_opts.split && !tails.empty()) {
+                /* 49..96 literals: the class-pair kernel filters them at 3 TB/s where the 64-bit
+                 * per-byte entries cost two shared-memory wavefronts a byte; its 8 bucket bits
+                 * carry buckets i and i + 8 (confirmKernel unfolds them) */
+                table.clear();
+                pairStage(false);
+                im->bucketFold = 1;
+            }
         } else {
             delete im;
             return HS_INVALID;
@@ -1113,6 +1131,7 @@ void fillParams(const hs_scratch *s, const DevImage *im, const hs_b200_corpus *c
     p->bitmapBytes = im->bitmapBytes;
     p->pairBytes = im->pairBytes;
     p->bitmapHoles = im->bitmapHoles;
+    p->bucketFold = im->bucketFold;
     p->bitmapBits = im->bitmapBits;
     p->bitmapShift = im->bitmapShift;
     p->keyBytes = im->keyBytes;
@@ -1329,7 +1348,7 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"first_stage", &g_opts.firstStage}, {"wide", &g_opts.wide},
         {"split", &g_opts.split},       {"big_set", &g_opts.bigSet},
         {"big_set_classes", &g_opts.bigSetClasses}, {"heavy", &g_opts.heavy},
-        {"gram", &g_opts.gram}};
+        {"gram", &g_opts.gram},                {"fat_pair", &g_opts.fatPair}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;

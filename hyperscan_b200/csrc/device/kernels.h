@@ -121,6 +121,8 @@ struct ScanParams {
     u32 bitmapHoles;       /* FK_PAIR32: 1 = the (32 KiB) bitmap sits in the class rows' upper halves;
                             * 0 = bitmapBytes contiguous bytes after the pair table (large sets) */
     u32 bitmapBits;        /* FK_PAIR32: bits of the first-level bitmap; index = mulhi(key * K, bits) */
+    u32 bucketFold;        /* 1 = 16 confirm buckets (fat Teddy) behind 8 first-stage bits: bit i of a
+                            * candidate stands for buckets i and i + 8 */
     const u32 *bitmap2;    /* optional second-level bitmap in HBM/L2 (large literal sets) */
     u32 bitmap2Shift;      /* 32 - log2(bits); 0 = none */
     u32 confOff;           /* CK_FDR: offset of the confirm base in bc */

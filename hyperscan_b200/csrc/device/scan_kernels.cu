@@ -2174,6 +2174,9 @@ __global__ void __launch_bounds__(256) confirmKernel(const HSB_GRID_CONSTANT Sca
         const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(list + i));
         const u64 g = ((u64)raw.y << 32) | raw.x;
         u32 buckets = raw.z;
+        if (p.bucketFold) {
+            buckets |= buckets << 8;
+        }
         const u64 confVal = confValAt(p, g);
         if (p.confirmKind == CK_NOODLE) {
             if (buckets & 1) {

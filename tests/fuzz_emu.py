@@ -22,7 +22,8 @@ import oracle.ref as ref  # noqa: E402
 
 DEFAULTS = {"warps": 0, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1, "rebuild": 1,
             "domain": 0, "direct": 1, "replicas": 1, "pf_dist": 8, "queue": 2, "first_stage": 3, "wide": 1,
-            "split": 1, "big_set": 0, "big_set_classes": 4, "heavy": 1, "gram": 1, "initial_ring": 1 << 20}
+            "split": 1, "big_set": 0, "big_set_classes": 4, "heavy": 1, "gram": 1, "fat_pair": 1,
+            "initial_ring": 1 << 20}
 
 
 def fuzz_streams(args, rng):
@@ -185,6 +186,8 @@ def main():
                         prefilter=int(rng.integers(0, 2)), tile_bytes=int(rng.choice([512, 1024, 4096])))
         # modes 8, 9: the defaults (class-pair for FDR sets, wide + split for the per-byte tables)
         fat = 48 < nl <= 96 and rng.random() < 0.5 and ref.best_isa() != "corei7"
+        if fat:   # 16 buckets: through the class-pair kernel (folded buckets) or the 64-bit per-byte entries
+            opts["fat_pair"] = int(rng.integers(0, 2))
         for k, v in opts.items():
             capi.set_runtime_option(k, v)
         lens = [int(x) for x in rng.choice([0, 1, 2, 3, 15, 16, 17, 31, 32, 33, 63, 511, 512, 513, 1023, 1024, 1025, 3000, 9000],

@@ -19,11 +19,6 @@ run 8 n8_nccl --exchange nccl --no-cpu
 run 4 n4 --no-cpu
 run 2 n2 --no-cpu
 run 1 n1 --no-cpu
-python - <<'PY'
-import json, glob
-for f in sorted(glob.glob('gpurun_out/${P}_bench_*.json'.replace('${P}', '''$P'''))):
-    pass
-PY
 for f in $O/${P}_bench_*.json; do python - "$f" <<'PY'
 import json, sys
 try:
