@@ -20,7 +20,7 @@ DEFAULT = ("replicas=1;replicas=2;replicas=4;domain=12,replicas=8;domain=12,repl
            "replicas=4,direct=0,warps=24,tile_bytes=1024;replicas=4,tile_bytes=4096")
 BASE = {"warps": 0, "tile_bytes": 1024, "stages": 2, "wide_fdr": 0, "stride": 1, "prefilter": 1,
         "rebuild": 1, "domain": 0, "direct": 1, "replicas": 1, "pf_dist": 8, "queue": 2, "first_stage": 3, "wide": 1,
-        "split": 1, "big_set": 0, "big_set_classes": 4, "heavy": 1, "gram": 1}
+        "split": 1, "big_set": 0, "big_set_classes": 4, "heavy": 1, "gram": 1, "fat_pair": 1}
 
 
 def main():
@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--alphabet", default="")
     ap.add_argument("--lib", default="", help="A/B: another build of libhs_b200.so (same ABI)")
+    ap.add_argument("--avx2", action="store_true", help="compile for an AVX2 platform (49..96 literals: fat Teddy)")
     args = ap.parse_args()
     if args.lib:
         capi.LIB_PATH = os.path.abspath(args.lib)
@@ -43,7 +44,11 @@ def main():
     if args.alphabet:
         al = np.frombuffer(args.alphabet.encode(), dtype=np.uint8)
         data = al[np.random.default_rng(5).integers(0, al.size, size=data.size)]
-    db = capi.compile_lit_multi(lits, flags, ids)
+    plat = None
+    if args.avx2:
+        import ctypes as C
+        plat = C.byref(capi.PlatformInfo(0, capi.HS_CPU_FEATURES_AVX2, 0, 0))
+    db = capi.compile_lit_multi(lits, flags, ids, platform=plat)
     info = db.info()
     print("engine", info.engine_id, "domain", info.fdr_domain, "stride", info.fdr_stride, flush=True)
     corpus = capi.Corpus.upload(data, off, ln)
