@@ -1987,6 +1987,10 @@ hs_error_t hs_b200_nfa_scan_corpus(const void *nfa, size_t nfa_len, const hs_b20
         }
         const u32 rows = hdr.type == NFA_MCCLELLAN_16 ? m.sherman_limit : m.state_count;
         p.tableBytes = (rows << m.alphaShift) * (hdr.type == NFA_MCCLELLAN_16 ? 2u : 1u);
+        p.states = m.state_count;
+        if (hdr.type == NFA_MCCLELLAN_8 && (m.state_count == 0 || m.state_count > 256)) {
+            return HS_INVALID;
+        }
         if (sizeof(NFA) + sizeof(McClellan) + p.tableBytes > nfa_len) {
             return HS_INVALID;
         }

@@ -13,9 +13,10 @@
  *
  * A DFA run is one dependent table lookup per byte, so the parallelism is across
  * blocks: one thread per block (the configurations scan 10^6..10^7 blocks of
- * ~1 KiB), 16 corpus bytes per load.  The transition table sits in shared memory
- * when it fits (McClellan: remap + successor table; Sheng: the 4 KiB of shuffle
- * masks as a byte table), else it is read through L1/L2.  Acceleration schemes
+ * ~1 KiB), the 32 blocks of a warp staged through a shared-memory tile (see "staged
+ * walk" below).  The transition table sits in shared memory when it fits beside the
+ * tiles (McClellan: remap + successor table; Sheng: the 4 KiB of shuffle masks as a
+ * byte table), else it is read through L1/L2.  Acceleration schemes
  * (ACCEL_FLAG states, src/nfa/accel.h) are skip-ahead optimisations only and are
  * ignored; wide states (has_wide) are not handled -- the C ABI refuses them.
  */
@@ -100,138 +101,226 @@ __device__ u32 shermanNext(const u8 *nfa, u32 shermanOffset, u32 shermanLimit, u
     return __ldg(succ + (daddy << as) + cprime);
 }
 
-template <int WIDE16, int SMEM_TABLE>
-__global__ void __launch_bounds__(256) mcclellanKernel(const HSB_GRID_CONSTANT DfaParams p) {
-    HSB_DYNAMIC_SMEM(smem);
-    const u8 *m = p.nfa + sizeof(NFA); /* struct mcclellan */
-    u8 *remapS = smem;
-    for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
-        remapS[i] = __ldg(m + offsetof(McClellan, remap) + i);
+/* ---- staged walk ------------------------------------------------------------------
+ *
+ * One thread per block means 32 lanes reading 32 different blocks, and a dependent lookup
+ * per byte.  Two things decide the speed: how a warp's corpus bytes arrive and how many
+ * instructions a byte costs (the first version: 29 per byte, issue bound at 0.5-1.0 TB/s).
+ *
+ *  - A warp stages its 32 blocks through shared memory: CH bytes of every block per
+ *    refill, loaded coalesced (8 lanes x 16 B = 128 contiguous bytes of one block, four
+ *    blocks per load instruction) into a tile whose rows are CH + 16 bytes apart -- lane t
+ *    then reads ITS row 16 bytes at a time and the eight lanes of a 128-bit shared-memory
+ *    wavefront fall into eight disjoint bank groups (row stride 36 words = 4 banks).  No
+ *    block-wide barrier in the loop: a tile belongs to one warp.
+ *  - The tables are re-laid for the GPU when the CTA starts, from the engine's own bytes:
+ *      McClellan-8: tab[s][byte] = succ[(s << alphaShift) + remap[byte]] (<= 64 KiB): the
+ *        index is ONE byte permute of the data word and the state, one lookup per byte;
+ *      Sheng: 8 copies of the 16 successor bytes of every input byte, copy r in banks
+ *        4r .. 4r+3 (row = byte, 128 B): lane l uses copy l & 7, so only the four lanes
+ *        of a copy can collide;
+ *      McClellan-16: remap in shared memory, the successor table where it is (L1/L2), or
+ *        in shared memory when it fits beside the tiles.
+ *    Full 16-byte pieces run without per-byte bounds or liveness checks (a dead state
+ *    stays dead: checked per piece); accepts leave the loop through an out-of-line call. */
+template <int CH> struct DfaTile {
+    static constexpr u32 ROW = CH + 16;
+    static constexpr u32 WARP_BYTES = 32 * ROW;
+    static constexpr u32 PIECES = CH / 16;          /* 16-byte pieces per row */
+    static constexpr u32 ROWS_PER_LOAD = 32 / PIECES;
+};
+
+enum { ENG_MCC8 = 0, ENG_MCC16 = 1, ENG_SHENG = 2 };
+enum { SHENG_TABLE_BYTES = 256 * 128 };
+
+struct DfaConsts {
+    u32 as, single, report, start, auxOffset, shermanOffset, shermanLimit, acceptLimit8, auxSize, stateMask;
+};
+
+/* reports of a state that was just entered at offset `to` (doComplexReport, mcclellan.c:43-91;
+ * fireReports, sheng_impl.h:116-155) */
+__device__ HSB_NOINLINE void emitAccept(const DfaParams &p, const DfaConsts &k, u32 state, u32 block, u64 to) {
+    if (k.single) {
+        emitDfaMatch(p, k.report, block, to);
+    } else {
+        emitReportList(p, g32(p.nfa + k.auxOffset + k.auxSize * (state & k.stateMask)), block, to);
     }
-    const u8 *succG = m + sizeof(McClellan);
-    if (SMEM_TABLE) {
-        u32 *d = reinterpret_cast<u32 *>(smem + 256);
-        for (u32 i = threadIdx.x; i < (p.tableBytes + 3) / 4; i += blockDim.x) {
-            d[i] = __ldg(reinterpret_cast<const u32 *>(succG) + i);
+}
+
+template <int ENGINE, int SMEM_TABLE, int CH>
+__global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTANT DfaParams p) {
+    HSB_DYNAMIC_SMEM(smem);
+    typedef DfaTile<CH> Tile;
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const u8 *eng = p.nfa + sizeof(NFA); /* struct mcclellan / struct sheng */
+    const u8 *succG = eng + sizeof(McClellan);
+    DfaConsts k;
+    k.as = 0;
+    k.shermanOffset = 0;
+    k.shermanLimit = 0xffffffffu;
+    k.acceptLimit8 = 0;
+    if (ENGINE == ENG_SHENG) {
+        k.start = __ldg(eng + offsetof(Sheng, anchored));
+        k.single = __ldg(eng + offsetof(Sheng, flags)) & SHENG_FLAG_SINGLE_REPORT;
+        k.report = g32(eng + offsetof(Sheng, report));
+        k.auxOffset = g32(eng + offsetof(Sheng, aux_offset));
+        k.auxSize = (u32)sizeof(SstateAux);
+        k.stateMask = SHENG_STATE_MASK;
+    } else {
+        k.as = __ldg(eng + offsetof(McClellan, alphaShift));
+        k.single = __ldg(eng + offsetof(McClellan, flags)) & MCCLELLAN_FLAG_SINGLE;
+        k.report = g32(eng + offsetof(McClellan, arb_report));
+        k.start = g16(eng + offsetof(McClellan, start_anchored));
+        k.auxOffset = g32(eng + offsetof(McClellan, aux_offset));
+        k.shermanOffset = g32(eng + offsetof(McClellan, sherman_offset));
+        if (ENGINE == ENG_MCC16) {
+            k.shermanLimit = g16(eng + offsetof(McClellan, sherman_limit));
+        }
+        k.acceptLimit8 = g16(eng + offsetof(McClellan, accept_limit_8));
+        k.auxSize = (u32)sizeof(MStateAux);
+        k.stateMask = 0xffffffffu;
+    }
+    u32 tabArea;
+    if (ENGINE == ENG_SHENG) {
+        /* [byte][copy r][16 successor bytes] */
+        for (u32 i = threadIdx.x; i < SHENG_TABLE_BYTES; i += blockDim.x) {
+            smem[i] = __ldg(eng + (i >> 7) * 16 + (i & 15));
+        }
+        tabArea = SHENG_TABLE_BYTES;
+    } else if (ENGINE == ENG_MCC8) {
+        const u32 states = g16(eng + offsetof(McClellan, state_count));
+        for (u32 i = threadIdx.x; i < states * 256; i += blockDim.x) {
+            const u32 cp = __ldg(eng + offsetof(McClellan, remap) + (i & 255));
+            smem[i] = __ldg(succG + ((i >> 8) << k.as) + cp);
+        }
+        tabArea = states * 256;
+    } else {
+        for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
+            smem[i] = __ldg(eng + offsetof(McClellan, remap) + i);
+        }
+        tabArea = 256;
+        if (SMEM_TABLE) {
+            u32 *d = reinterpret_cast<u32 *>(smem + 256);
+            const u32 *g = reinterpret_cast<const u32 *>(succG);
+            for (u32 i = threadIdx.x; i < (p.tableBytes + 3) / 4; i += blockDim.x) {
+                d[i] = __ldg(g + i);
+            }
+            tabArea += HSB_ROUNDUP(p.tableBytes, 16);
         }
     }
     __syncthreads();
-    const u32 as = __ldg(m + offsetof(McClellan, alphaShift));
-    const u32 single = __ldg(m + offsetof(McClellan, flags)) & MCCLELLAN_FLAG_SINGLE;
-    const u32 arb = g32(m + offsetof(McClellan, arb_report));
-    const u32 start = g16(m + offsetof(McClellan, start_anchored));
-    const u32 auxOffset = g32(m + offsetof(McClellan, aux_offset));
-    const u32 shermanOffset = g32(m + offsetof(McClellan, sherman_offset));
-    const u32 shermanLimit = WIDE16 ? g16(m + offsetof(McClellan, sherman_limit)) : 0xffffffffu;
-    const u32 acceptLimit8 = g16(m + offsetof(McClellan, accept_limit_8));
-    const u8 *succ8 = SMEM_TABLE ? smem + 256 : succG;
-    const u16 *succ16 = reinterpret_cast<const u16 *>(succ8);
+    u8 *const tile = smem + tabArea + warp * Tile::WARP_BYTES;
+    const u8 *const myRow = tile + lane * Tile::ROW;
+    const u16 *succ16 = reinterpret_cast<const u16 *>(SMEM_TABLE ? smem + 256 : succG);
+    const u32 copyOff = (lane & 7) * 16; /* Sheng: this lane's copy of a row */
 
-    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < p.nblocks; b += gridDim.x * blockDim.x) {
-        const BlockSpan blk = blockSpan(p, b);
-        u32 s = start;
-        u32 i = 0;
-        while (i < blk.len && s) {
-            const uint4 v = load16(p, blk.base + i);
-            const u32 w[4] = {v.x, v.y, v.z, v.w};
-            const u32 n = blk.len - i < 16 ? blk.len - i : 16;
+    /* one input byte: byte j of data word w.  Returns true when the state entered accepts. */
+    auto step = [&](const u32 w, const u32 j, u32 &s) -> bool {
+        if (ENGINE == ENG_MCC8) {
+            s = smem[__byte_perm(w, s, 0x5540 + j)]; /* (s << 8) | byte */
+            return s >= k.acceptLimit8;
+        } else if (ENGINE == ENG_SHENG) {
+            const u32 ch = __byte_perm(w, 0, 0x4440 + j);
+            s = smem[ch * 128 + ((s & SHENG_STATE_MASK) | copyOff)]; /* pshufb(masks[byte], state) */
+            return (s & SHENG_STATE_ACCEPT) != 0;
+        } else {
+            const u32 cp = smem[__byte_perm(w, 0, 0x4440 + j)];
+            u32 e;
+            if (s < k.shermanLimit) {
+                e = SMEM_TABLE ? succ16[(s << k.as) + cp] : __ldg(succ16 + (s << k.as) + cp);
+            } else {
+                e = shermanNext(p.nfa, k.shermanOffset, k.shermanLimit, s, cp, reinterpret_cast<const u16 *>(succG),
+                                k.as);
+            }
+            s = e & MCC_STATE_MASK;
+            return (e & MCC_ACCEPT_FLAG) != 0;
+        }
+    };
+    auto dead = [&](const u32 s) -> bool { return ENGINE == ENG_SHENG ? (s & SHENG_STATE_DEAD) != 0 : s == 0; };
+
+    const u32 ngroups = (p.nblocks + 31) / 32;
+    for (u32 g = blockIdx.x * nwarps + warp; g < ngroups; g += gridDim.x * nwarps) {
+        const u32 b = g * 32 + lane;
+        u64 off = 0;
+        u32 len = 0;
+        if (b < p.nblocks) {
+            const BlockSpan blk = blockSpan(p, b);
+            off = (u64)(blk.base - p.corpus);
+            len = blk.len;
+        }
+        u32 s = k.start;
+        bool live = len != 0;
+        for (u32 r = 0;; r++) {
+            const u32 done = r * CH;
+            if (!__any_sync(0xffffffffu, live && done < len)) {
+                break;
+            }
+            /* refill: rows ROWS_PER_LOAD * i .. of the tile, one 16-byte piece per lane */
 #pragma unroll
-            for (u32 j = 0; j < 16; j++) {
-                if (j < n && s) {
-                    const u32 c = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    const u32 cp = remapS[c];
-                    u32 e;
-                    bool accept;
-                    if (WIDE16) {
-                        if (s < shermanLimit) {
-                            e = SMEM_TABLE ? succ16[(s << as) + cp] : __ldg(succ16 + (s << as) + cp);
-                        } else {
-                            e = shermanNext(p.nfa, shermanOffset, shermanLimit, s, cp,
-                                            reinterpret_cast<const u16 *>(succG), as);
+            for (u32 i = 0; i < Tile::PIECES; i++) {
+                const u32 row = i * Tile::ROWS_PER_LOAD + lane / Tile::PIECES;
+                const u32 piece = lane % Tile::PIECES;
+                const u32 rOffLo = __shfl_sync(0xffffffffu, (u32)off, row);
+                const u32 rOffHi = __shfl_sync(0xffffffffu, (u32)(off >> 32), row);
+                const u32 rLen = __shfl_sync(0xffffffffu, len, row);
+                const u32 pos = done + piece * 16;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (pos < rLen) {
+                    v = load16(p, p.corpus + (((u64)rOffHi << 32) | rOffLo) + pos);
+                }
+                *reinterpret_cast<uint4 *>(tile + row * Tile::ROW + piece * 16) = v;
+            }
+            __syncwarp();
+            if (live && done < len) {
+                const u32 n = len - done < (u32)CH ? len - done : (u32)CH;
+                u32 c = 0;
+#pragma unroll 1
+                for (; c * 16 + 16 <= n && live; c++) { /* full pieces: no per-byte checks */
+                    const uint4 v = *reinterpret_cast<const uint4 *>(myRow + c * 16);
+                    const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (u32 j = 0; j < 16; j++) {
+                        if (step(w[j >> 2], j & 3, s)) {
+                            emitAccept(p, k, s, b, (u64)done + c * 16 + j + 1);
                         }
-                        accept = (e & MCC_ACCEPT_FLAG) != 0;
-                        e &= MCC_STATE_MASK;
-                    } else {
-                        e = SMEM_TABLE ? succ8[(s << as) + cp] : __ldg(succ8 + (s << as) + cp);
-                        accept = e >= acceptLimit8;
                     }
-                    s = e;
-                    if (accept) {
-                        if (single) {
-                            emitDfaMatch(p, arb, b, (u64)i + j + 1);
-                        } else {
-                            emitReportList(p, g32(p.nfa + auxOffset + sizeof(MStateAux) * s), b, (u64)i + j + 1);
+                    live = !dead(s);
+                }
+                if (live && c * 16 < n) { /* the block's last, partial piece */
+                    const uint4 v = *reinterpret_cast<const uint4 *>(myRow + c * 16);
+                    const u32 w[4] = {v.x, v.y, v.z, v.w};
+                    const u32 m = n - c * 16;
+#pragma unroll 1
+                    for (u32 j = 0; j < m; j++) {
+                        if (step(w[j >> 2] >> (8 * (j & 3)), 0, s)) {
+                            emitAccept(p, k, s, b, (u64)done + c * 16 + j + 1);
                         }
                     }
+                    live = !dead(s);
                 }
             }
-            i += 16;
+            __syncwarp();
         }
-        /* nfaExecMcClellan*_Bi: reports of the final state that fire at end of data */
-        const u32 eod = g32(p.nfa + auxOffset + sizeof(MStateAux) * s + offsetof(MStateAux, accept_eod));
-        if (eod) {
-            emitReportList(p, eod, b, blk.len);
+        /* nfaExec*_B: reports of the final state that fire at end of data */
+        if (b < p.nblocks) {
+            const u32 eodOff = ENGINE == ENG_SHENG ? (u32)offsetof(SstateAux, accept_eod)
+                                                   : (u32)offsetof(MStateAux, accept_eod);
+            const u32 eod = g32(p.nfa + k.auxOffset + k.auxSize * (s & k.stateMask) + eodOff);
+            if (eod) {
+                emitReportList(p, eod, b, len);
+            }
         }
     }
 }
 
-/* ---- Sheng ---------------------------------------------------------------------- */
-
-__global__ void __launch_bounds__(256) shengKernel(const HSB_GRID_CONSTANT DfaParams p) {
-    HSB_DYNAMIC_SMEM(smem);
-    const u8 *sh = p.nfa + sizeof(NFA); /* struct sheng: 256 x 16 successor bytes first */
-    {
-        u32 *d = reinterpret_cast<u32 *>(smem);
-        for (u32 i = threadIdx.x; i < 1024; i += blockDim.x) {
-            d[i] = __ldg(reinterpret_cast<const u32 *>(sh) + i);
-        }
-    }
-    __syncthreads();
-    const u32 start = __ldg(sh + offsetof(Sheng, anchored));
-    const u32 single = __ldg(sh + offsetof(Sheng, flags)) & SHENG_FLAG_SINGLE_REPORT;
-    const u32 report = g32(sh + offsetof(Sheng, report));
-    const u32 auxOffset = g32(sh + offsetof(Sheng, aux_offset));
-    for (u32 b = blockIdx.x * blockDim.x + threadIdx.x; b < p.nblocks; b += gridDim.x * blockDim.x) {
-        const BlockSpan blk = blockSpan(p, b);
-        u32 s = start;
-        u32 i = 0;
-        while (i < blk.len && !(s & SHENG_STATE_DEAD)) {
-            const uint4 v = load16(p, blk.base + i);
-            const u32 w[4] = {v.x, v.y, v.z, v.w};
-            const u32 n = blk.len - i < 16 ? blk.len - i : 16;
-#pragma unroll
-            for (u32 j = 0; j < 16; j++) {
-                if (j < n) {
-                    const u32 c = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    s = smem[c * 16 + (s & SHENG_STATE_MASK)]; /* pshufb(masks[c], state) */
-                    if (s & SHENG_STATE_ACCEPT) {
-                        if (single) {
-                            emitDfaMatch(p, report, b, (u64)i + j + 1);
-                        } else {
-                            emitReportList(p, g32(p.nfa + auxOffset + sizeof(SstateAux) * (s & SHENG_STATE_MASK)), b,
-                                           (u64)i + j + 1);
-                        }
-                    }
-                }
-            }
-            i += 16;
-        }
-        const u32 eod = g32(p.nfa + auxOffset + sizeof(SstateAux) * (s & SHENG_STATE_MASK) +
-                            offsetof(SstateAux, accept_eod));
-        if (eod) {
-            emitReportList(p, eod, b, blk.len);
-        }
-    }
-}
-
-template <int WIDE16, int SMEM_TABLE>
-cudaError_t launchMcClellan(const DfaParams &p, int grid, size_t smem, cudaStream_t stream) {
-    void (*kern)(const DfaParams) = mcclellanKernel<WIDE16, SMEM_TABLE>;
+template <int ENGINE, int SMEM_TABLE>
+cudaError_t launchStaged(const DfaParams &p, int grid, int threads, size_t smem, cudaStream_t stream) {
+    void (*kern)(const DfaParams) = dfaStagedKernel<ENGINE, SMEM_TABLE, 128>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         return e;
     }
-    HSB_LAUNCH(kern, grid, 256, smem, stream, p);
+    HSB_LAUNCH(kern, grid, threads, smem, stream, p);
     return cudaGetLastError();
 }
 
@@ -241,23 +330,22 @@ cudaError_t launchDfa(const DfaParams &p, int smCount, int maxSmem, cudaStream_t
     if (!p.nblocks) {
         return cudaSuccess;
     }
-    const u32 perSm = 8; /* 2048 threads per SM when the table is small */
-    const int grid = (int)std::min<u64>((u64)smCount * perSm, ((u64)p.nblocks + 255) / 256);
+    /* one CTA of 32 warps per SM: table area + 32 tiles of 32 x (128 + 16) bytes (144 KiB) */
+    const int threads = 1024;
+    const size_t tiles = (size_t)(threads / 32) * DfaTile<128>::WARP_BYTES;
+    const u64 groups = ((u64)p.nblocks + 31) / 32;
+    const int grid = (int)std::min<u64>((u64)smCount, (groups + threads / 32 - 1) / (threads / 32));
     if (p.kind == NFA_SHENG) {
-        HSB_LAUNCH(shengKernel, grid, 256, 4096, stream, p);
-        return cudaGetLastError();
-    }
-    const bool inSmem = p.tableBytes && (size_t)p.tableBytes + 256 + 1024 <= (size_t)maxSmem;
-    const size_t smem = 256 + (inSmem ? HSB_ROUNDUP((size_t)p.tableBytes, 16) : 0);
-    /* a big table leaves room for one CTA per SM only: keep the grid at one wave of CTAs */
-    const int g = inSmem && smem > 24 * 1024
-                      ? (int)std::min<u64>((u64)grid, (u64)smCount * std::max(1, (int)(maxSmem / (int)smem)))
-                      : grid;
-    if (p.kind == NFA_MCCLELLAN_16) {
-        return inSmem ? launchMcClellan<1, 1>(p, g, smem, stream) : launchMcClellan<1, 0>(p, g, smem, stream);
+        return launchStaged<ENG_SHENG, 1>(p, grid, threads, SHENG_TABLE_BYTES + tiles, stream);
     }
     if (p.kind == NFA_MCCLELLAN_8) {
-        return inSmem ? launchMcClellan<0, 1>(p, g, smem, stream) : launchMcClellan<0, 0>(p, g, smem, stream);
+        return launchStaged<ENG_MCC8, 1>(p, grid, threads, (size_t)p.states * 256 + tiles, stream); /* <= 64 KiB */
+    }
+    if (p.kind == NFA_MCCLELLAN_16) {
+        const size_t inTable = 256 + HSB_ROUNDUP((size_t)p.tableBytes, 16);
+        const bool inSmem = p.tableBytes && inTable + tiles <= (size_t)maxSmem;
+        return inSmem ? launchStaged<ENG_MCC16, 1>(p, grid, threads, inTable + tiles, stream)
+                      : launchStaged<ENG_MCC16, 0>(p, grid, threads, 256 + tiles, stream);
     }
     return cudaErrorInvalidValue;
 }
