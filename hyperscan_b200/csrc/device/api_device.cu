@@ -77,6 +77,7 @@ struct RuntimeOpts {
     int heavy = 1;           /* FK_PAIR32 candidate path: 0 = per-lane entries, 2 = per-word entries (sets that
                               * pass many candidates), 1 = by the modelled first-stage rate */
     int bigSetClasses = 4;   /* ... classes left to the second byte (pair table = 4 KiB each) */
+    int dfaIlp = 2;          /* DFA kernels: blocks walked by one lane at a time (independent state chains) */
     int fatPair = 1;         /* fat Teddy (16 buckets): 1 = class-pair first stage with the buckets folded onto
                               * 8 bits (3.0 TB/s), 0 = 64-bit per-byte entries (FK_BYTE64, 1.75 TB/s) */
     int chunkMB = 128;       /* host->device pipeline granularity */
@@ -101,7 +102,8 @@ void initOpts() {
         {"HSB200_FIRST_STAGE", &g_opts.firstStage}, {"HSB200_WIDE", &g_opts.wide},
         {"HSB200_SPLIT", &g_opts.split},       {"HSB200_BIG_SET", &g_opts.bigSet},
         {"HSB200_BIG_SET_CLASSES", &g_opts.bigSetClasses}, {"HSB200_HEAVY", &g_opts.heavy},
-        {"HSB200_GRAM", &g_opts.gram},         {"HSB200_FAT_PAIR", &g_opts.fatPair}};
+        {"HSB200_GRAM", &g_opts.gram},         {"HSB200_FAT_PAIR", &g_opts.fatPair},
+        {"HSB200_DFA_ILP", &g_opts.dfaIlp}};
     for (auto &x : e) {
         const char *s = getenv(x.env);
         if (s && *s) {
@@ -1348,7 +1350,8 @@ hs_error_t hs_b200_set_runtime_option(const char *key, int value) {
         {"first_stage", &g_opts.firstStage}, {"wide", &g_opts.wide},
         {"split", &g_opts.split},       {"big_set", &g_opts.bigSet},
         {"big_set_classes", &g_opts.bigSetClasses}, {"heavy", &g_opts.heavy},
-        {"gram", &g_opts.gram},                {"fat_pair", &g_opts.fatPair}};
+        {"gram", &g_opts.gram},                {"fat_pair", &g_opts.fatPair},
+        {"dfa_ilp", &g_opts.dfaIlp}};
     for (auto &x : k) {
         if (!strcmp(key, x.n)) {
             *x.v = value;
@@ -1976,6 +1979,7 @@ hs_error_t hs_b200_nfa_scan_corpus(const void *nfa, size_t nfa_len, const hs_b20
     DfaParams p;
     memset(&p, 0, sizeof(p));
     p.kind = hdr.type;
+    p.ilp = g_opts.dfaIlp == 1 ? 1u : 2u;
     if (hdr.type == NFA_MCCLELLAN_8 || hdr.type == NFA_MCCLELLAN_16) {
         if (nfa_len < sizeof(NFA) + sizeof(McClellan)) {
             return HS_INVALID;

@@ -147,7 +147,7 @@ __device__ HSB_NOINLINE void emitAccept(const DfaParams &p, const DfaConsts &k, 
     }
 }
 
-template <int ENGINE, int SMEM_TABLE, int CH>
+template <int ENGINE, int SMEM_TABLE, int CH, int ILP>
 __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTANT DfaParams p) {
     HSB_DYNAMIC_SMEM(smem);
     typedef DfaTile<CH> Tile;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
         }
     }
     __syncthreads();
-    u8 *const tile = smem + tabArea + warp * Tile::WARP_BYTES;
+    u8 *const tile = smem + tabArea + warp * (ILP * Tile::WARP_BYTES);
     const u8 *const myRow = tile + lane * Tile::ROW;
     const u16 *succ16 = reinterpret_cast<const u16 *>(SMEM_TABLE ? smem + 256 : succG);
     const u32 copyOff = (lane & 7) * 16; /* Sheng: this lane's copy of a row */
@@ -238,84 +238,162 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     };
     auto dead = [&](const u32 s) -> bool { return ENGINE == ENG_SHENG ? (s & SHENG_STATE_DEAD) != 0 : s == 0; };
 
-    const u32 ngroups = (p.nblocks + 31) / 32;
+    /* a warp takes 32 * ILP consecutive blocks at a time; lane t owns blocks t, t + 32, ...
+     * of the group: ILP independent state chains in one instruction stream */
+    const u32 perGroup = 32 * ILP;
+    const u32 ngroups = (p.nblocks + perGroup - 1) / perGroup;
     for (u32 g = blockIdx.x * nwarps + warp; g < ngroups; g += gridDim.x * nwarps) {
-        const u32 b = g * 32 + lane;
-        u64 off = 0;
-        u32 len = 0;
-        if (b < p.nblocks) {
-            const BlockSpan blk = blockSpan(p, b);
-            off = (u64)(blk.base - p.corpus);
-            len = blk.len;
+        u32 b[ILP], len[ILP], s[ILP];
+        u64 off[ILP];
+        bool live[ILP];
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+            b[u] = g * perGroup + 32 * u + lane;
+            off[u] = 0;
+            len[u] = 0;
+            if (b[u] < p.nblocks) {
+                const BlockSpan blk = blockSpan(p, b[u]);
+                off[u] = (u64)(blk.base - p.corpus);
+                len[u] = blk.len;
+            }
+            s[u] = k.start;
+            live[u] = len[u] != 0;
         }
-        u32 s = k.start;
-        bool live = len != 0;
         for (u32 r = 0;; r++) {
             const u32 done = r * CH;
-            if (!__any_sync(0xffffffffu, live && done < len)) {
+            bool more = false;
+#pragma unroll
+            for (int u = 0; u < ILP; u++) {
+                more |= live[u] && done < len[u];
+            }
+            if (!__any_sync(0xffffffffu, more)) {
                 break;
             }
-            /* refill: rows ROWS_PER_LOAD * i .. of the tile, one 16-byte piece per lane */
+            /* refill: every load of the tile in flight before the first store */
+            uint4 v[ILP * Tile::PIECES];
 #pragma unroll
-            for (u32 i = 0; i < Tile::PIECES; i++) {
-                const u32 row = i * Tile::ROWS_PER_LOAD + lane / Tile::PIECES;
-                const u32 piece = lane % Tile::PIECES;
-                const u32 rOffLo = __shfl_sync(0xffffffffu, (u32)off, row);
-                const u32 rOffHi = __shfl_sync(0xffffffffu, (u32)(off >> 32), row);
-                const u32 rLen = __shfl_sync(0xffffffffu, len, row);
-                const u32 pos = done + piece * 16;
-                uint4 v = make_uint4(0, 0, 0, 0);
+            for (u32 i = 0; i < ILP * Tile::PIECES; i++) {
+                const u32 u = i / Tile::PIECES;                                 /* which of the lane's blocks' rows */
+                const u32 src = (i % Tile::PIECES) * Tile::ROWS_PER_LOAD + lane / Tile::PIECES; /* owning lane */
+                const u32 rOffLo = __shfl_sync(0xffffffffu, (u32)off[u], src);
+                const u32 rOffHi = __shfl_sync(0xffffffffu, (u32)(off[u] >> 32), src);
+                const u32 rLen = __shfl_sync(0xffffffffu, len[u], src);
+                const u32 pos = done + (lane % Tile::PIECES) * 16;
+                v[i] = make_uint4(0, 0, 0, 0);
                 if (pos < rLen) {
-                    v = load16(p, p.corpus + (((u64)rOffHi << 32) | rOffLo) + pos);
+                    v[i] = load16(p, p.corpus + (((u64)rOffHi << 32) | rOffLo) + pos);
                 }
-                *reinterpret_cast<uint4 *>(tile + row * Tile::ROW + piece * 16) = v;
+            }
+#pragma unroll
+            for (u32 i = 0; i < ILP * Tile::PIECES; i++) {
+                const u32 u = i / Tile::PIECES;
+                const u32 src = (i % Tile::PIECES) * Tile::ROWS_PER_LOAD + lane / Tile::PIECES;
+                *reinterpret_cast<uint4 *>(tile + (u * 32 + src) * Tile::ROW + (lane % Tile::PIECES) * 16) = v[i];
             }
             __syncwarp();
-            if (live && done < len) {
-                const u32 n = len - done < (u32)CH ? len - done : (u32)CH;
-                u32 c = 0;
+            u32 n[ILP];
+            bool fullAll = true;
+#pragma unroll
+            for (int u = 0; u < ILP; u++) {
+                n[u] = !live[u] || done >= len[u] ? 0u : (len[u] - done < (u32)CH ? len[u] - done : (u32)CH);
+            }
+            u32 c = 0;
+            if (ILP > 1) {
+                /* all chains of the lane alive with a full piece ahead: interleaved */
 #pragma unroll 1
-                for (; c * 16 + 16 <= n && live; c++) { /* full pieces: no per-byte checks */
-                    const uint4 v = *reinterpret_cast<const uint4 *>(myRow + c * 16);
-                    const u32 w[4] = {v.x, v.y, v.z, v.w};
+                for (;; c++) {
+                    fullAll = true;
+#pragma unroll
+                    for (int u = 0; u < ILP; u++) {
+                        fullAll &= live[u] && c * 16 + 16 <= n[u];
+                    }
+                    if (!fullAll) {
+                        break;
+                    }
+                    u32 w[ILP][4];
+#pragma unroll
+                    for (int u = 0; u < ILP; u++) {
+                        const uint4 x = *reinterpret_cast<const uint4 *>(myRow + u * 32 * Tile::ROW + c * 16);
+                        w[u][0] = x.x;
+                        w[u][1] = x.y;
+                        w[u][2] = x.z;
+                        w[u][3] = x.w;
+                    }
 #pragma unroll
                     for (u32 j = 0; j < 16; j++) {
-                        if (step(w[j >> 2], j & 3, s)) {
-                            emitAccept(p, k, s, b, (u64)done + c * 16 + j + 1);
+#pragma unroll
+                        for (int u = 0; u < ILP; u++) {
+                            if (step(w[u][j >> 2], j & 3, s[u])) {
+                                emitAccept(p, k, s[u], b[u], (u64)done + c * 16 + j + 1);
+                            }
                         }
                     }
-                    live = !dead(s);
+#pragma unroll
+                    for (int u = 0; u < ILP; u++) {
+                        live[u] = !dead(s[u]);
+                    }
                 }
-                if (live && c * 16 < n) { /* the block's last, partial piece */
-                    const uint4 v = *reinterpret_cast<const uint4 *>(myRow + c * 16);
-                    const u32 w[4] = {v.x, v.y, v.z, v.w};
-                    const u32 m = n - c * 16;
+            }
+            /* what is left of each chain's CH bytes, one chain at a time */
+#pragma unroll
+            for (int u = 0; u < ILP; u++) {
+                const u8 *row = myRow + u * 32 * Tile::ROW;
+                u32 cc = c;
+#pragma unroll 1
+                for (; live[u] && cc * 16 + 16 <= n[u]; cc++) { /* full pieces: no per-byte checks */
+                    const uint4 x = *reinterpret_cast<const uint4 *>(row + cc * 16);
+                    const u32 w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (u32 j = 0; j < 16; j++) {
+                        if (step(w[j >> 2], j & 3, s[u])) {
+                            emitAccept(p, k, s[u], b[u], (u64)done + cc * 16 + j + 1);
+                        }
+                    }
+                    live[u] = !dead(s[u]);
+                }
+                if (live[u] && cc * 16 < n[u]) { /* the block's last, partial piece */
+                    const uint4 x = *reinterpret_cast<const uint4 *>(row + cc * 16);
+                    const u32 w[4] = {x.x, x.y, x.z, x.w};
+                    const u32 m = n[u] - cc * 16;
 #pragma unroll 1
                     for (u32 j = 0; j < m; j++) {
-                        if (step(w[j >> 2] >> (8 * (j & 3)), 0, s)) {
-                            emitAccept(p, k, s, b, (u64)done + c * 16 + j + 1);
+                        if (step(w[j >> 2] >> (8 * (j & 3)), 0, s[u])) {
+                            emitAccept(p, k, s[u], b[u], (u64)done + cc * 16 + j + 1);
                         }
                     }
-                    live = !dead(s);
+                    live[u] = !dead(s[u]);
                 }
             }
             __syncwarp();
         }
         /* nfaExec*_B: reports of the final state that fire at end of data */
-        if (b < p.nblocks) {
-            const u32 eodOff = ENGINE == ENG_SHENG ? (u32)offsetof(SstateAux, accept_eod)
-                                                   : (u32)offsetof(MStateAux, accept_eod);
-            const u32 eod = g32(p.nfa + k.auxOffset + k.auxSize * (s & k.stateMask) + eodOff);
-            if (eod) {
-                emitReportList(p, eod, b, len);
+#pragma unroll
+        for (int u = 0; u < ILP; u++) {
+            if (b[u] < p.nblocks) {
+                const u32 eodOff = ENGINE == ENG_SHENG ? (u32)offsetof(SstateAux, accept_eod)
+                                                       : (u32)offsetof(MStateAux, accept_eod);
+                const u32 eod = g32(p.nfa + k.auxOffset + k.auxSize * (s[u] & k.stateMask) + eodOff);
+                if (eod) {
+                    emitReportList(p, eod, b[u], len[u]);
+                }
             }
         }
     }
 }
 
 template <int ENGINE, int SMEM_TABLE>
-cudaError_t launchStaged(const DfaParams &p, int grid, int threads, size_t smem, cudaStream_t stream) {
-    void (*kern)(const DfaParams) = dfaStagedKernel<ENGINE, SMEM_TABLE, 128>;
+cudaError_t launchStaged(const DfaParams &p, int smCount, size_t tableBytes, cudaStream_t stream) {
+    /* one CTA of 32 warps per SM: table area + per warp a tile of 32 * ILP rows.
+     * ilp 2: two blocks per lane, 64 bytes of each per refill (160 KiB of tiles);
+     * ilp 1: one block per lane, 128 bytes per refill (144 KiB) */
+    const int threads = 1024;
+    const bool two = p.ilp != 1;
+    const size_t tiles = (size_t)(threads / 32) * (two ? 2 * DfaTile<64>::WARP_BYTES : DfaTile<128>::WARP_BYTES);
+    const u64 groups = ((u64)p.nblocks + (two ? 63 : 31)) / (two ? 64 : 32);
+    const int grid = (int)std::min<u64>((u64)smCount, (groups + threads / 32 - 1) / (threads / 32));
+    void (*kern)(const DfaParams) =
+        two ? dfaStagedKernel<ENGINE, SMEM_TABLE, 64, 2> : dfaStagedKernel<ENGINE, SMEM_TABLE, 128, 1>;
+    const size_t smem = tableBytes + tiles;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
         return e;
@@ -330,22 +408,18 @@ cudaError_t launchDfa(const DfaParams &p, int smCount, int maxSmem, cudaStream_t
     if (!p.nblocks) {
         return cudaSuccess;
     }
-    /* one CTA of 32 warps per SM: table area + 32 tiles of 32 x (128 + 16) bytes (144 KiB) */
-    const int threads = 1024;
-    const size_t tiles = (size_t)(threads / 32) * DfaTile<128>::WARP_BYTES;
-    const u64 groups = ((u64)p.nblocks + 31) / 32;
-    const int grid = (int)std::min<u64>((u64)smCount, (groups + threads / 32 - 1) / (threads / 32));
+    const size_t tilesMax = 32 * 2 * DfaTile<64>::WARP_BYTES;
     if (p.kind == NFA_SHENG) {
-        return launchStaged<ENG_SHENG, 1>(p, grid, threads, SHENG_TABLE_BYTES + tiles, stream);
+        return launchStaged<ENG_SHENG, 1>(p, smCount, SHENG_TABLE_BYTES, stream);
     }
     if (p.kind == NFA_MCCLELLAN_8) {
-        return launchStaged<ENG_MCC8, 1>(p, grid, threads, (size_t)p.states * 256 + tiles, stream); /* <= 64 KiB */
+        return launchStaged<ENG_MCC8, 1>(p, smCount, (size_t)p.states * 256, stream); /* <= 64 KiB */
     }
     if (p.kind == NFA_MCCLELLAN_16) {
         const size_t inTable = 256 + HSB_ROUNDUP((size_t)p.tableBytes, 16);
-        const bool inSmem = p.tableBytes && inTable + tiles <= (size_t)maxSmem;
-        return inSmem ? launchStaged<ENG_MCC16, 1>(p, grid, threads, inTable + tiles, stream)
-                      : launchStaged<ENG_MCC16, 0>(p, grid, threads, 256 + tiles, stream);
+        const bool inSmem = p.tableBytes && inTable + tilesMax <= (size_t)maxSmem;
+        return inSmem ? launchStaged<ENG_MCC16, 1>(p, smCount, inTable, stream)
+                      : launchStaged<ENG_MCC16, 0>(p, smCount, 256, stream);
     }
     return cudaErrorInvalidValue;
 }

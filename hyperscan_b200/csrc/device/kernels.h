@@ -189,6 +189,7 @@ struct DfaParams {
     const u8 *nfa;
     u32 kind;        /* NFA.type: NFA_MCCLELLAN_8 / NFA_MCCLELLAN_16 / NFA_SHENG */
     u32 tableBytes;  /* McClellan: bytes of the successor table (staged in shared memory if it fits) */
+    u32 ilp;         /* blocks walked by one lane at a time: 1 or 2 (runtime option dfa_ilp) */
     u32 states;      /* McClellan-8: state_count (<= 256): rows of the byte-indexed table built in shared memory */
     DevMatch *out;   /* {report, block, offset after the last byte} */
     u32 outCap;

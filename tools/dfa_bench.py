@@ -19,9 +19,11 @@ def main():
     ap.add_argument("--mb", type=int, default=256)
     ap.add_argument("--block-len", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--ilp", type=int, default=2, help="blocks per lane (runtime option dfa_ilp)")
     args = ap.parse_args()
     bl = args.block_len
     nb = (args.mb << 20) // bl
+    capi.set_runtime_option("dfa_ilp", args.ilp)
     for name, (kind, nl, lo, hi) in KINDS.items():
         alpha = b"abcdefghijklmnopqrstuvwxyz" if nl > 100 else (b"abcdefgh" if nl > 4 else b"abc")
         lits, flags, ids = synth.literal_set(nl, min_len=lo, max_len=hi, seed=nl, caseless_frac=0.0, alphabet=alpha)
@@ -34,7 +36,7 @@ def main():
             if i >= 2:
                 ms.append(kms)
         k = float(np.median(ms))
-        print(json.dumps({"engine": name, "engine_bytes": len(eng), "blocks": nb, "block_len": bl, "ms": round(k, 4),
+        print(json.dumps({"engine": name, "engine_bytes": len(eng), "blocks": nb, "block_len": bl, "ilp": args.ilp, "ms": round(k, 4),
                           "GBps": round(nb * bl / (k * 1e-3) / 1e9, 1), "records": int(got.size)}), flush=True)
         corpus.free()
 
