@@ -77,7 +77,8 @@ struct RuntimeOpts {
     int heavy = 1;           /* FK_PAIR32 candidate path: 0 = per-lane entries, 2 = per-word entries (sets that
                               * pass many candidates), 1 = by the modelled first-stage rate */
     int bigSetClasses = 4;   /* ... classes left to the second byte (pair table = 4 KiB each) */
-    int dfaIlp = 2;          /* DFA kernels: blocks walked by one lane at a time (independent state chains) */
+    int dfaIlp = 1;          /* DFA kernels: blocks walked by one lane at a time; 2 = two interleaved state chains
+                              * per lane, measured SLOWER (half the warps per block count: profiles/r02_dfa.log) */
     int fatPair = 1;         /* fat Teddy (16 buckets): 1 = class-pair first stage with the buckets folded onto
                               * 8 bits (3.0 TB/s), 0 = 64-bit per-byte entries (FK_BYTE64, 1.75 TB/s) */
     int chunkMB = 128;       /* host->device pipeline granularity */
@@ -1979,7 +1980,7 @@ hs_error_t hs_b200_nfa_scan_corpus(const void *nfa, size_t nfa_len, const hs_b20
     DfaParams p;
     memset(&p, 0, sizeof(p));
     p.kind = hdr.type;
-    p.ilp = g_opts.dfaIlp == 1 ? 1u : 2u;
+    p.ilp = g_opts.dfaIlp == 2 ? 2u : 1u;
     if (hdr.type == NFA_MCCLELLAN_8 || hdr.type == NFA_MCCLELLAN_16) {
         if (nfa_len < sizeof(NFA) + sizeof(McClellan)) {
             return HS_INVALID;
@@ -2049,10 +2050,12 @@ hs_error_t hs_b200_nfa_scan_corpus(const void *nfa, size_t nfa_len, const hs_b20
             capDev = ctr[CTR_MATCHES] + ctr[CTR_MATCHES] / 8 + 1024;
             continue;
         }
-        host.resize(ctr[CTR_MATCHES]);
+        host.resize(ctr[CTR_MATCHES]); /* reserved slots: the lanes' unused ones carry id 0xffffffff */
         if (!host.empty()) {
             e = cudaMemcpy(host.data(), d_out, host.size() * sizeof(DevMatch), cudaMemcpyDeviceToHost);
         }
+        host.erase(std::remove_if(host.begin(), host.end(), [](const DevMatch &m) { return m.id == 0xffffffffu; }),
+                   host.end());
         if (kernel_ms && e == cudaSuccess) {
             cudaEventElapsedTime(kernel_ms, ev0, ev1);
         }

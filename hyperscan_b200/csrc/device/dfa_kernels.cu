@@ -34,22 +34,45 @@ namespace {
 __device__ __forceinline__ u32 g32(const u8 *p) { return __ldg(reinterpret_cast<const u32 *>(p)); }
 __device__ __forceinline__ u16 g16(const u8 *p) { return __ldg(reinterpret_cast<const u16 *>(p)); }
 
-__device__ __forceinline__ void emitDfaMatch(const DfaParams &p, u32 id, u32 block, u64 to) {
-    const u32 i = atomicAdd(p.counters + CTR_MATCHES, 1u);
-    if (i < p.outCap) {
+/* Records leave through slots a LANE reserves eight at a time (`cursor` = its next slot;
+ * a multiple of 8 = nothing reserved): one atomic on the shared counter per eight records
+ * instead of one -- and one dependent L2 round trip -- per record.  Slots a lane reserved
+ * but did not fill are written as DFA_NO_RECORD and dropped by the caller; CTR_MATCHES
+ * counts reserved slots. */
+enum : u32 { DFA_SLOTS = 8, DFA_NO_RECORD = 0xffffffffu };
+
+__device__ __forceinline__ u32 emitDfaMatch(const DfaParams &p, u32 cursor, u32 id, u32 block, u64 to) {
+    if ((cursor & (DFA_SLOTS - 1)) == 0) {
+        cursor = atomicAdd(p.counters + CTR_MATCHES, (u32)DFA_SLOTS);
+    }
+    if (cursor < p.outCap) {
         DevMatch m;
         m.id = id;
         m.block = block;
         m.to = to;
-        *reinterpret_cast<uint4 *>(p.out + i) = *reinterpret_cast<const uint4 *>(&m);
+        *reinterpret_cast<uint4 *>(p.out + cursor) = *reinterpret_cast<const uint4 *>(&m);
     }
+    return cursor + 1;
 }
 
 /* struct report_list {u32 count; ReportID report[]} at NFA offset `off` */
-__device__ void emitReportList(const DfaParams &p, u32 off, u32 block, u64 to) {
+__device__ u32 emitReportList(const DfaParams &p, u32 cursor, u32 off, u32 block, u64 to) {
     const u32 n = g32(p.nfa + off);
     for (u32 i = 0; i < n; i++) {
-        emitDfaMatch(p, g32(p.nfa + off + 4 + 4 * i), block, to);
+        cursor = emitDfaMatch(p, cursor, g32(p.nfa + off + 4 + 4 * i), block, to);
+    }
+    return cursor;
+}
+
+__device__ void padReserved(const DfaParams &p, u32 cursor) {
+    for (; cursor & (DFA_SLOTS - 1); cursor++) {
+        if (cursor < p.outCap) {
+            DevMatch m;
+            m.id = DFA_NO_RECORD;
+            m.block = 0;
+            m.to = 0;
+            *reinterpret_cast<uint4 *>(p.out + cursor) = *reinterpret_cast<const uint4 *>(&m);
+        }
     }
 }
 
@@ -60,15 +83,20 @@ struct BlockSpan {
 
 /* 16 corpus bytes at q (16-byte aligned: blocks start aligned); bytes past the readable
  * end read as zero (they lie behind the block's end and are not consumed) */
+__device__ HSB_NOINLINE uint4 load16Tail(const u8 *q, const u8 *end) { /* the corpus' last bytes: out of line */
+    u32 w[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (u32 i = 0; i < 16 && q + i < end; i++) {
+        w[i >> 2] |= (u32)__ldg(q + i) << (8 * (i & 3));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 __device__ __forceinline__ uint4 load16(const DfaParams &p, const u8 *q) {
     if (q + 16 <= p.corpus + p.readableEnd) {
         return __ldg(reinterpret_cast<const uint4 *>(q));
     }
-    u32 w[4] = {0, 0, 0, 0};
-    for (u32 i = 0; i < 16 && q + i < p.corpus + p.readableEnd; i++) {
-        w[i >> 2] |= (u32)__ldg(q + i) << (8 * (i & 3));
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
+    return load16Tail(q, p.corpus + p.readableEnd);
 }
 
 __device__ __forceinline__ BlockSpan blockSpan(const DfaParams &p, u32 b) {
@@ -138,13 +166,13 @@ struct DfaConsts {
 };
 
 /* reports of a state that was just entered at offset `to` (doComplexReport, mcclellan.c:43-91;
- * fireReports, sheng_impl.h:116-155) */
-__device__ HSB_NOINLINE void emitAccept(const DfaParams &p, const DfaConsts &k, u32 state, u32 block, u64 to) {
-    if (k.single) {
-        emitDfaMatch(p, k.report, block, to);
-    } else {
-        emitReportList(p, g32(p.nfa + k.auxOffset + k.auxSize * (state & k.stateMask)), block, to);
+ * fireReports, sheng_impl.h:116-155).  what = the one report of a single-report engine, else
+ * the offset of the state's aux record.  Returns the lane's record cursor. */
+__device__ HSB_NOINLINE u32 emitAccept(const DfaParams &p, u32 cursor, u32 single, u32 what, u32 block, u64 to) {
+    if (single) {
+        return emitDfaMatch(p, cursor, what, block, to);
     }
+    return emitReportList(p, cursor, g32(p.nfa + what), block, to);
 }
 
 template <int ENGINE, int SMEM_TABLE, int CH, int ILP>
@@ -236,6 +264,10 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
             return (e & MCC_ACCEPT_FLAG) != 0;
         }
     };
+    auto acceptWhat = [&](const u32 s) -> u32 {
+        return k.single ? k.report : k.auxOffset + k.auxSize * (s & k.stateMask);
+    };
+    u32 cursor = 0; /* this lane's next record slot (emitDfaMatch) */
     auto dead = [&](const u32 s) -> bool { return ENGINE == ENG_SHENG ? (s & SHENG_STATE_DEAD) != 0 : s == 0; };
 
     /* a warp takes 32 * ILP consecutive blocks at a time; lane t owns blocks t, t + 32, ...
@@ -324,7 +356,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
 #pragma unroll
                         for (int u = 0; u < ILP; u++) {
                             if (step(w[u][j >> 2], j & 3, s[u])) {
-                                emitAccept(p, k, s[u], b[u], (u64)done + c * 16 + j + 1);
+                                cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + c * 16 + j + 1);
                             }
                         }
                     }
@@ -346,7 +378,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
 #pragma unroll
                     for (u32 j = 0; j < 16; j++) {
                         if (step(w[j >> 2], j & 3, s[u])) {
-                            emitAccept(p, k, s[u], b[u], (u64)done + cc * 16 + j + 1);
+                            cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + cc * 16 + j + 1);
                         }
                     }
                     live[u] = !dead(s[u]);
@@ -358,7 +390,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
 #pragma unroll 1
                     for (u32 j = 0; j < m; j++) {
                         if (step(w[j >> 2] >> (8 * (j & 3)), 0, s[u])) {
-                            emitAccept(p, k, s[u], b[u], (u64)done + cc * 16 + j + 1);
+                            cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + cc * 16 + j + 1);
                         }
                     }
                     live[u] = !dead(s[u]);
@@ -374,11 +406,12 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
                                                        : (u32)offsetof(MStateAux, accept_eod);
                 const u32 eod = g32(p.nfa + k.auxOffset + k.auxSize * (s[u] & k.stateMask) + eodOff);
                 if (eod) {
-                    emitReportList(p, eod, b[u], len[u]);
+                    cursor = emitReportList(p, cursor, eod, b[u], len[u]);
                 }
             }
         }
     }
+    padReserved(p, cursor);
 }
 
 template <int ENGINE, int SMEM_TABLE>
@@ -387,7 +420,7 @@ cudaError_t launchStaged(const DfaParams &p, int smCount, size_t tableBytes, cud
      * ilp 2: two blocks per lane, 64 bytes of each per refill (160 KiB of tiles);
      * ilp 1: one block per lane, 128 bytes per refill (144 KiB) */
     const int threads = 1024;
-    const bool two = p.ilp != 1;
+    const bool two = p.ilp == 2;
     const size_t tiles = (size_t)(threads / 32) * (two ? 2 * DfaTile<64>::WARP_BYTES : DfaTile<128>::WARP_BYTES);
     const u64 groups = ((u64)p.nblocks + (two ? 63 : 31)) / (two ? 64 : 32);
     const int grid = (int)std::min<u64>((u64)smCount, (groups + threads / 32 - 1) / (threads / 32));

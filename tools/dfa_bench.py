@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--mb", type=int, default=256)
     ap.add_argument("--block-len", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--ilp", type=int, default=2, help="blocks per lane (runtime option dfa_ilp)")
+    ap.add_argument("--ilp", type=int, default=1, help="blocks per lane (runtime option dfa_ilp)")
     args = ap.parse_args()
     bl = args.block_len
     nb = (args.mb << 20) // bl
