@@ -452,7 +452,7 @@ def secondary_single_gpu(args, capi, torch, base, peak):
 
     # DFA engines: literal-set automata in the reference layout, one block per thread
     kinds = {"mcclellan16_2000lits": (2, 2000, 4, 8), "mcclellan8_30lits": (1, 30, 2, 4), "sheng_4lits": (3, 4, 1, 3)}
-    ndfa = min(nb, 1 << 18)
+    ndfa = nb
     off = np.arange(ndfa, dtype=np.uint64) * np.uint64(bl)
     ln = np.full(ndfa, bl, dtype=np.uint32)
     for name, (kind, nl, lo, hi) in kinds.items():
