@@ -144,11 +144,12 @@ __device__ u32 shermanNext(const u8 *nfa, u32 shermanOffset, u32 shermanLimit, u
  *  - The tables are re-laid for the GPU when the CTA starts, from the engine's own bytes:
  *      McClellan-8: tab[s][byte] = succ[(s << alphaShift) + remap[byte]] (<= 64 KiB): the
  *        index is ONE byte permute of the data word and the state, one lookup per byte;
- *      Sheng: 8 copies of the 16 successor bytes of every input byte (lane l uses copy
- *        l & 7), rows 144 bytes apart: copy r of byte c starts at bank 4 (c + r) mod 32, so
- *        the four lanes of a copy collide only when their bytes agree modulo 8 -- with
- *        128-byte rows they met in bank 4r whenever the automaton sat in its first states
- *        (4.75 wavefronts per lookup measured, the shared-memory pipe 92 % busy);
+ *      Sheng: 8 copies of the 16 successor bytes of every input byte c (row = c, 128 B;
+ *        lane l uses copy l & 7 = banks 4r .. 4r+3), the successor of state s at position
+ *        (s + 4c) & 15 of its copy: the four lanes of a copy, which mostly sit in the same
+ *        few states, collide only when their bytes agree modulo 4 -- unrotated they met in
+ *        one bank (4.75 wavefronts per lookup measured, the shared-memory pipe 92 % busy;
+ *        rotating whole rows instead threw all 32 lanes onto 8 banks: slower still);
  *      McClellan-16: remap in shared memory, the successor table where it is (L1/L2), or
  *        in shared memory when it fits beside the tiles.
  *    Full 16-byte pieces run without per-byte bounds or liveness checks (a dead state
@@ -161,7 +162,7 @@ template <int CH> struct DfaTile {
 };
 
 enum { ENG_MCC8 = 0, ENG_MCC16 = 1, ENG_SHENG = 2 };
-enum { SHENG_ROW = 144, SHENG_TABLE_BYTES = 256 * SHENG_ROW };
+enum { SHENG_ROW = 128, SHENG_TABLE_BYTES = 256 * SHENG_ROW };
 
 struct DfaConsts {
     u32 as, single, report, start, auxOffset, shermanOffset, shermanLimit, acceptLimit8, auxSize, stateMask;
@@ -212,9 +213,10 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     }
     u32 tabArea;
     if (ENGINE == ENG_SHENG) {
-        /* [byte][copy r][16 successor bytes], rows SHENG_ROW = 144 bytes apart */
-        for (u32 i = threadIdx.x; i < 256 * 128; i += blockDim.x) {
-            smem[(i >> 7) * SHENG_ROW + (i & 127)] = __ldg(eng + (i >> 7) * 16 + (i & 15));
+        /* [byte c][copy r][16 successor bytes, the one of state s at position (s + 4c) & 15] */
+        for (u32 i = threadIdx.x; i < SHENG_TABLE_BYTES; i += blockDim.x) {
+            const u32 c = i >> 7;
+            smem[i] = __ldg(eng + c * 16 + (((i & 15) - 4 * c) & 15));
         }
         tabArea = SHENG_TABLE_BYTES;
     } else if (ENGINE == ENG_MCC8) {
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
             return s >= k.acceptLimit8;
         } else if (ENGINE == ENG_SHENG) {
             const u32 ch = __byte_perm(w, 0, 0x4440 + j);
-            s = smem[ch * SHENG_ROW + ((s & SHENG_STATE_MASK) | copyOff)]; /* pshufb(masks[byte], state) */
+            s = smem[ch * SHENG_ROW + (((s + 4 * ch) & SHENG_STATE_MASK) | copyOff)]; /* pshufb(masks[byte], state) */
             return (s & SHENG_STATE_ACCEPT) != 0;
         } else {
             const u32 cp = smem[__byte_perm(w, 0, 0x4440 + j)];

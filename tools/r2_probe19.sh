@@ -1,0 +1,14 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+O=gpurun_out
+P=${1:-r02b}
+python -m pytest tests/test_dfa.py tests/test_small_write.py -x -q -m gpu > $O/${P}_gpu_tests_dfa.log 2>&1
+tail -2 $O/${P}_gpu_tests_dfa.log
+python tools/dfa_bench.py --mb 256 > $O/${P}_dfa.log 2>&1
+python tools/dfa_bench.py --mb 1024 >> $O/${P}_dfa.log 2>&1
+cat $O/${P}_dfa.log
+ncu --set full --import-source on --clock-control none -k regex:dfaStaged -s 7 -c 1 -o $O/${P}_dfa_sheng \
+    python tools/dfa_bench.py --mb 256 --reps 1 > $O/${P}_ncu_dfa2.out 2>&1
+python bench.py > $O/${P}_bench_n1.json 2> $O/${P}_bench_n1.err
+tail -c 300 $O/${P}_bench_n1.err; echo
