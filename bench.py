@@ -6,12 +6,14 @@
 
 Workload = BASELINE.json configs[1]: 1 000 short literals, 1 GiB synthetic corpus
 as 2^20 blocks x 1 KiB, block mode, one B200 (per rank; blocks shard by rank).
-One "step" = one hsbench repeat GROUP: --passes-per-step (default 10) passes of the
+One "step" = one hsbench repeat GROUP: --passes-per-step (default 40) passes of the
 literal scan path over the whole resident corpus (hsbench's inner loop: every block
 through hs_scan once per repeat, -n repeats, tools/hsbench/main.cpp:503-527); the
-driver's --steps 20 therefore times 200 passes, so that the barrier around the
-timed region is < 0.5 % of it.  Metric: Gbit/s = 8 * corpus bytes * passes /
-seconds / 1e9 (main.cpp:721-725), whole job.
+default --steps 10 therefore times 400 passes (~146 ms per GPU), so that a barrier
+is < 0.5 % of the region and nvidia-smi gets its samples.  The region is timed with
+CUDA events on the launching stream, max over ranks (the wall clock with the closing
+barrier is printed beside it).  Metric: Gbit/s = 8 * corpus bytes * passes / seconds /
+1e9 (main.cpp:721-725), whole job.
 
 Prints ONE JSON line (rank 0):
   value      corpus resident in HBM, device-timed region, max over ranks
@@ -23,7 +25,8 @@ Prints ONE JSON line (rank 0):
   secondary  (N = 1) the other literal configurations of BASELINE.json, each with
              kernel-event roofline and a bit-exact check against the reference
              runtime: config 1 through the stock hs_scan, Teddy 48, fat Teddy 96,
-             config-5 shape (50 000 literals), config-4 shape (stream set)
+             config-5 shape (50 000 literals), config-4 shape (stream set), the DFA
+             engines (McClellan 8 / 16, Sheng) against the reference engines
              (N > 1) the config-5 shape sharded at 8 GiB per GPU
 """
 import argparse
