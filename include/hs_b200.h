@@ -491,8 +491,18 @@ hs_error_t hs_b200_test_compile_programs(const char *const *lits, const size_t *
  * (rebuilt table's hash bits, 0 = as compiled), "direct" (1: corpus loaded
  * straight into registers, 0: TMA-staged tiles in shared memory), "chunk_mb"
  * (host->device pipeline granularity),
- * "initial_ring" (match records).  Options that shape the device image
- * ("wide_fdr", "prefilter", "rebuild", "domain") apply to scratches allocated afterwards. */
+ * "initial_ring" (match records); kernel selection: "first_stage" (FDR sets: 3 =
+ * class-pair tables, 1 = two-byte hash table, 2 = per-byte table), "wide" / "split"
+ * (per-byte tables: 32-byte lanes / confirm in a second kernel), "queue", "replicas",
+ * "pf_dist", "gram" (class 4-gram first stage: 0 never, 1 from 10 000 prefilter keys,
+ * 2 whenever all literals have 4 bytes), "heavy" (class-pair candidate path: per-word
+ * queue entries 0 never / 1 by the modelled rate / 2 always), "big_set",
+ * "big_set_classes", "fat_pair" (fat Teddy through the class-pair kernel, 1) and
+ * "dfa_ilp" (DFA kernels: blocks per lane, 1).  Options that shape the device image
+ * ("wide_fdr", "prefilter", "rebuild", "domain", "first_stage", "gram", "big_set*",
+ * "fat_pair") apply to scratches allocated afterwards.  The defaults are the measured
+ * best; the others exist for A/B runs (tools/sweep.py) and are all
+ * covered by the parity tests and the fuzzer. */
 hs_error_t hs_b200_set_runtime_option(const char *key, int value);
 
 /* Counters of the last finished scan: [0] raw records, [1] error, [2]
