@@ -621,6 +621,57 @@ def dfa_from_table(next_table, start_anchored, start_floating, reports, reports_
     return out.raw[:sz]
 
 
+def limex32_from_literals(lits, caseless, reports):
+    """hs_b200_limex32_from_literals: the engine bytes (struct NFA + LimExNFA32 ...)."""
+    n = len(lits)
+    arr = (C.c_char_p * n)(*[bytes(x) for x in lits])
+    lens = (C.c_size_t * n)(*[len(x) for x in lits])
+    cl = (C.c_uint * n)(*[int(bool(x)) for x in (caseless or [0] * n)])
+    rp = (C.c_uint * n)(*[int(x) for x in reports])
+    L = lib()
+    L.hs_b200_limex32_from_literals.restype = C.c_long
+    L.hs_b200_limex32_from_literals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p,
+                                                C.c_size_t]
+    cap = 1 << 20
+    out = C.create_string_buffer(cap)
+    sz = L.hs_b200_limex32_from_literals(arr, lens, cl, rp, n, out, cap)
+    if sz < 0:
+        raise HsError(HS_COMPILER_ERROR, "limex32_from_literals")
+    return out.raw[:sz]
+
+
+def limex32_from_spec(reach, init, init_ds, succ, reports, reports_eod, squash_mask=None, squash_kind=None):
+    """hs_b200_limex32_from_spec: reach uint32[256], succ uint32[nstates], reports / reports_eod one
+    list of report ids per state, squash_kind uint8[nstates] (0 / 1 / 3) with squash_mask."""
+    sc = np.ascontiguousarray(succ, dtype=np.uint32)
+    n = sc.size
+    rc = np.ascontiguousarray(reach, dtype=np.uint32)
+
+    def flat(lists):
+        off = np.zeros(n + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(x) for x in lists])
+        vals = np.array([v for x in lists for v in x] + [0], dtype=np.uint32)
+        return off, vals
+
+    ro, rv = flat(reports)
+    eo, ev = flat(reports_eod)
+    sm = np.ascontiguousarray(squash_mask if squash_mask is not None else np.full(n, 0xffffffff), dtype=np.uint32)
+    sk = np.ascontiguousarray(squash_kind if squash_kind is not None else np.zeros(n), dtype=np.uint8)
+    L = lib()
+    L.hs_b200_limex32_from_spec.restype = C.c_long
+    L.hs_b200_limex32_from_spec.argtypes = [C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_size_t]
+    cap = 1 << 20
+    out = C.create_string_buffer(cap)
+    sz = L.hs_b200_limex32_from_spec(n, rc.ctypes.data, int(init), int(init_ds), sc.ctypes.data, sm.ctypes.data,
+                                     sk.ctypes.data, ro.ctypes.data, rv.ctypes.data, eo.ctypes.data, ev.ctypes.data,
+                                     out, cap)
+    if sz < 0:
+        raise HsError(HS_COMPILER_ERROR, "limex32_from_spec")
+    return out.raw[:sz]
+
+
 def nfa_scan_corpus(nfa_bytes, corpus, cap=1 << 20):
     """hs_b200_nfa_scan_corpus: the engine over every block of a resident corpus.
     Returns (records MATCH_DTYPE ordered by (block, to, id), kernel ms)."""

@@ -2003,6 +2003,22 @@ hs_error_t hs_b200_nfa_scan_corpus(const void *nfa, size_t nfa_len, const hs_b20
         if (nfa_len < sizeof(NFA) + sizeof(Sheng)) {
             return HS_INVALID;
         }
+    } else if (hdr.type == NFA_LIMEX_32) {
+        if (nfa_len < sizeof(NFA) + sizeof(LimExNFA32)) {
+            return HS_INVALID;
+        }
+        LimExNFA32 lx;
+        memcpy(&lx, (const u8 *)nfa + sizeof(NFA), sizeof(lx));
+        if (lx.repeatCount) {
+            return HS_ARCH_ERROR; /* bounded repeats (repeat control blocks, tug / pos triggers) are not built */
+        }
+        const size_t body = nfa_len - sizeof(NFA);
+        if (lx.shiftCount > 8 || lx.exceptionCount > 32 || sizeof(LimExNFA32) + 4ull * lx.reachSize > body ||
+            (size_t)lx.exceptionOffset + (size_t)lx.exceptionCount * sizeof(NFAException32) > body ||
+            (size_t)lx.acceptOffset + (size_t)lx.acceptCount * sizeof(NFAAccept) > body ||
+            (size_t)lx.acceptEodOffset + (size_t)lx.acceptEodCount * sizeof(NFAAccept) > body) {
+            return HS_INVALID;
+        }
     } else {
         return HS_ARCH_ERROR; /* LimEx, McSheng, Gough, Castle, ...: not built */
     }

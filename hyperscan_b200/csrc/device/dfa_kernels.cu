@@ -64,6 +64,39 @@ __device__ u32 emitReportList(const DfaParams &p, u32 cursor, u32 off, u32 block
     return cursor;
 }
 
+/* LimEx report list: ReportID[] terminated by MO_INVALID_IDX (limexRunReports, limex_runtime.h:90-103) */
+__device__ HSB_NOINLINE u32 emitLimexReports(const DfaParams &p, u32 cursor, u32 listOff, u32 block, u64 to) {
+    const u8 *lx = p.nfa + sizeof(NFA);
+    for (u32 i = 0;; i++) {
+        const u32 id = g32(lx + listOff + 4 * i);
+        if (id == MO_INVALID_IDX) {
+            break;
+        }
+        cursor = emitDfaMatch(p, cursor, id, block, to);
+    }
+    return cursor;
+}
+
+/* accepts of the states in `found` through an NFAAccept table (PROCESS_ACCEPTS_IMPL_FN,
+ * limex_common_impl.h:116-163; the squash of PROCESS_ACCEPTS_FN is dead code there) */
+__device__ HSB_NOINLINE u32 emitLimexAccepts(const DfaParams &p, u32 cursor, u32 found, u32 mask, u32 tableOff,
+                                             u32 block, u64 to) {
+    const u8 *lx = p.nfa + sizeof(NFA);
+    while (found) {
+        const u32 bit = (u32)__ffs((int)found) - 1;
+        found &= found - 1;
+        const u32 idx = (u32)__popc(mask & ((1u << bit) - 1));
+        const u8 *a = lx + tableOff + idx * (u32)sizeof(NFAAccept);
+        const u32 reports = g32(a + offsetof(NFAAccept, reports));
+        if (__ldg(a + offsetof(NFAAccept, single_report))) {
+            cursor = emitDfaMatch(p, cursor, reports, block, to);
+        } else {
+            cursor = emitLimexReports(p, cursor, reports, block, to);
+        }
+    }
+    return cursor;
+}
+
 __device__ void padReserved(const DfaParams &p, u32 cursor) {
     for (; cursor & (DFA_SLOTS - 1); cursor++) {
         if (cursor < p.outCap) {
@@ -161,7 +194,8 @@ template <int CH> struct DfaTile {
     static constexpr u32 ROWS_PER_LOAD = 32 / PIECES;
 };
 
-enum { ENG_MCC8 = 0, ENG_MCC16 = 1, ENG_SHENG = 2 };
+enum { ENG_MCC8 = 0, ENG_MCC16 = 1, ENG_SHENG = 2, ENG_LIMEX32 = 3 };
+enum { LIMEX_TABLE_BYTES = 1024 + 512 }; /* reach mask per byte value, then 32 exceptions x 16 B */
 enum { SHENG_ROW = 128, SHENG_TABLE_BYTES = 256 * SHENG_ROW };
 
 struct DfaConsts {
@@ -190,7 +224,25 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     k.shermanOffset = 0;
     k.shermanLimit = 0xffffffffu;
     k.acceptLimit8 = 0;
-    if (ENGINE == ENG_SHENG) {
+    u32 lxShift[8], lxAmount[8], lxShiftCount = 0, lxExcMask = 0, lxAccept = 0, lxAcceptEod = 0;
+    if (ENGINE == ENG_LIMEX32) {
+        /* eng = struct LimExNFA32; a top at offset 0 switches `init` on (moNfaTop32) */
+        k.start = g32(eng + offsetof(LimExNFA32, init));
+        k.single = 0;
+        k.report = 0;
+        k.auxOffset = 0;
+        k.auxSize = 0;
+        k.stateMask = 0xffffffffu;
+        lxShiftCount = g32(eng + offsetof(LimExNFA32, shiftCount));
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            lxShift[i] = g32(eng + offsetof(LimExNFA32, shift) + 4 * i);
+            lxAmount[i] = __ldg(eng + offsetof(LimExNFA32, shiftAmount) + i);
+        }
+        lxExcMask = g32(eng + offsetof(LimExNFA32, exceptionMask));
+        lxAccept = g32(eng + offsetof(LimExNFA32, accept));
+        lxAcceptEod = g32(eng + offsetof(LimExNFA32, acceptAtEOD));
+    } else if (ENGINE == ENG_SHENG) {
         k.start = __ldg(eng + offsetof(Sheng, anchored));
         k.single = __ldg(eng + offsetof(Sheng, flags)) & SHENG_FLAG_SINGLE_REPORT;
         k.report = g32(eng + offsetof(Sheng, report));
@@ -212,7 +264,29 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
         k.stateMask = 0xffffffffu;
     }
     u32 tabArea;
-    if (ENGINE == ENG_SHENG) {
+    if (ENGINE == ENG_LIMEX32) {
+        /* reach mask by byte value (reach[reachMap[b]]), then the exception table as
+         * {squash, successors, reports, hasSquash} */
+        u32 *d = reinterpret_cast<u32 *>(smem);
+        const u8 *reach = eng + sizeof(LimExNFA32);
+        for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
+            d[i] = g32(reach + 4 * __ldg(eng + offsetof(LimExNFA32, reachMap) + i));
+        }
+        const u32 nexc = g32(eng + offsetof(LimExNFA32, exceptionCount));
+        const u8 *exc = eng + g32(eng + offsetof(LimExNFA32, exceptionOffset));
+        for (u32 i = threadIdx.x; i < 32; i += blockDim.x) {
+            uint4 e = make_uint4(0xffffffffu, 0, MO_INVALID_IDX, 0);
+            if (i < nexc) {
+                const u8 *x = exc + i * (u32)sizeof(NFAException32);
+                e.x = g32(x + offsetof(NFAException32, squash));
+                e.y = g32(x + offsetof(NFAException32, successors));
+                e.z = g32(x + offsetof(NFAException32, reports));
+                e.w = __ldg(x + offsetof(NFAException32, hasSquash));
+            }
+            reinterpret_cast<uint4 *>(smem + 1024)[i] = e;
+        }
+        tabArea = LIMEX_TABLE_BYTES;
+    } else if (ENGINE == ENG_SHENG) {
         /* [byte c][copy r][16 successor bytes, the one of state s at position (s + 4c) & 15] */
         for (u32 i = threadIdx.x; i < SHENG_TABLE_BYTES; i += blockDim.x) {
             const u32 c = i >> 7;
@@ -246,9 +320,40 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     const u16 *succ16 = reinterpret_cast<const u16 *>(SMEM_TABLE ? smem + 256 : succG);
     const u32 copyOff = (lane & 7) * 16; /* Sheng: this lane's copy of a row */
 
-    /* one input byte: byte j of data word w.  Returns true when the state entered accepts. */
-    auto step = [&](const u32 w, const u32 j, u32 &s) -> bool {
-        if (ENGINE == ENG_MCC8) {
+    u32 cursor = 0; /* this lane's next record slot (emitDfaMatch) */
+    /* one input byte: byte j of data word w, at block offset pos.  DFAs: returns true when the
+     * state entered accepts.  LimEx (LOOP_NOACCEL_FN, limex_runtime_impl.h:209-243): the states
+     * that are on BEFORE the byte run their exceptions -- reports at offset pos, except at the
+     * first byte of the scan (NO_OUTPUT | FIRST_BYTE) -- then succ & reach[byte]. */
+    auto step = [&](const u32 w, const u32 j, u32 &s, const u32 pos, const u32 blk) -> bool {
+        if (ENGINE == ENG_LIMEX32) {
+            u32 succ = (s & lxShift[0]) << lxAmount[0];
+#pragma unroll
+            for (int i = 1; i < 8; i++) {
+                if ((u32)i < lxShiftCount) {
+                    succ |= (s & lxShift[i]) << lxAmount[i];
+                }
+            }
+            u32 est = s & lxExcMask;
+            if (est) { /* processExceptional32 (limex_exceptional.h:190-330), cache aside */
+                u32 local = 0;
+                do {
+                    const u32 bit = (u32)__ffs((int)est) - 1;
+                    est &= est - 1;
+                    const uint4 e = reinterpret_cast<const uint4 *>(smem + 1024)[__popc(lxExcMask & ((1u << bit) - 1))];
+                    if (e.z != MO_INVALID_IDX && pos != 0) {
+                        cursor = emitLimexReports(p, cursor, e.z, blk, pos);
+                    }
+                    local |= e.y;
+                    if (e.w == LIMEX_SQUASH_CYCLIC || e.w == LIMEX_SQUASH_REPORT) {
+                        succ &= e.x;
+                    }
+                } while (est);
+                succ |= local;
+            }
+            s = succ & reinterpret_cast<const u32 *>(smem)[__byte_perm(w, 0, 0x4440 + j)];
+            return false;
+        } else if (ENGINE == ENG_MCC8) {
             s = smem[__byte_perm(w, s, 0x5540 + j)]; /* (s << 8) | byte */
             return s >= k.acceptLimit8;
         } else if (ENGINE == ENG_SHENG) {
@@ -271,7 +376,6 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     auto acceptWhat = [&](const u32 s) -> u32 {
         return k.single ? k.report : k.auxOffset + k.auxSize * (s & k.stateMask);
     };
-    u32 cursor = 0; /* this lane's next record slot (emitDfaMatch) */
     auto dead = [&](const u32 s) -> bool { return ENGINE == ENG_SHENG ? (s & SHENG_STATE_DEAD) != 0 : s == 0; };
 
     /* a warp takes 32 * ILP consecutive blocks at a time; lane t owns blocks t, t + 32, ...
@@ -359,7 +463,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
                     for (u32 j = 0; j < 16; j++) {
 #pragma unroll
                         for (int u = 0; u < ILP; u++) {
-                            if (step(w[u][j >> 2], j & 3, s[u])) {
+                            if (step(w[u][j >> 2], j & 3, s[u], done + c * 16 + j, b[u])) {
                                 cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + c * 16 + j + 1);
                             }
                         }
@@ -381,7 +485,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
                     const u32 w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
                     for (u32 j = 0; j < 16; j++) {
-                        if (step(w[j >> 2], j & 3, s[u])) {
+                        if (step(w[j >> 2], j & 3, s[u], done + cc * 16 + j, b[u])) {
                             cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + cc * 16 + j + 1);
                         }
                     }
@@ -393,7 +497,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
                     const u32 m = n[u] - cc * 16;
 #pragma unroll 1
                     for (u32 j = 0; j < m; j++) {
-                        if (step(w[j >> 2] >> (8 * (j & 3)), 0, s[u])) {
+                        if (step(w[j >> 2] >> (8 * (j & 3)), 0, s[u], done + cc * 16 + j, b[u])) {
                             cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + cc * 16 + j + 1);
                         }
                     }
@@ -405,7 +509,20 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
         /* nfaExec*_B: reports of the final state that fire at end of data */
 #pragma unroll
         for (int u = 0; u < ILP; u++) {
-            if (b[u] < p.nblocks) {
+            if (ENGINE == ENG_LIMEX32) {
+                if (b[u] < p.nblocks) {
+                    /* STREAM_FN's closing accept check (only if the block had bytes to stream),
+                     * then nfaExecLimEx32_testEOD (limex_common_impl.h:192-218) */
+                    if (len[u] && (s[u] & lxAccept)) {
+                        cursor = emitLimexAccepts(p, cursor, s[u] & lxAccept, lxAccept,
+                                                  g32(eng + offsetof(LimExNFA32, acceptOffset)), b[u], len[u]);
+                    }
+                    if (s[u] & lxAcceptEod) {
+                        cursor = emitLimexAccepts(p, cursor, s[u] & lxAcceptEod, lxAcceptEod,
+                                                  g32(eng + offsetof(LimExNFA32, acceptEodOffset)), b[u], len[u]);
+                    }
+                }
+            } else if (b[u] < p.nblocks) {
                 const u32 eodOff = ENGINE == ENG_SHENG ? (u32)offsetof(SstateAux, accept_eod)
                                                        : (u32)offsetof(MStateAux, accept_eod);
                 const u32 eod = g32(p.nfa + k.auxOffset + k.auxSize * (s[u] & k.stateMask) + eodOff);
@@ -448,6 +565,9 @@ cudaError_t launchDfa(const DfaParams &p, int smCount, int maxSmem, cudaStream_t
     const size_t tilesMax = 32 * 2 * DfaTile<64>::WARP_BYTES;
     if (p.kind == NFA_SHENG) {
         return launchStaged<ENG_SHENG, 1>(p, smCount, SHENG_TABLE_BYTES, stream);
+    }
+    if (p.kind == NFA_LIMEX_32) {
+        return launchStaged<ENG_LIMEX32, 1>(p, smCount, LIMEX_TABLE_BYTES, stream);
     }
     if (p.kind == NFA_MCCLELLAN_8) {
         return launchStaged<ENG_MCC8, 1>(p, smCount, (size_t)p.states * 256, stream); /* <= 64 KiB */

@@ -21,6 +21,7 @@
 #include "api_internal.h"
 #include "rose_build.h"
 #include "dfa_build.h"
+#include "limex_build.h"
 
 using namespace hsb;
 
@@ -1242,6 +1243,67 @@ extern "C" long hs_b200_dfa_from_table(unsigned nstates, const unsigned short *n
         d.startAnchored = (u16)start_anchored;
         d.startFloating = (u16)start_floating;
         return emitInto(d, kind, sherman, out, cap);
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+/* ---- LimEx-32 emitters (include/hs_b200.h) ------------------------------------------- */
+
+static long copyOut(const std::vector<u8> &b, void *out, size_t cap) {
+    if (b.size() > cap || !out) {
+        return -1;
+    }
+    memcpy(out, b.data(), b.size());
+    return (long)b.size();
+}
+
+extern "C" long hs_b200_limex32_from_literals(const char *const *lits, const size_t *lens, const unsigned *caseless,
+                                              const unsigned *reports, unsigned n, void *out, size_t cap) {
+    if (!lits || !lens || !reports || !n) {
+        return -1;
+    }
+    try {
+        std::vector<hsb::DfaLiteral> v(n);
+        for (unsigned i = 0; i < n; i++) {
+            v[i].s.assign(lits[i], lens[i]);
+            v[i].caseless = caseless && caseless[i];
+            v[i].report = reports[i];
+        }
+        return copyOut(hsb::emitLimEx32(hsb::nfaFromLiterals(v)), out, cap);
+    } catch (const std::exception &) {
+        return -1;
+    }
+}
+
+extern "C" long hs_b200_limex32_from_spec(unsigned nstates, const unsigned *reach256, unsigned init, unsigned init_ds,
+                                          const unsigned *succ, const unsigned *squash_mask,
+                                          const unsigned char *squash_kind, const unsigned *report_off,
+                                          const unsigned *reports, const unsigned *eod_off,
+                                          const unsigned *eod_reports, void *out, size_t cap) {
+    if (!reach256 || !succ || !report_off || !eod_off || nstates == 0 || nstates > 32) {
+        return -1;
+    }
+    try {
+        hsb::RawNfa32 n;
+        n.nstates = nstates;
+        memcpy(n.reach, reach256, sizeof(n.reach));
+        n.init = init;
+        n.initDS = init_ds;
+        n.succ.assign(succ, succ + nstates);
+        n.squashMask.assign(nstates, 0xffffffffu);
+        n.squashKind.assign(nstates, 0);
+        n.reports.resize(nstates);
+        n.reportsEod.resize(nstates);
+        for (unsigned i = 0; i < nstates; i++) {
+            if (squash_mask && squash_kind) {
+                n.squashMask[i] = squash_mask[i];
+                n.squashKind[i] = squash_kind[i];
+            }
+            n.reports[i].assign(reports + report_off[i], reports + report_off[i + 1]);
+            n.reportsEod[i].assign(eod_reports + eod_off[i], eod_reports + eod_off[i + 1]);
+        }
+        return copyOut(hsb::emitLimEx32(n), out, cap);
     } catch (const std::exception &) {
         return -1;
     }

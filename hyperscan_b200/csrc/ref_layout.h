@@ -356,7 +356,7 @@ struct InstrSetExhaust { u8 code; u32 ekey; };
 /* ---- NFA engines (DFA subset): src/nfa/nfa_internal.h:53-126,
  *      src/nfa/mcclellan_internal.h:36-106 -------------------------------- */
 
-enum { NFA_MCCLELLAN_8 = 6, NFA_MCCLELLAN_16 = 7, NFA_SHENG = 17 };
+enum { NFA_LIMEX_32 = 0, NFA_MCCLELLAN_8 = 6, NFA_MCCLELLAN_16 = 7, NFA_SHENG = 17 };
 
 struct alignas(64) NFA {
     u32 flags;
@@ -403,6 +403,42 @@ struct McClellan {
     u32 haig_offset;
     u32 wide_offset;
 };
+
+/* ---- LimEx NFA, 32-state model: src/nfa/limex_internal.h:102-203 (CREATE_NFA_LIMEX(32)).
+ *      The reach table (u32 per reach class) follows the struct; the other tables sit at
+ *      the offsets it names, all relative to the start of the LimExNFA32. ------------- */
+struct NFAException32 {
+    u32 squash;       /* mask of states to leave on */
+    u32 successors;   /* mask of states to switch on */
+    u32 reports;      /* offset of a MO_INVALID_IDX-terminated report list, or MO_INVALID_IDX */
+    u32 repeatOffset; /* offset of NFARepeatInfo, or MO_INVALID_IDX */
+    u8 hasSquash;     /* enum LimExSquash */
+    u8 trigger;       /* enum LimExTrigger */
+};
+struct NFAAccept {
+    u8 single_report; /* 1: `reports` is the report id itself */
+    u32 reports;      /* else offset of a MO_INVALID_IDX-terminated list */
+    u32 squash;       /* offset of a squash mask, or MO_INVALID_IDX */
+};
+struct LimExNFA32 {
+    u8 reachMap[256];
+    u32 reachSize, accelCount, accelTableOffset, accelAuxCount, accelAuxOffset;
+    u32 acceptCount, acceptOffset, acceptEodCount, acceptEodOffset;
+    u32 exceptionCount, exceptionOffset, repeatCount, repeatOffset;
+    u32 squashOffset, squashCount, topCount, topOffset, stateSize, flags;
+    u32 init, initDS, accept, acceptAtEOD, accel, accelPermute, accelCompare, accel_and_friends;
+    u32 compressMask, exceptionMask, repeatCyclicMask, zombieMask;
+    u32 shift[8];
+    u32 shiftCount;
+    u8 shiftAmount[8];
+    alignas(64) u8 exceptionShufMask[64];
+    alignas(64) u8 exceptionBitMask[64];
+    alignas(64) u8 exceptionAndMask[64];
+};
+static const u32 MO_INVALID_IDX = 0xffffffffu;            /* src/ue2common.h */
+static const u32 LIMEX_FLAG_CANNOT_DIE = 4;               /* limex_internal.h:89 */
+static const u8 LIMEX_SQUASH_NONE = 0, LIMEX_SQUASH_CYCLIC = 1, LIMEX_SQUASH_TUG = 2, LIMEX_SQUASH_REPORT = 3;
+static const u8 LIMEX_TRIGGER_NONE = 0;
 
 /* ---- small-write engine header: src/smallwrite/smallwrite_internal.h:35-39 (the
  *      struct NFA of a McClellan / Sheng DFA follows at the next cache line) ------ */

@@ -460,6 +460,22 @@ long hs_b200_dfa_from_table(unsigned nstates, const unsigned short *next, unsign
                             const unsigned *eod_off, const unsigned *eod_reports, int kind, int sherman,
                             void *out, size_t cap);
 
+/* LimEx NFA, 32-state model (src/nfa/limex_internal.h:102-203), emitted in the reference's
+ * layout from a literal set (position automaton, <= 31 literal bytes in total) or from a
+ * finished NFA: reach256[b] = states that may be on after byte b; succ[i] = successor set of
+ * state i; init / init_ds = states a top switches on at offset 0 / later; squash_kind[i]
+ * (0 none, 1 cyclic, 3 report: src/nfa/limex_internal.h:98-103) with squash_mask[i];
+ * report_off / eod_off: nstates + 1 offsets into reports / eod_reports.  The engine runs
+ * on hs_b200_nfa_scan_corpus like the DFAs (block-mode semantics of an outfix: one top at
+ * offset 0, nfaExecLimEx32_Q over the block, then _testEOD).  Size written, or -1. */
+long hs_b200_limex32_from_literals(const char *const *lits, const size_t *lens, const unsigned *caseless,
+                                   const unsigned *reports, unsigned n, void *out, size_t cap);
+long hs_b200_limex32_from_spec(unsigned nstates, const unsigned *reach256, unsigned init, unsigned init_ds,
+                               const unsigned *succ, const unsigned *squash_mask,
+                               const unsigned char *squash_kind, const unsigned *report_off,
+                               const unsigned *reports, const unsigned *eod_off, const unsigned *eod_reports,
+                               void *out, size_t cap);
+
 /* Test hook: pure-literal block database whose literal programs are raw
  * instruction bytes (layouts: src/rose/rose_program.h:214-724).  `area` is
  * placed at bytecode offset hs_b200_test_program_base(); prog_off[i] = offset of

@@ -399,6 +399,8 @@ static int nfa_cb(u64a start, u64a end, ReportID id, void *ctx) {
  * 937,963; src/nfa/sheng.c:706) over every block, offset 0 each, callbacks collected
  * as (report, block, end).  `nfa` must be 64-byte aligned.  Returns the number of
  * callbacks (may exceed cap) or -1 for an engine type not handled here. */
+int ref_limex32_block(const struct NFA *n, const u8 *buf, size_t len, NfaCallback cb, void *ctx); /* ref_limex.c */
+
 API long ref_nfa_exec_blocks(const void *nfa, const char *data, const unsigned long long *offsets,
                              const unsigned *lengths, size_t nblocks, struct rec16 *out,
                              size_t cap) {
@@ -418,7 +420,9 @@ API long ref_nfa_exec_blocks(const void *nfa, const char *data, const unsigned l
             nfaExecSheng_B(n, 0, buf, lengths[b], nfa_cb, &c);
             break;
         default:
-            return -1;
+            if (!ref_limex32_block(n, buf, lengths[b], nfa_cb, &c)) {
+                return -1;
+            }
         }
     }
     return (long)c.n;
@@ -431,6 +435,7 @@ API long ref_nfa_exec_blocks(const void *nfa, const char *data, const unsigned l
     printf("  \"%s.%s\": %zu,\n", #s, #f, offsetof(struct s, f))
 
 void ref_layout_dump_sheng(void); /* ref_sheng_layout.c: sheng_internal.h redefines report_list */
+void ref_layout_dump_limex(void); /* ref_limex.c */
 
 API void ref_layout_dump(void) {
     printf("{\n");
@@ -567,6 +572,7 @@ API void ref_layout_dump(void) {
     OFF(mstate_aux, top); OFF(mstate_aux, accel_offset);
 
 ref_layout_dump_sheng();
+    ref_layout_dump_limex();
 
     /* rose program instruction sizes (8-byte rounded stride is what matters) */
 #define ISZ(n) printf("  \"sizeof(ROSE_STRUCT_%s)\": %zu,\n", #n, sizeof(struct ROSE_STRUCT_##n))

@@ -1,0 +1,83 @@
+/* ref_limex.c -- the reference's LimEx-32 engine over blocks, the way Rose runs an outfix
+ * in block mode (src/rose/block.c:218-262, src/rose/match.h:initQueue / pushQueue...):
+ * a queue {MQE_START@0, MQE_TOP@0, MQE_END@len} through nfaExecLimEx32_Q, then
+ * nfaExecLimEx32_testEOD; plus sizeof/offsetof of its structures for ref_layout_dump().
+ * TEST INFRASTRUCTURE ONLY (part of oracle/_ref). */
+#include <stddef.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ue2common.h"
+#include "nfa/nfa_internal.h"
+#include "nfa/nfa_api.h"
+#include "nfa/nfa_api_queue.h"
+#include "nfa/limex.h"
+#include "nfa/limex_internal.h"
+
+struct limex_collect {
+    int (*cb)(u64a start, u64a end, ReportID id, void *ctx);
+    void *ctx;
+};
+
+/* one block: returns 0 if the engine type is not LimEx-32 */
+int ref_limex32_block(const struct NFA *n, const u8 *buf, size_t len, NfaCallback cb, void *ctx) {
+    if (n->type != LIMEX_NFA_32) {
+        return 0;
+    }
+    struct mq *q = (struct mq *)calloc(1, sizeof(struct mq));
+    char *state = (char *)calloc(1, n->scratchStateSize + 64);
+    char *sstate = (char *)calloc(1, n->streamStateSize + 64);
+    q->nfa = n;
+    q->cur = q->end = 0;
+    q->state = state;
+    q->streamState = sstate;
+    q->offset = 0;
+    q->buffer = buf;
+    q->length = len;
+    q->history = NULL;
+    q->hlength = 0;
+    q->scratch = NULL;
+    q->report_current = 0;
+    q->cb = cb;
+    q->context = ctx;
+    nfaExecLimEx32_queueInitState(n, q);
+    pushQueue(q, MQE_START, 0);
+    pushQueue(q, MQE_TOP, 0);
+    pushQueue(q, MQE_END, (s64a)len);
+    nfaExecLimEx32_Q(n, q, (s64a)len);
+    nfaExecLimEx32_testEOD(n, q->state, q->streamState, len, cb, ctx);
+    free(sstate);
+    free(state);
+    free(q);
+    return 1;
+}
+
+#define SZ(s) printf("  \"sizeof(%s)\": %zu,\n", #s, sizeof(struct s))
+#define OFF(s, f) printf("  \"%s.%s\": %zu,\n", #s, #f, offsetof(struct s, f))
+
+void ref_layout_dump_limex(void) {
+    SZ(LimExNFA32);
+    OFF(LimExNFA32, reachMap); OFF(LimExNFA32, reachSize); OFF(LimExNFA32, accelCount);
+    OFF(LimExNFA32, accelTableOffset); OFF(LimExNFA32, accelAuxCount); OFF(LimExNFA32, accelAuxOffset);
+    OFF(LimExNFA32, acceptCount); OFF(LimExNFA32, acceptOffset); OFF(LimExNFA32, acceptEodCount);
+    OFF(LimExNFA32, acceptEodOffset); OFF(LimExNFA32, exceptionCount); OFF(LimExNFA32, exceptionOffset);
+    OFF(LimExNFA32, repeatCount); OFF(LimExNFA32, repeatOffset); OFF(LimExNFA32, squashOffset);
+    OFF(LimExNFA32, squashCount); OFF(LimExNFA32, topCount); OFF(LimExNFA32, topOffset);
+    OFF(LimExNFA32, stateSize); OFF(LimExNFA32, flags); OFF(LimExNFA32, init); OFF(LimExNFA32, initDS);
+    OFF(LimExNFA32, accept); OFF(LimExNFA32, acceptAtEOD); OFF(LimExNFA32, accel);
+    OFF(LimExNFA32, accelPermute); OFF(LimExNFA32, accelCompare); OFF(LimExNFA32, accel_and_friends);
+    OFF(LimExNFA32, compressMask); OFF(LimExNFA32, exceptionMask); OFF(LimExNFA32, repeatCyclicMask);
+    OFF(LimExNFA32, zombieMask); OFF(LimExNFA32, shift); OFF(LimExNFA32, shiftCount);
+    OFF(LimExNFA32, shiftAmount); OFF(LimExNFA32, exceptionShufMask); OFF(LimExNFA32, exceptionBitMask);
+    OFF(LimExNFA32, exceptionAndMask);
+    SZ(NFAException32);
+    OFF(NFAException32, squash); OFF(NFAException32, successors); OFF(NFAException32, reports);
+    OFF(NFAException32, repeatOffset); OFF(NFAException32, hasSquash); OFF(NFAException32, trigger);
+    SZ(NFAAccept);
+    OFF(NFAAccept, single_report); OFF(NFAAccept, reports); OFF(NFAAccept, squash);
+    printf("  \"LIMEX_NFA_32\": %d,\n", (int)LIMEX_NFA_32);
+    printf("  \"LIMEX_FLAG_CANNOT_DIE\": %d,\n", (int)LIMEX_FLAG_CANNOT_DIE);
+    printf("  \"LIMEX_SQUASH_CYCLIC\": %d,\n", (int)LIMEX_SQUASH_CYCLIC);
+    printf("  \"LIMEX_SQUASH_REPORT\": %d,\n", (int)LIMEX_SQUASH_REPORT);
+}

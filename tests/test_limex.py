@@ -1,0 +1,143 @@
+"""LimEx NFA, 32-state model (SURVEY.md section 8a rows a20 LimEx, a21 struct NFA / mq):
+engines emitted by the host builder in the reference's byte layout run on the UNMODIFIED
+reference engine -- the way Rose runs an outfix in block mode: a queue {START@0, TOP@0,
+END@len} through nfaExecLimEx32_Q, then nfaExecLimEx32_testEOD (oracle/ref/ref_limex.c) --
+which pins the emitter and the Python restatement of the runtime (oracle/limex.py); on the
+GPU box the device kernel must fire the same (report, block, offset) multiset."""
+import numpy as np
+import pytest
+
+from hyperscan_b200 import synth
+import oracle.brute as brute
+import oracle.limex as model
+
+
+def _triples(recs):
+    return sorted((int(r["id"]), int(r["block"]), int(r["to"])) for r in recs)
+
+
+LIT_SETS = [([b"abc", b"bcd", b"xyz", b"ab"], [0, 0, 1, 0]), ([b"a"], [0]), ([b"aaaa", b"aa"], [0, 0]),
+            ([b"abcdefghijklmnopqrstuvwxyzABCDE"], [1]), ([b"ab", b"cd", b"ef", b"gh", b"ab", b"b", b"hgfedcba"], [0, 1] * 3 + [0])]
+LENS = [0, 1, 2, 3, 4, 15, 16, 17, 31, 32, 33, 100, 127, 128, 129, 1000, 1024, 1025, 3000]
+
+
+def _lit_case(i):
+    lits, cl = LIT_SETS[i]
+    ids = [100 + (k % 3) for k in range(len(lits))]                  # shared report ids
+    data, off, ln = synth.ragged_corpus(LENS, lits, seed=40 + i, plant_per_kb=40, alphabet=b"abcdefghxyzXYZAB")
+    return lits, cl, ids, data, off, ln
+
+
+@pytest.mark.parametrize("i", range(len(LIT_SETS)))
+def test_literal_nfas_run_on_the_reference(hs, ref, i):
+    lits, cl, ids, data, off, ln = _lit_case(i)
+    eng = hs.limex32_from_literals(lits, cl, ids)
+    assert eng[8] == 0                                                # NFA.type = LIMEX_NFA_32
+    got = _triples(ref.nfa_exec_blocks(eng, data, off, ln))
+    want = brute.scan_blocks(lits, cl, ids, data, off, ln)
+    # one callback per accepting STATE: two literals with one report id ending together fire it twice
+    assert sorted(set(got)) == sorted({(int(r["id"]), int(r["block"]), int(r["to"])) for r in want})
+    assert got == sorted(model.walk_blocks(eng, data, off, ln))
+    assert len(got) > 20
+
+
+def _random_nfa(seed):
+    """reach, init, succ, reports, eod reports, squash: anything goes -- the reference runs any
+    well-formed LimEx structure, so the emitter's choice of shifts / exceptions is exercised too"""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 33))
+    full = (1 << n) - 1
+    classes = rng.integers(0, 5, size=256)
+    masks = [int(rng.integers(0, 1 << 32)) & full for _ in range(5)]
+    masks[0] |= 1                                                     # keep the automaton alive on class 0
+    reach = np.array([masks[c] for c in classes], dtype=np.uint32)
+    succ = np.zeros(n, dtype=np.uint32)
+    for s in range(n):
+        m = 0
+        if rng.random() < 0.8 and s + 1 < n:
+            m |= 1 << (s + 1)
+        for _ in range(int(rng.integers(0, 4))):
+            m |= 1 << int(rng.integers(0, n))
+        if rng.random() < 0.3:
+            m |= 1 << s
+        succ[s] = m
+    succ[0] |= 1
+    reports = [sorted(set(rng.integers(0, 6, size=int(rng.integers(1, 3))).tolist())) if rng.random() < 0.25 else []
+               for _ in range(n)]
+    eod = [[int(rng.integers(50, 54))] if rng.random() < 0.2 else [] for _ in range(n)]
+    kind = np.array([int(rng.choice([0, 0, 0, 1, 3])) for _ in range(n)], dtype=np.uint8)
+    sqm = np.array([int(rng.integers(0, 1 << 32)) & full for _ in range(n)], dtype=np.uint32)
+    init = 1 | (int(rng.integers(0, 1 << 32)) & full & 0x7)
+    return reach, init, succ, reports, eod, sqm, kind
+
+
+def _random_corpus(seed):
+    rng = np.random.default_rng(seed)
+    data, off, ln = synth.ragged_corpus(LENS[:16], None, seed=seed, plant_per_kb=0)
+    return rng.integers(0, 256, size=data.size, dtype=np.uint8), off, ln
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_nfas_reference_equals_restatement(hs, ref, seed):
+    reach, init, succ, reports, eod, sqm, kind = _random_nfa(seed)
+    eng = hs.limex32_from_spec(reach, init, init, succ, reports, eod, sqm, kind)
+    data, off, ln = _random_corpus(100 + seed)
+    got = _triples(ref.nfa_exec_blocks(eng, data, off, ln))
+    assert got == sorted(model.walk_blocks(eng, data, off, ln))
+
+
+def test_builder_limits(hs):
+    with pytest.raises(hs.HsError):
+        hs.limex32_from_literals([b"a" * 32], [0], [1])              # 33 states
+    assert hs.limex32_from_literals([b"a" * 31], [0], [1])[8] == 0
+
+
+# ---- device --------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(len(LIT_SETS)))
+def test_device_limex_equals_reference_literals(hs, ref, i):
+    lits, cl, ids, data, off, ln = _lit_case(i)
+    eng = hs.limex32_from_literals(lits, cl, ids)
+    corpus = hs.Corpus.upload(data, off, ln)
+    got, ms = hs.nfa_scan_corpus(eng, corpus)
+    assert _triples(got) == _triples(ref.nfa_exec_blocks(eng, data, off, ln))
+    corpus.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(24))
+def test_device_limex_equals_reference_random(hs, ref, seed):
+    reach, init, succ, reports, eod, sqm, kind = _random_nfa(seed)
+    eng = hs.limex32_from_spec(reach, init, init, succ, reports, eod, sqm, kind)
+    data, off, ln = _random_corpus(200 + seed)
+    corpus = hs.Corpus.upload(data, off, ln)
+    got, ms = hs.nfa_scan_corpus(eng, corpus, cap=64)                 # forces the grow-and-retry path
+    want = ref.nfa_exec_blocks(eng, data, off, ln)
+    assert _triples(got) == _triples(want)
+    corpus.free()
+
+
+@pytest.mark.gpu
+def test_device_limex_uniform_blocks(hs, ref):
+    lits = [b"needle", b"hay", b"stack", b"ne"]
+    eng = hs.limex32_from_literals(lits, [0, 1, 0, 0], [1, 2, 3, 4])
+    data, off, ln, _ = synth.block_corpus(2048, 1024, lits, plant_per_kb=2.0, seed=12)
+    corpus = hs.Corpus.upload(data, off, ln)
+    got, ms = hs.nfa_scan_corpus(eng, corpus)
+    want = ref.nfa_exec_blocks(eng, data, off, ln)
+    assert _triples(got) == _triples(want) and len(want) > 1000
+    corpus.free()
+
+
+@pytest.mark.gpu
+def test_device_refuses_bounded_repeats(hs):
+    import struct
+    eng = bytearray(hs.limex32_from_literals([b"ab"], [0], [1]))
+    struct.pack_into("<I", eng, 64 + 300, 1)                          # LimExNFA32.repeatCount
+    data, off, ln = synth.ragged_corpus([64], None, seed=1, plant_per_kb=0)
+    corpus = hs.Corpus.upload(data, off, ln)
+    with pytest.raises(hs.HsError) as e:
+        hs.nfa_scan_corpus(bytes(eng), corpus)
+    assert e.value.code == hs.HS_ARCH_ERROR
+    corpus.free()
