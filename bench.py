@@ -453,15 +453,19 @@ def secondary_single_gpu(args, capi, torch, base, peak):
     sset.close()
     sc.free()
 
-    # DFA engines: literal-set automata in the reference layout, one block per thread
-    kinds = {"mcclellan16_2000lits": (2, 2000, 4, 8), "mcclellan8_30lits": (1, 30, 2, 4), "sheng_4lits": (3, 4, 1, 3)}
+    # DFA / NFA engines: literal-set automata in the reference layout, one block per thread
+    kinds = {"mcclellan16_2000lits": (2, 2000, 4, 8), "mcclellan8_30lits": (1, 30, 2, 4), "sheng_4lits": (3, 4, 1, 3),
+             "limex32_6lits": (-1, 6, 4, 5)}
     ndfa = nb
     off = np.arange(ndfa, dtype=np.uint64) * np.uint64(bl)
     ln = np.full(ndfa, bl, dtype=np.uint32)
     for name, (kind, nl, lo, hi) in kinds.items():
         alpha = b"abcdefghijklmnopqrstuvwxyz" if nl > 100 else (b"abcdefgh" if nl > 4 else b"abc")
         lits, flags, ids = synth.literal_set(nl, min_len=lo, max_len=hi, seed=nl, caseless_frac=0.0, alphabet=alpha)
-        eng = capi.dfa_from_literals(lits, None, ids, kind=kind)
+        if kind < 0:      # LimEx-32 position automaton of the literals (<= 31 literal bytes)
+            eng = capi.limex32_from_literals(lits, None, ids)
+        else:
+            eng = capi.dfa_from_literals(lits, None, ids, kind=kind)
         data = replant(base, ndfa, bl, lits, 0.01, 97)
         corpus = capi.Corpus.upload(data, off, ln)
         ms = []
@@ -480,7 +484,8 @@ def secondary_single_gpu(args, capi, torch, base, peak):
         sec["dfa_" + name] = {"engine_bytes": len(eng), "blocks": ndfa, "block_len": bl, "kernel_ms": kms,
                               "roofline_gbs": ach, "roofline_frac": ach / peak, "records": int(got.size),
                               "verified_blocks": vb, "bit_exact_vs_reference_engine": exact,
-                              "api": "hs_b200_nfa_scan_corpus (nfaExecMcClellan16_B / 8_B / Sheng_B semantics)"}
+                              "api": "hs_b200_nfa_scan_corpus (nfaExecMcClellan16_B / 8_B / Sheng_B / LimEx32_Q + testEOD "
+                                     "semantics)"}
         corpus.free()
     return sec
 
