@@ -195,7 +195,7 @@ template <int CH> struct DfaTile {
 };
 
 enum { ENG_MCC8 = 0, ENG_MCC16 = 1, ENG_SHENG = 2, ENG_LIMEX32 = 3 };
-enum { LIMEX_TABLE_BYTES = 1024 + 512 }; /* reach mask per byte value, then 32 exceptions x 16 B */
+enum { LIMEX_TABLE_BYTES = 1024 + 512 }; /* reach mask per byte value, then 32 states x 16 B */
 enum { SHENG_ROW = 128, SHENG_TABLE_BYTES = 256 * SHENG_ROW };
 
 struct DfaConsts {
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     k.shermanOffset = 0;
     k.shermanLimit = 0xffffffffu;
     k.acceptLimit8 = 0;
-    u32 lxShift[8], lxAmount[8], lxShiftCount = 0, lxExcMask = 0, lxAccept = 0, lxAcceptEod = 0;
+    u32 lxAccept = 0, lxAcceptEod = 0;
     if (ENGINE == ENG_LIMEX32) {
         /* eng = struct LimExNFA32; a top at offset 0 switches `init` on (moNfaTop32) */
         k.start = g32(eng + offsetof(LimExNFA32, init));
@@ -233,13 +233,6 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
         k.auxOffset = 0;
         k.auxSize = 0;
         k.stateMask = 0xffffffffu;
-        lxShiftCount = g32(eng + offsetof(LimExNFA32, shiftCount));
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            lxShift[i] = g32(eng + offsetof(LimExNFA32, shift) + 4 * i);
-            lxAmount[i] = __ldg(eng + offsetof(LimExNFA32, shiftAmount) + i);
-        }
-        lxExcMask = g32(eng + offsetof(LimExNFA32, exceptionMask));
         lxAccept = g32(eng + offsetof(LimExNFA32, accept));
         lxAcceptEod = g32(eng + offsetof(LimExNFA32, acceptAtEOD));
     } else if (ENGINE == ENG_SHENG) {
@@ -265,23 +258,34 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     }
     u32 tabArea;
     if (ENGINE == ENG_LIMEX32) {
-        /* reach mask by byte value (reach[reachMap[b]]), then the exception table as
-         * {squash, successors, reports, hasSquash} */
+        /* reach mask by byte value (reach[reachMap[b]]), then ONE row per state i:
+         *   x = its limited successors: OR over the shifts k with bit i of shift[k] of 1 << (i + shiftAmount[k])
+         *   y = its exception's successors, z = its exception's report list, w = its squash mask
+         *       (all ones unless the exception squashes: LIMEX_SQUASH_CYCLIC / _REPORT)
+         * so a byte costs work in proportion to the states that are ON, not eight shift-and-mask rounds */
         u32 *d = reinterpret_cast<u32 *>(smem);
         const u8 *reach = eng + sizeof(LimExNFA32);
         for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
             d[i] = g32(reach + 4 * __ldg(eng + offsetof(LimExNFA32, reachMap) + i));
         }
-        const u32 nexc = g32(eng + offsetof(LimExNFA32, exceptionCount));
+        const u32 excMask = g32(eng + offsetof(LimExNFA32, exceptionMask));
+        const u32 nshift = g32(eng + offsetof(LimExNFA32, shiftCount));
         const u8 *exc = eng + g32(eng + offsetof(LimExNFA32, exceptionOffset));
         for (u32 i = threadIdx.x; i < 32; i += blockDim.x) {
-            uint4 e = make_uint4(0xffffffffu, 0, MO_INVALID_IDX, 0);
-            if (i < nexc) {
-                const u8 *x = exc + i * (u32)sizeof(NFAException32);
-                e.x = g32(x + offsetof(NFAException32, squash));
+            uint4 e = make_uint4(0, 0, MO_INVALID_IDX, 0xffffffffu);
+            for (u32 q = 0; q < nshift && q < 8; q++) {
+                if ((g32(eng + offsetof(LimExNFA32, shift) + 4 * q) >> i) & 1) {
+                    e.x |= (1u << i) << __ldg(eng + offsetof(LimExNFA32, shiftAmount) + q); /* LSHIFT_STATE: bits past 31 fall off */
+                }
+            }
+            if ((excMask >> i) & 1) {
+                const u8 *x = exc + (u32)__popc(excMask & ((1u << i) - 1)) * (u32)sizeof(NFAException32);
+                const u32 kind = __ldg(x + offsetof(NFAException32, hasSquash));
                 e.y = g32(x + offsetof(NFAException32, successors));
                 e.z = g32(x + offsetof(NFAException32, reports));
-                e.w = __ldg(x + offsetof(NFAException32, hasSquash));
+                if (kind == LIMEX_SQUASH_CYCLIC || kind == LIMEX_SQUASH_REPORT) {
+                    e.w = g32(x + offsetof(NFAException32, squash));
+                }
             }
             reinterpret_cast<uint4 *>(smem + 1024)[i] = e;
         }
@@ -327,31 +331,22 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
      * first byte of the scan (NO_OUTPUT | FIRST_BYTE) -- then succ & reach[byte]. */
     auto step = [&](const u32 w, const u32 j, u32 &s, const u32 pos, const u32 blk) -> bool {
         if (ENGINE == ENG_LIMEX32) {
-            u32 succ = (s & lxShift[0]) << lxAmount[0];
-#pragma unroll
-            for (int i = 1; i < 8; i++) {
-                if ((u32)i < lxShiftCount) {
-                    succ |= (s & lxShift[i]) << lxAmount[i];
+            /* NFA_EXEC_GET_LIM_SUCC + processExceptional32 (limex_exceptional.h:190-330, cache
+             * aside) over the states that are on, in ascending order: every exception's squash
+             * cuts the limited successors only, the exception successors are OR-ed in afterwards */
+            u32 lim = 0, local = 0, keep = 0xffffffffu, on = s;
+            while (on) {
+                const u32 bit = (u32)__ffs((int)on) - 1;
+                on &= on - 1;
+                const uint4 e = reinterpret_cast<const uint4 *>(smem + 1024)[bit];
+                if (e.z != MO_INVALID_IDX && pos != 0) {
+                    cursor = emitLimexReports(p, cursor, e.z, blk, pos);
                 }
+                lim |= e.x;
+                local |= e.y;
+                keep &= e.w;
             }
-            u32 est = s & lxExcMask;
-            if (est) { /* processExceptional32 (limex_exceptional.h:190-330), cache aside */
-                u32 local = 0;
-                do {
-                    const u32 bit = (u32)__ffs((int)est) - 1;
-                    est &= est - 1;
-                    const uint4 e = reinterpret_cast<const uint4 *>(smem + 1024)[__popc(lxExcMask & ((1u << bit) - 1))];
-                    if (e.z != MO_INVALID_IDX && pos != 0) {
-                        cursor = emitLimexReports(p, cursor, e.z, blk, pos);
-                    }
-                    local |= e.y;
-                    if (e.w == LIMEX_SQUASH_CYCLIC || e.w == LIMEX_SQUASH_REPORT) {
-                        succ &= e.x;
-                    }
-                } while (est);
-                succ |= local;
-            }
-            s = succ & reinterpret_cast<const u32 *>(smem)[__byte_perm(w, 0, 0x4440 + j)];
+            s = ((lim & keep) | local) & reinterpret_cast<const u32 *>(smem)[__byte_perm(w, 0, 0x4440 + j)];
             return false;
         } else if (ENGINE == ENG_MCC8) {
             s = smem[__byte_perm(w, s, 0x5540 + j)]; /* (s << 8) | byte */
