@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -129,6 +130,10 @@ struct DevImage {
     u32 bitmapBytes = 0, bitmapShift = 0, keyBytes = 0;
     u32 pairBytes = 0, bitmapHoles = 0, bitmapBits = 0; /* FK_PAIR32 layout (kernels.h) */
     u32 bucketFold = 0;
+    u32 nfaOffset = 0, nfaLength = 0;   /* FK_OUTFIX: the sole engine (bytecode offset, NFA.length) */
+    DfaParams nfaParams;                /* ... and what launchDfa needs to know about it */
+    /* FK_OUTFIX: report program offset -> its (onmatch, offset_adjust) list, filled as programs are met */
+    mutable std::unordered_map<u32, std::vector<std::pair<u32, s32>>> progReports;
     double pairRate = 0;     /* FK_PAIR32: modelled first-stage candidates per byte (printable ASCII) */
     u8 *d_bitmap2 = nullptr; /* second level (HBM / L2) for large literal sets */
     u32 bitmap2Shift = 0;
@@ -142,7 +147,7 @@ struct DevImage {
     u64 groups = 0;
     u32 minWidth = 0;
     bool hasDedupe = false;              /* RoseEngine.dkeyCount != 0 */
-    std::unordered_set<u32> exhaustible; /* report ids under HS_FLAG_SINGLEMATCH */
+    mutable std::unordered_set<u32> exhaustible; /* report ids under HS_FLAG_SINGLEMATCH (FK_OUTFIX: found with the programs) */
     size_t deviceBytes = 0;
 };
 
@@ -507,6 +512,66 @@ std::vector<u8> buildByteTable(const std::vector<LitTail> &tails, double *rate) 
     return out;
 }
 
+/* What launchDfa needs to know about a serialized engine (struct NFA + McClellan 8 / 16,
+ * Sheng or LimEx-32), checked against its length.  HS_ARCH_ERROR: an engine or a feature
+ * (wide states, bounded repeats) the DFA / NFA kernels do not implement. */
+hs_error_t engineParams(const void *nfa, size_t nfa_len, DfaParams *out) {
+    if (!nfa || nfa_len < sizeof(NFA) + 64) {
+        return HS_INVALID;
+    }
+    NFA hdr;
+    memcpy(&hdr, nfa, sizeof(hdr));
+    if (hdr.length > nfa_len) {
+        return HS_INVALID;
+    }
+    DfaParams &p = *out;
+    memset(&p, 0, sizeof(p));
+    p.kind = hdr.type;
+    p.ilp = g_opts.dfaIlp == 2 ? 2u : 1u;
+    if (hdr.type == NFA_MCCLELLAN_8 || hdr.type == NFA_MCCLELLAN_16) {
+        if (nfa_len < sizeof(NFA) + sizeof(McClellan)) {
+            return HS_INVALID;
+        }
+        McClellan m;
+        memcpy(&m, (const u8 *)nfa + sizeof(NFA), sizeof(m));
+        if (m.has_wide) {
+            return HS_ARCH_ERROR; /* wide states (mcclellan.c:168-225) are not built here */
+        }
+        const u32 rows = hdr.type == NFA_MCCLELLAN_16 ? m.sherman_limit : m.state_count;
+        p.tableBytes = (rows << m.alphaShift) * (hdr.type == NFA_MCCLELLAN_16 ? 2u : 1u);
+        p.states = m.state_count;
+        if (hdr.type == NFA_MCCLELLAN_8 && (m.state_count == 0 || m.state_count > 256)) {
+            return HS_INVALID;
+        }
+        if (sizeof(NFA) + sizeof(McClellan) + p.tableBytes > nfa_len) {
+            return HS_INVALID;
+        }
+    } else if (hdr.type == NFA_SHENG) {
+        if (nfa_len < sizeof(NFA) + sizeof(Sheng)) {
+            return HS_INVALID;
+        }
+    } else if (hdr.type == NFA_LIMEX_32) {
+        if (nfa_len < sizeof(NFA) + sizeof(LimExNFA32)) {
+            return HS_INVALID;
+        }
+        LimExNFA32 lx;
+        memcpy(&lx, (const u8 *)nfa + sizeof(NFA), sizeof(lx));
+        if (lx.repeatCount) {
+            return HS_ARCH_ERROR; /* bounded repeats (repeat control blocks, tug / pos triggers) are not built */
+        }
+        const size_t body = nfa_len - sizeof(NFA);
+        if (lx.shiftCount > 8 || lx.exceptionCount > 32 || sizeof(LimExNFA32) + 4ull * lx.reachSize > body ||
+            (size_t)lx.exceptionOffset + (size_t)lx.exceptionCount * sizeof(NFAException32) > body ||
+            (size_t)lx.acceptOffset + (size_t)lx.acceptCount * sizeof(NFAAccept) > body ||
+            (size_t)lx.acceptEodOffset + (size_t)lx.acceptEodCount * sizeof(NFAAccept) > body) {
+            return HS_INVALID;
+        }
+    } else {
+        return HS_ARCH_ERROR; /* LimEx, McSheng, Gough, Castle, ...: not built */
+    }
+    return HS_SUCCESS;
+}
+
 void freeImage(DevImage *im) {
     if (!im) {
         return;
@@ -525,8 +590,11 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     const DbHeader *h = (const DbHeader *)db;
     const RoseEngine *r = dbRose(db);
     const u8 *bc = (const u8 *)r;
-    if (r->runtimeImpl != RUNTIME_PURE_LITERAL || !r->fmatcherOffset) {
-        /* FULL_ROSE / SINGLE_OUTFIX databases need the regex engines
+    const bool soleOutfix = r->runtimeImpl == RUNTIME_SINGLE_OUTFIX && r->mode == MODE_BLOCK && r->queueCount == 1 &&
+                            r->outfixBeginQueue == 0 && r->outfixEndQueue == 1 && r->nfaInfoOffset &&
+                            !r->amatcherOffset && !r->ematcherOffset && !r->fmatcherOffset && !r->hasSom;
+    if (!soleOutfix && (r->runtimeImpl != RUNTIME_PURE_LITERAL || !r->fmatcherOffset)) {
+        /* FULL_ROSE databases need the full rose interpreter and the catch-up machinery
          * (SURVEY.md section 8f rank 1): not in this build */
         return HS_ARCH_ERROR;
     }
@@ -548,6 +616,48 @@ hs_error_t buildImage(const hs_database_t *db, DevImage **out) {
     im->groups = r->initialGroups & r->floating_group_mask;
     im->minWidth = r->minWidth;
     im->hasDedupe = r->dkeyCount != 0;
+    if (soleOutfix) {
+        /* hs_scan -> soleOutfixBlockExec (src/runtime.c:245-280): ONE engine over the whole block,
+         * its reports are report programs (roseReportAdaptor, src/rose/match.c:611-633).  The
+         * engine runs on the DFA / NFA kernels (dfa_kernels.cu) straight from the bytecode copy;
+         * the programs are resolved on the host when the records are ordered (postprocess). */
+        if ((size_t)r->nfaInfoOffset + sizeof(NfaInfo) > h->length) {
+            delete im;
+            return HS_INVALID;
+        }
+        NfaInfo ni;
+        memcpy(&ni, bc + r->nfaInfoOffset, sizeof(ni));
+        if (ni.nfaOffset % 64 || (size_t)ni.nfaOffset + sizeof(NFA) > h->length) {
+            delete im;
+            return HS_INVALID;
+        }
+        NFA nh;
+        memcpy(&nh, bc + ni.nfaOffset, sizeof(nh));
+        if ((size_t)ni.nfaOffset + nh.length > h->length) {
+            delete im;
+            return HS_INVALID;
+        }
+        const hs_error_t er = engineParams(bc + ni.nfaOffset, nh.length, &im->nfaParams);
+        if (er != HS_SUCCESS) {
+            delete im;
+            return er;
+        }
+        im->kind = FK_OUTFIX;
+        im->nfaOffset = ni.nfaOffset;
+        im->nfaLength = nh.length;
+        im->groups = 0;
+        cudaError_t e = cudaMalloc(&im->d_bc, HSB_ROUNDUP(h->length, 16));
+        if (e == cudaSuccess) {
+            e = cudaMemcpy(im->d_bc, bc, h->length, cudaMemcpyHostToDevice);
+        }
+        if (e != cudaSuccess) {
+            freeImage(im);
+            return e == cudaErrorMemoryAllocation ? HS_NOMEM : HS_UNKNOWN_ERROR;
+        }
+        im->deviceBytes = HSB_ROUNDUP(h->length, 16);
+        *out = im;
+        return HS_SUCCESS;
+    }
     const HWLM *hw = (const HWLM *)(bc + r->fmatcherOffset);
     const u32 engOff = r->fmatcherOffset + HWLM_ENGINE_OFFSET;
     std::vector<u8> table, pairBitmap, pairBitmap2;
@@ -1004,6 +1114,12 @@ struct ScanPlan {
 
 hs_error_t planScan(const hs_scratch *s, const DevImage *im, ScanPlan *pl) {
     initOpts();
+    if (im->kind == FK_OUTFIX) { /* one launch over all blocks once the corpus has arrived (launchRange) */
+        memset(&pl->cfg, 0, sizeof(pl->cfg));
+        pl->tileBytes = 1u << 20;
+        pl->nstages = 0;
+        return HS_SUCCESS;
+    }
     const int direct = g_opts.direct ? 1 : 0;
     int warps = g_opts.warps > 0 ? std::min(32, g_opts.warps) : (direct ? 28 : 32);
     u32 tile = (u32)std::max(512, g_opts.tileBytes) & ~511u;
@@ -1162,6 +1278,32 @@ hs_error_t launchRange(hs_scratch *s, const DevImage *im, const hs_b200_corpus *
     if (t1 <= t0) {
         return HS_SUCCESS;
     }
+    if (im->kind == FK_OUTFIX) {
+        /* a block is one thread's walk from its first byte: wait for the last range of the
+         * corpus, then run the engine over every block */
+        const u32 ntiles = (u32)((c->bytes + pl.tileBytes - 1) / pl.tileBytes);
+        if (t1 < ntiles) {
+            return HS_SUCCESS;
+        }
+        DfaParams dp = im->nfaParams;
+        dp.corpus = c->d_data;
+        dp.readableEnd = c->readableEnd;
+        dp.blockOff = c->d_off;
+        dp.blockLen = c->d_len;
+        dp.nblocks = (u32)c->nblocks;
+        dp.uniformPitch = c->uniformPitch;
+        dp.uniformLen = c->uniformLen;
+        dp.nfa = im->d_bc + im->nfaOffset;
+        dp.out = s->d_out;
+        dp.outCap = s->outCap;
+        dp.counters = s->d_counters;
+        int smCount = 0, maxSmem = 0;
+        cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, s->device);
+        cudaDeviceGetAttribute(&maxSmem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
+        CUDA_TRY(launchDfa(dp, smCount, maxSmem, stream));
+        g_launches++;
+        return HS_SUCCESS;
+    }
     ScanParams p;
     fillParams(s, im, c, pl, &p);
     p.tileFirst = t0;
@@ -1183,6 +1325,43 @@ hs_error_t launchRange(hs_scratch *s, const DevImage *im, const hs_b200_corpus *
 
 size_t postprocess(const DevImage *im, DevMatch *m, size_t n) {
     return postprocessRecords(im->exhaustible, (MatchRec *)m, n);
+}
+
+/* Records of a scan, ordered and with the order-dependent report rules applied (see
+ * postprocessRecords).  Single-outfix databases: the kernel's records carry report PROGRAM
+ * offsets (and the padding of the lanes' reserved slots); each is replaced by the reports its
+ * program raises -- roseReportAdaptor -> roseRunProgram (src/rose/match.c:611-633) -- first. */
+hs_error_t postprocessVec(const DevImage *im, std::vector<DevMatch> *v) {
+    if (im->kind != FK_OUTFIX) {
+        v->resize(postprocess(im, v->data(), v->size()));
+        return HS_SUCCESS;
+    }
+    const u8 *bc = (const u8 *)dbRose((const hs_database_t *)(im->dbCopy.data() + im->dbCopyShift));
+    std::vector<DevMatch> outv;
+    outv.reserve(v->size());
+    for (const DevMatch &m : *v) {
+        if (m.id == 0xffffffffu) {
+            continue; /* a slot some lane reserved and did not fill */
+        }
+        auto it = im->progReports.find(m.id);
+        if (it == im->progReports.end()) {
+            std::vector<std::pair<u32, s32>> reps;
+            if (m.id % INSTR_ALIGN || m.id < sizeof(RoseEngine) || m.id >= im->length ||
+                !collectProgramReports(bc, im->length, m.id, &im->exhaustible, &reps)) {
+                return HS_UNKNOWN_ERROR; /* a program with a state-carrying opcode (or a corrupt record) */
+            }
+            it = im->progReports.emplace(m.id, std::move(reps)).first;
+        }
+        for (const auto &rp : it->second) {
+            DevMatch o = m;
+            o.id = rp.first;
+            o.to = (u64)((long long)m.to + rp.second);
+            outv.push_back(o);
+        }
+    }
+    outv.resize(postprocess(im, outv.data(), outv.size()));
+    v->swap(outv);
+    return HS_SUCCESS;
 }
 
 hs_error_t finishScan(hs_scratch *s, u32 *count) {
@@ -1947,7 +2126,11 @@ hs_error_t hs_b200_fetch_matches(const hs_database_t *db, hs_scratch_t *scratch,
                                  cudaMemcpyDeviceToHost, scratch->copyStream));
         CUDA_TRY(cudaStreamSynchronize(scratch->copyStream));
     }
-    const size_t m = postprocess(im, tmp.data(), n);
+    r = postprocessVec(im, &tmp);
+    if (r != HS_SUCCESS) {
+        return r;
+    }
+    const size_t m = tmp.size();
     if (nmatches) {
         *nmatches = m;
     }
@@ -1978,49 +2161,11 @@ hs_error_t hs_b200_nfa_scan_corpus(const void *nfa, size_t nfa_len, const hs_b20
         return HS_INVALID;
     }
     DfaParams p;
-    memset(&p, 0, sizeof(p));
-    p.kind = hdr.type;
-    p.ilp = g_opts.dfaIlp == 2 ? 2u : 1u;
-    if (hdr.type == NFA_MCCLELLAN_8 || hdr.type == NFA_MCCLELLAN_16) {
-        if (nfa_len < sizeof(NFA) + sizeof(McClellan)) {
-            return HS_INVALID;
+    {
+        const hs_error_t er = engineParams(nfa, nfa_len, &p);
+        if (er != HS_SUCCESS) {
+            return er;
         }
-        McClellan m;
-        memcpy(&m, (const u8 *)nfa + sizeof(NFA), sizeof(m));
-        if (m.has_wide) {
-            return HS_ARCH_ERROR; /* wide states (mcclellan.c:168-225) are not built here */
-        }
-        const u32 rows = hdr.type == NFA_MCCLELLAN_16 ? m.sherman_limit : m.state_count;
-        p.tableBytes = (rows << m.alphaShift) * (hdr.type == NFA_MCCLELLAN_16 ? 2u : 1u);
-        p.states = m.state_count;
-        if (hdr.type == NFA_MCCLELLAN_8 && (m.state_count == 0 || m.state_count > 256)) {
-            return HS_INVALID;
-        }
-        if (sizeof(NFA) + sizeof(McClellan) + p.tableBytes > nfa_len) {
-            return HS_INVALID;
-        }
-    } else if (hdr.type == NFA_SHENG) {
-        if (nfa_len < sizeof(NFA) + sizeof(Sheng)) {
-            return HS_INVALID;
-        }
-    } else if (hdr.type == NFA_LIMEX_32) {
-        if (nfa_len < sizeof(NFA) + sizeof(LimExNFA32)) {
-            return HS_INVALID;
-        }
-        LimExNFA32 lx;
-        memcpy(&lx, (const u8 *)nfa + sizeof(NFA), sizeof(lx));
-        if (lx.repeatCount) {
-            return HS_ARCH_ERROR; /* bounded repeats (repeat control blocks, tug / pos triggers) are not built */
-        }
-        const size_t body = nfa_len - sizeof(NFA);
-        if (lx.shiftCount > 8 || lx.exceptionCount > 32 || sizeof(LimExNFA32) + 4ull * lx.reachSize > body ||
-            (size_t)lx.exceptionOffset + (size_t)lx.exceptionCount * sizeof(NFAException32) > body ||
-            (size_t)lx.acceptOffset + (size_t)lx.acceptCount * sizeof(NFAAccept) > body ||
-            (size_t)lx.acceptEodOffset + (size_t)lx.acceptEodCount * sizeof(NFAAccept) > body) {
-            return HS_INVALID;
-        }
-    } else {
-        return HS_ARCH_ERROR; /* LimEx, McSheng, Gough, Castle, ...: not built */
     }
     DeviceGuard guard(corpus->device);
     int smCount = 0, maxSmem = 0;
@@ -2240,9 +2385,12 @@ static hs_error_t scanHostBlocks(const DevImage *im, hs_scratch *s, const char *
             tRec = nowMs();
             /* nobody will look at the order, and neither dedupe keys nor
              * exhaustion keys exist: the raw count IS the delivered count */
-            const bool plain = countOnly && im->exhaustible.empty() && !im->hasDedupe;
+            const bool plain = countOnly && im->exhaustible.empty() && !im->hasDedupe && im->kind != FK_OUTFIX;
             if (!plain) {
-                matches->resize(postprocess(im, matches->data(), count));
+                r = postprocessVec(im, matches);
+                if (r != HS_SUCCESS) {
+                    return r;
+                }
             }
             if (trace) {
                 fprintf(stderr, "[hs_b200 trace] host scan: layout %.3f ms, enqueue %.3f, wait %.3f, records %.3f, "

@@ -60,6 +60,8 @@ enum FilterKind {
                       literals are all >= 4 bytes.  Table image: 256 class words
                       (4 * c); ScanParams.bitmap = the bitmap (bitmapBytes), bit c[e] of word
                       c[e-3] + 33 c[e-2] + 1025 c[e-1] */
+    FK_OUTFIX = 6, /* no literal first stage at all: a single-outfix database, its one engine runs on
+                      the DFA / NFA kernels (dfa_kernels.cu) */
 };
 
 enum ConfirmKind {

@@ -891,6 +891,7 @@ static hs_error_t compileCommon(const char *const *expressions,
             }
         }
         applyBuildOptions(&opts.hwlm);
+        opts.outfixKind = outfixEngineOption();
         if (opts.hwlm.allowFatTeddy) {
             opts.platform &= ~PLATFORM_NOAVX2; /* 16-bucket Teddy needs AVX2 on CPUs */
         }
@@ -1042,10 +1043,15 @@ hs_error_t hs_expression_ext_info(const char *expression, unsigned int flags,
  * (unit/internal/fdr.cpp:114-137, src/fdr/fdr_compile.cpp:862-866) and its
  * tools override Grey values with -G.  Keys: "force_engine" (-1 auto, 0 FDR,
  * 3..18 Teddy id), "fdr_domain", "fdr_stride", "max_domain", "allow_teddy",
- * "allow_fat_teddy", "allow_flood", "allow_noodle". */
+ * "allow_fat_teddy", "allow_flood", "allow_noodle"; "outfix_engine" (0 = literal
+ * matchers as usual; 1 DFA chosen by size, 2 McClellan-8, 3 McClellan-16, 4 Sheng,
+ * 5 LimEx-32: block-mode literal sets are compiled to a database whose only matcher is
+ * that engine run as an outfix, ROSE_RUNTIME_SINGLE_OUTFIX). */
 namespace hsb {
 static HwlmBuildOpts g_tunables;
 static bool g_tun_set[8];
+static int g_outfixEngine = 0; /* "outfix_engine": see enum OutfixKind (rose_build.h) */
+int outfixEngineOption() { return g_outfixEngine; }
 void applyBuildOptions(HwlmBuildOpts *o) {
     if (g_tun_set[0]) o->forceEngine = g_tunables.forceEngine;
     if (g_tun_set[1]) o->forceDomain = g_tunables.forceDomain;
@@ -1066,6 +1072,14 @@ extern "C" hs_error_t hs_b200_set_build_option(const char *key, int value) {
     if (k == "reset") {
         memset(g_tun_set, 0, sizeof(g_tun_set));
         g_tunables = HwlmBuildOpts();
+        hsb::g_outfixEngine = 0;
+        return HS_SUCCESS;
+    }
+    if (k == "outfix_engine") {
+        if (value < 0 || value > 5) {
+            return HS_INVALID;
+        }
+        hsb::g_outfixEngine = value;
         return HS_SUCCESS;
     }
     struct { const char *n; int i; } keys[] = {

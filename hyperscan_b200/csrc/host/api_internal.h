@@ -21,6 +21,7 @@ static inline const RoseEngine *dbRose(const hs_database_t *db) {
 /** Apply the process-wide build tunables set through hs_b200_set_build_option
  * (the analogue of the reference's Grey overrides, src/grey.cpp:40-160). */
 void applyBuildOptions(HwlmBuildOpts *o);
+int outfixEngineOption(); /* build option "outfix_engine" (api_host.cpp) */
 
 } // namespace hsb
 #endif

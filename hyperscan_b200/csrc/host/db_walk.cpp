@@ -16,7 +16,8 @@ namespace hsb {
  * runProgram) does not implement -- the state-carrying ones of
  * roseRunProgram_l: PUSH_DELAYED, CATCH_UP*, SOM_*, TRIGGER_SUFFIX, REPORT_CHAIN,
  * REPORT_SOM*, SET_LOGICAL, SET_COMBINATION, FLUSH_COMBINATION, SET_EXHAUST. */
-bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex) {
+bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex,
+                           std::vector<std::pair<u32, s32>> *reports) {
     u32 pc = prog, furthest = prog;
     auto jump = [&](u32 from, u32 rel) { furthest = std::max(furthest, from + rel); };
 #define STEP(T) pc += (u32)HSB_ROUNDUP(sizeof(T), INSTR_ALIGN)
@@ -39,12 +40,18 @@ bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
             }
             STEP(InstrEnd);
             break;
-        case OP_FINAL_REPORT:
+        case OP_FINAL_REPORT: {
+            if (reports) {
+                InstrFinalReport in;
+                memcpy(&in, bc + pc, sizeof(in));
+                reports->push_back({in.onmatch, in.offset_adjust});
+            }
             if (furthest <= pc) {
                 return true;
             }
             STEP(InstrFinalReport);
             break;
+        }
         case OP_CHECK_GROUPS: STEP(InstrCheckGroups); break;
         case OP_CHECK_MASK: STEP_JUMP(InstrCheckMask); break;
         case OP_CHECK_MASK_32: STEP_JUMP(InstrCheckMask32); break;
@@ -56,15 +63,34 @@ bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
         case OP_CHECK_LONG_LIT_NOCASE: STEP_JUMP(InstrCheckLit); break;
         case OP_CHECK_EXHAUSTED: STEP_JUMP(InstrCheckExhausted); break;
         case OP_DEDUPE: STEP_JUMP(InstrDedupe); break;
-        case OP_REPORT: STEP(InstrReport); break;
+        case OP_REPORT: {
+            if (reports) {
+                InstrReport in;
+                memcpy(&in, bc + pc, sizeof(in));
+                reports->push_back({in.onmatch, in.offset_adjust});
+            }
+            STEP(InstrReport);
+            break;
+        }
         case OP_REPORT_EXHAUST: {
             InstrReportExhaust in;
             memcpy(&in, bc + pc, sizeof(in));
             ex->insert(in.onmatch);
+            if (reports) {
+                reports->push_back({in.onmatch, in.offset_adjust});
+            }
             STEP(InstrReportExhaust);
             break;
         }
-        case OP_DEDUPE_AND_REPORT: STEP_JUMP(InstrDedupeAndReport); break;
+        case OP_DEDUPE_AND_REPORT: {
+            if (reports) {
+                InstrDedupeAndReport in;
+                memcpy(&in, bc + pc, sizeof(in));
+                reports->push_back({in.onmatch, in.offset_adjust});
+            }
+            STEP_JUMP(InstrDedupeAndReport);
+            break;
+        }
         case OP_SQUASH_GROUPS: STEP(InstrSquashGroups); break;
         case OP_CLEAR_WORK_DONE: pc += INSTR_ALIGN; break;
         case OP_INCLUDED_JUMP: STEP(InstrIncludedJump); break;

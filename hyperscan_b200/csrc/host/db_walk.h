@@ -9,6 +9,7 @@
 #define HSB200_DB_WALK_H
 
 #include <unordered_set>
+#include <utility>
 #include <vector>
 
 #include "../../../include/hs_b200.h"
@@ -30,7 +31,9 @@ struct MatchRec { /* == hs_b200_match_t */
 
 /* Both return false if a program holds an opcode the device does not implement
  * (callers refuse the database with HS_ARCH_ERROR instead of failing mid-scan). */
-bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex);
+bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex,
+                           std::vector<std::pair<u32, s32>> *reports = nullptr); /* reports: (onmatch, offset_adjust) of every
+                                                                                  * report instruction, in program order */
 
 bool walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
                  std::unordered_set<u32> *ex, std::vector<LitTail> *tails);

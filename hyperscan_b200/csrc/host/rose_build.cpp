@@ -23,6 +23,7 @@
  */
 #include "rose_build.h"
 #include "dfa_build.h"
+#include "limex_build.h"
 
 #include <algorithm>
 #include <cstring>
@@ -85,6 +86,74 @@ struct RoseTail {
     bool canExhaust;
     u32 smallWriteOffset = 0;
 };
+
+/* A database whose only matcher is ONE engine run as an outfix over the whole block
+ * (ROSE_RUNTIME_SINGLE_OUTFIX: hs_scan -> soleOutfixBlockExec, src/runtime.c:245-280): queue 0,
+ * no literal matchers.  What the reference's compiler emits for a pattern set that is all
+ * engine and no literal (rose_build_bytecode.cpp:3672-3690 pickRuntimeImpl); here it is built
+ * for literal sets on request, so that the DFA / NFA engines run inside a real database. */
+std::vector<u8> finishOutfixRose(Blob &blob, const std::vector<u8> &nfa, const RoseTail &t, const CompileOpts &opts) {
+    NFA hdr;
+    memcpy(&hdr, nfa.data(), sizeof(hdr));
+    const u32 nfaOffset = blob.add(nfa.data(), nfa.size(), 64);
+    RoseEngine r;
+    memset(&r, 0, sizeof(r));
+    r.pureLiteral = 0;
+    r.runtimeImpl = RUNTIME_SINGLE_OUTFIX;
+    r.canExhaust = t.canExhaust ? 1 : 0;
+    r.mode = MODE_BLOCK;
+    r.ekeyCount = t.ekeyCount;
+    r.dkeyCount = t.dkeyCount;
+    r.dkeyLogSize = fatbitSize(r.dkeyCount);
+    r.invDkeyOffset = t.invDkeyOffset;
+    r.somLocationFatbitSize = fatbitSize(0);
+    r.activeArrayCount = 1;
+    r.queueCount = 1;
+    r.activeQueueArraySize = fatbitSize(1);
+    r.handledKeyFatbitSize = fatbitSize(0);
+    r.minWidth = t.minLen;
+    r.minWidthExcludingBoundaries = t.minLen;
+    r.maxBiAnchoredWidth = ROSE_BOUND_INF;
+    r.floatingDistance = ROSE_BOUND_INF;
+    r.initialGroups = 0;
+    r.delay_fatbit_size = fatbitSize(0);
+    r.anchored_fatbit_size = fatbitSize(0);
+    r.outfixBeginQueue = 0;
+    r.outfixEndQueue = 1;
+    r.leftfixBeginQueue = 1;
+    r.initMpvNfa = 0xffffffffu;
+    r.scratchStateSize = (u32)HSB_ROUNDUP(hdr.scratchStateSize, 64); /* the queue's full state, in scratch */
+    StateOffsets &so = r.stateOffsets;
+    u32 cur = 1; /* status byte; no roles */
+    so.activeLeafArray = cur;
+    so.activeLeafArray_size = mmbitSize(1);
+    cur += so.activeLeafArray_size;
+    so.activeLeftArray = so.longLitState = so.leftfixLagTable = so.anchorState = cur;
+    so.groups = cur;
+    so.groups_size = 0;
+    so.history = cur;
+    so.exhausted = cur;
+    so.exhausted_size = mmbitSize(r.ekeyCount);
+    cur += so.exhausted_size;
+    so.logicalVec = so.combVec = cur;
+    so.nfaStateBegin = cur;
+    NfaInfo ni;
+    memset(&ni, 0, sizeof(ni));
+    ni.nfaOffset = nfaOffset;
+    ni.stateOffset = cur;
+    ni.fullStateOffset = 0;
+    cur += hdr.streamStateSize;
+    so.end = cur;
+    r.stateSize = cur;
+    r.nfaInfoOffset = blob.add(&ni, sizeof(ni), 4);
+    const u32 total = (u32)HSB_ROUNDUP(blob.base + blob.bytes.size(), 64);
+    r.size = total;
+    (void)opts;
+    std::vector<u8> out(total, 0);
+    memcpy(out.data(), &r, sizeof(r));
+    memcpy(out.data() + blob.base, blob.bytes.data(), blob.bytes.size());
+    return out;
+}
 
 /* Floating literal matcher + RoseEngine header around a finished program blob. */
 std::vector<u8> finishRose(Blob &blob, const std::vector<HwlmLit> &hl, const RoseTail &t,
@@ -240,6 +309,103 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
             }
             pi.dkey = it->second;
         }
+    }
+
+    if (opts.outfixKind) {
+        /* --- single-outfix database: report programs ([CHECK_EXHAUSTED] [DEDUPE] REPORT_EXHAUST |
+         * DEDUPE_AND_REPORT | REPORT, END -- run by roseReportAdaptor / roseRunProgram), one engine
+         * over the whole literals whose reports are those programs' offsets --- */
+        if (opts.streaming) {
+            throw CompileError{"Single-engine databases are built for block mode only.", -1};
+        }
+        Blob blob((u32)HSB_ROUNDUP(sizeof(RoseEngine), 64));
+        std::vector<DfaLiteral> dl;
+        u32 minLen = ~0u, maxLen = 0;
+        for (const PatInfo &pi : pats) {
+            minLen = std::min<u32>(minLen, (u32)pi.p->s.size());
+            maxLen = std::max<u32>(maxLen, (u32)pi.p->s.size());
+            const u32 sz = blockSize(pi) - (pi.p->s.size() > 8 ? instrSize<InstrCheckLit>() : 0) + instrSize<InstrEnd>();
+            u32 pc = blob.reserve(sz, INSTR_ALIGN);
+            const u32 prog = pc, endAt = pc + sz - instrSize<InstrEnd>();
+            if (pi.ekey != INVALID_EKEY) {
+                InstrCheckExhausted ce;
+                memset(&ce, 0, sizeof(ce));
+                ce.code = OP_CHECK_EXHAUSTED;
+                ce.ekey = pi.ekey;
+                ce.fail_jump = endAt - pc;
+                memcpy(blob.at(pc), &ce, sizeof(ce));
+                pc += instrSize<InstrCheckExhausted>();
+                if (pi.dkey != INVALID_DKEY) {
+                    InstrDedupe dd;
+                    memset(&dd, 0, sizeof(dd));
+                    dd.code = OP_DEDUPE;
+                    dd.dkey = pi.dkey;
+                    dd.fail_jump = endAt - pc;
+                    memcpy(blob.at(pc), &dd, sizeof(dd));
+                    pc += instrSize<InstrDedupe>();
+                }
+                InstrReportExhaust re;
+                memset(&re, 0, sizeof(re));
+                re.code = OP_REPORT_EXHAUST;
+                re.onmatch = pi.p->report;
+                re.ekey = pi.ekey;
+                memcpy(blob.at(pc), &re, sizeof(re));
+            } else if (pi.dkey != INVALID_DKEY) {
+                InstrDedupeAndReport dr;
+                memset(&dr, 0, sizeof(dr));
+                dr.code = OP_DEDUPE_AND_REPORT;
+                dr.dkey = pi.dkey;
+                dr.onmatch = pi.p->report;
+                dr.fail_jump = endAt - pc;
+                memcpy(blob.at(pc), &dr, sizeof(dr));
+            } else {
+                InstrReport rr;
+                memset(&rr, 0, sizeof(rr));
+                rr.code = OP_REPORT;
+                rr.onmatch = pi.p->report;
+                memcpy(blob.at(pc), &rr, sizeof(rr));
+            }
+            InstrEnd e;
+            e.code = OP_END;
+            memcpy(blob.at(endAt), &e, sizeof(e));
+            DfaLiteral l;
+            l.s = pi.p->s;
+            l.caseless = pi.p->caseless && pi.anyAlpha;
+            l.report = prog;
+            dl.push_back(l);
+        }
+        RoseTail t;
+        t.minLen = minLen;
+        t.maxLen = maxLen;
+        t.ekeyCount = (u32)ekeys.size();
+        t.dkeyCount = (u32)dkeys.size();
+        t.invDkeyOffset = 0;
+        if (!dkeys.empty()) {
+            std::vector<u32> inv(dkeys.size());
+            for (const auto &d : dkeys) {
+                inv[d.second] = d.first;
+            }
+            t.invDkeyOffset = blob.add(inv.data(), inv.size() * sizeof(u32), 4);
+        }
+        t.canExhaust = allHighlander;
+        std::vector<u8> nfa;
+        try {
+            if (opts.outfixKind == OUTFIX_LIMEX32) {
+                nfa = emitLimEx32(nfaFromLiterals(dl));
+            } else {
+                const DfaKind k = opts.outfixKind == OUTFIX_MCCLELLAN8    ? DFA_MCCLELLAN8
+                                  : opts.outfixKind == OUTFIX_MCCLELLAN16 ? DFA_MCCLELLAN16
+                                  : opts.outfixKind == OUTFIX_SHENG       ? DFA_SHENG
+                                                                          : DFA_AUTO;
+                nfa = emitDfa(dfaFromLiterals(dl, false), k, false);
+            }
+        } catch (const std::runtime_error &e) {
+            throw CompileError{std::string("Unable to build the engine: ") + e.what(), -1};
+        }
+        if (info) {
+            memset(info, 0, sizeof(*info));
+        }
+        return finishOutfixRose(blob, nfa, t, opts);
     }
 
     /* --- group into fragments by (8-byte suffix, effective nocase) --- */

@@ -35,9 +35,14 @@ struct CompileOpts {
     bool vectored = false;       /* HS_MODE_VECTORED: a streaming database stamped for hs_scan_vector */
     bool smallWrite = true;      /* block mode: also emit the small-write DFA (src/smallwrite/) for buffers
                                   * shorter than 70 bytes when the literal set's automaton stays small */
+    int outfixKind = 0;          /* != 0: no literal matcher, ONE engine over the whole literals run as an
+                                  * outfix (ROSE_RUNTIME_SINGLE_OUTFIX): see enum OutfixKind */
     u64 platform = PLATFORM_NOAVX2 | PLATFORM_NOAVX512 | PLATFORM_NOAVX512VBMI;
     HwlmBuildOpts hwlm;
 };
+
+enum OutfixKind { OUTFIX_NONE = 0, OUTFIX_DFA_AUTO = 1, OUTFIX_MCCLELLAN8 = 2, OUTFIX_MCCLELLAN16 = 3, OUTFIX_SHENG = 4,
+                  OUTFIX_LIMEX32 = 5 };
 
 /* grey-box limits mirrored from src/grey.cpp:40-160 */
 static const size_t LIMIT_PATTERN_LENGTH = 16000;
