@@ -404,7 +404,11 @@ hs_error_t hs_b200_db_info(const hs_database_t *db, hs_b200_db_info_t *info);
  * overrides and of the engine "hints" its unit tests use,
  * unit/internal/fdr.cpp:114-137).  Keys: "force_engine" (-1 auto, 0 FDR, 3..18
  * Teddy engine id), "fdr_domain" (9..15), "fdr_stride" (1,2,4), "max_domain",
- * "allow_teddy", "allow_fat_teddy", "allow_flood", "allow_noodle"; key "reset"
+ * "allow_teddy", "allow_fat_teddy", "allow_flood", "allow_noodle"; "outfix_engine"
+ * (0: literal matchers as usual; 1 DFA chosen by size, 2 McClellan-8, 3 McClellan-16,
+ * 4 Sheng, 5 LimEx-32: hs_compile_lit* in block mode emit a database whose only matcher
+ * is that engine over the whole literals, run as an outfix -- ROSE_RUNTIME_SINGLE_OUTFIX,
+ * src/runtime.c:245-280; the reference's hs_scan and this one both scan it); key "reset"
  * restores the defaults. */
 hs_error_t hs_b200_set_build_option(const char *key, int value);
 
