@@ -22,6 +22,7 @@
 #include "rose_build.h"
 #include "dfa_build.h"
 #include "limex_build.h"
+#include "regex_nfa.h"
 
 using namespace hsb;
 
@@ -803,6 +804,8 @@ static hs_error_t compileCommon(const char *const *expressions,
     try {
         std::vector<LitPattern> pats;
         pats.reserve(elements);
+        std::vector<RegexPattern> rpats; /* every expression, for the NFA route */
+        bool needNfa = false;
         for (unsigned i = 0; i < elements; i++) {
             const unsigned f = flags ? flags[i] : 0;
             if (!expressions[i]) {
@@ -850,9 +853,26 @@ static hs_error_t compileCommon(const char *const *expressions,
                     throw CompileError{"HS_FLAG_SOM_LEFTMOST is not supported by the B200 "
                                        "literal compiler yet.", (int)i};
                 }
+                {
+                    RegexPattern rp;
+                    rp.re = expressions[i];
+                    rp.flags = f;
+                    rp.report = p.report;
+                    rp.index = i;
+                    rpats.push_back(rp);
+                }
                 /* one literal per string of the expression's (finite) language,
                  * all under the expression's id */
-                const std::vector<std::string> lang = regexToLiterals(expressions[i], f, (int)i);
+                std::vector<std::string> lang;
+                try {
+                    lang = regexToLiterals(expressions[i], f, (int)i);
+                } catch (const CompileError &ce) {
+                    if (ce.msg.find("regex back end") == std::string::npos) {
+                        throw;
+                    }
+                    needNfa = true; /* not a finite set of literals: the whole set goes to one LimEx-32 NFA */
+                    continue;
+                }
                 for (const std::string &str : lang) {
                     if (str.empty()) {
                         throw CompileError{(f & HS_FLAG_ALLOWEMPTY)
@@ -895,7 +915,7 @@ static hs_error_t compileCommon(const char *const *expressions,
         if (opts.hwlm.allowFatTeddy) {
             opts.platform &= ~PLATFORM_NOAVX2; /* 16-bucket Teddy needs AVX2 on CPUs */
         }
-        std::vector<u8> bc = buildLiteralRose(pats, opts, nullptr);
+        std::vector<u8> bc = needNfa ? buildRegexRose(rpats, opts) : buildLiteralRose(pats, opts, nullptr);
         hs_error_t aerr;
         hs_database_t *out = dbCreate(bc, opts.platform, &aerr);
         if (!out) {
@@ -1002,11 +1022,25 @@ static hs_error_t exprInfo(const char *expression, unsigned flags, const hs_expr
             throw CompileError{"Extended parameters need the regex back end; this build compiles "
                                "literal patterns only.", 0};
         }
-        const std::vector<std::string> lang = regexToLiterals(expression, flags, 0);
-        size_t minW = lang.empty() ? 0 : lang[0].size(), maxW = 0;
-        for (const std::string &str : lang) {
-            minW = std::min(minW, str.size());
-            maxW = std::max(maxW, str.size());
+        size_t minW = 0, maxW = 0;
+        try {
+            const std::vector<std::string> lang = regexToLiterals(expression, flags, 0);
+            minW = lang.empty() ? 0 : lang[0].size();
+            for (const std::string &str : lang) {
+                minW = std::min(minW, str.size());
+                maxW = std::max(maxW, str.size());
+            }
+        } catch (const CompileError &ce) {
+            if (ce.msg.find("regex back end") == std::string::npos) {
+                throw;
+            }
+            try { /* not a finite set of literals: the NFA route's parser knows the widths */
+                const RegexInfo ri = regexInfo(expression, flags);
+                minW = ri.minLen;
+                maxW = ri.maxLen; /* 0xffffffff = unbounded, as in the reference (src/hs.cpp:398-403) */
+            } catch (const RegexError &re) {
+                throw CompileError{re.msg, 0};
+            }
         }
         hs_expr_info_t *out = (hs_expr_info_t *)g_misc_alloc(sizeof(*out));
         if (!out) {

@@ -1,0 +1,567 @@
+/* regex_nfa.cpp -- see regex_nfa.h */
+#include "regex_nfa.h"
+
+#include <algorithm>
+#include <bitset>
+#include <cstring>
+#include <memory>
+
+#include "../../../include/hs_b200.h"
+
+namespace hsb {
+
+namespace {
+
+typedef std::bitset<256> CharSet;
+
+struct Node {
+    enum Kind { CLASS, CAT, ALT, STAR, PLUS, OPT, EMPTY } kind = EMPTY;
+    CharSet cls;
+    std::vector<std::shared_ptr<Node>> kids;
+    bool anchored = false; /* top-level alternative that starts with "^" */
+};
+typedef std::shared_ptr<Node> NodeP;
+
+NodeP mk(Node::Kind k) {
+    NodeP n = std::make_shared<Node>();
+    n->kind = k;
+    return n;
+}
+
+NodeP clone(const NodeP &n) {
+    NodeP c = std::make_shared<Node>(*n);
+    for (NodeP &k : c->kids) {
+        k = clone(k);
+    }
+    return c;
+}
+
+class Parser {
+public:
+    Parser(const char *re_in, unsigned flags_in) : re(re_in), n(strlen(re_in)), flags(flags_in) {}
+
+    NodeP parse() {
+        if (flags & (HS_FLAG_UTF8 | HS_FLAG_UCP)) {
+            fail("HS_FLAG_UTF8 / HS_FLAG_UCP need the reference's Unicode compiler.");
+        }
+        if (flags & HS_FLAG_SOM_LEFTMOST) {
+            fail("HS_FLAG_SOM_LEFTMOST is not supported.");
+        }
+        NodeP r = alt(true);
+        if (pos != n) {
+            fail("Unmatched parentheses.");
+        }
+        return r;
+    }
+
+private:
+    const char *re;
+    size_t n, pos = 0;
+    unsigned flags;
+
+    [[noreturn]] void fail(const std::string &m) const { throw RegexError{m}; }
+    bool at(char c) const { return pos < n && re[pos] == c; }
+
+    CharSet fold(CharSet s) const {
+        if (flags & HS_FLAG_CASELESS) {
+            for (int c = 'a'; c <= 'z'; c++) {
+                if (s[c] || s[c - 32]) {
+                    s[c] = s[c - 32] = true;
+                }
+            }
+        }
+        return s;
+    }
+
+    NodeP alt(bool top) {
+        std::vector<NodeP> arms;
+        arms.push_back(seq(top));
+        while (at('|')) {
+            pos++;
+            arms.push_back(seq(top));
+        }
+        if (arms.size() == 1) {
+            return arms[0];
+        }
+        NodeP a = mk(Node::ALT);
+        a->kids = arms;
+        return a;
+    }
+
+    NodeP seq(bool top) {
+        NodeP s = mk(Node::CAT);
+        if (at('^')) {
+            if (!top) {
+                fail("'^' inside a group needs the reference's assertion handling.");
+            }
+            if (flags & HS_FLAG_MULTILINE) {
+                fail("'^' under HS_FLAG_MULTILINE is not supported.");
+            }
+            pos++;
+            s->anchored = true;
+        }
+        while (pos < n && re[pos] != '|' && re[pos] != ')') {
+            NodeP a = atom();
+            a = quantified(a);
+            s->kids.push_back(a);
+        }
+        return s;
+    }
+
+    NodeP repeat(const NodeP &a, unsigned lo, long hi /* -1 = unbounded */) {
+        NodeP s = mk(Node::CAT);
+        for (unsigned i = 0; i < lo; i++) {
+            s->kids.push_back(clone(a));
+        }
+        if (hi < 0) {
+            if (lo == 0) {
+                NodeP st = mk(Node::STAR);
+                st->kids.push_back(clone(a));
+                s->kids.push_back(st);
+            } else { /* x{n,} = x^(n-1) x+ */
+                NodeP pl = mk(Node::PLUS);
+                pl->kids.push_back(s->kids.back());
+                s->kids.back() = pl;
+            }
+        } else {
+            for (long i = lo; i < hi; i++) { /* x{n,m}: m - n optional copies (same language as the nested form) */
+                NodeP o = mk(Node::OPT);
+                o->kids.push_back(clone(a));
+                s->kids.push_back(o);
+            }
+        }
+        return s;
+    }
+
+    NodeP quantified(NodeP a) {
+        if (pos >= n) {
+            return a;
+        }
+        const char c = re[pos];
+        unsigned lo = 1;
+        long hi = 1;
+        if (c == '*') {
+            pos++;
+            lo = 0;
+            hi = -1;
+        } else if (c == '+') {
+            pos++;
+            lo = 1;
+            hi = -1;
+        } else if (c == '?') {
+            pos++;
+            lo = 0;
+            hi = 1;
+        } else if (c == '{') {
+            size_t q = pos + 1;
+            unsigned long x = 0, y = 0;
+            bool haveX = false, haveY = false, comma = false;
+            while (q < n && isdigit((unsigned char)re[q])) {
+                x = std::min(x * 10 + (unsigned long)(re[q++] - '0'), 100000ul);
+                haveX = true;
+            }
+            if (q < n && re[q] == ',') {
+                comma = true;
+                q++;
+                while (q < n && isdigit((unsigned char)re[q])) {
+                    y = std::min(y * 10 + (unsigned long)(re[q++] - '0'), 100000ul);
+                    haveY = true;
+                }
+            }
+            if (!haveX || q >= n || re[q] != '}') {
+                fail("A '{' that does not start a repeat is not supported.");
+            }
+            if (comma && haveY && y < x) {
+                fail("Bounded repeat is invalid: min > max.");
+            }
+            if (x > 32 || (haveY && y > 32)) {
+                fail("Pattern is too large.");
+            }
+            pos = q + 1;
+            lo = (unsigned)x;
+            hi = !comma ? (long)x : haveY ? (long)y : -1;
+        } else {
+            return a;
+        }
+        if (pos < n && re[pos] == '?') {
+            pos++; /* lazy: same set of match ends */
+        } else if (pos < n && re[pos] == '+') {
+            fail("Possessive quantifiers are not supported.");
+        }
+        if (lo == 1 && hi == 1) {
+            return a;
+        }
+        if (lo == 0 && hi == 0) {
+            return mk(Node::EMPTY);
+        }
+        return repeat(a, lo, hi);
+    }
+
+    static int hexval(char c) {
+        if (c >= '0' && c <= '9') return c - '0';
+        if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+        if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+        return -1;
+    }
+
+    static CharSet classEscape(char e) {
+        CharSet s;
+        switch (e | 0x20) {
+        case 'd':
+            for (int c = '0'; c <= '9'; c++) s[c] = true;
+            break;
+        case 'w':
+            for (int c = '0'; c <= '9'; c++) s[c] = true;
+            for (int c = 'a'; c <= 'z'; c++) s[c] = s[c - 32] = true;
+            s['_'] = true;
+            break;
+        case 's': /* PCRE 8.41 \s: space, \t \n \v \f \r */
+            s[' '] = s['\t'] = s['\n'] = s[0x0b] = s['\f'] = s['\r'] = true;
+            break;
+        }
+        return (e >= 'A' && e <= 'Z') ? ~s : s;
+    }
+
+    /* an escape: either one character (*single) or a class */
+    CharSet escape(bool inClass, int *single) {
+        *single = -1;
+        if (++pos >= n) {
+            fail("Unterminated escape at end of pattern.");
+        }
+        const unsigned char e = (unsigned char)re[pos++];
+        CharSet s;
+        switch (e) {
+        case 'n': *single = '\n'; break;
+        case 't': *single = '\t'; break;
+        case 'r': *single = '\r'; break;
+        case 'f': *single = '\f'; break;
+        case 'a': *single = '\a'; break;
+        case 'e': *single = 0x1b; break;
+        case 'd': case 'D': case 'w': case 'W': case 's': case 'S':
+            return classEscape((char)e);
+        case 'x': {
+            const int h1 = pos < n ? hexval(re[pos]) : -1;
+            const int h2 = pos + 1 < n ? hexval(re[pos + 1]) : -1;
+            if (h1 < 0 || h2 < 0) {
+                fail("Invalid hex escape; only \\xHH is accepted.");
+            }
+            pos += 2;
+            *single = h1 * 16 + h2;
+            break;
+        }
+        default:
+            if (inClass && e == 'b') {
+                *single = 0x08;
+            } else if (isalnum(e)) {
+                fail(std::string("Escape sequence \\") + (char)e + " is not supported.");
+            } else {
+                *single = e;
+            }
+        }
+        s[(size_t)*single] = true;
+        return s;
+    }
+
+    CharSet charClass() {
+        pos++; /* [ */
+        bool negate = false;
+        if (at('^')) {
+            negate = true;
+            pos++;
+        }
+        CharSet set;
+        bool first = true;
+        int prev = -1;
+        for (;; first = false) {
+            if (pos >= n) {
+                fail("Unterminated character class.");
+            }
+            const unsigned char c = (unsigned char)re[pos];
+            if (c == ']' && !first) {
+                pos++;
+                break;
+            }
+            if (c == '[' && pos + 1 < n && (re[pos + 1] == ':' || re[pos + 1] == '.' || re[pos + 1] == '=')) {
+                fail("POSIX character classes are not supported.");
+            }
+            if (c == '-' && prev >= 0 && pos + 1 < n && re[pos + 1] != ']') {
+                pos++;
+                int hi;
+                if (re[pos] == '\\') {
+                    escape(true, &hi);
+                    if (hi < 0) {
+                        fail("Invalid range in character class.");
+                    }
+                } else {
+                    hi = (unsigned char)re[pos++];
+                }
+                if (hi < prev) {
+                    fail("Invalid range in character class.");
+                }
+                for (int v = prev; v <= hi; v++) {
+                    set[(size_t)v] = true;
+                }
+                prev = -1;
+                continue;
+            }
+            if (c == '\\') {
+                int single;
+                const CharSet e = escape(true, &single);
+                set |= e;
+                prev = single;
+            } else {
+                set[c] = true;
+                prev = c;
+                pos++;
+            }
+        }
+        set = fold(set);
+        return negate ? ~set : set;
+    }
+
+    NodeP leaf(const CharSet &s) {
+        if (s.none()) {
+            fail("Empty character class.");
+        }
+        NodeP l = mk(Node::CLASS);
+        l->cls = s;
+        return l;
+    }
+
+    NodeP atom() {
+        const unsigned char c = (unsigned char)re[pos];
+        if (c == '(') {
+            pos++;
+            if (at('?')) {
+                if (pos + 1 < n && re[pos + 1] == ':') {
+                    pos += 2;
+                } else {
+                    fail("Group options, look-around and named groups are not supported.");
+                }
+            }
+            NodeP r = alt(false);
+            if (!at(')')) {
+                fail("Missing close parenthesis.");
+            }
+            pos++;
+            return r;
+        }
+        if (c == '[') {
+            return leaf(charClass());
+        }
+        if (c == '\\') {
+            int single;
+            CharSet s = escape(false, &single);
+            return leaf(single >= 0 ? fold(s) : s);
+        }
+        if (c == '.') {
+            pos++;
+            CharSet s;
+            s.set();
+            if (!(flags & HS_FLAG_DOTALL)) {
+                s['\n'] = false;
+            }
+            return leaf(s);
+        }
+        if (c == '$') {
+            fail("'$' needs the reference's end-of-data handling.");
+        }
+        if (c == '^') {
+            fail("'^' in the middle of an expression is not supported.");
+        }
+        if (strchr("*+?{", c)) {
+            fail("Invalid repeat: nothing to repeat.");
+        }
+        pos++;
+        CharSet s;
+        s[c] = true;
+        return leaf(fold(s));
+    }
+};
+
+/* Glushkov: positions, nullable / first / last / follow */
+struct Glushkov {
+    std::vector<CharSet> cls;         /* per position */
+    std::vector<u32> follow;          /* per position: bitmask over positions */
+    struct Sets {
+        bool nullable;
+        u32 first, last;
+    };
+
+    Sets build(const NodeP &n) {
+        switch (n->kind) {
+        case Node::EMPTY:
+            return {true, 0, 0};
+        case Node::CLASS: {
+            if (cls.size() >= 31) {
+                throw RegexError{"Pattern is too large: more than 31 character positions need the larger NFA models."};
+            }
+            const u32 p = (u32)cls.size();
+            cls.push_back(n->cls);
+            follow.push_back(0);
+            return {false, 1u << p, 1u << p};
+        }
+        case Node::CAT: {
+            Sets acc = {true, 0, 0};
+            for (const NodeP &k : n->kids) {
+                const Sets s = build(k);
+                link(acc.last, s.first);
+                const u32 first = acc.nullable ? (acc.first | s.first) : acc.first;
+                const u32 last = s.nullable ? (acc.last | s.last) : s.last;
+                acc = {acc.nullable && s.nullable, first, last};
+            }
+            return acc;
+        }
+        case Node::ALT: {
+            Sets acc = {false, 0, 0};
+            for (const NodeP &k : n->kids) {
+                const Sets s = build(k);
+                acc = {acc.nullable || s.nullable, acc.first | s.first, acc.last | s.last};
+            }
+            return acc;
+        }
+        case Node::STAR:
+        case Node::PLUS: {
+            const Sets s = build(n->kids[0]);
+            link(s.last, s.first);
+            return {n->kind == Node::STAR || s.nullable, s.first, s.last};
+        }
+        case Node::OPT: {
+            const Sets s = build(n->kids[0]);
+            return {true, s.first, s.last};
+        }
+        }
+        return {true, 0, 0};
+    }
+
+    void link(u32 from, u32 to) {
+        for (u32 p = 0; p < follow.size(); p++) {
+            if ((from >> p) & 1) {
+                follow[p] |= to;
+            }
+        }
+    }
+};
+
+u32 minLenOf(const NodeP &n) {
+    switch (n->kind) {
+    case Node::EMPTY: return 0;
+    case Node::CLASS: return 1;
+    case Node::CAT: {
+        u32 s = 0;
+        for (const NodeP &k : n->kids) s += minLenOf(k);
+        return s;
+    }
+    case Node::ALT: {
+        u32 m = ~0u;
+        for (const NodeP &k : n->kids) m = std::min(m, minLenOf(k));
+        return m;
+    }
+    case Node::PLUS: return minLenOf(n->kids[0]);
+    case Node::STAR:
+    case Node::OPT: return 0;
+    }
+    return 0;
+}
+
+u64 maxLenOf(const NodeP &n) { /* > 0xfffffffe = unbounded */
+    const u64 INF = 1ull << 40;
+    switch (n->kind) {
+    case Node::EMPTY: return 0;
+    case Node::CLASS: return 1;
+    case Node::CAT: {
+        u64 s = 0;
+        for (const NodeP &k : n->kids) s = std::min(INF, s + maxLenOf(k));
+        return s;
+    }
+    case Node::ALT: {
+        u64 m = 0;
+        for (const NodeP &k : n->kids) m = std::max(m, maxLenOf(k));
+        return m;
+    }
+    case Node::PLUS:
+    case Node::STAR: return maxLenOf(n->kids[0]) ? INF : 0;
+    case Node::OPT: return maxLenOf(n->kids[0]);
+    }
+    return 0;
+}
+
+/* top-level alternatives of the expression, each with its anchored flag */
+std::vector<NodeP> topArms(const NodeP &root) {
+    if (root->kind == Node::ALT) {
+        return root->kids;
+    }
+    return {root};
+}
+
+} // namespace
+
+RegexInfo regexInfo(const char *re, unsigned flags) {
+    const NodeP root = Parser(re, flags).parse();
+    Glushkov g;
+    RegexInfo info;
+    info.minLen = ~0u;
+    for (const NodeP &arm : topArms(root)) {
+        const Glushkov::Sets s = g.build(arm);
+        if (s.nullable) {
+            throw RegexError{"Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY to enable support."};
+        }
+        info.minLen = std::min(info.minLen, minLenOf(arm));
+        const u64 mx = maxLenOf(arm);
+        info.maxLen = std::max<u32>(info.maxLen, mx > 0xfffffffeull ? 0xffffffffu : (u32)mx);
+    }
+    info.positions = (u32)g.cls.size();
+    return info;
+}
+
+void regexNfaInit(RawNfa32 *nfa) {
+    *nfa = RawNfa32();
+    nfa->nstates = 2; /* 0 = floating start (.* loop), 1 = anchored start (offset 0 only) */
+    nfa->succ.assign(2, 0);
+    nfa->succ[0] = 1u;
+    nfa->squashMask.assign(2, 0xffffffffu);
+    nfa->squashKind.assign(2, LIMEX_SQUASH_NONE);
+    nfa->reports.resize(2);
+    nfa->reportsEod.resize(2);
+    for (u32 b = 0; b < 256; b++) {
+        nfa->reach[b] = 1u; /* the floating start survives every byte; nothing re-enters state 1 */
+    }
+    nfa->init = nfa->initDS = 3u;
+}
+
+void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report) {
+    const NodeP root = Parser(re, flags).parse();
+    for (const NodeP &arm : topArms(root)) {
+        Glushkov g;
+        const Glushkov::Sets s = g.build(arm);
+        if (s.nullable) {
+            throw RegexError{"Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY to enable support."};
+        }
+        const u32 base = nfa->nstates;
+        const u32 np = (u32)g.cls.size();
+        if (base + np > 32) {
+            throw RegexError{"Pattern set is too large: its character positions exceed the 32-state NFA model."};
+        }
+        nfa->nstates += np;
+        nfa->succ.resize(nfa->nstates, 0);
+        nfa->squashMask.resize(nfa->nstates, 0xffffffffu);
+        nfa->squashKind.resize(nfa->nstates, LIMEX_SQUASH_NONE);
+        nfa->reports.resize(nfa->nstates);
+        nfa->reportsEod.resize(nfa->nstates);
+        const bool anchored = arm->kind == Node::CAT && arm->anchored;
+        nfa->succ[anchored ? 1 : 0] |= s.first << base;
+        for (u32 p = 0; p < np; p++) {
+            nfa->succ[base + p] = g.follow[p] << base;
+            for (u32 b = 0; b < 256; b++) {
+                if (g.cls[p][b]) {
+                    nfa->reach[b] |= 1u << (base + p);
+                }
+            }
+            if ((s.last >> p) & 1) {
+                nfa->reports[base + p].push_back(report);
+            }
+        }
+    }
+}
+
+} // namespace hsb

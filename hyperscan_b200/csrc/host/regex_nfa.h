@@ -1,0 +1,49 @@
+/*
+ * regex_nfa.h -- small regular expressions to a LimEx-32 NFA: the position (Glushkov)
+ * automaton the reference builds for its NFA engines (src/nfagraph/ng_builder.cpp,
+ * src/parser/buildstate.cpp: one state per character position, epsilon free), for
+ * expression sets whose positions fit the 32-state model together with the start states.
+ *
+ * Syntax (PCRE as the reference's parser accepts it, src/parser/Parser.rl): literal
+ * characters and escapes (\n \t \r \f \a \e \xHH, escaped punctuation), the class escapes
+ * \d \D \w \W \s \S, "." (any byte but \n; any byte under HS_FLAG_DOTALL), character
+ * classes with ranges, negation and class escapes, groups "(...)" / "(?:...)" (Hyperscan
+ * does not capture), alternation, the quantifiers ? * + {n} {n,} {n,m} (a lazy "?" suffix
+ * changes nothing when every match end is reported), "^" at the start of the expression
+ * or of a top-level alternative.  HS_FLAG_CASELESS folds letters.  Everything else --
+ * "$", \b, look-around, back-references, possessive quantifiers, UTF-8 / UCP, SOM,
+ * multi-line anchors, expressions that match the empty string -- is refused with a compile
+ * error: those need parts of the reference's compiler and runtime this build does not have.
+ */
+#ifndef HSB200_REGEX_NFA_H
+#define HSB200_REGEX_NFA_H
+
+#include <string>
+#include <vector>
+
+#include "limex_build.h"
+
+namespace hsb {
+
+struct RegexError {
+    std::string msg;
+};
+
+struct RegexInfo {
+    u32 minLen = 0;      /* length of the shortest match */
+    u32 maxLen = 0;      /* of the longest; 0xffffffff = unbounded (hs_expr_info_t.max_width convention) */
+    u32 positions = 0;   /* character positions of the expression */
+};
+
+/* Number of positions / shortest match of one expression (throws RegexError). */
+RegexInfo regexInfo(const char *re, unsigned flags);
+
+/* Add the expression's position automaton to `nfa`: its accepting positions raise `report`.
+ * State 0 of `nfa` is the floating start (always on), state 1 the anchored start (on at
+ * offset 0 only); call regexNfaInit first.  Throws RegexError, also when the 32 states
+ * are exceeded. */
+void regexNfaInit(RawNfa32 *nfa);
+void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report);
+
+} // namespace hsb
+#endif

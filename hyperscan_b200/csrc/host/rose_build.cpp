@@ -24,6 +24,8 @@
 #include "rose_build.h"
 #include "dfa_build.h"
 #include "limex_build.h"
+#include "regex_nfa.h"
+#include "../../../include/hs_b200.h"
 
 #include <algorithm>
 #include <cstring>
@@ -644,6 +646,120 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
         }
     }
     return finishRose(blob, hl, t, opts, info);
+}
+
+std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const CompileOpts &opts) {
+    if (pats.empty()) {
+        throw CompileError{"Invalid parameter: elements is zero", -1};
+    }
+    if (opts.streaming) {
+        throw CompileError{"Expressions that need an NFA engine are compiled for block mode only in this build.", -1};
+    }
+    /* report keys: one exhaustion key per HS_FLAG_SINGLEMATCH report id; one dedupe key per report
+     * id, always -- several accepting positions (or expressions) may raise one id at one offset and
+     * the reference delivers a report once (dedupe, src/report.h:55-119) */
+    std::map<u32, std::pair<bool, u32>> highlander;
+    std::map<u32, u32> ekeys, dkeys;
+    bool allHighlander = true;
+    for (const RegexPattern &p : pats) {
+        const bool single = (p.flags & HS_FLAG_SINGLEMATCH) != 0;
+        auto it = highlander.find(p.report);
+        if (it == highlander.end()) {
+            highlander[p.report] = {single, p.index};
+        } else if (it->second.first != single) {
+            std::string m = "Expression (index " + std::to_string(p.index) + ") with match ID " +
+                            std::to_string(p.report) + " ";
+            m += single ? "specified " : "did not specify ";
+            m += "HS_FLAG_SINGLEMATCH whereas previous expression (index " + std::to_string(it->second.second) +
+                 ") with the same match ID did";
+            m += single ? " not." : ".";
+            throw CompileError{m, (int)p.index};
+        }
+        if (single) {
+            ekeys.emplace(p.report, (u32)ekeys.size());
+        } else {
+            allHighlander = false;
+        }
+        dkeys.emplace(p.report, (u32)dkeys.size());
+    }
+    Blob blob((u32)HSB_ROUNDUP(sizeof(RoseEngine), 64));
+    RawNfa32 nfa;
+    regexNfaInit(&nfa);
+    u32 minLen = ~0u;
+    std::map<u32, u32> progOf; /* report id -> its report program */
+    for (const RegexPattern &p : pats) {
+        u32 prog;
+        auto pit = progOf.find(p.report);
+        if (pit != progOf.end()) {
+            prog = pit->second;
+        } else {
+            const bool single = (p.flags & HS_FLAG_SINGLEMATCH) != 0;
+            u32 sz = instrSize<InstrEnd>();
+            sz += single ? instrSize<InstrCheckExhausted>() + instrSize<InstrDedupe>() + instrSize<InstrReportExhaust>()
+                         : instrSize<InstrDedupeAndReport>();
+            u32 pc = blob.reserve(sz, INSTR_ALIGN);
+            prog = pc;
+            const u32 endAt = pc + sz - instrSize<InstrEnd>();
+            if (single) {
+                InstrCheckExhausted ce;
+                memset(&ce, 0, sizeof(ce));
+                ce.code = OP_CHECK_EXHAUSTED;
+                ce.ekey = ekeys[p.report];
+                ce.fail_jump = endAt - pc;
+                memcpy(blob.at(pc), &ce, sizeof(ce));
+                pc += instrSize<InstrCheckExhausted>();
+                InstrDedupe dd;
+                memset(&dd, 0, sizeof(dd));
+                dd.code = OP_DEDUPE;
+                dd.dkey = dkeys[p.report];
+                dd.fail_jump = endAt - pc;
+                memcpy(blob.at(pc), &dd, sizeof(dd));
+                pc += instrSize<InstrDedupe>();
+                InstrReportExhaust re;
+                memset(&re, 0, sizeof(re));
+                re.code = OP_REPORT_EXHAUST;
+                re.onmatch = p.report;
+                re.ekey = ekeys[p.report];
+                memcpy(blob.at(pc), &re, sizeof(re));
+            } else {
+                InstrDedupeAndReport dr;
+                memset(&dr, 0, sizeof(dr));
+                dr.code = OP_DEDUPE_AND_REPORT;
+                dr.dkey = dkeys[p.report];
+                dr.onmatch = p.report;
+                dr.fail_jump = endAt - pc;
+                memcpy(blob.at(pc), &dr, sizeof(dr));
+            }
+            InstrEnd e;
+            e.code = OP_END;
+            memcpy(blob.at(endAt), &e, sizeof(e));
+            progOf[p.report] = prog;
+        }
+        try {
+            minLen = std::min(minLen, regexInfo(p.re.c_str(), p.flags).minLen);
+            regexNfaAdd(&nfa, p.re.c_str(), p.flags, prog);
+        } catch (const RegexError &e) {
+            throw CompileError{e.msg, (int)p.index};
+        }
+    }
+    RoseTail t;
+    t.minLen = minLen;
+    t.maxLen = 0;
+    t.ekeyCount = (u32)ekeys.size();
+    t.dkeyCount = (u32)dkeys.size();
+    std::vector<u32> inv(dkeys.size());
+    for (const auto &d : dkeys) {
+        inv[d.second] = d.first;
+    }
+    t.invDkeyOffset = blob.add(inv.data(), inv.size() * sizeof(u32), 4);
+    t.canExhaust = allHighlander;
+    std::vector<u8> eng;
+    try {
+        eng = emitLimEx32(nfa);
+    } catch (const std::runtime_error &e) {
+        throw CompileError{std::string("Unable to build the NFA: ") + e.what(), -1};
+    }
+    return finishOutfixRose(blob, eng, t, opts);
 }
 
 /* Test hook (hs_b200_test_compile_programs): a pure-literal block database whose

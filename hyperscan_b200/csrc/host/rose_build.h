@@ -53,6 +53,16 @@ static const size_t LIMIT_LITERAL_COUNT = 8000000;
 std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &pats,
                                  const CompileOpts &opts, HwlmBuildInfo *info);
 
+/** Expressions that need an NFA (regex_nfa.h): ONE LimEx-32 engine over all of them, run as the
+ * database's single outfix (ROSE_RUNTIME_SINGLE_OUTFIX).  Block mode only.  Throws CompileError. */
+struct RegexPattern {
+    std::string re;
+    unsigned flags = 0;
+    u32 report = 0;
+    u32 index = 0;
+};
+std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const CompileOpts &opts);
+
 /** Test hook: pure-literal block database from raw literal programs (`area`
  * is placed at programAreaBase(); lits[i].id = its program's offset in area). */
 u32 programAreaBase();

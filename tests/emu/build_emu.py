@@ -14,7 +14,7 @@ SANITIZE = os.environ.get("HSB_EMU_SANITIZE") == "1"
 OUT_DIR = os.path.join(HERE, "_build_asan" if SANITIZE else "_build")
 OUT = os.path.join(OUT_DIR, "libhs_b200_simt_emu.so")
 HOST = ["host/api_host.cpp", "host/rose_build.cpp", "host/hwlm_build.cpp", "host/db_walk.cpp",
-        "host/pair_table.cpp", "host/dfa_build.cpp", "host/limex_build.cpp"]
+        "host/pair_table.cpp", "host/dfa_build.cpp", "host/limex_build.cpp", "host/regex_nfa.cpp"]
 DEVICE = ["device/scan_kernels.cu", "device/api_device.cu", "device/accel_kernels.cu", "device/dfa_kernels.cu"]
 
 

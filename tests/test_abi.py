@@ -55,7 +55,7 @@ def test_compile_arg_checks(hs):
     assert L.hs_compile(b"foo", 0, hs.HS_MODE_BLOCK, None, C.byref(db), None) == hs.HS_COMPILER_ERROR
     # unsupported construct reports the expression index
     with pytest.raises(hs.HsError) as e:
-        hs.compile_multi([b"abc", b"a.*b"])
+        hs.compile_multi([b"abc", b"a.*b$"])             # "$" is beyond both the literal and the NFA route
     assert e.value.expression == 1
     with pytest.raises(hs.HsError):
         hs.compile_lit_multi([b""])
@@ -188,7 +188,10 @@ def test_expression_info(hs):
     assert (info.contents.min_width, info.contents.max_width) == (7, 7)
     assert info.contents.unordered_matches == b"\0" and info.contents.matches_at_eod == b"\0"
     C.CDLL(None).free(info)
-    assert L.hs_expression_info(b"foo.*bar", 0, C.byref(info), C.byref(err)) == hs.HS_COMPILER_ERROR
+    assert L.hs_expression_info(b"foo.*bar", 0, C.byref(info), C.byref(err)) == 0      # NFA route: widths known
+    assert (info.contents.min_width, info.contents.max_width) == (6, 0xffffffff)
+    C.CDLL(None).free(info)
+    assert L.hs_expression_info(b"foo.*bar$", 0, C.byref(info), C.byref(err)) == hs.HS_COMPILER_ERROR
     assert err and err.contents.message
     L.hs_free_compile_error(err)
     assert L.hs_expression_info(None, 0, C.byref(info), C.byref(err)) == hs.HS_COMPILER_ERROR
@@ -224,12 +227,12 @@ def test_finite_language_expressions(hs, ref, pat, caseless):
 
 
 def test_finite_language_limits_and_errors(hs):
-    for bad, why in [(rb"a*", "Unbounded"), (rb"a+b", "Unbounded"), (rb"a.b", "Metacharacter"),
-                     (rb"^ab", "Metacharacter"), (rb"ab$", "Metacharacter"), (rb"[^a]b", "Negated"),
-                     (rb"a{2,}", "Unbounded"), (rb"(?i)ab", "Group option"), (rb"a|", "empty buffer"),
-                     (rb"(ab", "parenthesis"), (rb"ab)", "parentheses"), (rb"\d+", "Escape sequence"),
-                     (rb"a??", "Lazy"), (rb"[[:alpha:]]", "POSIX"), (rb"[a-z]{4}", "4096"),
-                     (rb"a{3,2}", "min > max"), (rb"*a", "nothing to repeat"), (rb"[ab", "Unterminated")]:
+    # (expressions with unbounded repeats, ".", "^", negated classes or class escapes are no longer errors:
+    # they compile through the NFA route, tests/test_regex.py)
+    for bad, why in [(rb"a*", "empty buffer"), (rb"ab$", "'$'"), (rb"(?i)ab", "Group options"), (rb"a|", "empty buffer"),
+                     (rb"(ab", "parenthesis"), (rb"ab)", "parentheses"), (rb"a\bc", "Escape sequence"),
+                     (rb"a??", "empty buffer"), (rb"[[:alpha:]]", "POSIX"), (rb"a{3,2}", "min > max"),
+                     (rb"*a", "nothing to repeat"), (rb"[ab", "Unterminated"), (rb"[a-z]{33}x+", "too large")]:
         with pytest.raises(hs.HsError) as e:
             hs.compile_multi([b"ok", bad])
         assert why in e.value.message, (bad, e.value.message)
@@ -245,4 +248,7 @@ def test_finite_language_limits_and_errors(hs):
     err = C.POINTER(hs.CompileError)()
     assert L.hs_expression_info(rb"x?(foo){2,3}bar", 0, C.byref(info), C.byref(err)) == 0
     assert (info.contents.min_width, info.contents.max_width) == (9, 13)
+    C.CDLL(None).free(info)
+    assert L.hs_expression_info(rb"ab+c?|x{2,4}y", 0, C.byref(info), C.byref(err)) == 0
+    assert (info.contents.min_width, info.contents.max_width) == (2, 0xffffffff)
     C.CDLL(None).free(info)

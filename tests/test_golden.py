@@ -88,3 +88,19 @@ def test_oracle_reproduces_hscollider_vectors(hs, case):
     db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
     data, off, ln, ends = _collider_blocks(case)
     _check_collider(case, port.scan_sorted(db.ptr, data, off, ln), ends)
+
+
+# --- ... and for expressions that take the NFA route (regex_nfa.cpp -> LimEx-32 -> single-outfix database) --
+# tests/golden/hscollider_regex.json (tests/golden/gen_hscollider_regex.py): 398 patterns / 4 824 corpora of the
+# same suite that are NOT a finite set of literals and fit the 32-state model.  The checker here is the unmodified
+# reference runtime scanning the database this compiler emits.
+with open(os.path.join(ROOT, "tests", "golden", "hscollider_regex.json")) as f:
+    COLLIDER_REGEX = json.load(f)["cases"]
+
+
+@pytest.mark.parametrize("case", COLLIDER_REGEX, ids=[str(c["id"]) for c in COLLIDER_REGEX])
+def test_reference_runtime_reproduces_hscollider_regex_vectors(hs, ref, case):
+    db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+    assert db.info().runtime_impl == 2
+    data, off, ln, ends = _collider_blocks(case)
+    _check_collider(case, ref.scan_sorted(db.ptr, data, off, ln), ends)

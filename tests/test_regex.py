@@ -1,0 +1,121 @@
+"""Expressions that are not a finite set of literals: hs_compile* builds their position
+(Glushkov) automaton as ONE LimEx-32 NFA and wraps it in a single-outfix database
+(hyperscan_b200/csrc/host/regex_nfa.cpp, rose_build.cpp buildRegexRose).
+
+CPU half: the UNMODIFIED reference hs_scan scanning those databases reports exactly the
+match ends the definition gives -- every end offset e such that some data[s:e] is in the
+expression's language (Hyperscan reports all match ends, doc/dev-reference/compilation.rst
+"Semantics"), computed with Python's re.fullmatch -- which pins the compiler; the recorded
+vectors of the reference's own regression suite are in test_zz_recorded_vectors_gpu.py.
+GPU half: this runtime's hs_scan / scan_blocks on the same database against the reference."""
+import re
+
+import numpy as np
+import pytest
+
+from hyperscan_b200 import synth
+
+CASELESS, DOTALL, SINGLE = 1, 2, 8
+PATTERNS = [
+    (rb"ab+c", 0), (rb"a[bc]*d", 0), (rb"x.y", 0), (rb"x.y", DOTALL), (rb"\d+\.\d\d", 0), (rb"^abc", 0),
+    (rb"(ab|cd)+e", 0), (rb"[^a-z]{2,3}q", 0), (rb"fo{1,}d?", CASELESS), (rb"a(bc)?d|x+y", 0),
+    (rb"^a.*b", DOTALL), (rb"\w+@\w+", 0), (rb"[a-c]{3}", 0), (rb"q\s*=\s*\d", 0), (rb"(?:ab){2,}c", 0),
+    (rb"a+?b", 0), (rb"^x|y\x41z", 0), (rb"[\d\-x]+y", 0), (rb"a.{2,4}b", 0), (rb"\Sq\S", CASELESS),
+]
+ALPHA = b"abcdxyqAB.12e\nfoFOD =@-_z"
+SEED_TEXT = b"abc abbcd acbd x\ny 3.14 ababe 12q fOOd ad xxy a\nb u_1@v2 cab q = 7 ababababc aab yAz 1-x2y a123b .q, "
+
+
+def _ends(pat, flags, data):
+    rx = re.compile(pat, (re.I if flags & CASELESS else 0) | (re.S if flags & DOTALL else 0))
+    return sorted({e for s in range(len(data) + 1) for e in range(s + 1, len(data) + 1) if rx.fullmatch(data, s, e)})
+
+
+def _data(seed, n=48):
+    rng = np.random.default_rng(seed)
+    a = np.frombuffer(ALPHA, dtype=np.uint8)
+    return a[rng.integers(0, a.size, size=n)].tobytes()
+
+
+def _ref_ends(ref, db, data):
+    a = np.frombuffer(data, dtype=np.uint8) if data else np.zeros(0, np.uint8)
+    r = ref.scan_sorted(db.ptr, a, np.array([0], np.uint64), np.array([len(data)], np.uint32))
+    return [(int(x["id"]), int(x["to"])) for x in r]
+
+
+@pytest.mark.parametrize("pi", range(len(PATTERNS)))
+def test_reference_hs_scan_on_compiled_expressions_equals_definition(hs, ref, pi):
+    pat, fl = PATTERNS[pi]
+    db = hs.compile_multi([pat], [fl], [7])
+    assert db.info().runtime_impl == (1 if pat == rb"[a-c]{3}" else 2)   # single outfix, unless the language is finite
+    hits = 0
+    for seed in range(10):
+        data = (SEED_TEXT if seed == 0 else b"") + _data(100 * pi + seed)
+        want = [(7, e) for e in _ends(pat, fl, data)]
+        assert _ref_ends(ref, db, data) == want, (pat, data)
+        hits += len(want)
+    assert hits > 0
+
+
+def test_several_expressions_share_one_nfa_and_report_rules_hold(hs, ref):
+    pats = [rb"ab+", rb"b+c", rb"[xy]z", rb"a.c"]
+    flags = [0, 0, SINGLE, 0]
+    ids = [1, 1, 2, 3]
+    db = hs.compile_multi(pats, flags, ids)
+    for seed in range(8):
+        data = _data(900 + seed, 80) + b"abbbc xz yz"
+        want = set()
+        for p, f, i in zip(pats, flags, ids):
+            e = _ends(p, f, data)
+            want |= {(i, x) for x in (e[:1] if f & SINGLE else e)}   # SINGLEMATCH: the first match only
+        assert sorted(_ref_ends(ref, db, data), key=lambda t: (t[1], t[0])) == sorted(want, key=lambda t: (t[1], t[0]))
+
+
+@pytest.mark.parametrize("pat,msg", [
+    (rb"a*", "empty"), (rb"ab$", "'$'"), (rb"\bab", "Escape"), (rb"(?=a)b", "look-around"), (rb"a++b", "Possessive"),
+    (rb"(a|b)\1", "Escape"), (rb"[a-z]{40}x+", "too large"), (rb"abcdefghijklmnopqrstuvwxyz0123456+", "too large")])
+def test_what_the_nfa_route_refuses(hs, pat, msg):
+    with pytest.raises(hs.HsError) as e:
+        hs.compile_multi([pat], [0], [1])
+    assert msg.lower() in str(e.value).lower()
+
+
+def test_nfa_route_is_block_mode_only_and_literal_sets_are_untouched(hs):
+    with pytest.raises(hs.HsError):
+        hs.compile_multi([rb"ab+c"], [0], [1], mode=hs.HS_MODE_STREAM)
+    assert hs.compile_multi([rb"ab(c|d)e"], [0], [1]).info().runtime_impl == 1    # finite: pure literal as before
+
+
+# ---- device --------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pi", range(len(PATTERNS)))
+def test_device_scans_compiled_expressions(hs, ref, pi):
+    pat, fl = PATTERNS[pi]
+    db = hs.compile_multi([pat], [fl], [7])
+    scratch = hs.Scratch(db)
+    lens = [0, 1, 2, 3, 17, 64, 100, 1000, 1024, 1025]
+    rng = np.random.default_rng(pi)
+    a = np.frombuffer(ALPHA, dtype=np.uint8)
+    data, off, ln = synth.ragged_corpus(lens, None, seed=pi, plant_per_kb=0)
+    data = a[rng.integers(0, a.size, size=data.size)].astype(np.uint8)
+    want = ref.scan_sorted(db.ptr, data, off, ln)
+    got = np.sort(hs.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
+    assert np.array_equal(got, want)
+    b = 8
+    buf = data[int(off[b]):int(off[b]) + int(ln[b])].tobytes()
+    rc, out = hs.scan(db, buf, scratch)
+    assert rc == hs.HS_SUCCESS and sorted(out) == sorted((int(r["id"]), int(r["to"])) for r in want[want["block"] == b])
+    scratch.free()
+
+
+@pytest.mark.gpu
+def test_device_expression_set_with_report_rules(hs, ref):
+    pats = [rb"ab+", rb"b+c", rb"[xy]z", rb"a.c", rb"\d{2,}"]
+    db = hs.compile_multi(pats, [0, 0, SINGLE, 0, CASELESS], [1, 1, 2, 3, 4])
+    data, off, ln, _ = synth.block_corpus(512, 512, [b"abbbc", b"xz", b"a1c22"], plant_per_kb=8.0, seed=3)
+    want = ref.scan_sorted(db.ptr, data, off, ln)
+    scratch = hs.Scratch(db)
+    got = np.sort(hs.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
+    assert np.array_equal(got, want) and want.size > 500
+    scratch.free()

@@ -1,5 +1,5 @@
-"""The reference's recorded hscollider vectors (tests/golden/hscollider_literals.json,
-tests/golden/gen_hscollider_literals.py) through the CUDA path.  The CPU half (C oracle
+"""The reference's recorded hscollider vectors (tests/golden/hscollider_literals.json and
+hscollider_regex.json, tests/golden/gen_hscollider_*.py) through the CUDA path.  The CPU half (C oracle
 against the same fixture) is in tests/test_golden.py; this file sorts last on
 purpose: it is the widest sweep over compiler-accepted expressions (groups,
 alternation, classes, bounded repeats -> many literals under one id)."""
@@ -8,11 +8,14 @@ import base64
 import numpy as np
 import pytest
 
-from test_golden import COLLIDER, _check_collider, _collider_blocks
+from test_golden import COLLIDER, COLLIDER_REGEX, _check_collider, _collider_blocks
+
+
+ALL_CASES = COLLIDER + COLLIDER_REGEX   # literal route, then the NFA route (LimEx-32 single-outfix databases)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", COLLIDER, ids=[str(c["id"]) for c in COLLIDER])
+@pytest.mark.parametrize("case", ALL_CASES, ids=[str(c["id"]) for c in ALL_CASES])
 def test_cuda_path_reproduces_hscollider_vectors(hs, case):
     db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
     data, off, ln, ends = _collider_blocks(case)
