@@ -30,6 +30,7 @@ struct RawNfa32 {
     u32 nstates = 0;
     u32 reach[256] = {0};              /* states that may be ON after consuming the byte */
     u32 init = 0, initDS = 0;          /* switched on by a top at offset 0 / at a later offset */
+    u32 mlStartState = 0;              /* regex_nfa.cpp: the shared "after a newline" state, 0 = none yet */
     std::vector<u32> succ;             /* [state] successor set */
     std::vector<u32> squashMask;       /* [state] kept states when the exception's squash applies */
     std::vector<u8> squashKind;        /* [state] LIMEX_SQUASH_NONE / _CYCLIC / _REPORT */

@@ -18,7 +18,9 @@ struct Node {
     enum Kind { CLASS, CAT, ALT, STAR, PLUS, OPT, EMPTY } kind = EMPTY;
     CharSet cls;
     std::vector<std::shared_ptr<Node>> kids;
-    bool anchored = false; /* top-level alternative that starts with "^" */
+    bool anchored = false; /* top-level alternative that starts with "^" / "\\A" */
+    bool mlStart = false;  /* ... with "^" under HS_FLAG_MULTILINE: at offset 0 or right after a newline */
+    enum End { END_NONE, END_EOD, END_DOLLAR, END_ML_DOLLAR } end = END_NONE; /* "\\z" | "$", "\\Z" | "$" under (?m) */
 };
 typedef std::shared_ptr<Node> NodeP;
 
@@ -46,6 +48,19 @@ public:
         }
         if (flags & HS_FLAG_SOM_LEFTMOST) {
             fail("HS_FLAG_SOM_LEFTMOST is not supported.");
+        }
+        /* leading option group "(?ism)": as if the flags had been passed */
+        if (n >= 4 && re[0] == '(' && re[1] == '?') {
+            size_t q = 2;
+            unsigned add = 0;
+            while (q < n && (re[q] == 'i' || re[q] == 's' || re[q] == 'm')) {
+                add |= re[q] == 'i' ? HS_FLAG_CASELESS : re[q] == 's' ? HS_FLAG_DOTALL : HS_FLAG_MULTILINE;
+                q++;
+            }
+            if (q > 2 && q < n && re[q] == ')') {
+                flags |= add;
+                pos = q + 1;
+            }
         }
         NodeP r = alt(true);
         if (pos != n) {
@@ -90,17 +105,37 @@ private:
 
     NodeP seq(bool top) {
         NodeP s = mk(Node::CAT);
-        if (at('^')) {
+        if (at('^') || (at('\\') && pos + 1 < n && re[pos + 1] == 'A')) {
             if (!top) {
                 fail("'^' inside a group needs the reference's assertion handling.");
             }
-            if (flags & HS_FLAG_MULTILINE) {
-                fail("'^' under HS_FLAG_MULTILINE is not supported.");
+            if (re[pos] == '^' && (flags & HS_FLAG_MULTILINE)) {
+                s->mlStart = true;
+            } else {
+                s->anchored = true;
             }
-            pos++;
-            s->anchored = true;
+            pos += re[pos] == '^' ? 1 : 2;
         }
         while (pos < n && re[pos] != '|' && re[pos] != ')') {
+            /* end anchors: only as the last thing of a top-level alternative */
+            Node::End e = Node::END_NONE;
+            size_t len = 0;
+            if (re[pos] == '$') {
+                e = (flags & HS_FLAG_MULTILINE) ? Node::END_ML_DOLLAR : Node::END_DOLLAR;
+                len = 1;
+            } else if (re[pos] == '\\' && pos + 1 < n && (re[pos + 1] == 'z' || re[pos + 1] == 'Z')) {
+                e = re[pos + 1] == 'z' ? Node::END_EOD : Node::END_DOLLAR;
+                len = 2;
+            }
+            if (e != Node::END_NONE) {
+                if (!top || (pos + len < n && re[pos + len] != '|')) {
+                    fail("'$' / \\z / \\Z anywhere but at the end of the expression or of a top-level alternative "
+                         "needs the reference's assertion handling.");
+                }
+                pos += len;
+                s->end = e;
+                break;
+            }
             NodeP a = atom();
             a = quantified(a);
             s->kids.push_back(a);
@@ -222,6 +257,30 @@ private:
         return (e >= 'A' && e <= 'Z') ? ~s : s;
     }
 
+    static bool posixClass(const std::string &name, CharSet *out) { /* C locale, as PCRE */
+        static const struct { const char *n; int (*f)(int); } tab[] = {
+            {"alpha", isalpha}, {"digit", isdigit}, {"alnum", isalnum}, {"upper", isupper}, {"lower", islower},
+            {"space", isspace}, {"punct", ispunct}, {"print", isprint}, {"graph", isgraph}, {"cntrl", iscntrl},
+            {"xdigit", isxdigit}, {"blank", isblank}};
+        for (const auto &t : tab) {
+            if (name == t.n) {
+                for (int c = 0; c < 128; c++) {
+                    if (t.f(c)) (*out)[(size_t)c] = true;
+                }
+                return true;
+            }
+        }
+        if (name == "word") {
+            *out = classEscape('w');
+            return true;
+        }
+        if (name == "ascii") {
+            for (int c = 0; c < 128; c++) (*out)[(size_t)c] = true;
+            return true;
+        }
+        return false;
+    }
+
     /* an escape: either one character (*single) or a class */
     CharSet escape(bool inClass, int *single) {
         *single = -1;
@@ -281,8 +340,29 @@ private:
                 pos++;
                 break;
             }
-            if (c == '[' && pos + 1 < n && (re[pos + 1] == ':' || re[pos + 1] == '.' || re[pos + 1] == '=')) {
-                fail("POSIX character classes are not supported.");
+            if (c == '[' && pos + 1 < n && re[pos + 1] == ':') {
+                const char *close = strstr(re + pos + 2, ":]");
+                if (!close) {
+                    fail("Unterminated POSIX character class.");
+                }
+                std::string name(re + pos + 2, close);
+                bool neg = false;
+                if (!name.empty() && name[0] == '^') {
+                    neg = true;
+                    name.erase(0, 1);
+                }
+                CharSet pc;
+                if (!posixClass(name, &pc)) {
+                    fail("Unknown POSIX character class.");
+                }
+                pc = fold(pc); /* under CASELESS [:upper:] and [:lower:] are all letters, THEN the "^" applies */
+                set |= neg ? ~pc : pc;
+                pos = (size_t)(close - re) + 2;
+                prev = -1;
+                continue;
+            }
+            if (c == '[' && pos + 1 < n && (re[pos + 1] == '.' || re[pos + 1] == '=')) {
+                fail("POSIX collating elements are not supported.");
             }
             if (c == '-' && prev >= 0 && pos + 1 < n && re[pos + 1] != ']') {
                 pos++;
@@ -507,6 +587,7 @@ RegexInfo regexInfo(const char *re, unsigned flags) {
             throw RegexError{"Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY to enable support."};
         }
         info.minLen = std::min(info.minLen, minLenOf(arm));
+        info.needsAdjust |= arm->end == Node::END_DOLLAR || arm->end == Node::END_ML_DOLLAR;
         const u64 mx = maxLenOf(arm);
         info.maxLen = std::max<u32>(info.maxLen, mx > 0xfffffffeull ? 0xffffffffu : (u32)mx);
     }
@@ -529,7 +610,7 @@ void regexNfaInit(RawNfa32 *nfa) {
     nfa->init = nfa->initDS = 3u;
 }
 
-void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report) {
+void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline) {
     const NodeP root = Parser(re, flags).parse();
     for (const NodeP &arm : topArms(root)) {
         Glushkov g;
@@ -548,17 +629,67 @@ void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report) {
         nfa->squashKind.resize(nfa->nstates, LIMEX_SQUASH_NONE);
         nfa->reports.resize(nfa->nstates);
         nfa->reportsEod.resize(nfa->nstates);
-        const bool anchored = arm->kind == Node::CAT && arm->anchored;
-        nfa->succ[anchored ? 1 : 0] |= s.first << base;
+        auto newState = [&]() -> u32 {
+            if (nfa->nstates >= 32) {
+                throw RegexError{"Pattern set is too large: its character positions exceed the 32-state NFA model."};
+            }
+            nfa->nstates++;
+            nfa->succ.push_back(0);
+            nfa->squashMask.push_back(0xffffffffu);
+            nfa->squashKind.push_back(LIMEX_SQUASH_NONE);
+            nfa->reports.emplace_back();
+            nfa->reportsEod.emplace_back();
+            return nfa->nstates - 1;
+        };
+        const bool isCat = arm->kind == Node::CAT;
+        if (isCat && arm->mlStart) {
+            /* "^" under (?m): entered at offset 0 (anchored start) or right after any newline --
+             * one state shared by all such alternatives, on after every '\n' */
+            if (!nfa->mlStartState) {
+                nfa->mlStartState = newState();
+                nfa->reach[(u8)'\n'] |= 1u << nfa->mlStartState;
+                nfa->succ[0] |= 1u << nfa->mlStartState;
+            }
+            nfa->succ[1] |= s.first << base;
+            nfa->succ[nfa->mlStartState] |= s.first << base;
+        } else {
+            nfa->succ[isCat && arm->anchored ? 1 : 0] |= s.first << base;
+        }
         for (u32 p = 0; p < np; p++) {
-            nfa->succ[base + p] = g.follow[p] << base;
+            nfa->succ[base + p] |= g.follow[p] << base;
             for (u32 b = 0; b < 256; b++) {
                 if (g.cls[p][b]) {
                     nfa->reach[b] |= 1u << (base + p);
                 }
             }
-            if ((s.last >> p) & 1) {
+        }
+        const Node::End end = isCat ? arm->end : Node::END_NONE;
+        u32 nl = 0;
+        if (end == Node::END_DOLLAR || end == Node::END_ML_DOLLAR) {
+            /* the expression's end may sit before a newline: a state for that newline, whose report is
+             * delivered one byte back (offset_adjust -1, as the reference compiles "$") */
+            if (!reportBeforeNewline) {
+                throw RegexError{"internal: no adjusted report program"};
+            }
+            nl = newState();
+            nfa->reach[(u8)'\n'] |= 1u << nl;
+            if (end == Node::END_DOLLAR) {
+                nfa->reportsEod[nl].push_back(reportBeforeNewline); /* ... only if that newline ends the data */
+            } else {
+                nfa->reports[nl].push_back(reportBeforeNewline);
+            }
+        }
+        for (u32 p = 0; p < np; p++) {
+            if (!((s.last >> p) & 1)) {
+                continue;
+            }
+            if (end == Node::END_NONE) {
                 nfa->reports[base + p].push_back(report);
+            } else {
+                nfa->reportsEod[base + p].push_back(report);
+                if (nl) {
+                    nfa->succ[base + p] |= 1u << nl;
+                }
             }
         }
     }

@@ -10,10 +10,14 @@
  * classes with ranges, negation and class escapes, groups "(...)" / "(?:...)" (Hyperscan
  * does not capture), alternation, the quantifiers ? * + {n} {n,} {n,m} (a lazy "?" suffix
  * changes nothing when every match end is reported), "^" at the start of the expression
- * or of a top-level alternative.  HS_FLAG_CASELESS folds letters.  Everything else --
- * "$", \b, look-around, back-references, possessive quantifiers, UTF-8 / UCP, SOM,
- * multi-line anchors, expressions that match the empty string -- is refused with a compile
- * error: those need parts of the reference's compiler and runtime this build does not have.
+ * or of a top-level alternative (\A likewise; under HS_FLAG_MULTILINE "^" also matches after any
+ * newline), "$" / \Z (end of data or before a final newline), \z (end of data), "$" under
+ * HS_FLAG_MULTILINE (before any newline or at the end) at the end of the expression or of a
+ * top-level alternative, POSIX classes inside classes, a leading "(?ism)".  HS_FLAG_CASELESS
+ * folds letters.  Everything else -- \b, look-around, back-references, possessive
+ * quantifiers, anchors inside groups, UTF-8 / UCP, SOM, expressions that match the empty
+ * string -- is refused with a compile error: those need parts of the reference's compiler and
+ * runtime this build does not have.
  */
 #ifndef HSB200_REGEX_NFA_H
 #define HSB200_REGEX_NFA_H
@@ -33,6 +37,7 @@ struct RegexInfo {
     u32 minLen = 0;      /* length of the shortest match */
     u32 maxLen = 0;      /* of the longest; 0xffffffff = unbounded (hs_expr_info_t.max_width convention) */
     u32 positions = 0;   /* character positions of the expression */
+    bool needsAdjust = false; /* an alternative ends in "$" / \Z: see regexNfaAdd */
 };
 
 /* Number of positions / shortest match of one expression (throws RegexError). */
@@ -43,7 +48,9 @@ RegexInfo regexInfo(const char *re, unsigned flags);
  * offset 0 only); call regexNfaInit first.  Throws RegexError, also when the 32 states
  * are exceeded. */
 void regexNfaInit(RawNfa32 *nfa);
-void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report);
+void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline = 0);
+/* reportBeforeNewline: the same report delivered one byte back (a report program with offset_adjust -1) --
+ * needed when RegexInfo.needsAdjust: "$" / \Z match before a final newline, "$" under (?m) before any */
 
 } // namespace hsb
 #endif

@@ -686,58 +686,63 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
     RawNfa32 nfa;
     regexNfaInit(&nfa);
     u32 minLen = ~0u;
-    std::map<u32, u32> progOf; /* report id -> its report program */
-    for (const RegexPattern &p : pats) {
-        u32 prog;
-        auto pit = progOf.find(p.report);
+    std::map<std::pair<u32, int>, u32> progOf; /* (report id, offset_adjust) -> its report program */
+    auto program = [&](const RegexPattern &p, int adjust) -> u32 {
+        auto pit = progOf.find({p.report, adjust});
         if (pit != progOf.end()) {
-            prog = pit->second;
-        } else {
-            const bool single = (p.flags & HS_FLAG_SINGLEMATCH) != 0;
-            u32 sz = instrSize<InstrEnd>();
-            sz += single ? instrSize<InstrCheckExhausted>() + instrSize<InstrDedupe>() + instrSize<InstrReportExhaust>()
-                         : instrSize<InstrDedupeAndReport>();
-            u32 pc = blob.reserve(sz, INSTR_ALIGN);
-            prog = pc;
-            const u32 endAt = pc + sz - instrSize<InstrEnd>();
-            if (single) {
-                InstrCheckExhausted ce;
-                memset(&ce, 0, sizeof(ce));
-                ce.code = OP_CHECK_EXHAUSTED;
-                ce.ekey = ekeys[p.report];
-                ce.fail_jump = endAt - pc;
-                memcpy(blob.at(pc), &ce, sizeof(ce));
-                pc += instrSize<InstrCheckExhausted>();
-                InstrDedupe dd;
-                memset(&dd, 0, sizeof(dd));
-                dd.code = OP_DEDUPE;
-                dd.dkey = dkeys[p.report];
-                dd.fail_jump = endAt - pc;
-                memcpy(blob.at(pc), &dd, sizeof(dd));
-                pc += instrSize<InstrDedupe>();
-                InstrReportExhaust re;
-                memset(&re, 0, sizeof(re));
-                re.code = OP_REPORT_EXHAUST;
-                re.onmatch = p.report;
-                re.ekey = ekeys[p.report];
-                memcpy(blob.at(pc), &re, sizeof(re));
-            } else {
-                InstrDedupeAndReport dr;
-                memset(&dr, 0, sizeof(dr));
-                dr.code = OP_DEDUPE_AND_REPORT;
-                dr.dkey = dkeys[p.report];
-                dr.onmatch = p.report;
-                dr.fail_jump = endAt - pc;
-                memcpy(blob.at(pc), &dr, sizeof(dr));
-            }
-            InstrEnd e;
-            e.code = OP_END;
-            memcpy(blob.at(endAt), &e, sizeof(e));
-            progOf[p.report] = prog;
+            return pit->second;
         }
+        const bool single = (p.flags & HS_FLAG_SINGLEMATCH) != 0;
+        u32 sz = instrSize<InstrEnd>();
+        sz += single ? instrSize<InstrCheckExhausted>() + instrSize<InstrDedupe>() + instrSize<InstrReportExhaust>()
+                     : instrSize<InstrDedupeAndReport>();
+        u32 pc = blob.reserve(sz, INSTR_ALIGN);
+        const u32 prog = pc;
+        const u32 endAt = pc + sz - instrSize<InstrEnd>();
+        if (single) {
+            InstrCheckExhausted ce;
+            memset(&ce, 0, sizeof(ce));
+            ce.code = OP_CHECK_EXHAUSTED;
+            ce.ekey = ekeys[p.report];
+            ce.fail_jump = endAt - pc;
+            memcpy(blob.at(pc), &ce, sizeof(ce));
+            pc += instrSize<InstrCheckExhausted>();
+            InstrDedupe dd;
+            memset(&dd, 0, sizeof(dd));
+            dd.code = OP_DEDUPE;
+            dd.dkey = dkeys[p.report];
+            dd.offset_adjust = adjust;
+            dd.fail_jump = endAt - pc;
+            memcpy(blob.at(pc), &dd, sizeof(dd));
+            pc += instrSize<InstrDedupe>();
+            InstrReportExhaust re;
+            memset(&re, 0, sizeof(re));
+            re.code = OP_REPORT_EXHAUST;
+            re.onmatch = p.report;
+            re.offset_adjust = adjust;
+            re.ekey = ekeys[p.report];
+            memcpy(blob.at(pc), &re, sizeof(re));
+        } else {
+            InstrDedupeAndReport dr;
+            memset(&dr, 0, sizeof(dr));
+            dr.code = OP_DEDUPE_AND_REPORT;
+            dr.dkey = dkeys[p.report];
+            dr.onmatch = p.report;
+            dr.offset_adjust = adjust;
+            dr.fail_jump = endAt - pc;
+            memcpy(blob.at(pc), &dr, sizeof(dr));
+        }
+        InstrEnd e;
+        e.code = OP_END;
+        memcpy(blob.at(endAt), &e, sizeof(e));
+        progOf[{p.report, adjust}] = prog;
+        return prog;
+    };
+    for (const RegexPattern &p : pats) {
         try {
-            minLen = std::min(minLen, regexInfo(p.re.c_str(), p.flags).minLen);
-            regexNfaAdd(&nfa, p.re.c_str(), p.flags, prog);
+            const RegexInfo ri = regexInfo(p.re.c_str(), p.flags);
+            minLen = std::min(minLen, ri.minLen);
+            regexNfaAdd(&nfa, p.re.c_str(), p.flags, program(p, 0), ri.needsAdjust ? program(p, -1) : 0);
         } catch (const RegexError &e) {
             throw CompileError{e.msg, (int)p.index};
         }
