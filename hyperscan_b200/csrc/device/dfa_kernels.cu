@@ -324,6 +324,12 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     const u16 *succ16 = reinterpret_cast<const u16 *>(SMEM_TABLE ? smem + 256 : succG);
     const u32 copyOff = (lane & 7) * 16; /* Sheng: this lane's copy of a row */
 
+    uint4 lxRow0 = make_uint4(0, 0, 0, 0);
+    bool lxRow0Plain = false; /* state 0 raises no reports: its row can be applied without the loop */
+    if (ENGINE == ENG_LIMEX32) {
+        lxRow0 = reinterpret_cast<const uint4 *>(smem + 1024)[0];
+        lxRow0Plain = lxRow0.z == MO_INVALID_IDX;
+    }
     u32 cursor = 0; /* this lane's next record slot (emitDfaMatch) */
     /* one input byte: byte j of data word w, at block offset pos.  DFAs: returns true when the
      * state entered accepts.  LimEx (LOOP_NOACCEL_FN, limex_runtime_impl.h:209-243): the states
@@ -334,7 +340,15 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
             /* NFA_EXEC_GET_LIM_SUCC + processExceptional32 (limex_exceptional.h:190-330, cache
              * aside) over the states that are on, in ascending order: every exception's squash
              * cuts the limited successors only, the exception successors are OR-ed in afterwards */
+            /* state 0 first, from registers: in a position automaton it is the floating start,
+             * on at every byte -- most bytes of most inputs have nothing else on */
             u32 lim = 0, local = 0, keep = 0xffffffffu, on = s;
+            if (lxRow0Plain && (s & 1u)) {
+                lim = lxRow0.x;
+                local = lxRow0.y;
+                keep = lxRow0.w;
+                on &= ~1u;
+            }
             while (on) {
                 const u32 bit = (u32)__ffs((int)on) - 1;
                 on &= on - 1;
