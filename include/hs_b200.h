@@ -120,10 +120,14 @@ typedef int (*match_event_handler)(unsigned int id, unsigned long long from,
  * that denotes a FINITE set of strings -- literal text and PCRE escapes,
  * groups, alternation, character classes without negation, the bounded
  * repeats ?, {n}, {n,m} (at most 4096 strings per expression) -- each string
- * becoming one literal under the expression's id.  Anything else (., *, +,
- * anchors, look-around, back-references, ...) yields HS_COMPILER_ERROR with
- * an explanatory hs_compile_error_t, exactly as the reference reports
- * unsupported constructs. */
+ * becoming one literal under the expression's id.  An expression set that is
+ * not such a set (unbounded repeats, ".", negated / POSIX classes, \d \w \s,
+ * "^" \A "$" \z \Z at the ends of top-level alternatives) is compiled, in block
+ * mode, to ONE LimEx NFA of the 32-state model inside a single-outfix database
+ * (ROSE_RUNTIME_SINGLE_OUTFIX) when its positions fit -- DESIGN.md section 10b.
+ * Anything else (\b, look-around, back-references, larger sets, ...) yields
+ * HS_COMPILER_ERROR with an explanatory hs_compile_error_t, exactly as the
+ * reference reports unsupported constructs. */
 hs_error_t hs_compile(const char *expression, unsigned int flags,
                       unsigned int mode, const hs_platform_info_t *platform,
                       hs_database_t **db, hs_compile_error_t **error);
