@@ -672,6 +672,38 @@ def limex32_from_spec(reach, init, init_ds, succ, reports, reports_eod, squash_m
     return out.raw[:sz]
 
 
+def limex_from_spec64(reach, init, init_ds, succ, reports, reports_eod, squash_mask=None, squash_kind=None):
+    """hs_b200_limex_from_spec64: as limex32_from_spec over uint64 state sets (up to 64 states)."""
+    sc = np.ascontiguousarray(succ, dtype=np.uint64)
+    n = sc.size
+    rc = np.ascontiguousarray(reach, dtype=np.uint64)
+
+    def flat(lists):
+        off = np.zeros(n + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(x) for x in lists])
+        vals = np.array([v for x in lists for v in x] + [0], dtype=np.uint32)
+        return off, vals
+
+    ro, rv = flat(reports)
+    eo, ev = flat(reports_eod)
+    sm = np.ascontiguousarray(squash_mask if squash_mask is not None else np.full(n, 0xffffffffffffffff, dtype=np.uint64),
+                              dtype=np.uint64)
+    sk = np.ascontiguousarray(squash_kind if squash_kind is not None else np.zeros(n), dtype=np.uint8)
+    L = lib()
+    L.hs_b200_limex_from_spec64.restype = C.c_long
+    L.hs_b200_limex_from_spec64.argtypes = [C.c_uint, C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_size_t]
+    cap = 1 << 20
+    out = C.create_string_buffer(cap)
+    sz = L.hs_b200_limex_from_spec64(n, rc.ctypes.data, int(init), int(init_ds), sc.ctypes.data, sm.ctypes.data,
+                                     sk.ctypes.data, ro.ctypes.data, rv.ctypes.data, eo.ctypes.data, ev.ctypes.data,
+                                     out, cap)
+    if sz < 0:
+        raise HsError(HS_COMPILER_ERROR, "limex_from_spec64")
+    return out.raw[:sz]
+
+
 def nfa_scan_corpus(nfa_bytes, corpus, cap=1 << 20):
     """hs_b200_nfa_scan_corpus: the engine over every block of a resident corpus.
     Returns (records MATCH_DTYPE ordered by (block, to, id), kernel ms)."""

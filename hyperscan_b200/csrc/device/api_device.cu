@@ -550,18 +550,25 @@ hs_error_t engineParams(const void *nfa, size_t nfa_len, DfaParams *out) {
         if (nfa_len < sizeof(NFA) + sizeof(Sheng)) {
             return HS_INVALID;
         }
-    } else if (hdr.type == NFA_LIMEX_32) {
-        if (nfa_len < sizeof(NFA) + sizeof(LimExNFA32)) {
+    } else if (hdr.type == NFA_LIMEX_32 || hdr.type == NFA_LIMEX_64) {
+        const bool wide = hdr.type == NFA_LIMEX_64;
+        const size_t structSize = wide ? sizeof(LimExNFA64) : sizeof(LimExNFA32);
+        if (nfa_len < sizeof(NFA) + structSize) {
             return HS_INVALID;
         }
+        /* the count / offset fields precede the state-sized ones and sit at the same offsets in both models */
         LimExNFA32 lx;
-        memcpy(&lx, (const u8 *)nfa + sizeof(NFA), sizeof(lx));
+        memcpy(&lx, (const u8 *)nfa + sizeof(NFA), offsetof(LimExNFA32, init));
+        u32 shiftCount;
+        memcpy(&shiftCount, (const u8 *)nfa + sizeof(NFA) + (wide ? offsetof(LimExNFA64, shiftCount) : offsetof(LimExNFA32, shiftCount)), 4);
         if (lx.repeatCount) {
             return HS_ARCH_ERROR; /* bounded repeats (repeat control blocks, tug / pos triggers) are not built */
         }
         const size_t body = nfa_len - sizeof(NFA);
-        if (lx.shiftCount > 8 || lx.exceptionCount > 32 || sizeof(LimExNFA32) + 4ull * lx.reachSize > body ||
-            (size_t)lx.exceptionOffset + (size_t)lx.exceptionCount * sizeof(NFAException32) > body ||
+        const size_t excSize = wide ? sizeof(NFAException64) : sizeof(NFAException32);
+        if (shiftCount > 8 || lx.exceptionCount > (wide ? 64u : 32u) ||
+            structSize + (wide ? 8ull : 4ull) * lx.reachSize > body ||
+            (size_t)lx.exceptionOffset + (size_t)lx.exceptionCount * excSize > body ||
             (size_t)lx.acceptOffset + (size_t)lx.acceptCount * sizeof(NFAAccept) > body ||
             (size_t)lx.acceptEodOffset + (size_t)lx.acceptEodCount * sizeof(NFAAccept) > body) {
             return HS_INVALID;

@@ -64,6 +64,13 @@ __device__ u32 emitReportList(const DfaParams &p, u32 cursor, u32 off, u32 block
     return cursor;
 }
 
+__device__ __forceinline__ u32 ldgState(const u8 *p, u32) { return g32(p); }
+__device__ __forceinline__ u64 ldgState(const u8 *p, u64) { return __ldg(reinterpret_cast<const u64 *>(p)); }
+__device__ __forceinline__ u32 lowestBit(u32 v) { return (u32)__ffs((int)v) - 1; }
+__device__ __forceinline__ u32 lowestBit(u64 v) { return (u32)__ffsll((long long)v) - 1; }
+__device__ __forceinline__ u32 rankBelow(u32 mask, u32 bit) { return (u32)__popc(mask & ((1u << bit) - 1)); }
+__device__ __forceinline__ u32 rankBelow(u64 mask, u32 bit) { return (u32)__popcll(mask & ((1ull << bit) - 1)); }
+
 /* LimEx report list: ReportID[] terminated by MO_INVALID_IDX (limexRunReports, limex_runtime.h:90-103) */
 __device__ HSB_NOINLINE u32 emitLimexReports(const DfaParams &p, u32 cursor, u32 listOff, u32 block, u64 to) {
     const u8 *lx = p.nfa + sizeof(NFA);
@@ -79,13 +86,14 @@ __device__ HSB_NOINLINE u32 emitLimexReports(const DfaParams &p, u32 cursor, u32
 
 /* accepts of the states in `found` through an NFAAccept table (PROCESS_ACCEPTS_IMPL_FN,
  * limex_common_impl.h:116-163; the squash of PROCESS_ACCEPTS_FN is dead code there) */
-__device__ HSB_NOINLINE u32 emitLimexAccepts(const DfaParams &p, u32 cursor, u32 found, u32 mask, u32 tableOff,
+template <class ST>
+__device__ HSB_NOINLINE u32 emitLimexAccepts(const DfaParams &p, u32 cursor, ST found, ST mask, u32 tableOff,
                                              u32 block, u64 to) {
     const u8 *lx = p.nfa + sizeof(NFA);
     while (found) {
-        const u32 bit = (u32)__ffs((int)found) - 1;
+        const u32 bit = lowestBit(found);
         found &= found - 1;
-        const u32 idx = (u32)__popc(mask & ((1u << bit) - 1));
+        const u32 idx = rankBelow(mask, bit);
         const u8 *a = lx + tableOff + idx * (u32)sizeof(NFAAccept);
         const u32 reports = g32(a + offsetof(NFAAccept, reports));
         if (__ldg(a + offsetof(NFAAccept, single_report))) {
@@ -194,8 +202,19 @@ template <int CH> struct DfaTile {
     static constexpr u32 ROWS_PER_LOAD = 32 / PIECES;
 };
 
-enum { ENG_MCC8 = 0, ENG_MCC16 = 1, ENG_SHENG = 2, ENG_LIMEX32 = 3 };
-enum { LIMEX_TABLE_BYTES = 1024 + 512 }; /* reach mask per byte value, then 32 states x 16 B */
+enum { ENG_MCC8 = 0, ENG_MCC16 = 1, ENG_SHENG = 2, ENG_LIMEX32 = 3, ENG_LIMEX64 = 4 };
+
+/* the state of a block's walk: a DFA state id, or the LimEx state set (32 or 64 states) */
+template <int ENGINE> struct WalkState { typedef u32 type; };
+template <> struct WalkState<ENG_LIMEX64> { typedef u64 type; };
+/* the engine structures of the two LimEx models share their field names */
+template <class ST> struct LimexLayout;
+template <> struct LimexLayout<u32> { typedef LimExNFA32 Nfa; typedef NFAException32 Exc; };
+template <> struct LimexLayout<u64> { typedef LimExNFA64 Nfa; typedef NFAException64 Exc; };
+/* shared-memory tables of a LimEx engine: the reach mask per byte value, then per state a row of four
+ * ST: limited successors, exception successors, squash mask, report list offset */
+template <class ST> struct LimexTable { static constexpr u32 BYTES = 256u * sizeof(ST) + 8u * sizeof(ST) * 4u * sizeof(ST); };
+
 enum { SHENG_ROW = 128, SHENG_TABLE_BYTES = 256 * SHENG_ROW };
 
 struct DfaConsts {
@@ -224,17 +243,22 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     k.shermanOffset = 0;
     k.shermanLimit = 0xffffffffu;
     k.acceptLimit8 = 0;
-    u32 lxAccept = 0, lxAcceptEod = 0;
-    if (ENGINE == ENG_LIMEX32) {
-        /* eng = struct LimExNFA32; a top at offset 0 switches `init` on (moNfaTop32) */
-        k.start = g32(eng + offsetof(LimExNFA32, init));
+    typedef typename WalkState<ENGINE>::type ST;
+    typedef typename LimexLayout<ST>::Nfa LxNfa;
+    typedef typename LimexLayout<ST>::Exc LxExc;
+    constexpr bool LIMEX = ENGINE == ENG_LIMEX32 || ENGINE == ENG_LIMEX64;
+    ST lxAccept = 0, lxAcceptEod = 0, lxStart = 0;
+    if (LIMEX) {
+        /* eng = struct LimExNFA32 / 64; a top at offset 0 switches `init` on (moNfaTop) */
+        lxStart = ldgState(eng + offsetof(LxNfa, init), ST());
+        k.start = 0;
         k.single = 0;
         k.report = 0;
         k.auxOffset = 0;
         k.auxSize = 0;
         k.stateMask = 0xffffffffu;
-        lxAccept = g32(eng + offsetof(LimExNFA32, accept));
-        lxAcceptEod = g32(eng + offsetof(LimExNFA32, acceptAtEOD));
+        lxAccept = ldgState(eng + offsetof(LxNfa, accept), ST());
+        lxAcceptEod = ldgState(eng + offsetof(LxNfa, acceptAtEOD), ST());
     } else if (ENGINE == ENG_SHENG) {
         k.start = __ldg(eng + offsetof(Sheng, anchored));
         k.single = __ldg(eng + offsetof(Sheng, flags)) & SHENG_FLAG_SINGLE_REPORT;
@@ -257,39 +281,43 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
         k.stateMask = 0xffffffffu;
     }
     u32 tabArea;
-    if (ENGINE == ENG_LIMEX32) {
-        /* reach mask by byte value (reach[reachMap[b]]), then ONE row per state i:
-         *   x = its limited successors: OR over the shifts k with bit i of shift[k] of 1 << (i + shiftAmount[k])
-         *   y = its exception's successors, z = its exception's report list, w = its squash mask
-         *       (all ones unless the exception squashes: LIMEX_SQUASH_CYCLIC / _REPORT)
+    if (LIMEX) {
+        /* reach mask by byte value (reach[reachMap[b]]), then ONE row of four ST per state i:
+         *   [0] its limited successors: OR over the shifts k with bit i of shift[k] of 1 << (i + shiftAmount[k])
+         *   [1] its exception's successors, [2] its squash mask (all ones unless the exception squashes:
+         *   LIMEX_SQUASH_CYCLIC / _REPORT), [3] its exception's report list
          * so a byte costs work in proportion to the states that are ON, not eight shift-and-mask rounds */
-        u32 *d = reinterpret_cast<u32 *>(smem);
-        const u8 *reach = eng + sizeof(LimExNFA32);
+        ST *d = reinterpret_cast<ST *>(smem);
+        const u8 *reach = eng + sizeof(LxNfa);
         for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
-            d[i] = g32(reach + 4 * __ldg(eng + offsetof(LimExNFA32, reachMap) + i));
+            d[i] = ldgState(reach + sizeof(ST) * __ldg(eng + offsetof(LxNfa, reachMap) + i), ST());
         }
-        const u32 excMask = g32(eng + offsetof(LimExNFA32, exceptionMask));
-        const u32 nshift = g32(eng + offsetof(LimExNFA32, shiftCount));
-        const u8 *exc = eng + g32(eng + offsetof(LimExNFA32, exceptionOffset));
-        for (u32 i = threadIdx.x; i < 32; i += blockDim.x) {
-            uint4 e = make_uint4(0, 0, MO_INVALID_IDX, 0xffffffffu);
+        const ST excMask = ldgState(eng + offsetof(LxNfa, exceptionMask), ST());
+        const u32 nshift = g32(eng + offsetof(LxNfa, shiftCount));
+        const u8 *exc = eng + g32(eng + offsetof(LxNfa, exceptionOffset));
+        ST *rows = d + 256;
+        for (u32 i = threadIdx.x; i < 8 * sizeof(ST); i += blockDim.x) {
+            ST lim = 0, local = 0, keep = ~(ST)0, rep = MO_INVALID_IDX;
             for (u32 q = 0; q < nshift && q < 8; q++) {
-                if ((g32(eng + offsetof(LimExNFA32, shift) + 4 * q) >> i) & 1) {
-                    e.x |= (1u << i) << __ldg(eng + offsetof(LimExNFA32, shiftAmount) + q); /* LSHIFT_STATE: bits past 31 fall off */
+                if ((ldgState(eng + offsetof(LxNfa, shift) + sizeof(ST) * q, ST()) >> i) & 1) {
+                    lim |= ((ST)1 << i) << __ldg(eng + offsetof(LxNfa, shiftAmount) + q); /* LSHIFT_STATE: high bits fall off */
                 }
             }
             if ((excMask >> i) & 1) {
-                const u8 *x = exc + (u32)__popc(excMask & ((1u << i) - 1)) * (u32)sizeof(NFAException32);
-                const u32 kind = __ldg(x + offsetof(NFAException32, hasSquash));
-                e.y = g32(x + offsetof(NFAException32, successors));
-                e.z = g32(x + offsetof(NFAException32, reports));
+                const u8 *x = exc + rankBelow(excMask, i) * (u32)sizeof(LxExc);
+                const u32 kind = __ldg(x + offsetof(LxExc, hasSquash));
+                local = ldgState(x + offsetof(LxExc, successors), ST());
+                rep = g32(x + offsetof(LxExc, reports));
                 if (kind == LIMEX_SQUASH_CYCLIC || kind == LIMEX_SQUASH_REPORT) {
-                    e.w = g32(x + offsetof(NFAException32, squash));
+                    keep = ldgState(x + offsetof(LxExc, squash), ST());
                 }
             }
-            reinterpret_cast<uint4 *>(smem + 1024)[i] = e;
+            rows[4 * i + 0] = lim;
+            rows[4 * i + 1] = local;
+            rows[4 * i + 2] = keep;
+            rows[4 * i + 3] = rep;
         }
-        tabArea = LIMEX_TABLE_BYTES;
+        tabArea = LimexTable<ST>::BYTES;
     } else if (ENGINE == ENG_SHENG) {
         /* [byte c][copy r][16 successor bytes, the one of state s at position (s + 4c) & 15] */
         for (u32 i = threadIdx.x; i < SHENG_TABLE_BYTES; i += blockDim.x) {
@@ -324,43 +352,48 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     const u16 *succ16 = reinterpret_cast<const u16 *>(SMEM_TABLE ? smem + 256 : succG);
     const u32 copyOff = (lane & 7) * 16; /* Sheng: this lane's copy of a row */
 
-    uint4 lxRow0 = make_uint4(0, 0, 0, 0);
+    const ST *lxReach = reinterpret_cast<const ST *>(smem);
+    const ST *lxRows = lxReach + 256;
+    ST lxLim0 = 0, lxLocal0 = 0, lxKeep0 = ~(ST)0;
     bool lxRow0Plain = false; /* state 0 raises no reports: its row can be applied without the loop */
-    if (ENGINE == ENG_LIMEX32) {
-        lxRow0 = reinterpret_cast<const uint4 *>(smem + 1024)[0];
-        lxRow0Plain = lxRow0.z == MO_INVALID_IDX;
+    if (LIMEX) {
+        lxLim0 = lxRows[0];
+        lxLocal0 = lxRows[1];
+        lxKeep0 = lxRows[2];
+        lxRow0Plain = (u32)lxRows[3] == MO_INVALID_IDX;
     }
     u32 cursor = 0; /* this lane's next record slot (emitDfaMatch) */
     /* one input byte: byte j of data word w, at block offset pos.  DFAs: returns true when the
      * state entered accepts.  LimEx (LOOP_NOACCEL_FN, limex_runtime_impl.h:209-243): the states
      * that are on BEFORE the byte run their exceptions -- reports at offset pos, except at the
      * first byte of the scan (NO_OUTPUT | FIRST_BYTE) -- then succ & reach[byte]. */
-    auto step = [&](const u32 w, const u32 j, u32 &s, const u32 pos, const u32 blk) -> bool {
-        if (ENGINE == ENG_LIMEX32) {
-            /* NFA_EXEC_GET_LIM_SUCC + processExceptional32 (limex_exceptional.h:190-330, cache
+    auto step = [&](const u32 w, const u32 j, ST &s, const u32 pos, const u32 blk) -> bool {
+        if (LIMEX) {
+            /* NFA_EXEC_GET_LIM_SUCC + processExceptional (limex_exceptional.h:190-330, cache
              * aside) over the states that are on, in ascending order: every exception's squash
              * cuts the limited successors only, the exception successors are OR-ed in afterwards */
             /* state 0 first, from registers: in a position automaton it is the floating start,
              * on at every byte -- most bytes of most inputs have nothing else on */
-            u32 lim = 0, local = 0, keep = 0xffffffffu, on = s;
+            ST lim = 0, local = 0, keep = ~(ST)0, on = s;
             if (lxRow0Plain && (s & 1u)) {
-                lim = lxRow0.x;
-                local = lxRow0.y;
-                keep = lxRow0.w;
-                on &= ~1u;
+                lim = lxLim0;
+                local = lxLocal0;
+                keep = lxKeep0;
+                on &= ~(ST)1;
             }
             while (on) {
-                const u32 bit = (u32)__ffs((int)on) - 1;
+                const u32 bit = lowestBit(on);
                 on &= on - 1;
-                const uint4 e = reinterpret_cast<const uint4 *>(smem + 1024)[bit];
-                if (e.z != MO_INVALID_IDX && pos != 0) {
-                    cursor = emitLimexReports(p, cursor, e.z, blk, pos);
+                const ST *e = lxRows + 4 * bit;
+                const u32 rep = (u32)e[3];
+                if (rep != MO_INVALID_IDX && pos != 0) {
+                    cursor = emitLimexReports(p, cursor, rep, blk, pos);
                 }
-                lim |= e.x;
-                local |= e.y;
-                keep &= e.w;
+                lim |= e[0];
+                local |= e[1];
+                keep &= e[2];
             }
-            s = ((lim & keep) | local) & reinterpret_cast<const u32 *>(smem)[__byte_perm(w, 0, 0x4440 + j)];
+            s = ((lim & keep) | local) & lxReach[__byte_perm(w, 0, 0x4440 + j)];
             return false;
         } else if (ENGINE == ENG_MCC8) {
             s = smem[__byte_perm(w, s, 0x5540 + j)]; /* (s << 8) | byte */
@@ -382,17 +415,18 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
             return (e & MCC_ACCEPT_FLAG) != 0;
         }
     };
-    auto acceptWhat = [&](const u32 s) -> u32 {
-        return k.single ? k.report : k.auxOffset + k.auxSize * (s & k.stateMask);
+    auto acceptWhat = [&](const ST s) -> u32 {
+        return k.single ? k.report : k.auxOffset + k.auxSize * ((u32)s & k.stateMask);
     };
-    auto dead = [&](const u32 s) -> bool { return ENGINE == ENG_SHENG ? (s & SHENG_STATE_DEAD) != 0 : s == 0; };
+    auto dead = [&](const ST s) -> bool { return ENGINE == ENG_SHENG ? (s & SHENG_STATE_DEAD) != 0 : s == 0; };
 
     /* a warp takes 32 * ILP consecutive blocks at a time; lane t owns blocks t, t + 32, ...
      * of the group: ILP independent state chains in one instruction stream */
     const u32 perGroup = 32 * ILP;
     const u32 ngroups = (p.nblocks + perGroup - 1) / perGroup;
     for (u32 g = blockIdx.x * nwarps + warp; g < ngroups; g += gridDim.x * nwarps) {
-        u32 b[ILP], len[ILP], s[ILP];
+        u32 b[ILP], len[ILP];
+        ST s[ILP];
         u64 off[ILP];
         bool live[ILP];
 #pragma unroll
@@ -405,7 +439,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
                 off[u] = (u64)(blk.base - p.corpus);
                 len[u] = blk.len;
             }
-            s[u] = k.start;
+            s[u] = LIMEX ? lxStart : (ST)k.start;
             live[u] = len[u] != 0;
         }
         for (u32 r = 0;; r++) {
@@ -518,23 +552,23 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
         /* nfaExec*_B: reports of the final state that fire at end of data */
 #pragma unroll
         for (int u = 0; u < ILP; u++) {
-            if (ENGINE == ENG_LIMEX32) {
+            if (LIMEX) {
                 if (b[u] < p.nblocks) {
                     /* STREAM_FN's closing accept check (only if the block had bytes to stream),
-                     * then nfaExecLimEx32_testEOD (limex_common_impl.h:192-218) */
+                     * then nfaExecLimEx*_testEOD (limex_common_impl.h:192-218) */
                     if (len[u] && (s[u] & lxAccept)) {
-                        cursor = emitLimexAccepts(p, cursor, s[u] & lxAccept, lxAccept,
-                                                  g32(eng + offsetof(LimExNFA32, acceptOffset)), b[u], len[u]);
+                        cursor = emitLimexAccepts<ST>(p, cursor, s[u] & lxAccept, lxAccept,
+                                                      g32(eng + offsetof(LxNfa, acceptOffset)), b[u], len[u]);
                     }
                     if (s[u] & lxAcceptEod) {
-                        cursor = emitLimexAccepts(p, cursor, s[u] & lxAcceptEod, lxAcceptEod,
-                                                  g32(eng + offsetof(LimExNFA32, acceptEodOffset)), b[u], len[u]);
+                        cursor = emitLimexAccepts<ST>(p, cursor, s[u] & lxAcceptEod, lxAcceptEod,
+                                                      g32(eng + offsetof(LxNfa, acceptEodOffset)), b[u], len[u]);
                     }
                 }
             } else if (b[u] < p.nblocks) {
                 const u32 eodOff = ENGINE == ENG_SHENG ? (u32)offsetof(SstateAux, accept_eod)
                                                        : (u32)offsetof(MStateAux, accept_eod);
-                const u32 eod = g32(p.nfa + k.auxOffset + k.auxSize * (s[u] & k.stateMask) + eodOff);
+                const u32 eod = g32(p.nfa + k.auxOffset + k.auxSize * ((u32)s[u] & k.stateMask) + eodOff);
                 if (eod) {
                     cursor = emitReportList(p, cursor, eod, b[u], len[u]);
                 }
@@ -576,7 +610,10 @@ cudaError_t launchDfa(const DfaParams &p, int smCount, int maxSmem, cudaStream_t
         return launchStaged<ENG_SHENG, 1>(p, smCount, SHENG_TABLE_BYTES, stream);
     }
     if (p.kind == NFA_LIMEX_32) {
-        return launchStaged<ENG_LIMEX32, 1>(p, smCount, LIMEX_TABLE_BYTES, stream);
+        return launchStaged<ENG_LIMEX32, 1>(p, smCount, LimexTable<u32>::BYTES, stream);
+    }
+    if (p.kind == NFA_LIMEX_64) {
+        return launchStaged<ENG_LIMEX64, 1>(p, smCount, LimexTable<u64>::BYTES, stream);
     }
     if (p.kind == NFA_MCCLELLAN_8) {
         return launchStaged<ENG_MCC8, 1>(p, smCount, (size_t)p.states * 256, stream); /* <= 64 KiB */

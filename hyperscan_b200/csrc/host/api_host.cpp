@@ -1318,28 +1318,30 @@ extern "C" long hs_b200_limex32_from_literals(const char *const *lits, const siz
             v[i].caseless = caseless && caseless[i];
             v[i].report = reports[i];
         }
-        return copyOut(hsb::emitLimEx32(hsb::nfaFromLiterals(v)), out, cap);
+        return copyOut(hsb::emitLimEx(hsb::nfaFromLiterals(v)), out, cap);
     } catch (const std::exception &) {
         return -1;
     }
 }
 
-extern "C" long hs_b200_limex32_from_spec(unsigned nstates, const unsigned *reach256, unsigned init, unsigned init_ds,
-                                          const unsigned *succ, const unsigned *squash_mask,
-                                          const unsigned char *squash_kind, const unsigned *report_off,
-                                          const unsigned *reports, const unsigned *eod_off,
-                                          const unsigned *eod_reports, void *out, size_t cap) {
-    if (!reach256 || !succ || !report_off || !eod_off || nstates == 0 || nstates > 32) {
+static long limexFromSpec(unsigned nstates, const unsigned long long *reach256, unsigned long long init,
+                          unsigned long long init_ds, const unsigned long long *succ,
+                          const unsigned long long *squash_mask, const unsigned char *squash_kind,
+                          const unsigned *report_off, const unsigned *reports, const unsigned *eod_off,
+                          const unsigned *eod_reports, void *out, size_t cap) {
+    if (!reach256 || !succ || !report_off || !eod_off || nstates == 0 || nstates > 64) {
         return -1;
     }
     try {
-        hsb::RawNfa32 n;
+        hsb::RawNfa n;
         n.nstates = nstates;
-        memcpy(n.reach, reach256, sizeof(n.reach));
+        for (unsigned b = 0; b < 256; b++) {
+            n.reach[b] = reach256[b];
+        }
         n.init = init;
         n.initDS = init_ds;
         n.succ.assign(succ, succ + nstates);
-        n.squashMask.assign(nstates, 0xffffffffu);
+        n.squashMask.assign(nstates, ~0ull);
         n.squashKind.assign(nstates, 0);
         n.reports.resize(nstates);
         n.reportsEod.resize(nstates);
@@ -1351,8 +1353,34 @@ extern "C" long hs_b200_limex32_from_spec(unsigned nstates, const unsigned *reac
             n.reports[i].assign(reports + report_off[i], reports + report_off[i + 1]);
             n.reportsEod[i].assign(eod_reports + eod_off[i], eod_reports + eod_off[i + 1]);
         }
-        return copyOut(hsb::emitLimEx32(n), out, cap);
+        return copyOut(hsb::emitLimEx(n), out, cap);
     } catch (const std::exception &) {
         return -1;
     }
+}
+
+extern "C" long hs_b200_limex_from_spec64(unsigned nstates, const unsigned long long *reach256,
+                                          unsigned long long init, unsigned long long init_ds,
+                                          const unsigned long long *succ, const unsigned long long *squash_mask,
+                                          const unsigned char *squash_kind, const unsigned *report_off,
+                                          const unsigned *reports, const unsigned *eod_off,
+                                          const unsigned *eod_reports, void *out, size_t cap) {
+    return limexFromSpec(nstates, reach256, init, init_ds, succ, squash_mask, squash_kind, report_off, reports, eod_off,
+                         eod_reports, out, cap);
+}
+
+extern "C" long hs_b200_limex32_from_spec(unsigned nstates, const unsigned *reach256, unsigned init, unsigned init_ds,
+                                          const unsigned *succ, const unsigned *squash_mask,
+                                          const unsigned char *squash_kind, const unsigned *report_off,
+                                          const unsigned *reports, const unsigned *eod_off,
+                                          const unsigned *eod_reports, void *out, size_t cap) {
+    if (!reach256 || !succ || nstates == 0 || nstates > 32) {
+        return -1;
+    }
+    std::vector<unsigned long long> r(reach256, reach256 + 256), sc(succ, succ + nstates), sq;
+    if (squash_mask) {
+        sq.assign(squash_mask, squash_mask + nstates);
+    }
+    return limexFromSpec(nstates, r.data(), init, init_ds, sc.data(), squash_mask ? sq.data() : nullptr, squash_kind,
+                         report_off, reports, eod_off, eod_reports, out, cap);
 }

@@ -8,8 +8,8 @@
 
 namespace hsb {
 
-RawNfa32 nfaFromLiterals(const std::vector<DfaLiteral> &lits) {
-    RawNfa32 n;
+RawNfa nfaFromLiterals(const std::vector<DfaLiteral> &lits) {
+    RawNfa n;
     size_t total = 1;
     for (const DfaLiteral &l : lits) {
         if (l.s.empty()) {
@@ -17,12 +17,12 @@ RawNfa32 nfaFromLiterals(const std::vector<DfaLiteral> &lits) {
         }
         total += l.s.size();
     }
-    if (total > 32) {
-        throw std::runtime_error("more than 32 NFA states");
+    if (total > 64) {
+        throw std::runtime_error("more than 64 NFA states");
     }
     n.nstates = (u32)total;
     n.succ.assign(total, 0);
-    n.squashMask.assign(total, 0xffffffffu);
+    n.squashMask.assign(total, ~0ull);
     n.squashKind.assign(total, LIMEX_SQUASH_NONE);
     n.reports.resize(total);
     n.reportsEod.resize(total);
@@ -36,11 +36,11 @@ RawNfa32 nfaFromLiterals(const std::vector<DfaLiteral> &lits) {
         u32 prev = 0;
         for (size_t i = 0; i < l.s.size(); i++) {
             const u32 st = next++;
-            n.succ[prev] |= 1u << st;
+            n.succ[prev] |= 1ull << st;
             const u8 c = (u8)l.s[i];
-            n.reach[c] |= 1u << st;
+            n.reach[c] |= 1ull << st;
             if (l.caseless && ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'))) {
-                n.reach[c ^ 0x20] |= 1u << st;
+                n.reach[c ^ 0x20] |= 1ull << st;
             }
             prev = st;
         }
@@ -67,21 +67,22 @@ size_t alignUp(std::vector<u8> &b, size_t a) {
 
 } // namespace
 
-std::vector<u8> emitLimEx32(const RawNfa32 &n) {
-    if (n.nstates == 0 || n.nstates > 32 || n.succ.size() != n.nstates || n.reports.size() != n.nstates ||
+template <class LX, class EX, class T> std::vector<u8> emitLimExT(const RawNfa &n, u8 nfaType) {
+    const u32 WIDTH = (u32)sizeof(T) * 8;
+    if (n.nstates == 0 || n.nstates > WIDTH || n.succ.size() != n.nstates || n.reports.size() != n.nstates ||
         n.reportsEod.size() != n.nstates || n.squashMask.size() != n.nstates || n.squashKind.size() != n.nstates) {
         throw std::runtime_error("bad NFA description");
     }
-    const u32 all = n.nstates == 32 ? 0xffffffffu : (1u << n.nstates) - 1;
-    LimExNFA32 lx;
+    const T all = n.nstates == WIDTH ? (T)~(T)0 : (T)(((T)1 << n.nstates) - 1);
+    LX lx;
     memset(&lx, 0, sizeof(lx));
 
     /* reach classes: bytes with the same reach mask share an entry */
-    std::vector<u32> reachTab;
+    std::vector<T> reachTab;
     {
-        std::map<u32, u32> seen;
+        std::map<T, u32> seen;
         for (u32 b = 0; b < 256; b++) {
-            const u32 m = n.reach[b] & all;
+            const T m = (T)n.reach[b] & all;
             auto it = seen.find(m);
             if (it == seen.end()) {
                 it = seen.emplace(m, (u32)reachTab.size()).first;
@@ -112,9 +113,9 @@ std::vector<u8> emitLimEx32(const RawNfa32 &n) {
         amounts.resize(8);
     }
     std::sort(amounts.begin(), amounts.end());
-    std::vector<u32> exceptional(n.nstates, 0); /* successors not covered by a shift */
+    std::vector<T> exceptional(n.nstates, 0); /* successors not covered by a shift */
     for (u32 i = 0; i < n.nstates; i++) {
-        exceptional[i] = n.succ[i] & all;
+        exceptional[i] = (T)n.succ[i] & all;
     }
     lx.shiftCount = std::max<u32>(1, (u32)amounts.size()); /* "should be always greater or equal to 1" */
     for (size_t k = 0; k < amounts.size(); k++) {
@@ -122,35 +123,35 @@ std::vector<u8> emitLimEx32(const RawNfa32 &n) {
         lx.shiftAmount[k] = (u8)a;
         for (u32 i = 0; i + a < n.nstates; i++) {
             if ((n.succ[i] >> (i + a)) & 1) {
-                lx.shift[k] |= 1u << i;
-                exceptional[i] &= ~(1u << (i + a));
+                lx.shift[k] |= (T)1 << i;
+                exceptional[i] &= ~((T)1 << (i + a));
             }
         }
     }
 
     for (u32 i = 0; i < n.nstates; i++) {
         if (!n.reports[i].empty()) {
-            lx.accept |= 1u << i;
+            lx.accept |= (T)1 << i;
         }
         if (!n.reportsEod[i].empty()) {
-            lx.acceptAtEOD |= 1u << i;
+            lx.acceptAtEOD |= (T)1 << i;
         }
         if (exceptional[i] || !n.reports[i].empty() || n.squashKind[i] != LIMEX_SQUASH_NONE) {
-            lx.exceptionMask |= 1u << i;
+            lx.exceptionMask |= (T)1 << i;
         }
     }
-    lx.init = n.init & all;
-    lx.initDS = n.initDS & all;
+    lx.init = (T)n.init & all;
+    lx.initDS = (T)n.initDS & all;
     lx.stateSize = (n.nstates + 7) / 8;
-    lx.acceptCount = (u32)__builtin_popcount(lx.accept);
-    lx.acceptEodCount = (u32)__builtin_popcount(lx.acceptAtEOD);
-    lx.exceptionCount = (u32)__builtin_popcount(lx.exceptionMask);
+    lx.acceptCount = (u32)__builtin_popcountll(lx.accept);
+    lx.acceptEodCount = (u32)__builtin_popcountll(lx.acceptAtEOD);
+    lx.exceptionCount = (u32)__builtin_popcountll(lx.exceptionMask);
 
     /* body after the struct: reach table, report lists, accept tables, exception table
      * (offsets relative to the LimExNFA32) */
-    std::vector<u8> body(sizeof(LimExNFA32), 0);
+    std::vector<u8> body(sizeof(LX), 0);
     for (size_t i = 0; i < reachTab.size(); i++) {
-        put(body, sizeof(LimExNFA32) + 4 * i, reachTab[i]);
+        put(body, sizeof(LX) + sizeof(T) * i, reachTab[i]);
     }
     auto reportList = [&](const std::vector<u32> &r) -> u32 {
         const u32 off = (u32)alignUp(body, 4);
@@ -169,7 +170,7 @@ std::vector<u8> emitLimEx32(const RawNfa32 &n) {
             listOffEod[i] = reportList(n.reportsEod[i]);
         }
     }
-    auto acceptTable = [&](u32 mask, const std::vector<std::vector<u32>> &reps, const std::vector<u32> &offs) -> u32 {
+    auto acceptTable = [&](T mask, const std::vector<std::vector<u32>> &reps, const std::vector<u32> &offs) -> u32 {
         const u32 off = (u32)alignUp(body, 4);
         for (u32 i = 0; i < n.nstates; i++) {
             if (!((mask >> i) & 1)) {
@@ -191,9 +192,9 @@ std::vector<u8> emitLimEx32(const RawNfa32 &n) {
         if (!((lx.exceptionMask >> i) & 1)) {
             continue;
         }
-        NFAException32 e;
+        EX e;
         memset(&e, 0, sizeof(e));
-        e.squash = n.squashKind[i] != LIMEX_SQUASH_NONE ? (n.squashMask[i] & all) : all;
+        e.squash = n.squashKind[i] != LIMEX_SQUASH_NONE ? ((T)n.squashMask[i] & all) : all;
         e.successors = exceptional[i];
         e.reports = listOff[i];
         e.repeatOffset = MO_INVALID_IDX;
@@ -207,16 +208,21 @@ std::vector<u8> emitLimEx32(const RawNfa32 &n) {
 
     NFA hdr;
     memset(&hdr, 0, sizeof(hdr));
-    hdr.type = NFA_LIMEX_32;
+    hdr.type = nfaType;
     hdr.length = (u32)(sizeof(NFA) + body.size());
     hdr.nPositions = n.nstates;
-    hdr.scratchStateSize = 4;
+    hdr.scratchStateSize = (u32)sizeof(T);
     hdr.streamStateSize = lx.stateSize;
     hdr.flags = lx.acceptEodCount ? NFA_ACCEPTS_EOD : 0;
     std::vector<u8> out(sizeof(NFA));
     memcpy(out.data(), &hdr, sizeof(hdr));
     out.insert(out.end(), body.begin(), body.end());
     return out;
+}
+
+std::vector<u8> emitLimEx(const RawNfa &n) {
+    return n.nstates <= 32 ? emitLimExT<LimExNFA32, NFAException32, u32>(n, NFA_LIMEX_32)
+                           : emitLimExT<LimExNFA64, NFAException64, u64>(n, NFA_LIMEX_64);
 }
 
 } // namespace hsb

@@ -209,7 +209,7 @@ private:
             if (comma && haveY && y < x) {
                 fail("Bounded repeat is invalid: min > max.");
             }
-            if (x > 32 || (haveY && y > 32)) {
+            if (x > 64 || (haveY && y > 64)) {
                 fail("Pattern is too large.");
             }
             pos = q + 1;
@@ -462,10 +462,10 @@ private:
 /* Glushkov: positions, nullable / first / last / follow */
 struct Glushkov {
     std::vector<CharSet> cls;         /* per position */
-    std::vector<u32> follow;          /* per position: bitmask over positions */
+    std::vector<u64> follow;          /* per position: bitmask over positions */
     struct Sets {
         bool nullable;
-        u32 first, last;
+        u64 first, last;
     };
 
     Sets build(const NodeP &n) {
@@ -473,21 +473,21 @@ struct Glushkov {
         case Node::EMPTY:
             return {true, 0, 0};
         case Node::CLASS: {
-            if (cls.size() >= 31) {
-                throw RegexError{"Pattern is too large: more than 31 character positions need the larger NFA models."};
+            if (cls.size() >= 62) {
+                throw RegexError{"Pattern is too large: more than 62 character positions need the larger NFA models."};
             }
             const u32 p = (u32)cls.size();
             cls.push_back(n->cls);
             follow.push_back(0);
-            return {false, 1u << p, 1u << p};
+            return {false, 1ull << p, 1ull << p};
         }
         case Node::CAT: {
             Sets acc = {true, 0, 0};
             for (const NodeP &k : n->kids) {
                 const Sets s = build(k);
                 link(acc.last, s.first);
-                const u32 first = acc.nullable ? (acc.first | s.first) : acc.first;
-                const u32 last = s.nullable ? (acc.last | s.last) : s.last;
+                const u64 first = acc.nullable ? (acc.first | s.first) : acc.first;
+                const u64 last = s.nullable ? (acc.last | s.last) : s.last;
                 acc = {acc.nullable && s.nullable, first, last};
             }
             return acc;
@@ -514,7 +514,7 @@ struct Glushkov {
         return {true, 0, 0};
     }
 
-    void link(u32 from, u32 to) {
+    void link(u64 from, u64 to) {
         for (u32 p = 0; p < follow.size(); p++) {
             if ((from >> p) & 1) {
                 follow[p] |= to;
@@ -595,12 +595,12 @@ RegexInfo regexInfo(const char *re, unsigned flags) {
     return info;
 }
 
-void regexNfaInit(RawNfa32 *nfa) {
-    *nfa = RawNfa32();
+void regexNfaInit(RawNfa *nfa) {
+    *nfa = RawNfa();
     nfa->nstates = 2; /* 0 = floating start (.* loop), 1 = anchored start (offset 0 only) */
     nfa->succ.assign(2, 0);
     nfa->succ[0] = 1u;
-    nfa->squashMask.assign(2, 0xffffffffu);
+    nfa->squashMask.assign(2, ~0ull);
     nfa->squashKind.assign(2, LIMEX_SQUASH_NONE);
     nfa->reports.resize(2);
     nfa->reportsEod.resize(2);
@@ -610,7 +610,7 @@ void regexNfaInit(RawNfa32 *nfa) {
     nfa->init = nfa->initDS = 3u;
 }
 
-void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline) {
+void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline) {
     const NodeP root = Parser(re, flags).parse();
     for (const NodeP &arm : topArms(root)) {
         Glushkov g;
@@ -620,22 +620,22 @@ void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report, u32 
         }
         const u32 base = nfa->nstates;
         const u32 np = (u32)g.cls.size();
-        if (base + np > 32) {
-            throw RegexError{"Pattern set is too large: its character positions exceed the 32-state NFA model."};
+        if (base + np > 64) {
+            throw RegexError{"Pattern set is too large: its character positions exceed the 64-state NFA model."};
         }
         nfa->nstates += np;
         nfa->succ.resize(nfa->nstates, 0);
-        nfa->squashMask.resize(nfa->nstates, 0xffffffffu);
+        nfa->squashMask.resize(nfa->nstates, ~0ull);
         nfa->squashKind.resize(nfa->nstates, LIMEX_SQUASH_NONE);
         nfa->reports.resize(nfa->nstates);
         nfa->reportsEod.resize(nfa->nstates);
         auto newState = [&]() -> u32 {
-            if (nfa->nstates >= 32) {
-                throw RegexError{"Pattern set is too large: its character positions exceed the 32-state NFA model."};
+            if (nfa->nstates >= 64) {
+                throw RegexError{"Pattern set is too large: its character positions exceed the 64-state NFA model."};
             }
             nfa->nstates++;
             nfa->succ.push_back(0);
-            nfa->squashMask.push_back(0xffffffffu);
+            nfa->squashMask.push_back(~0ull);
             nfa->squashKind.push_back(LIMEX_SQUASH_NONE);
             nfa->reports.emplace_back();
             nfa->reportsEod.emplace_back();
@@ -647,8 +647,8 @@ void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report, u32 
              * one state shared by all such alternatives, on after every '\n' */
             if (!nfa->mlStartState) {
                 nfa->mlStartState = newState();
-                nfa->reach[(u8)'\n'] |= 1u << nfa->mlStartState;
-                nfa->succ[0] |= 1u << nfa->mlStartState;
+                nfa->reach[(u8)'\n'] |= 1ull << nfa->mlStartState;
+                nfa->succ[0] |= 1ull << nfa->mlStartState;
             }
             nfa->succ[1] |= s.first << base;
             nfa->succ[nfa->mlStartState] |= s.first << base;
@@ -659,7 +659,7 @@ void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report, u32 
             nfa->succ[base + p] |= g.follow[p] << base;
             for (u32 b = 0; b < 256; b++) {
                 if (g.cls[p][b]) {
-                    nfa->reach[b] |= 1u << (base + p);
+                    nfa->reach[b] |= 1ull << (base + p);
                 }
             }
         }
@@ -672,7 +672,7 @@ void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report, u32 
                 throw RegexError{"internal: no adjusted report program"};
             }
             nl = newState();
-            nfa->reach[(u8)'\n'] |= 1u << nl;
+            nfa->reach[(u8)'\n'] |= 1ull << nl;
             if (end == Node::END_DOLLAR) {
                 nfa->reportsEod[nl].push_back(reportBeforeNewline); /* ... only if that newline ends the data */
             } else {
@@ -688,7 +688,7 @@ void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report, u32 
             } else {
                 nfa->reportsEod[base + p].push_back(report);
                 if (nl) {
-                    nfa->succ[base + p] |= 1u << nl;
+                    nfa->succ[base + p] |= 1ull << nl;
                 }
             }
         }

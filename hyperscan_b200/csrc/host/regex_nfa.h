@@ -1,8 +1,8 @@
 /*
- * regex_nfa.h -- small regular expressions to a LimEx-32 NFA: the position (Glushkov)
+ * regex_nfa.h -- small regular expressions to a LimEx NFA (32- or 64-state model): the position (Glushkov)
  * automaton the reference builds for its NFA engines (src/nfagraph/ng_builder.cpp,
  * src/parser/buildstate.cpp: one state per character position, epsilon free), for
- * expression sets whose positions fit the 32-state model together with the start states.
+ * expression sets whose positions fit the 64-state model together with the start states.
  *
  * Syntax (PCRE as the reference's parser accepts it, src/parser/Parser.rl): literal
  * characters and escapes (\n \t \r \f \a \e \xHH, escaped punctuation), the class escapes
@@ -45,10 +45,10 @@ RegexInfo regexInfo(const char *re, unsigned flags);
 
 /* Add the expression's position automaton to `nfa`: its accepting positions raise `report`.
  * State 0 of `nfa` is the floating start (always on), state 1 the anchored start (on at
- * offset 0 only); call regexNfaInit first.  Throws RegexError, also when the 32 states
+ * offset 0 only); call regexNfaInit first.  Throws RegexError, also when the 64 states
  * are exceeded. */
-void regexNfaInit(RawNfa32 *nfa);
-void regexNfaAdd(RawNfa32 *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline = 0);
+void regexNfaInit(RawNfa *nfa);
+void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline = 0);
 /* reportBeforeNewline: the same report delivered one byte back (a report program with offset_adjust -1) --
  * needed when RegexInfo.needsAdjust: "$" / \Z match before a final newline, "$" under (?m) before any */
 

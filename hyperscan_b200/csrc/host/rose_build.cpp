@@ -393,7 +393,7 @@ std::vector<u8> buildLiteralRose(const std::vector<LitPattern> &patsIn,
         std::vector<u8> nfa;
         try {
             if (opts.outfixKind == OUTFIX_LIMEX32) {
-                nfa = emitLimEx32(nfaFromLiterals(dl));
+                nfa = emitLimEx(nfaFromLiterals(dl));
             } else {
                 const DfaKind k = opts.outfixKind == OUTFIX_MCCLELLAN8    ? DFA_MCCLELLAN8
                                   : opts.outfixKind == OUTFIX_MCCLELLAN16 ? DFA_MCCLELLAN16
@@ -683,7 +683,7 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
         dkeys.emplace(p.report, (u32)dkeys.size());
     }
     Blob blob((u32)HSB_ROUNDUP(sizeof(RoseEngine), 64));
-    RawNfa32 nfa;
+    RawNfa nfa;
     regexNfaInit(&nfa);
     u32 minLen = ~0u;
     std::map<std::pair<u32, int>, u32> progOf; /* (report id, offset_adjust) -> its report program */
@@ -760,7 +760,7 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
     t.canExhaust = allHighlander;
     std::vector<u8> eng;
     try {
-        eng = emitLimEx32(nfa);
+        eng = emitLimEx(nfa);
     } catch (const std::runtime_error &e) {
         throw CompileError{std::string("Unable to build the NFA: ") + e.what(), -1};
     }

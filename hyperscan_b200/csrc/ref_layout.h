@@ -356,7 +356,7 @@ struct InstrSetExhaust { u8 code; u32 ekey; };
 /* ---- NFA engines (DFA subset): src/nfa/nfa_internal.h:53-126,
  *      src/nfa/mcclellan_internal.h:36-106 -------------------------------- */
 
-enum { NFA_LIMEX_32 = 0, NFA_MCCLELLAN_8 = 6, NFA_MCCLELLAN_16 = 7, NFA_SHENG = 17 };
+enum { NFA_LIMEX_32 = 0, NFA_LIMEX_64 = 1, NFA_MCCLELLAN_8 = 6, NFA_MCCLELLAN_16 = 7, NFA_SHENG = 17 };
 
 struct alignas(64) NFA {
     u32 flags;
@@ -429,6 +429,27 @@ struct LimExNFA32 {
     u32 init, initDS, accept, acceptAtEOD, accel, accelPermute, accelCompare, accel_and_friends;
     u32 compressMask, exceptionMask, repeatCyclicMask, zombieMask;
     u32 shift[8];
+    u32 shiftCount;
+    u8 shiftAmount[8];
+    alignas(64) u8 exceptionShufMask[64];
+    alignas(64) u8 exceptionBitMask[64];
+    alignas(64) u8 exceptionAndMask[64];
+};
+/* ... and the 64-state model (CREATE_NFA_LIMEX(64): the same fields over u64) */
+struct NFAException64 {
+    u64 squash, successors;
+    u32 reports, repeatOffset;
+    u8 hasSquash, trigger;
+};
+struct LimExNFA64 {
+    u8 reachMap[256];
+    u32 reachSize, accelCount, accelTableOffset, accelAuxCount, accelAuxOffset;
+    u32 acceptCount, acceptOffset, acceptEodCount, acceptEodOffset;
+    u32 exceptionCount, exceptionOffset, repeatCount, repeatOffset;
+    u32 squashOffset, squashCount, topCount, topOffset, stateSize, flags;
+    u64 init, initDS, accept, acceptAtEOD, accel, accelPermute, accelCompare, accel_and_friends;
+    u64 compressMask, exceptionMask, repeatCyclicMask, zombieMask;
+    u64 shift[8];
     u32 shiftCount;
     u8 shiftAmount[8];
     alignas(64) u8 exceptionShufMask[64];

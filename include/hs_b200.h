@@ -123,7 +123,7 @@ typedef int (*match_event_handler)(unsigned int id, unsigned long long from,
  * becoming one literal under the expression's id.  An expression set that is
  * not such a set (unbounded repeats, ".", negated / POSIX classes, \d \w \s,
  * "^" \A "$" \z \Z at the ends of top-level alternatives) is compiled, in block
- * mode, to ONE LimEx NFA of the 32-state model inside a single-outfix database
+ * mode, to ONE LimEx NFA of the 32- or 64-state model inside a single-outfix database
  * (ROSE_RUNTIME_SINGLE_OUTFIX) when its positions fit -- DESIGN.md section 10b.
  * Anything else (\b, look-around, back-references, larger sets, ...) yields
  * HS_COMPILER_ERROR with an explanatory hs_compile_error_t, exactly as the
@@ -483,6 +483,14 @@ long hs_b200_limex32_from_spec(unsigned nstates, const unsigned *reach256, unsig
                                const unsigned char *squash_kind, const unsigned *report_off,
                                const unsigned *reports, const unsigned *eod_off, const unsigned *eod_reports,
                                void *out, size_t cap);
+/* the same over 64-bit state sets: up to 64 states; more than 32 are emitted as the 64-state
+ * model (struct LimExNFA64, nfaExecLimEx64_Q); hs_b200_limex32_from_literals does the same
+ * for literal sets of up to 63 bytes in total */
+long hs_b200_limex_from_spec64(unsigned nstates, const unsigned long long *reach256, unsigned long long init,
+                               unsigned long long init_ds, const unsigned long long *succ,
+                               const unsigned long long *squash_mask, const unsigned char *squash_kind,
+                               const unsigned *report_off, const unsigned *reports, const unsigned *eod_off,
+                               const unsigned *eod_reports, void *out, size_t cap);
 
 /* Test hook: pure-literal block database whose literal programs are raw
  * instruction bytes (layouts: src/rose/rose_program.h:214-724).  `area` is

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE (like the rest of oracle/): a plain-Python restatement of the
-reference's LimEx-32 runtime in block mode, read straight from the engine's bytes
-(struct NFA + struct LimExNFA32, src/nfa/limex_internal.h:102-203).  Only tests/ may
+reference's LimEx runtime (32- and 64-state models) in block mode, read straight from the
+engine's bytes (struct NFA + struct LimExNFA32 / 64, src/nfa/limex_internal.h:102-203).  Only tests/ may
 import it; the product never does.
 
 Follows, for one block scanned the way Rose runs an outfix (queue {START@0, TOP@0,
@@ -15,14 +15,25 @@ END@len} through nfaExecLimEx32_Q, then nfaExecLimEx32_testEOD):
     the shift successors for LIMEX_SQUASH_CYCLIC / _REPORT
   * moProcessAccepts32 (limex_common_impl.h:116-176) and moNfaTestEod32 (:192-218)
 Bounded repeats and acceleration are not modelled (the emitters do not produce them)."""
+import json
+import os
 import struct
 
 INVALID = 0xffffffff
 NFA_HDR = 64
-O = {"reachMap": 0, "reachSize": 256, "acceptCount": 276, "acceptOffset": 280, "acceptEodCount": 284,
-     "acceptEodOffset": 288, "exceptionCount": 292, "exceptionOffset": 296, "repeatCount": 300, "flags": 328,
-     "init": 332, "initDS": 336, "accept": 340, "acceptAtEOD": 344, "exceptionMask": 368, "shift": 380,
-     "shiftCount": 412, "shiftAmount": 416, "sizeof": 640}
+# field offsets of struct LimExNFA32 / LimExNFA64 and their exception records: the reference's own
+# sizeof / offsetof, recorded in tests/golden/ref_layout.json (tests/golden/gen_ref_layout.py)
+with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                       "ref_layout.json")) as _f:
+    _LAYOUT = json.load(_f)
+
+
+def _offsets(bits):
+    name = "LimExNFA%d" % bits
+    o = {k.split(".", 1)[1]: v for k, v in _LAYOUT.items() if k.startswith(name + ".")}
+    o["sizeof"] = _LAYOUT["sizeof(%s)" % name]
+    o["exc_size"] = _LAYOUT["sizeof(NFAException%d)" % bits]
+    return o
 
 
 def _u32(b, off):
@@ -40,7 +51,7 @@ def _reports(lx, off):
 
 
 def _accepts(lx, found, mask, table, to, out, block):
-    for bit in range(32):
+    for bit in range(64):
         if not (found >> bit) & 1:
             continue
         idx = bin(mask & ((1 << bit) - 1)).count("1")
@@ -49,20 +60,28 @@ def _accepts(lx, found, mask, table, to, out, block):
             out.append((r, block, to))
 
 
+def _state(b, off, bits):
+    return struct.unpack_from("<I" if bits == 32 else "<Q", b, off)[0]
+
+
 def walk_blocks(engine, data, offsets, lengths):
     """[(report, block, to)] in callback order"""
-    assert engine[8] == 0, "not LIMEX_NFA_32"
+    assert engine[8] in (0, 1), "neither LIMEX_NFA_32 nor LIMEX_NFA_64"
+    bits = 32 if engine[8] == 0 else 64
+    full = (1 << bits) - 1
+    O = _offsets(bits)
     lx = bytes(engine[NFA_HDR:])
     assert _u32(lx, O["repeatCount"]) == 0
     reach_map = lx[0:256]
-    reach = [_u32(lx, O["sizeof"] + 4 * i) for i in range(_u32(lx, O["reachSize"]))]
+    reach = [_state(lx, O["sizeof"] + (bits // 8) * i, bits) for i in range(_u32(lx, O["reachSize"]))]
     nshift = _u32(lx, O["shiftCount"])
-    shifts = [(_u32(lx, O["shift"] + 4 * k), lx[O["shiftAmount"] + k]) for k in range(nshift)]
-    emask = _u32(lx, O["exceptionMask"])
+    shifts = [(_state(lx, O["shift"] + (bits // 8) * k, bits), lx[O["shiftAmount"] + k]) for k in range(nshift)]
+    emask = _state(lx, O["exceptionMask"], bits)
     eoff = _u32(lx, O["exceptionOffset"])
-    exc = [struct.unpack_from("<IIIIBB", lx, eoff + 20 * i) for i in range(_u32(lx, O["exceptionCount"]))]
-    accept, accept_eod = _u32(lx, O["accept"]), _u32(lx, O["acceptAtEOD"])
-    init = _u32(lx, O["init"])
+    fmt = "<IIIIBB" if bits == 32 else "<QQIIBB"
+    exc = [struct.unpack_from(fmt, lx, eoff + O["exc_size"] * i) for i in range(_u32(lx, O["exceptionCount"]))]
+    accept, accept_eod = _state(lx, O["accept"], bits), _state(lx, O["acceptAtEOD"], bits)
+    init = _state(lx, O["init"], bits)
     out = []
     for b, (o, n) in enumerate(zip(offsets, lengths)):
         o, n = int(o), int(n)
@@ -70,11 +89,11 @@ def walk_blocks(engine, data, offsets, lengths):
         for i in range(n):
             succ = 0
             for m, a in shifts:
-                succ |= ((s & m) << a) & 0xffffffff
+                succ |= ((s & m) << a) & full
             est = s & emask
             if est:
                 local = 0
-                for bit in range(32):
+                for bit in range(bits):
                     if not (est >> bit) & 1:
                         continue
                     squash, successors, reports, _rep, has_squash, _trig = exc[bin(emask & ((1 << bit) - 1)).count("1")]

@@ -20,9 +20,9 @@ struct limex_collect {
     void *ctx;
 };
 
-/* one block: returns 0 if the engine type is not LimEx-32 */
+/* one block: returns 0 if the engine type is neither LimEx-32 nor LimEx-64 */
 int ref_limex32_block(const struct NFA *n, const u8 *buf, size_t len, NfaCallback cb, void *ctx) {
-    if (n->type != LIMEX_NFA_32) {
+    if (n->type != LIMEX_NFA_32 && n->type != LIMEX_NFA_64) {
         return 0;
     }
     struct mq *q = (struct mq *)calloc(1, sizeof(struct mq));
@@ -41,12 +41,21 @@ int ref_limex32_block(const struct NFA *n, const u8 *buf, size_t len, NfaCallbac
     q->report_current = 0;
     q->cb = cb;
     q->context = ctx;
-    nfaExecLimEx32_queueInitState(n, q);
+    if (n->type == LIMEX_NFA_32) {
+        nfaExecLimEx32_queueInitState(n, q);
+    } else {
+        nfaExecLimEx64_queueInitState(n, q);
+    }
     pushQueue(q, MQE_START, 0);
     pushQueue(q, MQE_TOP, 0);
     pushQueue(q, MQE_END, (s64a)len);
-    nfaExecLimEx32_Q(n, q, (s64a)len);
-    nfaExecLimEx32_testEOD(n, q->state, q->streamState, len, cb, ctx);
+    if (n->type == LIMEX_NFA_32) {
+        nfaExecLimEx32_Q(n, q, (s64a)len);
+        nfaExecLimEx32_testEOD(n, q->state, q->streamState, len, cb, ctx);
+    } else {
+        nfaExecLimEx64_Q(n, q, (s64a)len);
+        nfaExecLimEx64_testEOD(n, q->state, q->streamState, len, cb, ctx);
+    }
     free(sstate);
     free(state);
     free(q);
@@ -74,9 +83,27 @@ void ref_layout_dump_limex(void) {
     SZ(NFAException32);
     OFF(NFAException32, squash); OFF(NFAException32, successors); OFF(NFAException32, reports);
     OFF(NFAException32, repeatOffset); OFF(NFAException32, hasSquash); OFF(NFAException32, trigger);
+    SZ(LimExNFA64);
+    OFF(LimExNFA64, reachMap); OFF(LimExNFA64, reachSize); OFF(LimExNFA64, accelCount);
+    OFF(LimExNFA64, accelTableOffset); OFF(LimExNFA64, accelAuxCount); OFF(LimExNFA64, accelAuxOffset);
+    OFF(LimExNFA64, acceptCount); OFF(LimExNFA64, acceptOffset); OFF(LimExNFA64, acceptEodCount);
+    OFF(LimExNFA64, acceptEodOffset); OFF(LimExNFA64, exceptionCount); OFF(LimExNFA64, exceptionOffset);
+    OFF(LimExNFA64, repeatCount); OFF(LimExNFA64, repeatOffset); OFF(LimExNFA64, squashOffset);
+    OFF(LimExNFA64, squashCount); OFF(LimExNFA64, topCount); OFF(LimExNFA64, topOffset);
+    OFF(LimExNFA64, stateSize); OFF(LimExNFA64, flags); OFF(LimExNFA64, init); OFF(LimExNFA64, initDS);
+    OFF(LimExNFA64, accept); OFF(LimExNFA64, acceptAtEOD); OFF(LimExNFA64, accel);
+    OFF(LimExNFA64, accelPermute); OFF(LimExNFA64, accelCompare); OFF(LimExNFA64, accel_and_friends);
+    OFF(LimExNFA64, compressMask); OFF(LimExNFA64, exceptionMask); OFF(LimExNFA64, repeatCyclicMask);
+    OFF(LimExNFA64, zombieMask); OFF(LimExNFA64, shift); OFF(LimExNFA64, shiftCount);
+    OFF(LimExNFA64, shiftAmount); OFF(LimExNFA64, exceptionShufMask); OFF(LimExNFA64, exceptionBitMask);
+    OFF(LimExNFA64, exceptionAndMask);
+    SZ(NFAException64);
+    OFF(NFAException64, squash); OFF(NFAException64, successors); OFF(NFAException64, reports);
+    OFF(NFAException64, repeatOffset); OFF(NFAException64, hasSquash); OFF(NFAException64, trigger);
     SZ(NFAAccept);
     OFF(NFAAccept, single_report); OFF(NFAAccept, reports); OFF(NFAAccept, squash);
     printf("  \"LIMEX_NFA_32\": %d,\n", (int)LIMEX_NFA_32);
+    printf("  \"LIMEX_NFA_64\": %d,\n", (int)LIMEX_NFA_64);
     printf("  \"LIMEX_FLAG_CANNOT_DIE\": %d,\n", (int)LIMEX_FLAG_CANNOT_DIE);
     printf("  \"LIMEX_SQUASH_CYCLIC\": %d,\n", (int)LIMEX_SQUASH_CYCLIC);
     printf("  \"LIMEX_SQUASH_REPORT\": %d,\n", (int)LIMEX_SQUASH_REPORT);

@@ -95,6 +95,8 @@ static inline void __syncthreads() { hsb_emu::blockBarrier(); }
 /* ---- scalar intrinsics ------------------------------------------------------- */
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) {
     const uint64_t v = ((uint64_t)hi << 32) | lo;
     return (uint32_t)((v << (s & 31)) >> 32);

@@ -32,7 +32,7 @@ def _lit_case(i):
 def test_literal_nfas_run_on_the_reference(hs, ref, i):
     lits, cl, ids, data, off, ln = _lit_case(i)
     eng = hs.limex32_from_literals(lits, cl, ids)
-    assert eng[8] == 0                                                # NFA.type = LIMEX_NFA_32
+    assert eng[8] == (0 if sum(map(len, lits)) < 32 else 1)            # NFA.type = LIMEX_NFA_32 / _64
     got = _triples(ref.nfa_exec_blocks(eng, data, off, ln))
     want = brute.scan_blocks(lits, cl, ids, data, off, ln)
     # one callback per accepting STATE: two literals with one report id ending together fire it twice
@@ -41,17 +41,18 @@ def test_literal_nfas_run_on_the_reference(hs, ref, i):
     assert len(got) > 20
 
 
-def _random_nfa(seed):
+def _random_nfa(seed, wide=False):
     """reach, init, succ, reports, eod reports, squash: anything goes -- the reference runs any
     well-formed LimEx structure, so the emitter's choice of shifts / exceptions is exercised too"""
     rng = np.random.default_rng(seed)
-    n = int(rng.integers(2, 33))
+    n = int(rng.integers(33, 65)) if wide else int(rng.integers(2, 33))
     full = (1 << n) - 1
     classes = rng.integers(0, 5, size=256)
-    masks = [int(rng.integers(0, 1 << 32)) & full for _ in range(5)]
+    rand = lambda: (int(rng.integers(0, 1 << 32)) | (int(rng.integers(0, 1 << 32)) << 32)) & full
+    masks = [rand() for _ in range(5)]
     masks[0] |= 1                                                     # keep the automaton alive on class 0
-    reach = np.array([masks[c] for c in classes], dtype=np.uint32)
-    succ = np.zeros(n, dtype=np.uint32)
+    reach = np.array([masks[c] for c in classes], dtype=np.uint64)
+    succ = np.zeros(n, dtype=np.uint64)
     for s in range(n):
         m = 0
         if rng.random() < 0.8 and s + 1 < n:
@@ -60,15 +61,23 @@ def _random_nfa(seed):
             m |= 1 << int(rng.integers(0, n))
         if rng.random() < 0.3:
             m |= 1 << s
-        succ[s] = m
-    succ[0] |= 1
+        succ[s] = np.uint64(m)
+    succ[0] |= np.uint64(1)
     reports = [sorted(set(rng.integers(0, 6, size=int(rng.integers(1, 3))).tolist())) if rng.random() < 0.25 else []
                for _ in range(n)]
     eod = [[int(rng.integers(50, 54))] if rng.random() < 0.2 else [] for _ in range(n)]
     kind = np.array([int(rng.choice([0, 0, 0, 1, 3])) for _ in range(n)], dtype=np.uint8)
-    sqm = np.array([int(rng.integers(0, 1 << 32)) & full for _ in range(n)], dtype=np.uint32)
-    init = 1 | (int(rng.integers(0, 1 << 32)) & full & 0x7)
+    sqm = np.array([rand() for _ in range(n)], dtype=np.uint64)
+    init = 1 | (rand() & 0x7)
     return reach, init, succ, reports, eod, sqm, kind
+
+
+def _emit(hs, spec):
+    reach, init, succ, reports, eod, sqm, kind = spec
+    if len(succ) <= 32 and int(np.max(reach)) < (1 << 32):
+        return hs.limex32_from_spec(reach.astype(np.uint32), init, init, succ.astype(np.uint32), reports, eod,
+                                    sqm.astype(np.uint32), kind)
+    return hs.limex_from_spec64(reach, init, init, succ, reports, eod, sqm, kind)
 
 
 def _random_corpus(seed):
@@ -77,10 +86,11 @@ def _random_corpus(seed):
     return rng.integers(0, 256, size=data.size, dtype=np.uint8), off, ln
 
 
+@pytest.mark.parametrize("wide", [False, True])
 @pytest.mark.parametrize("seed", range(12))
-def test_random_nfas_reference_equals_restatement(hs, ref, seed):
-    reach, init, succ, reports, eod, sqm, kind = _random_nfa(seed)
-    eng = hs.limex32_from_spec(reach, init, init, succ, reports, eod, sqm, kind)
+def test_random_nfas_reference_equals_restatement(hs, ref, seed, wide):
+    eng = _emit(hs, _random_nfa(seed, wide))
+    assert eng[8] == (1 if wide else 0)
     data, off, ln = _random_corpus(100 + seed)
     got = _triples(ref.nfa_exec_blocks(eng, data, off, ln))
     assert got == sorted(model.walk_blocks(eng, data, off, ln))
@@ -88,8 +98,9 @@ def test_random_nfas_reference_equals_restatement(hs, ref, seed):
 
 def test_builder_limits(hs):
     with pytest.raises(hs.HsError):
-        hs.limex32_from_literals([b"a" * 32], [0], [1])              # 33 states
+        hs.limex32_from_literals([b"a" * 64], [0], [1])              # 65 states
     assert hs.limex32_from_literals([b"a" * 31], [0], [1])[8] == 0
+    assert hs.limex32_from_literals([b"a" * 32], [0], [1])[8] == 1   # 33 states: the 64-state model
 
 
 # ---- device --------------------------------------------------------------------------------
@@ -106,10 +117,10 @@ def test_device_limex_equals_reference_literals(hs, ref, i):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("wide", [False, True])
 @pytest.mark.parametrize("seed", range(24))
-def test_device_limex_equals_reference_random(hs, ref, seed):
-    reach, init, succ, reports, eod, sqm, kind = _random_nfa(seed)
-    eng = hs.limex32_from_spec(reach, init, init, succ, reports, eod, sqm, kind)
+def test_device_limex_equals_reference_random(hs, ref, seed, wide):
+    eng = _emit(hs, _random_nfa(seed, wide))
     data, off, ln = _random_corpus(200 + seed)
     corpus = hs.Corpus.upload(data, off, ln)
     got, ms = hs.nfa_scan_corpus(eng, corpus, cap=64)                 # forces the grow-and-retry path

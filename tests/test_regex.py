@@ -73,7 +73,7 @@ def test_several_expressions_share_one_nfa_and_report_rules_hold(hs, ref):
 
 @pytest.mark.parametrize("pat,msg", [
     (rb"a*", "empty"), (rb"a$b", "'$'"), (rb"(a$|b)c", "'$'"), (rb"\bab", "Escape"), (rb"(?=a)b", "look-around"), (rb"a++b", "Possessive"),
-    (rb"(a|b)\1", "Escape"), (rb"[a-z]{40}x+", "too large"), (rb"abcdefghijklmnopqrstuvwxyz0123456+", "too large")])
+    (rb"(a|b)\1", "Escape"), (rb"[a-z]{70}x+", "too large"), (rb"(abcdefghijklmnopqrstuvwxyz0123456){2}+", "Possessive"), (rb"abcdefghijklmnopqrstuvwxyz0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ_+", "too large")])
 def test_what_the_nfa_route_refuses(hs, pat, msg):
     with pytest.raises(hs.HsError) as e:
         hs.compile_multi([pat], [0], [1])
