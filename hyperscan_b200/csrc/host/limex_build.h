@@ -31,6 +31,7 @@ struct RawNfa {
     u64 reach[256] = {0};              /* states that may be ON after consuming the byte */
     u64 init = 0, initDS = 0;          /* switched on by a top at offset 0 / at a later offset */
     u32 mlStartState = 0;              /* regex_nfa.cpp: the shared "after a newline" state, 0 = none yet */
+    u32 ctxWord = 0, ctxNonWord = 0;   /* regex_nfa.cpp: "the previous byte is / is not a word character" */
     std::vector<u64> succ;             /* [state] successor set */
     std::vector<u64> squashMask;       /* [state] kept states when the exception's squash applies */
     std::vector<u8> squashKind;        /* [state] LIMEX_SQUASH_NONE / _CYCLIC / _REPORT */

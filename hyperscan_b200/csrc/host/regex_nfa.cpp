@@ -15,7 +15,8 @@ namespace {
 typedef std::bitset<256> CharSet;
 
 struct Node {
-    enum Kind { CLASS, CAT, ALT, STAR, PLUS, OPT, EMPTY } kind = EMPTY;
+    enum Kind { CLASS, CAT, ALT, STAR, PLUS, OPT, EMPTY, ASSERT } kind = EMPTY;
+    int assertKind = 0;    /* ASSERT: 1 = \\b (word boundary), 2 = \\B (not a word boundary) */
     CharSet cls;
     std::vector<std::shared_ptr<Node>> kids;
     bool anchored = false; /* top-level alternative that starts with "^" / "\\A" */
@@ -173,6 +174,9 @@ private:
             return a;
         }
         const char c = re[pos];
+        if (a->kind == Node::ASSERT && (c == '*' || c == '+' || c == '?' || c == '{')) {
+            fail("A quantifier on \\b / \\B is not supported.");
+        }
         unsigned lo = 1;
         long hi = 1;
         if (c == '*') {
@@ -429,6 +433,12 @@ private:
         if (c == '[') {
             return leaf(charClass());
         }
+        if (c == '\\' && pos + 1 < n && (re[pos + 1] == 'b' || re[pos + 1] == 'B')) {
+            NodeP a = mk(Node::ASSERT);
+            a->assertKind = re[pos + 1] == 'b' ? 1 : 2;
+            pos += 2;
+            return a;
+        }
         if (c == '\\') {
             int single;
             CharSet s = escape(false, &single);
@@ -463,6 +473,8 @@ private:
 struct Glushkov {
     std::vector<CharSet> cls;         /* per position */
     std::vector<u64> follow;          /* per position: bitmask over positions */
+    std::vector<int> assertion;       /* per position: 0 = a character position, 1 / 2 = a zero-width \\b / \\B
+                                       * pseudo-position (eliminated by resolveAssertions) */
     struct Sets {
         bool nullable;
         u64 first, last;
@@ -479,6 +491,17 @@ struct Glushkov {
             const u32 p = (u32)cls.size();
             cls.push_back(n->cls);
             follow.push_back(0);
+            assertion.push_back(0);
+            return {false, 1ull << p, 1ull << p};
+        }
+        case Node::ASSERT: {
+            if (cls.size() >= 62) {
+                throw RegexError{"Pattern is too large: more than 62 character positions need the larger NFA models."};
+            }
+            const u32 p = (u32)cls.size();
+            cls.push_back(CharSet());
+            follow.push_back(0);
+            assertion.push_back(n->assertKind);
             return {false, 1ull << p, 1ull << p};
         }
         case Node::CAT: {
@@ -521,7 +544,102 @@ struct Glushkov {
             }
         }
     }
+
+    /* ---- zero-width assertions --------------------------------------------------------------
+     * A path between two character positions p -> q may cross \b / \B pseudo-positions; what they
+     * assert is about the two characters on either side: (p is a word character) != / == (q is).
+     * need: bit 0 = some \b crossed, bit 1 = some \B crossed. */
+    static bool holds(u32 need, bool leftWord, bool rightWord) {
+        return !((need & 1) && leftWord == rightWord) && !((need & 2) && leftWord != rightWord);
+    }
+    bool isWord(u32 p) const { /* positions of an expression with assertions are split: all word or none */
+        static const CharSet W = wordSet();
+        return (cls[p] & W).any();
+    }
+    static CharSet wordSet() {
+        CharSet w;
+        for (int c = '0'; c <= '9'; c++) w[(size_t)c] = true;
+        for (int c = 'a'; c <= 'z'; c++) w[(size_t)c] = w[(size_t)(c - 32)] = true;
+        w['_'] = true;
+        return w;
+    }
+    /* character positions reachable from the position set `from` through assertion pseudo-positions only,
+     * each with the assertions crossed: out[(q, need)] */
+    void reachThroughAssertions(u64 from, u32 need, std::vector<std::pair<u32, u32>> *out,
+                                std::vector<u8> *seen /* [position][need] */) const {
+        for (u32 x = 0; x < cls.size(); x++) {
+            if (!((from >> x) & 1)) {
+                continue;
+            }
+            if (!assertion[x]) {
+                out->push_back({x, need});
+                continue;
+            }
+            const u32 n2 = need | (u32)assertion[x];
+            u8 &mark = (*seen)[x * 4 + n2];
+            if (mark) {
+                continue;
+            }
+            mark = 1;
+            reachThroughAssertions(follow[x], n2, out, seen);
+        }
+    }
+    /* the assertion sets under which a path from p (exclusive) through assertions only ends in `last` */
+    void exitsThroughAssertions(u64 from, u32 need, u64 last, std::vector<u32> *needs, std::vector<u8> *seen) const {
+        for (u32 x = 0; x < cls.size(); x++) {
+            if (!((from >> x) & 1) || !assertion[x]) {
+                continue;
+            }
+            const u32 n2 = need | (u32)assertion[x];
+            u8 &mark = (*seen)[x * 4 + n2];
+            if (mark) {
+                continue;
+            }
+            mark = 1;
+            if ((last >> x) & 1) {
+                needs->push_back(n2);
+            }
+            exitsThroughAssertions(follow[x], n2, last, needs, seen);
+        }
+    }
+    bool anyAssertion() const {
+        for (int a : assertion) {
+            if (a) return true;
+        }
+        return false;
+    }
 };
+
+bool hasAssertion(const NodeP &n) {
+    if (n->kind == Node::ASSERT) {
+        return true;
+    }
+    for (const NodeP &k : n->kids) {
+        if (hasAssertion(k)) return true;
+    }
+    return false;
+}
+
+/* an expression with \b / \B: every class that mixes word and non-word characters becomes an
+ * alternation of its two halves, so that each character position is one or the other */
+void splitByWordness(NodeP &n) {
+    if (n->kind == Node::CLASS) {
+        const CharSet W = Glushkov::wordSet();
+        const CharSet w = n->cls & W, o = n->cls & ~W;
+        if (w.any() && o.any()) {
+            NodeP a = mk(Node::ALT);
+            NodeP l = mk(Node::CLASS), r = mk(Node::CLASS);
+            l->cls = w;
+            r->cls = o;
+            a->kids = {l, r};
+            n = a;
+        }
+        return;
+    }
+    for (NodeP &k : n->kids) {
+        splitByWordness(k);
+    }
+}
 
 u32 minLenOf(const NodeP &n) {
     switch (n->kind) {
@@ -581,9 +699,13 @@ RegexInfo regexInfo(const char *re, unsigned flags) {
     Glushkov g;
     RegexInfo info;
     info.minLen = ~0u;
-    for (const NodeP &arm : topArms(root)) {
+    for (NodeP arm : topArms(root)) {
+        if (hasAssertion(arm)) {
+            splitByWordness(arm);
+            info.needsAdjust = true; /* an assertion at the end looks one byte ahead */
+        }
         const Glushkov::Sets s = g.build(arm);
-        if (s.nullable) {
+        if (s.nullable || minLenOf(arm) == 0) {
             throw RegexError{"Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY to enable support."};
         }
         info.minLen = std::min(info.minLen, minLenOf(arm));
@@ -612,58 +734,117 @@ void regexNfaInit(RawNfa *nfa) {
 
 void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline) {
     const NodeP root = Parser(re, flags).parse();
-    for (const NodeP &arm : topArms(root)) {
-        Glushkov g;
-        const Glushkov::Sets s = g.build(arm);
-        if (s.nullable) {
-            throw RegexError{"Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY to enable support."};
-        }
-        const u32 base = nfa->nstates;
-        const u32 np = (u32)g.cls.size();
-        if (base + np > 64) {
+    const CharSet W = Glushkov::wordSet();
+    auto newState = [&]() -> u32 {
+        if (nfa->nstates >= 64) {
             throw RegexError{"Pattern set is too large: its character positions exceed the 64-state NFA model."};
         }
-        nfa->nstates += np;
-        nfa->succ.resize(nfa->nstates, 0);
-        nfa->squashMask.resize(nfa->nstates, ~0ull);
-        nfa->squashKind.resize(nfa->nstates, LIMEX_SQUASH_NONE);
-        nfa->reports.resize(nfa->nstates);
-        nfa->reportsEod.resize(nfa->nstates);
-        auto newState = [&]() -> u32 {
-            if (nfa->nstates >= 64) {
-                throw RegexError{"Pattern set is too large: its character positions exceed the 64-state NFA model."};
+        nfa->nstates++;
+        nfa->succ.push_back(0);
+        nfa->squashMask.push_back(~0ull);
+        nfa->squashKind.push_back(LIMEX_SQUASH_NONE);
+        nfa->reports.emplace_back();
+        nfa->reportsEod.emplace_back();
+        return nfa->nstates - 1;
+    };
+    auto reachClass = [&](u32 st, const CharSet &c) {
+        for (u32 b = 0; b < 256; b++) {
+            if (c[b]) {
+                nfa->reach[b] |= 1ull << st;
             }
-            nfa->nstates++;
-            nfa->succ.push_back(0);
-            nfa->squashMask.push_back(~0ull);
-            nfa->squashKind.push_back(LIMEX_SQUASH_NONE);
-            nfa->reports.emplace_back();
-            nfa->reportsEod.emplace_back();
-            return nfa->nstates - 1;
-        };
-        const bool isCat = arm->kind == Node::CAT;
-        if (isCat && arm->mlStart) {
-            /* "^" under (?m): entered at offset 0 (anchored start) or right after any newline --
-             * one state shared by all such alternatives, on after every '\n' */
-            if (!nfa->mlStartState) {
-                nfa->mlStartState = newState();
-                nfa->reach[(u8)'\n'] |= 1ull << nfa->mlStartState;
-                nfa->succ[0] |= 1ull << nfa->mlStartState;
-            }
-            nfa->succ[1] |= s.first << base;
-            nfa->succ[nfa->mlStartState] |= s.first << base;
-        } else {
-            nfa->succ[isCat && arm->anchored ? 1 : 0] |= s.first << base;
         }
+    };
+    for (NodeP arm : topArms(root)) {
+        const bool asserts = hasAssertion(arm);
+        if (asserts) {
+            splitByWordness(arm);
+        }
+        Glushkov g;
+        const Glushkov::Sets s = g.build(arm);
+        if (s.nullable || minLenOf(arm) == 0) {
+            throw RegexError{"Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY to enable support."};
+        }
+        const u32 np = (u32)g.cls.size();
+        /* NFA state of every character position (assertion pseudo-positions get none) */
+        std::vector<u32> st(np, 0);
         for (u32 p = 0; p < np; p++) {
-            nfa->succ[base + p] |= g.follow[p] << base;
-            for (u32 b = 0; b < 256; b++) {
-                if (g.cls[p][b]) {
-                    nfa->reach[b] |= 1ull << (base + p);
+            if (!g.assertion[p]) {
+                st[p] = newState();
+                reachClass(st[p], g.cls[p]);
+            }
+        }
+        const bool isCat = arm->kind == Node::CAT;
+        const Node::End end = isCat ? arm->end : Node::END_NONE;
+        if (asserts && end != Node::END_NONE) {
+            /* (an assertion elsewhere in the alternative would be fine, but telling them apart is not worth it) */
+            throw RegexError{"\\b / \\B together with '$' / \\z / \\Z in one alternative is not supported."};
+        }
+
+        /* --- transitions between character positions --- */
+        for (u32 p = 0; p < np; p++) {
+            if (g.assertion[p]) {
+                continue;
+            }
+            std::vector<std::pair<u32, u32>> to;
+            std::vector<u8> seen(np * 4, 0);
+            g.reachThroughAssertions(g.follow[p], 0, &to, &seen);
+            for (const auto &e : to) {
+                if (Glushkov::holds(e.second, g.isWord(p), g.isWord(e.first))) {
+                    nfa->succ[st[p]] |= 1ull << st[e.first];
                 }
             }
         }
-        const Node::End end = isCat ? arm->end : Node::END_NONE;
+
+        /* --- entries --- */
+        std::vector<std::pair<u32, u32>> entries;
+        {
+            std::vector<u8> seen(np * 4, 0);
+            g.reachThroughAssertions(s.first, 0, &entries, &seen);
+        }
+        const bool mlStart = isCat && arm->mlStart, anchored = isCat && arm->anchored;
+        if (mlStart && !nfa->mlStartState) {
+            /* "^" under (?m): entered at offset 0 (anchored start) or right after any newline --
+             * one state shared by all such alternatives, on after every '\n' */
+            nfa->mlStartState = newState();
+            nfa->reach[(u8)'\n'] |= 1ull << nfa->mlStartState;
+            nfa->succ[0] |= 1ull << nfa->mlStartState;
+        }
+        for (const auto &e : entries) {
+            const u64 bit = 1ull << st[e.first];
+            const bool qw = asserts && g.isWord(e.first);
+            if (mlStart || anchored) {
+                /* what precedes is the start of the data or a newline: not a word character */
+                if (Glushkov::holds(e.second, false, qw)) {
+                    nfa->succ[1] |= bit;
+                    if (mlStart) {
+                        nfa->succ[nfa->mlStartState] |= bit;
+                    }
+                }
+            } else if (e.second == 0) {
+                nfa->succ[0] |= bit;
+            } else {
+                /* a leading assertion in a floating alternative: the byte before the match decides.  Two
+                 * shared context states hang off the floating start: "previous byte is a word character"
+                 * and "previous byte is none, or not a word character" (the latter also on at offset 0) */
+                if (!nfa->ctxWord) {
+                    nfa->ctxWord = newState();
+                    nfa->ctxNonWord = newState();
+                    reachClass(nfa->ctxWord, W);
+                    reachClass(nfa->ctxNonWord, ~W);
+                    nfa->succ[0] |= (1ull << nfa->ctxWord) | (1ull << nfa->ctxNonWord);
+                    nfa->init |= 1ull << nfa->ctxNonWord;
+                    nfa->initDS |= 1ull << nfa->ctxNonWord;
+                }
+                if (Glushkov::holds(e.second, true, qw)) {
+                    nfa->succ[nfa->ctxWord] |= bit;
+                }
+                if (Glushkov::holds(e.second, false, qw)) {
+                    nfa->succ[nfa->ctxNonWord] |= bit;
+                }
+            }
+        }
+
+        /* --- accepts --- */
         u32 nl = 0;
         if (end == Node::END_DOLLAR || end == Node::END_ML_DOLLAR) {
             /* the expression's end may sit before a newline: a state for that newline, whose report is
@@ -679,16 +860,50 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                 nfa->reports[nl].push_back(reportBeforeNewline);
             }
         }
+        u32 aheadWord = 0, aheadNonWord = 0; /* trailing assertion: one byte of look-ahead, reported one byte back */
         for (u32 p = 0; p < np; p++) {
-            if (!((s.last >> p) & 1)) {
+            if (g.assertion[p]) {
                 continue;
             }
-            if (end == Node::END_NONE) {
-                nfa->reports[base + p].push_back(report);
-            } else {
-                nfa->reportsEod[base + p].push_back(report);
-                if (nl) {
-                    nfa->succ[base + p] |= 1ull << nl;
+            if ((s.last >> p) & 1) {
+                if (end == Node::END_NONE) {
+                    nfa->reports[st[p]].push_back(report);
+                } else {
+                    nfa->reportsEod[st[p]].push_back(report);
+                    if (nl) {
+                        nfa->succ[st[p]] |= 1ull << nl;
+                    }
+                }
+            }
+            if (!asserts) {
+                continue;
+            }
+            std::vector<u32> needs;
+            std::vector<u8> seen(np * 4, 0);
+            g.exitsThroughAssertions(g.follow[p], 0, s.last, &needs, &seen);
+            for (u32 need : needs) {
+                const bool pw = g.isWord(p);
+                if (Glushkov::holds(need, pw, false)) { /* the end of the data counts as a non-word character */
+                    nfa->reportsEod[st[p]].push_back(report);
+                }
+                if (!reportBeforeNewline) {
+                    throw RegexError{"internal: no adjusted report program"};
+                }
+                if (Glushkov::holds(need, pw, true)) {
+                    if (!aheadWord) {
+                        aheadWord = newState();
+                        reachClass(aheadWord, W);
+                        nfa->reports[aheadWord].push_back(reportBeforeNewline);
+                    }
+                    nfa->succ[st[p]] |= 1ull << aheadWord;
+                }
+                if (Glushkov::holds(need, pw, false)) {
+                    if (!aheadNonWord) {
+                        aheadNonWord = newState();
+                        reachClass(aheadNonWord, ~W);
+                        nfa->reports[aheadNonWord].push_back(reportBeforeNewline);
+                    }
+                    nfa->succ[st[p]] |= 1ull << aheadNonWord;
                 }
             }
         }

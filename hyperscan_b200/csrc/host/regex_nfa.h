@@ -13,8 +13,8 @@
  * or of a top-level alternative (\A likewise; under HS_FLAG_MULTILINE "^" also matches after any
  * newline), "$" / \Z (end of data or before a final newline), \z (end of data), "$" under
  * HS_FLAG_MULTILINE (before any newline or at the end) at the end of the expression or of a
- * top-level alternative, POSIX classes inside classes, a leading "(?ism)".  HS_FLAG_CASELESS
- * folds letters.  Everything else -- \b, look-around, back-references, possessive
+ * top-level alternative, \b and \B, POSIX classes inside classes, a leading "(?ism)".
+ * HS_FLAG_CASELESS folds letters.  Everything else -- look-around, back-references, possessive
  * quantifiers, anchors inside groups, UTF-8 / UCP, SOM, expressions that match the empty
  * string -- is refused with a compile error: those need parts of the reference's compiler and
  * runtime this build does not have.

@@ -36,6 +36,9 @@ def gen_atom(rng, depth):
         return (b"[^" if rng.random() < 0.3 else b"[") + body + b"]"
     if r < 0.80:
         return [rb"\d", rb"\w", rb"\s", rb"\D", rb"\W", rb"\S"][int(rng.integers(0, 6))]
+    if r < 0.86:
+        return [rb"\b", rb"\B"][int(rng.integers(0, 2))] + gen_atom(rng, depth + 1) if rng.random() < 0.5 \
+            else gen_atom(rng, depth + 1) + [rb"\b", rb"\B"][int(rng.integers(0, 2))]
     if depth >= 2:
         return b"a"
     arms = [gen_seq(rng, depth + 1) for _ in range(int(rng.integers(1, 3)))]
@@ -64,26 +67,30 @@ def gen_seq(rng, depth):
 
 
 def definition(body, flags, start, end, data):
-    rx = re.compile(body, (re.I if flags & 1 else 0) | (re.S if flags & 2 else 0))
+    """every end offset e such that the body matches some data[s:e] IN CONTEXT (\\b / \\B look at the bytes around
+    the match): for each e the body is followed by a fixed-width look-behind that pins the match end to e"""
+    fl = (re.I if flags & 1 else 0) | (re.S if flags & 2 else 0)
     n = len(data)
     ml = bool(flags & 4)
     out = set()
-    for s in range(n + 1):
-        if start and not (s == 0 or (ml and data[s - 1:s] == b"\n")):
+    for e in range(1, n + 1):
+        if end == b"":
+            ok = True
+        elif end == rb"\z":
+            ok = e == n
+        elif not ml or end == rb"\Z":   # "$" / \Z (which ignores (?m)): at the end or before a final newline
+            ok = e == n or (e == n - 1 and data[e:e + 1] == b"\n")
+        else:               # "$" under (?m): before any newline or at the end
+            ok = e == n or data[e:e + 1] == b"\n"
+        if not ok:
             continue
-        for e in range(s + 1, n + 1):
-            if not rx.fullmatch(data, s, e):
+        rx = re.compile(b"(?:" + body + b")(?<=(?s:\\A.{%d}))" % e, fl)
+        for s in range(e):
+            if start and not (s == 0 or (ml and data[s - 1:s] == b"\n")):
                 continue
-            if end == b"":
-                ok = True
-            elif end == rb"\z":
-                ok = e == n
-            elif not ml or end == rb"\Z":   # "$" / \Z (which ignores (?m)): at the end or before a final newline
-                ok = e == n or (e == n - 1 and data[e:e + 1] == b"\n")
-            else:               # "$" under (?m): before any newline or at the end
-                ok = e == n or data[e:e + 1] == b"\n"
-            if ok:
+            if rx.match(data, s):
                 out.add(e)
+                break
     return sorted(out)
 
 
@@ -95,7 +102,7 @@ def main():
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     capi.lib()
-    t0, n, refused, literal, skipped = time.time(), 0, 0, 0, 0
+    t0, n, refused, literal, skipped, asserted = time.time(), 0, 0, 0, 0, 0
 
     def on_alarm(signum, frame):
         raise TimeoutError()
@@ -125,6 +132,7 @@ def main():
         if db.info().runtime_impl != 2:
             literal += 1
         n += 1
+        asserted += (rb"\b" in body) or (rb"\B" in body)
         for trial in range(3):
             size = int(rng.integers(1, 28))
             a = np.frombuffer(ALPHA, dtype=np.uint8)
@@ -142,8 +150,9 @@ def main():
             if got != want:
                 print("MISMATCH expr", expr, "flags", flags, "data", data, "got", got, "want", want)
                 sys.exit(1)
-    print("fuzz regex: %d expressions (%d through the literal route, %d refused, %d inputs skipped: definition too "
-          "slow), all equal to the definition (%.0f s)" % (n, literal, refused, skipped, time.time() - t0))
+    print("fuzz regex: %d expressions (%d with \\b / \\B, %d through the literal route; %d refused, %d inputs skipped: "
+          "definition too slow), all equal to the definition (%.0f s)"
+          % (n, asserted, literal, refused, skipped, time.time() - t0))
 
 
 if __name__ == "__main__":

@@ -21,14 +21,22 @@ PATTERNS = [
     (rb"(ab|cd)+e", 0), (rb"[^a-z]{2,3}q", 0), (rb"fo{1,}d?", CASELESS), (rb"a(bc)?d|x+y", 0),
     (rb"^a.*b", DOTALL), (rb"\w+@\w+", 0), (rb"[a-c]{3}", 0), (rb"q\s*=\s*\d", 0), (rb"(?:ab){2,}c", 0),
     (rb"a+?b", 0), (rb"^x|y\x41z", 0), (rb"[\d\-x]+y", 0), (rb"a.{2,4}b", 0), (rb"\Sq\S", CASELESS),
+    (rb"\bab", 0), (rb"\w+\b", 0), (rb"\Bq\B", 0), (rb"a\b.\bb", 0), (rb"^\b\d", 0), (rb"x\B|\by", 0),
 ]
 ALPHA = b"abcdxyqAB.12e\nfoFOD =@-_z"
 SEED_TEXT = b"abc abbcd acbd x\ny 3.14 ababe 12q fOOd ad xxy a\nb u_1@v2 cab q = 7 ababababc aab yAz 1-x2y a123b .q, "
 
 
 def _ends(pat, flags, data):
-    rx = re.compile(pat, (re.I if flags & CASELESS else 0) | (re.S if flags & DOTALL else 0))
-    return sorted({e for s in range(len(data) + 1) for e in range(s + 1, len(data) + 1) if rx.fullmatch(data, s, e)})
+    """every end offset e such that the expression matches some data[s:e] in context (\\b / \\B see the bytes
+    around the match): a fixed-width look-behind pins the match end to e"""
+    fl = (re.I if flags & CASELESS else 0) | (re.S if flags & DOTALL else 0)
+    out = []
+    for e in range(1, len(data) + 1):
+        rx = re.compile(b"(?:" + pat + b")(?<=(?s:\\A.{%d}))" % e, fl)
+        if any(rx.match(data, s) for s in range(e)):
+            out.append(e)
+    return out
 
 
 def _data(seed, n=48):
@@ -72,7 +80,7 @@ def test_several_expressions_share_one_nfa_and_report_rules_hold(hs, ref):
 
 
 @pytest.mark.parametrize("pat,msg", [
-    (rb"a*", "empty"), (rb"a$b", "'$'"), (rb"(a$|b)c", "'$'"), (rb"\bab", "Escape"), (rb"(?=a)b", "look-around"), (rb"a++b", "Possessive"),
+    (rb"a*", "empty"), (rb"a$b", "'$'"), (rb"(a$|b)c", "'$'"), (rb"\b+ab", "quantifier"), (rb"\bab$", "together"), (rb"(?=a)b", "look-around"), (rb"a++b", "Possessive"),
     (rb"(a|b)\1", "Escape"), (rb"[a-z]{70}x+", "too large"), (rb"(abcdefghijklmnopqrstuvwxyz0123456){2}+", "Possessive"), (rb"abcdefghijklmnopqrstuvwxyz0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ_+", "too large")])
 def test_what_the_nfa_route_refuses(hs, pat, msg):
     with pytest.raises(hs.HsError) as e:
