@@ -5,7 +5,7 @@ recorded regression vectors (tools/hscollider/test_cases/{pcre,corpora}/*.txt).
 Only entries on this path are kept: patterns this library's hs_compile compiles through
 its NFA route (expressions that are NOT a finite set of literals and fit the LimEx-32 model:
 regex_nfa.h; database runtimeImpl = ROSE_RUNTIME_SINGLE_OUTFIX) with flags out of
-{i, s, H, O}, together with the corpora
+{i, s, m, H, O}, together with the corpora
 lines that carry recorded match offsets (`id="data": to1,to2,...`, format per
 tools/hscollider/ColliderCorporaParser.rl:100-150; pattern flag letters per
 util/ExpressionParser.rl:60-85).  The pattern TEXT and the recorded offsets are
@@ -30,7 +30,7 @@ from hyperscan_b200 import capi  # noqa: E402
 import oracle.ref as ref  # noqa: E402
 
 BASE = "/root/reference/tools/hscollider/test_cases"
-FLAG = {"i": capi.HS_FLAG_CASELESS, "s": 2, "H": capi.HS_FLAG_SINGLEMATCH, "O": 0}
+FLAG = {"i": capi.HS_FLAG_CASELESS, "s": 2, "m": 4, "H": capi.HS_FLAG_SINGLEMATCH, "O": 0}
 SPECIAL = {"0": 0, "a": 7, "e": 27, "f": 12, "n": 10, "v": 11, "r": 13, "t": 9}
 
 
