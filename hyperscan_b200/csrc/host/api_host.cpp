@@ -641,7 +641,7 @@ private:
             const int h1 = pos < n ? hexval(re[pos]) : -1;
             const int h2 = pos + 1 < n ? hexval(re[pos + 1]) : -1;
             if (h1 < 0 || h2 < 0) {
-                fail("Invalid hex escape; only \\xHH is accepted.");
+                needsRegex("A hex escape other than \\xHH");
             }
             pos += 2;
             return (unsigned char)(h1 * 16 + h2);

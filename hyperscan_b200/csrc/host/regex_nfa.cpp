@@ -16,12 +16,23 @@ typedef std::bitset<256> CharSet;
 
 struct Node {
     enum Kind { CLASS, CAT, ALT, STAR, PLUS, OPT, EMPTY, ASSERT } kind = EMPTY;
-    int assertKind = 0;    /* ASSERT: 1 = \\b (word boundary), 2 = \\B (not a word boundary) */
+    int assertKind = 0;    /* ASSERT: one of the A_* bits below */
     CharSet cls;
     std::vector<std::shared_ptr<Node>> kids;
-    bool anchored = false; /* top-level alternative that starts with "^" / "\\A" */
-    bool mlStart = false;  /* ... with "^" under HS_FLAG_MULTILINE: at offset 0 or right after a newline */
-    enum End { END_NONE, END_EOD, END_DOLLAR, END_ML_DOLLAR } end = END_NONE; /* "\\z" | "$", "\\Z" | "$" under (?m) */
+};
+/* zero-width assertions; a path through several of them carries the union of their bits */
+enum {
+    A_WORD_B = 1,      /* \\b */
+    A_NOT_WORD_B = 2,  /* \\B */
+    A_BEGIN = 4,       /* \\A, "^": offset 0 */
+    A_BEGIN_LINE = 8,  /* "^" under HS_FLAG_MULTILINE: offset 0 or right after a newline */
+    A_END = 16,        /* \\z: end of the data */
+    A_END_LF = 32,     /* "$", \\Z: end of the data, or before a newline that ends the data */
+    A_END_LINE = 64,   /* "$" under HS_FLAG_MULTILINE: end of the data or before any newline */
+    A_BOUNDARY = A_WORD_B | A_NOT_WORD_B,
+    A_STARTS = A_BEGIN | A_BEGIN_LINE,
+    A_ENDS = A_END | A_END_LF | A_END_LINE,
+    A_ALL = 127
 };
 typedef std::shared_ptr<Node> NodeP;
 
@@ -50,23 +61,14 @@ public:
         if (flags & HS_FLAG_SOM_LEFTMOST) {
             fail("HS_FLAG_SOM_LEFTMOST is not supported.");
         }
-        /* leading option group "(?ism)": as if the flags had been passed */
-        if (n >= 4 && re[0] == '(' && re[1] == '?') {
-            size_t q = 2;
-            unsigned add = 0;
-            while (q < n && (re[q] == 'i' || re[q] == 's' || re[q] == 'm')) {
-                add |= re[q] == 'i' ? HS_FLAG_CASELESS : re[q] == 's' ? HS_FLAG_DOTALL : HS_FLAG_MULTILINE;
-                q++;
-            }
-            if (q > 2 && q < n && re[q] == ')') {
-                flags |= add;
-                pos = q + 1;
-            }
-        }
-        NodeP r = alt(true);
+        NodeP r = alt();
         if (pos != n) {
             fail("Unmatched parentheses.");
         }
+        /* anchors only where the reference takes them (ComponentBoundary::checkEmbeddedStartAnchor / EndAnchor,
+         * src/parser/ComponentBoundary.cpp:162-185, and the callers' rules in ComponentSequence / Alternation / Repeat) */
+        embeddedStart(r, true);
+        embeddedEnd(r, true);
         return r;
     }
 
@@ -74,6 +76,7 @@ private:
     const char *re;
     size_t n, pos = 0;
     unsigned flags;
+    bool quoting = false; /* between \\Q and \\E: every byte is a literal */
 
     [[noreturn]] void fail(const std::string &m) const { throw RegexError{m}; }
     bool at(char c) const { return pos < n && re[pos] == c; }
@@ -89,12 +92,12 @@ private:
         return s;
     }
 
-    NodeP alt(bool top) {
+    NodeP alt() {
         std::vector<NodeP> arms;
-        arms.push_back(seq(top));
+        arms.push_back(seq());
         while (at('|')) {
             pos++;
-            arms.push_back(seq(top));
+            arms.push_back(seq());
         }
         if (arms.size() == 1) {
             return arms[0];
@@ -104,44 +107,87 @@ private:
         return a;
     }
 
-    NodeP seq(bool top) {
+    NodeP seq() {
         NodeP s = mk(Node::CAT);
-        if (at('^') || (at('\\') && pos + 1 < n && re[pos + 1] == 'A')) {
-            if (!top) {
-                fail("'^' inside a group needs the reference's assertion handling.");
-            }
-            if (re[pos] == '^' && (flags & HS_FLAG_MULTILINE)) {
-                s->mlStart = true;
-            } else {
-                s->anchored = true;
-            }
-            pos += re[pos] == '^' ? 1 : 2;
-        }
-        while (pos < n && re[pos] != '|' && re[pos] != ')') {
-            /* end anchors: only as the last thing of a top-level alternative */
-            Node::End e = Node::END_NONE;
-            size_t len = 0;
-            if (re[pos] == '$') {
-                e = (flags & HS_FLAG_MULTILINE) ? Node::END_ML_DOLLAR : Node::END_DOLLAR;
-                len = 1;
-            } else if (re[pos] == '\\' && pos + 1 < n && (re[pos + 1] == 'z' || re[pos + 1] == 'Z')) {
-                e = re[pos + 1] == 'z' ? Node::END_EOD : Node::END_DOLLAR;
-                len = 2;
-            }
-            if (e != Node::END_NONE) {
-                if (!top || (pos + len < n && re[pos + len] != '|')) {
-                    fail("'$' / \\z / \\Z anywhere but at the end of the expression or of a top-level alternative "
-                         "needs the reference's assertion handling.");
-                }
-                pos += len;
-                s->end = e;
-                break;
-            }
+        while (pos < n && (quoting || (re[pos] != '|' && re[pos] != ')'))) {
             NodeP a = atom();
             a = quantified(a);
             s->kids.push_back(a);
         }
         return s;
+    }
+
+    /* may the match still start here (nothing consumed before on any way to this node)?  A start anchor
+     * anywhere else is refused, as the reference does. */
+    static bool embeddedStart(const NodeP &x, bool atStart) {
+        switch (x->kind) {
+        case Node::CLASS:
+            return false;
+        case Node::EMPTY:
+            return atStart;
+        case Node::ASSERT:
+            if (x->assertKind & A_BOUNDARY) {
+                return false;
+            }
+            if ((x->assertKind & A_STARTS) && !atStart) {
+                throw RegexError{"Embedded start anchors not supported."};
+            }
+            return atStart;
+        case Node::CAT:
+            for (const NodeP &k : x->kids) {
+                atStart = embeddedStart(k, atStart);
+            }
+            return atStart;
+        case Node::ALT: {
+            bool rv = true;
+            for (const NodeP &k : x->kids) {
+                rv &= embeddedStart(k, atStart);
+            }
+            return rv;
+        }
+        case Node::STAR:
+        case Node::PLUS:
+            atStart = embeddedStart(x->kids[0], atStart);
+            return embeddedStart(x->kids[0], atStart);
+        case Node::OPT:
+            return embeddedStart(x->kids[0], atStart);
+        }
+        return false;
+    }
+    static bool embeddedEnd(const NodeP &x, bool atEnd) {
+        switch (x->kind) {
+        case Node::CLASS:
+            return false;
+        case Node::EMPTY:
+            return atEnd;
+        case Node::ASSERT:
+            if (x->assertKind & A_BOUNDARY) {
+                return false;
+            }
+            if ((x->assertKind & A_ENDS) && !atEnd) {
+                throw RegexError{"Embedded end anchors not supported."};
+            }
+            return atEnd;
+        case Node::CAT:
+            for (auto k = x->kids.rbegin(); k != x->kids.rend(); ++k) {
+                atEnd = embeddedEnd(*k, atEnd);
+            }
+            return atEnd;
+        case Node::ALT: {
+            bool rv = true;
+            for (const NodeP &k : x->kids) {
+                rv &= embeddedEnd(k, atEnd);
+            }
+            return rv;
+        }
+        case Node::STAR:
+        case Node::PLUS:
+            atEnd = embeddedEnd(x->kids[0], atEnd);
+            return embeddedEnd(x->kids[0], atEnd);
+        case Node::OPT:
+            return embeddedEnd(x->kids[0], atEnd);
+        }
+        return false;
     }
 
     NodeP repeat(const NodeP &a, unsigned lo, long hi /* -1 = unbounded */) {
@@ -170,12 +216,16 @@ private:
     }
 
     NodeP quantified(NodeP a) {
-        if (pos >= n) {
+        while (pos + 1 < n && re[pos] == '\\' && re[pos + 1] == 'E') { /* "\\Qab\\E+": the quantifier binds to the "b" */
+            quoting = false;
+            pos += 2;
+        }
+        if (pos >= n || quoting) {
             return a;
         }
         const char c = re[pos];
         if (a->kind == Node::ASSERT && (c == '*' || c == '+' || c == '?' || c == '{')) {
-            fail("A quantifier on \\b / \\B is not supported.");
+            fail("A quantifier on an assertion is not supported.");
         }
         unsigned lo = 1;
         long hi = 1;
@@ -302,19 +352,69 @@ private:
         case 'e': *single = 0x1b; break;
         case 'd': case 'D': case 'w': case 'W': case 's': case 'S':
             return classEscape((char)e);
+        case 'h': case 'H': /* horizontal white space, 8-bit: \t, space, 0xa0 */
+            s['\t'] = s[' '] = s[0xa0] = true;
+            return e == 'H' ? ~s : s;
+        case 'v': case 'V': /* vertical white space, 8-bit: \n \v \f \r, 0x85 */
+            s['\n'] = s[0x0b] = s['\f'] = s['\r'] = s[0x85] = true;
+            return e == 'V' ? ~s : s;
+        case 'N': /* not a newline, whatever HS_FLAG_DOTALL says */
+            s.set();
+            s['\n'] = false;
+            return s;
         case 'x': {
-            const int h1 = pos < n ? hexval(re[pos]) : -1;
-            const int h2 = pos + 1 < n ? hexval(re[pos + 1]) : -1;
-            if (h1 < 0 || h2 < 0) {
-                fail("Invalid hex escape; only \\xHH is accepted.");
+            if (pos < n && re[pos] == '{') { /* \x{h..h} */
+                size_t q = pos + 1;
+                unsigned long v = 0;
+                while (q < n && hexval(re[q]) >= 0) {
+                    v = std::min(v * 16 + (unsigned long)hexval(re[q]), 0x10000ul);
+                    q++;
+                }
+                if (q == pos + 1 || q >= n || re[q] != '}') {
+                    fail("Invalid hex escape: \\x{ without hexadecimal digits and a closing brace.");
+                }
+                if (v > 0xff) {
+                    fail("Hexadecimal value is greater than \\xFF.");
+                }
+                pos = q + 1;
+                *single = (int)v;
+                break;
             }
-            pos += 2;
-            *single = h1 * 16 + h2;
+            int v = 0; /* \x followed by up to two hexadecimal digits (none: a NUL byte) */
+            for (int k = 0; k < 2 && pos < n && hexval(re[pos]) >= 0; k++) {
+                v = v * 16 + hexval(re[pos++]);
+            }
+            *single = v;
+            break;
+        }
+        case 'c': { /* control character: the next byte, upper-cased, with bit 6 flipped */
+            if (pos >= n) {
+                fail("\\c at end of pattern.");
+            }
+            const unsigned char x = (unsigned char)re[pos++];
+            if (x >= 128) {
+                fail("\\c must be followed by an ASCII character.");
+            }
+            *single = toupper(x) ^ 0x40;
+            break;
+        }
+        case '0': { /* \0 and up to two more octal digits */
+            int v = 0;
+            for (int k = 0; k < 2 && pos < n && re[pos] >= '0' && re[pos] <= '7'; k++) {
+                v = v * 8 + (re[pos++] - '0');
+            }
+            *single = v;
             break;
         }
         default:
             if (inClass && e == 'b') {
                 *single = 0x08;
+            } else if (inClass && e >= '1' && e <= '7') { /* no back-references in a class: octal, up to three digits */
+                int v = e - '0';
+                for (int k = 0; k < 2 && pos < n && re[pos] >= '0' && re[pos] <= '7'; k++) {
+                    v = v * 8 + (re[pos++] - '0');
+                }
+                *single = v & 0xff;
             } else if (isalnum(e)) {
                 fail(std::string("Escape sequence \\") + (char)e + " is not supported.");
             } else {
@@ -333,17 +433,31 @@ private:
             pos++;
         }
         CharSet set;
-        bool first = true;
+        bool first = true;   /* no member yet: a "]" is a literal */
+        bool quoted = false; /* between \\Q and \\E */
         int prev = -1;
-        for (;; first = false) {
+        for (;;) {
             if (pos >= n) {
                 fail("Unterminated character class.");
             }
             const unsigned char c = (unsigned char)re[pos];
+            if (c == '\\' && pos + 1 < n && (re[pos + 1] == 'E' || (re[pos + 1] == 'Q' && !quoted))) {
+                quoted = re[pos + 1] == 'Q';
+                pos += 2;
+                continue;
+            }
+            if (quoted) {
+                set[c] = true;
+                prev = c;
+                pos++;
+                first = false;
+                continue;
+            }
             if (c == ']' && !first) {
                 pos++;
                 break;
             }
+            first = false;
             if (c == '[' && pos + 1 < n && re[pos + 1] == ':') {
                 const char *close = strstr(re + pos + 2, ":]");
                 if (!close) {
@@ -372,6 +486,9 @@ private:
                 pos++;
                 int hi;
                 if (re[pos] == '\\') {
+                    if (pos + 1 < n && (re[pos + 1] == 'Q' || re[pos + 1] == 'E')) {
+                        fail("\\Q / \\E as the end of a range is not supported.");
+                    }
                     escape(true, &hi);
                     if (hi < 0) {
                         fail("Invalid range in character class.");
@@ -413,30 +530,73 @@ private:
     }
 
     NodeP atom() {
+        /* \\Q ... \\E: literal bytes (an \\E without \\Q is ignored) */
+        while (pos + 1 < n && re[pos] == '\\' && (re[pos + 1] == 'E' || (re[pos + 1] == 'Q' && !quoting))) {
+            quoting = re[pos + 1] == 'Q';
+            pos += 2;
+        }
+        if (pos >= n || (!quoting && (re[pos] == '|' || re[pos] == ')'))) {
+            return mk(Node::EMPTY);
+        }
         const unsigned char c = (unsigned char)re[pos];
+        if (quoting) {
+            pos++;
+            CharSet s;
+            s[c] = true;
+            return leaf(fold(s));
+        }
         if (c == '(') {
             pos++;
+            const unsigned saved = flags; /* an option change lasts to the end of the group it is in */
             if (at('?')) {
-                if (pos + 1 < n && re[pos + 1] == ':') {
-                    pos += 2;
+                /* (?ims-ims) and (?ims-ims: ... ) */
+                size_t q = pos + 1;
+                unsigned on = 0, off = 0;
+                bool neg = false, any = false;
+                for (; q < n && strchr("ims-", re[q]); q++) {
+                    if (re[q] == '-') {
+                        neg = true;
+                        continue;
+                    }
+                    const unsigned f = re[q] == 'i' ? HS_FLAG_CASELESS : re[q] == 's' ? HS_FLAG_DOTALL : HS_FLAG_MULTILINE;
+                    (neg ? off : on) |= f;
+                    any = true;
+                }
+                if (q < n && re[q] == ')' && any) {
+                    flags = (flags | on) & ~off;
+                    pos = q + 1;
+                    return mk(Node::EMPTY);
+                }
+                if (q < n && re[q] == ':') {
+                    flags = (flags | on) & ~off;
+                    pos = q + 1;
                 } else {
-                    fail("Group options, look-around and named groups are not supported.");
+                    fail("Look-around, named groups, comments and the other (?...) groups are not supported.");
                 }
             }
-            NodeP r = alt(false);
+            NodeP r = alt();
             if (!at(')')) {
                 fail("Missing close parenthesis.");
             }
             pos++;
+            flags = saved;
             return r;
         }
         if (c == '[') {
             return leaf(charClass());
         }
-        if (c == '\\' && pos + 1 < n && (re[pos + 1] == 'b' || re[pos + 1] == 'B')) {
+        if (c == '\\' && pos + 1 < n && strchr("bBAzZ", re[pos + 1])) {
             NodeP a = mk(Node::ASSERT);
-            a->assertKind = re[pos + 1] == 'b' ? 1 : 2;
+            const char e = re[pos + 1];
+            a->assertKind = e == 'b' ? A_WORD_B : e == 'B' ? A_NOT_WORD_B : e == 'A' ? A_BEGIN : e == 'z' ? A_END : A_END_LF;
             pos += 2;
+            return a;
+        }
+        if (c == '^' || c == '$') {
+            NodeP a = mk(Node::ASSERT);
+            const bool ml = flags & HS_FLAG_MULTILINE;
+            a->assertKind = c == '^' ? (ml ? A_BEGIN_LINE : A_BEGIN) : (ml ? A_END_LINE : A_END_LF);
+            pos++;
             return a;
         }
         if (c == '\\') {
@@ -453,12 +613,6 @@ private:
             }
             return leaf(s);
         }
-        if (c == '$') {
-            fail("'$' needs the reference's end-of-data handling.");
-        }
-        if (c == '^') {
-            fail("'^' in the middle of an expression is not supported.");
-        }
         if (strchr("*+?{", c)) {
             fail("Invalid repeat: nothing to repeat.");
         }
@@ -473,8 +627,8 @@ private:
 struct Glushkov {
     std::vector<CharSet> cls;         /* per position */
     std::vector<u64> follow;          /* per position: bitmask over positions */
-    std::vector<int> assertion;       /* per position: 0 = a character position, 1 / 2 = a zero-width \\b / \\B
-                                       * pseudo-position (eliminated by resolveAssertions) */
+    std::vector<int> assertion;       /* per position: 0 = a character position, else the A_* bit of a zero-width
+                                       * pseudo-position (eliminated when the NFA is wired) */
     struct Sets {
         bool nullable;
         u64 first, last;
@@ -576,7 +730,7 @@ struct Glushkov {
                 continue;
             }
             const u32 n2 = need | (u32)assertion[x];
-            u8 &mark = (*seen)[x * 4 + n2];
+            u8 &mark = (*seen)[x * (A_ALL + 1) + n2];
             if (mark) {
                 continue;
             }
@@ -591,7 +745,7 @@ struct Glushkov {
                 continue;
             }
             const u32 n2 = need | (u32)assertion[x];
-            u8 &mark = (*seen)[x * 4 + n2];
+            u8 &mark = (*seen)[x * (A_ALL + 1) + n2];
             if (mark) {
                 continue;
             }
@@ -610,12 +764,12 @@ struct Glushkov {
     }
 };
 
-bool hasAssertion(const NodeP &n) {
-    if (n->kind == Node::ASSERT) {
+bool hasAssertion(const NodeP &n, int kinds) {
+    if (n->kind == Node::ASSERT && (n->assertKind & kinds)) {
         return true;
     }
     for (const NodeP &k : n->kids) {
-        if (hasAssertion(k)) return true;
+        if (hasAssertion(k, kinds)) return true;
     }
     return false;
 }
@@ -700,16 +854,16 @@ RegexInfo regexInfo(const char *re, unsigned flags) {
     RegexInfo info;
     info.minLen = ~0u;
     for (NodeP arm : topArms(root)) {
-        if (hasAssertion(arm)) {
+        if (hasAssertion(arm, A_BOUNDARY)) {
             splitByWordness(arm);
-            info.needsAdjust = true; /* an assertion at the end looks one byte ahead */
         }
+        /* an assertion at the end may look one byte ahead */
+        info.needsAdjust |= hasAssertion(arm, A_BOUNDARY | A_END_LF | A_END_LINE);
         const Glushkov::Sets s = g.build(arm);
         if (s.nullable || minLenOf(arm) == 0) {
             throw RegexError{"Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY to enable support."};
         }
         info.minLen = std::min(info.minLen, minLenOf(arm));
-        info.needsAdjust |= arm->end == Node::END_DOLLAR || arm->end == Node::END_ML_DOLLAR;
         const u64 mx = maxLenOf(arm);
         info.maxLen = std::max<u32>(info.maxLen, mx > 0xfffffffeull ? 0xffffffffu : (u32)mx);
     }
@@ -755,7 +909,7 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
         }
     };
     for (NodeP arm : topArms(root)) {
-        const bool asserts = hasAssertion(arm);
+        const bool asserts = hasAssertion(arm, A_BOUNDARY);
         if (asserts) {
             splitByWordness(arm);
         }
@@ -773,12 +927,6 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                 reachClass(st[p], g.cls[p]);
             }
         }
-        const bool isCat = arm->kind == Node::CAT;
-        const Node::End end = isCat ? arm->end : Node::END_NONE;
-        if (asserts && end != Node::END_NONE) {
-            /* (an assertion elsewhere in the alternative would be fine, but telling them apart is not worth it) */
-            throw RegexError{"\\b / \\B together with '$' / \\z / \\Z in one alternative is not supported."};
-        }
 
         /* --- transitions between character positions --- */
         for (u32 p = 0; p < np; p++) {
@@ -786,9 +934,12 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                 continue;
             }
             std::vector<std::pair<u32, u32>> to;
-            std::vector<u8> seen(np * 4, 0);
+            std::vector<u8> seen(np * (A_ALL + 1), 0);
             g.reachThroughAssertions(g.follow[p], 0, &to, &seen);
             for (const auto &e : to) {
+                if (e.second & (A_STARTS | A_ENDS)) {
+                    continue; /* an anchor between two characters (the parser lets none through) */
+                }
                 if (Glushkov::holds(e.second, g.isWord(p), g.isWord(e.first))) {
                     nfa->succ[st[p]] |= 1ull << st[e.first];
                 }
@@ -798,32 +949,35 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
         /* --- entries --- */
         std::vector<std::pair<u32, u32>> entries;
         {
-            std::vector<u8> seen(np * 4, 0);
+            std::vector<u8> seen(np * (A_ALL + 1), 0);
             g.reachThroughAssertions(s.first, 0, &entries, &seen);
-        }
-        const bool mlStart = isCat && arm->mlStart, anchored = isCat && arm->anchored;
-        if (mlStart && !nfa->mlStartState) {
-            /* "^" under (?m): entered at offset 0 (anchored start) or right after any newline --
-             * one state shared by all such alternatives, on after every '\n' */
-            nfa->mlStartState = newState();
-            nfa->reach[(u8)'\n'] |= 1ull << nfa->mlStartState;
-            nfa->succ[0] |= 1ull << nfa->mlStartState;
         }
         for (const auto &e : entries) {
             const u64 bit = 1ull << st[e.first];
             const bool qw = asserts && g.isWord(e.first);
-            if (mlStart || anchored) {
+            if (e.second & A_ENDS) {
+                continue; /* a character after the end of the data */
+            }
+            if (e.second & A_STARTS) {
                 /* what precedes is the start of the data or a newline: not a word character */
-                if (Glushkov::holds(e.second, false, qw)) {
-                    nfa->succ[1] |= bit;
-                    if (mlStart) {
-                        nfa->succ[nfa->mlStartState] |= bit;
+                if (!Glushkov::holds(e.second, false, qw)) {
+                    continue;
+                }
+                nfa->succ[1] |= bit;
+                if (!(e.second & A_BEGIN)) {
+                    /* "^" under (?m): entered at offset 0 (anchored start) or right after any newline --
+                     * one state shared by all such entries, on after every '\n' */
+                    if (!nfa->mlStartState) {
+                        nfa->mlStartState = newState();
+                        nfa->reach[(u8)'\n'] |= 1ull << nfa->mlStartState;
+                        nfa->succ[0] |= 1ull << nfa->mlStartState;
                     }
+                    nfa->succ[nfa->mlStartState] |= bit;
                 }
             } else if (e.second == 0) {
                 nfa->succ[0] |= bit;
             } else {
-                /* a leading assertion in a floating alternative: the byte before the match decides.  Two
+                /* a leading \b / \B of a floating entry: the byte before the match decides.  Two
                  * shared context states hang off the floating start: "previous byte is a word character"
                  * and "previous byte is none, or not a word character" (the latter also on at offset 0) */
                 if (!nfa->ctxWord) {
@@ -845,55 +999,65 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
         }
 
         /* --- accepts --- */
-        u32 nl = 0;
-        if (end == Node::END_DOLLAR || end == Node::END_ML_DOLLAR) {
-            /* the expression's end may sit before a newline: a state for that newline, whose report is
-             * delivered one byte back (offset_adjust -1, as the reference compiles "$") */
+        auto adjusted = [&]() -> u32 {
             if (!reportBeforeNewline) {
                 throw RegexError{"internal: no adjusted report program"};
             }
-            nl = newState();
-            nfa->reach[(u8)'\n'] |= 1ull << nl;
-            if (end == Node::END_DOLLAR) {
-                nfa->reportsEod[nl].push_back(reportBeforeNewline); /* ... only if that newline ends the data */
-            } else {
-                nfa->reports[nl].push_back(reportBeforeNewline);
+            return reportBeforeNewline;
+        };
+        auto addOnce = [](std::vector<u32> &v, u32 r) {
+            if (std::find(v.begin(), v.end(), r) == v.end()) {
+                v.push_back(r);
             }
-        }
-        u32 aheadWord = 0, aheadNonWord = 0; /* trailing assertion: one byte of look-ahead, reported one byte back */
+        };
+        /* one byte of look-ahead, reported one byte back (offset_adjust -1, as the reference compiles "$"):
+         * a word character, a non-word character (trailing \b / \B), any newline ("$" under (?m)), a newline
+         * that ends the data ("$", \Z) */
+        u32 aheadWord = 0, aheadNonWord = 0, aheadNewline = 0, aheadLastNewline = 0;
         for (u32 p = 0; p < np; p++) {
             if (g.assertion[p]) {
                 continue;
             }
             if ((s.last >> p) & 1) {
-                if (end == Node::END_NONE) {
-                    nfa->reports[st[p]].push_back(report);
-                } else {
-                    nfa->reportsEod[st[p]].push_back(report);
-                    if (nl) {
-                        nfa->succ[st[p]] |= 1ull << nl;
-                    }
-                }
-            }
-            if (!asserts) {
-                continue;
+                addOnce(nfa->reports[st[p]], report);
             }
             std::vector<u32> needs;
-            std::vector<u8> seen(np * 4, 0);
+            std::vector<u8> seen(np * (A_ALL + 1), 0);
             g.exitsThroughAssertions(g.follow[p], 0, s.last, &needs, &seen);
+            const bool pw = asserts && g.isWord(p);
             for (u32 need : needs) {
-                const bool pw = g.isWord(p);
-                if (Glushkov::holds(need, pw, false)) { /* the end of the data counts as a non-word character */
-                    nfa->reportsEod[st[p]].push_back(report);
+                if (need & A_STARTS) {
+                    continue; /* a start anchor after a character (the parser lets none through) */
                 }
-                if (!reportBeforeNewline) {
-                    throw RegexError{"internal: no adjusted report program"};
+                if (Glushkov::holds(need, pw, false)) { /* the end of the data counts as a non-word character */
+                    addOnce(nfa->reportsEod[st[p]], report);
+                }
+                if (need & A_ENDS) {
+                    if ((need & A_END) || !Glushkov::holds(need, pw, false)) {
+                        continue; /* \z: nothing but the end of the data will do; a newline is not a word character */
+                    }
+                    if (need & A_END_LF) {
+                        if (!aheadLastNewline) {
+                            aheadLastNewline = newState();
+                            nfa->reach[(u8)'\n'] |= 1ull << aheadLastNewline;
+                            nfa->reportsEod[aheadLastNewline].push_back(adjusted());
+                        }
+                        nfa->succ[st[p]] |= 1ull << aheadLastNewline;
+                    } else {
+                        if (!aheadNewline) {
+                            aheadNewline = newState();
+                            nfa->reach[(u8)'\n'] |= 1ull << aheadNewline;
+                            nfa->reports[aheadNewline].push_back(adjusted());
+                        }
+                        nfa->succ[st[p]] |= 1ull << aheadNewline;
+                    }
+                    continue;
                 }
                 if (Glushkov::holds(need, pw, true)) {
                     if (!aheadWord) {
                         aheadWord = newState();
                         reachClass(aheadWord, W);
-                        nfa->reports[aheadWord].push_back(reportBeforeNewline);
+                        nfa->reports[aheadWord].push_back(adjusted());
                     }
                     nfa->succ[st[p]] |= 1ull << aheadWord;
                 }
@@ -901,7 +1065,7 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                     if (!aheadNonWord) {
                         aheadNonWord = newState();
                         reachClass(aheadNonWord, ~W);
-                        nfa->reports[aheadNonWord].push_back(reportBeforeNewline);
+                        nfa->reports[aheadNonWord].push_back(adjusted());
                     }
                     nfa->succ[st[p]] |= 1ull << aheadNonWord;
                 }

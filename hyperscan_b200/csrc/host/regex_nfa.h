@@ -5,19 +5,20 @@
  * expression sets whose positions fit the 64-state model together with the start states.
  *
  * Syntax (PCRE as the reference's parser accepts it, src/parser/Parser.rl): literal
- * characters and escapes (\n \t \r \f \a \e \xHH, escaped punctuation), the class escapes
- * \d \D \w \W \s \S, "." (any byte but \n; any byte under HS_FLAG_DOTALL), character
- * classes with ranges, negation and class escapes, groups "(...)" / "(?:...)" (Hyperscan
- * does not capture), alternation, the quantifiers ? * + {n} {n,} {n,m} (a lazy "?" suffix
- * changes nothing when every match end is reported), "^" at the start of the expression
- * or of a top-level alternative (\A likewise; under HS_FLAG_MULTILINE "^" also matches after any
- * newline), "$" / \Z (end of data or before a final newline), \z (end of data), "$" under
- * HS_FLAG_MULTILINE (before any newline or at the end) at the end of the expression or of a
- * top-level alternative, \b and \B, POSIX classes inside classes, a leading "(?ism)".
- * HS_FLAG_CASELESS folds letters.  Everything else -- look-around, back-references, possessive
- * quantifiers, anchors inside groups, UTF-8 / UCP, SOM, expressions that match the empty
- * string -- is refused with a compile error: those need parts of the reference's compiler and
- * runtime this build does not have.
+ * characters and escapes (\n \t \r \f \a \e \xHH \x{hh} \0oo \cX, escaped punctuation, \Q...\E),
+ * the class escapes \d \D \w \W \s \S \h \H \v \V \N, "." (any byte but \n; any byte under
+ * HS_FLAG_DOTALL), character classes with ranges, negation, class escapes and POSIX classes,
+ * groups "(...)" / "(?:...)" (Hyperscan does not capture), option groups "(?ims-ims)" and
+ * "(?ims-ims:...)" scoped to the enclosing group, alternation, the quantifiers ? * + {n} {n,}
+ * {n,m} (a lazy "?" suffix changes nothing when every match end is reported), \b and \B, and the
+ * anchors "^" \A (offset 0; "^" under HS_FLAG_MULTILINE also after any newline), "$" \Z (end of
+ * data or before a final newline; "$" under HS_FLAG_MULTILINE before any newline or at the end),
+ * \z (end of data) -- anywhere the reference takes them: where nothing can have been consumed
+ * before a start anchor / can be consumed after an end anchor (ComponentBoundary.cpp:162-185),
+ * groups and alternations included.  HS_FLAG_CASELESS folds letters.  Everything else --
+ * look-around, back-references, possessive quantifiers, UTF-8 / UCP, SOM, expressions that match
+ * the empty string -- is refused with a compile error: those need parts of the reference's
+ * compiler and runtime this build does not have.
  */
 #ifndef HSB200_REGEX_NFA_H
 #define HSB200_REGEX_NFA_H

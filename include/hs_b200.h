@@ -121,11 +121,12 @@ typedef int (*match_event_handler)(unsigned int id, unsigned long long from,
  * groups, alternation, character classes without negation, the bounded
  * repeats ?, {n}, {n,m} (at most 4096 strings per expression) -- each string
  * becoming one literal under the expression's id.  An expression set that is
- * not such a set (unbounded repeats, ".", negated / POSIX classes, \d \w \s,
- * "^" \A "$" \z \Z at the ends of top-level alternatives) is compiled, in block
+ * not such a set (unbounded repeats, ".", negated / POSIX classes, \d \w \s \h \v,
+ * \b \B, "^" \A "$" \z \Z where the reference takes them, option groups (?ims-ims),
+ * \Q..\E, ...) is compiled, in block
  * mode, to ONE LimEx NFA of the 32- or 64-state model inside a single-outfix database
  * (ROSE_RUNTIME_SINGLE_OUTFIX) when its positions fit -- DESIGN.md section 10b.
- * Anything else (\b, look-around, back-references, larger sets, ...) yields
+ * Anything else (look-around, back-references, UTF-8 / UCP, larger sets, ...) yields
  * HS_COMPILER_ERROR with an explanatory hs_compile_error_t, exactly as the
  * reference reports unsupported constructs. */
 hs_error_t hs_compile(const char *expression, unsigned int flags,

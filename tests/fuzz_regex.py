@@ -24,8 +24,15 @@ import oracle.ref as ref  # noqa: E402
 ALPHA = b"abc1 \n_X"
 
 
+ANCHORS = False   # main(): anchors as atoms anywhere (most placements are refused, as the reference refuses them)
+
+
 def gen_atom(rng, depth):
     r = rng.random()
+    if ANCHORS and rng.random() < 0.12:
+        a = [b"^", b"$", rb"\A", rb"\z", rb"\Z"][int(rng.integers(0, 5))]
+        return b"(" + a + b"|" + gen_atom(rng, depth + 1) + b")" if rng.random() < 0.4 else \
+            b"(" + a + b")?" if rng.random() < 0.3 else a
     if r < 0.45:
         return re.escape(bytes([ALPHA[rng.integers(0, len(ALPHA))]]))
     if r < 0.55:
@@ -42,7 +49,8 @@ def gen_atom(rng, depth):
     if depth >= 2:
         return b"a"
     arms = [gen_seq(rng, depth + 1) for _ in range(int(rng.integers(1, 3)))]
-    return (b"(?:" if rng.random() < 0.5 else b"(") + b"|".join(arms) + b")"
+    opener = [b"(?:", b"(", b"(?:", b"(", b"(?i:", b"(?s:", b"(?-i:", b"(?i-s:"][int(rng.integers(0, 8))]
+    return opener + b"|".join(arms) + b")"
 
 
 def gen_seq(rng, depth):
@@ -94,6 +102,19 @@ def definition(body, flags, start, end, data):
     return sorted(out)
 
 
+def definition_whole(expr, flags, data):
+    """the same for an expression with anchors anywhere: Python's own reading of ^ $ \\A, with PCRE's \\z and \\Z
+    spelled its way"""
+    fl = (re.I if flags & 1 else 0) | (re.S if flags & 2 else 0) | (re.M if flags & 4 else 0)
+    expr = expr.replace(b"\\Z", b"(?=\n?\0)").replace(b"\\z", b"\\Z").replace(b"\0", b"\\Z")
+    out = []
+    for e in range(1, len(data) + 1):
+        rx = re.compile(b"(?:" + expr + b")(?<=(?s:\\A.{%d}))" % e, fl)
+        if any(rx.match(data, s) for s in range(e)):
+            out.append(e)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=60)
@@ -107,7 +128,10 @@ def main():
     def on_alarm(signum, frame):
         raise TimeoutError()
     signal.signal(signal.SIGALRM, on_alarm)
+    global ANCHORS
+    anchored_cases = 0
     while time.time() - t0 < args.seconds:
+        ANCHORS = rng.random() < 0.35
         body = b"|".join(gen_seq(rng, 0) for _ in range(int(rng.integers(1, 3))))
         single_arm = b"|" not in body or body.count(b"(") > 0 and False
         start = rng.random() < 0.2
@@ -115,8 +139,11 @@ def main():
         flags = int(rng.choice([0, 0, 1, 2, 3, 4, 6]))
         # anchors bind to ONE top-level alternative in the expression: wrap the body to keep the definition simple
         expr = (b"^" if start else b"") + b"(?:" + body + b")" + end
+        whole = ANCHORS and any(a in body for a in (b"^", b"$", rb"\A", rb"\z", rb"\Z"))
+        if whole:
+            expr = body
         try:
-            if re.compile(body).fullmatch(b"") is not None:
+            if not whole and re.compile(body).fullmatch(b"") is not None:
                 continue                                   # matches the empty string: refused by design
         except re.error:
             continue
@@ -133,6 +160,7 @@ def main():
             literal += 1
         n += 1
         asserted += (rb"\b" in body) or (rb"\B" in body)
+        anchored_cases += whole
         for trial in range(3):
             size = int(rng.integers(1, 28))
             a = np.frombuffer(ALPHA, dtype=np.uint8)
@@ -141,7 +169,7 @@ def main():
             got = [int(r["to"]) for r in ref.scan_sorted(db.ptr, arr, np.array([0], np.uint64), np.array([size], np.uint32))]
             try:                                            # Python's backtracking matcher can blow up on nested
                 signal.setitimer(signal.ITIMER_REAL, 2.0)   # nullable repeats: such a case is skipped, not judged
-                want = definition(body, flags, start, end, data)
+                want = definition_whole(expr, flags, data) if whole else definition(body, flags, start, end, data)
             except TimeoutError:
                 skipped += 1
                 continue
@@ -150,9 +178,9 @@ def main():
             if got != want:
                 print("MISMATCH expr", expr, "flags", flags, "data", data, "got", got, "want", want)
                 sys.exit(1)
-    print("fuzz regex: %d expressions (%d with \\b / \\B, %d through the literal route; %d refused, %d inputs skipped: "
+    print("fuzz regex: %d expressions (%d with \\b / \\B, %d with anchors inside groups, %d through the literal route; %d refused, %d inputs skipped: "
           "definition too slow), all equal to the definition (%.0f s)"
-          % (n, asserted, literal, refused, skipped, time.time() - t0))
+          % (n, asserted, anchored_cases, literal, refused, skipped, time.time() - t0))
 
 
 if __name__ == "__main__":

@@ -229,7 +229,7 @@ def test_finite_language_expressions(hs, ref, pat, caseless):
 def test_finite_language_limits_and_errors(hs):
     # (expressions with unbounded repeats, ".", "^", negated classes or class escapes are no longer errors:
     # they compile through the NFA route, tests/test_regex.py)
-    for bad, why in [(rb"a*", "empty buffer"), (rb"a$b", "'$'"), (rb"(?<=a)b", "Group options"), (rb"a|", "empty buffer"),
+    for bad, why in [(rb"a*", "empty buffer"), (rb"a$b", "Embedded end anchors"), (rb"(?<=a)b", "Look-around"), (rb"a|", "empty buffer"),
                      (rb"(ab", "parenthesis"), (rb"ab)", "parentheses"), (rb"(a)\1", "Escape sequence"),
                      (rb"a??", "empty buffer"), (rb"[[:nope:]]", "POSIX"), (rb"a{3,2}", "min > max"),
                      (rb"*a", "nothing to repeat"), (rb"[ab", "Unterminated"), (rb"[a-z]{65}x+", "too large")]:

@@ -15,23 +15,28 @@ import pytest
 
 from hyperscan_b200 import synth
 
-CASELESS, DOTALL, SINGLE = 1, 2, 8
+CASELESS, DOTALL, MULTILINE, SINGLE = 1, 2, 4, 8
 PATTERNS = [
     (rb"ab+c", 0), (rb"a[bc]*d", 0), (rb"x.y", 0), (rb"x.y", DOTALL), (rb"\d+\.\d\d", 0), (rb"^abc", 0),
     (rb"(ab|cd)+e", 0), (rb"[^a-z]{2,3}q", 0), (rb"fo{1,}d?", CASELESS), (rb"a(bc)?d|x+y", 0),
     (rb"^a.*b", DOTALL), (rb"\w+@\w+", 0), (rb"[a-c]{3}", 0), (rb"q\s*=\s*\d", 0), (rb"(?:ab){2,}c", 0),
     (rb"a+?b", 0), (rb"^x|y\x41z", 0), (rb"[\d\-x]+y", 0), (rb"a.{2,4}b", 0), (rb"\Sq\S", CASELESS),
     (rb"\bab", 0), (rb"\w+\b", 0), (rb"\Bq\B", 0), (rb"a\b.\bb", 0), (rb"^\b\d", 0), (rb"x\B|\by", 0),
+    # anchors inside groups, where the reference takes them (nothing consumed before / after on any way there)
+    (rb"(^a|b)c", 0), (rb"(a|^)b+c", 0), (rb"(^|x)ab+", 0), (rb"(^)?ab+", 0), (rb"fo+($)?", CASELESS), (rb"ab+(\z|c)", 0),
+    (rb"\bab+$", 0), (rb"(^a|b)c", MULTILINE), (rb"b+($|x)", MULTILINE), (rb"[a-c]+(\Z|\d)", 0), (rb"(\Aa|^b|c)d+", MULTILINE),
 ]
 ALPHA = b"abcdxyqAB.12e\nfoFOD =@-_z"
+TAILS = [b"", b" abb", b"1abb\n", b"bcd\n", b"\nfoo", b"xbb\n\n"]   # for the end anchors
 SEED_TEXT = b"abc abbcd acbd x\ny 3.14 ababe 12q fOOd ad xxy a\nb u_1@v2 cab q = 7 ababababc aab yAz 1-x2y a123b .q, "
 
 
 def _ends(pat, flags, data):
     """every end offset e such that the expression matches some data[s:e] in context (\\b / \\B see the bytes
     around the match): a fixed-width look-behind pins the match end to e"""
-    fl = (re.I if flags & CASELESS else 0) | (re.S if flags & DOTALL else 0)
+    fl = (re.I if flags & CASELESS else 0) | (re.S if flags & DOTALL else 0) | (re.M if flags & MULTILINE else 0)
     out = []
+    pat = pat.replace(b"\\Z", b"(?=\n?\0)").replace(b"\\z", b"\\Z").replace(b"\0", b"\\Z")   # PCRE \Z, \z in Python's spelling
     for e in range(1, len(data) + 1):
         rx = re.compile(b"(?:" + pat + b")(?<=(?s:\\A.{%d}))" % e, fl)
         if any(rx.match(data, s) for s in range(e)):
@@ -58,7 +63,7 @@ def test_reference_hs_scan_on_compiled_expressions_equals_definition(hs, ref, pi
     assert db.info().runtime_impl == (1 if pat == rb"[a-c]{3}" else 2)   # single outfix, unless the language is finite
     hits = 0
     for seed in range(10):
-        data = (SEED_TEXT if seed == 0 else b"") + _data(100 * pi + seed)
+        data = (SEED_TEXT if seed == 0 else b"") + _data(100 * pi + seed) + TAILS[seed % len(TAILS)]
         want = [(7, e) for e in _ends(pat, fl, data)]
         assert _ref_ends(ref, db, data) == want, (pat, data)
         hits += len(want)
@@ -79,8 +84,29 @@ def test_several_expressions_share_one_nfa_and_report_rules_hold(hs, ref):
         assert sorted(_ref_ends(ref, db, data), key=lambda t: (t[1], t[0])) == sorted(want, key=lambda t: (t[1], t[0]))
 
 
+@pytest.mark.parametrize("a,b,fl", [
+    (rb"foo(?i)bar+", rb"foo(?i:bar+)", 0), (rb"(?i)fo+(?-i)d", rb"[fF][oO]+d", 0), (rb"\Qa.b\E+c", rb"a\.b+c", 0),
+    (rb"\x{41}+b", rb"A+b", 0), (rb"[\060-\071]+x", rb"[0-9]+x", 0), (rb"\cAb+", rb"\x01b+", 0), (rb"\h+a", rb"[\t \xa0]+a", 0),
+    (rb"[\Qa]\E]+y", rb"[a\]]+y", 0), (rb"a(?s).b+", rb"a(?s:.)b+", 0), (rb"\V+\v", rb"[^\n\x0b\f\r\x85]+[\n\x0b\f\r\x85]", 0),
+    (rb"(?m)^ab+", rb"^ab+", MULTILINE), (rb"x\N+y", rb"x[^\n]+y", DOTALL), (rb"\0+a", rb"\x00+a", 0)])
+def test_other_spellings_of_the_same_expression(hs, ref, a, b, fl):
+    """option groups, \\Q..\\E, \\x{..}, octal, \\c, \\h \\v \\N against the plain spelling of the same language (the reference's
+    own vectors for these, tools/hscollider test cases 11xxx / 19xxx / 24xxx, are in tests/golden/hscollider_regex.json)"""
+    da, dbb = hs.compile_multi([a], [fl], [7]), hs.compile_multi([b], [fl], [7])
+    alpha = b"abfoFOBARbar.dD\n\t \xa0\x00\x01A019]xy\x0b\x85"
+    hits = 0
+    for seed in range(12):
+        rng = np.random.default_rng(seed)
+        data = np.frombuffer(alpha, dtype=np.uint8)[rng.integers(0, len(alpha), size=200)].tobytes()
+        data += b" fooBARr foobaR FoOd food a.bbc a.b.bc AAb 0129x \x01bb \t \xa0a a]ay a\nbb a\nb q\n\x0b\n abb\nabb x12y xy \x00\x00a "
+        got = _ref_ends(ref, da, data)
+        assert got == _ref_ends(ref, dbb, data), (a, b, data)
+        hits += len(got)
+    assert hits > 0
+
+
 @pytest.mark.parametrize("pat,msg", [
-    (rb"a*", "empty"), (rb"a$b", "'$'"), (rb"(a$|b)c", "'$'"), (rb"\b+ab", "quantifier"), (rb"\bab$", "together"), (rb"(?=a)b", "look-around"), (rb"a++b", "Possessive"),
+    (rb"a*", "empty"), (rb"a$b", "Embedded end"), (rb"(a$|b)c", "Embedded end"), (rb"a^b", "Embedded start"), (rb"(^a)+b", "Embedded start"), (rb"\b+ab", "quantifier"), (rb"(?=a)b", "Look-around"), (rb"a++b", "Possessive"),
     (rb"(a|b)\1", "Escape"), (rb"[a-z]{70}x+", "too large"), (rb"(abcdefghijklmnopqrstuvwxyz0123456){2}+", "Possessive"), (rb"abcdefghijklmnopqrstuvwxyz0123456789ABCDEFGHIJKLMNOPQRSTUVWXYZ_+", "too large")])
 def test_what_the_nfa_route_refuses(hs, pat, msg):
     with pytest.raises(hs.HsError) as e:
