@@ -704,6 +704,41 @@ def limex_from_spec64(reach, init, init_ds, succ, reports, reports_eod, squash_m
     return out.raw[:sz]
 
 
+def limex_from_spec_wide(reach, init, init_ds, succ, reports, reports_eod, squash_mask=None, squash_kind=None):
+    """hs_b200_limex_from_spec_wide: state sets are Python ints (bit i = state i), up to 512 states; the model
+    emitted is the smallest of 32 / 64 / 128 / 256 / 512 that holds len(succ) states."""
+    n = len(succ)
+    words = max(1, (n + 63) // 64)
+    m64 = (1 << 64) - 1
+
+    def sets(vals):
+        return np.array([(int(v) >> (64 * j)) & m64 for v in vals for j in range(words)], dtype=np.uint64)
+
+    def flat(lists):
+        off = np.zeros(n + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(x) for x in lists])
+        vals = np.array([v for x in lists for v in x] + [0], dtype=np.uint32)
+        return off, vals
+
+    ro, rv = flat(reports)
+    eo, ev = flat(reports_eod)
+    rc, sc = sets(reach), sets(succ)
+    i0, i1 = sets([init]), sets([init_ds])
+    sm = sets(squash_mask if squash_mask is not None else [(1 << (64 * words)) - 1] * n)
+    sk = np.ascontiguousarray(squash_kind if squash_kind is not None else np.zeros(n), dtype=np.uint8)
+    L = lib()
+    L.hs_b200_limex_from_spec_wide.restype = C.c_long
+    L.hs_b200_limex_from_spec_wide.argtypes = [C.c_uint, C.c_uint] + [C.c_void_p] * 11 + [C.c_size_t]
+    cap = 4 << 20
+    out = C.create_string_buffer(cap)
+    sz = L.hs_b200_limex_from_spec_wide(n, words, rc.ctypes.data, i0.ctypes.data, i1.ctypes.data, sc.ctypes.data,
+                                        sm.ctypes.data, sk.ctypes.data, ro.ctypes.data, rv.ctypes.data, eo.ctypes.data,
+                                        ev.ctypes.data, out, cap)
+    if sz < 0:
+        raise HsError(HS_COMPILER_ERROR, "limex_from_spec_wide")
+    return out.raw[:sz]
+
+
 def nfa_scan_corpus(nfa_bytes, corpus, cap=1 << 20):
     """hs_b200_nfa_scan_corpus: the engine over every block of a resident corpus.
     Returns (records MATCH_DTYPE ordered by (block, to, id), kernel ms)."""

@@ -513,7 +513,7 @@ std::vector<u8> buildByteTable(const std::vector<LitTail> &tails, double *rate) 
 }
 
 /* What launchDfa needs to know about a serialized engine (struct NFA + McClellan 8 / 16,
- * Sheng or LimEx-32), checked against its length.  HS_ARCH_ERROR: an engine or a feature
+ * Sheng or LimEx-32 ... -512), checked against its length.  HS_ARCH_ERROR: an engine or a feature
  * (wide states, bounded repeats) the DFA / NFA kernels do not implement. */
 hs_error_t engineParams(const void *nfa, size_t nfa_len, DfaParams *out) {
     if (!nfa || nfa_len < sizeof(NFA) + 64) {
@@ -550,31 +550,48 @@ hs_error_t engineParams(const void *nfa, size_t nfa_len, DfaParams *out) {
         if (nfa_len < sizeof(NFA) + sizeof(Sheng)) {
             return HS_INVALID;
         }
-    } else if (hdr.type == NFA_LIMEX_32 || hdr.type == NFA_LIMEX_64) {
-        const bool wide = hdr.type == NFA_LIMEX_64;
-        const size_t structSize = wide ? sizeof(LimExNFA64) : sizeof(LimExNFA32);
+    } else if (hdr.type == NFA_LIMEX_32 || hdr.type == NFA_LIMEX_64 || hdr.type == NFA_LIMEX_128 ||
+               hdr.type == NFA_LIMEX_256 || hdr.type == NFA_LIMEX_512) {
+        /* (the 384-state model is not built: the emitter here never produces it) */
+        size_t structSize, excSize, stateBytes, shiftCountAt;
+        switch (hdr.type) {
+#define HSB_LIMEX_MODEL(T, L, E, B)                                                     \
+        case T:                                                                         \
+            structSize = sizeof(L), excSize = sizeof(E), stateBytes = B, shiftCountAt = offsetof(L, shiftCount); \
+            break;
+            HSB_LIMEX_MODEL(NFA_LIMEX_32, LimExNFA32, NFAException32, 4)
+            HSB_LIMEX_MODEL(NFA_LIMEX_64, LimExNFA64, NFAException64, 8)
+            HSB_LIMEX_MODEL(NFA_LIMEX_128, LimExNFA128, NFAException128, 16)
+            HSB_LIMEX_MODEL(NFA_LIMEX_256, LimExNFA256, NFAException256, 32)
+        default:
+            HSB_LIMEX_MODEL(NFA_LIMEX_512, LimExNFA512, NFAException512, 64)
+#undef HSB_LIMEX_MODEL
+        }
         if (nfa_len < sizeof(NFA) + structSize) {
             return HS_INVALID;
         }
-        /* the count / offset fields precede the state-sized ones and sit at the same offsets in both models */
+        /* the count / offset fields precede the state-sized ones and sit at the same offsets in every model */
         LimExNFA32 lx;
         memcpy(&lx, (const u8 *)nfa + sizeof(NFA), offsetof(LimExNFA32, init));
         u32 shiftCount;
-        memcpy(&shiftCount, (const u8 *)nfa + sizeof(NFA) + (wide ? offsetof(LimExNFA64, shiftCount) : offsetof(LimExNFA32, shiftCount)), 4);
+        memcpy(&shiftCount, (const u8 *)nfa + sizeof(NFA) + shiftCountAt, 4);
         if (lx.repeatCount) {
             return HS_ARCH_ERROR; /* bounded repeats (repeat control blocks, tug / pos triggers) are not built */
         }
+        if (stateBytes > 8 && ((uintptr_t)nfa & 7)) {
+            return HS_INVALID; /* the wide state sets are read as 64-bit words */
+        }
         const size_t body = nfa_len - sizeof(NFA);
-        const size_t excSize = wide ? sizeof(NFAException64) : sizeof(NFAException32);
-        if (shiftCount > 8 || lx.exceptionCount > (wide ? 64u : 32u) ||
-            structSize + (wide ? 8ull : 4ull) * lx.reachSize > body ||
+        if (shiftCount > 8 || lx.exceptionCount > 8 * stateBytes ||
+            structSize + stateBytes * lx.reachSize > body ||
             (size_t)lx.exceptionOffset + (size_t)lx.exceptionCount * excSize > body ||
             (size_t)lx.acceptOffset + (size_t)lx.acceptCount * sizeof(NFAAccept) > body ||
             (size_t)lx.acceptEodOffset + (size_t)lx.acceptEodCount * sizeof(NFAAccept) > body) {
             return HS_INVALID;
         }
+        p.states = hdr.nPositions;
     } else {
-        return HS_ARCH_ERROR; /* LimEx, McSheng, Gough, Castle, ...: not built */
+        return HS_ARCH_ERROR; /* LimEx-384, McSheng, Gough, Castle, ...: not built */
     }
     return HS_SUCCESS;
 }

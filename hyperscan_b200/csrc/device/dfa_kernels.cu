@@ -71,6 +71,119 @@ __device__ __forceinline__ u32 lowestBit(u64 v) { return (u32)__ffsll((long long
 __device__ __forceinline__ u32 rankBelow(u32 mask, u32 bit) { return (u32)__popc(mask & ((1u << bit) - 1)); }
 __device__ __forceinline__ u32 rankBelow(u64 mask, u32 bit) { return (u32)__popcll(mask & ((1ull << bit) - 1)); }
 
+/* the LimEx state set: u32 / u64 for the 32- and 64-state models, W 64-bit words for the wider ones (the reference's
+ * m128 / m256 / m512); StOps gives both kinds the same few operations */
+template <int W> struct alignas(16) WideSt {
+    u64 w[W];
+};
+template <class ST> struct StOps {
+    static __device__ __forceinline__ ST zero() { return 0; }
+    static __device__ __forceinline__ ST ones() { return ~(ST)0; }
+    static __device__ __forceinline__ bool any(ST a) { return a != 0; }
+    static __device__ __forceinline__ ST band(ST a, ST b) { return a & b; }
+    static __device__ __forceinline__ ST bor(ST a, ST b) { return a | b; }
+    static __device__ __forceinline__ bool test(ST a, u32 i) { return (a >> i) & 1; }
+    static __device__ __forceinline__ ST clear0(ST a) { return a & ~(ST)1; }
+    /* LSHIFT_STATE of the one bit i: the high bits fall off */
+    static __device__ __forceinline__ ST shiftedBit(u32 i, u32 amount) { return ((ST)1 << i) << amount; }
+    static __device__ __forceinline__ u32 low32(ST a) { return (u32)a; }
+    static __device__ __forceinline__ ST fromU32(u32 x) { return x; }
+    static __device__ __forceinline__ u32 rank(ST mask, u32 bit) { return rankBelow(mask, bit); }
+    static __device__ __forceinline__ ST load(const u8 *p) { return ldgState(p, ST()); }
+    template <class F> static __device__ __forceinline__ void forEach(ST on, F f) { /* ascending */
+        while (on) {
+            f(lowestBit(on));
+            on &= on - 1;
+        }
+    }
+};
+template <int W> struct StOps<WideSt<W>> {
+    typedef WideSt<W> ST;
+    static __device__ __forceinline__ ST zero() {
+        ST r;
+#pragma unroll
+        for (int j = 0; j < W; j++) r.w[j] = 0;
+        return r;
+    }
+    static __device__ __forceinline__ ST ones() {
+        ST r;
+#pragma unroll
+        for (int j = 0; j < W; j++) r.w[j] = ~0ull;
+        return r;
+    }
+    static __device__ __forceinline__ bool any(const ST &a) {
+        u64 x = 0;
+#pragma unroll
+        for (int j = 0; j < W; j++) x |= a.w[j];
+        return x != 0;
+    }
+    static __device__ __forceinline__ ST band(const ST &a, const ST &b) {
+        ST r;
+#pragma unroll
+        for (int j = 0; j < W; j++) r.w[j] = a.w[j] & b.w[j];
+        return r;
+    }
+    static __device__ __forceinline__ ST bor(const ST &a, const ST &b) {
+        ST r;
+#pragma unroll
+        for (int j = 0; j < W; j++) r.w[j] = a.w[j] | b.w[j];
+        return r;
+    }
+    static __device__ __forceinline__ bool test(const ST &a, u32 i) {
+        u64 x = 0;
+#pragma unroll
+        for (int j = 0; j < W; j++) x = (i >> 6) == (u32)j ? a.w[j] : x;
+        return (x >> (i & 63)) & 1;
+    }
+    static __device__ __forceinline__ ST clear0(ST a) {
+        a.w[0] &= ~1ull;
+        return a;
+    }
+    /* the wide models shift every 64-bit lane on its own (lshift64_m128 ...): a bit never crosses into the next lane */
+    static __device__ __forceinline__ ST shiftedBit(u32 i, u32 amount) {
+        ST r = zero();
+        const u64 v = (1ull << (i & 63)) << amount;
+#pragma unroll
+        for (int j = 0; j < W; j++) r.w[j] = (i >> 6) == (u32)j ? v : 0;
+        return r;
+    }
+    static __device__ __forceinline__ u32 low32(const ST &a) { return (u32)a.w[0]; }
+    static __device__ __forceinline__ ST fromU32(u32 x) {
+        ST r = zero();
+        r.w[0] = x;
+        return r;
+    }
+    static __device__ __forceinline__ u32 rank(const ST &mask, u32 bit) {
+        u32 c = 0;
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+            const u32 lo = 64u * j;
+            if (bit >= lo + 64) {
+                c += (u32)__popcll(mask.w[j]);
+            } else if (bit > lo) {
+                c += (u32)__popcll(mask.w[j] & ((1ull << (bit - lo)) - 1));
+            }
+        }
+        return c;
+    }
+    static __device__ __forceinline__ ST load(const u8 *p) {
+        ST r;
+#pragma unroll
+        for (int j = 0; j < W; j++) r.w[j] = __ldg(reinterpret_cast<const u64 *>(p) + j);
+        return r;
+    }
+    template <class F> static __device__ __forceinline__ void forEach(const ST &on, F f) {
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+            u64 x = on.w[j];
+            while (x) {
+                f(64u * j + lowestBit(x));
+                x &= x - 1;
+            }
+        }
+    }
+};
+
 /* LimEx report list: ReportID[] terminated by MO_INVALID_IDX (limexRunReports, limex_runtime.h:90-103) */
 __device__ HSB_NOINLINE u32 emitLimexReports(const DfaParams &p, u32 cursor, u32 listOff, u32 block, u64 to) {
     const u8 *lx = p.nfa + sizeof(NFA);
@@ -90,10 +203,8 @@ template <class ST>
 __device__ HSB_NOINLINE u32 emitLimexAccepts(const DfaParams &p, u32 cursor, ST found, ST mask, u32 tableOff,
                                              u32 block, u64 to) {
     const u8 *lx = p.nfa + sizeof(NFA);
-    while (found) {
-        const u32 bit = lowestBit(found);
-        found &= found - 1;
-        const u32 idx = rankBelow(mask, bit);
+    StOps<ST>::forEach(found, [&](const u32 bit) {
+        const u32 idx = StOps<ST>::rank(mask, bit);
         const u8 *a = lx + tableOff + idx * (u32)sizeof(NFAAccept);
         const u32 reports = g32(a + offsetof(NFAAccept, reports));
         if (__ldg(a + offsetof(NFAAccept, single_report))) {
@@ -101,7 +212,7 @@ __device__ HSB_NOINLINE u32 emitLimexAccepts(const DfaParams &p, u32 cursor, ST 
         } else {
             cursor = emitLimexReports(p, cursor, reports, block, to);
         }
-    }
+    });
     return cursor;
 }
 
@@ -202,15 +313,24 @@ template <int CH> struct DfaTile {
     static constexpr u32 ROWS_PER_LOAD = 32 / PIECES;
 };
 
-enum { ENG_MCC8 = 0, ENG_MCC16 = 1, ENG_SHENG = 2, ENG_LIMEX32 = 3, ENG_LIMEX64 = 4 };
+enum { ENG_MCC8 = 0, ENG_MCC16 = 1, ENG_SHENG = 2, ENG_LIMEX32 = 3, ENG_LIMEX64 = 4, ENG_LIMEX128 = 5, ENG_LIMEX256 = 6,
+       ENG_LIMEX512 = 7 };
 
-/* the state of a block's walk: a DFA state id, or the LimEx state set (32 or 64 states) */
+/* the state of a block's walk: a DFA state id, or the LimEx state set */
 template <int ENGINE> struct WalkState { typedef u32 type; };
 template <> struct WalkState<ENG_LIMEX64> { typedef u64 type; };
-/* the engine structures of the two LimEx models share their field names */
+template <> struct WalkState<ENG_LIMEX128> { typedef WideSt<2> type; };
+template <> struct WalkState<ENG_LIMEX256> { typedef WideSt<4> type; };
+template <> struct WalkState<ENG_LIMEX512> { typedef WideSt<8> type; };
+/* the engine structures of the LimEx models share their field names */
 template <class ST> struct LimexLayout;
 template <> struct LimexLayout<u32> { typedef LimExNFA32 Nfa; typedef NFAException32 Exc; };
 template <> struct LimexLayout<u64> { typedef LimExNFA64 Nfa; typedef NFAException64 Exc; };
+template <> struct LimexLayout<WideSt<2>> { typedef LimExNFA128 Nfa; typedef NFAException128 Exc; };
+template <> struct LimexLayout<WideSt<4>> { typedef LimExNFA256 Nfa; typedef NFAException256 Exc; };
+template <> struct LimexLayout<WideSt<8>> { typedef LimExNFA512 Nfa; typedef NFAException512 Exc; };
+/* CTA size: the wide state sets need the registers of a 512-thread CTA (and the 512-state tables the room) */
+template <int ENGINE> struct StagedThreads { static constexpr int N = ENGINE >= ENG_LIMEX256 ? 512 : 1024; };
 /* shared-memory tables of a LimEx engine: the reach mask per byte value, then per state a row of four
  * ST: limited successors, exception successors, squash mask, report list offset */
 template <class ST> struct LimexTable { static constexpr u32 BYTES = 256u * sizeof(ST) + 8u * sizeof(ST) * 4u * sizeof(ST); };
@@ -232,7 +352,7 @@ __device__ HSB_NOINLINE u32 emitAccept(const DfaParams &p, u32 cursor, u32 singl
 }
 
 template <int ENGINE, int SMEM_TABLE, int CH, int ILP>
-__global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTANT DfaParams p) {
+__global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(const HSB_GRID_CONSTANT DfaParams p) {
     HSB_DYNAMIC_SMEM(smem);
     typedef DfaTile<CH> Tile;
     const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -246,19 +366,20 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
     typedef typename WalkState<ENGINE>::type ST;
     typedef typename LimexLayout<ST>::Nfa LxNfa;
     typedef typename LimexLayout<ST>::Exc LxExc;
-    constexpr bool LIMEX = ENGINE == ENG_LIMEX32 || ENGINE == ENG_LIMEX64;
-    ST lxAccept = 0, lxAcceptEod = 0, lxStart = 0;
+    typedef StOps<ST> Ops;
+    constexpr bool LIMEX = ENGINE >= ENG_LIMEX32;
+    ST lxAccept = Ops::zero(), lxAcceptEod = Ops::zero(), lxStart = Ops::zero();
     if (LIMEX) {
-        /* eng = struct LimExNFA32 / 64; a top at offset 0 switches `init` on (moNfaTop) */
-        lxStart = ldgState(eng + offsetof(LxNfa, init), ST());
+        /* eng = struct LimExNFA32 ... 512; a top at offset 0 switches `init` on (moNfaTop) */
+        lxStart = Ops::load(eng + offsetof(LxNfa, init));
         k.start = 0;
         k.single = 0;
         k.report = 0;
         k.auxOffset = 0;
         k.auxSize = 0;
         k.stateMask = 0xffffffffu;
-        lxAccept = ldgState(eng + offsetof(LxNfa, accept), ST());
-        lxAcceptEod = ldgState(eng + offsetof(LxNfa, acceptAtEOD), ST());
+        lxAccept = Ops::load(eng + offsetof(LxNfa, accept));
+        lxAcceptEod = Ops::load(eng + offsetof(LxNfa, acceptAtEOD));
     } else if (ENGINE == ENG_SHENG) {
         k.start = __ldg(eng + offsetof(Sheng, anchored));
         k.single = __ldg(eng + offsetof(Sheng, flags)) & SHENG_FLAG_SINGLE_REPORT;
@@ -290,26 +411,26 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
         ST *d = reinterpret_cast<ST *>(smem);
         const u8 *reach = eng + sizeof(LxNfa);
         for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
-            d[i] = ldgState(reach + sizeof(ST) * __ldg(eng + offsetof(LxNfa, reachMap) + i), ST());
+            d[i] = Ops::load(reach + sizeof(ST) * __ldg(eng + offsetof(LxNfa, reachMap) + i));
         }
-        const ST excMask = ldgState(eng + offsetof(LxNfa, exceptionMask), ST());
+        const ST excMask = Ops::load(eng + offsetof(LxNfa, exceptionMask));
         const u32 nshift = g32(eng + offsetof(LxNfa, shiftCount));
         const u8 *exc = eng + g32(eng + offsetof(LxNfa, exceptionOffset));
         ST *rows = d + 256;
         for (u32 i = threadIdx.x; i < 8 * sizeof(ST); i += blockDim.x) {
-            ST lim = 0, local = 0, keep = ~(ST)0, rep = MO_INVALID_IDX;
+            ST lim = Ops::zero(), local = Ops::zero(), keep = Ops::ones(), rep = Ops::fromU32(MO_INVALID_IDX);
             for (u32 q = 0; q < nshift && q < 8; q++) {
-                if ((ldgState(eng + offsetof(LxNfa, shift) + sizeof(ST) * q, ST()) >> i) & 1) {
-                    lim |= ((ST)1 << i) << __ldg(eng + offsetof(LxNfa, shiftAmount) + q); /* LSHIFT_STATE: high bits fall off */
+                if (Ops::test(Ops::load(eng + offsetof(LxNfa, shift) + sizeof(ST) * q), i)) {
+                    lim = Ops::bor(lim, Ops::shiftedBit(i, __ldg(eng + offsetof(LxNfa, shiftAmount) + q)));
                 }
             }
-            if ((excMask >> i) & 1) {
-                const u8 *x = exc + rankBelow(excMask, i) * (u32)sizeof(LxExc);
+            if (Ops::test(excMask, i)) {
+                const u8 *x = exc + Ops::rank(excMask, i) * (u32)sizeof(LxExc);
                 const u32 kind = __ldg(x + offsetof(LxExc, hasSquash));
-                local = ldgState(x + offsetof(LxExc, successors), ST());
-                rep = g32(x + offsetof(LxExc, reports));
+                local = Ops::load(x + offsetof(LxExc, successors));
+                rep = Ops::fromU32(g32(x + offsetof(LxExc, reports)));
                 if (kind == LIMEX_SQUASH_CYCLIC || kind == LIMEX_SQUASH_REPORT) {
-                    keep = ldgState(x + offsetof(LxExc, squash), ST());
+                    keep = Ops::load(x + offsetof(LxExc, squash));
                 }
             }
             rows[4 * i + 0] = lim;
@@ -354,13 +475,13 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
 
     const ST *lxReach = reinterpret_cast<const ST *>(smem);
     const ST *lxRows = lxReach + 256;
-    ST lxLim0 = 0, lxLocal0 = 0, lxKeep0 = ~(ST)0;
+    ST lxLim0 = Ops::zero(), lxLocal0 = Ops::zero(), lxKeep0 = Ops::ones();
     bool lxRow0Plain = false; /* state 0 raises no reports: its row can be applied without the loop */
-    if (LIMEX) {
+    if (LIMEX && sizeof(ST) <= 8) { /* (the wide models read it from shared memory like every other row) */
         lxLim0 = lxRows[0];
         lxLocal0 = lxRows[1];
         lxKeep0 = lxRows[2];
-        lxRow0Plain = (u32)lxRows[3] == MO_INVALID_IDX;
+        lxRow0Plain = Ops::low32(lxRows[3]) == MO_INVALID_IDX;
     }
     u32 cursor = 0; /* this lane's next record slot (emitDfaMatch) */
     /* one input byte: byte j of data word w, at block offset pos.  DFAs: returns true when the
@@ -368,37 +489,35 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
      * that are on BEFORE the byte run their exceptions -- reports at offset pos, except at the
      * first byte of the scan (NO_OUTPUT | FIRST_BYTE) -- then succ & reach[byte]. */
     auto step = [&](const u32 w, const u32 j, ST &s, const u32 pos, const u32 blk) -> bool {
-        if (LIMEX) {
+        if constexpr (LIMEX) {
             /* NFA_EXEC_GET_LIM_SUCC + processExceptional (limex_exceptional.h:190-330, cache
              * aside) over the states that are on, in ascending order: every exception's squash
              * cuts the limited successors only, the exception successors are OR-ed in afterwards */
             /* state 0 first, from registers: in a position automaton it is the floating start,
              * on at every byte -- most bytes of most inputs have nothing else on */
-            ST lim = 0, local = 0, keep = ~(ST)0, on = s;
-            if (lxRow0Plain && (s & 1u)) {
+            ST lim = Ops::zero(), local = Ops::zero(), keep = Ops::ones(), on = s;
+            if (lxRow0Plain && Ops::test(s, 0)) {
                 lim = lxLim0;
                 local = lxLocal0;
                 keep = lxKeep0;
-                on &= ~(ST)1;
+                on = Ops::clear0(on);
             }
-            while (on) {
-                const u32 bit = lowestBit(on);
-                on &= on - 1;
+            Ops::forEach(on, [&](const u32 bit) {
                 const ST *e = lxRows + 4 * bit;
-                const u32 rep = (u32)e[3];
+                const u32 rep = Ops::low32(e[3]);
                 if (rep != MO_INVALID_IDX && pos != 0) {
                     cursor = emitLimexReports(p, cursor, rep, blk, pos);
                 }
-                lim |= e[0];
-                local |= e[1];
-                keep &= e[2];
-            }
-            s = ((lim & keep) | local) & lxReach[__byte_perm(w, 0, 0x4440 + j)];
+                lim = Ops::bor(lim, e[0]);
+                local = Ops::bor(local, e[1]);
+                keep = Ops::band(keep, e[2]);
+            });
+            s = Ops::band(Ops::bor(Ops::band(lim, keep), local), lxReach[__byte_perm(w, 0, 0x4440 + j)]);
             return false;
-        } else if (ENGINE == ENG_MCC8) {
+        } else if constexpr (ENGINE == ENG_MCC8) {
             s = smem[__byte_perm(w, s, 0x5540 + j)]; /* (s << 8) | byte */
             return s >= k.acceptLimit8;
-        } else if (ENGINE == ENG_SHENG) {
+        } else if constexpr (ENGINE == ENG_SHENG) {
             const u32 ch = __byte_perm(w, 0, 0x4440 + j);
             s = smem[ch * SHENG_ROW + (((s + 4 * ch) & SHENG_STATE_MASK) | copyOff)]; /* pshufb(masks[byte], state) */
             return (s & SHENG_STATE_ACCEPT) != 0;
@@ -415,10 +534,12 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
             return (e & MCC_ACCEPT_FLAG) != 0;
         }
     };
-    auto acceptWhat = [&](const ST s) -> u32 {
-        return k.single ? k.report : k.auxOffset + k.auxSize * ((u32)s & k.stateMask);
+    auto acceptWhat = [&](const ST &s) -> u32 {
+        return k.single ? k.report : k.auxOffset + k.auxSize * (Ops::low32(s) & k.stateMask);
     };
-    auto dead = [&](const ST s) -> bool { return ENGINE == ENG_SHENG ? (s & SHENG_STATE_DEAD) != 0 : s == 0; };
+    auto dead = [&](const ST &s) -> bool {
+        return ENGINE == ENG_SHENG ? (Ops::low32(s) & SHENG_STATE_DEAD) != 0 : !Ops::any(s);
+    };
 
     /* a warp takes 32 * ILP consecutive blocks at a time; lane t owns blocks t, t + 32, ...
      * of the group: ILP independent state chains in one instruction stream */
@@ -439,7 +560,7 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
                 off[u] = (u64)(blk.base - p.corpus);
                 len[u] = blk.len;
             }
-            s[u] = LIMEX ? lxStart : (ST)k.start;
+            s[u] = LIMEX ? lxStart : Ops::fromU32(k.start);
             live[u] = len[u] != 0;
         }
         for (u32 r = 0;; r++) {
@@ -556,19 +677,19 @@ __global__ void __launch_bounds__(1024, 1) dfaStagedKernel(const HSB_GRID_CONSTA
                 if (b[u] < p.nblocks) {
                     /* STREAM_FN's closing accept check (only if the block had bytes to stream),
                      * then nfaExecLimEx*_testEOD (limex_common_impl.h:192-218) */
-                    if (len[u] && (s[u] & lxAccept)) {
-                        cursor = emitLimexAccepts<ST>(p, cursor, s[u] & lxAccept, lxAccept,
+                    if (len[u] && Ops::any(Ops::band(s[u], lxAccept))) {
+                        cursor = emitLimexAccepts<ST>(p, cursor, Ops::band(s[u], lxAccept), lxAccept,
                                                       g32(eng + offsetof(LxNfa, acceptOffset)), b[u], len[u]);
                     }
-                    if (s[u] & lxAcceptEod) {
-                        cursor = emitLimexAccepts<ST>(p, cursor, s[u] & lxAcceptEod, lxAcceptEod,
+                    if (Ops::any(Ops::band(s[u], lxAcceptEod))) {
+                        cursor = emitLimexAccepts<ST>(p, cursor, Ops::band(s[u], lxAcceptEod), lxAcceptEod,
                                                       g32(eng + offsetof(LxNfa, acceptEodOffset)), b[u], len[u]);
                     }
                 }
             } else if (b[u] < p.nblocks) {
                 const u32 eodOff = ENGINE == ENG_SHENG ? (u32)offsetof(SstateAux, accept_eod)
                                                        : (u32)offsetof(MStateAux, accept_eod);
-                const u32 eod = g32(p.nfa + k.auxOffset + k.auxSize * ((u32)s[u] & k.stateMask) + eodOff);
+                const u32 eod = g32(p.nfa + k.auxOffset + k.auxSize * (Ops::low32(s[u]) & k.stateMask) + eodOff);
                 if (eod) {
                     cursor = emitReportList(p, cursor, eod, b[u], len[u]);
                 }
@@ -583,7 +704,7 @@ cudaError_t launchStaged(const DfaParams &p, int smCount, size_t tableBytes, cud
     /* one CTA of 32 warps per SM: table area + per warp a tile of 32 * ILP rows.
      * ilp 2: two blocks per lane, 64 bytes of each per refill (160 KiB of tiles);
      * ilp 1: one block per lane, 128 bytes per refill (144 KiB) */
-    const int threads = 1024;
+    const int threads = StagedThreads<ENGINE>::N;
     const bool two = p.ilp == 2;
     const size_t tiles = (size_t)(threads / 32) * (two ? 2 * DfaTile<64>::WARP_BYTES : DfaTile<128>::WARP_BYTES);
     const u64 groups = ((u64)p.nblocks + (two ? 63 : 31)) / (two ? 64 : 32);
@@ -614,6 +735,15 @@ cudaError_t launchDfa(const DfaParams &p, int smCount, int maxSmem, cudaStream_t
     }
     if (p.kind == NFA_LIMEX_64) {
         return launchStaged<ENG_LIMEX64, 1>(p, smCount, LimexTable<u64>::BYTES, stream);
+    }
+    if (p.kind == NFA_LIMEX_128) {
+        return launchStaged<ENG_LIMEX128, 1>(p, smCount, LimexTable<WideSt<2>>::BYTES, stream);
+    }
+    if (p.kind == NFA_LIMEX_256) {
+        return launchStaged<ENG_LIMEX256, 1>(p, smCount, LimexTable<WideSt<4>>::BYTES, stream);
+    }
+    if (p.kind == NFA_LIMEX_512) {
+        return launchStaged<ENG_LIMEX512, 1>(p, smCount, LimexTable<WideSt<8>>::BYTES, stream);
     }
     if (p.kind == NFA_MCCLELLAN_8) {
         return launchStaged<ENG_MCC8, 1>(p, smCount, (size_t)p.states * 256, stream); /* <= 64 KiB */

@@ -1324,30 +1324,41 @@ extern "C" long hs_b200_limex32_from_literals(const char *const *lits, const siz
     }
 }
 
-static long limexFromSpec(unsigned nstates, const unsigned long long *reach256, unsigned long long init,
-                          unsigned long long init_ds, const unsigned long long *succ,
-                          const unsigned long long *squash_mask, const unsigned char *squash_kind,
-                          const unsigned *report_off, const unsigned *reports, const unsigned *eod_off,
-                          const unsigned *eod_reports, void *out, size_t cap) {
-    if (!reach256 || !succ || !report_off || !eod_off || nstates == 0 || nstates > 64) {
+/* state sets as `words` little-endian 64-bit words each */
+static hsb::StateSet setFromWords(const unsigned long long *w, unsigned words) {
+    hsb::StateSet s;
+    for (unsigned j = 0; j < words; j++) {
+        s |= hsb::stateSetOf(w[j]) << (64 * j);
+    }
+    return s;
+}
+
+static long limexFromSpec(unsigned nstates, unsigned words, const unsigned long long *reach256,
+                          const unsigned long long *init, const unsigned long long *init_ds,
+                          const unsigned long long *succ, const unsigned long long *squash_mask,
+                          const unsigned char *squash_kind, const unsigned *report_off, const unsigned *reports,
+                          const unsigned *eod_off, const unsigned *eod_reports, void *out, size_t cap) {
+    if (!reach256 || !succ || !init || !init_ds || !report_off || !eod_off || nstates == 0 || words == 0 ||
+        words > hsb::MAX_NFA_STATES / 64 || nstates > 64 * words) {
         return -1;
     }
     try {
         hsb::RawNfa n;
         n.nstates = nstates;
         for (unsigned b = 0; b < 256; b++) {
-            n.reach[b] = reach256[b];
+            n.reach[b] = setFromWords(reach256 + (size_t)b * words, words);
         }
-        n.init = init;
-        n.initDS = init_ds;
-        n.succ.assign(succ, succ + nstates);
-        n.squashMask.assign(nstates, ~0ull);
+        n.init = setFromWords(init, words);
+        n.initDS = setFromWords(init_ds, words);
+        n.succ.resize(nstates);
+        n.squashMask.assign(nstates, hsb::allStates());
         n.squashKind.assign(nstates, 0);
         n.reports.resize(nstates);
         n.reportsEod.resize(nstates);
         for (unsigned i = 0; i < nstates; i++) {
+            n.succ[i] = setFromWords(succ + (size_t)i * words, words);
             if (squash_mask && squash_kind) {
-                n.squashMask[i] = squash_mask[i];
+                n.squashMask[i] = setFromWords(squash_mask + (size_t)i * words, words);
                 n.squashKind[i] = squash_kind[i];
             }
             n.reports[i].assign(reports + report_off[i], reports + report_off[i + 1]);
@@ -1359,14 +1370,27 @@ static long limexFromSpec(unsigned nstates, const unsigned long long *reach256, 
     }
 }
 
+extern "C" long hs_b200_limex_from_spec_wide(unsigned nstates, unsigned words, const unsigned long long *reach256,
+                                             const unsigned long long *init, const unsigned long long *init_ds,
+                                             const unsigned long long *succ, const unsigned long long *squash_mask,
+                                             const unsigned char *squash_kind, const unsigned *report_off,
+                                             const unsigned *reports, const unsigned *eod_off,
+                                             const unsigned *eod_reports, void *out, size_t cap) {
+    return limexFromSpec(nstates, words, reach256, init, init_ds, succ, squash_mask, squash_kind, report_off, reports,
+                         eod_off, eod_reports, out, cap);
+}
+
 extern "C" long hs_b200_limex_from_spec64(unsigned nstates, const unsigned long long *reach256,
                                           unsigned long long init, unsigned long long init_ds,
                                           const unsigned long long *succ, const unsigned long long *squash_mask,
                                           const unsigned char *squash_kind, const unsigned *report_off,
                                           const unsigned *reports, const unsigned *eod_off,
                                           const unsigned *eod_reports, void *out, size_t cap) {
-    return limexFromSpec(nstates, reach256, init, init_ds, succ, squash_mask, squash_kind, report_off, reports, eod_off,
-                         eod_reports, out, cap);
+    if (nstates > 64) {
+        return -1;
+    }
+    return limexFromSpec(nstates, 1, reach256, &init, &init_ds, succ, squash_mask, squash_kind, report_off, reports,
+                         eod_off, eod_reports, out, cap);
 }
 
 extern "C" long hs_b200_limex32_from_spec(unsigned nstates, const unsigned *reach256, unsigned init, unsigned init_ds,
@@ -1381,6 +1405,7 @@ extern "C" long hs_b200_limex32_from_spec(unsigned nstates, const unsigned *reac
     if (squash_mask) {
         sq.assign(squash_mask, squash_mask + nstates);
     }
-    return limexFromSpec(nstates, r.data(), init, init_ds, sc.data(), squash_mask ? sq.data() : nullptr, squash_kind,
+    const unsigned long long i0 = init, i1 = init_ds;
+    return limexFromSpec(nstates, 1, r.data(), &i0, &i1, sc.data(), squash_mask ? sq.data() : nullptr, squash_kind,
                          report_off, reports, eod_off, eod_reports, out, cap);
 }

@@ -17,30 +17,30 @@ RawNfa nfaFromLiterals(const std::vector<DfaLiteral> &lits) {
         }
         total += l.s.size();
     }
-    if (total > 64) {
-        throw std::runtime_error("more than 64 NFA states");
+    if (total > MAX_NFA_STATES) {
+        throw std::runtime_error("more than 512 NFA states");
     }
     n.nstates = (u32)total;
-    n.succ.assign(total, 0);
-    n.squashMask.assign(total, ~0ull);
+    n.succ.assign(total, StateSet());
+    n.squashMask.assign(total, allStates());
     n.squashKind.assign(total, LIMEX_SQUASH_NONE);
     n.reports.resize(total);
     n.reportsEod.resize(total);
-    n.init = n.initDS = 1u;
-    n.succ[0] = 1u; /* the start state stays on (.* prefix) */
+    n.init = n.initDS = stateBit(0);
+    n.succ[0] = stateBit(0); /* the start state stays on (.* prefix) */
     for (u32 b = 0; b < 256; b++) {
-        n.reach[b] = 1u;
+        n.reach[b] = stateBit(0);
     }
     u32 next = 1;
     for (const DfaLiteral &l : lits) {
         u32 prev = 0;
         for (size_t i = 0; i < l.s.size(); i++) {
             const u32 st = next++;
-            n.succ[prev] |= 1ull << st;
+            n.succ[prev].set(st);
             const u8 c = (u8)l.s[i];
-            n.reach[c] |= 1ull << st;
+            n.reach[c].set(st);
             if (l.caseless && ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'))) {
-                n.reach[c ^ 0x20] |= 1ull << st;
+                n.reach[c ^ 0x20].set(st);
             }
             prev = st;
         }
@@ -67,22 +67,52 @@ size_t alignUp(std::vector<u8> &b, size_t a) {
 
 } // namespace
 
+/* a state set in an engine field: u32 / u64 take the low word, the wide models all their words */
+template <class T> T fromSet(const StateSet &s) {
+    T t;
+    memset(&t, 0, sizeof(t));
+    for (u32 j = 0; j < sizeof(T) / 8; j++) {
+        const u64 w = stateWord(s, j);
+        memcpy((u8 *)&t + 8 * j, &w, 8);
+    }
+    if (sizeof(T) < 8) {
+        const u32 w = (u32)stateWord(s, 0);
+        memcpy(&t, &w, sizeof(T));
+    }
+    return t;
+}
+
+struct SetLess {
+    bool operator()(const StateSet &a, const StateSet &b) const {
+        for (u32 j = MAX_NFA_STATES / 64; j-- > 0;) {
+            const u64 x = stateWord(a, j), y = stateWord(b, j);
+            if (x != y) {
+                return x < y;
+            }
+        }
+        return false;
+    }
+};
+
 template <class LX, class EX, class T> std::vector<u8> emitLimExT(const RawNfa &n, u8 nfaType) {
     const u32 WIDTH = (u32)sizeof(T) * 8;
     if (n.nstates == 0 || n.nstates > WIDTH || n.succ.size() != n.nstates || n.reports.size() != n.nstates ||
         n.reportsEod.size() != n.nstates || n.squashMask.size() != n.nstates || n.squashKind.size() != n.nstates) {
         throw std::runtime_error("bad NFA description");
     }
-    const T all = n.nstates == WIDTH ? (T)~(T)0 : (T)(((T)1 << n.nstates) - 1);
+    StateSet all;
+    for (u32 i = 0; i < n.nstates; i++) {
+        all.set(i);
+    }
     LX lx;
     memset(&lx, 0, sizeof(lx));
 
     /* reach classes: bytes with the same reach mask share an entry */
-    std::vector<T> reachTab;
+    std::vector<StateSet> reachTab;
     {
-        std::map<T, u32> seen;
+        std::map<StateSet, u32, SetLess> seen;
         for (u32 b = 0; b < 256; b++) {
-            const T m = (T)n.reach[b] & all;
+            const StateSet m = n.reach[b] & all;
             auto it = seen.find(m);
             if (it == seen.end()) {
                 it = seen.emplace(m, (u32)reachTab.size()).first;
@@ -93,11 +123,13 @@ template <class LX, class EX, class T> std::vector<u8> emitLimExT(const RawNfa &
     }
     lx.reachSize = (u32)reachTab.size();
 
-    /* limited transitions: the most common forward distances become shifts */
+    /* limited transitions: the most common forward distances become shifts; a shift never carries a
+     * bit from one 64-bit lane of the state into the next ("can't jump over a bollard") */
+    auto limited = [](u32 from, u32 to) { return (from & ~63u) == (to & ~63u); };
     u32 count[17] = {0};
     for (u32 i = 0; i < n.nstates; i++) {
         for (u32 j = i; j < n.nstates && j <= i + 16; j++) {
-            if ((n.succ[i] >> j) & 1) {
+            if (n.succ[i].test(j) && limited(i, j)) {
                 count[j - i]++;
             }
         }
@@ -113,45 +145,51 @@ template <class LX, class EX, class T> std::vector<u8> emitLimExT(const RawNfa &
         amounts.resize(8);
     }
     std::sort(amounts.begin(), amounts.end());
-    std::vector<T> exceptional(n.nstates, 0); /* successors not covered by a shift */
+    std::vector<StateSet> exceptional(n.nstates); /* successors not covered by a shift */
     for (u32 i = 0; i < n.nstates; i++) {
-        exceptional[i] = (T)n.succ[i] & all;
+        exceptional[i] = n.succ[i] & all;
     }
     lx.shiftCount = std::max<u32>(1, (u32)amounts.size()); /* "should be always greater or equal to 1" */
     for (size_t k = 0; k < amounts.size(); k++) {
         const u32 a = amounts[k];
         lx.shiftAmount[k] = (u8)a;
+        StateSet mask;
         for (u32 i = 0; i + a < n.nstates; i++) {
-            if ((n.succ[i] >> (i + a)) & 1) {
-                lx.shift[k] |= (T)1 << i;
-                exceptional[i] &= ~((T)1 << (i + a));
+            if (n.succ[i].test(i + a) && limited(i, i + a)) {
+                mask.set(i);
+                exceptional[i].reset(i + a);
             }
         }
+        lx.shift[k] = fromSet<T>(mask);
     }
 
+    StateSet accept, acceptEod, excMask;
     for (u32 i = 0; i < n.nstates; i++) {
         if (!n.reports[i].empty()) {
-            lx.accept |= (T)1 << i;
+            accept.set(i);
         }
         if (!n.reportsEod[i].empty()) {
-            lx.acceptAtEOD |= (T)1 << i;
+            acceptEod.set(i);
         }
-        if (exceptional[i] || !n.reports[i].empty() || n.squashKind[i] != LIMEX_SQUASH_NONE) {
-            lx.exceptionMask |= (T)1 << i;
+        if (exceptional[i].any() || !n.reports[i].empty() || n.squashKind[i] != LIMEX_SQUASH_NONE) {
+            excMask.set(i);
         }
     }
-    lx.init = (T)n.init & all;
-    lx.initDS = (T)n.initDS & all;
+    lx.accept = fromSet<T>(accept);
+    lx.acceptAtEOD = fromSet<T>(acceptEod);
+    lx.exceptionMask = fromSet<T>(excMask);
+    lx.init = fromSet<T>(n.init & all);
+    lx.initDS = fromSet<T>(n.initDS & all);
     lx.stateSize = (n.nstates + 7) / 8;
-    lx.acceptCount = (u32)__builtin_popcountll(lx.accept);
-    lx.acceptEodCount = (u32)__builtin_popcountll(lx.acceptAtEOD);
-    lx.exceptionCount = (u32)__builtin_popcountll(lx.exceptionMask);
+    lx.acceptCount = (u32)accept.count();
+    lx.acceptEodCount = (u32)acceptEod.count();
+    lx.exceptionCount = (u32)excMask.count();
 
     /* body after the struct: reach table, report lists, accept tables, exception table
-     * (offsets relative to the LimExNFA32) */
+     * (offsets relative to the LimExNFA) */
     std::vector<u8> body(sizeof(LX), 0);
     for (size_t i = 0; i < reachTab.size(); i++) {
-        put(body, sizeof(LX) + sizeof(T) * i, reachTab[i]);
+        put(body, sizeof(LX) + sizeof(T) * i, fromSet<T>(reachTab[i]));
     }
     auto reportList = [&](const std::vector<u32> &r) -> u32 {
         const u32 off = (u32)alignUp(body, 4);
@@ -170,10 +208,10 @@ template <class LX, class EX, class T> std::vector<u8> emitLimExT(const RawNfa &
             listOffEod[i] = reportList(n.reportsEod[i]);
         }
     }
-    auto acceptTable = [&](T mask, const std::vector<std::vector<u32>> &reps, const std::vector<u32> &offs) -> u32 {
+    auto acceptTable = [&](const StateSet &mask, const std::vector<std::vector<u32>> &reps, const std::vector<u32> &offs) -> u32 {
         const u32 off = (u32)alignUp(body, 4);
         for (u32 i = 0; i < n.nstates; i++) {
-            if (!((mask >> i) & 1)) {
+            if (!mask.test(i)) {
                 continue;
             }
             NFAAccept a;
@@ -185,17 +223,17 @@ template <class LX, class EX, class T> std::vector<u8> emitLimExT(const RawNfa &
         }
         return off;
     };
-    lx.acceptOffset = acceptTable(lx.accept, n.reports, listOff);
-    lx.acceptEodOffset = acceptTable(lx.acceptAtEOD, n.reportsEod, listOffEod);
-    lx.exceptionOffset = (u32)alignUp(body, 16);
+    lx.acceptOffset = acceptTable(accept, n.reports, listOff);
+    lx.acceptEodOffset = acceptTable(acceptEod, n.reportsEod, listOffEod);
+    lx.exceptionOffset = (u32)alignUp(body, alignof(EX) > 16 ? alignof(EX) : 16);
     for (u32 i = 0; i < n.nstates; i++) {
-        if (!((lx.exceptionMask >> i) & 1)) {
+        if (!excMask.test(i)) {
             continue;
         }
         EX e;
         memset(&e, 0, sizeof(e));
-        e.squash = n.squashKind[i] != LIMEX_SQUASH_NONE ? ((T)n.squashMask[i] & all) : all;
-        e.successors = exceptional[i];
+        e.squash = fromSet<T>(n.squashKind[i] != LIMEX_SQUASH_NONE ? (n.squashMask[i] & all) : all);
+        e.successors = fromSet<T>(exceptional[i]);
         e.reports = listOff[i];
         e.repeatOffset = MO_INVALID_IDX;
         e.hasSquash = n.squashKind[i];
@@ -211,7 +249,7 @@ template <class LX, class EX, class T> std::vector<u8> emitLimExT(const RawNfa &
     hdr.type = nfaType;
     hdr.length = (u32)(sizeof(NFA) + body.size());
     hdr.nPositions = n.nstates;
-    hdr.scratchStateSize = (u32)sizeof(T);
+    hdr.scratchStateSize = (u32)std::max<size_t>(sizeof(T), nfaType == NFA_LIMEX_64 ? 16 : 0); /* NFATraits::scratch_state_size, limex_compile.cpp:2419-2428 */
     hdr.streamStateSize = lx.stateSize;
     hdr.flags = lx.acceptEodCount ? NFA_ACCEPTS_EOD : 0;
     std::vector<u8> out(sizeof(NFA));
@@ -221,8 +259,19 @@ template <class LX, class EX, class T> std::vector<u8> emitLimExT(const RawNfa &
 }
 
 std::vector<u8> emitLimEx(const RawNfa &n) {
-    return n.nstates <= 32 ? emitLimExT<LimExNFA32, NFAException32, u32>(n, NFA_LIMEX_32)
-                           : emitLimExT<LimExNFA64, NFAException64, u64>(n, NFA_LIMEX_64);
+    if (n.nstates <= 32) {
+        return emitLimExT<LimExNFA32, NFAException32, u32>(n, NFA_LIMEX_32);
+    }
+    if (n.nstates <= 64) {
+        return emitLimExT<LimExNFA64, NFAException64, u64>(n, NFA_LIMEX_64);
+    }
+    if (n.nstates <= 128) {
+        return emitLimExT<LimExNFA128, NFAException128, StateWord128>(n, NFA_LIMEX_128);
+    }
+    if (n.nstates <= 256) {
+        return emitLimExT<LimExNFA256, NFAException256, StateWord256>(n, NFA_LIMEX_256);
+    }
+    return emitLimExT<LimExNFA512, NFAException512, StateWord512>(n, NFA_LIMEX_512);
 }
 
 } // namespace hsb

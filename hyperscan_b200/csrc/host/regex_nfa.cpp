@@ -76,6 +76,7 @@ private:
     const char *re;
     size_t n, pos = 0;
     unsigned flags;
+    size_t unrolled = 0;  /* positions made by unrolling bounded repeats so far */
     bool quoting = false; /* between \\Q and \\E: every byte is a literal */
 
     [[noreturn]] void fail(const std::string &m) const { throw RegexError{m}; }
@@ -190,7 +191,20 @@ private:
         return false;
     }
 
+    static size_t leaves(const NodeP &x) {
+        size_t c = x->kind == Node::CLASS || x->kind == Node::ASSERT;
+        for (const NodeP &k : x->kids) {
+            c += leaves(k);
+        }
+        return c;
+    }
+
     NodeP repeat(const NodeP &a, unsigned lo, long hi /* -1 = unbounded */) {
+        /* repeats are unrolled: refuse before copying what cannot fit the largest model anyway */
+        unrolled += leaves(a) * std::max<size_t>(hi < 0 ? lo + 1 : (size_t)hi, 1);
+        if (unrolled > 4 * MAX_NFA_STATES) {
+            fail("Pattern is too large.");
+        }
         NodeP s = mk(Node::CAT);
         for (unsigned i = 0; i < lo; i++) {
             s->kids.push_back(clone(a));
@@ -263,7 +277,7 @@ private:
             if (comma && haveY && y < x) {
                 fail("Bounded repeat is invalid: min > max.");
             }
-            if (x > 64 || (haveY && y > 64)) {
+            if (x > 1000 || (haveY && y > 1000)) {
                 fail("Pattern is too large.");
             }
             pos = q + 1;
@@ -626,51 +640,52 @@ private:
 /* Glushkov: positions, nullable / first / last / follow */
 struct Glushkov {
     std::vector<CharSet> cls;         /* per position */
-    std::vector<u64> follow;          /* per position: bitmask over positions */
+    std::vector<StateSet> follow;     /* per position: set of positions */
     std::vector<int> assertion;       /* per position: 0 = a character position, else the A_* bit of a zero-width
                                        * pseudo-position (eliminated when the NFA is wired) */
     struct Sets {
         bool nullable;
-        u64 first, last;
+        StateSet first, last;
     };
+    static const u32 MAX_POSITIONS = MAX_NFA_STATES - 2; /* the two start states come first */
 
     Sets build(const NodeP &n) {
         switch (n->kind) {
         case Node::EMPTY:
-            return {true, 0, 0};
+            return {true, StateSet(), StateSet()};
         case Node::CLASS: {
-            if (cls.size() >= 62) {
-                throw RegexError{"Pattern is too large: more than 62 character positions need the larger NFA models."};
+            if (cls.size() >= MAX_POSITIONS) {
+                throw RegexError{"Pattern is too large: more than 510 character positions."};
             }
             const u32 p = (u32)cls.size();
             cls.push_back(n->cls);
-            follow.push_back(0);
+            follow.push_back(StateSet());
             assertion.push_back(0);
-            return {false, 1ull << p, 1ull << p};
+            return {false, stateBit(p), stateBit(p)};
         }
         case Node::ASSERT: {
-            if (cls.size() >= 62) {
-                throw RegexError{"Pattern is too large: more than 62 character positions need the larger NFA models."};
+            if (cls.size() >= MAX_POSITIONS) {
+                throw RegexError{"Pattern is too large: more than 510 character positions."};
             }
             const u32 p = (u32)cls.size();
             cls.push_back(CharSet());
-            follow.push_back(0);
+            follow.push_back(StateSet());
             assertion.push_back(n->assertKind);
-            return {false, 1ull << p, 1ull << p};
+            return {false, stateBit(p), stateBit(p)};
         }
         case Node::CAT: {
-            Sets acc = {true, 0, 0};
+            Sets acc = {true, StateSet(), StateSet()};
             for (const NodeP &k : n->kids) {
                 const Sets s = build(k);
                 link(acc.last, s.first);
-                const u64 first = acc.nullable ? (acc.first | s.first) : acc.first;
-                const u64 last = s.nullable ? (acc.last | s.last) : s.last;
+                const StateSet first = acc.nullable ? (acc.first | s.first) : acc.first;
+                const StateSet last = s.nullable ? (acc.last | s.last) : s.last;
                 acc = {acc.nullable && s.nullable, first, last};
             }
             return acc;
         }
         case Node::ALT: {
-            Sets acc = {false, 0, 0};
+            Sets acc = {false, StateSet(), StateSet()};
             for (const NodeP &k : n->kids) {
                 const Sets s = build(k);
                 acc = {acc.nullable || s.nullable, acc.first | s.first, acc.last | s.last};
@@ -688,12 +703,12 @@ struct Glushkov {
             return {true, s.first, s.last};
         }
         }
-        return {true, 0, 0};
+        return {true, StateSet(), StateSet()};
     }
 
-    void link(u64 from, u64 to) {
+    void link(const StateSet &from, const StateSet &to) {
         for (u32 p = 0; p < follow.size(); p++) {
-            if ((from >> p) & 1) {
+            if (from.test(p)) {
                 follow[p] |= to;
             }
         }
@@ -719,10 +734,10 @@ struct Glushkov {
     }
     /* character positions reachable from the position set `from` through assertion pseudo-positions only,
      * each with the assertions crossed: out[(q, need)] */
-    void reachThroughAssertions(u64 from, u32 need, std::vector<std::pair<u32, u32>> *out,
+    void reachThroughAssertions(const StateSet &from, u32 need, std::vector<std::pair<u32, u32>> *out,
                                 std::vector<u8> *seen /* [position][need] */) const {
         for (u32 x = 0; x < cls.size(); x++) {
-            if (!((from >> x) & 1)) {
+            if (!from.test(x)) {
                 continue;
             }
             if (!assertion[x]) {
@@ -739,9 +754,9 @@ struct Glushkov {
         }
     }
     /* the assertion sets under which a path from p (exclusive) through assertions only ends in `last` */
-    void exitsThroughAssertions(u64 from, u32 need, u64 last, std::vector<u32> *needs, std::vector<u8> *seen) const {
+    void exitsThroughAssertions(const StateSet &from, u32 need, const StateSet &last, std::vector<u32> *needs, std::vector<u8> *seen) const {
         for (u32 x = 0; x < cls.size(); x++) {
-            if (!((from >> x) & 1) || !assertion[x]) {
+            if (!from.test(x) || !assertion[x]) {
                 continue;
             }
             const u32 n2 = need | (u32)assertion[x];
@@ -750,7 +765,7 @@ struct Glushkov {
                 continue;
             }
             mark = 1;
-            if ((last >> x) & 1) {
+            if (last.test(x)) {
                 needs->push_back(n2);
             }
             exitsThroughAssertions(follow[x], n2, last, needs, seen);
@@ -874,28 +889,28 @@ RegexInfo regexInfo(const char *re, unsigned flags) {
 void regexNfaInit(RawNfa *nfa) {
     *nfa = RawNfa();
     nfa->nstates = 2; /* 0 = floating start (.* loop), 1 = anchored start (offset 0 only) */
-    nfa->succ.assign(2, 0);
-    nfa->succ[0] = 1u;
-    nfa->squashMask.assign(2, ~0ull);
+    nfa->succ.assign(2, StateSet());
+    nfa->succ[0] = stateBit(0);
+    nfa->squashMask.assign(2, allStates());
     nfa->squashKind.assign(2, LIMEX_SQUASH_NONE);
     nfa->reports.resize(2);
     nfa->reportsEod.resize(2);
     for (u32 b = 0; b < 256; b++) {
-        nfa->reach[b] = 1u; /* the floating start survives every byte; nothing re-enters state 1 */
+        nfa->reach[b] = stateBit(0); /* the floating start survives every byte; nothing re-enters state 1 */
     }
-    nfa->init = nfa->initDS = 3u;
+    nfa->init = nfa->initDS = stateSetOf(3);
 }
 
 void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline) {
     const NodeP root = Parser(re, flags).parse();
     const CharSet W = Glushkov::wordSet();
     auto newState = [&]() -> u32 {
-        if (nfa->nstates >= 64) {
-            throw RegexError{"Pattern set is too large: its character positions exceed the 64-state NFA model."};
+        if (nfa->nstates >= MAX_NFA_STATES) {
+            throw RegexError{"Pattern set is too large: its character positions exceed the 512-state NFA model."};
         }
         nfa->nstates++;
-        nfa->succ.push_back(0);
-        nfa->squashMask.push_back(~0ull);
+        nfa->succ.push_back(StateSet());
+        nfa->squashMask.push_back(allStates());
         nfa->squashKind.push_back(LIMEX_SQUASH_NONE);
         nfa->reports.emplace_back();
         nfa->reportsEod.emplace_back();
@@ -904,7 +919,7 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
     auto reachClass = [&](u32 st, const CharSet &c) {
         for (u32 b = 0; b < 256; b++) {
             if (c[b]) {
-                nfa->reach[b] |= 1ull << st;
+                nfa->reach[b].set(st);
             }
         }
     };
@@ -941,7 +956,7 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                     continue; /* an anchor between two characters (the parser lets none through) */
                 }
                 if (Glushkov::holds(e.second, g.isWord(p), g.isWord(e.first))) {
-                    nfa->succ[st[p]] |= 1ull << st[e.first];
+                    nfa->succ[st[p]].set(st[e.first]);
                 }
             }
         }
@@ -953,7 +968,7 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
             g.reachThroughAssertions(s.first, 0, &entries, &seen);
         }
         for (const auto &e : entries) {
-            const u64 bit = 1ull << st[e.first];
+            const u32 entry = st[e.first];
             const bool qw = asserts && g.isWord(e.first);
             if (e.second & A_ENDS) {
                 continue; /* a character after the end of the data */
@@ -963,19 +978,19 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                 if (!Glushkov::holds(e.second, false, qw)) {
                     continue;
                 }
-                nfa->succ[1] |= bit;
+                nfa->succ[1].set(entry);
                 if (!(e.second & A_BEGIN)) {
                     /* "^" under (?m): entered at offset 0 (anchored start) or right after any newline --
                      * one state shared by all such entries, on after every '\n' */
                     if (!nfa->mlStartState) {
                         nfa->mlStartState = newState();
-                        nfa->reach[(u8)'\n'] |= 1ull << nfa->mlStartState;
-                        nfa->succ[0] |= 1ull << nfa->mlStartState;
+                        nfa->reach[(u8)'\n'].set(nfa->mlStartState);
+                        nfa->succ[0].set(nfa->mlStartState);
                     }
-                    nfa->succ[nfa->mlStartState] |= bit;
+                    nfa->succ[nfa->mlStartState].set(entry);
                 }
             } else if (e.second == 0) {
-                nfa->succ[0] |= bit;
+                nfa->succ[0].set(entry);
             } else {
                 /* a leading \b / \B of a floating entry: the byte before the match decides.  Two
                  * shared context states hang off the floating start: "previous byte is a word character"
@@ -985,15 +1000,15 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                     nfa->ctxNonWord = newState();
                     reachClass(nfa->ctxWord, W);
                     reachClass(nfa->ctxNonWord, ~W);
-                    nfa->succ[0] |= (1ull << nfa->ctxWord) | (1ull << nfa->ctxNonWord);
-                    nfa->init |= 1ull << nfa->ctxNonWord;
-                    nfa->initDS |= 1ull << nfa->ctxNonWord;
+                    nfa->succ[0].set(nfa->ctxWord).set(nfa->ctxNonWord);
+                    nfa->init.set(nfa->ctxNonWord);
+                    nfa->initDS.set(nfa->ctxNonWord);
                 }
                 if (Glushkov::holds(e.second, true, qw)) {
-                    nfa->succ[nfa->ctxWord] |= bit;
+                    nfa->succ[nfa->ctxWord].set(entry);
                 }
                 if (Glushkov::holds(e.second, false, qw)) {
-                    nfa->succ[nfa->ctxNonWord] |= bit;
+                    nfa->succ[nfa->ctxNonWord].set(entry);
                 }
             }
         }
@@ -1018,7 +1033,7 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
             if (g.assertion[p]) {
                 continue;
             }
-            if ((s.last >> p) & 1) {
+            if (s.last.test(p)) {
                 addOnce(nfa->reports[st[p]], report);
             }
             std::vector<u32> needs;
@@ -1039,17 +1054,17 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                     if (need & A_END_LF) {
                         if (!aheadLastNewline) {
                             aheadLastNewline = newState();
-                            nfa->reach[(u8)'\n'] |= 1ull << aheadLastNewline;
+                            nfa->reach[(u8)'\n'].set(aheadLastNewline);
                             nfa->reportsEod[aheadLastNewline].push_back(adjusted());
                         }
-                        nfa->succ[st[p]] |= 1ull << aheadLastNewline;
+                        nfa->succ[st[p]].set(aheadLastNewline);
                     } else {
                         if (!aheadNewline) {
                             aheadNewline = newState();
-                            nfa->reach[(u8)'\n'] |= 1ull << aheadNewline;
+                            nfa->reach[(u8)'\n'].set(aheadNewline);
                             nfa->reports[aheadNewline].push_back(adjusted());
                         }
-                        nfa->succ[st[p]] |= 1ull << aheadNewline;
+                        nfa->succ[st[p]].set(aheadNewline);
                     }
                     continue;
                 }
@@ -1059,7 +1074,7 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                         reachClass(aheadWord, W);
                         nfa->reports[aheadWord].push_back(adjusted());
                     }
-                    nfa->succ[st[p]] |= 1ull << aheadWord;
+                    nfa->succ[st[p]].set(aheadWord);
                 }
                 if (Glushkov::holds(need, pw, false)) {
                     if (!aheadNonWord) {
@@ -1067,7 +1082,7 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                         reachClass(aheadNonWord, ~W);
                         nfa->reports[aheadNonWord].push_back(adjusted());
                     }
-                    nfa->succ[st[p]] |= 1ull << aheadNonWord;
+                    nfa->succ[st[p]].set(aheadNonWord);
                 }
             }
         }

@@ -356,7 +356,7 @@ struct InstrSetExhaust { u8 code; u32 ekey; };
 /* ---- NFA engines (DFA subset): src/nfa/nfa_internal.h:53-126,
  *      src/nfa/mcclellan_internal.h:36-106 -------------------------------- */
 
-enum { NFA_LIMEX_32 = 0, NFA_LIMEX_64 = 1, NFA_MCCLELLAN_8 = 6, NFA_MCCLELLAN_16 = 7, NFA_SHENG = 17 };
+enum { NFA_LIMEX_32 = 0, NFA_LIMEX_64 = 1, NFA_LIMEX_128 = 2, NFA_LIMEX_256 = 3, NFA_LIMEX_384 = 4, NFA_LIMEX_512 = 5, NFA_MCCLELLAN_8 = 6, NFA_MCCLELLAN_16 = 7, NFA_SHENG = 17 };
 
 struct alignas(64) NFA {
     u32 flags;
@@ -456,6 +456,41 @@ struct LimExNFA64 {
     alignas(64) u8 exceptionBitMask[64];
     alignas(64) u8 exceptionAndMask[64];
 };
+/* ... and the 128-, 256- and 512-state models (CREATE_NFA_LIMEX(128 / 256 / 512)): the same fields over m128 /
+ * m256 / m512, which are restated here as arrays of 64-bit words with the vector types' alignment (the 384-state
+ * model is not emitted: an automaton of 257-384 states takes the 512-state one) */
+template <unsigned BYTES> struct alignas(BYTES) StateWordT {
+    u64 w[BYTES / 8];
+};
+typedef StateWordT<16> StateWord128;
+typedef StateWordT<32> StateWord256;
+typedef StateWordT<64> StateWord512;
+template <class T> struct NFAExceptionW {
+    T squash, successors;
+    u32 reports, repeatOffset;
+    u8 hasSquash, trigger;
+};
+template <class T> struct LimExNFAW {
+    u8 reachMap[256];
+    u32 reachSize, accelCount, accelTableOffset, accelAuxCount, accelAuxOffset;
+    u32 acceptCount, acceptOffset, acceptEodCount, acceptEodOffset;
+    u32 exceptionCount, exceptionOffset, repeatCount, repeatOffset;
+    u32 squashOffset, squashCount, topCount, topOffset, stateSize, flags;
+    T init, initDS, accept, acceptAtEOD, accel, accelPermute, accelCompare, accel_and_friends;
+    T compressMask, exceptionMask, repeatCyclicMask, zombieMask;
+    T shift[8];
+    u32 shiftCount;
+    u8 shiftAmount[8];
+    alignas(64) u8 exceptionShufMask[64];
+    alignas(64) u8 exceptionBitMask[64];
+    alignas(64) u8 exceptionAndMask[64];
+};
+typedef NFAExceptionW<StateWord128> NFAException128;
+typedef NFAExceptionW<StateWord256> NFAException256;
+typedef NFAExceptionW<StateWord512> NFAException512;
+typedef LimExNFAW<StateWord128> LimExNFA128;
+typedef LimExNFAW<StateWord256> LimExNFA256;
+typedef LimExNFAW<StateWord512> LimExNFA512;
 static const u32 MO_INVALID_IDX = 0xffffffffu;            /* src/ue2common.h */
 static const u32 LIMEX_FLAG_CANNOT_DIE = 4;               /* limex_internal.h:89 */
 static const u8 LIMEX_SQUASH_NONE = 0, LIMEX_SQUASH_CYCLIC = 1, LIMEX_SQUASH_TUG = 2, LIMEX_SQUASH_REPORT = 3;

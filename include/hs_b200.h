@@ -492,6 +492,16 @@ long hs_b200_limex_from_spec64(unsigned nstates, const unsigned long long *reach
                                const unsigned long long *squash_mask, const unsigned char *squash_kind,
                                const unsigned *report_off, const unsigned *reports, const unsigned *eod_off,
                                const unsigned *eod_reports, void *out, size_t cap);
+/* ... and over state sets of `words` 64-bit words each (words <= 8: up to 512 states; every set argument is
+ * `words` little-endian words per set, reach256 = 256 sets, succ / squash_mask = nstates sets): emitted as the
+ * smallest of the 32 / 64 / 128 / 256 / 512-state models that holds nstates (struct LimExNFA128 ...,
+ * nfaExecLimEx128_Q ...; an automaton of 257-384 states takes the 512-state model) */
+long hs_b200_limex_from_spec_wide(unsigned nstates, unsigned words, const unsigned long long *reach256,
+                                  const unsigned long long *init, const unsigned long long *init_ds,
+                                  const unsigned long long *succ, const unsigned long long *squash_mask,
+                                  const unsigned char *squash_kind, const unsigned *report_off,
+                                  const unsigned *reports, const unsigned *eod_off, const unsigned *eod_reports,
+                                  void *out, size_t cap);
 
 /* Test hook: pure-literal block database whose literal programs are raw
  * instruction bytes (layouts: src/rose/rose_program.h:214-724).  `area` is

@@ -1,6 +1,6 @@
 """TEST INFRASTRUCTURE (like the rest of oracle/): a plain-Python restatement of the
-reference's LimEx runtime (32- and 64-state models) in block mode, read straight from the
-engine's bytes (struct NFA + struct LimExNFA32 / 64, src/nfa/limex_internal.h:102-203).  Only tests/ may
+reference's LimEx runtime (32- to 512-state models) in block mode, read straight from the
+engine's bytes (struct NFA + struct LimExNFA32 ... 512, src/nfa/limex_internal.h:102-203).  Only tests/ may
 import it; the product never does.
 
 Follows, for one block scanned the way Rose runs an outfix (queue {START@0, TOP@0,
@@ -14,6 +14,8 @@ END@len} through nfaExecLimEx32_Q, then nfaExecLimEx32_testEOD):
     of the scan (NO_OUTPUT | FIRST_BYTE), successors collected aside, squash applied to
     the shift successors for LIMEX_SQUASH_CYCLIC / _REPORT
   * moProcessAccepts32 (limex_common_impl.h:116-176) and moNfaTestEod32 (:192-218)
+The models above 64 states shift each 64-bit lane of the state on its own (lshift_m128 = lshift64_m128 ...,
+src/util/uniform_ops.h:142-145).
 Bounded repeats and acceleration are not modelled (the emitters do not produce them)."""
 import json
 import os
@@ -51,7 +53,7 @@ def _reports(lx, off):
 
 
 def _accepts(lx, found, mask, table, to, out, block):
-    for bit in range(64):
+    for bit in range(found.bit_length()):
         if not (found >> bit) & 1:
             continue
         idx = bin(mask & ((1 << bit) - 1)).count("1")
@@ -61,14 +63,21 @@ def _accepts(lx, found, mask, table, to, out, block):
 
 
 def _state(b, off, bits):
-    return struct.unpack_from("<I" if bits == 32 else "<Q", b, off)[0]
+    return int.from_bytes(b[off:off + bits // 8], "little")
+
+
+def _shift_lanes(v, a, bits):
+    """LSHIFT_STATE: a plain shift up to 64 bits, lane by lane (64-bit lanes) above"""
+    if bits <= 64:
+        return (v << a) & ((1 << bits) - 1)
+    m64 = (1 << 64) - 1
+    return sum(((((v >> (64 * j)) & m64) << a) & m64) << (64 * j) for j in range(bits // 64))
 
 
 def walk_blocks(engine, data, offsets, lengths):
     """[(report, block, to)] in callback order"""
-    assert engine[8] in (0, 1), "neither LIMEX_NFA_32 nor LIMEX_NFA_64"
-    bits = 32 if engine[8] == 0 else 64
-    full = (1 << bits) - 1
+    assert engine[8] in (0, 1, 2, 3, 5), "not one of the LimEx models restated here"
+    bits = {0: 32, 1: 64, 2: 128, 3: 256, 5: 512}[engine[8]]
     O = _offsets(bits)
     lx = bytes(engine[NFA_HDR:])
     assert _u32(lx, O["repeatCount"]) == 0
@@ -78,8 +87,11 @@ def walk_blocks(engine, data, offsets, lengths):
     shifts = [(_state(lx, O["shift"] + (bits // 8) * k, bits), lx[O["shiftAmount"] + k]) for k in range(nshift)]
     emask = _state(lx, O["exceptionMask"], bits)
     eoff = _u32(lx, O["exceptionOffset"])
-    fmt = "<IIIIBB" if bits == 32 else "<QQIIBB"
-    exc = [struct.unpack_from(fmt, lx, eoff + O["exc_size"] * i) for i in range(_u32(lx, O["exceptionCount"]))]
+    sb = bits // 8
+
+    def exception(off):
+        return (_state(lx, off, bits), _state(lx, off + sb, bits)) + struct.unpack_from("<IIBB", lx, off + 2 * sb)
+    exc = [exception(eoff + O["exc_size"] * i) for i in range(_u32(lx, O["exceptionCount"]))]
     accept, accept_eod = _state(lx, O["accept"], bits), _state(lx, O["acceptAtEOD"], bits)
     init = _state(lx, O["init"], bits)
     out = []
@@ -89,11 +101,11 @@ def walk_blocks(engine, data, offsets, lengths):
         for i in range(n):
             succ = 0
             for m, a in shifts:
-                succ |= ((s & m) << a) & full
+                succ |= _shift_lanes(s & m, a, bits)
             est = s & emask
             if est:
                 local = 0
-                for bit in range(bits):
+                for bit in range(est.bit_length()):
                     if not (est >> bit) & 1:
                         continue
                     squash, successors, reports, _rep, has_squash, _trig = exc[bin(emask & ((1 << bit) - 1)).count("1")]

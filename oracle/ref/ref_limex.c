@@ -1,7 +1,7 @@
-/* ref_limex.c -- the reference's LimEx-32 engine over blocks, the way Rose runs an outfix
+/* ref_limex.c -- the reference's LimEx engines (32 ... 512 states) over blocks, the way Rose runs an outfix
  * in block mode (src/rose/block.c:218-262, src/rose/match.h:initQueue / pushQueue...):
- * a queue {MQE_START@0, MQE_TOP@0, MQE_END@len} through nfaExecLimEx32_Q, then
- * nfaExecLimEx32_testEOD; plus sizeof/offsetof of its structures for ref_layout_dump().
+ * a queue {MQE_START@0, MQE_TOP@0, MQE_END@len} through nfaExecLimEx<N>_Q, then
+ * nfaExecLimEx<N>_testEOD; plus sizeof/offsetof of its structures for ref_layout_dump().
  * TEST INFRASTRUCTURE ONLY (part of oracle/_ref). */
 #include <stddef.h>
 #include <stdio.h>
@@ -20,14 +20,16 @@ struct limex_collect {
     void *ctx;
 };
 
-/* one block: returns 0 if the engine type is neither LimEx-32 nor LimEx-64 */
+/* one block: returns 0 if the engine type is not one of the LimEx models (32 ... 512 states) */
+#define LIMEX_CASES(X) X(32) X(64) X(128) X(256) X(384) X(512)
 int ref_limex32_block(const struct NFA *n, const u8 *buf, size_t len, NfaCallback cb, void *ctx) {
-    if (n->type != LIMEX_NFA_32 && n->type != LIMEX_NFA_64) {
+    if (n->type > LIMEX_NFA_512) {
         return 0;
     }
     struct mq *q = (struct mq *)calloc(1, sizeof(struct mq));
-    char *state = (char *)calloc(1, n->scratchStateSize + 64);
+    char *state = (char *)aligned_alloc(64, (n->scratchStateSize + 127) / 64 * 64);  /* m512 state: aligned loads */
     char *sstate = (char *)calloc(1, n->streamStateSize + 64);
+    memset(state, 0, (n->scratchStateSize + 127) / 64 * 64);
     q->nfa = n;
     q->cur = q->end = 0;
     q->state = state;
@@ -41,20 +43,19 @@ int ref_limex32_block(const struct NFA *n, const u8 *buf, size_t len, NfaCallbac
     q->report_current = 0;
     q->cb = cb;
     q->context = ctx;
-    if (n->type == LIMEX_NFA_32) {
-        nfaExecLimEx32_queueInitState(n, q);
-    } else {
-        nfaExecLimEx64_queueInitState(n, q);
+    switch (n->type) {
+#define INIT(sz) case LIMEX_NFA_##sz: nfaExecLimEx##sz##_queueInitState(n, q); break;
+        LIMEX_CASES(INIT)
     }
     pushQueue(q, MQE_START, 0);
     pushQueue(q, MQE_TOP, 0);
     pushQueue(q, MQE_END, (s64a)len);
-    if (n->type == LIMEX_NFA_32) {
-        nfaExecLimEx32_Q(n, q, (s64a)len);
-        nfaExecLimEx32_testEOD(n, q->state, q->streamState, len, cb, ctx);
-    } else {
-        nfaExecLimEx64_Q(n, q, (s64a)len);
-        nfaExecLimEx64_testEOD(n, q->state, q->streamState, len, cb, ctx);
+    switch (n->type) {
+#define RUN(sz) case LIMEX_NFA_##sz:                                                   \
+        nfaExecLimEx##sz##_Q(n, q, (s64a)len);                                         \
+        nfaExecLimEx##sz##_testEOD(n, q->state, q->streamState, len, cb, ctx);         \
+        break;
+        LIMEX_CASES(RUN)
     }
     free(sstate);
     free(state);
@@ -100,6 +101,20 @@ void ref_layout_dump_limex(void) {
     SZ(NFAException64);
     OFF(NFAException64, squash); OFF(NFAException64, successors); OFF(NFAException64, reports);
     OFF(NFAException64, repeatOffset); OFF(NFAException64, hasSquash); OFF(NFAException64, trigger);
+#define DUMP_WIDE(L, E)                                                                                  \
+    SZ(L); OFF(L, reachMap); OFF(L, reachSize); OFF(L, acceptCount); OFF(L, acceptOffset); OFF(L, acceptEodCount); \
+    OFF(L, acceptEodOffset); OFF(L, exceptionCount); OFF(L, exceptionOffset); OFF(L, repeatCount); OFF(L, topOffset); OFF(L, stateSize); \
+    OFF(L, flags); OFF(L, init); OFF(L, initDS); OFF(L, accept); OFF(L, acceptAtEOD); OFF(L, accel);         \
+    OFF(L, compressMask); OFF(L, exceptionMask); OFF(L, repeatCyclicMask); OFF(L, zombieMask); OFF(L, shift); \
+    OFF(L, shiftCount); OFF(L, shiftAmount); OFF(L, exceptionShufMask); OFF(L, exceptionBitMask);            \
+    OFF(L, exceptionAndMask); SZ(E); OFF(E, squash); OFF(E, successors); OFF(E, reports); OFF(E, repeatOffset); \
+    OFF(E, hasSquash); OFF(E, trigger);
+    DUMP_WIDE(LimExNFA128, NFAException128)
+    DUMP_WIDE(LimExNFA256, NFAException256)
+    DUMP_WIDE(LimExNFA512, NFAException512)
+    printf("  \"LIMEX_NFA_128\": %d,\n", (int)LIMEX_NFA_128);
+    printf("  \"LIMEX_NFA_256\": %d,\n", (int)LIMEX_NFA_256);
+    printf("  \"LIMEX_NFA_512\": %d,\n", (int)LIMEX_NFA_512);
     SZ(NFAAccept);
     OFF(NFAAccept, single_report); OFF(NFAAccept, reports); OFF(NFAAccept, squash);
     printf("  \"LIMEX_NFA_32\": %d,\n", (int)LIMEX_NFA_32);

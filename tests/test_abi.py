@@ -232,7 +232,7 @@ def test_finite_language_limits_and_errors(hs):
     for bad, why in [(rb"a*", "empty buffer"), (rb"a$b", "Embedded end anchors"), (rb"(?<=a)b", "Look-around"), (rb"a|", "empty buffer"),
                      (rb"(ab", "parenthesis"), (rb"ab)", "parentheses"), (rb"(a)\1", "Escape sequence"),
                      (rb"a??", "empty buffer"), (rb"[[:nope:]]", "POSIX"), (rb"a{3,2}", "min > max"),
-                     (rb"*a", "nothing to repeat"), (rb"[ab", "Unterminated"), (rb"[a-z]{65}x+", "too large")]:
+                     (rb"*a", "nothing to repeat"), (rb"[ab", "Unterminated"), (rb"[a-z]{1001}x+", "too large")]:
         with pytest.raises(hs.HsError) as e:
             hs.compile_multi([b"ok", bad])
         assert why in e.value.message, (bad, e.value.message)

@@ -168,7 +168,7 @@ def test_device_refuses_other_engines(hs):
     eng = bytearray(hs.dfa_from_literals([b"ab"], None, [1], kind=KINDS["mcclellan16"]))
     data, off, ln = synth.ragged_corpus([64], None, seed=1, plant_per_kb=0)
     corpus = hs.Corpus.upload(data, off, ln)
-    eng[8] = 2                                                   # LIMEX_NFA_128
+    eng[8] = 4                                                   # LIMEX_NFA_384: not built
     with pytest.raises(hs.HsError) as e:
         hs.nfa_scan_corpus(bytes(eng), corpus)
     assert e.value.code == hs.HS_ARCH_ERROR

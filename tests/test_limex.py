@@ -96,11 +96,62 @@ def test_random_nfas_reference_equals_restatement(hs, ref, seed, wide):
     assert got == sorted(model.walk_blocks(eng, data, off, ln))
 
 
+def _random_wide_nfa(seed, n):
+    """the same over n > 64 states, state sets as Python ints; sparse enough that the automaton neither dies at
+    once nor saturates: every state has a neighbour edge (a limited shift unless it crosses a 64-bit lane) and a
+    few far ones (exceptions)"""
+    rng = np.random.default_rng(seed)
+    full = (1 << n) - 1
+
+    def rand(density):
+        return sum(1 << i for i in np.flatnonzero(rng.random(n) < density).tolist())
+    classes = rng.integers(0, 6, size=256)
+    masks = [rand(0.5) | 1 for _ in range(6)]
+    reach = [masks[c] for c in classes]
+    succ = []
+    for s in range(n):
+        m = 0
+        for d in (1, 2, 5):
+            if rng.random() < (0.8 if d == 1 else 0.25) and s + d < n:
+                m |= 1 << (s + d)
+        for _ in range(int(rng.integers(0, 3))):
+            m |= 1 << int(rng.integers(0, n))
+        if rng.random() < 0.2:
+            m |= 1 << s
+        succ.append(m)
+    succ[0] |= 1
+    reports = [sorted(set(rng.integers(0, 6, size=int(rng.integers(1, 3))).tolist())) if rng.random() < 0.1 else []
+               for _ in range(n)]
+    eod = [[int(rng.integers(50, 54))] if rng.random() < 0.1 else [] for _ in range(n)]
+    kind = [int(rng.choice([0, 0, 0, 0, 1, 3])) for _ in range(n)]
+    sqm = [rand(0.9) for _ in range(n)]
+    init = 1 | (rand(0.02) & full)
+    return reach, init, succ, reports, eod, sqm, kind
+
+
+WIDE_SIZES = [(65, 2), (100, 2), (128, 2), (129, 3), (200, 3), (256, 3), (257, 5), (300, 5), (384, 5), (450, 5), (512, 5)]
+
+
+@pytest.mark.parametrize("n,kind", WIDE_SIZES)
+def test_random_wide_nfas_reference_equals_restatement(hs, ref, n, kind):
+    for seed in range(3):
+        reach, init, succ, reports, eod, sqm, sk = _random_wide_nfa(1000 * n + seed, n)
+        eng = hs.limex_from_spec_wide(reach, init, init, succ, reports, eod, sqm, sk)
+        assert eng[8] == kind                                         # LIMEX_NFA_128 / _256 / _512
+        data, off, ln = _random_corpus(300 + seed)
+        got = _triples(ref.nfa_exec_blocks(eng, data, off, ln))
+        assert got == sorted(model.walk_blocks(eng, data, off, ln))
+        assert len(got) > 50
+
+
 def test_builder_limits(hs):
     with pytest.raises(hs.HsError):
-        hs.limex32_from_literals([b"a" * 64], [0], [1])              # 65 states
+        hs.limex32_from_literals([b"a" * 512], [0], [1])             # 513 states
     assert hs.limex32_from_literals([b"a" * 31], [0], [1])[8] == 0
     assert hs.limex32_from_literals([b"a" * 32], [0], [1])[8] == 1   # 33 states: the 64-state model
+    assert hs.limex32_from_literals([b"a" * 64], [0], [1])[8] == 2   # 65: LIMEX_NFA_128
+    assert hs.limex32_from_literals([b"ab" * 100], [0], [1])[8] == 3
+    assert hs.limex32_from_literals([b"abc" * 100], [0], [1])[8] == 5
 
 
 # ---- device --------------------------------------------------------------------------------
@@ -126,6 +177,34 @@ def test_device_limex_equals_reference_random(hs, ref, seed, wide):
     got, ms = hs.nfa_scan_corpus(eng, corpus, cap=64)                 # forces the grow-and-retry path
     want = ref.nfa_exec_blocks(eng, data, off, ln)
     assert _triples(got) == _triples(want)
+    corpus.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,kind", WIDE_SIZES)
+def test_device_wide_limex_equals_reference_random(hs, ref, n, kind):
+    for seed in range(3):
+        reach, init, succ, reports, eod, sqm, sk = _random_wide_nfa(1000 * n + seed, n)
+        eng = hs.limex_from_spec_wide(reach, init, init, succ, reports, eod, sqm, sk)
+        assert eng[8] == kind
+        data, off, ln = _random_corpus(300 + seed)
+        corpus = hs.Corpus.upload(data, off, ln)
+        got, ms = hs.nfa_scan_corpus(eng, corpus, cap=64)
+        assert _triples(got) == _triples(ref.nfa_exec_blocks(eng, data, off, ln))
+        corpus.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reps,kind", [(10, 2), (30, 3), (70, 5)])
+def test_device_wide_limex_literals(hs, ref, reps, kind):
+    lits = [b"needle" * reps, b"hay", b"stack" * 3, b"ne"]
+    eng = hs.limex32_from_literals(lits, [0, 1, 0, 0], [1, 2, 3, 4])
+    assert eng[8] == kind
+    data, off, ln, _ = synth.block_corpus(512, 1024, lits, plant_per_kb=2.0, seed=12)
+    corpus = hs.Corpus.upload(data, off, ln)
+    got, ms = hs.nfa_scan_corpus(eng, corpus)
+    want = ref.nfa_exec_blocks(eng, data, off, ln)
+    assert _triples(got) == _triples(want) and len(want) > 300
     corpus.free()
 
 

@@ -55,7 +55,7 @@ def test_outfix_database_limits(hs):
     with pytest.raises(hs.HsError):
         _compile(hs, "sheng", *SETS["mixed"])                      # more than 16 states
     with pytest.raises(hs.HsError):
-        _compile(hs, "limex32", [b"a" * 70], [0], [1])             # more than 64 positions
+        _compile(hs, "limex32", [b"a" * 520], [0], [1])            # more than 512 positions
     hs.set_build_option("outfix_engine", 3)
     try:
         with pytest.raises(hs.HsError):                            # block mode only
