@@ -1,8 +1,8 @@
 /*
- * regex_nfa.h -- small regular expressions to a LimEx NFA (32- or 64-state model): the position (Glushkov)
+ * regex_nfa.h -- regular expressions to a LimEx NFA (32- to 512-state model): the position (Glushkov)
  * automaton the reference builds for its NFA engines (src/nfagraph/ng_builder.cpp,
  * src/parser/buildstate.cpp: one state per character position, epsilon free), for
- * expression sets whose positions fit the 64-state model together with the start states.
+ * expression sets whose positions fit the 512-state model together with the start states.
  *
  * Syntax (PCRE as the reference's parser accepts it, src/parser/Parser.rl): literal
  * characters and escapes (\n \t \r \f \a \e \xHH \x{hh} \0oo \cX, escaped punctuation, \Q...\E),

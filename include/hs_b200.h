@@ -124,7 +124,7 @@ typedef int (*match_event_handler)(unsigned int id, unsigned long long from,
  * not such a set (unbounded repeats, ".", negated / POSIX classes, \d \w \s \h \v,
  * \b \B, "^" \A "$" \z \Z where the reference takes them, option groups (?ims-ims),
  * \Q..\E, ...) is compiled, in block
- * mode, to ONE LimEx NFA of the 32- or 64-state model inside a single-outfix database
+ * mode, to ONE LimEx NFA (32- to 512-state model) inside a single-outfix database
  * (ROSE_RUNTIME_SINGLE_OUTFIX) when its positions fit -- DESIGN.md section 10b.
  * Anything else (look-around, back-references, UTF-8 / UCP, larger sets, ...) yields
  * HS_COMPILER_ERROR with an explanatory hs_compile_error_t, exactly as the

@@ -65,7 +65,8 @@ def gen_seq(rng, depth):
         elif q < 0.40:
             a += b"+"
         elif q < 0.50:
-            lo = int(rng.integers(0, 3))
+            big = rng.random() < 0.06                      # now and then a repeat that needs the 128- ... 512-state models
+            lo = int(rng.integers(20, 90)) if big else int(rng.integers(0, 3))
             hi = lo + int(rng.integers(0, 3))
             a += [b"{%d}" % max(lo, 1), b"{%d,%d}" % (lo, max(hi, 1)), b"{%d,}" % lo][int(rng.integers(0, 3))]
         if q < 0.5 and rng.random() < 0.15:
@@ -164,6 +165,9 @@ def main():
         for trial in range(3):
             size = int(rng.integers(1, 28))
             a = np.frombuffer(ALPHA, dtype=np.uint8)
+            if re.search(rb"\{[2-9][0-9]", body) and trial:       # a long repeat: long data over few letters
+                size = int(rng.integers(60, 160))
+                a = np.frombuffer(ALPHA[:2] if trial == 1 else ALPHA[:4], dtype=np.uint8)
             data = a[rng.integers(0, a.size, size=size)].tobytes()
             arr = np.frombuffer(data, dtype=np.uint8)
             got = [int(r["to"]) for r in ref.scan_sorted(db.ptr, arr, np.array([0], np.uint64), np.array([size], np.uint32))]

@@ -91,7 +91,7 @@ def test_oracle_reproduces_hscollider_vectors(hs, case):
 
 
 # --- ... and for expressions that take the NFA route (regex_nfa.cpp -> LimEx-32 -> single-outfix database) --
-# tests/golden/hscollider_regex.json (tests/golden/gen_hscollider_regex.py): 878 patterns / 7 707 corpora of the
+# tests/golden/hscollider_regex.json (tests/golden/gen_hscollider_regex.py): 1 058 patterns / 9 293 corpora of the
 # same suite that are NOT a finite set of literals and fit the 32-state model.  The checker here is the unmodified
 # reference runtime scanning the database this compiler emits.
 with open(os.path.join(ROOT, "tests", "golden", "hscollider_regex.json")) as f:

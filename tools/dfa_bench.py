@@ -12,7 +12,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from hyperscan_b200 import capi, synth  # noqa: E402
 
 KINDS = {"mcclellan16_2000lits": (2, 2000, 4, 8), "mcclellan8_30lits": (1, 30, 2, 4), "sheng_4lits": (3, 4, 1, 3),
-         "limex32_6lits": (-1, 6, 4, 5)}
+         "limex32_6lits": (-1, 6, 4, 5), "limex128_12lits": (-1, 12, 6, 10), "limex256_20lits": (-1, 20, 8, 12),
+         "limex512_40lits": (-1, 40, 8, 12)}
 
 
 def main():
@@ -28,7 +29,7 @@ def main():
     for name, (kind, nl, lo, hi) in KINDS.items():
         alpha = b"abcdefghijklmnopqrstuvwxyz" if nl > 100 else (b"abcdefgh" if nl > 4 else b"abc")
         lits, flags, ids = synth.literal_set(nl, min_len=lo, max_len=hi, seed=nl, caseless_frac=0.0, alphabet=alpha)
-        if kind < 0:      # LimEx-32 position automaton (<= 31 literal bytes)
+        if kind < 0:      # LimEx position automaton: the model that holds the literals' bytes + 1 states
             eng = capi.limex32_from_literals(lits, None, ids)
         else:
             eng = capi.dfa_from_literals(lits, None, ids, kind=kind)
