@@ -488,8 +488,9 @@ def secondary_single_gpu(args, capi, torch, base, peak):
                                      "semantics)"}
         corpus.free()
 
-    # a regular-expression database: hs_compile -> position automaton -> LimEx-32 -> single-outfix database,
-    # scanned through the ordinary entry points
+    # a regular-expression database: hs_compile -> position automaton -> McClellan DFA when its determinisation
+    # stays small (here), else LimEx -> single-outfix database, scanned through the ordinary entry points
+    # 
     pats = [rb"ab+c", rb"[0-9]{2,}\.[0-9]", rb"^GET\s", rb"(foo|bar)x*z", rb"q.{2,4}w$"]
     db = capi.compile_multi(pats, [0, 0, 0, capi.HS_FLAG_CASELESS, 0], list(range(1, len(pats) + 1)))
     data = replant(base, ndfa, bl, [b"abbbc", b"123.4", b"GET /", b"fooxxz", b"q123w"], 0.05, 96)
@@ -510,11 +511,15 @@ def secondary_single_gpu(args, capi, torch, base, peak):
     exact = bool(np.array_equal(np.sort(got[got["block"] < vb], order=["block", "to", "id"]), want))
     kms = float(np.median(ms))
     ach = (ndfa * bl + 16 * int(got.size)) / (kms * 1e-3) / 1e9
-    sec["regex_5_expressions_limex32"] = {
-        "expressions": [p.decode() for p in pats], "blocks": ndfa, "block_len": bl, "kernel_ms": kms,
+    info = db.info()
+    engine = {0: "LimEx-32", 1: "LimEx-64", 2: "LimEx-128", 3: "LimEx-256", 5: "LimEx-512", 6: "McClellan-8",
+              7: "McClellan-16"}.get(int(info.engine_id), str(int(info.engine_id)))
+    sec["regex_5_expressions"] = {
+        "expressions": [p.decode() for p in pats], "engine": engine, "engine_states": int(info.num_literals),
+        "blocks": ndfa, "block_len": bl, "kernel_ms": kms,
         "roofline_gbs": ach, "roofline_frac": ach / peak, "matches": int(got.size), "verified_blocks": vb,
         "bit_exact_vs_reference_hs_scan": exact,
-        "api": "hs_compile_multi -> single-outfix database (LimEx-32) -> hs_b200_scan_corpus_* / fetch_matches"}
+        "api": "hs_compile_multi -> single-outfix database -> hs_b200_scan_corpus_* / fetch_matches"}
     corpus.free()
     sc.free()
     return sec

@@ -590,6 +590,11 @@ hs_error_t engineParams(const void *nfa, size_t nfa_len, DfaParams *out) {
             return HS_INVALID;
         }
         p.states = hdr.nPositions;
+        for (u32 i = 0; i < lx.exceptionCount; i++) {
+            /* hasSquash sits right after the two state-sized masks and the two u32 of every model's exception */
+            const u8 kind = *((const u8 *)nfa + sizeof(NFA) + lx.exceptionOffset + i * excSize + 2 * stateBytes + 8);
+            p.squashes |= kind == LIMEX_SQUASH_CYCLIC || kind == LIMEX_SQUASH_REPORT;
+        }
     } else {
         return HS_ARCH_ERROR; /* LimEx-384, McSheng, Gough, Castle, ...: not built */
     }

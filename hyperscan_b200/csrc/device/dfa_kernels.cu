@@ -24,6 +24,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "kernels.h"
 
@@ -182,6 +183,43 @@ template <int W> struct StOps<WideSt<W>> {
             }
         }
     }
+    /* the same with the word index as a compile-time constant: f(integral_constant<int, j>, bit) */
+    template <int J, class F> struct EachWord {
+        static __device__ __forceinline__ void run(const ST &on, F &f) {
+            u64 x = on.w[J];
+            while (x) {
+                f(std::integral_constant<int, J>(), 64u * J + lowestBit(x));
+                x &= x - 1;
+            }
+            EachWord<J + 1, F>::run(on, f);
+        }
+    };
+    template <class F> struct EachWord<W, F> {
+        static __device__ __forceinline__ void run(const ST &, F &) {}
+    };
+    template <class F> static __device__ __forceinline__ void forEachWord(const ST &on, F f) {
+        EachWord<0, F>::run(on, f);
+    }
+    /* shared-memory tables of state sets are kept chunk-major -- the k-th 16 bytes of every entry side by side --
+     * so that lanes reading DIFFERENT entries hit different banks (entry-major, a 64-byte set per entry would put
+     * every entry on the same two bank groups) */
+    static __device__ __forceinline__ ST loadChunks(const uint4 *tab, u32 entries, u32 index) {
+        ST r;
+#pragma unroll
+        for (int k = 0; k < W / 2; k++) {
+            const uint4 v = tab[k * entries + index];
+            r.w[2 * k] = (u64)v.x | ((u64)v.y << 32);
+            r.w[2 * k + 1] = (u64)v.z | ((u64)v.w << 32);
+        }
+        return r;
+    }
+    static __device__ __forceinline__ void storeChunks(uint4 *tab, u32 entries, u32 index, const ST &v) {
+#pragma unroll
+        for (int k = 0; k < W / 2; k++) {
+            tab[k * entries + index] = make_uint4((u32)v.w[2 * k], (u32)(v.w[2 * k] >> 32), (u32)v.w[2 * k + 1],
+                                                  (u32)(v.w[2 * k + 1] >> 32));
+        }
+    }
 };
 
 /* LimEx report list: ReportID[] terminated by MO_INVALID_IDX (limexRunReports, limex_runtime.h:90-103) */
@@ -334,6 +372,13 @@ template <int ENGINE> struct StagedThreads { static constexpr int N = ENGINE >= 
 /* shared-memory tables of a LimEx engine: the reach mask per byte value, then per state a row of four
  * ST: limited successors, exception successors, squash mask, report list offset */
 template <class ST> struct LimexTable { static constexpr u32 BYTES = 256u * sizeof(ST) + 8u * sizeof(ST) * 4u * sizeof(ST); };
+/* ... of the wide models: reach, exception successors and squash masks chunk-major (StOps::loadChunks), then per
+ * state its limited successors as ONE 64-bit word (they stay inside the state's own lane) and its report list */
+template <int W> struct LimexTable<WideSt<W>> {
+    static constexpr u32 STATES = 64u * W;
+    static constexpr u32 REACH = 0, LOCAL = 256u * 8u * W, KEEP = LOCAL + STATES * 8u * W, LIM = KEEP + STATES * 8u * W,
+                         REP = LIM + STATES * 8u, BYTES = REP + STATES * 4u;
+};
 
 enum { SHENG_ROW = 128, SHENG_TABLE_BYTES = 256 * SHENG_ROW };
 
@@ -368,6 +413,7 @@ __global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(c
     typedef typename LimexLayout<ST>::Exc LxExc;
     typedef StOps<ST> Ops;
     constexpr bool LIMEX = ENGINE >= ENG_LIMEX32;
+    constexpr bool WIDE = ENGINE >= ENG_LIMEX128; /* state sets of several 64-bit words */
     ST lxAccept = Ops::zero(), lxAcceptEod = Ops::zero(), lxStart = Ops::zero();
     if (LIMEX) {
         /* eng = struct LimExNFA32 ... 512; a top at offset 0 switches `init` on (moNfaTop) */
@@ -403,22 +449,18 @@ __global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(c
     }
     u32 tabArea;
     if (LIMEX) {
-        /* reach mask by byte value (reach[reachMap[b]]), then ONE row of four ST per state i:
+        /* (32- and 64-state models) reach mask by byte value (reach[reachMap[b]]), then ONE row of four ST per state i:
          *   [0] its limited successors: OR over the shifts k with bit i of shift[k] of 1 << (i + shiftAmount[k])
          *   [1] its exception's successors, [2] its squash mask (all ones unless the exception squashes:
          *   LIMEX_SQUASH_CYCLIC / _REPORT), [3] its exception's report list
          * so a byte costs work in proportion to the states that are ON, not eight shift-and-mask rounds */
-        ST *d = reinterpret_cast<ST *>(smem);
         const u8 *reach = eng + sizeof(LxNfa);
-        for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
-            d[i] = Ops::load(reach + sizeof(ST) * __ldg(eng + offsetof(LxNfa, reachMap) + i));
-        }
         const ST excMask = Ops::load(eng + offsetof(LxNfa, exceptionMask));
         const u32 nshift = g32(eng + offsetof(LxNfa, shiftCount));
         const u8 *exc = eng + g32(eng + offsetof(LxNfa, exceptionOffset));
-        ST *rows = d + 256;
-        for (u32 i = threadIdx.x; i < 8 * sizeof(ST); i += blockDim.x) {
-            ST lim = Ops::zero(), local = Ops::zero(), keep = Ops::ones(), rep = Ops::fromU32(MO_INVALID_IDX);
+        /* row of state i: limited successors, exception successors, squash mask, report list */
+        auto rowOf = [&](const u32 i, ST &lim, ST &local, ST &keep, u32 &rep) {
+            lim = Ops::zero(), local = Ops::zero(), keep = Ops::ones(), rep = MO_INVALID_IDX;
             for (u32 q = 0; q < nshift && q < 8; q++) {
                 if (Ops::test(Ops::load(eng + offsetof(LxNfa, shift) + sizeof(ST) * q), i)) {
                     lim = Ops::bor(lim, Ops::shiftedBit(i, __ldg(eng + offsetof(LxNfa, shiftAmount) + q)));
@@ -428,15 +470,47 @@ __global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(c
                 const u8 *x = exc + Ops::rank(excMask, i) * (u32)sizeof(LxExc);
                 const u32 kind = __ldg(x + offsetof(LxExc, hasSquash));
                 local = Ops::load(x + offsetof(LxExc, successors));
-                rep = Ops::fromU32(g32(x + offsetof(LxExc, reports)));
+                rep = g32(x + offsetof(LxExc, reports));
                 if (kind == LIMEX_SQUASH_CYCLIC || kind == LIMEX_SQUASH_REPORT) {
                     keep = Ops::load(x + offsetof(LxExc, squash));
                 }
             }
-            rows[4 * i + 0] = lim;
-            rows[4 * i + 1] = local;
-            rows[4 * i + 2] = keep;
-            rows[4 * i + 3] = rep;
+        };
+        if constexpr (WIDE) {
+            typedef LimexTable<ST> T;
+            for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
+                Ops::storeChunks(reinterpret_cast<uint4 *>(smem + T::REACH), 256, i,
+                                 Ops::load(reach + sizeof(ST) * __ldg(eng + offsetof(LxNfa, reachMap) + i)));
+            }
+            for (u32 i = threadIdx.x; i < T::STATES; i += blockDim.x) {
+                ST lim, local, keep;
+                u32 rep;
+                rowOf(i, lim, local, keep, rep);
+                Ops::storeChunks(reinterpret_cast<uint4 *>(smem + T::LOCAL), T::STATES, i, local);
+                Ops::storeChunks(reinterpret_cast<uint4 *>(smem + T::KEEP), T::STATES, i, keep);
+                u64 own = 0; /* the limited successors sit in the state's own 64-bit lane */
+#pragma unroll
+                for (u32 j = 0; j < sizeof(ST) / 8; j++) {
+                    own = (i >> 6) == j ? lim.w[j] : own;
+                }
+                reinterpret_cast<u64 *>(smem + T::LIM)[i] = own;
+                reinterpret_cast<u32 *>(smem + T::REP)[i] = rep;
+            }
+        } else {
+            ST *d = reinterpret_cast<ST *>(smem);
+            for (u32 i = threadIdx.x; i < 256; i += blockDim.x) {
+                d[i] = Ops::load(reach + sizeof(ST) * __ldg(eng + offsetof(LxNfa, reachMap) + i));
+            }
+            ST *rows = d + 256;
+            for (u32 i = threadIdx.x; i < 8 * sizeof(ST); i += blockDim.x) {
+                ST lim, local, keep;
+                u32 rep;
+                rowOf(i, lim, local, keep, rep);
+                rows[4 * i + 0] = lim;
+                rows[4 * i + 1] = local;
+                rows[4 * i + 2] = keep;
+                rows[4 * i + 3] = Ops::fromU32(rep);
+            }
         }
         tabArea = LimexTable<ST>::BYTES;
     } else if (ENGINE == ENG_SHENG) {
@@ -477,7 +551,7 @@ __global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(c
     const ST *lxRows = lxReach + 256;
     ST lxLim0 = Ops::zero(), lxLocal0 = Ops::zero(), lxKeep0 = Ops::ones();
     bool lxRow0Plain = false; /* state 0 raises no reports: its row can be applied without the loop */
-    if (LIMEX && sizeof(ST) <= 8) { /* (the wide models read it from shared memory like every other row) */
+    if (LIMEX && !WIDE) { /* (the wide models read it from shared memory like every other row) */
         lxLim0 = lxRows[0];
         lxLocal0 = lxRows[1];
         lxKeep0 = lxRows[2];
@@ -489,7 +563,28 @@ __global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(c
      * that are on BEFORE the byte run their exceptions -- reports at offset pos, except at the
      * first byte of the scan (NO_OUTPUT | FIRST_BYTE) -- then succ & reach[byte]. */
     auto step = [&](const u32 w, const u32 j, ST &s, const u32 pos, const u32 blk) -> bool {
-        if constexpr (LIMEX) {
+        if constexpr (WIDE) {
+            /* the same walk over the ON states as below, on the chunk-major tables; the squash masks are read only
+             * if the engine has a squashing exception at all */
+            typedef LimexTable<ST> T;
+            const uint4 *tLocal = reinterpret_cast<const uint4 *>(smem + T::LOCAL);
+            const uint4 *tKeep = reinterpret_cast<const uint4 *>(smem + T::KEEP);
+            ST lim = Ops::zero(), local = Ops::zero(), keep = Ops::ones();
+            Ops::forEachWord(s, [&](auto word, const u32 bit) {
+                const u32 rep = reinterpret_cast<const u32 *>(smem + T::REP)[bit];
+                if (rep != MO_INVALID_IDX && pos != 0) {
+                    cursor = emitLimexReports(p, cursor, rep, blk, pos);
+                }
+                lim.w[decltype(word)::value] |= reinterpret_cast<const u64 *>(smem + T::LIM)[bit];
+                local = Ops::bor(local, Ops::loadChunks(tLocal, T::STATES, bit));
+                if (p.squashes) {
+                    keep = Ops::band(keep, Ops::loadChunks(tKeep, T::STATES, bit));
+                }
+            });
+            s = Ops::band(Ops::bor(Ops::band(lim, keep), local),
+                          Ops::loadChunks(reinterpret_cast<const uint4 *>(smem + T::REACH), 256, __byte_perm(w, 0, 0x4440 + j)));
+            return false;
+        } else if constexpr (LIMEX) {
             /* NFA_EXEC_GET_LIM_SUCC + processExceptional (limex_exceptional.h:190-330, cache
              * aside) over the states that are on, in ascending order: every exception's squash
              * cuts the limited successors only, the exception successors are OR-ed in afterwards */

@@ -193,6 +193,7 @@ struct DfaParams {
     u32 tableBytes;  /* McClellan: bytes of the successor table (staged in shared memory if it fits) */
     u32 ilp;         /* blocks walked by one lane at a time: 1 or 2 (runtime option dfa_ilp) */
     u32 states;      /* McClellan-8: state_count (<= 256): rows of the byte-indexed table built in shared memory */
+    u32 squashes;    /* LimEx: some exception squashes (LIMEX_SQUASH_CYCLIC / _REPORT): the kernel reads the squash masks */
     DevMatch *out;   /* {report, block, offset after the last byte} */
     u32 outCap;
     u32 *counters;   /* CTR_MATCHES */

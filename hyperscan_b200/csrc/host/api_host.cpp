@@ -420,6 +420,11 @@ hs_error_t hs_b200_db_info(const hs_database_t *db, hs_b200_db_info_t *out) {
                 out->fdr_stride = f->stride;
             }
         }
+    } else if (r->runtimeImpl == RUNTIME_SINGLE_OUTFIX && r->nfaInfoOffset) {
+        const NfaInfo *ni = (const NfaInfo *)((const u8 *)r + r->nfaInfoOffset);
+        const NFA *n = (const NFA *)((const u8 *)r + ni->nfaOffset);
+        out->engine_id = n->type;        /* enum NFAEngineType: LimEx 0..5, McClellan 6 / 7, Sheng 17 */
+        out->num_literals = n->nPositions; /* states of the engine */
     }
     return HS_SUCCESS;
 }
@@ -912,6 +917,7 @@ static hs_error_t compileCommon(const char *const *expressions,
         }
         applyBuildOptions(&opts.hwlm);
         opts.outfixKind = outfixEngineOption();
+        opts.regexDfa = regexDfaOption() != 0;
         if (opts.hwlm.allowFatTeddy) {
             opts.platform &= ~PLATFORM_NOAVX2; /* 16-bucket Teddy needs AVX2 on CPUs */
         }
@@ -1080,12 +1086,15 @@ hs_error_t hs_expression_ext_info(const char *expression, unsigned int flags,
  * "allow_fat_teddy", "allow_flood", "allow_noodle"; "outfix_engine" (0 = literal
  * matchers as usual; 1 DFA chosen by size, 2 McClellan-8, 3 McClellan-16, 4 Sheng,
  * 5 LimEx-32: block-mode literal sets are compiled to a database whose only matcher is
- * that engine run as an outfix, ROSE_RUNTIME_SINGLE_OUTFIX). */
+ * that engine run as an outfix, ROSE_RUNTIME_SINGLE_OUTFIX); "regex_dfa" (1: regular expressions whose
+ * determinised automaton stays small run as a McClellan DFA, 0: always as a LimEx NFA). */
 namespace hsb {
 static HwlmBuildOpts g_tunables;
 static bool g_tun_set[8];
 static int g_outfixEngine = 0; /* "outfix_engine": see enum OutfixKind (rose_build.h) */
+static int g_regexDfa = 1;     /* "regex_dfa": 0 = expressions always become a LimEx NFA */
 int outfixEngineOption() { return g_outfixEngine; }
+int regexDfaOption() { return g_regexDfa; }
 void applyBuildOptions(HwlmBuildOpts *o) {
     if (g_tun_set[0]) o->forceEngine = g_tunables.forceEngine;
     if (g_tun_set[1]) o->forceDomain = g_tunables.forceDomain;
@@ -1107,6 +1116,11 @@ extern "C" hs_error_t hs_b200_set_build_option(const char *key, int value) {
         memset(g_tun_set, 0, sizeof(g_tun_set));
         g_tunables = HwlmBuildOpts();
         hsb::g_outfixEngine = 0;
+        hsb::g_regexDfa = 1;
+        return HS_SUCCESS;
+    }
+    if (k == "regex_dfa") {
+        hsb::g_regexDfa = value != 0;
         return HS_SUCCESS;
     }
     if (k == "outfix_engine") {

@@ -22,6 +22,7 @@ static inline const RoseEngine *dbRose(const hs_database_t *db) {
  * (the analogue of the reference's Grey overrides, src/grey.cpp:40-160). */
 void applyBuildOptions(HwlmBuildOpts *o);
 int outfixEngineOption(); /* build option "outfix_engine" (api_host.cpp) */
+int regexDfaOption();     /* build option "regex_dfa" (api_host.cpp) */
 
 } // namespace hsb
 #endif

@@ -51,6 +51,107 @@ RawNfa nfaFromLiterals(const std::vector<DfaLiteral> &lits) {
 
 namespace {
 
+struct SetLess {
+    bool operator()(const StateSet &a, const StateSet &b) const {
+        for (u32 j = MAX_NFA_STATES / 64; j-- > 0;) {
+            const u64 x = stateWord(a, j), y = stateWord(b, j);
+            if (x != y) {
+                return x < y;
+            }
+        }
+        return false;
+    }
+};
+
+} // namespace
+
+bool determinize(const RawNfa &n, size_t maxStates, RawDfa *out) {
+    for (u8 k : n.squashKind) {
+        if (k != LIMEX_SQUASH_NONE) {
+            return false;
+        }
+    }
+    StateSet all;
+    for (u32 i = 0; i < n.nstates; i++) {
+        all.set(i);
+    }
+    /* bytes with the same reach mask behave alike */
+    std::vector<StateSet> classes;
+    u8 classOf[256];
+    {
+        std::map<StateSet, u32, SetLess> seen;
+        for (u32 b = 0; b < 256; b++) {
+            const StateSet m = n.reach[b] & all;
+            auto it = seen.find(m);
+            if (it == seen.end()) {
+                it = seen.emplace(m, (u32)classes.size()).first;
+                classes.push_back(m);
+            }
+            classOf[b] = (u8)it->second;
+        }
+    }
+    RawDfa d;
+    std::map<StateSet, u16, SetLess> ids;
+    std::vector<StateSet> sets;
+    auto add = [&](const StateSet &s) -> int {
+        auto it = ids.find(s);
+        if (it != ids.end()) {
+            return it->second;
+        }
+        if (sets.size() >= maxStates || sets.size() >= 0xfffe) {
+            return -1;
+        }
+        const u16 id = (u16)sets.size();
+        ids.emplace(s, id);
+        sets.push_back(s);
+        d.next.emplace_back();
+        d.next.back().fill(0);
+        std::vector<u32> r, e;
+        for (u32 q = 0; q < n.nstates; q++) {
+            if (s.test(q)) {
+                r.insert(r.end(), n.reports[q].begin(), n.reports[q].end());
+                e.insert(e.end(), n.reportsEod[q].begin(), n.reportsEod[q].end());
+            }
+        }
+        for (std::vector<u32> *v : {&r, &e}) {
+            std::sort(v->begin(), v->end());
+            v->erase(std::unique(v->begin(), v->end()), v->end());
+        }
+        d.reports.push_back(r);
+        d.reportsEod.push_back(e);
+        return id;
+    };
+    add(StateSet()); /* state 0: the dead state */
+    const int start = add(n.init & all);
+    if (start <= 0) {
+        return false;
+    }
+    d.startAnchored = d.startFloating = (u16)start;
+    for (size_t cur = 1; cur < sets.size(); cur++) {
+        StateSet succ;
+        const StateSet s = sets[cur];
+        for (u32 q = 0; q < n.nstates; q++) {
+            if (s.test(q)) {
+                succ |= n.succ[q];
+            }
+        }
+        std::vector<int> to(classes.size());
+        for (size_t c = 0; c < classes.size(); c++) {
+            to[c] = add(succ & classes[c]);
+            if (to[c] < 0) {
+                return false;
+            }
+        }
+        for (u32 b = 0; b < 256; b++) {
+            d.next[cur][b] = (u16)to[classOf[b]];
+        }
+    }
+    *out = d;
+    return true;
+}
+
+namespace {
+
 template <class T> void put(std::vector<u8> &b, size_t off, const T &v) {
     if (b.size() < off + sizeof(T)) {
         b.resize(off + sizeof(T), 0);
@@ -81,18 +182,6 @@ template <class T> T fromSet(const StateSet &s) {
     }
     return t;
 }
-
-struct SetLess {
-    bool operator()(const StateSet &a, const StateSet &b) const {
-        for (u32 j = MAX_NFA_STATES / 64; j-- > 0;) {
-            const u64 x = stateWord(a, j), y = stateWord(b, j);
-            if (x != y) {
-                return x < y;
-            }
-        }
-        return false;
-    }
-};
 
 template <class LX, class EX, class T> std::vector<u8> emitLimExT(const RawNfa &n, u8 nfaType) {
     const u32 WIDTH = (u32)sizeof(T) * 8;

@@ -59,6 +59,14 @@ typedef RawNfa RawNfa32; /* the name the 32-state-only version had */
  * per literal byte; throws if more than 511 positions are needed */
 RawNfa nfaFromLiterals(const std::vector<DfaLiteral> &lits);
 
+/* Subset construction: the DFA of an NFA without squashes (what regex_nfa.cpp builds), for the McClellan
+ * emitters -- the reference also turns small NFA graphs into DFAs before it settles for LimEx
+ * (src/nfagraph/ng_mcclellan.cpp, determinise with a state limit).  A DFA state's reports are those of its NFA
+ * states: raised when the set is entered, i.e. at the offset after the byte, which is where the LimEx run raises
+ * them (the exceptions of the next byte, or the accepts after the last one); EOD reports likewise.  Returns false
+ * if more than maxStates subsets (the dead state included) are needed or the NFA has squashing exceptions. */
+bool determinize(const RawNfa &n, size_t maxStates, RawDfa *out);
+
 /* struct NFA + LimExNFA32 / 64 / 128 / 256 / 512 (the smallest that holds nstates) + tables */
 std::vector<u8> emitLimEx(const RawNfa &n);
 inline std::vector<u8> emitLimEx32(const RawNfa &n) { return emitLimEx(n); }

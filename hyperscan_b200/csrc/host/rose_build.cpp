@@ -760,7 +760,14 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
     t.canExhaust = allHighlander;
     std::vector<u8> eng;
     try {
-        eng = emitLimEx(nfa);
+        /* small automata run as DFAs, as in the reference (ng_mcclellan before LimEx); the report programs are
+         * the same either way */
+        RawDfa dfa;
+        if (opts.regexDfa && determinize(nfa, 1024, &dfa)) {
+            eng = emitDfa(dfa, dfa.size() <= 256 ? DFA_MCCLELLAN8 : DFA_MCCLELLAN16, true);
+        } else {
+            eng = emitLimEx(nfa);
+        }
     } catch (const std::runtime_error &e) {
         throw CompileError{std::string("Unable to build the NFA: ") + e.what(), -1};
     }

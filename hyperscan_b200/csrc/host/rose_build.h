@@ -37,6 +37,8 @@ struct CompileOpts {
                                   * shorter than 70 bytes when the literal set's automaton stays small */
     int outfixKind = 0;          /* != 0: no literal matcher, ONE engine over the whole literals run as an
                                   * outfix (ROSE_RUNTIME_SINGLE_OUTFIX): see enum OutfixKind */
+    bool regexDfa = true;        /* regex route: determinise the position automaton when the DFA stays small
+                                  * (McClellan-8 up to 256 states, McClellan-16 up to 1024), else LimEx */
     u64 platform = PLATFORM_NOAVX2 | PLATFORM_NOAVX512 | PLATFORM_NOAVX512VBMI;
     HwlmBuildOpts hwlm;
 };

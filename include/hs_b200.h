@@ -396,7 +396,8 @@ hs_error_t hs_b200_streams_close(hs_b200_stream_set_t *set);
 typedef struct hs_b200_db_info {
     unsigned int runtime_impl;   /* RoseEngine.runtimeImpl */
     unsigned int hwlm_type;      /* 16 noodle, 12 FDR/Teddy, 0 none */
-    unsigned int engine_id;      /* FDR: 0; Teddy: 3..18 */
+    unsigned int engine_id;      /* FDR: 0; Teddy: 3..18; single-outfix databases: the engine's NFAEngineType
+                                  * (LimEx 0..5, McClellan-8 / -16 6 / 7, Sheng 17), its state count in num_literals */
     unsigned int fdr_domain;
     unsigned int fdr_stride;
     unsigned int num_literals;   /* HWLM literal fragments */

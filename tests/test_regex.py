@@ -56,11 +56,18 @@ def _ref_ends(ref, db, data):
     return [(int(x["id"]), int(x["to"])) for x in r]
 
 
+@pytest.mark.parametrize("dfa", [1, 0])
 @pytest.mark.parametrize("pi", range(len(PATTERNS)))
-def test_reference_hs_scan_on_compiled_expressions_equals_definition(hs, ref, pi):
+def test_reference_hs_scan_on_compiled_expressions_equals_definition(hs, ref, pi, dfa):
     pat, fl = PATTERNS[pi]
-    db = hs.compile_multi([pat], [fl], [7])
+    hs.set_build_option("regex_dfa", dfa)            # the engine of the outfix: McClellan if small (default), or LimEx
+    try:
+        db = hs.compile_multi([pat], [fl], [7])
+    finally:
+        hs.set_build_option("regex_dfa", 1)
     assert db.info().runtime_impl == (1 if pat == rb"[a-c]{3}" else 2)   # single outfix, unless the language is finite
+    if db.info().runtime_impl == 2:
+        assert db.info().engine_id in ((6, 7) if dfa else (0, 1, 2, 3, 5))
     hits = 0
     for seed in range(10):
         data = (SEED_TEXT if seed == 0 else b"") + _data(100 * pi + seed) + TAILS[seed % len(TAILS)]

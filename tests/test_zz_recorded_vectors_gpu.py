@@ -11,7 +11,7 @@ import pytest
 from test_golden import COLLIDER, COLLIDER_REGEX, _check_collider, _collider_blocks
 
 
-ALL_CASES = COLLIDER + COLLIDER_REGEX   # literal route, then the NFA route (LimEx-32 single-outfix databases)
+ALL_CASES = COLLIDER + COLLIDER_REGEX   # literal route, then the regex route (single-outfix databases: McClellan / LimEx)
 
 
 @pytest.mark.gpu
@@ -30,3 +30,18 @@ def test_cuda_path_reproduces_hscollider_vectors(hs, case):
             assert (len(tos) == 1 and tos[0] in want) if want else not tos
         else:
             assert tos == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", COLLIDER_REGEX[1::3], ids=[str(c["id"]) for c in COLLIDER_REGEX[1::3]])
+def test_cuda_path_reproduces_hscollider_vectors_limex_forced(hs, case):
+    hs.set_build_option("regex_dfa", 0)
+    try:
+        db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+    finally:
+        hs.set_build_option("regex_dfa", 1)
+    assert db.info().engine_id <= 5
+    data, off, ln, ends = _collider_blocks(case)
+    scratch = hs.Scratch(db)
+    got = np.sort(hs.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
+    _check_collider(case, got, ends)
