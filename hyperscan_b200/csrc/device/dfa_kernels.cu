@@ -372,12 +372,12 @@ template <int ENGINE> struct StagedThreads { static constexpr int N = ENGINE >= 
 /* shared-memory tables of a LimEx engine: the reach mask per byte value, then per state a row of four
  * ST: limited successors, exception successors, squash mask, report list offset */
 template <class ST> struct LimexTable { static constexpr u32 BYTES = 256u * sizeof(ST) + 8u * sizeof(ST) * 4u * sizeof(ST); };
-/* ... of the wide models: reach, exception successors and squash masks chunk-major (StOps::loadChunks), then per
- * state its limited successors as ONE 64-bit word (they stay inside the state's own lane) and its report list */
+/* ... of the wide models: reach, exception successors and squash masks chunk-major (StOps::loadChunks), the
+ * report list of every state's exception, then the (up to eight) shift masks and the exception mask as they are */
 template <int W> struct LimexTable<WideSt<W>> {
     static constexpr u32 STATES = 64u * W;
-    static constexpr u32 REACH = 0, LOCAL = 256u * 8u * W, KEEP = LOCAL + STATES * 8u * W, LIM = KEEP + STATES * 8u * W,
-                         REP = LIM + STATES * 8u, BYTES = REP + STATES * 4u;
+    static constexpr u32 REACH = 0, LOCAL = 256u * 8u * W, KEEP = LOCAL + STATES * 8u * W, REP = KEEP + STATES * 8u * W,
+                         SHIFT = REP + STATES * 4u, EXC = SHIFT + 8u * 8u * W, BYTES = EXC + 8u * W;
 };
 
 enum { SHENG_ROW = 128, SHENG_TABLE_BYTES = 256 * SHENG_ROW };
@@ -488,13 +488,11 @@ __global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(c
                 rowOf(i, lim, local, keep, rep);
                 Ops::storeChunks(reinterpret_cast<uint4 *>(smem + T::LOCAL), T::STATES, i, local);
                 Ops::storeChunks(reinterpret_cast<uint4 *>(smem + T::KEEP), T::STATES, i, keep);
-                u64 own = 0; /* the limited successors sit in the state's own 64-bit lane */
-#pragma unroll
-                for (u32 j = 0; j < sizeof(ST) / 8; j++) {
-                    own = (i >> 6) == j ? lim.w[j] : own;
-                }
-                reinterpret_cast<u64 *>(smem + T::LIM)[i] = own;
                 reinterpret_cast<u32 *>(smem + T::REP)[i] = rep;
+            }
+            for (u32 i = threadIdx.x; i < 9; i += blockDim.x) { /* shift masks 0..7, then the exception mask */
+                reinterpret_cast<ST *>(smem + T::SHIFT)[i] =
+                    i < 8 ? (i < nshift ? Ops::load(eng + offsetof(LxNfa, shift) + sizeof(ST) * i) : Ops::zero()) : excMask;
             }
         } else {
             ST *d = reinterpret_cast<ST *>(smem);
@@ -557,6 +555,12 @@ __global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(c
         lxKeep0 = lxRows[2];
         lxRow0Plain = Ops::low32(lxRows[3]) == MO_INVALID_IDX;
     }
+    u32 lxShiftCount = 0;
+    u64 lxShiftAmounts = 0; /* shiftAmount[0..7], one byte each */
+    if (WIDE) {
+        lxShiftCount = min(g32(eng + offsetof(LxNfa, shiftCount)), 8u);
+        lxShiftAmounts = (u64)g32(eng + offsetof(LxNfa, shiftAmount)) | ((u64)g32(eng + offsetof(LxNfa, shiftAmount) + 4) << 32);
+    }
     u32 cursor = 0; /* this lane's next record slot (emitDfaMatch) */
     /* one input byte: byte j of data word w, at block offset pos.  DFAs: returns true when the
      * state entered accepts.  LimEx (LOOP_NOACCEL_FN, limex_runtime_impl.h:209-243): the states
@@ -564,21 +568,28 @@ __global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(c
      * first byte of the scan (NO_OUTPUT | FIRST_BYTE) -- then succ & reach[byte]. */
     auto step = [&](const u32 w, const u32 j, ST &s, const u32 pos, const u32 blk) -> bool {
         if constexpr (WIDE) {
-            /* the same walk over the ON states as below, on the chunk-major tables; the squash masks are read only
-             * if the engine has a squashing exception at all */
+            /* the reference's own order of work (NFA_EXEC_GET_LIM_SUCC, then processExceptional over the
+             * exceptional states only): with many states on, shifting whole 64-bit lanes costs less than a visit
+             * per state; the squash masks are read only if the engine has a squashing exception at all */
             typedef LimexTable<ST> T;
-            const uint4 *tLocal = reinterpret_cast<const uint4 *>(smem + T::LOCAL);
-            const uint4 *tKeep = reinterpret_cast<const uint4 *>(smem + T::KEEP);
+            const ST *tShift = reinterpret_cast<const ST *>(smem + T::SHIFT);
             ST lim = Ops::zero(), local = Ops::zero(), keep = Ops::ones();
-            Ops::forEachWord(s, [&](auto word, const u32 bit) {
+            for (u32 q = 0; q < lxShiftCount; q++) {
+                const ST m = tShift[q];
+                const u32 a = (u32)(lxShiftAmounts >> (8 * q)) & 0xff;
+#pragma unroll
+                for (u32 x = 0; x < sizeof(ST) / 8; x++) {
+                    lim.w[x] |= (s.w[x] & m.w[x]) << a; /* LSHIFT_STATE: lane by lane */
+                }
+            }
+            Ops::forEach(Ops::band(s, tShift[8]), [&](const u32 bit) {
                 const u32 rep = reinterpret_cast<const u32 *>(smem + T::REP)[bit];
                 if (rep != MO_INVALID_IDX && pos != 0) {
                     cursor = emitLimexReports(p, cursor, rep, blk, pos);
                 }
-                lim.w[decltype(word)::value] |= reinterpret_cast<const u64 *>(smem + T::LIM)[bit];
-                local = Ops::bor(local, Ops::loadChunks(tLocal, T::STATES, bit));
+                local = Ops::bor(local, Ops::loadChunks(reinterpret_cast<const uint4 *>(smem + T::LOCAL), T::STATES, bit));
                 if (p.squashes) {
-                    keep = Ops::band(keep, Ops::loadChunks(tKeep, T::STATES, bit));
+                    keep = Ops::band(keep, Ops::loadChunks(reinterpret_cast<const uint4 *>(smem + T::KEEP), T::STATES, bit));
                 }
             });
             s = Ops::band(Ops::bor(Ops::band(lim, keep), local),

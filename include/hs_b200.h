@@ -124,7 +124,8 @@ typedef int (*match_event_handler)(unsigned int id, unsigned long long from,
  * not such a set (unbounded repeats, ".", negated / POSIX classes, \d \w \s \h \v,
  * \b \B, "^" \A "$" \z \Z where the reference takes them, option groups (?ims-ims),
  * \Q..\E, ...) is compiled, in block
- * mode, to ONE LimEx NFA (32- to 512-state model) inside a single-outfix database
+ * mode, to ONE engine -- a McClellan DFA when the determinised automaton is small, else a LimEx NFA (32- to
+ * 512-state model) -- inside a single-outfix database
  * (ROSE_RUNTIME_SINGLE_OUTFIX) when its positions fit -- DESIGN.md section 10b.
  * Anything else (look-around, back-references, UTF-8 / UCP, larger sets, ...) yields
  * HS_COMPILER_ERROR with an explanatory hs_compile_error_t, exactly as the
@@ -414,8 +415,10 @@ hs_error_t hs_b200_db_info(const hs_database_t *db, hs_b200_db_info_t *info);
  * (0: literal matchers as usual; 1 DFA chosen by size, 2 McClellan-8, 3 McClellan-16,
  * 4 Sheng, 5 LimEx-32: hs_compile_lit* in block mode emit a database whose only matcher
  * is that engine over the whole literals, run as an outfix -- ROSE_RUNTIME_SINGLE_OUTFIX,
- * src/runtime.c:245-280; the reference's hs_scan and this one both scan it); key "reset"
- * restores the defaults. */
+ * src/runtime.c:245-280; the reference's hs_scan and this one both scan it); "regex_dfa"
+ * (1, the default: a regular-expression set whose determinised automaton has at most 1 024
+ * states runs as a McClellan DFA; 0: always as a LimEx NFA); key "reset" restores the
+ * defaults. */
 hs_error_t hs_b200_set_build_option(const char *key, int value);
 
 /* Acceleration primitives (src/nfa/accel.h:46-121; shuftiExec src/nfa/shufti.c:150,
