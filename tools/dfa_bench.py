@@ -22,11 +22,14 @@ def main():
     ap.add_argument("--block-len", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--ilp", type=int, default=1, help="blocks per lane (runtime option dfa_ilp)")
+    ap.add_argument("--only", default="", help="run the engines whose name contains this")
     args = ap.parse_args()
     bl = args.block_len
     nb = (args.mb << 20) // bl
     capi.set_runtime_option("dfa_ilp", args.ilp)
     for name, (kind, nl, lo, hi) in KINDS.items():
+        if args.only not in name:
+            continue
         alpha = b"abcdefghijklmnopqrstuvwxyz" if nl > 100 else (b"abcdefgh" if nl > 4 else b"abc")
         lits, flags, ids = synth.literal_set(nl, min_len=lo, max_len=hi, seed=nl, caseless_frac=0.0, alphabet=alpha)
         if kind < 0:      # LimEx position automaton: the model that holds the literals' bytes + 1 states
