@@ -749,29 +749,42 @@ __global__ void __launch_bounds__(StagedThreads<ENGINE>::N, 1) dfaStagedKernel(c
             for (int u = 0; u < ILP; u++) {
                 const u8 *row = myRow + u * 32 * Tile::ROW;
                 u32 cc = c;
+                if constexpr (WIDE) {
+                    /* a step of the wide models is hundreds of instructions: the sixteen unrolled copies of it
+                     * (and a second set for the last piece) do not fit the instruction cache -- ncu's first stall
+                     * reason was "no instruction" -- so their bytes go through ONE copy of the step */
+                    if (live[u]) {
 #pragma unroll 1
-                for (; live[u] && cc * 16 + 16 <= n[u]; cc++) { /* full pieces: no per-byte checks */
-                    const uint4 x = *reinterpret_cast<const uint4 *>(row + cc * 16);
-                    const u32 w[4] = {x.x, x.y, x.z, x.w};
+                        for (u32 j = cc * 16; j < n[u]; j++) {
+                            (void)step(row[j], 0, s[u], done + j, b[u]);
+                        }
+                        live[u] = !dead(s[u]);
+                    }
+                } else {
+#pragma unroll 1
+                    for (; live[u] && cc * 16 + 16 <= n[u]; cc++) { /* full pieces: no per-byte checks */
+                        const uint4 x = *reinterpret_cast<const uint4 *>(row + cc * 16);
+                        const u32 w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-                    for (u32 j = 0; j < 16; j++) {
-                        if (step(w[j >> 2], j & 3, s[u], done + cc * 16 + j, b[u])) {
-                            cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + cc * 16 + j + 1);
+                        for (u32 j = 0; j < 16; j++) {
+                            if (step(w[j >> 2], j & 3, s[u], done + cc * 16 + j, b[u])) {
+                                cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + cc * 16 + j + 1);
+                            }
                         }
+                        live[u] = !dead(s[u]);
                     }
-                    live[u] = !dead(s[u]);
-                }
-                if (live[u] && cc * 16 < n[u]) { /* the block's last, partial piece */
-                    const uint4 x = *reinterpret_cast<const uint4 *>(row + cc * 16);
-                    const u32 w[4] = {x.x, x.y, x.z, x.w};
-                    const u32 m = n[u] - cc * 16;
+                    if (live[u] && cc * 16 < n[u]) { /* the block's last, partial piece */
+                        const uint4 x = *reinterpret_cast<const uint4 *>(row + cc * 16);
+                        const u32 w[4] = {x.x, x.y, x.z, x.w};
+                        const u32 m = n[u] - cc * 16;
 #pragma unroll 1
-                    for (u32 j = 0; j < m; j++) {
-                        if (step(w[j >> 2] >> (8 * (j & 3)), 0, s[u], done + cc * 16 + j, b[u])) {
-                            cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + cc * 16 + j + 1);
+                        for (u32 j = 0; j < m; j++) {
+                            if (step(w[j >> 2] >> (8 * (j & 3)), 0, s[u], done + cc * 16 + j, b[u])) {
+                                cursor = emitAccept(p, cursor, k.single, acceptWhat(s[u]), b[u], (u64)done + cc * 16 + j + 1);
+                            }
                         }
+                        live[u] = !dead(s[u]);
                     }
-                    live[u] = !dead(s[u]);
                 }
             }
             __syncwarp();
@@ -811,7 +824,7 @@ cudaError_t launchStaged(const DfaParams &p, int smCount, size_t tableBytes, cud
      * ilp 2: two blocks per lane, 64 bytes of each per refill (160 KiB of tiles);
      * ilp 1: one block per lane, 128 bytes per refill (144 KiB) */
     const int threads = StagedThreads<ENGINE>::N;
-    const bool two = p.ilp == 2;
+    const bool two = p.ilp == 2 && ENGINE < ENG_LIMEX128; /* (the wide models walk one block per lane) */
     const size_t tiles = (size_t)(threads / 32) * (two ? 2 * DfaTile<64>::WARP_BYTES : DfaTile<128>::WARP_BYTES);
     const u64 groups = ((u64)p.nblocks + (two ? 63 : 31)) / (two ? 64 : 32);
     const int grid = (int)std::min<u64>((u64)smCount, (groups + threads / 32 - 1) / (threads / 32));
