@@ -238,6 +238,39 @@ def compile_multi(exprs, flags=None, ids=None, mode=HS_MODE_BLOCK, platform=None
     return Database(db)
 
 
+class ExprExt(C.Structure):
+    _fields_ = [("flags", C.c_ulonglong), ("min_offset", C.c_ulonglong), ("max_offset", C.c_ulonglong),
+                ("min_length", C.c_ulonglong), ("edit_distance", C.c_uint), ("hamming_distance", C.c_uint)]
+
+
+def compile_ext_multi(exprs, flags=None, ids=None, ext=None, mode=HS_MODE_BLOCK, platform=None):
+    """hs_compile_ext_multi (src/hs_compile.h:422-520); ext: one dict per expression (or None) with any of
+    min_offset, max_offset, min_length, edit_distance, hamming_distance."""
+    n = len(exprs)
+    exprs = [x if isinstance(x, bytes) else x.encode("latin1") for x in exprs]
+    flags = list(flags) if flags is not None else [0] * n
+    ids = list(ids) if ids is not None else list(range(n))
+    bits = {"min_offset": 1, "max_offset": 2, "min_length": 4, "edit_distance": 8, "hamming_distance": 16}
+    structs, ptrs = [], (C.POINTER(ExprExt) * n)()
+    for i, e in enumerate(ext or [None] * n):
+        if e:
+            x = ExprExt()
+            for k, v in e.items():
+                x.flags |= bits[k]
+                setattr(x, k, int(v))
+            structs.append(x)
+            ptrs[i] = C.pointer(x)
+    arr = (C.c_char_p * n)(*exprs)
+    fl = (C.c_uint * n)(*flags)
+    idv = (C.c_uint * n)(*ids)
+    db = C.c_void_p()
+    err = C.POINTER(CompileError)()
+    rc = lib().hs_compile_ext_multi(arr, fl, idv, ptrs, n, mode, platform, C.byref(db), C.byref(err))
+    if rc != HS_SUCCESS:
+        _raise_compile(rc, err)
+    return Database(db)
+
+
 def set_build_option(key, value):
     _check(lib().hs_b200_set_build_option(key.encode(), int(value)), key)
 

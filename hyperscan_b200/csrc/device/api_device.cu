@@ -133,7 +133,7 @@ struct DevImage {
     u32 nfaOffset = 0, nfaLength = 0;   /* FK_OUTFIX: the sole engine (bytecode offset, NFA.length) */
     DfaParams nfaParams;                /* ... and what launchDfa needs to know about it */
     /* FK_OUTFIX: report program offset -> its (onmatch, offset_adjust) list, filled as programs are met */
-    mutable std::unordered_map<u32, std::vector<std::pair<u32, s32>>> progReports;
+    mutable std::unordered_map<u32, std::vector<ProgReport>> progReports;
     double pairRate = 0;     /* FK_PAIR32: modelled first-stage candidates per byte (printable ASCII) */
     u8 *d_bitmap2 = nullptr; /* second level (HBM / L2) for large literal sets */
     u32 bitmap2Shift = 0;
@@ -1374,17 +1374,20 @@ hs_error_t postprocessVec(const DevImage *im, std::vector<DevMatch> *v) {
         }
         auto it = im->progReports.find(m.id);
         if (it == im->progReports.end()) {
-            std::vector<std::pair<u32, s32>> reps;
+            std::vector<ProgReport> reps;
             if (m.id % INSTR_ALIGN || m.id < sizeof(RoseEngine) || m.id >= im->length ||
                 !collectProgramReports(bc, im->length, m.id, &im->exhaustible, &reps)) {
                 return HS_UNKNOWN_ERROR; /* a program with a state-carrying opcode (or a corrupt record) */
             }
             it = im->progReports.emplace(m.id, std::move(reps)).first;
         }
-        for (const auto &rp : it->second) {
+        for (const ProgReport &rp : it->second) {
+            if (m.to < rp.min_bound || m.to > rp.max_bound) {
+                continue; /* CHECK_BOUNDS (hs_expr_ext min_offset / max_offset) */
+            }
             DevMatch o = m;
-            o.id = rp.first;
-            o.to = (u64)((long long)m.to + rp.second);
+            o.id = rp.onmatch;
+            o.to = (u64)((long long)m.to + rp.offset_adjust);
             outv.push_back(o);
         }
     }

@@ -816,12 +816,29 @@ static hs_error_t compileCommon(const char *const *expressions,
             if (!expressions[i]) {
                 throw CompileError{"Invalid parameter: expression is NULL", (int)i};
             }
-            if (ext && ext[i] && ext[i]->flags != 0) {
-                throw CompileError{litApi ? "Extended parameters are not supported for "
-                                            "pure literal matching API."
-                                          : "Extended parameters need the regex back "
-                                            "end; this build compiles literal patterns "
-                                            "only.", (int)i};
+            const hs_expr_ext_t *xp = ext && ext[i] && ext[i]->flags != 0 ? ext[i] : nullptr;
+            if (xp) {
+                /* validation as src/compiler/compiler.cpp:80-110 */
+                if (litApi) {
+                    throw CompileError{"Extended parameters are not supported for pure literal matching API.", (int)i};
+                }
+                const unsigned long long known = HS_EXT_FLAG_MIN_OFFSET | HS_EXT_FLAG_MAX_OFFSET | HS_EXT_FLAG_MIN_LENGTH |
+                                                 HS_EXT_FLAG_EDIT_DISTANCE | HS_EXT_FLAG_HAMMING_DISTANCE;
+                if (xp->flags & ~known) {
+                    throw CompileError{"Invalid hs_expr_ext flag set.", (int)i};
+                }
+                if ((xp->flags & HS_EXT_FLAG_MIN_OFFSET) && (xp->flags & HS_EXT_FLAG_MAX_OFFSET) &&
+                    xp->min_offset > xp->max_offset) {
+                    throw CompileError{"In hs_expr_ext, min_offset must be less than or equal to max_offset.", (int)i};
+                }
+                if ((xp->flags & HS_EXT_FLAG_MIN_LENGTH) && (xp->flags & HS_EXT_FLAG_MAX_OFFSET) &&
+                    xp->min_length > xp->max_offset) {
+                    throw CompileError{"In hs_expr_ext, min_length must be less than or equal to max_offset.", (int)i};
+                }
+                if (xp->flags & (HS_EXT_FLAG_EDIT_DISTANCE | HS_EXT_FLAG_HAMMING_DISTANCE)) {
+                    throw CompileError{"Approximate matching (edit / Hamming distance) needs the reference's graph "
+                                       "transformations; not supported.", (int)i};
+                }
             }
             if (f & ~0x7ffu) {
                 throw CompileError{"Unrecognised flag.", (int)i};
@@ -864,7 +881,18 @@ static hs_error_t compileCommon(const char *const *expressions,
                     rp.flags = f;
                     rp.report = p.report;
                     rp.index = i;
+                    if (xp) {
+                        /* bounds on the match end and a minimum match length: the NFA route has them
+                         * (CHECK_BOUNDS in the report programs; a length counter in the automaton) */
+                        rp.minOffset = (xp->flags & HS_EXT_FLAG_MIN_OFFSET) ? xp->min_offset : 0;
+                        rp.maxOffset = (xp->flags & HS_EXT_FLAG_MAX_OFFSET) ? xp->max_offset : ~0ull;
+                        rp.minLength = (xp->flags & HS_EXT_FLAG_MIN_LENGTH) ? xp->min_length : 0;
+                        needNfa = true;
+                    }
                     rpats.push_back(rp);
+                }
+                if (xp) {
+                    continue; /* (no literal expansion: the literal programs carry no bounds) */
                 }
                 /* one literal per string of the expression's (finite) language,
                  * all under the expression's id */
@@ -1025,8 +1053,22 @@ static hs_error_t exprInfo(const char *expression, unsigned flags, const hs_expr
             throw CompileError{"Unrecognised flag.", 0};
         }
         if (ext && ext->flags != 0) {
-            throw CompileError{"Extended parameters need the regex back end; this build compiles "
-                               "literal patterns only.", 0};
+            if (ext->flags & ~(HS_EXT_FLAG_MIN_OFFSET | HS_EXT_FLAG_MAX_OFFSET | HS_EXT_FLAG_MIN_LENGTH |
+                               HS_EXT_FLAG_EDIT_DISTANCE | HS_EXT_FLAG_HAMMING_DISTANCE)) {
+                throw CompileError{"Invalid hs_expr_ext flag set.", 0};
+            }
+            if ((ext->flags & HS_EXT_FLAG_MIN_OFFSET) && (ext->flags & HS_EXT_FLAG_MAX_OFFSET) &&
+                ext->min_offset > ext->max_offset) {
+                throw CompileError{"In hs_expr_ext, min_offset must be less than or equal to max_offset.", 0};
+            }
+            if ((ext->flags & HS_EXT_FLAG_MIN_LENGTH) && (ext->flags & HS_EXT_FLAG_MAX_OFFSET) &&
+                ext->min_length > ext->max_offset) {
+                throw CompileError{"In hs_expr_ext, min_length must be less than or equal to max_offset.", 0};
+            }
+            if (ext->flags & (HS_EXT_FLAG_EDIT_DISTANCE | HS_EXT_FLAG_HAMMING_DISTANCE)) {
+                throw CompileError{"Approximate matching (edit / Hamming distance) needs the reference's graph "
+                                   "transformations; not supported.", 0};
+            }
         }
         size_t minW = 0, maxW = 0;
         try {
@@ -1054,6 +1096,16 @@ static hs_error_t exprInfo(const char *expression, unsigned flags, const hs_expr
             return HS_COMPILER_ERROR;
         }
         memset(out, 0, sizeof(*out));
+        if (ext && (ext->flags & HS_EXT_FLAG_MIN_LENGTH) && ext->min_length <= 0xfffffffeull) {
+            /* a min_length is a lower bound for the match width (checkVertex, src/nfagraph/ng_expr_info.cpp:104-109) */
+            minW = std::max<size_t>(minW, (size_t)ext->min_length);
+            maxW = std::max<size_t>(maxW, (size_t)ext->min_length);
+        }
+        if (ext && (ext->flags & HS_EXT_FLAG_MAX_OFFSET) && ext->max_offset && ext->max_offset <= 0xfffffffeull) {
+            /* ... and a max_offset an upper bound (:111-116) */
+            minW = std::min<size_t>(minW, (size_t)ext->max_offset);
+            maxW = std::min<size_t>(maxW, (size_t)ext->max_offset);
+        }
         out->min_width = (unsigned)minW;
         out->max_width = (unsigned)maxW;
         *info = out;

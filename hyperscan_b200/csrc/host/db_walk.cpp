@@ -17,8 +17,21 @@ namespace hsb {
  * roseRunProgram_l: PUSH_DELAYED, CATCH_UP*, SOM_*, TRIGGER_SUFFIX, REPORT_CHAIN,
  * REPORT_SOM*, SET_LOGICAL, SET_COMBINATION, FLUSH_COMBINATION, SET_EXHAUST. */
 bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex,
-                           std::vector<std::pair<u32, s32>> *reports) {
+                           std::vector<ProgReport> *reports) {
     u32 pc = prog, furthest = prog;
+    /* CHECK_BOUNDS guards the instructions up to its fail_jump target */
+    struct Guard { u32 until; u64 lo, hi; };
+    std::vector<Guard> guards;
+    auto report = [&](u32 onmatch, s32 adjust) {
+        u64 lo = 0, hi = ~0ull;
+        for (const Guard &g : guards) {
+            if (pc < g.until) {
+                lo = std::max(lo, g.lo);
+                hi = std::min(hi, g.hi);
+            }
+        }
+        reports->push_back({onmatch, adjust, lo, hi});
+    };
     auto jump = [&](u32 from, u32 rel) { furthest = std::max(furthest, from + rel); };
 #define STEP(T) pc += (u32)HSB_ROUNDUP(sizeof(T), INSTR_ALIGN)
 #define STEP_JUMP(T)                                \
@@ -44,7 +57,7 @@ bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
             if (reports) {
                 InstrFinalReport in;
                 memcpy(&in, bc + pc, sizeof(in));
-                reports->push_back({in.onmatch, in.offset_adjust});
+                report(in.onmatch, in.offset_adjust);
             }
             if (furthest <= pc) {
                 return true;
@@ -53,6 +66,13 @@ bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
             break;
         }
         case OP_CHECK_GROUPS: STEP(InstrCheckGroups); break;
+        case OP_CHECK_BOUNDS: {
+            InstrCheckBounds in;
+            memcpy(&in, bc + pc, sizeof(in));
+            guards.push_back({pc + in.fail_jump, in.min_bound, in.max_bound});
+            STEP_JUMP(InstrCheckBounds);
+            break;
+        }
         case OP_CHECK_MASK: STEP_JUMP(InstrCheckMask); break;
         case OP_CHECK_MASK_32: STEP_JUMP(InstrCheckMask32); break;
         case OP_CHECK_MASK_64: STEP_JUMP(InstrCheckMask64); break;
@@ -67,7 +87,7 @@ bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
             if (reports) {
                 InstrReport in;
                 memcpy(&in, bc + pc, sizeof(in));
-                reports->push_back({in.onmatch, in.offset_adjust});
+                report(in.onmatch, in.offset_adjust);
             }
             STEP(InstrReport);
             break;
@@ -77,7 +97,7 @@ bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
             memcpy(&in, bc + pc, sizeof(in));
             ex->insert(in.onmatch);
             if (reports) {
-                reports->push_back({in.onmatch, in.offset_adjust});
+                report(in.onmatch, in.offset_adjust);
             }
             STEP(InstrReportExhaust);
             break;
@@ -86,7 +106,7 @@ bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set
             if (reports) {
                 InstrDedupeAndReport in;
                 memcpy(&in, bc + pc, sizeof(in));
-                reports->push_back({in.onmatch, in.offset_adjust});
+                report(in.onmatch, in.offset_adjust);
             }
             STEP_JUMP(InstrDedupeAndReport);
             break;

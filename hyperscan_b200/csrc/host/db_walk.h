@@ -31,9 +31,15 @@ struct MatchRec { /* == hs_b200_match_t */
 
 /* Both return false if a program holds an opcode the device does not implement
  * (callers refuse the database with HS_ARCH_ERROR instead of failing mid-scan). */
+/* a report instruction of a program: what it raises, and the bounds on the match end (CHECK_BOUNDS,
+ * src/rose/program_runtime.c:2319-2326) under which the program reaches it */
+struct ProgReport {
+    u32 onmatch;
+    s32 offset_adjust;
+    u64 min_bound, max_bound;
+};
 bool collectProgramReports(const u8 *bc, u32 bcLen, u32 prog, std::unordered_set<u32> *ex,
-                           std::vector<std::pair<u32, s32>> *reports = nullptr); /* reports: (onmatch, offset_adjust) of every
-                                                                                  * report instruction, in program order */
+                           std::vector<ProgReport> *reports = nullptr); /* every report instruction, in program order */
 
 bool walkConfirm(const u8 *bc, u32 bcLen, u32 confOff, u32 nBuckets,
                  std::unordered_set<u32> *ex, std::vector<LitTail> *tails);

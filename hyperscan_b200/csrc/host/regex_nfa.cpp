@@ -901,7 +901,7 @@ void regexNfaInit(RawNfa *nfa) {
     nfa->init = nfa->initDS = stateSetOf(3);
 }
 
-void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline) {
+void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline, u64 minLength) {
     const NodeP root = Parser(re, flags).parse();
     const CharSet W = Glushkov::wordSet();
     auto newState = [&]() -> u32 {
@@ -934,13 +934,28 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
             throw RegexError{"Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY to enable support."};
         }
         const u32 np = (u32)g.cls.size();
-        /* NFA state of every character position (assertion pseudo-positions get none) */
-        std::vector<u32> st(np, 0);
+        /* hs_expr_ext.min_length: only matches of at least that many bytes count.  The automaton then carries the
+         * number of bytes consumed since the match began, saturating at the minimum: K copies ("levels") of every
+         * position, a transition goes one level up, and only the top level accepts.  (No minimum, or every match
+         * is long enough anyway: one level.) */
+        if (minLength > MAX_NFA_STATES) {
+            throw RegexError{"Pattern is too large: min_length beyond the 512-state NFA model."};
+        }
+        const u32 K = minLength > minLenOf(arm) ? (u32)minLength : 1;
+        /* NFA states of every character position, one per level (assertion pseudo-positions get none) */
+        std::vector<std::vector<u32>> lv(np, std::vector<u32>(K, 0));
         for (u32 p = 0; p < np; p++) {
             if (!g.assertion[p]) {
-                st[p] = newState();
-                reachClass(st[p], g.cls[p]);
+                for (u32 c = 0; c < K; c++) {
+                    lv[p][c] = newState();
+                    reachClass(lv[p][c], g.cls[p]);
+                }
             }
+        }
+        /* the accepting copy of a position */
+        std::vector<u32> st(np, 0);
+        for (u32 p = 0; p < np; p++) {
+            st[p] = lv[p][K - 1];
         }
 
         /* --- transitions between character positions --- */
@@ -956,7 +971,9 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
                     continue; /* an anchor between two characters (the parser lets none through) */
                 }
                 if (Glushkov::holds(e.second, g.isWord(p), g.isWord(e.first))) {
-                    nfa->succ[st[p]].set(st[e.first]);
+                    for (u32 c = 0; c < K; c++) {
+                        nfa->succ[lv[p][c]].set(lv[e.first][std::min(c + 1, K - 1)]);
+                    }
                 }
             }
         }
@@ -968,7 +985,7 @@ void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 re
             g.reachThroughAssertions(s.first, 0, &entries, &seen);
         }
         for (const auto &e : entries) {
-            const u32 entry = st[e.first];
+            const u32 entry = lv[e.first][0]; /* one byte consumed */
             const bool qw = asserts && g.isWord(e.first);
             if (e.second & A_ENDS) {
                 continue; /* a character after the end of the data */

@@ -49,7 +49,8 @@ RegexInfo regexInfo(const char *re, unsigned flags);
  * offset 0 only); call regexNfaInit first.  Throws RegexError, also when the 64 states
  * are exceeded. */
 void regexNfaInit(RawNfa *nfa);
-void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline = 0);
+void regexNfaAdd(RawNfa *nfa, const char *re, unsigned flags, u32 report, u32 reportBeforeNewline = 0,
+                 u64 minLength = 0); /* minLength: hs_expr_ext.min_length, 0 = none */
 /* reportBeforeNewline: the same report delivered one byte back (a report program with offset_adjust -1) --
  * needed when RegexInfo.needsAdjust: "$" / \Z match before a final newline, "$" under (?m) before any */
 

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <tuple>
 #include <set>
 #include <stdexcept>
 
@@ -686,19 +687,33 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
     RawNfa nfa;
     regexNfaInit(&nfa);
     u32 minLen = ~0u;
-    std::map<std::pair<u32, int>, u32> progOf; /* (report id, offset_adjust) -> its report program */
+    std::map<std::tuple<u32, int, u64, u64>, u32> progOf; /* (report id, offset_adjust, bounds) -> its report program */
     auto program = [&](const RegexPattern &p, int adjust) -> u32 {
-        auto pit = progOf.find({p.report, adjust});
+        const auto key = std::make_tuple(p.report, adjust, p.minOffset, p.maxOffset);
+        auto pit = progOf.find(key);
         if (pit != progOf.end()) {
             return pit->second;
         }
         const bool single = (p.flags & HS_FLAG_SINGLEMATCH) != 0;
-        u32 sz = instrSize<InstrEnd>();
+        const bool bounded = p.minOffset > 0 || p.maxOffset != ~0ull;
+        u32 sz = instrSize<InstrEnd>() + (bounded ? instrSize<InstrCheckBounds>() : 0);
         sz += single ? instrSize<InstrCheckExhausted>() + instrSize<InstrDedupe>() + instrSize<InstrReportExhaust>()
                      : instrSize<InstrDedupeAndReport>();
         u32 pc = blob.reserve(sz, INSTR_ALIGN);
         const u32 prog = pc;
         const u32 endAt = pc + sz - instrSize<InstrEnd>();
+        if (bounded) {
+            /* makeReport (src/rose/rose_build_program.cpp:533-538): the bounds come first, and they are on the raw
+             * match end -- min_offset / max_offset less the report's offset_adjust (ng_extparam.cpp:199-211) */
+            InstrCheckBounds cb;
+            memset(&cb, 0, sizeof(cb));
+            cb.code = OP_CHECK_BOUNDS;
+            cb.min_bound = p.minOffset - (u64)(long long)adjust;
+            cb.max_bound = p.maxOffset == ~0ull ? ~0ull : p.maxOffset - (u64)(long long)adjust;
+            cb.fail_jump = endAt - pc;
+            memcpy(blob.at(pc), &cb, sizeof(cb));
+            pc += instrSize<InstrCheckBounds>();
+        }
         if (single) {
             InstrCheckExhausted ce;
             memset(&ce, 0, sizeof(ce));
@@ -735,14 +750,14 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
         InstrEnd e;
         e.code = OP_END;
         memcpy(blob.at(endAt), &e, sizeof(e));
-        progOf[{p.report, adjust}] = prog;
+        progOf[key] = prog;
         return prog;
     };
     for (const RegexPattern &p : pats) {
         try {
             const RegexInfo ri = regexInfo(p.re.c_str(), p.flags);
-            minLen = std::min(minLen, ri.minLen);
-            regexNfaAdd(&nfa, p.re.c_str(), p.flags, program(p, 0), ri.needsAdjust ? program(p, -1) : 0);
+            minLen = std::min<u32>(minLen, (u32)std::max<u64>(ri.minLen, std::min<u64>(p.minLength, 0xffffffffu)));
+            regexNfaAdd(&nfa, p.re.c_str(), p.flags, program(p, 0), ri.needsAdjust ? program(p, -1) : 0, p.minLength);
         } catch (const RegexError &e) {
             throw CompileError{e.msg, (int)p.index};
         }

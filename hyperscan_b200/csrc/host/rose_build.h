@@ -62,6 +62,8 @@ struct RegexPattern {
     unsigned flags = 0;
     u32 report = 0;
     u32 index = 0;
+    u64 minOffset = 0, maxOffset = ~0ull; /* hs_expr_ext: bounds on the match end (CHECK_BOUNDS in the report programs) */
+    u64 minLength = 0;                    /* hs_expr_ext: shortest match that counts (regex_nfa.cpp) */
 };
 std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const CompileOpts &opts);
 

@@ -311,6 +311,7 @@ struct FDRConfirm {
 enum RoseOp {
     OP_END = 0,
     OP_CHECK_GROUPS = 3,
+    OP_CHECK_BOUNDS = 5,
     OP_CHECK_MASK = 9,
     OP_CHECK_MASK_32 = 10,
     OP_CHECK_BYTE = 11,
@@ -342,6 +343,7 @@ struct InstrCheckMask { u8 code; u64 and_mask, cmp_mask, neg_mask; s32 offset; u
 struct InstrCheckMask32 { u8 code; u8 and_mask[32]; u8 cmp_mask[32]; u32 neg_mask; s32 offset; u32 fail_jump; };
 struct InstrCheckMask64 { u8 code; u8 and_mask[64]; u8 cmp_mask[64]; u64 neg_mask; s32 offset; u32 fail_jump; };
 struct InstrCheckByte { u8 code, and_mask, cmp_mask, negation; s32 offset; u32 fail_jump; };
+struct InstrCheckBounds { u8 code; u64 min_bound; u64 max_bound; u32 fail_jump; }; /* on the match end, before any offset_adjust */
 struct InstrDedupe { u8 code, quash_som; u32 dkey; s32 offset_adjust; u32 fail_jump; };
 struct InstrReport { u8 code; u32 onmatch; s32 offset_adjust; };
 struct InstrReportExhaust { u8 code; u32 onmatch; s32 offset_adjust; u32 ekey; };

@@ -89,6 +89,15 @@ typedef struct hs_platform_info {   /* src/hs_compile.h:134-165 */
     unsigned long long reserved2;
 } hs_platform_info_t;
 
+/* hs_expr_ext.flags (src/hs_compile.h:264-279): which fields are set.  The regex route takes min_offset,
+ * max_offset (bounds on the match end: CHECK_BOUNDS in the report programs) and min_length (a length counter
+ * in the automaton); edit / Hamming distance are refused. */
+#define HS_EXT_FLAG_MIN_OFFSET 1ULL
+#define HS_EXT_FLAG_MAX_OFFSET 2ULL
+#define HS_EXT_FLAG_MIN_LENGTH 4ULL
+#define HS_EXT_FLAG_EDIT_DISTANCE 8ULL
+#define HS_EXT_FLAG_HAMMING_DISTANCE 16ULL
+
 typedef struct hs_expr_ext {        /* src/hs_compile.h:214-262 */
     unsigned long long flags;
     unsigned long long min_offset;
@@ -123,7 +132,7 @@ typedef int (*match_event_handler)(unsigned int id, unsigned long long from,
  * becoming one literal under the expression's id.  An expression set that is
  * not such a set (unbounded repeats, ".", negated / POSIX classes, \d \w \s \h \v,
  * \b \B, "^" \A "$" \z \Z where the reference takes them, option groups (?ims-ims),
- * \Q..\E, ...) is compiled, in block
+ * \Q..\E, ...; hs_compile_ext_multi with min_offset / max_offset / min_length) is compiled, in block
  * mode, to ONE engine -- a McClellan DFA when the determinised automaton is small, else a LimEx NFA (32- to
  * 512-state model) -- inside a single-outfix database
  * (ROSE_RUNTIME_SINGLE_OUTFIX) when its positions fit -- DESIGN.md section 10b.

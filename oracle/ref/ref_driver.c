@@ -585,6 +585,7 @@ ref_layout_dump_sheng();
     IOFF(CHECK_MASK_32, neg_mask); IOFF(CHECK_MASK_32, offset); IOFF(CHECK_MASK_32, fail_jump);
     ISZ(CHECK_MASK_64); IOFF(CHECK_MASK_64, and_mask); IOFF(CHECK_MASK_64, cmp_mask);
     IOFF(CHECK_MASK_64, neg_mask); IOFF(CHECK_MASK_64, offset); IOFF(CHECK_MASK_64, fail_jump);
+    ISZ(CHECK_BOUNDS); IOFF(CHECK_BOUNDS, min_bound); IOFF(CHECK_BOUNDS, max_bound); IOFF(CHECK_BOUNDS, fail_jump);
     ISZ(CHECK_BYTE); IOFF(CHECK_BYTE, and_mask); IOFF(CHECK_BYTE, cmp_mask);
     IOFF(CHECK_BYTE, negation); IOFF(CHECK_BYTE, offset);
     IOFF(CHECK_BYTE, fail_jump);
@@ -610,6 +611,7 @@ ref_layout_dump_sheng();
     ISZ(SET_EXHAUST); IOFF(SET_EXHAUST, ekey);
     printf("  \"ROSE_INSTR_CHECK_GROUPS\": %d,\n", ROSE_INSTR_CHECK_GROUPS);
     printf("  \"ROSE_INSTR_CHECK_MASK\": %d,\n", ROSE_INSTR_CHECK_MASK);
+    printf("  \"ROSE_INSTR_CHECK_BOUNDS\": %d,\n", ROSE_INSTR_CHECK_BOUNDS);
     printf("  \"ROSE_INSTR_CHECK_BYTE\": %d,\n", ROSE_INSTR_CHECK_BYTE);
     printf("  \"ROSE_INSTR_CHECK_MASK_32\": %d,\n", ROSE_INSTR_CHECK_MASK_32);
     printf("  \"ROSE_INSTR_CHECK_MASK_64\": %d,\n", ROSE_INSTR_CHECK_MASK_64);

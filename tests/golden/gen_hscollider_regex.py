@@ -63,21 +63,25 @@ def main():
     pats = {}
     for f in sorted(glob.glob(BASE + "/pcre/*.txt")):
         for line in open(f, "rb"):
-            m = re.match(rb"^(\d+):/(.*)/([a-zA-Z8]*)\s*$", line.rstrip(b"\n"))
+            m = re.match(rb"^(\d+):/(.*)/([a-zA-Z8]*)(\{[a-z_0-9=,]*\})?\s*$", line.rstrip(b"\n"))
             if not m:
                 continue
             pid, pat, fl = int(m.group(1)), m.group(2), m.group(3).decode()
             if set(fl) - set(FLAG):
                 continue
+            # extended parameters (util/ExpressionParser.rl:95-120): {min_offset=..,max_offset=..,min_length=..}
+            ext = None
+            if m.group(4):
+                ext = {k: int(v) for k, v in (kv.split("=") for kv in m.group(4).decode()[1:-1].split(",") if kv)}
             flags = 0
             for c in fl:
                 flags |= FLAG[c]
             try:
-                if capi.compile_multi([pat], [flags], [pid]).info().runtime_impl != 2:
+                if capi.compile_ext_multi([pat], [flags], [pid], [ext]).info().runtime_impl != 2:
                     continue  # a finite set of literals: hscollider_literals.json has it
             except capi.HsError:
                 continue  # needs more of the regex back end than this build has
-            pats[pid] = (pat, fl, os.path.basename(f))
+            pats[pid] = (pat, fl, os.path.basename(f), ext)
     cases = {}
     for f in sorted(glob.glob(BASE + "/corpora/*.txt")):
         for line in open(f, "rb"):
@@ -89,11 +93,11 @@ def main():
             cases.setdefault(pid, []).append((decode_corpus(m.group(2)), ends, os.path.basename(f)))
     out = []
     for pid in sorted(cases):
-        pat, fl, pfile = pats[pid]
+        pat, fl, pfile, ext = pats[pid]
         flags = 0
         for c in fl:
             flags |= FLAG[c]
-        db = capi.compile_multi([pat], [flags], [pid])
+        db = capi.compile_ext_multi([pat], [flags], [pid], [ext])
         corp = []
         for data, ends, cfile in cases[pid]:
             arr = np.frombuffer(data, dtype=np.uint8)
@@ -108,7 +112,7 @@ def main():
                 assert tos == ends, (pid, pat, data, ends, got)
             corp.append({"data": base64.b64encode(data).decode(), "ends": ends, "file": cfile})
         out.append({"id": pid, "pattern": base64.b64encode(pat).decode(), "flag_letters": fl,
-                    "hs_flags": flags, "file": pfile, "corpora": corp})
+                    "hs_flags": flags, "ext": ext, "file": pfile, "corpora": corp})
         print(pid, pat, fl, len(corp), "corpora")
     with open(os.path.join(ROOT, "tests", "golden", "hscollider_regex.json"), "w") as f:
         json.dump({"generator": "tests/golden/gen_hscollider_regex.py",

@@ -85,13 +85,13 @@ def _check_collider(case, recs, ends):
 
 @pytest.mark.parametrize("case", COLLIDER, ids=[str(c["id"]) for c in COLLIDER])
 def test_oracle_reproduces_hscollider_vectors(hs, case):
-    db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+    db = hs.compile_ext_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]], [case.get("ext")])
     data, off, ln, ends = _collider_blocks(case)
     _check_collider(case, port.scan_sorted(db.ptr, data, off, ln), ends)
 
 
 # --- ... and for expressions that take the NFA route (regex_nfa.cpp -> LimEx-32 -> single-outfix database) --
-# tests/golden/hscollider_regex.json (tests/golden/gen_hscollider_regex.py): 1 058 patterns / 9 293 corpora of the
+# tests/golden/hscollider_regex.json (tests/golden/gen_hscollider_regex.py): 1 128 patterns / 9 838 corpora of the
 # same suite that are NOT a finite set of literals and fit the NFA models.  The checker here is the unmodified
 # reference runtime scanning the database this compiler emits: with its default engine choice (a McClellan DFA when
 # the determinised automaton is small, else LimEx), and -- every third pattern -- with LimEx forced.
@@ -101,7 +101,7 @@ with open(os.path.join(ROOT, "tests", "golden", "hscollider_regex.json")) as f:
 
 @pytest.mark.parametrize("case", COLLIDER_REGEX, ids=[str(c["id"]) for c in COLLIDER_REGEX])
 def test_reference_runtime_reproduces_hscollider_regex_vectors(hs, ref, case):
-    db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+    db = hs.compile_ext_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]], [case.get("ext")])
     assert db.info().runtime_impl == 2
     data, off, ln, ends = _collider_blocks(case)
     _check_collider(case, ref.scan_sorted(db.ptr, data, off, ln), ends)
@@ -111,7 +111,7 @@ def test_reference_runtime_reproduces_hscollider_regex_vectors(hs, ref, case):
 def test_reference_runtime_reproduces_hscollider_regex_vectors_limex_forced(hs, ref, case):
     hs.set_build_option("regex_dfa", 0)
     try:
-        db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+        db = hs.compile_ext_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]], [case.get("ext")])
     finally:
         hs.set_build_option("regex_dfa", 1)
     assert db.info().runtime_impl == 2 and db.info().engine_id <= 5         # a LimEx model

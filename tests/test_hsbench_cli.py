@@ -18,11 +18,12 @@ _spec.loader.exec_module(cli)
 
 
 def test_signature_lines():
-    assert cli.parse_signature_line(b"12:/foo.*bar/is\n") == (12, b"foo.*bar", 3)
-    assert cli.parse_signature_line(b"7:/a\\/b/H") == (7, b"a\\/b", 8)            # the LAST slash ends the regex
+    assert cli.parse_signature_line(b"12:/foo.*bar/is\n") == (12, b"foo.*bar", 3, None)
+    assert cli.parse_signature_line(b"7:/a\\/b/H") == (7, b"a\\/b", 8, None)      # the LAST slash ends the regex
+    assert cli.parse_signature_line(b"5:/x+y/i{min_offset=3,max_offset=40}") == (5, b"x+y", 1, {"min_offset": 3, "max_offset": 40})
     assert cli.parse_signature_line(b"  # comment\n") is None and cli.parse_signature_line(b"\n") is None
     assert cli.parse_signature_line(b"3:/x/8W")[2] == 32 | 64
-    for bad in (b"nope", b"5:/x/k", b"5:/x/i{min_offset=3}"):
+    for bad in (b"nope", b"5:/x/k", b"5:/x/i{min_offset=x}", b"5:/x/i{som=3}"):
         with pytest.raises(ValueError):
             cli.parse_signature_line(bad)
 

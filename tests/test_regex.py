@@ -44,6 +44,19 @@ def _ends(pat, flags, data):
     return out
 
 
+def _ends_ext(pat, flags, data, min_offset=0, max_offset=None, min_length=0):
+    """_ends under hs_expr_ext: the match end within [min_offset, max_offset], the match at least min_length long"""
+    fl = (re.I if flags & CASELESS else 0) | (re.S if flags & DOTALL else 0) | (re.M if flags & MULTILINE else 0)
+    out = []
+    for e in range(max(1, min_offset), len(data) + 1):
+        if max_offset is not None and e > max_offset:
+            break
+        rx = re.compile(b"(?:" + pat + b")(?<=(?s:\\A.{%d}))" % e, fl)
+        if any(rx.match(data, s) for s in range(e - max(min_length, 1) + 1)):
+            out.append(e)
+    return out
+
+
 def _data(seed, n=48):
     rng = np.random.default_rng(seed)
     a = np.frombuffer(ALPHA, dtype=np.uint8)
@@ -89,6 +102,41 @@ def test_several_expressions_share_one_nfa_and_report_rules_hold(hs, ref):
             e = _ends(p, f, data)
             want |= {(i, x) for x in (e[:1] if f & SINGLE else e)}   # SINGLEMATCH: the first match only
         assert sorted(_ref_ends(ref, db, data), key=lambda t: (t[1], t[0])) == sorted(want, key=lambda t: (t[1], t[0]))
+
+
+@pytest.mark.parametrize("pat,fl,ext", [
+    (rb"ab+c", 0, {"min_offset": 20}), (rb"ab+c", 0, {"max_offset": 30}), (rb"a.*d", DOTALL, {"min_offset": 10, "max_offset": 60}),
+    (rb"a.*d", DOTALL, {"min_length": 6}), (rb"a[bc]*d", 0, {"min_length": 4, "min_offset": 8}), (rb"x.y|ab+", 0, {"min_length": 3}),
+    (rb"\w+@\w+", 0, {"min_length": 7, "max_offset": 90}), (rb"b+(cd)?$", 0, {"min_offset": 5}), (rb"\bab+", 0, {"min_length": 3}),
+    (rb"^a.*b", DOTALL, {"min_length": 10}), (rb"[a-c]{2,}", 0, {"min_length": 4})])
+def test_extended_parameters_equal_definition(hs, ref, pat, fl, ext):
+    """hs_compile_ext_multi: min_offset / max_offset (CHECK_BOUNDS in the report programs) and min_length (levels in
+    the automaton), checked like the plain expressions -- the unmodified reference hs_scan on the database against
+    the definition; the reference's own vectors for them (tools/hscollider extparams.txt) are in the golden file"""
+    hits = 0
+    for dfa in (1, 0):
+        hs.set_build_option("regex_dfa", dfa)
+        try:
+            db = hs.compile_ext_multi([pat], [fl], [7], [ext])
+        finally:
+            hs.set_build_option("regex_dfa", 1)
+        assert db.info().runtime_impl == 2
+        for seed in range(8):
+            data = (SEED_TEXT if seed == 0 else b"") + _data(300 + seed) + TAILS[seed % len(TAILS)]
+            want = [(7, e) for e in _ends_ext(pat, fl, data, **ext)]
+            assert _ref_ends(ref, db, data) == want, (pat, ext, data)
+            hits += len(want)
+    assert hits > 0
+
+
+def test_extended_parameter_errors(hs):
+    for ext, msg in [({"min_offset": 9, "max_offset": 3}, "min_offset must be less"), ({"min_length": 9, "max_offset": 3}, "min_length must be less"),
+                     ({"edit_distance": 1}, "Approximate"), ({"hamming_distance": 1}, "Approximate")]:
+        with pytest.raises(hs.HsError) as e:
+            hs.compile_ext_multi([rb"ab+c"], [0], [1], [ext])
+        assert msg in str(e.value)
+    with pytest.raises(hs.HsError):
+        hs.compile_ext_multi([rb"a.{600}b"], [0], [1], [{"min_length": 600}])      # beyond the 512-state model
 
 
 @pytest.mark.parametrize("a,b,fl", [

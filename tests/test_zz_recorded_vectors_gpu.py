@@ -17,7 +17,7 @@ ALL_CASES = COLLIDER + COLLIDER_REGEX   # literal route, then the regex route (s
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ALL_CASES, ids=[str(c["id"]) for c in ALL_CASES])
 def test_cuda_path_reproduces_hscollider_vectors(hs, case):
-    db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+    db = hs.compile_ext_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]], [case.get("ext")])
     data, off, ln, ends = _collider_blocks(case)
     scratch = hs.Scratch(db)
     got = np.sort(hs.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
@@ -37,7 +37,7 @@ def test_cuda_path_reproduces_hscollider_vectors(hs, case):
 def test_cuda_path_reproduces_hscollider_vectors_limex_forced(hs, case):
     hs.set_build_option("regex_dfa", 0)
     try:
-        db = hs.compile_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]])
+        db = hs.compile_ext_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [case["id"]], [case.get("ext")])
     finally:
         hs.set_build_option("regex_dfa", 1)
     assert db.info().engine_id <= 5

@@ -34,15 +34,21 @@ FLAG_LETTERS = {"i": 1, "s": 2, "m": 4, "H": 8, "V": 16, "8": 32, "W": 64, "P": 
 
 
 def parse_signature_line(line):
-    """`ID:/regex/flags` -> (id, regex bytes, flags) or None for blanks / comments"""
+    """`ID:/regex/flags{ext}` -> (id, regex bytes, flags, ext dict or None) or None for blanks / comments"""
     line = line.rstrip(b"\r\n")
     if not line.strip() or line.lstrip().startswith(b"#"):
         return None
     m = re.match(rb"^\s*(\d+):/(.*)/([A-Za-z0-9]*)(\{[^}]*\})?\s*$", line)
     if not m:
         raise ValueError("cannot parse signature line %r" % line[:80])
-    if m.group(4):
-        raise ValueError("extended parameters are not supported: %r" % line[:80])
+    ext = None
+    if m.group(4):      # {min_offset=..,max_offset=..,min_length=..,edit_distance=..,hamming_distance=..}
+        try:
+            ext = {k.strip(): int(v) for k, v in (kv.split("=") for kv in m.group(4).decode()[1:-1].split(",") if kv.strip())}
+        except ValueError:
+            raise ValueError("cannot parse the extended parameters of %r" % line[:80])
+        if set(ext) - {"min_offset", "max_offset", "min_length", "edit_distance", "hamming_distance"}:
+            raise ValueError("unknown extended parameter in %r" % line[:80])
     flags = 0
     for c in m.group(3).decode():
         if c == "O":        # hscollider's "no prefilter conversion" marker: no flag
@@ -50,7 +56,7 @@ def parse_signature_line(line):
         if c not in FLAG_LETTERS:
             raise ValueError("unknown flag letter %r in %r" % (c, line[:80]))
         flags |= FLAG_LETTERS[c]
-    return int(m.group(1)), m.group(2), flags
+    return int(m.group(1)), m.group(2), flags, ext
 
 
 def load_signatures(path, only_ids=None):
@@ -165,7 +171,7 @@ def main(argv=None):
             if args.literal_on:
                 db = capi.compile_lit_multi(pats, flags, ids, mode=mode)
             else:
-                db = capi.compile_multi(pats, flags, ids, mode=mode)
+                db = capi.compile_ext_multi(pats, flags, ids, [s[3] for s in sigs], mode=mode)
         except capi.HsError as e:
             print("Error: compile failed: %s" % e)
             return 1
