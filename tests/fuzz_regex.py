@@ -75,6 +75,17 @@ def gen_seq(rng, depth):
     return out
 
 
+EXT = {}   # main(): the hs_expr_ext of the case under test (min_offset, max_offset, min_length)
+
+
+def _ext_ok(e):
+    return e >= EXT.get("min_offset", 0) and e <= EXT.get("max_offset", 1 << 62)
+
+
+def _starts(e):
+    return range(e - max(EXT.get("min_length", 0), 1) + 1)
+
+
 def definition(body, flags, start, end, data):
     """every end offset e such that the body matches some data[s:e] IN CONTEXT (\\b / \\B look at the bytes around
     the match): for each e the body is followed by a fixed-width look-behind that pins the match end to e"""
@@ -91,10 +102,10 @@ def definition(body, flags, start, end, data):
             ok = e == n or (e == n - 1 and data[e:e + 1] == b"\n")
         else:               # "$" under (?m): before any newline or at the end
             ok = e == n or data[e:e + 1] == b"\n"
-        if not ok:
+        if not ok or not _ext_ok(e):
             continue
         rx = re.compile(b"(?:" + body + b")(?<=(?s:\\A.{%d}))" % e, fl)
-        for s in range(e):
+        for s in _starts(e):
             if start and not (s == 0 or (ml and data[s - 1:s] == b"\n")):
                 continue
             if rx.match(data, s):
@@ -111,7 +122,7 @@ def definition_whole(expr, flags, data):
     out = []
     for e in range(1, len(data) + 1):
         rx = re.compile(b"(?:" + expr + b")(?<=(?s:\\A.{%d}))" % e, fl)
-        if any(rx.match(data, s) for s in range(e)):
+        if _ext_ok(e) and any(rx.match(data, s) for s in _starts(e)):
             out.append(e)
     return out
 
@@ -151,7 +162,15 @@ def main():
         if args.verbose:
             print("expr", expr, flags, flush=True)
         try:
-            db = capi.compile_multi([expr], [flags], [5])
+            EXT.clear()
+            if rng.random() < 0.3:     # extended parameters
+                if rng.random() < 0.5:
+                    EXT["min_offset"] = int(rng.integers(0, 12))
+                if rng.random() < 0.5:
+                    EXT["max_offset"] = EXT.get("min_offset", 0) + int(rng.integers(0, 20))
+                if rng.random() < 0.5:
+                    EXT["min_length"] = min(int(rng.integers(1, 7)), EXT.get("max_offset", 99))
+            db = capi.compile_ext_multi([expr], [flags], [5], [dict(EXT) or None])
         except capi.HsError as e:
             refused += 1
             if args.verbose:
@@ -180,7 +199,7 @@ def main():
             finally:
                 signal.setitimer(signal.ITIMER_REAL, 0)
             if got != want:
-                print("MISMATCH expr", expr, "flags", flags, "data", data, "got", got, "want", want)
+                print("MISMATCH expr", expr, "ext", EXT, "flags", flags, "data", data, "got", got, "want", want)
                 sys.exit(1)
     print("fuzz regex: %d expressions (%d with \\b / \\B, %d with anchors inside groups, %d through the literal route; %d refused, %d inputs skipped: "
           "definition too slow), all equal to the definition (%.0f s)"
