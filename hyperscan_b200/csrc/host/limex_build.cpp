@@ -150,6 +150,81 @@ bool determinize(const RawNfa &n, size_t maxStates, RawDfa *out) {
     return true;
 }
 
+void minimizeDfa(RawDfa *dfa) {
+    RawDfa &d = *dfa;
+    const size_t n = d.size();
+    /* bytes that behave alike in every state */
+    std::vector<u32> byteClass(256, 0);
+    u32 nclasses = 0;
+    {
+        std::map<std::vector<u16>, u32> cols;
+        for (u32 b = 0; b < 256; b++) {
+            std::vector<u16> col(n);
+            for (size_t i = 0; i < n; i++) {
+                col[i] = d.next[i][b];
+            }
+            auto it = cols.emplace(col, (u32)cols.size()).first;
+            byteClass[b] = it->second;
+        }
+        nclasses = (u32)cols.size();
+    }
+    std::vector<u32> rep(nclasses, 0); /* one byte of every class */
+    for (u32 b = 256; b-- > 0;) {
+        rep[byteClass[b]] = b;
+    }
+    /* Moore's refinement: start from what a state reports, split by where the classes lead */
+    std::vector<u32> part(n, 0);
+    {
+        std::map<std::pair<std::vector<u32>, std::vector<u32>>, u32> sig;
+        for (size_t i = 0; i < n; i++) {
+            part[i] = sig.emplace(std::make_pair(d.reports[i], d.reportsEod[i]), (u32)sig.size()).first->second;
+        }
+    }
+    for (size_t count = 0;;) {
+        std::map<std::vector<u32>, u32> sig;
+        std::vector<u32> next(n);
+        for (size_t i = 0; i < n; i++) {
+            std::vector<u32> key(nclasses + 1);
+            key[0] = part[i];
+            for (u32 c = 0; c < nclasses; c++) {
+                key[c + 1] = part[d.next[i][rep[c]]];
+            }
+            next[i] = sig.emplace(key, (u32)sig.size()).first->second;
+        }
+        part.swap(next);
+        if (sig.size() == count) {
+            break;
+        }
+        count = sig.size();
+    }
+    /* renumber: the dead state's class stays 0, the rest in order of first appearance */
+    std::vector<int> id(n, -1);
+    std::vector<size_t> first;
+    id[part[0]] = 0;
+    first.push_back(0);
+    for (size_t i = 1; i < n; i++) {
+        if (id[part[i]] < 0) {
+            id[part[i]] = (int)first.size();
+            first.push_back(i);
+        }
+    }
+    if (first.size() == n) {
+        return;
+    }
+    RawDfa m;
+    m.next.resize(first.size());
+    for (size_t k = 0; k < first.size(); k++) {
+        for (u32 b = 0; b < 256; b++) {
+            m.next[k][b] = (u16)id[part[d.next[first[k]][b]]];
+        }
+        m.reports.push_back(d.reports[first[k]]);
+        m.reportsEod.push_back(d.reportsEod[first[k]]);
+    }
+    m.startAnchored = (u16)id[part[d.startAnchored]];
+    m.startFloating = (u16)id[part[d.startFloating]];
+    d = m;
+}
+
 namespace {
 
 template <class T> void put(std::vector<u8> &b, size_t off, const T &v) {

@@ -67,6 +67,11 @@ RawNfa nfaFromLiterals(const std::vector<DfaLiteral> &lits);
  * if more than maxStates subsets (the dead state included) are needed or the NFA has squashing exceptions. */
 bool determinize(const RawNfa &n, size_t maxStates, RawDfa *out);
 
+/* Merge the states of a DFA that no input tells apart (same reports now and after every byte string): Moore's
+ * partition refinement; state 0 stays the dead state.  The reference minimises its DFAs too (minimize_hopcroft,
+ * src/nfagraph/ng_mcclellan.cpp via util/determinise.h users). */
+void minimizeDfa(RawDfa *dfa);
+
 /* struct NFA + LimExNFA32 / 64 / 128 / 256 / 512 (the smallest that holds nstates) + tables */
 std::vector<u8> emitLimEx(const RawNfa &n);
 inline std::vector<u8> emitLimEx32(const RawNfa &n) { return emitLimEx(n); }

@@ -778,7 +778,12 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
         /* small automata run as DFAs, as in the reference (ng_mcclellan before LimEx); the report programs are
          * the same either way */
         RawDfa dfa;
-        if (opts.regexDfa && determinize(nfa, 1024, &dfa)) {
+        bool asDfa = opts.regexDfa && determinize(nfa, 1024, &dfa);
+        if (asDfa) {
+            minimizeDfa(&dfa);
+            asDfa = dfa.size() <= 1024;
+        }
+        if (asDfa) {
             eng = emitDfa(dfa, dfa.size() <= 256 ? DFA_MCCLELLAN8 : DFA_MCCLELLAN16, true);
         } else {
             eng = emitLimEx(nfa);

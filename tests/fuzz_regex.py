@@ -155,10 +155,13 @@ def main():
         if whole:
             expr = body
         try:
+            signal.setitimer(signal.ITIMER_REAL, 2.0)      # (Python's matcher can blow up here too)
             if not whole and re.compile(body).fullmatch(b"") is not None:
                 continue                                   # matches the empty string: refused by design
-        except re.error:
+        except (re.error, TimeoutError):
             continue
+        finally:
+            signal.setitimer(signal.ITIMER_REAL, 0)
         if args.verbose:
             print("expr", expr, flags, flush=True)
         try:
