@@ -781,7 +781,8 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
         bool asDfa = opts.regexDfa && determinize(nfa, 1024, &dfa);
         if (asDfa) {
             minimizeDfa(&dfa);
-            asDfa = dfa.size() <= 1024;
+            /* (nothing left but the dead state: an expression set that cannot match; it stays an NFA) */
+            asDfa = dfa.size() >= 2 && dfa.size() <= 1024;
         }
         if (asDfa) {
             eng = emitDfa(dfa, dfa.size() <= 256 ? DFA_MCCLELLAN8 : DFA_MCCLELLAN16, true);

@@ -129,6 +129,15 @@ def test_extended_parameters_equal_definition(hs, ref, pat, fl, ext):
     assert hits > 0
 
 
+def test_an_expression_that_cannot_match_still_compiles(hs, ref):
+    """(its determinised automaton minimises to the dead state alone: it stays an NFA)"""
+    for pat in (rb"^\Bfoo", rb"can't_match\b\B"):
+        db = hs.compile_multi([pat, rb"fo+d"], [0, 0], [1, 2])
+        assert _ref_ends(ref, db, b"foo food can't_match") == [(2, 8)]
+        solo = hs.compile_multi([pat], [0], [1])
+        assert solo.info().engine_id <= 5 and _ref_ends(ref, solo, b"foo food can't_match") == []
+
+
 def test_extended_parameter_errors(hs):
     for ext, msg in [({"min_offset": 9, "max_offset": 3}, "min_offset must be less"), ({"min_length": 9, "max_offset": 3}, "min_length must be less"),
                      ({"edit_distance": 1}, "Approximate"), ({"hamming_distance": 1}, "Approximate")]:
