@@ -117,3 +117,29 @@ def test_reference_runtime_reproduces_hscollider_regex_vectors_limex_forced(hs, 
     assert db.info().runtime_impl == 2 and db.info().engine_id <= 5         # a LimEx model
     data, off, ln, ends = _collider_blocks(case)
     _check_collider(case, ref.scan_sorted(db.ptr, data, off, ln), ends)
+
+
+def _groups(n_groups=120, size=6, seed=5):
+    """random groups of recorded expressions (no single-match flag, no extended parameters) for the shared automaton"""
+    rng = np.random.default_rng(seed)
+    pool = [c for c in COLLIDER_REGEX if "H" not in c["flag_letters"] and not c.get("ext")]
+    return [[pool[int(i)] for i in rng.choice(len(pool), size=size, replace=False)] for _ in range(n_groups)]
+
+
+@pytest.mark.parametrize("gi", range(120))
+def test_recorded_expressions_compiled_together(hs, ref, gi):
+    """six recorded expressions in ONE database (one shared automaton, start / context helper states included):
+    on every corpus of every member, the matches under the member's id are the recorded ones"""
+    group = _groups()[gi]
+    try:
+        db = hs.compile_multi([base64.b64decode(c["pattern"]) for c in group], [c["hs_flags"] for c in group],
+                              [1000 + k for k in range(len(group))])
+    except hs.HsError as e:
+        assert "too large" in str(e)          # the six together exceed the 512-state model
+        return
+    for k, c in enumerate(group):
+        data, off, ln, ends = _collider_blocks(c)
+        got = ref.scan_sorted(db.ptr, data, off, ln)
+        mine = got[got["id"] == 1000 + k]
+        for b, want in enumerate(ends):
+            assert [int(r["to"]) for r in mine[mine["block"] == b]] == want, (base64.b64decode(c["pattern"]), b)

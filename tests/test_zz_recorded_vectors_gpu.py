@@ -45,3 +45,24 @@ def test_cuda_path_reproduces_hscollider_vectors_limex_forced(hs, case):
     scratch = hs.Scratch(db)
     got = np.sort(hs.scan_blocks(db, data, off, ln, scratch), order=["block", "to", "id"])
     _check_collider(case, got, ends)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gi", range(0, 120, 4))
+def test_cuda_path_on_recorded_expressions_compiled_together(hs, gi):
+    """six recorded expressions in one database (shared automaton: McClellan or LimEx-32 ... -512 by size) through
+    the device path: under each member's id, the recorded matches"""
+    from test_golden import _groups
+    group = _groups()[gi]
+    try:
+        db = hs.compile_multi([base64.b64decode(c["pattern"]) for c in group], [c["hs_flags"] for c in group],
+                              [1000 + k for k in range(len(group))])
+    except hs.HsError:
+        return
+    scratch = hs.Scratch(db)
+    for k, c in enumerate(group):
+        data, off, ln, ends = _collider_blocks(c)
+        got = hs.scan_blocks(db, data, off, ln, scratch)
+        mine = got[got["id"] == 1000 + k]
+        for b, want in enumerate(ends):
+            assert sorted(int(r["to"]) for r in mine[mine["block"] == b]) == want
