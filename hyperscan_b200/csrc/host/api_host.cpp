@@ -1071,6 +1071,7 @@ static hs_error_t exprInfo(const char *expression, unsigned flags, const hs_expr
             }
         }
         size_t minW = 0, maxW = 0;
+        RegexInfo ri;
         try {
             const std::vector<std::string> lang = regexToLiterals(expression, flags, 0);
             minW = lang.empty() ? 0 : lang[0].size();
@@ -1083,7 +1084,7 @@ static hs_error_t exprInfo(const char *expression, unsigned flags, const hs_expr
                 throw;
             }
             try { /* not a finite set of literals: the NFA route's parser knows the widths */
-                const RegexInfo ri = regexInfo(expression, flags);
+                ri = regexInfo(expression, flags, true);
                 minW = ri.minLen;
                 maxW = ri.maxLen; /* 0xffffffff = unbounded, as in the reference (src/hs.cpp:398-403) */
             } catch (const RegexError &re) {
@@ -1108,6 +1109,9 @@ static hs_error_t exprInfo(const char *expression, unsigned flags, const hs_expr
         }
         out->min_width = (unsigned)minW;
         out->max_width = (unsigned)maxW;
+        out->unordered_matches = ri.unordered;
+        out->matches_at_eod = ri.atEod;
+        out->matches_only_at_eod = ri.onlyAtEod;
         *info = out;
         *error = nullptr;
         return HS_SUCCESS;

@@ -229,6 +229,23 @@ private:
         return s;
     }
 
+    /* "{n}", "{n,}", "{n,m}" at q?  (anything else that starts with a brace is literal text) */
+    bool startsRepeat(size_t q) const {
+        if (q >= n || re[q] != '{') {
+            return false;
+        }
+        size_t k = q + 1;
+        while (k < n && isdigit((unsigned char)re[k])) k++;
+        if (k == q + 1) {
+            return false;
+        }
+        if (k < n && re[k] == ',') {
+            k++;
+            while (k < n && isdigit((unsigned char)re[k])) k++;
+        }
+        return k < n && re[k] == '}';
+    }
+
     NodeP quantified(NodeP a) {
         while (pos + 1 < n && re[pos] == '\\' && re[pos + 1] == 'E') { /* "\\Qab\\E+": the quantifier binds to the "b" */
             quoting = false;
@@ -272,7 +289,7 @@ private:
                 }
             }
             if (!haveX || q >= n || re[q] != '}') {
-                fail("A '{' that does not start a repeat is not supported.");
+                return a; /* not a quantifier: the brace is a literal (atom() reads it next) */
             }
             if (comma && haveY && y < x) {
                 fail("Bounded repeat is invalid: min > max.");
@@ -627,7 +644,7 @@ private:
             }
             return leaf(s);
         }
-        if (strchr("*+?{", c)) {
+        if (strchr("*+?", c) || (c == '{' && startsRepeat(pos))) {
             fail("Invalid repeat: nothing to repeat.");
         }
         pos++;
@@ -771,6 +788,24 @@ struct Glushkov {
             exitsThroughAssertions(follow[x], n2, last, needs, seen);
         }
     }
+    /* the assertion sets of the ways from `first` to `last` that cross assertions only (no character) */
+    void emptyPaths(const StateSet &from, u32 need, const StateSet &last, std::vector<u32> *needs, std::vector<u8> *seen) const {
+        for (u32 x = 0; x < cls.size(); x++) {
+            if (!from.test(x) || !assertion[x]) {
+                continue;
+            }
+            const u32 n2 = need | (u32)assertion[x];
+            u8 &mark = (*seen)[x * (A_ALL + 1) + n2];
+            if (mark) {
+                continue;
+            }
+            mark = 1;
+            if (last.test(x)) {
+                needs->push_back(n2);
+            }
+            emptyPaths(follow[x], n2, last, needs, seen);
+        }
+    }
     bool anyAssertion() const {
         for (int a : assertion) {
             if (a) return true;
@@ -863,26 +898,75 @@ std::vector<NodeP> topArms(const NodeP &root) {
 
 } // namespace
 
-RegexInfo regexInfo(const char *re, unsigned flags) {
+RegexInfo regexInfo(const char *re, unsigned flags, bool forInfo) {
     const NodeP root = Parser(re, flags).parse();
-    Glushkov g;
     RegexInfo info;
     info.minLen = ~0u;
+    bool someOtherExit = false;
+    /* one way out of the expression: the assertions crossed after the last character, and whether that character
+     * is a word character (-1: there is none, the byte before the match is whatever it is) */
+    auto exitVia = [&](u32 need, int leftWord) {
+        info.unordered |= (need & (A_BOUNDARY | A_END_LF | A_END_LINE)) != 0;
+        bool canEod = false;
+        if (need & (A_ENDS | A_BOUNDARY)) {
+            for (int lw = 0; lw < 2; lw++) {
+                if (leftWord >= 0 && lw != leftWord) {
+                    continue;
+                }
+                if ((need & A_STARTS) && lw) {
+                    continue; /* the start of the data / a newline before: not a word character */
+                }
+                canEod |= Glushkov::holds(need, lw != 0, false);
+            }
+        }
+        info.atEod |= canEod;
+        if (!(need & (A_END | A_END_LF))) {
+            someOtherExit = true;
+        }
+    };
     for (NodeP arm : topArms(root)) {
-        if (hasAssertion(arm, A_BOUNDARY)) {
+        const bool asserts = hasAssertion(arm, A_BOUNDARY);
+        if (asserts) {
             splitByWordness(arm);
         }
         /* an assertion at the end may look one byte ahead */
         info.needsAdjust |= hasAssertion(arm, A_BOUNDARY | A_END_LF | A_END_LINE);
+        Glushkov g;
         const Glushkov::Sets s = g.build(arm);
-        if (s.nullable || minLenOf(arm) == 0) {
+        if (!forInfo && (s.nullable || minLenOf(arm) == 0)) {
             throw RegexError{"Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY to enable support."};
         }
         info.minLen = std::min(info.minLen, minLenOf(arm));
         const u64 mx = maxLenOf(arm);
         info.maxLen = std::max<u32>(info.maxLen, mx > 0xfffffffeull ? 0xffffffffu : (u32)mx);
+        info.positions += (u32)g.cls.size();
+        const u32 np = (u32)g.cls.size();
+        for (u32 p = 0; p < np; p++) {
+            if (g.assertion[p]) {
+                continue;
+            }
+            const int lw = asserts ? (int)g.isWord(p) : -1;
+            if (s.last.test(p)) {
+                exitVia(0, lw);
+            }
+            std::vector<u32> needs;
+            std::vector<u8> seen(np * (A_ALL + 1), 0);
+            g.exitsThroughAssertions(g.follow[p], 0, s.last, &needs, &seen);
+            for (u32 need : needs) {
+                exitVia(need, lw);
+            }
+        }
+        if (s.nullable) {
+            exitVia(0, -1);
+        }
+        std::vector<u32> needs;
+        std::vector<u8> seen(np * (A_ALL + 1), 0);
+        g.emptyPaths(s.first, 0, s.last, &needs, &seen);
+        for (u32 need : needs) {
+            exitVia(need, -1);
+        }
     }
-    info.positions = (u32)g.cls.size();
+    info.onlyAtEod = info.atEod && !someOtherExit;
     return info;
 }
 

@@ -39,10 +39,15 @@ struct RegexInfo {
     u32 maxLen = 0;      /* of the longest; 0xffffffff = unbounded (hs_expr_info_t.max_width convention) */
     u32 positions = 0;   /* character positions of the expression */
     bool needsAdjust = false; /* an alternative ends in "$" / \Z: see regexNfaAdd */
+    /* hs_expr_info_t (src/hs_compile.h:169-216): some match is raised one byte late and delivered back in time
+     * (a trailing "$" / \Z / \b); some match can be raised at the end of the data only because it is the end
+     * ("$" \z \Z, a trailing \b); every match is of that kind */
+    bool unordered = false, atEod = false, onlyAtEod = false;
 };
 
-/* Number of positions / shortest match of one expression (throws RegexError). */
-RegexInfo regexInfo(const char *re, unsigned flags);
+/* Number of positions / shortest match of one expression (throws RegexError).  forInfo: hs_expression_info also
+ * describes expressions that match the empty buffer (hs_compile refuses those without HS_FLAG_ALLOWEMPTY). */
+RegexInfo regexInfo(const char *re, unsigned flags, bool forInfo = false);
 
 /* Add the expression's position automaton to `nfa`: its accepting positions raise `report`.
  * State 0 of `nfa` is the floating start (always on), state 1 the anchored start (on at
