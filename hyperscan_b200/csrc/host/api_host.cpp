@@ -697,6 +697,9 @@ private:
                 /* range prev-hi */
                 pos++;
                 unsigned char hi;
+                if (re[pos] == '[' && pos + 1 < n && strchr(":.=", re[pos + 1])) {
+                    fail("Invalid range in character class.");
+                }
                 if (re[pos] == '\\') {
                     hi = escape(true);
                 } else {
@@ -751,6 +754,20 @@ private:
             return r;
         }
         if (c == '[') {
+            /* "[:name:]", "[.x.]", "[=x=]" where a class should start (PCRE's check_posix_syntax) */
+            if (pos + 1 < n && strchr(":.=", re[pos + 1])) {
+                const char term = re[pos + 1];
+                for (size_t q = pos + 2; q < n; q++) {
+                    if (re[q] == '\\' && q + 1 < n && (re[q + 1] == ']' || re[q + 1] == '\\')) {
+                        q++;
+                    } else if ((re[q] == '[' && q + 1 < n && re[q + 1] == term) || re[q] == ']') {
+                        break;
+                    } else if (re[q] == term && q + 1 < n && re[q + 1] == ']') {
+                        fail(term == ':' ? "POSIX named classes are only supported inside a class."
+                                         : "Unsupported POSIX collating element.");
+                    }
+                }
+            }
             return charClass();
         }
         if (c == '\\') {

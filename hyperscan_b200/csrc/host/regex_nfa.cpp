@@ -516,6 +516,9 @@ private:
             if (c == '-' && prev >= 0 && pos + 1 < n && re[pos + 1] != ']') {
                 pos++;
                 int hi;
+                if (re[pos] == '[' && pos + 1 < n && strchr(":.=", re[pos + 1])) {
+                    fail("Invalid range in character class.");
+                }
                 if (re[pos] == '\\') {
                     if (pos + 1 < n && (re[pos + 1] == 'Q' || re[pos + 1] == 'E')) {
                         fail("\\Q / \\E as the end of a range is not supported.");
@@ -596,6 +599,9 @@ private:
                 if (q < n && re[q] == ')' && any) {
                     flags = (flags | on) & ~off;
                     pos = q + 1;
+                    if (pos < n && (strchr("*+?", re[pos]) || startsRepeat(pos))) {
+                        fail("Invalid repeat.");
+                    }
                     return mk(Node::EMPTY);
                 }
                 if (q < n && re[q] == ':') {
@@ -614,6 +620,20 @@ private:
             return r;
         }
         if (c == '[') {
+            /* "[:name:]", "[.x.]", "[=x=]" where a class should start: PCRE's check_posix_syntax */
+            if (pos + 1 < n && strchr(":.=", re[pos + 1])) {
+                const char term = re[pos + 1];
+                for (size_t q = pos + 2; q < n; q++) {
+                    if (re[q] == '\\' && q + 1 < n && (re[q + 1] == ']' || re[q + 1] == '\\')) {
+                        q++;
+                    } else if ((re[q] == '[' && q + 1 < n && re[q + 1] == term) || re[q] == ']') {
+                        break;
+                    } else if (re[q] == term && q + 1 < n && re[q + 1] == ']') {
+                        fail(term == ':' ? "POSIX named classes are only supported inside a class."
+                                         : "Unsupported POSIX collating element.");
+                    }
+                }
+            }
             return leaf(charClass());
         }
         if (c == '\\' && pos + 1 < n && strchr("bBAzZ", re[pos + 1])) {
@@ -902,7 +922,7 @@ RegexInfo regexInfo(const char *re, unsigned flags, bool forInfo) {
     const NodeP root = Parser(re, flags).parse();
     RegexInfo info;
     info.minLen = ~0u;
-    bool someOtherExit = false;
+    bool someOtherExit = false, someFloatingEntry = false;
     /* one way out of the expression: the assertions crossed after the last character, and whether that character
      * is a word character (-1: there is none, the byte before the match is whatever it is) */
     auto exitVia = [&](u32 need, int leftWord) {
@@ -956,8 +976,17 @@ RegexInfo regexInfo(const char *re, unsigned flags, bool forInfo) {
                 exitVia(need, lw);
             }
         }
+        {
+            std::vector<std::pair<u32, u32>> entries;
+            std::vector<u8> seenE(np * (A_ALL + 1), 0);
+            g.reachThroughAssertions(s.first, 0, &entries, &seenE);
+            for (const auto &e : entries) {
+                someFloatingEntry |= !(e.second & A_BEGIN);
+            }
+        }
         if (s.nullable) {
             exitVia(0, -1);
+            someFloatingEntry = true;
         }
         std::vector<u32> needs;
         std::vector<u8> seen(np * (A_ALL + 1), 0);
@@ -967,6 +996,7 @@ RegexInfo regexInfo(const char *re, unsigned flags, bool forInfo) {
         }
     }
     info.onlyAtEod = info.atEod && !someOtherExit;
+    info.anchored = !someFloatingEntry;
     return info;
 }
 

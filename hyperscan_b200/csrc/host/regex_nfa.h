@@ -43,6 +43,7 @@ struct RegexInfo {
      * (a trailing "$" / \Z / \b); some match can be raised at the end of the data only because it is the end
      * ("$" \z \Z, a trailing \b); every match is of that kind */
     bool unordered = false, atEod = false, onlyAtEod = false;
+    bool anchored = false; /* every way into the expression crosses \A / a non-multiline "^" */
 };
 
 /* Number of positions / shortest match of one expression (throws RegexError).  forInfo: hs_expression_info also

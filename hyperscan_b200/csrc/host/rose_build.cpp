@@ -756,6 +756,34 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
     for (const RegexPattern &p : pats) {
         try {
             const RegexInfo ri = regexInfo(p.re.c_str(), p.flags);
+            /* extended parameters no match can satisfy (src/nfagraph/ng_extparam.cpp:820-880) */
+            if (p.minLength && ri.maxLen != 0xffffffffu && p.minLength > ri.maxLen) {
+                throw CompileError{"Expression has min_length=" + std::to_string(p.minLength) + " but can only produce matches of length " +
+                                       std::to_string(ri.maxLen) + " bytes at most.", (int)p.index};
+            }
+            if (p.maxOffset != ~0ull && ri.minLen > p.maxOffset) {
+                throw CompileError{"Expression has max_offset=" + std::to_string(p.maxOffset) + " but requires " +
+                                       std::to_string(ri.minLen) + " bytes to match.", (int)p.index};
+            }
+            if (ri.anchored && p.minOffset && ri.maxLen != 0xffffffffu && p.minOffset > ri.maxLen) {
+                throw CompileError{"Expression is anchored and cannot satisfy min_offset=" + std::to_string(p.minOffset) +
+                                       " as it can only produce matches of length " + std::to_string(ri.maxLen) + " bytes at most.",
+                                   (int)p.index};
+            }
+            {
+                /* "Pattern can never match." (can_never_match after resolveAsserts, src/nfagraph/ng.cpp:330-350): the
+                 * expression's own automaton, determinised and minimised, is the dead state alone */
+                RawNfa own;
+                regexNfaInit(&own);
+                regexNfaAdd(&own, p.re.c_str(), p.flags, 1, ri.needsAdjust ? 2 : 0, p.minLength);
+                RawDfa d;
+                if (determinize(own, 1024, &d)) {
+                    minimizeDfa(&d);
+                    if (d.size() < 2) {
+                        throw CompileError{"Pattern can never match.", (int)p.index};
+                    }
+                }
+            }
             minLen = std::min<u32>(minLen, (u32)std::max<u64>(ri.minLen, std::min<u64>(p.minLength, 0xffffffffu)));
             regexNfaAdd(&nfa, p.re.c_str(), p.flags, program(p, 0), ri.needsAdjust ? program(p, -1) : 0, p.minLength);
         } catch (const RegexError &e) {

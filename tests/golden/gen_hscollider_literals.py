@@ -73,7 +73,8 @@ def main():
             for c in fl:
                 flags |= FLAG[c]
             try:
-                capi.compile_multi([pat], [flags], [pid])
+                if capi.compile_multi([pat], [flags], [pid]).info().runtime_impl != 1:
+                    continue  # not a finite set of literals: hscollider_regex.json has it
             except capi.HsError:
                 continue  # needs the regex back end
             pats[pid] = (pat, fl, os.path.basename(f))
