@@ -249,3 +249,30 @@ def test_what_the_reference_refuses_is_refused(hs, case):
         ext = None            # a malformed parameter in the file: the expression parser's error, not hs_compile's
     with pytest.raises(hs.HsError):
         hs.compile_ext_multi([base64.b64decode(case["pattern"])], [case["hs_flags"]], [1], [ext])
+
+
+def _large_offset_cases():
+    """unit/hyperscan/extparam.cpp:40-122 (LargeMinOffset, LargeExactOffset): (ext, corpus, expected ends)"""
+    pad = lambda n: b"hatstand" + b"_" * n + b"teakettle"
+    return [({"min_offset": 100000}, pad(80000), []), ({"min_offset": 100000}, pad(100000 - 17), [100000]),
+            ({"min_offset": 200000, "max_offset": 200000}, pad(199982), []),
+            ({"min_offset": 200000, "max_offset": 200000}, pad(199983), [200000]),
+            ({"min_offset": 200000, "max_offset": 200000}, pad(199984), [])]
+
+
+def test_large_offset_bounds_reference_runtime(hs, ref):
+    for ext, corpus, want in _large_offset_cases():
+        db = hs.compile_ext_multi([rb"hatstand.*teakettle"], [0], [0], [ext])
+        assert [e for _, e in _ref_ends(ref, db, corpus)] == want
+    with pytest.raises(hs.HsError):        # extparam.cpp:125 LargeMinLength: the length counter is in the automaton here
+        hs.compile_ext_multi([rb"hatstand.*teakettle"], [0], [0], [{"min_length": 100000}])
+
+
+@pytest.mark.gpu
+def test_large_offset_bounds_device(hs):
+    for ext, corpus, want in _large_offset_cases():
+        db = hs.compile_ext_multi([rb"hatstand.*teakettle"], [0], [0], [ext])
+        scratch = hs.Scratch(db)
+        tos = []
+        hs.scan(db, corpus, scratch, on_event=lambda i, frm, to, fl: tos.append(to) or 0)
+        assert tos == want
