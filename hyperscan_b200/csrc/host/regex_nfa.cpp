@@ -910,8 +910,12 @@ u64 maxLenOf(const NodeP &n) { /* > 0xfffffffe = unbounded */
 
 /* top-level alternatives of the expression, each with its anchored flag */
 std::vector<NodeP> topArms(const NodeP &root) {
-    if (root->kind == Node::ALT) {
-        return root->kids;
+    NodeP r = root; /* "(a|b)" as a whole expression is the alternation a|b */
+    while (r->kind == Node::CAT && r->kids.size() == 1) {
+        r = r->kids[0];
+    }
+    if (r->kind == Node::ALT) {
+        return r->kids;
     }
     return {root};
 }
@@ -959,6 +963,7 @@ RegexInfo regexInfo(const char *re, unsigned flags, bool forInfo) {
         info.minLen = std::min(info.minLen, minLenOf(arm));
         const u64 mx = maxLenOf(arm);
         info.maxLen = std::max<u32>(info.maxLen, mx > 0xfffffffeull ? 0xffffffffu : (u32)mx);
+        info.armWidths.push_back({minLenOf(arm), mx > 0xfffffffeull ? 0xffffffffu : (u32)mx});
         info.positions += (u32)g.cls.size();
         const u32 np = (u32)g.cls.size();
         for (u32 p = 0; p < np; p++) {

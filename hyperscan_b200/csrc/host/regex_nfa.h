@@ -43,6 +43,7 @@ struct RegexInfo {
      * (a trailing "$" / \Z / \b); some match can be raised at the end of the data only because it is the end
      * ("$" \z \Z, a trailing \b); every match is of that kind */
     bool unordered = false, atEod = false, onlyAtEod = false;
+    std::vector<std::pair<u32, u32>> armWidths; /* (shortest, longest) match of every top-level alternative */
     bool anchored = false; /* every way into the expression crosses \A / a non-multiline "^" */
 };
 

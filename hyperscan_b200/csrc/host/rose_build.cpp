@@ -770,6 +770,19 @@ std::vector<u8> buildRegexRose(const std::vector<RegexPattern> &pats, const Comp
                                        " as it can only produce matches of length " + std::to_string(ri.maxLen) + " bytes at most.",
                                    (int)p.index};
             }
+            if (p.minLength || p.maxOffset != ~0ull) {
+                /* ... and taken together: some alternative must have a match that is long enough and can end early
+                 * enough (the reference prunes the graph by the parameters and reports what is left) */
+                bool some = false;
+                for (const auto &w : ri.armWidths) {
+                    some |= (w.second == 0xffffffffu || w.second >= p.minLength) &&
+                            std::max<u64>(w.first, p.minLength) <= p.maxOffset;
+                }
+                if (!some) {
+                    throw CompileError{"Extended parameter constraints can not be satisfied for any match from this "
+                                       "expression.", (int)p.index};
+                }
+            }
             {
                 /* "Pattern can never match." (can_never_match after resolveAsserts, src/nfagraph/ng.cpp:330-350): the
                  * expression's own automaton, determinised and minimised, is the dead state alone */

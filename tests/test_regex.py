@@ -233,17 +233,10 @@ def test_device_expression_set_with_report_rules(hs, ref):
 
 with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bad_patterns.json")) as _f:
     BAD = json.load(_f)["cases"]
-# refused by the reference for a reason this compiler does not model (a joint analysis of the extended parameters
-# against every match of the expression); accepted here
-NOT_REFUSED_HERE = {"Extended parameter constraints can not be satisfied for any match from this expression."}
-
-
 @pytest.mark.parametrize("case", BAD, ids=[str(i) for i in range(len(BAD))])
 def test_what_the_reference_refuses_is_refused(hs, case):
     """unit/hyperscan/bad_patterns.txt: none of the reference's bad patterns compiles here either (the wording of the
     error is the reference's own where this compiler detects the same thing; otherwise it names what is missing)"""
-    if case["message"] in NOT_REFUSED_HERE:
-        pytest.skip("needs the reference's joint extended-parameter analysis")
     ext = case["ext"]
     if ext and any(not isinstance(v, int) for v in ext.values()):
         ext = None            # a malformed parameter in the file: the expression parser's error, not hs_compile's
